@@ -1,0 +1,165 @@
+"""Pins the CPU oracle against the reference's own known-answer tests.
+
+Tolerances are the reference's (``atol = rtol = 2e-4`` QP/conic, ``1e-2`` LP, ``1e-3``
+fixture), applied like Julia's ``isapprox`` on arrays: ``|x-y| <= max(atol, rtol*max(|x|,|y|))``
+in the 2-norm.
+"""
+import numpy as np
+import pytest
+
+from oracle import cones, conic, lsqr, qp
+
+
+def approx(x, y, tol):
+    x = np.asarray(x, float).ravel()
+    y = np.asarray(y, float).ravel()
+    return np.linalg.norm(x - y) <= max(tol, tol * max(np.linalg.norm(x), np.linalg.norm(y)))
+
+
+def _qp_arrays(c):
+    n, m, p = len(c["z"]), len(c["lam"]), len(c["nu"])
+    a = lambda k, shape: np.array(c[k], float).reshape(shape)
+    return (a("Q", (n, n)), a("q", n), a("G", (m, n)), a("h", m), a("A", (p, n)), a("b", p),
+            a("z", n), a("lam", m), a("nu", p))
+
+
+QP_CASES = ["qp_moi_examples_2", "qp_moi_examples_1", "qp_ineq_eq", "qp_trivial_1",
+            "qp_fixture_data", "lp_simplex_example", "lp_fixed_variable", "lp_nonactive"]
+
+
+@pytest.mark.parametrize("name", QP_CASES)
+def test_qp_kat(kat, name):
+    c = kat[name]
+    Q, q, G, h, A, b, z, lam, nu = _qp_arrays(c)
+    n, m, p = z.size, lam.size, nu.size
+    # the closed-form primal/dual really is a KKT point of the reference's problem
+    assert np.abs(Q @ z + q + G.T @ lam + A.T @ nu).max() < 1e-12
+    assert np.all(G @ z - h <= 1e-12) and np.all(lam >= 0)
+    assert np.abs(lam * (G @ z - h)).max(initial=0) < 1e-12
+    assert np.abs(A @ z - b).max(initial=0) < 1e-12
+    # LP cases take the reference's LSQR branch (QuadraticProgram.jl:333)
+    assert qp.is_iterative(Q) == name.startswith("lp")
+    tol = c["tol"]
+    dz, dl, dn = qp.reverse(Q, G, h, A, z, lam, nu, np.array(c["seed"], float))
+    got = dict(zip(["dQ", "dq", "dG", "dh", "dA", "db"], qp.reverse_param_grads(z, lam, nu, dz, dl, dn)))
+    got.update(grad_z=dz, grad_lam=dl, grad_nu=dn)
+    checked = c["exp"].keys()
+    if name == "qp_fixture_data":
+        checked = ["dq", "dh", "db"]  # what test/quadratic_program.jl:326-347 checks
+    for k in checked:
+        assert approx(got[k], c["exp"][k], tol), k
+    if "fwd" in c:
+        f = c["fwd"]
+        a = lambda k, shape: np.array(f[k], float).reshape(shape)
+        args = (a("dQ", (n, n)), a("dq", n), a("dG", (m, n)), a("dh", m), a("dA", (p, n)), a("db", p))
+        fz, fl, fn = qp.forward(Q, G, h, A, z, lam, nu, *args)
+        assert approx(fz, c["exp_fwd"]["dz"], tol)
+        if "rhs_z" in c["exp_fwd"]:
+            assert approx(qp.forward_rhs(z, lam, nu, *args)[:n], c["exp_fwd"]["rhs_z"], tol)
+        # forward/reverse inner-product identity (test/utils.jl:331-337), exact in the algebra
+        rb = np.zeros(n + m + p)
+        rb[:n] = c["seed"]
+        rf = qp.forward_rhs(z, lam, nu, *args)
+        assert abs(fz @ rb[:n] - rf @ np.concatenate([dz, dl, dn])) < 1e-9 * (1 + abs(fz @ rb[:n]))
+    if "seed2" in c:
+        dz, dl, dn = qp.reverse(Q, G, h, A, z, lam, nu, np.array(c["seed2"], float))
+        got = dict(zip(["dQ", "dq", "dG", "dh", "dA", "db"], qp.reverse_param_grads(z, lam, nu, dz, dl, dn)))
+        for k, e in c["exp2"].items():
+            assert approx(got[k], e, tol), k
+
+
+def test_fixture_files_loose_agreement(kat):
+    """dA.txt / db.txt agree to the fixture's own (low) accuracy — SURVEY.md §8c (5)."""
+    c = kat["qp_fixture_data"]
+    Q, q, G, h, A, b, z, lam, nu = _qp_arrays(c)
+    dz, dl, dn = qp.reverse(Q, G, h, A, z, lam, nu, np.ones(10))
+    g = qp.reverse_param_grads(z, lam, nu, dz, dl, dn)
+    assert np.abs(g[4] - np.array(c["exp"]["dA"])).max() < 1e-2
+    assert np.abs(g[5] - np.array(c["exp"]["db"])).max() < 1e-2
+
+
+def _conic(c):
+    A = -np.array(c["coefficients"], float)   # ConicProgram.jl:179-183
+    b = np.array(c["constants"], float)
+    cc = np.array(c["c"], float)
+    x, s, y = (np.array(c[k], float) for k in "xsy")
+    assert np.abs(A @ x + s - b).max() < 1e-12
+    return A, b, cc, x, s, y, conic.gradient_cache(A, b, cc, x, s, y, c["cone_types"], c["cone_dims"])
+
+
+@pytest.mark.parametrize("name", ["conic_socp", "conic_psd2", "conic_psd3"])
+def test_conic_kat(kat, name):
+    c = kat[name]
+    A, b, cc, x, s, y, cache = _conic(c)
+    for f in c.get("fwd", []):
+        dx, _ = conic.forward(cache, np.array(f["dA"], float), f["db"], f["dc"])
+        assert approx(dx, f["exp_dx"], c["tol"])
+    for r in c.get("rev", []):
+        g = conic.reverse(cache, r["seed"])
+        _, db, _ = conic.reverse_param_grads(cache, g)
+        assert approx(db[r["exp_db_rows"]], r["exp_db"], c["tol"])
+
+
+@pytest.mark.parametrize("name", ["conic_socp", "conic_psd2", "conic_psd3"])
+def test_matrix_free_M_equals_reference_M(kat, name):
+    c = kat[name]
+    A, b, cc, x, s, y, cache = _conic(c)
+    Md = cache.M.toarray()
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        t = rng.normal(size=Md.shape[0])
+        assert np.allclose(conic.M_apply(A, b, cc, y - s, c["cone_types"], c["cone_dims"], t), Md @ t, atol=1e-13)
+        assert np.allclose(conic.M_apply(A, b, cc, y - s, c["cone_types"], c["cone_dims"], t, True), Md.T @ t, atol=1e-13)
+
+
+def test_lsqr_min_norm_limit_on_singular_M(kat):
+    """M is singular by construction (rank N-1 on the SOCP test): LSQR from x0=0 must give pinv(M) g."""
+    c = kat["conic_socp"]
+    A, b, cc, x, s, y, cache = _conic(c)
+    Md = cache.M.toarray()
+    assert np.linalg.matrix_rank(Md) == Md.shape[0] - 1
+    f = c["fwd"][0]
+    _, dz = conic.forward(cache, np.array(f["dA"], float), f["db"], f["dc"], atol=1e-14, btol=1e-14)
+    dA = np.array(f["dA"], float)
+    g = np.concatenate([dA.T @ cache.vp, -dA @ x, [0.0]])
+    assert np.allclose(dz, np.linalg.pinv(Md) @ g, atol=1e-9)
+
+
+def test_lsqr_matches_scipy():
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    rng = np.random.default_rng(7)
+    A = sp.random(300, 200, density=0.05, random_state=3, format="csr") + sp.eye(300, 200)
+    b = rng.normal(size=300)
+    x, info = lsqr.lsqr(A, b, return_info=True)
+    ref = spla.lsqr(A, b, atol=lsqr.SQRT_EPS, btol=lsqr.SQRT_EPS, conlim=1 / lsqr.SQRT_EPS, iter_lim=300)
+    assert info.itn == ref[2] and info.istop == ref[1]
+    assert np.allclose(x, ref[0], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("ctype,k", [(cones.ZERO, 4), (cones.NONNEG, 7), (cones.SOC, 6), (cones.PSD, 10), (cones.PSD, 21)])
+def test_operator_form_equals_dense_gradient(ctype, k):
+    rng = np.random.default_rng(11 + k)
+    for trial in range(6):
+        v = rng.normal(size=k)
+        if ctype == cones.SOC:
+            v[0] = [0.1, 5.0, -5.0, 0.0, 0.3, -0.2][trial]   # boundary / interior / polar / generic
+        D = cones.project_gradient(v, ctype)
+        yv = rng.normal(size=k)
+        assert np.allclose(cones.apply_gradient(v, ctype, yv), D @ yv, atol=1e-12)
+        assert np.allclose(cones.apply_gradient(v, ctype, yv, transpose=True), D.T @ yv, atol=1e-12)
+
+
+def test_psd_gradient_is_transposed_jacobian():
+    """the reference's PSD block is the TRANSPOSE of d pi / d v (unscaled triangle)."""
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=6)
+    D = cones.project_gradient(v, cones.PSD)
+    J = np.empty((6, 6))
+    eps = 1e-6
+    for j in range(6):
+        e = np.zeros(6)
+        e[j] = eps
+        J[:, j] = (cones.project(v + e, cones.PSD) - cones.project(v - e, cones.PSD)) / (2 * eps)
+    assert np.allclose(D.T, J, atol=1e-6)
+    assert not np.allclose(D, D.T, atol=1e-3)
