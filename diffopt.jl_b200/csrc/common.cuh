@@ -1,0 +1,163 @@
+// Shared host-side plumbing of libdiffopt_b200: the opaque ctx, error handling and
+// grow-only device buffers.  No torch types anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/diffopt_b200.h"
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// Resident state of a qp_batch_setup.
+struct QpBatchState {
+    int64_t B = 0;
+    int n = 0, m = 0, p = 0;
+    bool valid = false;
+    DevBuf Q, G, A, h, z, lam, nu;  // device copies (or nothing when borrowed)
+    const double *dQ_ = nullptr, *dG_ = nullptr, *dA_ = nullptr, *dh_ = nullptr, *dz_ = nullptr,
+                 *dlam_ = nullptr, *dnu_ = nullptr;  // device pointers actually used
+};
+
+struct CsrDev {  // device CSR (0-based, int32 indices) of a sparse matrix and of its transpose
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    DevBuf rowptr, colind, val;     // A   (nrows x ncols)
+    DevBuf t_rowptr, t_colind, t_val;  // A'  (ncols x nrows)
+};
+
+struct ConicState {
+    bool valid = false;
+    int64_t n = 0, m = 0, ncones = 0;
+    CsrDev A;
+    DevBuf b, c, x, s, y, v, vp;
+    // per-row cone metadata and per-cone data
+    DevBuf row_kind;     // int8 per row: 0 identity (zero cone -> free dual), 1 nonneg, 2 soc, 3 psd
+    DevBuf nn_scale;     // double per row: (sign(v)+1)/2 for nonneg rows, 1 for zero rows
+    DevBuf soc_off, soc_dim, soc_case, soc_nx;  // per SOC cone
+    int64_t nsoc = 0;
+    // PSD cones
+    DevBuf psd_off, psd_d, psd_uoff;  // per PSD cone: row offset, side d, offset into U/B storage
+    DevBuf psd_U, psd_Bm, psd_ident;  // eigenvectors (col-major d x d), B matrix, identity flag
+    DevBuf psd_work;                  // scratch 3 * sum d^2
+    int64_t npsd = 0, psd_maxd = 0, psd_sumd2 = 0;
+    std::vector<int64_t> h_psd_off, h_psd_d, h_psd_uoff;
+    // work vectors for M apply / LSQR
+    DevBuf w1, w2, w3;
+};
+
+struct LsqrWork {
+    DevBuf u, v, w, x, tmp, scal;  // vectors and a small block of device scalars
+};
+
+struct diffopt_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // generic staging buffers for HOST-memspace calls
+    DevBuf in[16];
+    DevBuf out[8];
+    DevBuf info;
+    QpBatchState qp;
+    ConicState conic;
+    LsqrWork lsqr;
+    CsrDev lsqr_mat;
+};
+
+#define DO_CUDA(ctx, expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            char _b[512];                                                               \
+            snprintf(_b, sizeof _b, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,       \
+                     cudaGetErrorString(_e));                                           \
+            (ctx)->err = _b;                                                            \
+            return -100 - (int32_t)_e;                                                  \
+        }                                                                               \
+    } while (0)
+
+#define BAD_ARG(ctx, msg)   \
+    do {                    \
+        (ctx)->err = (msg); \
+        return -1;          \
+    } while (0)
+
+// Copies `bytes` from src (host or device per memspace) into buf (device) unless src is
+// already a device pointer, in which case it is used in place.  Returns the device pointer.
+static inline cudaError_t stage_in(diffopt_b200_ctx* ctx, DevBuf& buf, const void* src, size_t bytes,
+                                   int memspace, const void** dev_out) {
+    if (src == nullptr || bytes == 0) {
+        *dev_out = nullptr;
+        return cudaSuccess;
+    }
+    if (memspace == DIFFOPT_B200_DEVICE) {
+        *dev_out = src;
+        return cudaSuccess;
+    }
+    cudaError_t e = buf.reserve(bytes);
+    if (e != cudaSuccess) return e;
+    *dev_out = buf.ptr;
+    return cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+}
+
+static inline cudaError_t stage_out_prepare(DevBuf& buf, void* dst, size_t bytes, int memspace, void** dev_out) {
+    if (dst == nullptr || bytes == 0) {
+        *dev_out = nullptr;
+        return cudaSuccess;
+    }
+    if (memspace == DIFFOPT_B200_DEVICE) {
+        *dev_out = dst;
+        return cudaSuccess;
+    }
+    cudaError_t e = buf.reserve(bytes);
+    if (e != cudaSuccess) return e;
+    *dev_out = buf.ptr;
+    return cudaSuccess;
+}
+
+static inline cudaError_t stage_out_finish(diffopt_b200_ctx* ctx, void* dev, void* dst, size_t bytes, int memspace) {
+    if (dst == nullptr || bytes == 0 || memspace == DIFFOPT_B200_DEVICE) return cudaSuccess;
+    return cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+}
+
+// kernel-side launchers implemented in the .cu files -------------------------------------
+struct QpSolveArgs {
+    int64_t B;
+    int n, m, p;
+    const double *Q, *G, *A, *h, *z, *lam, *nu;
+    const double *dQ, *dq, *dG, *dh, *dA, *db, *seed;
+    double *fwd, *rev;
+    int* info;
+};
+int32_t qp_batch_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a);
+int32_t qp_param_grads_launch(diffopt_b200_ctx* ctx, int64_t B, int n, int m, int p, const double* z,
+                              const double* lam, const double* nu, const double* rev, int reduce,
+                              double* dQ, double* dq, double* dG, double* dh, double* dA, double* db);

@@ -1,0 +1,326 @@
+// Generic batched KKT sensitivity kernel: any (n, m, p) whose augmented KKT matrix fits in
+// one CTA's shared memory (N = n+m+p <= 165).  One CTA per QP instance:
+//
+//   assemble  LHS = [Q G'diag(lam) A'; G diag(Gz-h) 0; A 0 0]   (QuadraticProgram.jl:256-282)
+//   augment   column N = reverse RHS [dl_dz;0;0]                 (:324-329)
+//             row    N = forward RHS' (:429-433)
+//   LU with partial (row) pivoting in shared memory; the extra column/row receive the
+//   L- and U'-forward substitutions for free; one backward sweep finishes both
+//   LHS x_b = r_b  and  LHS' x_f = r_f  from the SAME factorisation (:335, :438).
+//
+// This is the shape-generic correctness path (ragged shapes, no-G / no-A problems).  The
+// n=64,m=64,p=16 headline shape is served by the tuned kernel in qp_batch_n144.cu.
+#include "common.cuh"
+
+namespace {
+
+constexpr int GEN_THREADS = 512;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// accumulate, for one column-major R x n matrix X (global), the products
+//   rowacc[r] += sum_j X[r,j] * zc[j]      (length R)
+//   colacc[j] += sum_r X[r,j] * wr[r]      (length n)        (wr == nullptr -> skipped)
+// rowscale (optional) multiplies the row sums' contribution: rowacc[r] += rowscale[r] * (...)
+__device__ void accum_matvecs(const double* __restrict__ X, int R, int n, const double* zc, const double* wr,
+                              double* rowacc, const double* rowscale, double* colacc) {
+    if (X == nullptr || R == 0) return;
+    const int tid = threadIdx.x;
+    const int Rp = (R + 31) & ~31;           // rows padded to a warp multiple
+    const int ngroups = GEN_THREADS / Rp;    // column groups processed concurrently
+    if (ngroups == 0) {                      // R > 512 never happens (N <= 165)
+        return;
+    }
+    const int r = tid % Rp;
+    const int g = tid / Rp;
+    if (g >= ngroups) return;                // whole warps only (Rp multiple of 32)
+    double racc = 0.0;
+    const double wv = (wr != nullptr && r < R) ? wr[r] : 0.0;
+    for (int j = g; j < n; j += ngroups) {
+        double v = (r < R) ? X[(size_t)j * R + r] : 0.0;
+        racc += v * zc[j];
+        if (colacc != nullptr) {
+            double c = warp_sum(v * wv);
+            if ((tid & 31) == 0) atomicAdd(&colacc[j], c);
+        }
+    }
+    if (rowacc != nullptr && r < R) atomicAdd(&rowacc[r], rowscale ? rowscale[r] * racc : racc);
+}
+
+__global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveArgs a) {
+    extern __shared__ double smem[];
+    const int n = a.n, m = a.m, p = a.p;
+    const int N = n + m + p;
+    const int ld = (N + 1) | 1;  // odd leading dimension: conflict-free row AND column access
+    double* K = smem;                       // (N+1) x (N+1) augmented, column-major, ld
+    double* zs = K + (size_t)ld * (N + 1);  // n
+    double* lams = zs + n;                  // m
+    double* nus = lams + m;                 // p
+    double* rf = nus + p;                   // N   forward RHS accumulator
+    double* scal = rf + N;                  // [0]=rinv [1]=old_kk [2]=pivot value
+    int* perm = reinterpret_cast<int*>(scal + 4);  // N
+    int* ipiv = perm + N + 1;                      // [0] = pivot row of this step, [1] = info
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    for (int64_t inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
+        const double* Q = a.Q + (size_t)inst * n * n;
+        const double* G = a.G ? a.G + (size_t)inst * m * n : nullptr;
+        const double* A = a.A ? a.A + (size_t)inst * p * n : nullptr;
+        const bool do_fwd = a.fwd != nullptr, do_rev = a.rev != nullptr;
+
+        // ---- load vectors, clear K
+        for (int i = tid; i < n; i += GEN_THREADS) zs[i] = a.z[(size_t)inst * n + i];
+        for (int i = tid; i < m; i += GEN_THREADS) lams[i] = a.lam[(size_t)inst * m + i];
+        for (int i = tid; i < p; i += GEN_THREADS) nus[i] = a.nu[(size_t)inst * p + i];
+        for (int i = tid; i < N; i += GEN_THREADS) {
+            rf[i] = 0.0;
+            perm[i] = i;
+        }
+        for (int i = tid; i < ld * (N + 1); i += GEN_THREADS) K[i] = 0.0;
+        if (tid == 0) ipiv[1] = 0;
+        __syncthreads();
+
+        // ---- assemble
+        for (int idx = tid; idx < n * n; idx += GEN_THREADS) {
+            int i = idx % n, j = idx / n;
+            K[i + j * ld] = Q[idx];
+        }
+        for (int idx = tid; idx < m * n; idx += GEN_THREADS) {
+            int i = idx % m, j = idx / m;
+            double v = G[idx];
+            K[(n + i) + j * ld] = v;
+            K[j + (n + i) * ld] = v * lams[i];
+        }
+        for (int idx = tid; idx < p * n; idx += GEN_THREADS) {
+            int i = idx % p, j = idx / p;
+            double v = A[idx];
+            K[(n + m + i) + j * ld] = v;
+            K[j + (n + m + i) * ld] = v;
+        }
+        // forward RHS (QuadraticProgram.jl:429-433) accumulated into rf via global reads
+        if (do_fwd) {
+            const size_t b = (size_t)inst;
+            accum_matvecs(a.dQ ? a.dQ + b * n * n : nullptr, n, n, zs, nullptr, rf, nullptr, nullptr);
+            accum_matvecs(a.dG ? a.dG + b * m * n : nullptr, m, n, zs, lams, rf + n, lams, rf);
+            accum_matvecs(a.dA ? a.dA + b * p * n : nullptr, p, n, zs, nus, rf + n + m, nullptr, rf);
+        }
+        __syncthreads();
+        // diag(Gz - h); finish rf; place the two right-hand sides
+        for (int i = tid; i < m; i += GEN_THREADS) {
+            double d = 0.0;
+            for (int j = 0; j < n; ++j) d += K[(n + i) + j * ld] * zs[j];
+            K[(n + i) + (n + i) * ld] = d - a.h[(size_t)inst * m + i];
+        }
+        if (do_fwd) {
+            for (int i = tid; i < N; i += GEN_THREADS) {
+                double v = rf[i];
+                if (i < n) {
+                    if (a.dq) v += a.dq[(size_t)inst * n + i];
+                } else if (i < n + m) {
+                    if (a.dh) v -= lams[i - n] * a.dh[(size_t)inst * m + (i - n)];
+                } else {
+                    if (a.db) v -= a.db[(size_t)inst * p + (i - n - m)];
+                }
+                K[N + i * ld] = v;  // row N
+            }
+        }
+        if (do_rev) {
+            for (int i = tid; i < n; i += GEN_THREADS) K[i + N * ld] = a.seed[(size_t)inst * n + i];
+        }
+        __syncthreads();
+
+        // ---- LU with partial pivoting (rows 0..N-1 eligible; row N and column N ride along)
+        for (int k = 0; k < N; ++k) {
+            if (warp == 0) {
+                double best = -1.0;
+                int bi = k;
+                for (int i = k + lane; i < N; i += 32) {
+                    double v = fabs(K[i + k * ld]);
+                    if (v > best) {
+                        best = v;
+                        bi = i;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) {
+                        best = ov;
+                        bi = oi;
+                    }
+                }
+                if (lane == 0) {
+                    double pv = K[bi + k * ld];
+                    ipiv[0] = bi;
+                    scal[1] = K[k + k * ld];
+                    scal[2] = pv;
+                    if (best == 0.0 || !(best == best)) {
+                        if (ipiv[1] == 0) ipiv[1] = k + 1;
+                        scal[0] = 0.0;
+                    } else {
+                        scal[0] = 1.0 / pv;
+                    }
+                    int t = perm[k];
+                    perm[k] = perm[bi];
+                    perm[bi] = t;
+                }
+            }
+            __syncthreads();
+            const int pr = ipiv[0];
+            const double rinv = scal[0];
+            // swap rows k <-> pr in every column but k; scale column k (rows k+1..N)
+            if (tid <= N) {
+                int j = tid;
+                if (j != k && pr != k) {
+                    double t = K[k + j * ld];
+                    K[k + j * ld] = K[pr + j * ld];
+                    K[pr + j * ld] = t;
+                }
+            } else if (tid >= 192 && tid < 192 + (N - k)) {
+                int i = k + 1 + (tid - 192);
+                double src = (i == pr) ? scal[1] : K[i + k * ld];
+                K[i + k * ld] = src * rinv;
+            } else if (tid == 191) {
+                K[k + k * ld] = scal[2];
+            }
+            __syncthreads();
+            // trailing update including the augmented row/column
+            {
+                double l[6];
+                const int i0 = k + 1 + lane;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    int i = i0 + 32 * q;
+                    l[q] = (i <= N) ? K[i + k * ld] : 0.0;
+                }
+                for (int j = k + 1 + warp; j <= N; j += GEN_THREADS / 32) {
+                    double u = K[k + j * ld];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        int i = i0 + 32 * q;
+                        if (i <= N) K[i + j * ld] -= l[q] * u;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- backward sweeps:  U x_b = y (column N)   and   L' v = w (row N)
+        for (int k = N - 1; k >= 0; --k) {
+            if (tid < 256) {
+                if (do_rev) {
+                    double xb = K[k + N * ld] / K[k + k * ld];
+                    if (tid < k) K[tid + N * ld] -= K[tid + k * ld] * xb;
+                    if (tid == k) rf[k] = xb;  // rf reused as x_b store
+                }
+            } else {
+                int j = tid - 256;
+                if (do_fwd && j < k) K[N + j * ld] -= K[k + j * ld] * K[N + k * ld];
+            }
+            __syncthreads();
+        }
+        // ---- outputs: (dz, dlam, dnu) = -x ; x_f = P' v
+        if (do_rev)
+            for (int i = tid; i < N; i += GEN_THREADS) a.rev[(size_t)inst * N + i] = -rf[i];
+        if (do_fwd)
+            for (int i = tid; i < N; i += GEN_THREADS) a.fwd[(size_t)inst * N + perm[i]] = -K[N + i * ld];
+        if (a.info && tid == 0) a.info[inst] = ipiv[1];
+        __syncthreads();
+    }
+}
+
+__global__ void qp_param_grads_kernel(int64_t B, int n, int m, int p, const double* __restrict__ z,
+                                      const double* __restrict__ lam, const double* __restrict__ nu,
+                                      const double* __restrict__ rev, int reduce, double* dQ, double* dq,
+                                      double* dG, double* dh, double* dA, double* db) {
+    // one thread per output element of one instance; loops over the batch when reducing
+    const int N = n + m + p;
+    const int64_t per = (int64_t)n * n + n + (int64_t)m * n + m + (int64_t)p * n + p;
+    const int64_t total = reduce ? per : per * B;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t e = t % per;
+        int64_t b0 = reduce ? 0 : t / per, b1 = reduce ? B : b0 + 1;
+        double acc = 0.0;
+        int kind;
+        int64_t i = 0, j = 0;
+        if (e < (int64_t)n * n) { kind = 0; i = e % n; j = e / n; }
+        else if ((e -= (int64_t)n * n) < n) { kind = 1; i = e; }
+        else if ((e -= n) < (int64_t)m * n) { kind = 2; i = e % m; j = e / m; }
+        else if ((e -= (int64_t)m * n) < m) { kind = 3; i = e; }
+        else if ((e -= m) < (int64_t)p * n) { kind = 4; i = e % p; j = e / p; }
+        else { e -= (int64_t)p * n; kind = 5; i = e; }
+        for (int64_t b = b0; b < b1; ++b) {
+            const double* zb = z + b * n;
+            const double* r = rev + b * N;
+            switch (kind) {
+                case 0: acc += 0.5 * (r[i] * zb[j] + zb[i] * r[j]); break;
+                case 1: acc += r[i]; break;
+                case 2: { double l = lam[b * m + i]; acc += l * r[n + i] * zb[j] + l * r[j]; } break;
+                case 3: acc += -lam[b * m + i] * r[n + i]; break;
+                case 4: acc += r[n + m + i] * zb[j] + nu[b * p + i] * r[j]; break;
+                default: acc += -r[n + m + i]; break;
+            }
+        }
+        double* dst = nullptr;
+        int64_t bo = reduce ? 0 : b0;
+        switch (kind) {
+            case 0: if (dQ) dst = dQ + bo * n * n + i + j * n; break;
+            case 1: if (dq) dst = dq + bo * n + i; break;
+            case 2: if (dG) dst = dG + bo * m * n + i + j * m; break;
+            case 3: if (dh) dst = dh + bo * m + i; break;
+            case 4: if (dA) dst = dA + bo * p * n + i + j * p; break;
+            default: if (db) dst = db + bo * p + i; break;
+        }
+        if (dst) *dst = acc;
+    }
+}
+
+}  // namespace
+
+size_t qp_generic_smem_bytes(int n, int m, int p) {
+    int N = n + m + p;
+    int ld = (N + 1) | 1;
+    size_t d = (size_t)ld * (N + 1) + n + m + p + N + 4;
+    return d * sizeof(double) + (size_t)(N + 1 + 4) * sizeof(int);
+}
+
+int32_t qp_batch_launch_generic(diffopt_b200_ctx* ctx, const QpSolveArgs& a) {
+    size_t smem = qp_generic_smem_bytes(a.n, a.m, a.p);
+    if (smem > ctx->smem_optin) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "qp_batch: N = n+m+p = %d needs %zu B shared memory > %zu available",
+                 a.n + a.m + a.p, smem, ctx->smem_optin);
+        ctx->err = buf;
+        return -3;
+    }
+    DO_CUDA(ctx, cudaFuncSetAttribute(qp_kkt_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = a.B < (int64_t)ctx->sm_count * 4 ? a.B : (int64_t)ctx->sm_count * 4;
+    qp_kkt_generic_kernel<<<(unsigned)grid, GEN_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    DO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+int32_t qp_param_grads_launch(diffopt_b200_ctx* ctx, int64_t B, int n, int m, int p, const double* z,
+                              const double* lam, const double* nu, const double* rev, int reduce,
+                              double* dQ, double* dq, double* dG, double* dh, double* dA, double* db) {
+    int64_t per = (int64_t)n * n + n + (int64_t)m * n + m + (int64_t)p * n + p;
+    int64_t total = reduce ? per : per * B;
+    int64_t blocks = (total + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    qp_param_grads_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(B, n, m, p, z, lam, nu, rev, reduce, dQ, dq,
+                                                                      dG, dh, dA, db);
+    ctx->launches++;
+    DO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}

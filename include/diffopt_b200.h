@@ -1,0 +1,173 @@
+/*
+ * diffopt_b200.h -- C ABI of the B200-native DiffOpt.jl sensitivity hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, plain
+ * pointers and sizes.  It is what a Julia `ccall` (see INTEGRATION.md and
+ * julia/DiffOptB200.jl) or any other FFI binds.  All references below are to the
+ * reference tree andrewrosemberg/DiffOpt.jl v0.5.0.
+ *
+ * Conventions
+ *  - every entry point returns int32 status: 0 ok; >0 LAPACK-style info (first
+ *    instance/pivot that failed, 1-based); <0 bad argument / unsupported shape /
+ *    CUDA error (text via diffopt_b200_last_error).  Nothing throws or aborts.
+ *  - all floating point data is IEEE fp64.  Dense matrices are COLUMN-MAJOR (Julia
+ *    layout) per instance, batches are instance-major (instance b starts at
+ *    b * rows * cols).
+ *  - `memspace` says where EVERY data pointer of that call lives:
+ *    DIFFOPT_B200_HOST (pageable or pinned host memory; copies happen inside the
+ *    call) or DIFFOPT_B200_DEVICE (device memory of the ctx's GPU; no copies).
+ *  - calls are blocking (the ctx stream is synchronised before return), so the
+ *    reference's `diff_time = @elapsed ...` (QuadraticProgram.jl:317,358;
+ *    ConicProgram.jl:258,337) stays truthful.  One ctx per GPU; a ctx is not
+ *    thread-safe.
+ *  - lam / nu are the reference's stored duals, i.e. the NEGATED MOI duals
+ *    (QuadraticProgram.jl:156-180).
+ */
+#ifndef DIFFOPT_B200_H
+#define DIFFOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct diffopt_b200_ctx diffopt_b200_ctx;
+
+#define DIFFOPT_B200_HOST 0
+#define DIFFOPT_B200_DEVICE 1
+
+/* cone type codes for the conic entry points (dual cone is taken internally,
+ * diff_opt.jl:496,515) */
+#define DIFFOPT_CONE_ZERO 0   /* MOI.Zeros           */
+#define DIFFOPT_CONE_NONNEG 1 /* MOI.Nonnegatives    */
+#define DIFFOPT_CONE_SOC 2    /* MOI.SecondOrderCone */
+#define DIFFOPT_CONE_PSD 3    /* MOI.PositiveSemidefiniteConeTriangle (unscaled, column-wise upper) */
+
+/* ---- lifetime ------------------------------------------------------------------- */
+int32_t diffopt_b200_version(void);
+/* Fails (<0) when no CUDA device / wrong architecture: there is no CPU fallback. */
+int32_t diffopt_b200_create(int32_t device, diffopt_b200_ctx** out);
+int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx);
+const char* diffopt_b200_last_error(diffopt_b200_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t diffopt_b200_launch_count(diffopt_b200_ctx* ctx);
+/* the ctx's cudaStream_t (as void*), so a caller that owns device buffers can order work */
+void* diffopt_b200_stream(diffopt_b200_ctx* ctx);
+/* pinned host buffers for callers that want full-speed PCIe copies */
+int32_t diffopt_b200_host_alloc(void** ptr, int64_t bytes);
+int32_t diffopt_b200_host_free(void* ptr);
+/* device time (ms, CUDA events on the ctx stream) of the kernels of the last call */
+double diffopt_b200_last_kernel_ms(diffopt_b200_ctx* ctx);
+
+/* ---- QuadraticProgram backend: batched dense KKT sensitivities --------------------
+ *
+ * Replaces, for a batch of B independent QPs with n variables, m inequality rows
+ * (G z <= h) and p equality rows (A z = b):
+ *   create_LHS_matrix        QuadraticProgram.jl:256-282
+ *   reverse_differentiate!   QuadraticProgram.jl:316-351   (RHS = [dl_dz; 0; 0], solve with LHS)
+ *   forward_differentiate!   QuadraticProgram.jl:357-446   (RHS :429-433, solve with LHS')
+ *   solve_system (direct)    QuadraticProgram.jl:486-492   (`LHS \ RHS`)
+ * Outputs are the reference's (dz, dlam, dnu) = -solve(...), concatenated per
+ * instance as N = n+m+p doubles.
+ *
+ * Q[B][n*n], G[B][m*n], A[B][p*n] column-major; h[B][m], z[B][n], lam[B][m], nu[B][p].
+ * Forward direction (any of these may be NULL = zero): dQ[B][n*n] (symmetric, as
+ * sparse_array_representation gives it), dq[B][n], dG[B][m*n], dh[B][m], dA[B][p*n],
+ * db[B][p] in the reference's packed sign convention (db,dh = -constant,
+ * QuadraticProgram.jl:374-395).  dl_dz[B][n] is the reverse seed.
+ * fwd_out / rev_out [B][N] may be NULL to skip that mode.  info[B] (may be NULL):
+ * 0 or the 1-based elimination step with an exactly zero pivot (the reference
+ * throws SingularException there).
+ * Return: 0, or (first failing instance + 1) if any info != 0.
+ */
+int32_t diffopt_b200_qp_batch_solve(
+    diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
+    const double* Q, const double* G, const double* A, const double* h,
+    const double* z, const double* lam, const double* nu,
+    const double* dQ, const double* dq, const double* dG, const double* dh,
+    const double* dA, const double* db, const double* dl_dz,
+    double* fwd_out, double* rev_out, int32_t* info, int32_t memspace);
+
+/* Two-phase form mirroring the reference's cache (`_gradient_cache` builds LHS once,
+ * QuadraticProgram.jl:182-213; seeds may then change): setup keeps the problem data
+ * resident on the device, forward/reverse solve against it. */
+int32_t diffopt_b200_qp_batch_setup(
+    diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
+    const double* Q, const double* G, const double* A, const double* h,
+    const double* z, const double* lam, const double* nu, int32_t memspace);
+int32_t diffopt_b200_qp_batch_reverse(
+    diffopt_b200_ctx* ctx, const double* dl_dz, double* rev_out, int32_t* info, int32_t memspace);
+int32_t diffopt_b200_qp_batch_forward(
+    diffopt_b200_ctx* ctx, const double* dQ, const double* dq, const double* dG,
+    const double* dh, const double* dA, const double* db,
+    double* fwd_out, int32_t* info, int32_t memspace);
+
+/* Reverse-mode gradients w.r.t. the problem data from rev = (dz, dlam, dnu)
+ * (getters QuadraticProgram.jl:307-314, :448-473; signs as the reference's tests read
+ * them, test/utils.jl:178-233):
+ *   dQ = (dz z' + z dz')/2, dq = dz, dG_i = lam_i dlam_i z + lam_i dz, dh = -lam.dlam,
+ *   dA_i = dnu_i z + nu_i dz, db = -dnu.
+ * reduce_over_batch = 0: outputs are per instance ([B][...]); 1: summed over the
+ * batch into single-instance sized outputs (parameters shared across instances --
+ * the local half of the multi-GPU all-reduce).  Needs a prior
+ * qp_batch_setup (z, lam, nu resident).  Any output may be NULL. */
+int32_t diffopt_b200_qp_batch_param_grads(
+    diffopt_b200_ctx* ctx, const double* rev, int32_t reduce_over_batch,
+    double* dQ, double* dq, double* dG, double* dh, double* dA, double* db, int32_t memspace);
+
+/* ---- LSQR (IterativeSolvers.lsqr call sites QuadraticProgram.jl:488, ConicProgram.jl:323,372)
+ *
+ * min ||M x - rhs|| from x0 = 0 on an explicit sparse matrix in Julia's
+ * SparseMatrixCSC{Float64,Int} layout (colptr/rowval 1-based int64).  trans = 1 solves
+ * with M' (the `Adjoint` the forward QP mode passes, QuadraticProgram.jl:438).
+ * This is the iterative branch of `solve_system` (LP case, Q == 0).
+ * out_stats[4] (may be NULL) = {istop, iterations, ||r|| estimate, ||M'r|| estimate}. */
+int32_t diffopt_b200_lsqr_csc(
+    diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols,
+    const int64_t* colptr, const int64_t* rowval, const double* nzval, int32_t trans,
+    const double* rhs, double atol, double btol, double conlim, int64_t maxiter,
+    double* x_out, double* out_stats, int32_t memspace);
+
+/* ---- ConicProgram backend ---------------------------------------------------------
+ *
+ * conic_setup replaces `_gradient_cache` (ConicProgram.jl:172-255): keeps A (m x n CSC,
+ * already the reference's A = -coefficients), b, c, the solution (x, s, y) and the cone
+ * list resident, computes v = y - s, vp = pi(v) (diff_opt.jl:491-499) and the
+ * operator-form data of Dpi(v) (diff_opt.jl:509-519) -- dense blocks are never formed.
+ * Cones are listed in row order: cone_type[i] in DIFFOPT_CONE_*, cone_dim[i] rows.
+ */
+int32_t diffopt_b200_conic_setup(
+    diffopt_b200_ctx* ctx, int64_t n, int64_t m,
+    const int64_t* A_colptr, const int64_t* A_rowval, const double* A_nzval,
+    const double* b, const double* c, const double* x, const double* s, const double* y,
+    int64_t ncones, const int32_t* cone_type, const int64_t* cone_dim, int32_t memspace);
+/* vp = pi(y - s) of the current setup (length m) */
+int32_t diffopt_b200_conic_get_vp(diffopt_b200_ctx* ctx, double* vp_out, int32_t memspace);
+/* out = Dpi(v) * t or Dpi(v)' * t (length m): the `Dπ` operator on its own */
+int32_t diffopt_b200_conic_dpi_apply(
+    diffopt_b200_ctx* ctx, const double* t, int32_t transpose, double* out, int32_t memspace);
+/* out = M t or M' t, M as in ConicProgram.jl:243-247 (length n+m+1) */
+int32_t diffopt_b200_conic_M_apply(
+    diffopt_b200_ctx* ctx, const double* t, int32_t transpose, double* out, int32_t memspace);
+/* forward_differentiate! (ConicProgram.jl:257-334): dA as COO triplets (1-based rows/cols,
+ * duplicates summed, values as packed by the reference i.e. un-negated), db[m], dc[n];
+ * dz_out[n+m+1] = lsqr(M, g) (zeros if ||g|| == 0); dx_out[n] = -(du - x dw) (:403-412).
+ * Any of dA (nnz = 0), db, dc may be NULL. */
+int32_t diffopt_b200_conic_forward(
+    diffopt_b200_ctx* ctx, int64_t dA_nnz, const int64_t* dA_row, const int64_t* dA_col,
+    const double* dA_val, const double* db, const double* dc,
+    double atol, double btol, double conlim, int64_t maxiter,
+    double* dx_out, double* dz_out, double* out_stats, int32_t memspace);
+/* reverse_differentiate! (ConicProgram.jl:336-394): g_out[n+m+1] = lsqr(M, [dx; 0; -x'dx])
+ * (zeros if the norm of that vector is <= 1e-4, :369).  Optional getters
+ * (:396-428): dc_out[n] = g[1:n] - g[N] x ; db_out[m] = g[n+I] - g[N] vp. */
+int32_t diffopt_b200_conic_reverse(
+    diffopt_b200_ctx* ctx, const double* dx_seed,
+    double atol, double btol, double conlim, int64_t maxiter,
+    double* g_out, double* dc_out, double* db_out, double* out_stats, int32_t memspace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFOPT_B200_H */

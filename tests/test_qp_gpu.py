@@ -1,0 +1,162 @@
+"""GPU parity tests for the QuadraticProgram hot path: CUDA (through the C ABI) vs the CPU oracle.
+
+Tolerance (BASELINE.json north_star): relative error <= 1e-8 for direct KKT sensitivities,
+measured per instance as ||x_gpu - x_oracle||_2 / ||x_oracle||_2.
+"""
+import numpy as np
+import pytest
+
+import bench_data
+import diffopt_b200
+from oracle import qp as oqp
+
+pytestmark = pytest.mark.gpu
+RTOL_DIRECT = 1e-8
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return diffopt_b200.Context(0)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), 1e-300)
+
+
+def _oracle_batch(d):
+    return oqp.batch_forward_reverse(d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], d["seed"],
+                                     d["dQ"], d["dq"], d["dG"], d["dh"], d["dA"], d["db"])
+
+
+@pytest.mark.parametrize("n,m,p,na", [(64, 64, 16, 16), (10, 25, 10, 0), (5, 0, 2, 0), (7, 9, 0, 3), (3, 0, 0, 0),
+                                      (33, 47, 5, 11), (1, 1, 0, 1), (80, 60, 20, 30)])
+def test_fused_solve_matches_oracle(ctx, n, m, p, na):
+    qpm = diffopt_b200.submodule("qp")
+    B = 24
+    d = bench_data.qp_batch(B, n, m, p, n_active=na, seed0=100 + n)
+    fwd, rev, info = qpm.solve_batch(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"],
+                                     fwd_dir=(d["dQ"], d["dq"], d["dG"], d["dh"], d["dA"], d["db"]), seed=d["seed"])
+    assert not info.any()
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+def test_setup_forward_reverse_and_param_grads(ctx):
+    qpm = diffopt_b200.submodule("qp")
+    B, n, m, p = 40, 64, 64, 16
+    d = bench_data.qp_batch(B, n, m, p)
+    batch = qpm.QPBatch(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"])
+    dz, dl, dn = batch.reverse(d["seed"])
+    fz, fl, fn = batch.forward(d["dQ"], d["dq"], d["dG"], d["dh"], d["dA"], d["db"])
+    of, orv = _oracle_batch(d)
+    assert rel_err(np.hstack([dz, dl, dn]), orv).max() <= RTOL_DIRECT
+    assert rel_err(np.hstack([fz, fl, fn]), of).max() <= RTOL_DIRECT
+    # partial forward direction (only dh), as in docs/src/examples/matrix-inversion-manual.jl
+    fz2, _, _ = batch.forward(dh=d["dh"])
+    for b in range(0, B, 13):
+        z0 = np.zeros
+        ref = oqp.forward(d["Q"][b], d["G"][b], d["h"][b], d["A"][b], d["z"][b], d["lam"][b], d["nu"][b],
+                          z0((n, n)), z0(n), z0((m, n)), d["dh"][b], z0((p, n)), z0(p))[0]
+        assert rel_err(fz2[b], ref) <= RTOL_DIRECT
+    rev = np.hstack([dz, dl, dn])
+    g = batch.param_grads(rev)
+    gsum = batch.param_grads(rev, reduce_over_batch=True)
+    for b in range(0, B, 7):
+        ref = oqp.reverse_param_grads(d["z"][b], d["lam"][b], d["nu"][b], orv[b, :n], orv[b, n:n + m], orv[b, n + m:])
+        for got, want in zip(g, ref):
+            assert np.allclose(got[b], want, rtol=1e-8, atol=1e-10)
+    refs = [oqp.reverse_param_grads(d["z"][b], d["lam"][b], d["nu"][b], orv[b, :n], orv[b, n:n + m], orv[b, n + m:])
+            for b in range(B)]
+    for k in range(6):
+        assert np.allclose(gsum[k], sum(r[k] for r in refs), rtol=1e-8, atol=1e-9)
+
+
+def test_reference_known_answers_through_qpmodel(ctx, kat):
+    """The reference's own QP literals (direct-solve cases) through the reference-shaped model."""
+    qpm = diffopt_b200.submodule("qp")
+    for name in ["qp_moi_examples_2", "qp_moi_examples_1", "qp_ineq_eq", "qp_trivial_1", "qp_fixture_data"]:
+        c = kat[name]
+        n, m, p = len(c["z"]), len(c["lam"]), len(c["nu"])
+        a = lambda k, shape: np.array(c[k], float).reshape(shape)
+        model = qpm.QPModel(ctx, a("Q", (n, n)), a("q", n), a("G", (m, n)), a("h", m), a("A", (p, n)), a("b", p))
+        model.set_variable_primal(c["z"])
+        model.set_constraint_dual_le(-a("lam", m))   # MOI duals; the model negates them like the reference
+        model.set_constraint_dual_eq(-a("nu", p))
+        model.reverse_differentiate(c["seed"])
+        assert model.diff_time == model.diff_time
+        dq, dQ = model.reverse_objective_function()
+        got = dict(dq=dq, dQ=dQ, grad_z=dq, grad_lam=model.back_grad_cache[1], grad_nu=model.back_grad_cache[2],
+                   dh=-np.array([model.get_db_le(i) for i in range(m)]),
+                   db=-np.array([model.get_db_eq(i) for i in range(p)]),
+                   dG=np.array([model.get_dA_le(i) for i in range(m)]).reshape(m, n),
+                   dA=np.array([model.get_dA_eq(i) for i in range(p)]).reshape(p, n))
+        keys = ["dq", "dh", "db"] if name == "qp_fixture_data" else c["exp"].keys()
+        tol = c["tol"]
+        for k in keys:
+            e = np.array(c["exp"][k], float).ravel()
+            g = np.asarray(got[k]).ravel()
+            assert np.linalg.norm(g - e) <= max(tol, tol * max(np.linalg.norm(g), np.linalg.norm(e))), (name, k)
+        if "fwd" in c:
+            f = c["fwd"]
+            fa = lambda k, shape: np.array(f[k], float).reshape(shape)
+            model.forward_differentiate(fa("dQ", (n, n)), fa("dq", n), fa("dG", (m, n)), fa("dh", m),
+                                        fa("dA", (p, n)), fa("db", p))
+            assert np.allclose(model.forward_variable_primal(), c["exp_fwd"]["dz"], atol=tol)
+
+
+def test_singular_kkt_reports_info(ctx):
+    """test/conic_program.jl:846+ `test_singular_exception`-style: duplicated equality rows -> exact zero pivot."""
+    qpm = diffopt_b200.submodule("qp")
+    Q = np.eye(2)[None]
+    A = np.array([[[1.0, 1.0], [1.0, 1.0]]])
+    z = np.array([[0.5, 0.5]])
+    fwd, rev, info = qpm.solve_batch(ctx, Q, None, A, None, z, None, np.zeros((1, 2)), seed=np.ones((1, 2)))
+    assert info[0] > 0
+    model = qpm.QPModel(ctx, np.eye(2), np.zeros(2), np.zeros((0, 2)), np.zeros(0), A[0], np.ones(2))
+    model.set_variable_primal(z[0]); model.set_constraint_dual_le(np.zeros(0)); model.set_constraint_dual_eq(np.zeros(2))
+    with pytest.raises(diffopt_b200.SingularException):
+        model.reverse_differentiate(np.ones(2))
+
+
+def test_full_size_batch_properties(ctx):
+    """Config 2 at full size (4096 x n=64): size-independent properties instead of a 4096-instance oracle run.
+    (a) residuals K x_b = -r_b and K' x_f = -r_f; (b) forward/reverse inner-product identity
+    (test/utils.jl:331-337); (c) a 64-instance slice against the oracle."""
+    qpm = diffopt_b200.submodule("qp")
+    B = 4096
+    d = bench_data.qp_batch_fast(B)
+    n, m, p = 64, 64, 16
+    fwd, rev, info = qpm.solve_batch(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"],
+                                     fwd_dir=(d["dQ"], d["dq"], d["dG"], d["dh"], d["dA"], d["db"]), seed=d["seed"])
+    assert not info.any()
+    N = n + m + p
+    K = np.zeros((B, N, N))
+    K[:, :n, :n] = d["Q"]
+    K[:, :n, n:n + m] = d["G"].transpose(0, 2, 1) * d["lam"][:, None, :]
+    K[:, :n, n + m:] = d["A"].transpose(0, 2, 1)
+    K[:, n:n + m, :n] = d["G"]
+    K[:, n + m:, :n] = d["A"]
+    idx = np.arange(m)
+    K[:, n + idx, n + idx] = np.einsum("bij,bj->bi", d["G"], d["z"]) - d["h"]
+    rb = np.zeros((B, N)); rb[:, :n] = d["seed"]
+    rf = np.concatenate([
+        np.einsum("bij,bj->bi", d["dQ"], d["z"]) + d["dq"] + np.einsum("bij,bi->bj", d["dG"], d["lam"]) +
+        np.einsum("bij,bi->bj", d["dA"], d["nu"]),
+        d["lam"] * (np.einsum("bij,bj->bi", d["dG"], d["z"]) - d["dh"]),
+        np.einsum("bij,bj->bi", d["dA"], d["z"]) - d["db"]], axis=1)
+    res_b = np.einsum("bij,bj->bi", K, rev) + rb
+    res_f = np.einsum("bji,bj->bi", K, fwd) + rf
+    scale_b = np.linalg.norm(K, axis=(1, 2)) * np.linalg.norm(rev, axis=1)
+    scale_f = np.linalg.norm(K, axis=(1, 2)) * np.linalg.norm(fwd, axis=1)
+    assert (np.linalg.norm(res_b, axis=1) / scale_b).max() < 1e-13
+    assert (np.linalg.norm(res_f, axis=1) / scale_f).max() < 1e-13
+    lhs = np.einsum("bi,bi->b", fwd[:, :n], d["seed"])
+    rhs = np.einsum("bi,bi->b", rf, rev)
+    assert np.abs(lhs - rhs).max() <= 1e-9 * np.abs(lhs).max()
+    sl = slice(1000, 1064)
+    sub = {k: v[sl] for k, v in d.items()}
+    of, orv = _oracle_batch(sub)
+    assert rel_err(fwd[sl], of).max() <= RTOL_DIRECT
+    assert rel_err(rev[sl], orv).max() <= RTOL_DIRECT
