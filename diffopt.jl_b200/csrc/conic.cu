@@ -1,0 +1,655 @@
+// ConicProgram backend entry points (include/diffopt_b200.h): cone analysis (pi, Dpi data), PSD
+// eigendecomposition (parallel cyclic Jacobi), forward / reverse differentiation via the persistent
+// LSQR kernel on the matrix-free M, and the explicit-CSC LSQR used by the QP backend's LP branch.
+#include <cmath>
+#include <vector>
+
+#include "lsqr.cuh"
+
+ConicOpView conic_view(diffopt_b200_ctx* ctx);
+
+namespace {
+
+// ---- diag rows (zero / nonneg cones): v = y - s, diag, vp ------------------------------------------
+__global__ void cone_rows_kernel(int m, const double* __restrict__ y, const double* __restrict__ s,
+                                 const signed char* __restrict__ kind, const signed char* __restrict__ rowtype,
+                                 double* v, double* diag, double* vp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        double vi = y[i] - s[i];
+        v[i] = vi;
+        if (kind[i] == 0) {
+            if (rowtype[i] == DIFFOPT_CONE_ZERO) {   // dual of Zeros is the free cone: pi = id, Dpi = I
+                diag[i] = 1.0;
+                vp[i] = vi;
+            } else {                                  // Nonnegatives: (sign(v)+1)/2, max(v,0)
+                diag[i] = vi > 0.0 ? 1.0 : (vi < 0.0 ? 0.0 : 0.5);
+                vp[i] = vi > 0.0 ? vi : 0.0;
+            }
+        } else {
+            diag[i] = 0.0;
+        }
+    }
+}
+
+// ---- SOC cones: one warp per cone ------------------------------------------------------------------
+__global__ void cone_soc_kernel(int nsoc, const int* __restrict__ off, const int* __restrict__ dim,
+                                const double* __restrict__ v, int* cs, double* nxo, double* vp) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int c = wid; c < nsoc; c += nw) {
+        const int o = off[c], dd = dim[c];
+        double acc = 0.0;
+        for (int k = 1 + lane; k < dd; k += 32) acc += v[o + k] * v[o + k];
+        for (int q = 16; q > 0; q >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, q);
+        const double nx = sqrt(acc), t = v[o];
+        int cas = nx <= t ? 0 : (nx <= -t ? 1 : 2);
+        if (lane == 0) {
+            cs[c] = cas;
+            nxo[c] = nx;
+        }
+        const double scale = cas == 2 ? (nx + t) * 0.5 : 0.0;
+        for (int k = lane; k < dd; k += 32) {
+            double r;
+            if (cas == 0) r = v[o + k];
+            else if (cas == 1) r = 0.0;
+            else r = (k == 0 ? 1.0 : v[o + k] / nx) * scale;
+            vp[o + k] = r;
+        }
+    }
+}
+
+// ---- PSD cones: one CTA per cone; parallel-order cyclic Jacobi on X = unvec(v) -----------------------
+constexpr int PSD_THREADS = 1024;
+constexpr double PSD_EIG_THRESHOLD = 1e-4;  // MathOptSetDistances' `λ < 1e-4`
+
+__global__ void __launch_bounds__(PSD_THREADS) psd_eig_kernel(const int* __restrict__ poff, const int* __restrict__ pd,
+                                                              const long long* __restrict__ uoff,
+                                                              const double* __restrict__ v, double* Awork, double* U,
+                                                              double* Bm, int* ident, double* vp, double* lam_out,
+                                                              int* sweeps_out) {
+    const int c = blockIdx.x;
+    const int d = pd[c], off = poff[c];
+    double* A = Awork + uoff[c];
+    double* V = U + uoff[c];
+    double* Bc = Bm + uoff[c];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double cs_c[512], cs_s[512];
+    __shared__ int pp[512], qq[512];
+    __shared__ double red[32];
+    __shared__ double s_off, s_tot;
+    __shared__ int s_allpos;
+    const long long dd = (long long)d * d;
+    for (long long e = tid; e < dd; e += nt) {
+        int i = (int)(e % d), j = (int)(e / d);
+        int r = i < j ? i : j, cc = i < j ? j : i;
+        A[e] = v[off + (long long)cc * (cc + 1) / 2 + r];
+        V[e] = i == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int de = d + (d & 1);     // players (padded to even)
+    const int npairs = de / 2;      // <= 512  (d <= 1024)
+    int sweep = 0;
+    for (; sweep < 40; ++sweep) {
+        // off-diagonal norm
+        double lo = 0.0, lt = 0.0;
+        for (long long e = tid; e < dd; e += nt) {
+            int i = (int)(e % d), j = (int)(e / d);
+            double a = A[e];
+            lt += a * a;
+            if (i != j) lo += a * a;
+        }
+        for (int q = 16; q > 0; q >>= 1) {
+            lo += __shfl_xor_sync(0xffffffffu, lo, q);
+            lt += __shfl_xor_sync(0xffffffffu, lt, q);
+        }
+        if ((tid & 31) == 0) red[tid >> 5] = lo;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0;
+            for (int w = 0; w < nt / 32; ++w) s += red[w];
+            s_off = s;
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = lt;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0;
+            for (int w = 0; w < nt / 32; ++w) s += red[w];
+            s_tot = s;
+        }
+        __syncthreads();
+        if (s_off <= 1e-30 * s_tot || s_tot == 0.0) break;
+        for (int r = 0; r < de - 1; ++r) {
+            for (int k = tid; k < npairs; k += nt) {
+                int p, q;
+                if (k == 0) {
+                    p = r % (de - 1);
+                    q = de - 1;
+                } else {
+                    p = (r + k) % (de - 1);
+                    q = (r + (de - 1) - k) % (de - 1);
+                }
+                if (p > q) { int t = p; p = q; q = t; }
+                double cr = 1.0, sr = 0.0;
+                if (q < d) {
+                    double apq = A[p + (long long)q * d];
+                    if (apq != 0.0) {
+                        double app = A[p + (long long)p * d], aqq = A[q + (long long)q * d];
+                        double theta = (aqq - app) / (2.0 * apq);
+                        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        cr = 1.0 / sqrt(t * t + 1.0);
+                        sr = t * cr;
+                    }
+                } else {
+                    q = -1;
+                }
+                pp[k] = p; qq[k] = q; cs_c[k] = cr; cs_s[k] = sr;
+            }
+            __syncthreads();
+            // columns: A <- A J, V <- V J
+            for (long long e = tid; e < (long long)npairs * d; e += nt) {
+                int i = (int)(e % d), k = (int)(e / d);
+                int p = pp[k], q = qq[k];
+                if (q < 0) continue;
+                double cr = cs_c[k], sr = cs_s[k];
+                double ap = A[i + (long long)p * d], aq = A[i + (long long)q * d];
+                A[i + (long long)p * d] = cr * ap - sr * aq;
+                A[i + (long long)q * d] = sr * ap + cr * aq;
+                double vp_ = V[i + (long long)p * d], vq = V[i + (long long)q * d];
+                V[i + (long long)p * d] = cr * vp_ - sr * vq;
+                V[i + (long long)q * d] = sr * vp_ + cr * vq;
+            }
+            __syncthreads();
+            // rows: A <- J' A
+            for (long long e = tid; e < (long long)npairs * d; e += nt) {
+                int k = (int)(e % npairs), j = (int)(e / npairs);
+                int p = pp[k], q = qq[k];
+                if (q < 0) continue;
+                double cr = cs_c[k], sr = cs_s[k];
+                double ap = A[p + (long long)j * d], aq = A[q + (long long)j * d];
+                A[p + (long long)j * d] = cr * ap - sr * aq;
+                A[q + (long long)j * d] = sr * ap + cr * aq;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        int allpos = 1;
+        for (int i = 0; i < d; ++i)
+            if (!(A[i + (long long)i * d] >= 0.0)) allpos = 0;
+        s_allpos = allpos;
+        ident[c] = allpos;
+        if (sweeps_out) sweeps_out[c] = sweep;
+    }
+    __syncthreads();
+    // B matrix from the eigenvalues (no sorting needed: F is invariant under permuting eigenpairs)
+    for (long long e = tid; e < dd; e += nt) {
+        int i = (int)(e % d), j = (int)(e / d);
+        double li = A[i + (long long)i * d], lj = A[j + (long long)j * d];
+        bool ni = li < PSD_EIG_THRESHOLD, nj = lj < PSD_EIG_THRESHOLD;
+        double b;
+        if (!ni && !nj) b = 1.0;
+        else if (ni && nj) b = 0.0;
+        else {
+            double lp = ni ? fmax(lj, 0.0) : fmax(li, 0.0);      // positive side
+            double lm = ni ? -fmin(li, 0.0) : -fmin(lj, 0.0);    // negative side
+            b = lp / (lm + lp);
+        }
+        Bc[e] = b;
+    }
+    if (lam_out)
+        for (int i = tid; i < d; i += nt) lam_out[off + i] = A[i + (long long)i * d];
+    // vp = vec(U max(L,0) U')
+    const int tri = d * (d + 1) / 2;
+    for (int e = tid; e < tri; e += nt) {
+        int cc = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((long long)(cc + 1) * (cc + 2) / 2 <= e) ++cc;
+        while ((long long)cc * (cc + 1) / 2 > e) --cc;
+        int r = e - cc * (cc + 1) / 2;
+        double acc = 0.0;
+        for (int k = 0; k < d; ++k) {
+            double l = A[k + (long long)k * d];
+            if (l > 0.0) acc += V[r + (long long)k * d] * l * V[cc + (long long)k * d];
+        }
+        vp[off + e] = acc;
+    }
+}
+
+__global__ void conic_fwd_rhs_kernel(int n, int m, long long nnz, const long long* __restrict__ rows,
+                                     const long long* __restrict__ cols, const double* __restrict__ vals,
+                                     const double* __restrict__ x, const double* __restrict__ vp, double* g) {
+    // g[0:n] += dA' vp ; g[n:n+m] -= dA x     (atomic scatter; COO duplicates are summed)
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz;
+         k += (long long)gridDim.x * blockDim.x) {
+        long long i = rows[k] - 1, j = cols[k] - 1;
+        if (i < 0 || i >= m || j < 0 || j >= n) continue;
+        double a = vals[k];
+        atomicAdd(&g[j], a * vp[i]);
+        atomicAdd(&g[n + i], -a * x[j]);
+    }
+}
+
+__global__ void conic_fwd_rhs_finish(int n, int m, const double* __restrict__ db, const double* __restrict__ dc,
+                                     const double* __restrict__ x, const double* __restrict__ vp, double* g,
+                                     double* normsq) {
+    // single CTA: add dc, db; last entry -dc'x - db'vp; ||g||^2
+    __shared__ double red[32];
+    __shared__ double s_last;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double d = dc ? dc[i] : 0.0;
+        g[i] += d;
+        acc -= d * x[i];
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double d = db ? db[i] : 0.0;
+        g[n + i] += d;
+        acc -= d * vp[i];
+    }
+    for (int q = 16; q > 0; q >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < blockDim.x / 32; ++w) s += red[w];
+        g[n + m] = s;
+        s_last = s;
+    }
+    __syncthreads();
+    double nn = 0.0;
+    for (int i = threadIdx.x; i < n + m; i += blockDim.x) nn += g[i] * g[i];
+    for (int q = 16; q > 0; q >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, q);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = s_last * s_last;
+        for (int w = 0; w < blockDim.x / 32; ++w) s += red[w];
+        *normsq = s;
+    }
+}
+
+__global__ void conic_rev_rhs_kernel(int n, int m, const double* __restrict__ dx, const double* __restrict__ x,
+                                     double* dz, double* normsq) {
+    // dz = [dx; 0; -x'dx]   (ConicProgram.jl:363-367 with dy = ds = 0)
+    __shared__ double red[32], red2[32];
+    double acc = 0.0, nn = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double d = dx[i];
+        dz[i] = d;
+        acc -= x[i] * d;
+        nn += d * d;
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) dz[n + i] = 0.0;
+    for (int q = 16; q > 0; q >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, q);
+        nn += __shfl_xor_sync(0xffffffffu, nn, q);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = acc;
+        red2[threadIdx.x >> 5] = nn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0, t = 0;
+        for (int w = 0; w < blockDim.x / 32; ++w) {
+            s += red[w];
+            t += red2[w];
+        }
+        dz[n + m] = s;
+        *normsq = t + s * s;
+    }
+}
+
+__global__ void conic_fwd_dx_kernel(int n, int m, const double* __restrict__ dz, const double* __restrict__ x, double* dx) {
+    const double dw = dz[n + m];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dx[i] = -(dz[i] - x[i] * dw);   // ConicProgram.jl:403-412
+}
+
+__global__ void conic_rev_getters_kernel(int n, int m, const double* __restrict__ g, const double* __restrict__ x,
+                                         const double* __restrict__ vp, double* dc, double* db) {
+    const double gN = g[n + m];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x) {
+        if (i < n) {
+            if (dc) dc[i] = g[i] - gN * x[i];            // :396-401
+        } else if (db) {
+            db[i - n] = g[i] - gN * vp[i - n];           // :414-428
+        }
+    }
+}
+
+int32_t to_host_copy(diffopt_b200_ctx* ctx, const void* src, size_t bytes, int memspace, std::vector<char>& tmp,
+                     const void** host) {
+    if (memspace == DIFFOPT_B200_HOST) {
+        *host = src;
+        return 0;
+    }
+    tmp.resize(bytes);
+    DO_CUDA(ctx, cudaMemcpy(tmp.data(), src, bytes, cudaMemcpyDeviceToHost));
+    *host = tmp.data();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t diffopt_b200_lsqr_csc(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, const int64_t* colptr,
+                              const int64_t* rowval, const double* nzval, int32_t trans, const double* rhs,
+                              double atol, double btol, double conlim, int64_t maxiter, double* x_out,
+                              double* out_stats, int32_t memspace) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    if (!colptr || !rowval || !nzval || !rhs || !x_out) BAD_ARG(ctx, "lsqr_csc: null argument");
+    std::vector<char> t0, t1, t2;
+    const void *hc, *hr, *hv;
+    if (int32_t rc = to_host_copy(ctx, colptr, sizeof(int64_t) * (size_t)(ncols + 1), memspace, t0, &hc)) return rc;
+    const int64_t nnz = ((const int64_t*)hc)[ncols] - 1;
+    if (int32_t rc = to_host_copy(ctx, rowval, sizeof(int64_t) * (size_t)nnz, memspace, t1, &hr)) return rc;
+    if (int32_t rc = to_host_copy(ctx, nzval, sizeof(double) * (size_t)nnz, memspace, t2, &hv)) return rc;
+    if (int32_t rc = csr_from_csc_host(ctx, nrows, ncols, (const int64_t*)hc, (const int64_t*)hr, (const double*)hv,
+                                       ctx->lsqr_mat))
+        return rc;
+    const int64_t rlen = trans ? ncols : nrows, xlen = trans ? nrows : ncols;
+    const void* drhs;
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[0], rhs, sizeof(double) * (size_t)rlen, memspace, &drhs));
+    void* dx;
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[0], x_out, sizeof(double) * (size_t)xlen, memspace, &dx));
+    LsqrParams prm{atol, btol, conlim, maxiter > 0 ? maxiter : (nrows > ncols ? nrows : ncols)};
+    double st[7];
+    if (int32_t rc = lsqr_run_csr(ctx, ctx->lsqr_mat, trans != 0, (const double*)drhs, prm, (double*)dx, st)) return rc;
+    DO_CUDA(ctx, stage_out_finish(ctx, dx, x_out, sizeof(double) * (size_t)xlen, memspace));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_stats) {
+        if (memspace == DIFFOPT_B200_HOST) memcpy(out_stats, st, sizeof(double) * 4);
+        else DO_CUDA(ctx, cudaMemcpy(out_stats, st, sizeof(double) * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int32_t diffopt_b200_conic_setup(diffopt_b200_ctx* ctx, int64_t n, int64_t m, const int64_t* A_colptr,
+                                 const int64_t* A_rowval, const double* A_nzval, const double* b, const double* c,
+                                 const double* x, const double* s, const double* y, int64_t ncones,
+                                 const int32_t* cone_type, const int64_t* cone_dim, int32_t memspace) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    ConicState& S = ctx->conic;
+    S.valid = false;
+    if (n <= 0 || m < 0 || ncones < 0) BAD_ARG(ctx, "conic_setup: bad sizes");
+    if (!A_colptr || !b || !c || !x || !s || !y || (ncones > 0 && (!cone_type || !cone_dim)))
+        BAD_ARG(ctx, "conic_setup: null argument");
+    std::vector<char> t0, t1, t2, t3, t4;
+    const void *hc, *hr, *hv, *hct, *hcd;
+    if (int32_t rc = to_host_copy(ctx, A_colptr, sizeof(int64_t) * (size_t)(n + 1), memspace, t0, &hc)) return rc;
+    const int64_t nnz = ((const int64_t*)hc)[n] - 1;
+    if (int32_t rc = to_host_copy(ctx, A_rowval, sizeof(int64_t) * (size_t)nnz, memspace, t1, &hr)) return rc;
+    if (int32_t rc = to_host_copy(ctx, A_nzval, sizeof(double) * (size_t)nnz, memspace, t2, &hv)) return rc;
+    if (int32_t rc = to_host_copy(ctx, cone_type, sizeof(int32_t) * (size_t)ncones, memspace, t3, &hct)) return rc;
+    if (int32_t rc = to_host_copy(ctx, cone_dim, sizeof(int64_t) * (size_t)ncones, memspace, t4, &hcd)) return rc;
+    const int32_t* ct = (const int32_t*)hct;
+    const int64_t* cd = (const int64_t*)hcd;
+    // cone bookkeeping (host): row kinds and per-cone index lists
+    std::vector<signed char> kind((size_t)m, 0), rowtype((size_t)m, 0);
+    std::vector<int> soc_off, soc_dim, psd_off, psd_d;
+    std::vector<long long> psd_uoff;
+    int64_t row = 0, sumd2 = 0, maxd = 0;
+    for (int64_t k = 0; k < ncones; ++k) {
+        const int64_t dim = cd[k];
+        if (dim < 0 || row + dim > m) BAD_ARG(ctx, "conic_setup: cone dimensions exceed the number of rows");
+        switch (ct[k]) {
+            case DIFFOPT_CONE_ZERO:
+            case DIFFOPT_CONE_NONNEG:
+                for (int64_t i = 0; i < dim; ++i) rowtype[(size_t)(row + i)] = (signed char)ct[k];
+                break;
+            case DIFFOPT_CONE_SOC:
+                if (dim < 1) BAD_ARG(ctx, "conic_setup: SOC dimension must be >= 1");
+                for (int64_t i = 0; i < dim; ++i) kind[(size_t)(row + i)] = 2;
+                soc_off.push_back((int)row);
+                soc_dim.push_back((int)dim);
+                break;
+            case DIFFOPT_CONE_PSD: {
+                int64_t d = (int64_t)((std::sqrt(8.0 * (double)dim + 1.0) - 1.0) / 2.0 + 0.5);
+                if (d * (d + 1) / 2 != dim) BAD_ARG(ctx, "conic_setup: PSD triangle length must be d(d+1)/2");
+                if (d > 1024) BAD_ARG(ctx, "conic_setup: PSD side > 1024 not supported");
+                for (int64_t i = 0; i < dim; ++i) kind[(size_t)(row + i)] = 3;
+                psd_off.push_back((int)row);
+                psd_d.push_back((int)d);
+                psd_uoff.push_back(sumd2);
+                sumd2 += d * d;
+                maxd = d > maxd ? d : maxd;
+            } break;
+            default:
+                BAD_ARG(ctx, "conic_setup: unknown cone type");
+        }
+        row += dim;
+    }
+    if (row != m) BAD_ARG(ctx, "conic_setup: cone dimensions do not add up to m");
+    S.n = n; S.m = m; S.ncones = ncones;
+    S.nsoc = (int64_t)soc_off.size();
+    S.npsd = (int64_t)psd_off.size();
+    S.psd_sumd2 = sumd2;
+    S.psd_maxd = maxd;
+    if (int32_t rc = csr_from_csc_host(ctx, m, n, (const int64_t*)hc, (const int64_t*)hr, (const double*)hv, S.A))
+        return rc;
+    const size_t d8 = sizeof(double);
+    cudaMemcpyKind kd = memspace == DIFFOPT_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    auto keep = [&](DevBuf& buf, const void* src, size_t bytes, cudaMemcpyKind k) -> cudaError_t {
+        cudaError_t e = buf.reserve(bytes ? bytes : 8);
+        if (e != cudaSuccess || bytes == 0) return e;
+        return cudaMemcpyAsync(buf.ptr, src, bytes, k, ctx->stream);
+    };
+    DO_CUDA(ctx, keep(S.b, b, d8 * m, kd));
+    DO_CUDA(ctx, keep(S.c, c, d8 * n, kd));
+    DO_CUDA(ctx, keep(S.x, x, d8 * n, kd));
+    DO_CUDA(ctx, keep(S.s, s, d8 * m, kd));
+    DO_CUDA(ctx, keep(S.y, y, d8 * m, kd));
+    DO_CUDA(ctx, keep(S.row_kind, kind.data(), (size_t)m, cudaMemcpyHostToDevice));
+    DO_CUDA(ctx, keep(ctx->in[15], rowtype.data(), (size_t)m, cudaMemcpyHostToDevice));
+    DO_CUDA(ctx, keep(S.soc_off, soc_off.data(), sizeof(int) * soc_off.size(), cudaMemcpyHostToDevice));
+    DO_CUDA(ctx, keep(S.soc_dim, soc_dim.data(), sizeof(int) * soc_dim.size(), cudaMemcpyHostToDevice));
+    DO_CUDA(ctx, keep(S.psd_off, psd_off.data(), sizeof(int) * psd_off.size(), cudaMemcpyHostToDevice));
+    DO_CUDA(ctx, keep(S.psd_d, psd_d.data(), sizeof(int) * psd_d.size(), cudaMemcpyHostToDevice));
+    DO_CUDA(ctx, keep(S.psd_uoff, psd_uoff.data(), sizeof(long long) * psd_uoff.size(), cudaMemcpyHostToDevice));
+    DO_CUDA(ctx, S.v.reserve(d8 * (m ? m : 1)));
+    DO_CUDA(ctx, S.vp.reserve(d8 * (m ? m : 1)));
+    DO_CUDA(ctx, S.nn_scale.reserve(d8 * (m ? m : 1)));
+    DO_CUDA(ctx, S.soc_case.reserve(sizeof(int) * (soc_off.size() + 1)));
+    DO_CUDA(ctx, S.soc_nx.reserve(d8 * (soc_off.size() + 1)));
+    DO_CUDA(ctx, S.psd_U.reserve(d8 * (size_t)(sumd2 + 1)));
+    DO_CUDA(ctx, S.psd_Bm.reserve(d8 * (size_t)(sumd2 + 1)));
+    DO_CUDA(ctx, S.psd_ident.reserve(sizeof(int) * (psd_off.size() + 1)));
+    DO_CUDA(ctx, S.psd_work.reserve(d8 * (size_t)(3 * sumd2 + 1)));
+    DO_CUDA(ctx, S.w1.reserve(d8 * (size_t)(2 * m + 2)));
+    DO_CUDA(ctx, S.w2.reserve(d8 * (size_t)(n + m + 2)));
+    DO_CUDA(ctx, S.w3.reserve(d8 * (size_t)(n + m + 2)));
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (m > 0) {
+        int blocks = (int)((m + 255) / 256);
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        cone_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((int)m, S.y.as<double>(), S.s.as<double>(),
+                                                           S.row_kind.as<signed char>(), ctx->in[15].as<signed char>(),
+                                                           S.v.as<double>(), S.nn_scale.as<double>(), S.vp.as<double>());
+        ctx->launches++;
+    }
+    if (S.nsoc > 0) {
+        int blocks = (int)((S.nsoc * 32 + 255) / 256);
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        cone_soc_kernel<<<blocks, 256, 0, ctx->stream>>>((int)S.nsoc, S.soc_off.as<int>(), S.soc_dim.as<int>(),
+                                                          S.v.as<double>(), S.soc_case.as<int>(), S.soc_nx.as<double>(),
+                                                          S.vp.as<double>());
+        ctx->launches++;
+    }
+    if (S.npsd > 0) {
+        psd_eig_kernel<<<(unsigned)S.npsd, PSD_THREADS, 0, ctx->stream>>>(
+            S.psd_off.as<int>(), S.psd_d.as<int>(), S.psd_uoff.as<long long>(), S.v.as<double>(),
+            S.psd_work.as<double>(), S.psd_U.as<double>(), S.psd_Bm.as<double>(), S.psd_ident.as<int>(),
+            S.vp.as<double>(), nullptr, nullptr);
+        ctx->launches++;
+    }
+    DO_CUDA(ctx, cudaGetLastError());
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    S.valid = true;
+    return 0;
+}
+
+int32_t diffopt_b200_conic_get_vp(diffopt_b200_ctx* ctx, double* vp_out, int32_t memspace) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    if (!ctx->conic.valid) BAD_ARG(ctx, "conic_get_vp: call conic_setup first");
+    if (!vp_out) BAD_ARG(ctx, "conic_get_vp: null output");
+    DO_CUDA(ctx, cudaMemcpyAsync(vp_out, ctx->conic.vp.ptr, sizeof(double) * (size_t)ctx->conic.m,
+                                 memspace == DIFFOPT_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int32_t conic_op_call(diffopt_b200_ctx* ctx, const double* t, int32_t transpose, double* out, int32_t memspace,
+                             bool full_M) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    ConicState& S = ctx->conic;
+    if (!S.valid) BAD_ARG(ctx, "conic operator: call conic_setup first");
+    if (!t || !out) BAD_ARG(ctx, "conic operator: null argument");
+    const size_t len = (size_t)(full_M ? S.n + S.m + 1 : S.m);
+    const void* dt;
+    void* dout;
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[0], t, sizeof(double) * len, memspace, &dt));
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[0], out, sizeof(double) * len, memspace, &dout));
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    int32_t rc = full_M ? conic_apply_M(ctx, (const double*)dt, transpose != 0, (double*)dout)
+                        : conic_apply_dpi(ctx, (const double*)dt, transpose != 0, (double*)dout);
+    if (rc) return rc;
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    DO_CUDA(ctx, stage_out_finish(ctx, dout, out, sizeof(double) * len, memspace));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    return 0;
+}
+
+int32_t diffopt_b200_conic_dpi_apply(diffopt_b200_ctx* ctx, const double* t, int32_t transpose, double* out,
+                                     int32_t memspace) {
+    return conic_op_call(ctx, t, transpose, out, memspace, false);
+}
+
+int32_t diffopt_b200_conic_M_apply(diffopt_b200_ctx* ctx, const double* t, int32_t transpose, double* out,
+                                   int32_t memspace) {
+    return conic_op_call(ctx, t, transpose, out, memspace, true);
+}
+
+int32_t diffopt_b200_conic_forward(diffopt_b200_ctx* ctx, int64_t dA_nnz, const int64_t* dA_row, const int64_t* dA_col,
+                                   const double* dA_val, const double* db, const double* dc, double atol, double btol,
+                                   double conlim, int64_t maxiter, double* dx_out, double* dz_out, double* out_stats,
+                                   int32_t memspace) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    ConicState& S = ctx->conic;
+    if (!S.valid) BAD_ARG(ctx, "conic_forward: call conic_setup first");
+    if (dA_nnz < 0 || (dA_nnz > 0 && (!dA_row || !dA_col || !dA_val))) BAD_ARG(ctx, "conic_forward: bad dA triplets");
+    const int n = (int)S.n, m = (int)S.m, N = n + m + 1;
+    const size_t d8 = sizeof(double);
+    const void *drow, *dcol, *dval, *ddb, *ddc;
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[0], dA_row, sizeof(int64_t) * (size_t)dA_nnz, memspace, &drow));
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[1], dA_col, sizeof(int64_t) * (size_t)dA_nnz, memspace, &dcol));
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[2], dA_val, d8 * (size_t)dA_nnz, memspace, &dval));
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[3], db, d8 * (size_t)m, memspace, &ddb));
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[4], dc, d8 * (size_t)n, memspace, &ddc));
+    double* g = S.w2.as<double>();
+    double* dz = S.w3.as<double>();
+    DO_CUDA(ctx, cudaMemsetAsync(g, 0, d8 * (size_t)(N + 1), ctx->stream));
+    if (dA_nnz > 0) {
+        int blocks = (int)((dA_nnz + 255) / 256);
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        conic_fwd_rhs_kernel<<<blocks, 256, 0, ctx->stream>>>(n, m, (long long)dA_nnz, (const long long*)drow,
+                                                               (const long long*)dcol, (const double*)dval,
+                                                               S.x.as<double>(), S.vp.as<double>(), g);
+        ctx->launches++;
+    }
+    conic_fwd_rhs_finish<<<1, 1024, 0, ctx->stream>>>(n, m, (const double*)ddb, (const double*)ddc, S.x.as<double>(),
+                                                      S.vp.as<double>(), g, g + N);
+    ctx->launches++;
+    double normsq = 0.0;
+    DO_CUDA(ctx, cudaMemcpyAsync(&normsq, g + N, d8, cudaMemcpyDeviceToHost, ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double st[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (std::sqrt(normsq) <= 0.0) {                       // `norm(RHS) <= 1e-400` == `<= 0.0` (ConicProgram.jl:320)
+        DO_CUDA(ctx, cudaMemsetAsync(dz, 0, d8 * (size_t)N, ctx->stream));
+    } else {
+        LsqrParams prm{atol, btol, conlim, maxiter > 0 ? maxiter : (int64_t)N};
+        if (int32_t rc = lsqr_run_conic(ctx, g, prm, dz, st)) return rc;
+    }
+    if (dx_out) {
+        void* ddx;
+        DO_CUDA(ctx, stage_out_prepare(ctx->out[0], dx_out, d8 * (size_t)n, memspace, &ddx));
+        conic_fwd_dx_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, m, dz, S.x.as<double>(), (double*)ddx);
+        ctx->launches++;
+        DO_CUDA(ctx, stage_out_finish(ctx, ddx, dx_out, d8 * (size_t)n, memspace));
+    }
+    if (dz_out)
+        DO_CUDA(ctx, cudaMemcpyAsync(dz_out, dz, d8 * (size_t)N,
+                                     memspace == DIFFOPT_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_stats) {
+        if (memspace == DIFFOPT_B200_HOST) memcpy(out_stats, st, d8 * 4);
+        else DO_CUDA(ctx, cudaMemcpy(out_stats, st, d8 * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int32_t diffopt_b200_conic_reverse(diffopt_b200_ctx* ctx, const double* dx_seed, double atol, double btol,
+                                   double conlim, int64_t maxiter, double* g_out, double* dc_out, double* db_out,
+                                   double* out_stats, int32_t memspace) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    ConicState& S = ctx->conic;
+    if (!S.valid) BAD_ARG(ctx, "conic_reverse: call conic_setup first");
+    if (!dx_seed) BAD_ARG(ctx, "conic_reverse: dx_seed is required");
+    const int n = (int)S.n, m = (int)S.m, N = n + m + 1;
+    const size_t d8 = sizeof(double);
+    const void* dseed;
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[0], dx_seed, d8 * (size_t)n, memspace, &dseed));
+    double* dz = S.w2.as<double>();
+    double* g = S.w3.as<double>();
+    conic_rev_rhs_kernel<<<1, 1024, 0, ctx->stream>>>(n, m, (const double*)dseed, S.x.as<double>(), dz, dz + N);
+    ctx->launches++;
+    double normsq = 0.0;
+    DO_CUDA(ctx, cudaMemcpyAsync(&normsq, dz + N, d8, cudaMemcpyDeviceToHost, ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double st[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (std::sqrt(normsq) <= 1e-4) {                       // ConicProgram.jl:369
+        DO_CUDA(ctx, cudaMemsetAsync(g, 0, d8 * (size_t)N, ctx->stream));
+    } else {
+        LsqrParams prm{atol, btol, conlim, maxiter > 0 ? maxiter : (int64_t)N};
+        if (int32_t rc = lsqr_run_conic(ctx, dz, prm, g, st)) return rc;
+    }
+    void *ddc, *ddb;
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[0], dc_out, d8 * (size_t)n, memspace, &ddc));
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[1], db_out, d8 * (size_t)m, memspace, &ddb));
+    if (dc_out || db_out) {
+        int blocks = (N + 255) / 256;
+        conic_rev_getters_kernel<<<blocks, 256, 0, ctx->stream>>>(n, m, g, S.x.as<double>(), S.vp.as<double>(),
+                                                                   (double*)ddc, (double*)ddb);
+        ctx->launches++;
+    }
+    DO_CUDA(ctx, stage_out_finish(ctx, ddc, dc_out, d8 * (size_t)n, memspace));
+    DO_CUDA(ctx, stage_out_finish(ctx, ddb, db_out, d8 * (size_t)m, memspace));
+    if (g_out)
+        DO_CUDA(ctx, cudaMemcpyAsync(g_out, g, d8 * (size_t)N,
+                                     memspace == DIFFOPT_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_stats) {
+        if (memspace == DIFFOPT_B200_HOST) memcpy(out_stats, st, d8 * 4);
+        else DO_CUDA(ctx, cudaMemcpy(out_stats, st, d8 * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,680 @@
+// Persistent cooperative LSQR kernel + the conic matrix-free operator.  See lsqr.cuh.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "lsqr.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int LSQR_THREADS = 256;
+constexpr int NSLOTS = 8;
+
+struct Dev {
+    cg::grid_group grid;
+    double* partials;  // [NSLOTS][nblk]
+    double* red;       // shared scratch (>= 2 * warps doubles)
+    int tid, lane, warp, nwarp, nblk, gtid, gthreads;
+};
+
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-level sum of `v`, result stored as this CTA's partial in `slot`
+__device__ void block_partial(Dev& d, int slot, double v) {
+    v = warp_sum_all(v);
+    if (d.lane == 0) d.red[d.warp] = v;
+    __syncthreads();
+    if (d.tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < d.nwarp; ++w) s += d.red[w];
+        d.partials[slot * d.nblk + blockIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// after a grid.sync(): fixed-order sum of all CTA partials of `slot` (bitwise identical in every thread)
+__device__ double total_of(Dev& d, int slot) {
+    const double* p = d.partials + slot * d.nblk;
+    double s = 0.0;
+    for (int i = d.lane; i < d.nblk; i += 32) s += __ldcg(p + i);
+    return warp_sum_all(s);
+}
+
+// dot product of sparse row `row` with x, computed by a group of T lanes (T = 1,2,4,...,32; groups are
+// aligned inside the warp).  All 32 lanes must call this together.
+template <bool kScaleNone = true>
+__device__ __forceinline__ double row_dot(const CsrView& A, int row, bool valid, const double* __restrict__ x,
+                                          int lane_in_group, int T) {
+    double acc = 0.0;
+    if (valid) {
+        int s = A.rowptr[row], e = A.rowptr[row + 1];
+        for (int k = s + lane_in_group; k < e; k += T) acc += A.val[k] * __ldcg(x + A.colind[k]);
+    }
+    for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
+__device__ __forceinline__ int pick_T(const CsrView& A) {
+    int nnz = A.rowptr[A.nrows];
+    int avg = A.nrows > 0 ? nnz / A.nrows : 1;
+    int T = 1;
+    while (T < 32 && T * 2 <= avg) T <<= 1;
+    return T;
+}
+
+// ---- SOC block of Dpi applied to y (symmetric block, so it serves Dpi and Dpi') ------------------
+// group of `T` lanes handles cone `c`; writes out[off .. off+dim)
+__device__ void soc_apply(const ConicOpView& op, int c, bool valid, const double* __restrict__ y, double* out,
+                          int lig, int T) {
+    int off = 0, dim = 0, cs = 0;
+    double nx = 1.0, t = 0.0;
+    if (valid) {
+        off = op.soc_off[c];
+        dim = op.soc_dim[c];
+        cs = op.soc_case[c];
+        nx = op.soc_nx[c];
+        t = op.v[off];
+    }
+    double xy = 0.0;
+    if (valid && cs == 2)
+        for (int k = 1 + lig; k < dim; k += T) xy += op.v[off + k] * __ldcg(y + off + k);
+    for (int o = T >> 1; o > 0; o >>= 1) xy += __shfl_xor_sync(0xffffffffu, xy, o);
+    if (!valid) return;
+    if (cs == 0) {
+        for (int k = lig; k < dim; k += T) out[off + k] = __ldcg(y + off + k);
+    } else if (cs == 1) {
+        for (int k = lig; k < dim; k += T) out[off + k] = 0.0;
+    } else {
+        const double y0 = __ldcg(y + off);
+        const double inv2 = 1.0 / (2.0 * nx);
+        const double coef = t / (nx * nx) * xy;
+        for (int k = lig; k < dim; k += T) {
+            double r;
+            if (k == 0)
+                r = nx * y0 + xy;
+            else {
+                double xk = op.v[off + k];
+                r = xk * y0 + (nx + t) * __ldcg(y + off + k) - coef * xk;
+            }
+            out[off + k] = r * inv2;
+        }
+    }
+}
+
+// ---- PSD block: out = Dpi*y (transpose=false) or Dpi'*y (true), whole grid cooperates ------------
+// Dpi' y = vec(F(unvec(y)));  Dpi y = S' F T' y  (diag of unvec doubled on the way in, halved on the way out),
+// F(X) = U (B o (U' X U)) U'.   Three d x d scratch matrices per cone; 5 grid syncs per call.
+__device__ void psd_gemm_phase(Dev& d, int dd, const double* __restrict__ Am, bool transA, const double* __restrict__ Bm_,
+                               bool transB, const double* __restrict__ mask, double* __restrict__ C) {
+    // C = op(A) * op(B) [o mask], column-major d x d, one output element per thread, grid-stride
+    const long long total = (long long)dd * dd;
+    for (long long e = d.gtid; e < total; e += d.gthreads) {
+        int i = (int)(e % dd), j = (int)(e / dd);
+        double acc = 0.0;
+        for (int k = 0; k < dd; ++k) {
+            double a = transA ? __ldcg(Am + k + (long long)i * dd) : __ldcg(Am + i + (long long)k * dd);
+            double b = transB ? __ldcg(Bm_ + j + (long long)k * dd) : __ldcg(Bm_ + k + (long long)j * dd);
+            acc += a * b;
+        }
+        if (mask) acc *= mask[e];
+        C[e] = acc;
+    }
+}
+
+__device__ void psd_apply_all(Dev& d, const ConicOpView& op, const double* __restrict__ y, double* out,
+                              bool transpose) {
+    if (op.npsd == 0) return;
+    // phase 0: unvec
+    for (int c = 0; c < op.npsd; ++c) {
+        const int dd = op.psd_d[c], off = op.psd_off[c];
+        double* X = op.psd_w0 + op.psd_uoff[c];
+        const long long total = (long long)dd * dd;
+        for (long long e = d.gtid; e < total; e += d.gthreads) {
+            int i = (int)(e % dd), j = (int)(e / dd);
+            int r = i < j ? i : j, cc = i < j ? j : i;
+            double val = __ldcg(y + off + (long long)cc * (cc + 1) / 2 + r);
+            if (!transpose && i == j) val *= 2.0;
+            X[e] = val;
+        }
+    }
+    d.grid.sync();
+    for (int c = 0; c < op.npsd; ++c) {  // W1 = U' X
+        const int dd = op.psd_d[c];
+        const long long uo = op.psd_uoff[c];
+        if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_U + uo, true, op.psd_w0 + uo, false, nullptr, op.psd_w1 + uo);
+    }
+    d.grid.sync();
+    for (int c = 0; c < op.npsd; ++c) {  // W2 = (W1 U) o B
+        const int dd = op.psd_d[c];
+        const long long uo = op.psd_uoff[c];
+        if (!op.psd_ident[c])
+            psd_gemm_phase(d, dd, op.psd_w1 + uo, false, op.psd_U + uo, false, op.psd_Bm + uo, op.psd_w2 + uo);
+    }
+    d.grid.sync();
+    for (int c = 0; c < op.npsd; ++c) {  // W1 = U W2
+        const int dd = op.psd_d[c];
+        const long long uo = op.psd_uoff[c];
+        if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_U + uo, false, op.psd_w2 + uo, false, nullptr, op.psd_w1 + uo);
+    }
+    d.grid.sync();
+    for (int c = 0; c < op.npsd; ++c) {  // W0 = W1 U'   (identity cones keep X in W0)
+        const int dd = op.psd_d[c];
+        const long long uo = op.psd_uoff[c];
+        if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_w1 + uo, false, op.psd_U + uo, true, nullptr, op.psd_w2 + uo);
+    }
+    d.grid.sync();
+    for (int c = 0; c < op.npsd; ++c) {  // vec
+        const int dd = op.psd_d[c], off = op.psd_off[c];
+        const double* R = (op.psd_ident[c] ? op.psd_w0 : op.psd_w2) + op.psd_uoff[c];
+        const int tri = dd * (dd + 1) / 2;
+        for (int e = d.gtid; e < tri; e += d.gthreads) {
+            // e -> (r, cc) with cc(cc+1)/2 + r = e
+            int cc = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while ((long long)(cc + 1) * (cc + 2) / 2 <= e) ++cc;
+            while ((long long)cc * (cc + 1) / 2 > e) --cc;
+            int r = e - cc * (cc + 1) / 2;
+            double val = __ldcg(R + r + (long long)cc * dd);
+            if (!transpose && r == cc) val *= 0.5;
+            out[off + e] = val;
+        }
+    }
+    // caller syncs
+}
+
+// Dpi (or Dpi') applied to y -> out, for all cones; ends WITHOUT a grid sync when there is no PSD cone
+__device__ void dpi_apply(Dev& d, const ConicOpView& op, const double* __restrict__ y, double* out, bool transpose) {
+    for (int i = d.gtid; i < op.m; i += d.gthreads)
+        if (op.kind[i] == 0) out[i] = op.diag[i] * __ldcg(y + i);
+    {
+        const int T = 8;
+        const int lig = d.lane & (T - 1);
+        const int ngroups = d.gthreads / T;
+        const int g = d.gtid / T;
+        for (int base = 0; base < op.nsoc; base += ngroups) {
+            int c = base + g;
+            soc_apply(op, c, c < op.nsoc, y, out, lig, T);
+        }
+    }
+    psd_apply_all(d, op, y, out, transpose);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Operator application  dst = OP(src)*s_src + s_dst*dst  with ||dst||^2 reduced into `slot`.
+// CSR:   OP = A (rows) or its transpose view (the caller hands the right CsrView).
+// CONIC: OP = M or M'.
+// All functions are called by the whole grid and contain grid syncs.
+
+__device__ void csr_apply(Dev& d, const CsrView& A, const double* __restrict__ src, double s_src, double* dst,
+                          double s_dst, int slot) {
+    const int T = pick_T(A);
+    const int lig = d.lane & (T - 1);
+    const int ngroups = d.gthreads / T;
+    const int g = d.gtid / T;
+    double acc = 0.0;
+    for (int base = 0; base < A.nrows; base += ngroups) {
+        int row = base + g;
+        bool valid = row < A.nrows;
+        double t = row_dot(A, row, valid, src, lig, T);
+        if (valid && lig == 0) {
+            t = t * s_src + s_dst * dst[row];
+            dst[row] = t;
+            acc += t * t;
+        }
+    }
+    block_partial(d, slot, acc);
+}
+
+// dst = s_src * (M src) + s_dst * dst ; slots: slot (norm), slot+1 (last-row dot)
+__device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const double* __restrict__ src,
+                            double s_src, double* dst, double s_dst, int slot) {
+    const int n = op.n, m = op.m, N = n + m + 1;
+    double dotacc = 0.0;
+    if (!transpose) {
+        // wc = Dpi t2
+        dpi_apply(d, op, src + n, op.wc, false);
+        d.grid.sync();
+        const double t3 = __ldcg(src + n + m);
+        double acc = 0.0;
+        {   // rows 0..n-1:  (A' wc)_j + c_j t3
+            const int T = pick_T(op.At);
+            const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
+            for (int base = 0; base < n; base += ngroups) {
+                int row = base + g;
+                bool valid = row < n;
+                double t = row_dot(op.At, row, valid, op.wc, lig, T);
+                if (valid && lig == 0) {
+                    t = (t + op.c[row] * t3) * s_src + s_dst * dst[row];
+                    dst[row] = t;
+                    acc += t * t;
+                    dotacc += op.c[row] * __ldcg(src + row);
+                }
+            }
+        }
+        {   // rows n..n+m-1:  -(A t1)_i + t2_i - wc_i + b_i t3
+            const int T = pick_T(op.A);
+            const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
+            for (int base = 0; base < m; base += ngroups) {
+                int row = base + g;
+                bool valid = row < m;
+                double t = row_dot(op.A, row, valid, src, lig, T);
+                if (valid && lig == 0) {
+                    double wci = __ldcg(op.wc + row);
+                    t = (-t + __ldcg(src + n + row) - wci + op.b[row] * t3) * s_src + s_dst * dst[n + row];
+                    dst[n + row] = t;
+                    acc += t * t;
+                    dotacc += op.b[row] * wci;
+                }
+            }
+        }
+        block_partial(d, slot, acc);
+        block_partial(d, slot + 1, dotacc);
+        d.grid.sync();
+        // last row: -(c't1 + b'wc)
+        double last = -total_of(d, slot + 1) * s_src + s_dst * __ldcg(dst + N - 1);
+        __syncthreads();
+        d.grid.sync();  // everyone has read the old dst[N-1] and the partials
+        if (d.gtid == 0) dst[N - 1] = last;
+        if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
+    } else {
+        // r = A u1 - u2 - b u3  -> wc
+        const double u3 = __ldcg(src + n + m);
+        {
+            const int T = pick_T(op.A);
+            const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
+            for (int base = 0; base < m; base += ngroups) {
+                int row = base + g;
+                bool valid = row < m;
+                double t = row_dot(op.A, row, valid, src, lig, T);
+                if (valid && lig == 0) {
+                    double u2 = __ldcg(src + n + row);
+                    op.wc[row] = t - u2 - op.b[row] * u3;
+                    dotacc += op.b[row] * u2;
+                }
+            }
+        }
+        d.grid.sync();
+        // out2 = Dpi' r + u2 : first Dpi' r into a second scratch = reuse psd-free path by writing to dst later.
+        // We need dst's old value (s_dst * dst), so stage Dpi' r in op.wc's partner buffer: the x-part of dst is
+        // disjoint, so compute into `tmp = psd_w-independent` region: use op.wc in place is unsafe (SOC reads all
+        // entries of its cone) -> stage through dst? no.  Use the dedicated second scratch stored after wc.
+        double* r2 = op.wc + m;  // second half of the 2m scratch
+        dpi_apply(d, op, op.wc, r2, true);
+        d.grid.sync();
+        double acc = 0.0;
+        {   // rows 0..n-1: -(A' u2)_j - c_j u3
+            const int T = pick_T(op.At);
+            const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
+            for (int base = 0; base < n; base += ngroups) {
+                int row = base + g;
+                bool valid = row < n;
+                double t = row_dot(op.At, row, valid, src + n, lig, T);
+                if (valid && lig == 0) {
+                    t = (-t - op.c[row] * u3) * s_src + s_dst * dst[row];
+                    dst[row] = t;
+                    acc += t * t;
+                    dotacc += op.c[row] * __ldcg(src + row);
+                }
+            }
+        }
+        for (int i = d.gtid; i < m; i += d.gthreads) {
+            double t = (__ldcg(r2 + i) + __ldcg(src + n + i)) * s_src + s_dst * dst[n + i];
+            dst[n + i] = t;
+            acc += t * t;
+        }
+        block_partial(d, slot, acc);
+        block_partial(d, slot + 1, dotacc);
+        d.grid.sync();
+        double last = total_of(d, slot + 1) * s_src + s_dst * __ldcg(dst + N - 1);
+        __syncthreads();
+        d.grid.sync();
+        if (d.gtid == 0) dst[N - 1] = last;
+        if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
+    }
+}
+
+struct OpArgs {
+    int kind;  // 0 csr, 1 conic
+    CsrView fwd, adj;  // csr: matrix for A*v and for A'*u
+    ConicOpView conic;
+    int conic_trans;   // solve with M' instead of M
+    int nrows, ncols;
+};
+
+__device__ void op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* src, double s_src, double* dst,
+                         double s_dst, int slot) {
+    if (o.kind == 0)
+        csr_apply(d, adjoint ? o.adj : o.fwd, src, s_src, dst, s_dst, slot);
+    else
+        conic_apply(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot);
+}
+
+__global__ void __launch_bounds__(LSQR_THREADS) lsqr_kernel(OpArgs o, const double* __restrict__ rhs, LsqrParams prm,
+                                                           LsqrVectors vec) {
+    __shared__ double red[64];
+    Dev d{cg::this_grid(), vec.partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
+          (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
+          (int)(gridDim.x * blockDim.x)};
+    const int nr = o.nrows, nc = o.ncols;
+    double *u = vec.u, *v = vec.v, *w = vec.w, *x = vec.x;
+
+    // u = b, beta = ||b||
+    {
+        double acc = 0.0;
+        for (int i = d.gtid; i < nr; i += d.gthreads) {
+            double t = rhs[i];
+            u[i] = t;
+            acc += t * t;
+        }
+        for (int i = d.gtid; i < nc; i += d.gthreads) {
+            x[i] = 0.0;
+            v[i] = 0.0;
+            w[i] = 0.0;
+        }
+        block_partial(d, 0, acc);
+    }
+    d.grid.sync();
+    double beta = sqrt(total_of(d, 0));
+    double alpha = 0.0;
+    double su = 1.0, sv = 1.0;  // true u = su * u_mem, true v = sv * v_mem
+    int istop = 0;
+    long long itn = 0;
+    double anorm = 0, acond = 0, ddnorm = 0, res2 = 0, xnorm = 0, xxnorm = 0, z = 0, sn2 = 0, cs2 = -1.0;
+    double rnorm = beta, arnorm = 0.0;
+    if (beta > 0) {
+        su = 1.0 / beta;
+        op_apply(d, o, true, u, su, v, 0.0, 2);   // v_mem = A' u_true
+        d.grid.sync();
+        alpha = sqrt(total_of(d, 2));
+    }
+    if (alpha > 0) sv = 1.0 / alpha;
+    arnorm = alpha * beta;
+    const double bnorm = beta;
+    double rhobar = alpha, phibar = beta;
+    const double ctol = prm.conlim > 0 ? 1.0 / prm.conlim : 0.0;
+    double t1 = 0, t2 = 0, rho = 1.0, tau = 0;
+    bool first = true;
+    bool pending = false;  // an iteration whose x/w update and stop tests are still to be applied
+
+    if (arnorm != 0.0) {
+        while (true) {
+            // ---- deferred vector update of the previous iteration (or w = v at start), fused with the next
+            //      bidiagonalisation product
+            double dd = 0.0;
+            if (first) {
+                for (int i = d.gtid; i < nc; i += d.gthreads) w[i] = sv * v[i];
+            } else {
+                const double irho = 1.0 / rho;
+                for (int i = d.gtid; i < nc; i += d.gthreads) {
+                    double wi = w[i];
+                    double dk = wi * irho;
+                    dd += dk * dk;
+                    x[i] += t1 * wi;
+                    w[i] = sv * v[i] + t2 * wi;
+                }
+            }
+            block_partial(d, 4, dd);
+            const bool more = itn < prm.maxiter;
+            if (more) op_apply(d, o, false, v, sv, u, -alpha * su, 0);  // u_mem = A v_true - alpha u_true
+            d.grid.sync();
+            if (pending) {
+                ddnorm += total_of(d, 4);
+                acond = anorm * sqrt(ddnorm);
+                const double test1 = rnorm / bnorm;
+                const double test2 = arnorm / (anorm * rnorm);
+                const double test3 = 1.0 / acond;
+                const double t1_ = test1 / (1.0 + anorm * xnorm / bnorm);
+                const double rtol = prm.btol + prm.atol * anorm * xnorm / bnorm;
+                if (itn >= prm.maxiter) istop = 7;
+                if (1.0 + test3 <= 1.0) istop = 6;
+                if (1.0 + test2 <= 1.0) istop = 5;
+                if (1.0 + t1_ <= 1.0) istop = 4;
+                if (test3 <= ctol) istop = 3;
+                if (test2 <= prm.atol) istop = 2;
+                if (test1 <= rtol) istop = 1;
+                pending = false;
+            }
+            first = false;
+            if (istop > 0 || !more) break;
+            itn += 1;
+            beta = sqrt(total_of(d, 0));
+            if (beta > 0) {
+                su = 1.0 / beta;
+                anorm = sqrt(anorm * anorm + alpha * alpha + beta * beta);
+                op_apply(d, o, true, u, su, v, -beta * sv, 2);  // v_mem = A' u_true - beta v_true
+                d.grid.sync();
+                alpha = sqrt(total_of(d, 2));
+                sv = alpha > 0 ? 1.0 / alpha : 1.0;
+            } else {
+                su = 1.0;  // u_mem is exactly zero
+            }
+            // plane rotations (damp = 0)
+            const double rhobar1 = rhobar;
+            rho = hypot(rhobar1, beta);
+            const double cs = rhobar1 / rho, sn = beta / rho;
+            const double theta = sn * alpha;
+            rhobar = -cs * alpha;
+            const double phi = cs * phibar;
+            phibar = sn * phibar;
+            tau = sn * phi;
+            t1 = phi / rho;
+            t2 = -theta / rho;
+            const double delta = sn2 * rho, gambar = -cs2 * rho, rhs_ = phi - delta * z;
+            const double zbar = rhs_ / gambar;
+            xnorm = sqrt(xxnorm + zbar * zbar);
+            const double gamma = hypot(gambar, theta);
+            cs2 = gambar / gamma;
+            sn2 = theta / gamma;
+            z = rhs_ / gamma;
+            xxnorm += z * z;
+            rnorm = sqrt(phibar * phibar + res2);
+            arnorm = alpha * fabs(tau);
+            pending = true;
+        }
+    }
+    if (d.gtid == 0) {
+        vec.stats[0] = (double)istop;
+        vec.stats[1] = (double)itn;
+        vec.stats[2] = rnorm;
+        vec.stats[3] = arnorm;
+        vec.stats[4] = anorm;
+        vec.stats[5] = acond;
+        vec.stats[6] = xnorm;
+    }
+}
+
+// stand-alone operator kernels (C-ABI conic_M_apply / conic_dpi_apply; also used by tests)
+__global__ void __launch_bounds__(LSQR_THREADS) conic_M_kernel(ConicOpView op, int transpose, const double* t, double* out,
+                                                              double* partials) {
+    __shared__ double red[64];
+    Dev d{cg::this_grid(), partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
+          (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
+          (int)(gridDim.x * blockDim.x)};
+    conic_apply(d, op, transpose != 0, t, 1.0, out, 0.0, 0);
+}
+
+__global__ void __launch_bounds__(LSQR_THREADS) conic_dpi_kernel(ConicOpView op, int transpose, const double* t, double* out,
+                                                                double* partials) {
+    __shared__ double red[64];
+    Dev d{cg::this_grid(), partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
+          (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
+          (int)(gridDim.x * blockDim.x)};
+    dpi_apply(d, op, t, out, transpose != 0);
+}
+
+CsrView view_of(const DevBuf& rp, const DevBuf& ci, const DevBuf& v, int64_t nrows, int64_t ncols) {
+    return CsrView{(int)nrows, (int)ncols, rp.as<int>(), ci.as<int>(), v.as<double>()};
+}
+
+}  // namespace
+
+ConicOpView conic_view(diffopt_b200_ctx* ctx) {
+    ConicState& s = ctx->conic;
+    ConicOpView o{};
+    o.n = (int)s.n;
+    o.m = (int)s.m;
+    o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n);
+    o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m);
+    o.b = s.b.as<double>();
+    o.c = s.c.as<double>();
+    o.diag = s.nn_scale.as<double>();
+    o.kind = s.row_kind.as<signed char>();
+    o.nsoc = (int)s.nsoc;
+    o.soc_off = s.soc_off.as<int>();
+    o.soc_dim = s.soc_dim.as<int>();
+    o.soc_case = s.soc_case.as<int>();
+    o.soc_nx = s.soc_nx.as<double>();
+    o.v = s.v.as<double>();
+    o.npsd = (int)s.npsd;
+    o.psd_off = s.psd_off.as<int>();
+    o.psd_d = s.psd_d.as<int>();
+    o.psd_uoff = s.psd_uoff.as<long long>();
+    o.psd_U = s.psd_U.as<double>();
+    o.psd_Bm = s.psd_Bm.as<double>();
+    o.psd_ident = s.psd_ident.as<int>();
+    o.psd_w0 = s.psd_work.as<double>();
+    o.psd_w1 = o.psd_w0 + s.psd_sumd2;
+    o.psd_w2 = o.psd_w1 + s.psd_sumd2;
+    o.wc = s.w1.as<double>();
+    return o;
+}
+
+static int coop_grid(diffopt_b200_ctx* ctx, const void* kernel, int64_t work) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LSQR_THREADS, 0);
+    if (per_sm < 1) per_sm = 1;
+    int64_t want = (work + LSQR_THREADS * 4 - 1) / (LSQR_THREADS * 4);
+    int64_t cap = (int64_t)ctx->sm_count;  // one CTA per SM keeps grid.sync cheap
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+static int32_t lsqr_launch(diffopt_b200_ctx* ctx, OpArgs& o, int64_t work, const double* rhs_dev, LsqrParams prm,
+                           double* x_dev, double* stats_host7) {
+    LsqrWork& wk = ctx->lsqr;
+    const size_t d = sizeof(double);
+    DO_CUDA(ctx, wk.u.reserve(d * (size_t)o.nrows));
+    DO_CUDA(ctx, wk.v.reserve(d * (size_t)o.ncols));
+    DO_CUDA(ctx, wk.w.reserve(d * (size_t)o.ncols));
+    int grid = coop_grid(ctx, (const void*)lsqr_kernel, work);
+    DO_CUDA(ctx, wk.tmp.reserve(d * (size_t)NSLOTS * (size_t)grid));
+    DO_CUDA(ctx, wk.scal.reserve(d * 8));
+    DO_CUDA(ctx, cudaMemsetAsync(wk.tmp.ptr, 0, d * (size_t)NSLOTS * (size_t)grid, ctx->stream));
+    LsqrVectors vec{wk.u.as<double>(), wk.v.as<double>(), wk.w.as<double>(), x_dev, wk.tmp.as<double>(),
+                    wk.scal.as<double>()};
+    void* args[] = {&o, (void*)&rhs_dev, &prm, &vec};
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    DO_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)lsqr_kernel, dim3(grid), dim3(LSQR_THREADS), args, 0,
+                                             ctx->stream));
+    ctx->launches++;
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    double st[7];
+    DO_CUDA(ctx, cudaMemcpyAsync(st, wk.scal.ptr, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    if (stats_host7) memcpy(stats_host7, st, sizeof st);
+    return 0;
+}
+
+int32_t lsqr_run_csr(diffopt_b200_ctx* ctx, const CsrDev& M, bool trans, const double* rhs_dev, LsqrParams prm,
+                     double* x_dev, double* stats_host7) {
+    OpArgs o{};
+    o.kind = 0;
+    CsrView a = view_of(M.rowptr, M.colind, M.val, M.nrows, M.ncols);
+    CsrView at = view_of(M.t_rowptr, M.t_colind, M.t_val, M.ncols, M.nrows);
+    o.fwd = trans ? at : a;
+    o.adj = trans ? a : at;
+    o.nrows = (int)(trans ? M.ncols : M.nrows);
+    o.ncols = (int)(trans ? M.nrows : M.ncols);
+    return lsqr_launch(ctx, o, M.nnz + M.nrows + M.ncols, rhs_dev, prm, x_dev, stats_host7);
+}
+
+int32_t lsqr_run_conic(diffopt_b200_ctx* ctx, const double* rhs_dev, LsqrParams prm, double* x_dev,
+                       double* stats_host7) {
+    ConicState& s = ctx->conic;
+    OpArgs o{};
+    o.kind = 1;
+    o.conic = conic_view(ctx);
+    o.conic_trans = 0;
+    o.nrows = o.ncols = (int)(s.n + s.m + 1);
+    int64_t work = s.A.nnz * 2 + s.n + 2 * s.m + s.psd_sumd2 * 8;
+    return lsqr_launch(ctx, o, work, rhs_dev, prm, x_dev, stats_host7);
+}
+
+static int32_t conic_small_launch(diffopt_b200_ctx* ctx, const void* kernel, const double* t_dev, bool transpose,
+                                  double* out_dev) {
+    ConicState& s = ctx->conic;
+    ConicOpView op = conic_view(ctx);
+    int64_t work = s.A.nnz * 2 + s.n + 2 * s.m + s.psd_sumd2 * 8;
+    int grid = coop_grid(ctx, kernel, work);
+    DO_CUDA(ctx, ctx->lsqr.tmp.reserve(sizeof(double) * (size_t)NSLOTS * (size_t)grid));
+    double* partials = ctx->lsqr.tmp.as<double>();
+    int tr = transpose ? 1 : 0;
+    void* args[] = {&op, &tr, (void*)&t_dev, &out_dev, &partials};
+    DO_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(LSQR_THREADS), args, 0, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
+int32_t conic_apply_M(diffopt_b200_ctx* ctx, const double* t_dev, bool transpose, double* out_dev) {
+    return conic_small_launch(ctx, (const void*)conic_M_kernel, t_dev, transpose, out_dev);
+}
+int32_t conic_apply_dpi(diffopt_b200_ctx* ctx, const double* t_dev, bool transpose, double* out_dev) {
+    return conic_small_launch(ctx, (const void*)conic_dpi_kernel, t_dev, transpose, out_dev);
+}
+
+// Host: Julia CSC (1-based int64) -> device CSR of the matrix and of its transpose (0-based int32).
+int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, const int64_t* colptr,
+                          const int64_t* rowval, const double* nzval, CsrDev& out) {
+    if (nrows < 0 || ncols < 0 || !colptr) BAD_ARG(ctx, "csc: bad dimensions");
+    const int64_t nnz = colptr[ncols] - colptr[0];
+    if (colptr[0] != 1) BAD_ARG(ctx, "csc: colptr must be 1-based (Julia SparseMatrixCSC)");
+    if (nnz < 0 || nnz > 2000000000LL || nrows > 2000000000LL || ncols > 2000000000LL)
+        BAD_ARG(ctx, "csc: too large for int32 indices");
+    // transpose view = CSC arrays reinterpreted: rows of A' are the columns of A
+    std::vector<int> t_rowptr((size_t)ncols + 1), t_colind((size_t)nnz);
+    for (int64_t j = 0; j <= ncols; ++j) t_rowptr[(size_t)j] = (int)(colptr[j] - 1);
+    for (int64_t k = 0; k < nnz; ++k) {
+        int64_t r = rowval[k] - 1;
+        if (r < 0 || r >= nrows) BAD_ARG(ctx, "csc: row index out of range");
+        t_colind[(size_t)k] = (int)r;
+    }
+    // CSR of A by counting sort over rows
+    std::vector<int> rowptr((size_t)nrows + 1, 0), colind((size_t)nnz);
+    std::vector<double> val((size_t)nnz);
+    for (int64_t k = 0; k < nnz; ++k) rowptr[(size_t)t_colind[(size_t)k] + 1]++;
+    for (int64_t i = 0; i < nrows; ++i) rowptr[(size_t)i + 1] += rowptr[(size_t)i];
+    std::vector<int> next(rowptr.begin(), rowptr.end() - 1);
+    for (int64_t j = 0; j < ncols; ++j)
+        for (int k = t_rowptr[(size_t)j]; k < t_rowptr[(size_t)j + 1]; ++k) {
+            int r = t_colind[(size_t)k];
+            int dst = next[(size_t)r]++;
+            colind[(size_t)dst] = (int)j;
+            val[(size_t)dst] = nzval[k];
+        }
+    out.nrows = nrows;
+    out.ncols = ncols;
+    out.nnz = nnz;
+    auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = b.reserve(bytes ? bytes : 8);
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpyAsync(b.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+    };
+    DO_CUDA(ctx, up(out.rowptr, rowptr.data(), sizeof(int) * rowptr.size()));
+    DO_CUDA(ctx, up(out.colind, colind.data(), sizeof(int) * colind.size()));
+    DO_CUDA(ctx, up(out.val, val.data(), sizeof(double) * val.size()));
+    DO_CUDA(ctx, up(out.t_rowptr, t_rowptr.data(), sizeof(int) * t_rowptr.size()));
+    DO_CUDA(ctx, up(out.t_colind, t_colind.data(), sizeof(int) * t_colind.size()));
+    DO_CUDA(ctx, up(out.t_val, nzval, sizeof(double) * (size_t)nnz));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die at return
+    return 0;
+}

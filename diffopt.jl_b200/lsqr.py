@@ -1,0 +1,38 @@
+"""Host wrapper of ``diffopt_b200_lsqr_csc``: LSQR on an explicit sparse matrix in Julia's CSC
+layout -- the ``iterative`` branch of ``solve_system`` (QuadraticProgram.jl:486-492)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from ._capi import HOST, Context, ptr
+
+SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)
+# IterativeSolvers.lsqr defaults (see oracle/lsqr.py for the parity note)
+DEFAULTS = dict(atol=SQRT_EPS, btol=SQRT_EPS, conlim=1.0 / SQRT_EPS)
+
+
+def julia_csc(M):
+    """scipy sparse / dense -> (colptr, rowval, nzval) 1-based int64 like SparseMatrixCSC{Float64,Int}."""
+    import scipy.sparse as sp
+    M = sp.csc_matrix(M, dtype=np.float64)
+    M.sort_indices()
+    return (M.indptr.astype(np.int64) + 1, M.indices.astype(np.int64) + 1,
+            np.ascontiguousarray(M.data, dtype=np.float64))
+
+
+def lsqr_csc(ctx: Context, M, rhs, trans=False, atol=None, btol=None, conlim=None, maxiter=None):
+    """x = argmin ||M x - rhs|| (or M' when ``trans``) from x0 = 0.  Returns (x, stats)."""
+    nrows, ncols = M.shape
+    colptr, rowval, nzval = julia_csc(M)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    x = np.empty(nrows if trans else ncols)
+    stats = np.zeros(4)
+    rc = ctx.lib.diffopt_b200_lsqr_csc(
+        ctx.h, nrows, ncols, ptr(colptr), ptr(rowval), ptr(nzval), int(trans), ptr(rhs),
+        DEFAULTS["atol"] if atol is None else atol, DEFAULTS["btol"] if btol is None else btol,
+        DEFAULTS["conlim"] if conlim is None else conlim, 0 if maxiter is None else int(maxiter),
+        ptr(x), ptr(stats), HOST)
+    ctx.check(rc)
+    return x, dict(istop=int(stats[0]), itn=int(stats[1]), rnorm=stats[2], arnorm=stats[3])

@@ -1,0 +1,213 @@
+"""GPU parity tests for the LSQR and ConicProgram hot path (through the C ABI) vs the CPU oracle.
+
+Tolerance (BASELINE.json north_star): relative error <= 1e-6 for LSQR-based sensitivities, both sides
+run with the same explicit tolerances (``matched residual tolerance``)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import bench_data
+import diffopt_b200
+from oracle import cones as ocones
+from oracle import conic as oconic
+from oracle import lsqr as olsqr
+from oracle import qp as oqp
+
+pytestmark = pytest.mark.gpu
+RTOL_LSQR = 1e-6
+TIGHT = dict(atol=1e-12, btol=1e-12, conlim=1e12)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return diffopt_b200.Context(0)
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_lsqr_csc_matches_oracle(ctx):
+    lsqr = diffopt_b200.submodule("lsqr")
+    rng = np.random.default_rng(3)
+    A = (sp.random(400, 250, density=0.04, random_state=1) + sp.eye(400, 250)).tocsc()
+    b = rng.normal(size=400)
+    x, st = lsqr.lsqr_csc(ctx, A, b)
+    xo, info = olsqr.lsqr(A, b, return_info=True)
+    assert st["itn"] == info.itn and st["istop"] == info.istop
+    assert rel(x, xo) <= 1e-10
+    bt = rng.normal(size=250)
+    xt, _ = lsqr.lsqr_csc(ctx, A, bt, trans=True)
+    assert rel(xt, olsqr.lsqr(A.T.tocsc(), bt)) <= 1e-10
+
+
+def test_lp_config1_lsqr_on_kkt(ctx):
+    """BASELINE config 1: LP n=200, m=100 -> rank-deficient KKT, minimum-norm LSQR limit."""
+    qpm = diffopt_b200.submodule("qp")
+    d = bench_data.lp_config1()
+    model = qpm.QPModel(ctx, d["Q"], d["q"], d["G"], d["h"], d["A"], d["b"])
+    model.set_variable_primal(d["z"]); model.set_constraint_dual_le(-d["lam"]); model.set_constraint_dual_eq(-d["nu"])
+    model.iterative_tolerances = dict(atol=1e-13, btol=1e-13, conlim=1e14, maxiter=5000)
+    model.reverse_differentiate(d["seed"])
+    got = np.concatenate(model.back_grad_cache)
+    want = np.concatenate(oqp.reverse(d["Q"], d["G"], d["h"], d["A"], d["z"], d["lam"], d["nu"], d["seed"],
+                                      atol=1e-13, btol=1e-13, conlim=1e14, maxiter=5000))
+    assert rel(got, want) <= RTOL_LSQR
+    K = oqp.create_lhs(d["z"], d["lam"], d["Q"], d["G"], d["h"], d["A"])
+    rhs = np.zeros(300); rhs[:200] = d["seed"]
+    assert rel(got, -np.linalg.pinv(K) @ rhs) <= 1e-5      # min-norm solution
+    # default tolerances as the reference would run it
+    model.iterative_tolerances = dict(atol=None, btol=None, conlim=None, maxiter=None)
+    model.reverse_differentiate(d["seed"])
+    want = np.concatenate(oqp.reverse(d["Q"], d["G"], d["h"], d["A"], d["z"], d["lam"], d["nu"], d["seed"]))
+    assert rel(np.concatenate(model.back_grad_cache), want) <= RTOL_LSQR
+
+
+def test_lp_known_answers(ctx, kat):
+    qpm = diffopt_b200.submodule("qp")
+    for name in ["lp_simplex_example", "lp_fixed_variable", "lp_nonactive"]:
+        c = kat[name]
+        n, m, p = len(c["z"]), len(c["lam"]), len(c["nu"])
+        a = lambda k, shape: np.array(c[k], float).reshape(shape)
+        model = qpm.QPModel(ctx, a("Q", (n, n)), a("q", n), a("G", (m, n)), a("h", m), a("A", (p, n)), a("b", p))
+        model.set_variable_primal(c["z"]); model.set_constraint_dual_le(-a("lam", m)); model.set_constraint_dual_eq(-a("nu", p))
+        model.reverse_differentiate(c["seed"])
+        dq, _ = model.reverse_objective_function()
+        got = dict(dq=dq, grad_z=dq, grad_lam=model.back_grad_cache[1],
+                   dh=-np.array([model.get_db_le(i) for i in range(m)]),
+                   db=-np.array([model.get_db_eq(i) for i in range(p)]),
+                   dG=np.array([model.get_dA_le(i) for i in range(m)]).reshape(m, n),
+                   dA=np.array([model.get_dA_eq(i) for i in range(p)]).reshape(p, n))
+        for k, e in c["exp"].items():
+            e = np.array(e, float).ravel(); g = np.asarray(got[k]).ravel()
+            assert np.linalg.norm(g - e) <= max(c["tol"], c["tol"] * max(np.linalg.norm(g), np.linalg.norm(e))), (name, k)
+        if "fwd" in c:
+            f = c["fwd"]
+            fa = lambda k, shape: np.array(f[k], float).reshape(shape)
+            model.forward_differentiate(fa("dQ", (n, n)), fa("dq", n), fa("dG", (m, n)), fa("dh", m), fa("dA", (p, n)), fa("db", p))
+            assert np.allclose(model.forward_variable_primal(), c["exp_fwd"]["dz"], atol=c["tol"])
+
+
+def _model_from_kat(ctx, c):
+    cm = diffopt_b200.submodule("conic")
+    model = cm.ConicModel.from_moi(ctx, np.array(c["coefficients"], float), c["constants"], c["c"],
+                                   c["cone_types"], c["cone_dims"])
+    model.set_variable_primal(c["x"]); model.set_constraint_primal(c["s"]); model.set_constraint_dual(c["y"])
+    return model
+
+
+@pytest.mark.parametrize("name", ["conic_socp", "conic_psd2", "conic_psd3"])
+def test_conic_reference_known_answers(ctx, kat, name):
+    c = kat[name]
+    model = _model_from_kat(ctx, c)
+    for f in c.get("fwd", []):
+        model.forward_differentiate(np.array(f["dA"], float), f["db"], f["dc"])
+        assert np.allclose(model.forward_variable_primal(), f["exp_dx"], atol=c["tol"])
+    for r in c.get("rev", []):
+        model.reverse_differentiate(r["seed"])
+        assert np.allclose(model.get_db(r["exp_db_rows"]), r["exp_db"], atol=c["tol"])
+
+
+def _oracle_cache(d):
+    return oconic.gradient_cache(d["A"], d["b"], d["c"], d["x"], d["s"], d["y"], d["cone_types"], d["cone_dims"])
+
+
+@pytest.mark.parametrize("psd_sides", [(), (4, 7), (12,)])
+def test_pi_dpi_and_M_operator(ctx, psd_sides):
+    cm = diffopt_b200.submodule("conic")
+    d = bench_data.conic_config4(n=60, n_zero=7, n_nonneg=30, n_soc=9, soc_dim=5, nnz_per_row=4, seed=11,
+                                 psd_sides=psd_sides)
+    model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+    model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
+    v = d["y"] - d["s"]
+    assert np.allclose(model.vp(), ocones.pi(v, d["cone_types"], d["cone_dims"]), rtol=1e-11, atol=1e-12)
+    D = ocones.Dpi_dense(v, d["cone_types"], d["cone_dims"])      # the reference's dense blocks
+    cache = _oracle_cache(d)
+    Md = cache.M.toarray()
+    rng = np.random.default_rng(0)
+    for _ in range(2):
+        t = rng.normal(size=D.shape[0])
+        assert rel(model.dpi_apply(t), D @ t) <= 1e-11
+        assert rel(model.dpi_apply(t, transpose=True), D.T @ t) <= 1e-11
+        T = rng.normal(size=Md.shape[0])
+        assert rel(model.M_apply(T), Md @ T) <= 1e-11
+        assert rel(model.M_apply(T, transpose=True), Md.T @ T) <= 1e-11
+
+
+@pytest.mark.parametrize("psd_sides", [(), (6,)])
+def test_conic_forward_reverse_match_oracle(ctx, psd_sides):
+    cm = diffopt_b200.submodule("conic")
+    d = bench_data.conic_config4(n=200, n_zero=20, n_nonneg=160, n_soc=12, soc_dim=10, nnz_per_row=6, seed=21,
+                                 psd_sides=psd_sides)
+    model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+    model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
+    model.tolerances = dict(TIGHT, maxiter=20000)
+    cache = _oracle_cache(d)
+    kw = dict(TIGHT, maxiter=20000)
+    model.reverse_differentiate(d["seed"])
+    g = oconic.reverse(cache, d["seed"], **kw)
+    _, db, dc = oconic.reverse_param_grads(cache, g, dense_dA=False)
+    assert rel(model.back_grad_cache["g"], g) <= RTOL_LSQR
+    assert rel(model.reverse_objective_function(), dc) <= RTOL_LSQR
+    assert rel(model.get_db(), db) <= RTOL_LSQR
+    rows = np.array([0, 25, 190])
+    dA_ref = np.outer(g[200 + rows], d["x"]) - np.outer(cache.vp[rows], g[:200])
+    assert rel(model.get_dA(rows), dA_ref) <= RTOL_LSQR
+    rng = np.random.default_rng(5)
+    dA = sp.random(*d["A"].shape, density=0.01, random_state=2).tocsc()
+    dbv, dcv = rng.normal(size=d["A"].shape[0]), rng.normal(size=200)
+    model.forward_differentiate(dA, dbv, dcv)
+    dx, dz = oconic.forward(cache, dA, dbv, dcv, **kw)
+    assert rel(model.forward_variable_primal(), dx) <= RTOL_LSQR
+    # zero perturbation -> zeros (ConicProgram.jl:320-321), tiny seed -> zeros (:369-370)
+    model.forward_differentiate(None, None, None)
+    assert not model.forward_variable_primal().any()
+    model.reverse_differentiate(np.full(200, 1e-7))
+    assert not model.back_grad_cache["g"].any()
+
+
+def test_conic_config4_full_size(ctx):
+    """BASELINE config 4 at full size (n=5000, m=7500): reverse mode vs the oracle at matched tolerances."""
+    cm = diffopt_b200.submodule("conic")
+    d = bench_data.conic_config4()
+    model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+    model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
+    tol = dict(atol=1e-10, btol=1e-10, conlim=1e12, maxiter=12501)
+    model.tolerances = tol
+    model.reverse_differentiate(d["seed"])
+    g = oconic.reverse(_oracle_cache(d), d["seed"], **tol)
+    assert rel(model.back_grad_cache["g"], g) <= RTOL_LSQR
+    # size-independent property: the answer is a least-squares solution, M'(M g - dz) ~ 0
+    dz = np.concatenate([d["seed"], np.zeros(7500), [-(d["x"] @ d["seed"])]])
+    r = model.M_apply(model.back_grad_cache["g"]) - dz
+    assert np.linalg.norm(model.M_apply(r, transpose=True)) <= 1e-6 * np.linalg.norm(dz)
+
+
+def test_psd_maxcut_200(ctx):
+    """BASELINE config 5: 200 x 200 PSD cone (max-cut SDP shape).  pi and the Dpi operator vs the oracle
+    (eigh + 4 GEMMs); the reference's literal dense 20100^2 Jacobian is never formed."""
+    cm = diffopt_b200.submodule("conic")
+    dd, r = 200, 20
+    rng = np.random.default_rng(5)
+    V = rng.normal(size=(dd, r)); V /= np.linalg.norm(V, axis=1, keepdims=True)
+    X = V @ V.T
+    Qf, _ = np.linalg.qr(np.hstack([V, rng.normal(size=(dd, dd - r))]))
+    W = Qf[:, r:]
+    Smat = (W * rng.uniform(0.5, 1.5, size=dd - r)) @ W.T
+    k = dd * (dd + 1) // 2
+    s = np.concatenate([np.zeros(dd), ocones.vec_symm(X)])
+    y = np.concatenate([rng.normal(size=dd), ocones.vec_symm(Smat)])
+    # rows: Zeros(200) (X_ii = 1) + PSD triangle; variables = the triangle
+    iu = [(i * (i + 1) // 2 + i) for i in range(dd)]
+    A = sp.vstack([sp.csc_matrix((np.ones(dd), (np.arange(dd), iu)), shape=(dd, k)), -sp.identity(k)]).tocsc()
+    x = ocones.vec_symm(X)
+    b = A @ x + s
+    c = -(A.T @ y)
+    model = cm.ConicModel(ctx, A, b, c, [ocones.ZERO, ocones.PSD], [dd, k])
+    model.set_variable_primal(x); model.set_constraint_primal(s); model.set_constraint_dual(y)
+    v = y - s
+    assert rel(model.vp(), ocones.pi(v, [ocones.ZERO, ocones.PSD], [dd, k])) <= 1e-9
+    t = rng.normal(size=dd + k)
+    for tr in (False, True):
+        want = ocones.Dpi_apply(v, [ocones.ZERO, ocones.PSD], [dd, k], t, transpose=tr)
+        assert rel(model.dpi_apply(t, transpose=tr), want) <= 1e-8
