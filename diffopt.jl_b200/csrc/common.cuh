@@ -156,6 +156,7 @@ struct QpSolveArgs {
     const double *dQ, *dq, *dG, *dh, *dA, *db, *seed;
     double *fwd, *rev;
     int* info;
+    long long* prof;  // optional per-phase clock counters of CTA 0 (DIFFOPT_B200_PROFILE=1)
 };
 int32_t qp_batch_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a);
 int32_t qp_param_grads_launch(diffopt_b200_ctx* ctx, int64_t B, int n, int m, int p, const double* z,
