@@ -44,6 +44,8 @@ int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {
     for (auto& b : ctx->in) b.release();
     for (auto& b : ctx->out) b.release();
     ctx->info.release();
+    ctx->qp_fb.release();
+    ctx->qp_max.release();
     QpBatchState& q = ctx->qp;
     q.Q.release(); q.G.release(); q.A.release(); q.h.release(); q.z.release(); q.lam.release(); q.nu.release();
     ConicState& c = ctx->conic;

@@ -86,6 +86,8 @@ struct diffopt_b200_ctx {
     DevBuf in[16];
     DevBuf out[8];
     DevBuf info;
+    DevBuf qp_fb;   // [count, list...] of instances the LDL' fast path hands to the pivoted LU kernel
+    DevBuf qp_max;  // device scalar: largest active-set size of the batch
     QpBatchState qp;
     ConicState conic;
     LsqrWork lsqr;

@@ -264,7 +264,9 @@ __device__ __forceinline__ void panel_dispatch(const Ctx& X, int j, int lane, in
     else panel_factor<1>(&X.S, X.K, X.nt, j, lane, np);
 }
 
-__global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a) {
+// list != nullptr: solve only the instances list[0 .. *count) (the ones the LDL' fast path rejected)
+__global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a, const int* __restrict__ list,
+                                                                  const int* __restrict__ count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemHdr& S = *reinterpret_cast<SmemHdr*>(smem_raw);
     double* const K = reinterpret_cast<double*>(smem_raw + sizeof(SmemHdr));
@@ -284,7 +286,9 @@ __global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a) 
 #define PROF(i)
 #endif
 
-    for (int64_t inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
+    const int64_t nwork = list ? (int64_t)*count : a.B;
+    for (int64_t work = blockIdx.x; work < nwork; work += gridDim.x) {
+        const int64_t inst = list ? (int64_t)list[work] : work;
         const double* Q = a.Q + (size_t)inst * NV * NV;
         const double* G = a.G + (size_t)inst * MI * NV;
         const double* A = a.A + (size_t)inst * PE * NV;
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a) 
             }
         }
         {   // L2 prefetch of the next instance of this CTA (inputs are streamed once from HBM)
-            const int64_t nxt = inst + gridDim.x;
+            const int64_t nxt = list ? a.B : inst + gridDim.x;
             if (nxt < a.B) {
                 const char* bases[6] = {(const char*)(a.Q + (size_t)nxt * NV * NV), (const char*)(a.G + (size_t)nxt * MI * NV),
                                         (const char*)(a.A + (size_t)nxt * PE * NV),
@@ -770,25 +774,11 @@ __global__ void max_active_kernel(int64_t B, const double* __restrict__ lam, int
 
 }  // namespace
 
-int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool* handled) {
+int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled);
+
+static int32_t lu_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, const int* list, const int* count,
+                         bool* handled) {
     *handled = false;
-    if (a.n != NV || a.m != MI || a.p != PE) return 0;
-    const char* force = getenv("DIFFOPT_B200_QP_KERNEL");
-    if (force && strcmp(force, "generic") == 0) return 0;
-    // size the tile matrix by the largest reduced system of the batch
-    static thread_local int* dmax = nullptr;
-    if (!dmax) DO_CUDA(ctx, cudaMalloc(&dmax, sizeof(int)));
-    DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
-    {
-        int64_t blocks = (a.B + 7) / 8;
-        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-        max_active_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a.B, a.lam, dmax);
-        ctx->launches++;
-    }
-    int hmax = 0;
-    DO_CUDA(ctx, cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int nt_cap = (NV + hmax + PE + 7) / 8;
     const size_t smem = sizeof(SmemHdr) + (size_t)nt_cap * nt_cap * 64 * sizeof(double);
     if (smem > ctx->smem_optin) return 0;  // falls back to the generic kernel
     *handled = true;
@@ -799,14 +789,16 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > a.B) grid = a.B;
     QpSolveArgs aa = a;
-    const bool profile = getenv("DIFFOPT_B200_PROFILE") != nullptr;
+    const bool profile = !list && getenv("DIFFOPT_B200_PROFILE") != nullptr;
     long long* dprof = nullptr;
     if (profile) {
         DO_CUDA(ctx, cudaMalloc(&dprof, 8 * sizeof(long long)));
         DO_CUDA(ctx, cudaMemsetAsync(dprof, 0, 8 * sizeof(long long), ctx->stream));
         aa.prof = dprof;
+    } else {
+        aa.prof = nullptr;
     }
-    qp_kkt_n144_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa);
+    qp_kkt_n144_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa, list, count);
     ctx->launches++;
     DO_CUDA(ctx, cudaGetLastError());
     if (profile) {
@@ -822,4 +814,42 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
                 h[5] / ninst);
     }
     return 0;
+}
+
+// the pivoted LU kernel over a device-side list of instances (fallback of the LDL' fast path)
+int32_t qp_lu_launch_list(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, const int* list, const int* count) {
+    bool handled = false;
+    int32_t rc = lu_launch(ctx, a, nt_cap, list, count, &handled);
+    if (rc == 0 && !handled) {
+        ctx->err = "qp_batch: pivoted-LU fallback does not fit in shared memory";
+        return -3;
+    }
+    return rc;
+}
+
+// DIFFOPT_B200_QP_KERNEL = generic | lu | (default) ldl : which kernel serves the n=64, m=64, p=16 shape
+int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool* handled) {
+    *handled = false;
+    if (a.n != NV || a.m != MI || a.p != PE) return 0;
+    const char* force = getenv("DIFFOPT_B200_QP_KERNEL");
+    if (force && strcmp(force, "generic") == 0) return 0;
+    // size the tile matrix by the largest reduced system of the batch
+    DO_CUDA(ctx, ctx->qp_max.reserve(sizeof(int)));
+    int* dmax = ctx->qp_max.as<int>();
+    DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
+    {
+        int64_t blocks = (a.B + 7) / 8;
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        max_active_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a.B, a.lam, dmax);
+        ctx->launches++;
+    }
+    int hmax = 0;
+    DO_CUDA(ctx, cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int nt_cap = (NV + hmax + PE + 7) / 8;
+    if (!(force && strcmp(force, "lu") == 0)) {
+        int32_t rc = qp_sqd_launch(ctx, a, nt_cap, handled);
+        if (rc != 0 || *handled) return rc;
+    }
+    return lu_launch(ctx, a, nt_cap, nullptr, nullptr, handled);
 }

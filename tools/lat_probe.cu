@@ -63,6 +63,31 @@ __global__ void probe(double* out, long long* t, double seed) {
 #pragma unroll
     for (int i = 0; i < REP; ++i) m = m * 1.0000001;
     t1 = clock64(); t[8] = (t1 - t0);
+    // rcp.approx.ftz.f64 + 2 Newton steps chain
+    double fr = m + 2.0;
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        double rr;
+        asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(fr));
+        double e = fma(-fr, rr, 1.0);
+        rr = fma(rr, e, rr);
+        e = fma(-fr, rr, 1.0);
+        rr = fma(rr, e, rr);
+        fr = rr + 1.5;
+    }
+    t1 = clock64(); t[10] = (t1 - t0) * 4;
+    // bare MUFU.RCP64H chain
+    double fq = fr;
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        double rr;
+        asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(fq));
+        fq = rr;
+    }
+    t1 = clock64(); t[11] = (t1 - t0) * 4;
+    m += fr + fq;
     // __syncthreads cost with 512 threads is measured separately
     out[lane] = x + c0 + c1 + k + s + b + idx + r + q + m;
 }
@@ -79,7 +104,7 @@ int main() {
     probe<<<1, 32>>>(out, t, 1.000001);
     barprobe<<<1, 512>>>(t);
     cudaDeviceSynchronize();
-    const char* names[] = {"DFMA", "DMMA.8x8x4", "REDUX.max", "SHFL", "ballot+ffs(+add)", "LDS chase(+cvt)", "DRCP(+add)", "STS/syncwarp/LDS", "DMUL", "syncthreads(512)"};
-    for (int i = 0; i < 10; ++i) printf("%-20s %.1f clk\n", names[i], (double)t[i] / REP);
+    const char* names[] = {"DFMA", "DMMA.8x8x4", "REDUX.max", "SHFL", "ballot+ffs(+add)", "LDS chase(+cvt)", "DRCP(+add)", "STS/syncwarp/LDS", "DMUL", "syncthreads(512)", "fast_rcp(+add)", "MUFU.RCP64H"};
+    for (int i = 0; i < 12; ++i) printf("%-20s %.1f clk\n", names[i], (double)t[i] / REP);
     return 0;
 }
