@@ -40,7 +40,8 @@ constexpr double PIV_RTOL = 1e-12;
 
 struct __align__(16) Hdr {
     double yf[N + 8], yb[N + 8];  // right-hand sides -> v = D^-1 L^-1 r -> solutions (reduced ordering)
-    double sf[N + 8], sb[N + 8];  // backward-substitution accumulators
+    double sf[N + 8], sb[N + 8];    // backward-substitution accumulators of the critical warps
+    double sf2[N + 8], sb2[N + 8];  // ... and of their helper warps
     double ref[N + 8];            // starting magnitude of every diagonal entry (pivot test)
     double rd[N + 8];             // 1 / d_k
     double zs[NV], lams[MI], nus[PE], dvec[MI];
@@ -62,15 +63,20 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-// 1/x to ~1 ulp: hardware estimate + two Newton steps (x is a checked pivot, never 0/inf/nan)
+// 1/x: hardware estimate (rel. error <= 2^-20) + one cubic Newton step r0 (1 + e + e^2), e = 1 - x r0:
+// rel. error e^3 < 2^-60, three dependent FMAs on the pivot chain instead of four.
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
+// named barrier of the warp pair that owns right-hand side r (ids 1, 2; id 0 is __syncthreads)
+__device__ __forceinline__ void pair_barrier(const int r) {
+    if (r) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else asm volatile("bar.sync 1, 64;" ::: "memory");
 }
 
 __device__ __forceinline__ double sum_over_g(double v) {  // lanes sharing t = lane & 3
@@ -85,10 +91,26 @@ __device__ __forceinline__ double sum_over_t(double v) {  // lanes sharing g = l
     return v;
 }
 
-// LDL' of the 8 x 8 diagonal block by warp 0: lane 0 eliminates in registers, then lanes 0..7 each build one
-// column of inv(L11) (unit lower).  On exit the tile holds inv(L11) (zeros above the diagonal), rd[] = 1/d.
-__device__ __forceinline__ void diag_block(double* D, const double* ref, double* rd, const bool positive, int* fail,
-                                           const int lane) {
+// trailing-triangle pair table: linear index q -> (ia >= ib), q = ia (ia + 1) / 2 + ib
+__constant__ unsigned char PAIR_A[160], PAIR_B[160];
+
+// one 8-tile row of a column-major matrix (leading dimension ld): lane (g, t) gets rows r0, r0+1 of column 8J+g
+__device__ __forceinline__ void load_row8(const double* M, const int ld, const int r0, const int g, double2 (&v)[8]) {
+    if (M) {
+#pragma unroll
+        for (int J = 0; J < 8; ++J) v[J] = ldg2(M + (8 * J + g) * ld + r0);
+    } else {
+#pragma unroll
+        for (int J = 0; J < 8; ++J) v[J] = make_double2(0.0, 0.0);
+    }
+}
+
+// LDL' of the 8 x 8 diagonal block by one warp: lane 0 eliminates in registers (products formed ahead of the
+// reciprocal so that one FMA follows it on the pivot chain), then lanes 0..7 each build one column of inv(L11)
+// (unit lower).  On exit the tile holds inv(L11) (zeros above the diagonal), rd[] = 1/d.  selfref: the pivot
+// test refers to the block's own starting diagonal (first block of the Schur complement).
+__device__ __noinline__ void diag_block(double* D, double* ref, double* rd, const bool positive, const bool selfref,
+                                           int* fail, const int lane) {
     if (lane == 0) {
         double a[8][8];
 #pragma unroll
@@ -102,32 +124,48 @@ __device__ __forceinline__ void diag_block(double* D, const double* ref, double*
                 }
             }
         }
-        bool bad = false;
+        double thr[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            double d = a[k][k];
-            const double mag = positive ? d : -d;
-            if (!(mag > PIV_RTOL * ref[k])) {
-                bad = true;
-                d = positive ? 1.0 : -1.0;
-            }
-            const double r = fast_rcp(d);
+            const double rf = selfref ? fabs(a[k][k]) : ref[k];
+            if (selfref) ref[k] = rf;
+            thr[k] = PIV_RTOL * rf;
+        }
+        bool bad = false;
+        // Software pipelined: the next pivot (one FMA behind r) and its reciprocal are started BEFORE the bulk of
+        // this step's rank-1 update is issued, so the update fills the reciprocal's latency.
+        double d = a[0][0];
+        if (!((positive ? d : -d) > thr[0])) {
+            bad = true;
+            d = positive ? 1.0 : -1.0;
+        }
+        double r = fast_rcp(d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
             rd[k] = r;
+            double rn = 0.0;
+            if (k < 7) {
+                double dn = fma(-(a[k + 1][k] * a[k + 1][k]), r, a[k + 1][k + 1]);
+                if (!((positive ? dn : -dn) > thr[k + 1])) {
+                    bad = true;
+                    dn = positive ? 1.0 : -1.0;
+                }
+                rn = fast_rcp(dn);
+            }
             double lk[8];
 #pragma unroll
             for (int i = k + 1; i < 8; ++i) lk[i] = a[i][k] * r;
 #pragma unroll
-            for (int i = k + 1; i < 8; ++i) {
+            for (int i = k + 2; i < 8; ++i) a[i][k + 1] = fma(-lk[i], a[k + 1][k], a[i][k + 1]);
 #pragma unroll
-                for (int c = k + 1; c <= i; ++c) a[i][c] = fma(-lk[i], a[c][k], a[i][c]);
+            for (int c = k + 2; c < 8; ++c) {
+#pragma unroll
+                for (int i = c; i < 8; ++i) a[i][c] = fma(-lk[i], a[c][k], a[i][c]);
             }
 #pragma unroll
-            for (int i = k + 1; i < 8; ++i) a[i][k] = lk[i];
+            for (int i = k + 1; i < 8; ++i) D[i * 8 + k] = lk[i];
+            r = rn;
         }
-#pragma unroll
-        for (int i = 1; i < 8; ++i)
-#pragma unroll
-            for (int c = 0; c < i; ++c) D[i * 8 + c] = a[i][c];
         if (bad) *fail = 1;
     }
     __syncwarp();
@@ -138,12 +176,13 @@ __device__ __forceinline__ void diag_block(double* D, const double* ref, double*
         for (int i = 1; i < 8; ++i)
 #pragma unroll
             for (int c = 0; c < i; ++c) l[i][c] = D[i * 8 + c];
+        // column `lane` of inv(L11): unit-lower solve in axpy form (one FMA per step on the chain)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            double s = (i == lane) ? 1.0 : 0.0;
+        for (int i = 0; i < 8; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-            for (int k = 0; k < i; ++k) s = fma(-l[i][k], x[k], s);
-            x[i] = (i >= lane) ? s : 0.0;
+        for (int k = 0; k < 7; ++k) {
+#pragma unroll
+            for (int i = k + 1; i < 8; ++i) x[i] = fma(-l[i][k], x[k], x[i]);
         }
     }
     __syncwarp();
@@ -160,6 +199,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // g, t: DMMA fragment coordinates; the same pair addresses the tile-shaped global loads (column g, rows 2t, 2t+1)
     const int g = lane >> 2, t = lane & 3;
+    const int fo = g * 8 + 2 * t;  // fragment offset inside a tile
     const bool do_fwd = a.fwd != nullptr, do_rev = a.rev != nullptr;
 #ifdef QP_PROFILE
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -175,17 +215,18 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
 #endif
 
     for (int64_t inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
-        const double* Q = a.Q + (size_t)inst * NV * NV;
-        const double* G = a.G + (size_t)inst * MI * NV;
-        const double* A = a.A + (size_t)inst * PE * NV;
+        const size_t b = (size_t)inst;
+        const double* Q = a.Q + b * NV * NV;
+        const double* G = a.G + b * MI * NV;
+        const double* A = a.A + b * PE * NV;
         // ---- vectors, active set
         if (tid < NV) {
-            S.zs[tid] = a.z[(size_t)inst * NV + tid];
-            S.yb[tid] = do_rev ? a.seed[(size_t)inst * NV + tid] : 0.0;
+            S.zs[tid] = a.z[b * NV + tid];
+            S.yb[tid] = do_rev ? a.seed[b * NV + tid] : 0.0;
         } else if (tid < NV + PE) {
-            S.nus[tid - NV] = a.nu[(size_t)inst * PE + tid - NV];
+            S.nus[tid - NV] = a.nu[b * PE + tid - NV];
         } else if (warp == 3) {
-            const double l0 = a.lam[(size_t)inst * MI + lane], l1 = a.lam[(size_t)inst * MI + 32 + lane];
+            const double l0 = a.lam[b * MI + lane], l1 = a.lam[b * MI + 32 + lane];
             S.lams[lane] = l0;
             S.lams[32 + lane] = l1;
             const unsigned m0 = __ballot_sync(FULL, l0 != 0.0), m1 = __ballot_sync(FULL, l1 != 0.0);
@@ -199,28 +240,23 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                 S.fail = 0;
             }
         }
-        // Q: lower-triangle tiles only; warp w owns tile rows w and 7-w (9 tiles each)
-        double2 qv[16];
+        // Loads are software pipelined through two 8-tile register buffers: the next group is in flight while
+        // the current one is consumed.  Q: lower-triangle tiles only; warp w owns tile rows w and 7-w (9 tiles).
+        double2 qv[9], bufA[8], bufB[8], av[4];
 #pragma unroll
-        for (int J = 0; J < 8; ++J) {
-            if (J <= warp) qv[J] = ldg2(Q + (8 * J + g) * NV + 8 * warp + 2 * t);
-            if (J <= 7 - warp) qv[8 + J] = ldg2(Q + (8 * J + g) * NV + 8 * (7 - warp) + 2 * t);
+        for (int s9 = 0; s9 < 9; ++s9) {
+            const bool first = s9 <= warp;
+            const int I = first ? warp : 7 - warp, J = first ? s9 : s9 - warp - 1;
+            qv[s9] = ldg2(Q + (8 * J + g) * NV + 8 * I + 2 * t);
         }
-        {   // L2 prefetch of the next instance of this CTA (inputs are streamed once from HBM)
-            const int64_t nxt = inst + gridDim.x;
-            if (nxt < a.B) {
-                const char* bases[6] = {(const char*)(a.Q + (size_t)nxt * NV * NV), (const char*)(a.G + (size_t)nxt * MI * NV),
-                                        do_fwd && a.dQ ? (const char*)(a.dQ + (size_t)nxt * NV * NV) : nullptr,
-                                        do_fwd && a.dG ? (const char*)(a.dG + (size_t)nxt * MI * NV) : nullptr,
-                                        (const char*)(a.A + (size_t)nxt * PE * NV),
-                                        do_fwd && a.dA ? (const char*)(a.dA + (size_t)nxt * PE * NV) : nullptr};
+        load_row8(G, MI, 8 * warp + 2 * t, g, bufA);
+        if (do_fwd) {  // this instance's direction data is consumed a few microseconds from now: pull it into L2
+            const char* bases[3] = {a.dQ ? (const char*)(a.dQ + b * NV * NV) : nullptr, a.dG ? (const char*)(a.dG + b * MI * NV) : nullptr,
+                                    a.dA ? (const char*)(a.dA + b * PE * NV) : nullptr};
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    if (!bases[q]) continue;
-                    const int lines = q < 4 ? 256 : 64;  // 128-byte lines
-                    for (int l = tid; l < lines; l += THREADS)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(bases[q] + (size_t)l * 128));
-                }
+            for (int q = 0; q < 3; ++q) {
+                if (!bases[q]) continue;
+                for (int l = tid; l < (q < 2 ? 256 : 64); l += THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(bases[q] + (size_t)l * 128));
             }
         }
         __syncthreads();
@@ -239,36 +275,32 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         for (int i = tid; i < np; i += THREADS) {
             S.sf[i] = 0.0;
             S.sb[i] = 0.0;
+            S.sf2[i] = 0.0;
+            S.sb2[i] = 0.0;
         }
 #pragma unroll
-        for (int J = 0; J < 8; ++J) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int I = hh ? 7 - warp : warp;
-                if (J <= I) {
-                    const double2 v = qv[8 * hh + J];
-                    double* tp = T + tix(I, J) * 64 + (2 * t) * 8 + g;
-                    tp[0] = v.x;
-                    tp[8] = v.y;
-                    if (J == I) {
-                        if (g == 2 * t) S.ref[8 * I + g] = v.x;
-                        if (g == 2 * t + 1) S.ref[8 * I + g] = v.y;
-                    }
-                }
+        for (int s9 = 0; s9 < 9; ++s9) {
+            const bool first = s9 <= warp;
+            const int I = first ? warp : 7 - warp, J = first ? s9 : s9 - warp - 1;
+            double* tp = T + tix(I, J) * 64 + (2 * t) * 8 + g;
+            tp[0] = qv[s9].x;
+            tp[8] = qv[s9].y;
+            if (J == I) {
+                if (g == 2 * t) S.ref[8 * I + g] = qv[s9].x;
+                if (g == 2 * t + 1) S.ref[8 * I + g] = qv[s9].y;
             }
         }
+        load_row8(G, MI, 8 * (warp + 4) + 2 * t, g, bufB);
+        double hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hv[q] = a.h[b * MI + 8 * (warp + 4 * (q >> 1)) + 2 * t + (q & 1)];
         __syncthreads();
-        if (tid >= nred && tid < np) {  // identity padding (negative block: -1)
-            T[tix(nt - 1, nt - 1) * 64 + (tid & 7) * 9] = -1.0;
-        }
+        if (tid >= nred && tid < np) T[tix(nt - 1, nt - 1) * 64 + (tid & 7) * 9] = -1.0;  // identity padding
         // ---- G: D = G z - h for every row; active rows go to the matrix; warp w owns tile rows w, w+4
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
+            double2(&gv)[8] = hh ? bufB : bufA;
             const int I = warp + 4 * hh, r0 = 8 * I + 2 * t;
-            double2 gv[8];
-#pragma unroll
-            for (int J = 0; J < 8; ++J) gv[J] = ldg2(G + (8 * J + g) * MI + r0);
-            const double h0 = (g == 0) ? a.h[(size_t)inst * MI + r0] : 0.0, h1 = (g == 0) ? a.h[(size_t)inst * MI + r0 + 1] : 0.0;
             double d0 = 0.0, d1 = 0.0;
 #pragma unroll
             for (int J = 0; J < 8; ++J) {
@@ -276,8 +308,6 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                 d0 = fma(gv[J].x, zc, d0);
                 d1 = fma(gv[J].y, zc, d1);
             }
-            d0 = sum_over_g(d0);
-            d1 = sum_over_g(d1);
             const int a0 = S.apos[r0], a1 = S.apos[r0 + 1];
             if (a0 >= 0) {
                 double* tp = T + tix(NTZ + (a0 >> 3), 0) * 64 + (a0 & 7) * 8 + g;
@@ -289,9 +319,13 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
 #pragma unroll
                 for (int J = 0; J < 8; ++J) tp[J * 64] = gv[J].y;
             }
+            // next group in flight: dQ tile rows (forward mode)
+            if (do_fwd) load_row8(a.dQ ? a.dQ + b * NV * NV : nullptr, NV, r0, g, gv);
+            d0 = sum_over_g(d0);
+            d1 = sum_over_g(d1);
             if (g == 0) {
-                d0 -= h0;
-                d1 -= h1;
+                d0 -= hv[2 * hh];
+                d1 -= hv[2 * hh + 1];
                 S.dvec[r0] = d0;
                 S.dvec[r0 + 1] = d1;
                 if (a0 >= 0) T[tix(NTZ + (a0 >> 3), NTZ + (a0 >> 3)) * 64 + (a0 & 7) * 9] = d0 / S.lams[r0];
@@ -301,259 +335,339 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
             }
         }
         // ---- A (16 x 64): warp w owns tile columns 2w, 2w+1
-        {
-            double2 av[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int J = 2 * warp + (q >> 1), Ia = q & 1;
-                av[q] = ldg2(A + (8 * J + g) * PE + 8 * Ia + 2 * t);
+        for (int q = 0; q < 4; ++q) av[q] = ldg2(A + (8 * (2 * warp + (q >> 1)) + g) * PE + 8 * (q & 1) + 2 * t);
+        double vq = 0.0, vh = 0.0, vb = 0.0;  // dq / dh / db entries this thread will need
+        if (do_fwd) {
+            if (tid < NV) {
+                if (a.dq) vq = a.dq[b * NV + tid];
+            } else {
+                if (a.dh) vh = a.dh[b * MI + tid - NV];
+                if (a.db && tid - NV < PE) vb = a.db[b * PE + tid - NV];
             }
+        }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int J = 2 * warp + (q >> 1), Ia = q & 1;
-                const int k0 = NV + ma + 8 * Ia + 2 * t, k1 = k0 + 1;
-                T[tix(k0 >> 3, J) * 64 + (k0 & 7) * 8 + g] = av[q].x;
-                T[tix(k1 >> 3, J) * 64 + (k1 & 7) * 8 + g] = av[q].y;
-            }
+        for (int q = 0; q < 4; ++q) {
+            const int J = 2 * warp + (q >> 1), Ia = q & 1;
+            const int k0 = NV + ma + 8 * Ia + 2 * t, k1 = k0 + 1;
+            T[tix(k0 >> 3, J) * 64 + (k0 & 7) * 8 + g] = av[q].x;
+            T[tix(k1 >> 3, J) * 64 + (k1 & 7) * 8 + g] = av[q].y;
         }
         // ---- forward right-hand side (QuadraticProgram.jl:429-433), symmetric-form scaling
         if (do_fwd) {
-            const size_t b = (size_t)inst;
-            if (a.dQ) {
-                const double* X = a.dQ + b * NV * NV;
+            if (a.dA) {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int r0 = 8 * (warp + 4 * hh) + 2 * t;
-                    double2 v[8];
+                for (int q = 0; q < 4; ++q) av[q] = ldg2(a.dA + b * PE * NV + (8 * (2 * warp + (q >> 1)) + g) * PE + 8 * (q & 1) + 2 * t);
+            } else {
 #pragma unroll
-                    for (int J = 0; J < 8; ++J) v[J] = ldg2(X + (8 * J + g) * NV + r0);
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int J = 0; J < 8; ++J) {
-                        const double zc = S.zs[8 * J + g];
-                        s0 = fma(v[J].x, zc, s0);
-                        s1 = fma(v[J].y, zc, s1);
-                    }
-                    s0 = sum_over_g(s0);
-                    s1 = sum_over_g(s1);
-                    if (g == 0) {
-                        S.rowq[r0] = s0;
-                        S.rowq[r0 + 1] = s1;
-                    }
-                }
+                for (int q = 0; q < 4; ++q) av[q] = make_double2(0.0, 0.0);
             }
-            if (a.dG) {
-                const double* X = a.dG + b * MI * NV;
-                double cs[8];
+            const double* dGp = a.dG ? a.dG + b * MI * NV : nullptr;
+            // dQ z
 #pragma unroll
-                for (int J = 0; J < 8; ++J) cs[J] = 0.0;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int r0 = 8 * (warp + 4 * hh) + 2 * t;
-                    double2 v[8];
-#pragma unroll
-                    for (int J = 0; J < 8; ++J) v[J] = ldg2(X + (8 * J + g) * MI + r0);
-                    const double l0 = S.lams[r0], l1 = S.lams[r0 + 1];
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int J = 0; J < 8; ++J) {
-                        const double zc = S.zs[8 * J + g];
-                        s0 = fma(v[J].x, zc, s0);
-                        s1 = fma(v[J].y, zc, s1);
-                        cs[J] = fma(v[J].x, l0, cs[J]);
-                        cs[J] = fma(v[J].y, l1, cs[J]);
-                    }
-                    s0 = sum_over_g(s0);
-                    s1 = sum_over_g(s1);
-                    if (g == 0) {
-                        S.rowg[r0] = s0;
-                        S.rowg[r0 + 1] = s1;
-                    }
-                }
+            for (int hh = 0; hh < 2; ++hh) {
+                double2(&v)[8] = hh ? bufB : bufA;
+                const int r0 = 8 * (warp + 4 * hh) + 2 * t;
+                double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int J = 0; J < 8; ++J) {
-                    const double c = sum_over_t(cs[J]);
-                    if (t == 0) S.gcol[warp][8 * J + g] = c;
+                    const double zc = S.zs[8 * J + g];
+                    s0 = fma(v[J].x, zc, s0);
+                    s1 = fma(v[J].y, zc, s1);
+                }
+                load_row8(dGp, MI, r0, g, v);
+                s0 = sum_over_g(s0);
+                s1 = sum_over_g(s1);
+                if (g == 0) {
+                    S.rowq[r0] = s0;
+                    S.rowq[r0 + 1] = s1;
                 }
             }
-            if (a.dA) {
-                const double* X = a.dA + b * PE * NV;
-                double2 v[4];
+            // dG z (rows) and dG' lam (columns)
+            double cs[8];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int J = 2 * warp + (q >> 1), Ia = q & 1;
-                    v[q] = ldg2(X + (8 * J + g) * PE + 8 * Ia + 2 * t);
-                }
+            for (int J = 0; J < 8; ++J) cs[J] = 0.0;
 #pragma unroll
-                for (int Ia = 0; Ia < 2; ++Ia) {  // partial row sums over this warp's 16 columns
-                    const double z0 = S.zs[16 * warp + g], z1 = S.zs[16 * warp + 8 + g];
-                    double s0 = fma(v[Ia].x, z0, v[2 + Ia].x * z1), s1 = fma(v[Ia].y, z0, v[2 + Ia].y * z1);
-                    s0 = sum_over_g(s0);
-                    s1 = sum_over_g(s1);
-                    if (g == 0) {
-                        S.arow[warp][8 * Ia + 2 * t] = s0;
-                        S.arow[warp][8 * Ia + 2 * t + 1] = s1;
-                    }
-                }
+            for (int hh = 0; hh < 2; ++hh) {
+                double2(&v)[8] = hh ? bufB : bufA;
+                const int r0 = 8 * (warp + 4 * hh) + 2 * t;
+                const double l0 = S.lams[r0], l1 = S.lams[r0 + 1];
+                double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {  // full column sums of dA .* nu
-                    double c = v[2 * jj].x * S.nus[2 * t] + v[2 * jj].y * S.nus[2 * t + 1] + v[2 * jj + 1].x * S.nus[8 + 2 * t] +
-                               v[2 * jj + 1].y * S.nus[8 + 2 * t + 1];
-                    c = sum_over_t(c);
-                    if (t == 0) S.acol[16 * warp + 8 * jj + g] = c;
+                for (int J = 0; J < 8; ++J) {
+                    const double zc = S.zs[8 * J + g];
+                    s0 = fma(v[J].x, zc, s0);
+                    s1 = fma(v[J].y, zc, s1);
+                    cs[J] = fma(v[J].x, l0, cs[J]);
+                    cs[J] = fma(v[J].y, l1, cs[J]);
                 }
+                s0 = sum_over_g(s0);
+                s1 = sum_over_g(s1);
+                if (g == 0) {
+                    S.rowg[r0] = s0;
+                    S.rowg[r0 + 1] = s1;
+                }
+            }
+#pragma unroll
+            for (int J = 0; J < 8; ++J) {
+                const double c = sum_over_t(cs[J]);
+                if (t == 0) S.gcol[warp][8 * J + g] = c;
+            }
+            // dA z (partial rows over this warp's 16 columns) and dA' nu (full columns)
+#pragma unroll
+            for (int Ia = 0; Ia < 2; ++Ia) {
+                const double z0 = S.zs[16 * warp + g], z1 = S.zs[16 * warp + 8 + g];
+                double s0 = fma(av[Ia].x, z0, av[2 + Ia].x * z1), s1 = fma(av[Ia].y, z0, av[2 + Ia].y * z1);
+                s0 = sum_over_g(s0);
+                s1 = sum_over_g(s1);
+                if (g == 0) {
+                    S.arow[warp][8 * Ia + 2 * t] = s0;
+                    S.arow[warp][8 * Ia + 2 * t + 1] = s1;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                double c = av[2 * jj].x * S.nus[2 * t] + av[2 * jj].y * S.nus[2 * t + 1] + av[2 * jj + 1].x * S.nus[8 + 2 * t] +
+                           av[2 * jj + 1].y * S.nus[8 + 2 * t + 1];
+                c = sum_over_t(c);
+                if (t == 0) S.acol[16 * warp + 8 * jj + g] = c;
             }
         }
         __syncthreads();
         if (tid < NV) {
             double v = 0.0;
-            if (do_fwd) {
-                const size_t b = (size_t)inst;
-                if (a.dQ) v += S.rowq[tid];
-                if (a.dq) v += a.dq[b * NV + tid];
-                if (a.dG) v += (S.gcol[0][tid] + S.gcol[1][tid]) + (S.gcol[2][tid] + S.gcol[3][tid]);
-                if (a.dA) v += S.acol[tid];
-            }
+            if (do_fwd) v = (S.rowq[tid] + vq) + ((S.gcol[0][tid] + S.gcol[1][tid]) + (S.gcol[2][tid] + S.gcol[3][tid])) + S.acol[tid];
             S.yf[tid] = v;
         } else if (do_fwd) {
-            const size_t b = (size_t)inst;
             const int i = tid - NV, ar = S.apos[i];
-            if (ar >= 0) {
-                double v = a.dG ? S.rowg[i] : 0.0;
-                if (a.dh) v -= a.dh[b * MI + i];
-                S.yf[NV + ar] = v;
-            }
-            if (i < PE) {
-                double v = a.dA ? (S.arow[0][i] + S.arow[1][i]) + (S.arow[2][i] + S.arow[3][i]) : 0.0;
-                if (a.db) v -= a.db[b * PE + i];
-                S.yf[NV + ma + i] = v;
-            }
+            if (ar >= 0) S.yf[NV + ar] = S.rowg[i] - vh;
+            if (i < PE) S.yf[NV + ma + i] = ((S.arow[0][i] + S.arow[1][i]) + (S.arow[2][i] + S.arow[3][i])) - vb;
+        }
+        if (warp == 0) {
+            __syncwarp();
+            diag_block(T, &S.ref[0], &S.rd[0], true, false, &S.fail, lane);
         }
         __syncthreads();
         PROF(0);
 
-        // ---- blocked LDL' (block 8), both right-hand sides riding along
+        // ---- blocked LDL' (block 8) with look-ahead, both right-hand sides riding along.
+        // Step j, phase A (all warps): panel W(I,j) = A(I,j) inv(L11)' for I > j and v_j = D^-1 inv(L11) r_j.
+        // Phase B: warp 0 updates tile (j+1,j+1) and factors it (the critical path); warps 1-3 apply the rest of
+        // the trailing update C(I,K) -= W(I,j) D^-1 W(K,j)' row by row (A fragment reused along a tile row,
+        // rows dealt to the warps in snake order) and r_I -= W(I,j) v_j.
         for (int j = 0; j < nt; ++j) {
             const int c0 = j << 3;
-            if (j == NTZ) {  // the Schur complement of the z block is complete: record its diagonal
-                if (tid < np - NV) S.ref[NV + tid] = fabs(T[tix(NTZ + (tid >> 3), NTZ + (tid >> 3)) * 64 + (tid & 7) * 9]);
-                __syncthreads();
-            }
             double* Dt = T + tix(j, j) * 64;
-            if (warp == 0) diag_block(Dt, &S.ref[c0], &S.rd[c0], j < NTZ, &S.fail, lane);
-            __syncthreads();
-            PROF(1);
-            // panel: W(I,j) = A(I,j) inv(L11)'  (DMMA);  v_j = D^-1 inv(L11) r_j
+            if (j == NTZ) {  // the Schur complement of the z block is complete: record its diagonal (tile NTZ did its own)
+                if (tid >= 8 && tid < np - NV) S.ref[NV + tid] = fabs(T[tix(NTZ + (tid >> 3), NTZ + (tid >> 3)) * 64 + (tid & 7) * 9]);
+            }
             {
-                const double2 bf = *reinterpret_cast<const double2*>(&Dt[g * 8 + 2 * t]);
-                for (int I = j + 1 + warp; I < nt; I += NWARP) {
-                    double2* tp = reinterpret_cast<double2*>(T + tix(I, j) * 64 + g * 8 + 2 * t);
-                    const double2 af = *tp;
-                    double2 c = make_double2(0.0, 0.0);
-                    dmma(c.x, c.y, af.x, bf.x);
-                    dmma(c.x, c.y, af.y, bf.y);
-                    *tp = c;
+                const double2 bf = *reinterpret_cast<const double2*>(&Dt[fo]);
+                for (int I0 = j + 1 + warp; I0 < nt; I0 += 3 * NWARP) {
+                    double2 af[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int I = I0 + NWARP * u;
+                        if (I < nt) af[u] = *reinterpret_cast<const double2*>(T + tix(I, j) * 64 + fo);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int I = I0 + NWARP * u;
+                        if (I < nt) {
+                            double2 c = make_double2(0.0, 0.0);
+                            dmma(c.x, c.y, af[u].x, bf.x);
+                            dmma(c.x, c.y, af[u].y, bf.y);
+                            *reinterpret_cast<double2*>(T + tix(I, j) * 64 + fo) = c;
+                        }
+                    }
                 }
                 if (warp == NWARP - 1) {
                     double* y = (lane & 8) ? S.yb : S.yf;
                     const int i = lane & 7;
-                    double u = 0.0;
+                    double u0 = 0.0, u1 = 0.0;
                     if (lane < 16) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) u = fma(Dt[i * 8 + k], y[c0 + k], u);
-                        u *= S.rd[c0 + i];
+                        for (int k = 0; k < 8; k += 2) {
+                            u0 = fma(Dt[i * 8 + k], y[c0 + k], u0);
+                            u1 = fma(Dt[i * 8 + k + 1], y[c0 + k + 1], u1);
+                        }
+                        u0 = (u0 + u1) * S.rd[c0 + i];
                     }
                     __syncwarp();
-                    if (lane < 16) y[c0 + i] = u;
+                    if (lane < 16) y[c0 + i] = u0;
                 }
+            }
+            __syncthreads();
+            PROF(1);
+            if (j < nt - 1) {
+#ifdef QP_PROFILE
+                const long long tb0 = clock64();
+#endif
+                const double nr0 = -S.rd[c0 + 2 * t], nr1 = -S.rd[c0 + 2 * t + 1];
+                if (warp == 0) {
+                    const double2 af = *reinterpret_cast<const double2*>(T + tix(j + 1, j) * 64 + fo);
+                    double* Dn = T + tix(j + 1, j + 1) * 64;
+                    double2 c = *reinterpret_cast<double2*>(Dn + fo);
+                    dmma(c.x, c.y, af.x * nr0, af.x);
+                    dmma(c.x, c.y, af.y * nr1, af.y);
+                    *reinterpret_cast<double2*>(Dn + fo) = c;
+                    __syncwarp();
+                    diag_block(Dn, &S.ref[c0 + 8], &S.rd[c0 + 8], j + 1 < NTZ, j + 1 == NTZ, &S.fail, lane);
+                } else {
+                    for (int rr = c0 + 8 + tid - 32; rr < np; rr += THREADS - 32) {
+                        const double2* wrow = reinterpret_cast<const double2*>(T + tix(rr >> 3, j) * 64 + (rr & 7) * 8);
+                        double uf = S.yf[rr], ub = S.yb[rr], uf2 = 0.0, ub2 = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double2 w2 = wrow[q];
+                            uf = fma(-w2.x, S.yf[c0 + 2 * q], uf);
+                            uf2 = fma(-w2.y, S.yf[c0 + 2 * q + 1], uf2);
+                            ub = fma(-w2.x, S.yb[c0 + 2 * q], ub);
+                            ub2 = fma(-w2.y, S.yb[c0 + 2 * q + 1], ub2);
+                        }
+                        S.yf[rr] = uf + uf2;
+                        S.yb[rr] = ub + ub2;
+                    }
+                    // tile rows I = nt-1 .. j+2 (row j+1 is warp 0's single tile), dealt in snake order
+                    const int nrows = nt - 2 - j, bw = warp - 1;
+                    const double* const b0p = T + tix(j + 1, j) * 64 + fo;
+                    for (int rnd = 0; 3 * rnd < nrows; ++rnd) {
+                        const int idx = 3 * rnd + ((rnd & 1) ? 2 - bw : bw);
+                        if (idx >= nrows) continue;
+                        const int I = nt - 1 - idx;
+                        double2 af = *reinterpret_cast<const double2*>(T + tix(I, j) * 64 + fo);
+                        af.x *= nr0;
+                        af.y *= nr1;
+                        const double* bp = b0p;
+                        double* cp = T + tix(I, j + 1) * 64 + fo;
+                        int K = j + 1;
+                        for (; K < I; K += 2) {
+                            const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                            const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);
+                            bp += (2 * K + 3) * 64;
+                            double2 ca = *reinterpret_cast<double2*>(cp), cb = *reinterpret_cast<double2*>(cp + 64);
+                            dmma(ca.x, ca.y, af.x, b0.x);
+                            dmma(cb.x, cb.y, af.x, b1.x);
+                            dmma(ca.x, ca.y, af.y, b0.y);
+                            dmma(cb.x, cb.y, af.y, b1.y);
+                            *reinterpret_cast<double2*>(cp) = ca;
+                            *reinterpret_cast<double2*>(cp + 64) = cb;
+                            cp += 128;
+                        }
+                        if (K == I) {
+                            const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                            double2 ca = *reinterpret_cast<double2*>(cp);
+                            dmma(ca.x, ca.y, af.x, b0.x);
+                            dmma(ca.x, ca.y, af.y, b0.y);
+                            *reinterpret_cast<double2*>(cp) = ca;
+                        }
+                    }
+                }
+#ifdef QP_PROFILE
+                pc[5] += clock64() - tb0;  // this warp's own phase-B work (before the barrier)
+#endif
             }
             __syncthreads();
             PROF(2);
-            // trailing update C(I,K) -= W(I,j) D^-1 W(K,j)' on the DMMA pipe; right-hand sides r_I -= W(I,j) v_j
-            if (j < nt - 1) {
-                for (int rr = c0 + 8 + tid; rr < np; rr += THREADS) {
-                    const double2* wrow = reinterpret_cast<const double2*>(T + tix(rr >> 3, j) * 64 + (rr & 7) * 8);
-                    double uf = S.yf[rr], ub = S.yb[rr];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const double2 w2 = wrow[q];
-                        uf = fma(-w2.x, S.yf[c0 + 2 * q], uf);
-                        uf = fma(-w2.y, S.yf[c0 + 2 * q + 1], uf);
-                        ub = fma(-w2.x, S.yb[c0 + 2 * q], ub);
-                        ub = fma(-w2.y, S.yb[c0 + 2 * q + 1], ub);
-                    }
-                    S.yf[rr] = uf;
-                    S.yb[rr] = ub;
-                }
-                const double nr0 = -S.rd[c0 + 2 * t], nr1 = -S.rd[c0 + 2 * t + 1];
-                const int Tn = nt - 1 - j, npairs = (Tn * (Tn + 1)) >> 1;
-                int ia = 0, ib = warp;  // pair index -> (ia >= ib) within the trailing triangle
-                while (ib > ia) {
-                    ib -= ia + 1;
-                    ++ia;
-                }
-                for (int q = warp; q < npairs; q += NWARP) {
-                    const int I = j + 1 + ia, K = j + 1 + ib;
-                    double2 af = *reinterpret_cast<const double2*>(T + tix(I, j) * 64 + g * 8 + 2 * t);
-                    const double2 bf = *reinterpret_cast<const double2*>(T + tix(K, j) * 64 + g * 8 + 2 * t);
-                    double2* cp = reinterpret_cast<double2*>(T + tix(I, K) * 64 + g * 8 + 2 * t);
-                    double2 c = *cp;
-                    dmma(c.x, c.y, af.x * nr0, bf.x);
-                    dmma(c.x, c.y, af.y * nr1, bf.y);
-                    *cp = c;
-                    ib += NWARP;
-                    while (ib > ia) {
-                        ib -= ia + 1;
-                        ++ia;
-                    }
-                }
-            }
-            __syncthreads();
-            PROF(3);
         }
 
-        // ---- backward substitution L' x = v: warp 0 the forward-mode system, warp 1 the reverse-mode system
-        if (warp < 2) {
-            double* y = warp ? S.yb : S.yf;
-            double* s = warp ? S.sb : S.sf;
-            for (int j = nt - 1; j >= 0; --j) {
-                const int c0 = j << 3;
-                const double* Dt = T + tix(j, j) * 64;
-                double xk = 0.0;
-                if (lane < 8) {
+        // ---- backward substitution L' x = v.  Right-hand side r (0: forward mode, 1: reverse mode) is owned by the
+        // warp pair (r, r+2): the critical warp r computes x_j = inv(L11)' (v_j - D^-1 (s + s2)_j) and folds
+        // W(j, .)' x_j into s for the 32 columns next to the diagonal; its helper warp r+2 folds the remaining
+        // columns into s2 one step behind.  The pair meets at a named barrier once per step.
+        {
+            const int rhs = warp & 1;
+            double* y = rhs ? S.yb : S.yf;
+            double* s1 = rhs ? S.sb : S.sf;
+            double* s2 = rhs ? S.sb2 : S.sf2;
+            if (warp < 2) {
+                for (int j = nt - 1; j >= 0; --j) {
+                    const int c0 = j << 3;
+                    const double* Dt = T + tix(j, j) * 64;
+                    pair_barrier(rhs);
+                    double tk = 0.0;
+                    if (lane < 8) tk = fma(-S.rd[c0 + lane], s1[c0 + lane] + s2[c0 + lane], y[c0 + lane]);
+                    double xk = 0.0, xk2 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) xk = fma(Dt[k * 8 + lane], fma(-S.rd[c0 + k], s[c0 + k], y[c0 + k]), xk);
+                    for (int k = 0; k < 8; k += 2) {
+                        const double t0 = __shfl_sync(FULL, tk, k), t1 = __shfl_sync(FULL, tk, k + 1);
+                        xk = fma(Dt[k * 8 + (lane & 7)], t0, xk);
+                        xk2 = fma(Dt[(k + 1) * 8 + (lane & 7)], t1, xk2);
+                    }
+                    xk += xk2;  // every lane: x_j[lane & 7]
+                    if (lane < 8) y[c0 + lane] = xk;
+                    double x8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x8[k] = __shfl_sync(FULL, xk, k);
+                    const int c = c0 - 1 - lane;
+                    if (c >= 0) {
+                        const double* wt = T + tix(j, c >> 3) * 64 + (c & 7);
+                        double v = s1[c], v2 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 8; k += 2) {
+                            v = fma(wt[k * 8], x8[k], v);
+                            v2 = fma(wt[(k + 1) * 8], x8[k + 1], v2);
+                        }
+                        s1[c] = v + v2;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (lane < 8) y[c0 + lane] = xk;
-                double x8[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) x8[k] = __shfl_sync(FULL, xk, k);
-                for (int c = lane; c < c0; c += 32) {
-                    const double* wt = T + tix(j, c >> 3) * 64 + (c & 7);
-                    double v = s[c];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v = fma(wt[k * 8], x8[k], v);
-                    s[c] = v;
+            } else {
+                if (warp == 2) {  // own forward-direction data and A into L2 early is done at assembly; here: G for the outputs
+                    if (do_rev)
+                        for (int l = lane; l < 256; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)G + (size_t)l * 128));
                 }
-                __syncwarp();
+                for (int j = nt - 1; j >= 0; --j) {
+                    pair_barrier(rhs);
+                    const int jj = j + 1, c1 = jj << 3;  // x_jj is published
+                    if (jj < nt && c1 > 32) {
+                        double x8[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k += 2) {
+                            const double2 xx = *reinterpret_cast<const double2*>(&y[c1 + k]);
+                            x8[k] = xx.x;
+                            x8[k + 1] = xx.y;
+                        }
+                        for (int c = c1 - 33 - lane; c >= 0; c -= 32) {
+                            const double* wt = T + tix(jj, c >> 3) * 64 + (c & 7);
+                            double v = s2[c], v2 = 0.0;
+#pragma unroll
+                            for (int k = 0; k < 8; k += 2) {
+                                v = fma(wt[k * 8], x8[k], v);
+                                v2 = fma(wt[(k + 1) * 8], x8[k + 1], v2);
+                            }
+                            s2[c] = v + v2;
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
-        PROF(4);
+        PROF(3);
         // ---- outputs (dz, dlam, dnu) = -x; inactive inequalities recovered from their singleton columns
         const bool failed = S.fail != 0;
+        {   // pull the next instance's Q (lower-triangle lines) and G towards L2 while this one is written out
+            const int64_t nxt = inst + gridDim.x;
+            if (nxt < a.B) {
+                const char* qn = (const char*)(a.Q + (size_t)nxt * NV * NV);
+                const char* gn = (const char*)(a.G + (size_t)nxt * MI * NV);
+                for (int l = tid; l < 256; l += THREADS) {
+                    if (16 * (l & 3) + 15 >= ((l >> 2) & ~7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(qn + (size_t)l * 128));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)l * 128));
+                }
+            }
+        }
         if (!failed) {
-            double* rev = do_rev ? a.rev + (size_t)inst * N : nullptr;
-            double* fwd = do_fwd ? a.fwd + (size_t)inst * N : nullptr;
+            double* rev = do_rev ? a.rev + b * N : nullptr;
+            double* fwd = do_fwd ? a.fwd + b * N : nullptr;
             if (do_rev) {
-                // inactive rows: out_lam_i = (G_i . x_z) / D_i   (G re-read: L2 resident)
+                // inactive rows: out_lam_i = (G_i . x_z) / D_i ; active rows: -w_i / lam_i.  Warp w: tile rows w, w+4
+                load_row8(G, MI, 8 * warp + 2 * t, g, bufA);
+                load_row8(G, MI, 8 * (warp + 4) + 2 * t, g, bufB);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    const int I = warp + 4 * hh, r0 = 8 * I + 2 * t;
-                    double2 gv[8];
-#pragma unroll
-                    for (int J = 0; J < 8; ++J) gv[J] = ldg2(G + (8 * J + g) * MI + r0);
+                    double2(&gv)[8] = hh ? bufB : bufA;
+                    const int r0 = 8 * (warp + 4 * hh) + 2 * t;
                     double d0 = 0.0, d1 = 0.0;
 #pragma unroll
                     for (int J = 0; J < 8; ++J) {
@@ -565,32 +679,38 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                     d1 = sum_over_g(d1);
                     if (g == 0) {
                         const int a0 = S.apos[r0], a1 = S.apos[r0 + 1];
-                        rev[NV + r0] = a0 >= 0 ? -S.yb[NV + a0] / S.lams[r0] : d0 / S.dvec[r0];
-                        rev[NV + r0 + 1] = a1 >= 0 ? -S.yb[NV + a1] / S.lams[r0 + 1] : d1 / S.dvec[r0 + 1];
+                        const double o0 = a0 >= 0 ? -S.yb[NV + a0] * fast_rcp(S.lams[r0]) : d0 * fast_rcp(S.dvec[r0]);
+                        const double o1 = a1 >= 0 ? -S.yb[NV + a1] * fast_rcp(S.lams[r0 + 1]) : d1 * fast_rcp(S.dvec[r0 + 1]);
+                        *reinterpret_cast<double2*>(rev + NV + r0) = make_double2(o0, o1);
                     }
                 }
-                if (tid < NV) rev[tid] = -S.yb[tid];
-                else if (tid < NV + PE) rev[NV + MI + tid - NV] = -S.yb[NV + ma + tid - NV];
             }
-            if (do_fwd) {
-                if (tid < NV) {
+            if (warp >= 2) {
+                const int u = tid - 64;
+                if (do_rev) {
+                    rev[u] = -S.yb[u];
+                    if (u < PE) rev[NV + MI + u] = -S.yb[NV + ma + u];
+                }
+            } else {
+                if (do_fwd) {
                     fwd[tid] = -S.yf[tid];
                     const int ar = S.apos[tid];
                     fwd[NV + tid] = ar >= 0 ? -S.yf[NV + ar] : 0.0;
-                } else if (tid < NV + PE) {
-                    fwd[NV + MI + tid - NV] = -S.yf[NV + ma + tid - NV];
+                    if (tid < PE) fwd[NV + MI + tid] = -S.yf[NV + ma + tid];
                 }
+                if (a.info && tid == 0) a.info[inst] = 0;
             }
-            if (a.info && tid == 0) a.info[inst] = 0;
         } else if (tid == 0) {
             fb_list[atomicAdd(fb_count, 1)] = (int)inst;
         }
         __syncthreads();
-        PROF(5);
+        PROF(4);
     }
 #ifdef QP_PROFILE
     if (a.prof && blockIdx.x == 0 && tid == 0)
-        for (int i = 0; i < 8; ++i) a.prof[i] = pc[i];
+        for (int i = 0; i < 6; ++i) a.prof[i] = pc[i];
+    if (a.prof && blockIdx.x == 0 && tid == 32) a.prof[6] = pc[5];
+    if (a.prof && blockIdx.x == 0 && tid == 96) a.prof[7] = pc[5];
 #endif
 }
 
@@ -602,6 +722,20 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
     *handled = false;
     const size_t smem = sizeof(Hdr) + (size_t)(nt_cap * (nt_cap + 1) / 2) * 64 * sizeof(double);
     if (smem > ctx->smem_optin) return 0;
+    static bool pair_table_ready[64] = {};
+    if (!pair_table_ready[ctx->device & 63]) {
+        unsigned char pa[160], pb[160];
+        int q = 0;
+        for (int ia = 0; q < 160; ++ia)
+            for (int ib = 0; ib <= ia && q < 160; ++ib, ++q) {
+                pa[q] = (unsigned char)ia;
+                pb[q] = (unsigned char)ib;
+            }
+        DO_CUDA(ctx, cudaMemcpyToSymbolAsync(PAIR_A, pa, sizeof pa, 0, cudaMemcpyHostToDevice, ctx->stream));
+        DO_CUDA(ctx, cudaMemcpyToSymbolAsync(PAIR_B, pb, sizeof pb, 0, cudaMemcpyHostToDevice, ctx->stream));
+        DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pair_table_ready[ctx->device & 63] = true;
+    }
     DO_CUDA(ctx, ctx->qp_fb.reserve(sizeof(int) * ((size_t)a.B + 1)));
     int* fb_count = ctx->qp_fb.as<int>();
     int* fb_list = fb_count + 1;
@@ -610,6 +744,7 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
     int per_sm = 1;
     DO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_kkt_sqd_kernel, THREADS, smem));
     if (per_sm < 1) per_sm = 1;
+    if (const char* cap = getenv("DIFFOPT_B200_SQD_PER_SM")) per_sm = atoi(cap) < per_sm && atoi(cap) > 0 ? atoi(cap) : per_sm;
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > a.B) grid = a.B;
     QpSolveArgs aa = a;
@@ -633,9 +768,9 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
         long long ninst = (a.B + grid - 1) / grid;
         fprintf(stderr,
                 "[qp_sqd profile, CTA 0, %lld instances, %d CTA/SM, nt_cap %d, smem %zu, %d to LU] clocks/instance: "
-                "assemble %lld diag %lld panel %lld update %lld backward %lld output %lld\n",
-                ninst, per_sm, nt_cap, smem, nfb, h[0] / ninst, h[1] / ninst, h[2] / ninst, h[3] / ninst, h[4] / ninst,
-                h[5] / ninst);
+                "assemble+diag0 %lld panel %lld update+diag %lld (own work: warp0 %lld warp1 %lld warp3 %lld) backward %lld output %lld\n",
+                ninst, per_sm, nt_cap, smem, nfb, h[0] / ninst, h[1] / ninst, h[2] / ninst, h[5] / ninst, h[6] / ninst,
+                h[7] / ninst, h[3] / ninst, h[4] / ninst);
     }
     *handled = true;
     return qp_lu_launch_list(ctx, a, nt_cap, fb_list, fb_count);
