@@ -31,6 +31,10 @@
 
 int32_t qp_lu_launch_list(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, const int* list, const int* count);
 
+#ifndef QP_ABLATE
+#define QP_ABLATE 0
+#endif
+
 namespace {
 
 constexpr int NV = 64, MI = 64, PE = 16, N = NV + MI + PE, NTZ = NV / 8;
@@ -73,10 +77,10 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(r, t, r);
 }
 
-// named barrier of the warp pair that owns right-hand side r (ids 1, 2; id 0 is __syncthreads)
+// named barrier of the warp pair that owns right-hand side r (ids 4, 5)
 __device__ __forceinline__ void pair_barrier(const int r) {
-    if (r) asm volatile("bar.sync 2, 64;" ::: "memory");
-    else asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (r) asm volatile("bar.sync 5, 64;" ::: "memory");
+    else asm volatile("bar.sync 4, 64;" ::: "memory");
 }
 
 __device__ __forceinline__ double sum_over_g(double v) {  // lanes sharing t = lane & 3
@@ -105,92 +109,104 @@ __device__ __forceinline__ void load_row8(const double* M, const int ld, const i
     }
 }
 
-// LDL' of the 8 x 8 diagonal block by one warp: lane 0 eliminates in registers (products formed ahead of the
-// reciprocal so that one FMA follows it on the pivot chain), then lanes 0..7 each build one column of inv(L11)
-// (unit lower).  On exit the tile holds inv(L11) (zeros above the diagonal), rd[] = 1/d.  selfref: the pivot
-// test refers to the block's own starting diagonal (first block of the Schur complement).
-__device__ __noinline__ void diag_block(double* D, double* ref, double* rd, const bool positive, const bool selfref,
-                                           int* fail, const int lane) {
-    if (lane == 0) {
-        double a[8][8];
+// LDL' of the 8 x 8 diagonal block by ONE thread, in registers.  The pivot chain is software pipelined: the next
+// pivot (one FMA behind r) and its reciprocal are started before the bulk of the rank-1 update is issued.
+// On exit the strict lower triangle of the tile holds the unit-lower factor L11, rd[] = 1/d.  Pivots are
+// checked after the chain (expected sign, |d_k| > PIV_RTOL x reference; NaN fails).  selfref: the reference is
+// the block's own starting diagonal (first block of the Schur complement), recorded into ref[].
+__device__ __noinline__ void elim8(double* D, double* ref, double* rd, const bool positive, const bool selfref, int* fail) {
+    double a[8][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 8; ++i) {
 #pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-                if (c <= i) {
-                    const double2 v = *reinterpret_cast<const double2*>(&D[i * 8 + c]);
-                    a[i][c] = v.x;
-                    a[i][c + 1] = v.y;
-                }
+        for (int c = 0; c < 8; c += 2) {
+            if (c <= i) {
+                const double2 v = *reinterpret_cast<const double2*>(&D[i * 8 + c]);
+                a[i][c] = v.x;
+                a[i][c + 1] = v.y;
             }
         }
-        double thr[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const double rf = selfref ? fabs(a[k][k]) : ref[k];
-            if (selfref) ref[k] = rf;
-            thr[k] = PIV_RTOL * rf;
-        }
-        bool bad = false;
-        // Software pipelined: the next pivot (one FMA behind r) and its reciprocal are started BEFORE the bulk of
-        // this step's rank-1 update is issued, so the update fills the reciprocal's latency.
-        double d = a[0][0];
-        if (!((positive ? d : -d) > thr[0])) {
-            bad = true;
-            d = positive ? 1.0 : -1.0;
-        }
-        double r = fast_rcp(d);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            rd[k] = r;
-            double rn = 0.0;
-            if (k < 7) {
-                double dn = fma(-(a[k + 1][k] * a[k + 1][k]), r, a[k + 1][k + 1]);
-                if (!((positive ? dn : -dn) > thr[k + 1])) {
-                    bad = true;
-                    dn = positive ? 1.0 : -1.0;
-                }
-                rn = fast_rcp(dn);
-            }
-            double lk[8];
-#pragma unroll
-            for (int i = k + 1; i < 8; ++i) lk[i] = a[i][k] * r;
-#pragma unroll
-            for (int i = k + 2; i < 8; ++i) a[i][k + 1] = fma(-lk[i], a[k + 1][k], a[i][k + 1]);
-#pragma unroll
-            for (int c = k + 2; c < 8; ++c) {
-#pragma unroll
-                for (int i = c; i < 8; ++i) a[i][c] = fma(-lk[i], a[c][k], a[i][c]);
-            }
-#pragma unroll
-            for (int i = k + 1; i < 8; ++i) D[i * 8 + k] = lk[i];
-            r = rn;
-        }
-        if (bad) *fail = 1;
     }
-    __syncwarp();
-    double x[8];
-    if (lane < 8) {
-        double l[8][8];
+    double thr[8];
 #pragma unroll
-        for (int i = 1; i < 8; ++i)
+    for (int k = 0; k < 8; ++k) {
+        const double rf = selfref ? fabs(a[k][k]) : ref[k];
+        if (selfref) ref[k] = rf;
+        thr[k] = PIV_RTOL * rf;
+    }
+    double r = fast_rcp(a[0][0]);
 #pragma unroll
-            for (int c = 0; c < i; ++c) l[i][c] = D[i * 8 + c];
-        // column `lane` of inv(L11): unit-lower solve in axpy form (one FMA per step on the chain)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-#pragma unroll
-            for (int i = k + 1; i < 8; ++i) x[i] = fma(-l[i][k], x[k], x[i]);
+    for (int k = 0; k < 8; ++k) {
+        rd[k] = r;
+        double rn = 0.0;
+        if (k < 7) {
+            const double dn = fma(-(a[k + 1][k] * a[k + 1][k]), r, a[k + 1][k + 1]);
+            a[k + 1][k + 1] = dn;
+            rn = fast_rcp(dn);
         }
-    }
-    __syncwarp();
-    if (lane < 8) {
+        double lk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) D[i * 8 + lane] = x[i];
+        for (int i = k + 1; i < 8; ++i) lk[i] = a[i][k] * r;
+#pragma unroll
+        for (int i = k + 2; i < 8; ++i) a[i][k + 1] = fma(-lk[i], a[k + 1][k], a[i][k + 1]);
+#pragma unroll
+        for (int c = k + 2; c < 8; ++c) {
+#pragma unroll
+            for (int i = c; i < 8; ++i) a[i][c] = fma(-lk[i], a[c][k], a[i][c]);
+        }
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i) D[i * 8 + k] = lk[i];
+        r = rn;
     }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ok = ok && ((positive ? a[k][k] : -a[k][k]) > thr[k]);
+    if (!ok) *fail = 1;
 }
+
+// One row w (8 doubles at p) of a panel tile: w <- w L11^-T, i.e. solve x L11' = w with the unit-lower L11 stored
+// in the strict lower triangle of tile Ld (axpy form: one FMA per step on the dependency chain).
+// scale != nullptr: the result is also multiplied by scale[0..7] (right-hand side rows: v = D^-1 L^-1 r).
+__device__ __forceinline__ void panel_row(double* p, const double* Ld, const double* scale) {
+    double w[8];
+    {
+        const double2* pp = reinterpret_cast<const double2*>(p);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double2 v = pp[q];
+            w[2 * q] = v.x;
+            w[2 * q + 1] = v.y;
+        }
+    }
+#pragma unroll
+    for (int c = 1; c < 8; ++c) {  // row c of L11: entries 0..c-1
+        double l[8];
+#pragma unroll
+        for (int k = 0; k < c; k += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(&Ld[c * 8 + k]);
+            l[k] = v.x;
+            l[k + 1] = v.y;
+        }
+        double acc = w[c], acc2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < c; ++k) {
+            if (k & 1) acc2 = fma(-w[k], l[k], acc2);
+            else acc = fma(-w[k], l[k], acc);
+        }
+        w[c] = acc + acc2;
+    }
+    if (scale) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[c] *= scale[c];
+    }
+    double2* pp = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pp[q] = make_double2(w[2 * q], w[2 * q + 1]);
+}
+
+// named barriers (id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(const int id, const int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, int* fb_list, int* fb_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -203,6 +219,8 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
     const bool do_fwd = a.fwd != nullptr, do_rev = a.rev != nullptr;
 #ifdef QP_PROFILE
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long sub[6] = {0, 0, 0, 0, 0, 0};
+    long long tsub = 0;
     long long tprev = clock64();
 #define PROF(i)                  \
     do {                         \
@@ -210,8 +228,17 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         pc[i] += _n - tprev;     \
         tprev = _n;              \
     } while (0)
+#define SUB0() tsub = clock64()
+#define SUB(i)                   \
+    do {                         \
+        long long _n = clock64(); \
+        sub[i] += _n - tsub;     \
+        tsub = _n;               \
+    } while (0)
 #else
 #define PROF(i)
+#define SUB0()
+#define SUB(i)
 #endif
 
     for (int64_t inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
@@ -443,136 +470,146 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
             if (ar >= 0) S.yf[NV + ar] = S.rowg[i] - vh;
             if (i < PE) S.yf[NV + ma + i] = ((S.arow[0][i] + S.arow[1][i]) + (S.arow[2][i] + S.arow[3][i])) - vb;
         }
-        if (warp == 0) {
-            __syncwarp();
-            diag_block(T, &S.ref[0], &S.rd[0], true, false, &S.fail, lane);
-        }
         __syncthreads();
         PROF(0);
 
-        // ---- blocked LDL' (block 8) with look-ahead, both right-hand sides riding along.
-        // Step j, phase A (all warps): panel W(I,j) = A(I,j) inv(L11)' for I > j and v_j = D^-1 inv(L11) r_j.
-        // Phase B: warp 0 updates tile (j+1,j+1) and factors it (the critical path); warps 1-3 apply the rest of
-        // the trailing update C(I,K) -= W(I,j) D^-1 W(K,j)' row by row (A fragment reused along a tile row,
-        // rows dealt to the warps in snake order) and r_I -= W(I,j) v_j.
-        for (int j = 0; j < nt; ++j) {
-            const int c0 = j << 3;
-            double* Dt = T + tix(j, j) * 64;
-            if (j == NTZ) {  // the Schur complement of the z block is complete: record its diagonal (tile NTZ did its own)
-                if (tid >= 8 && tid < np - NV) S.ref[NV + tid] = fabs(T[tix(NTZ + (tid >> 3), NTZ + (tid >> 3)) * 64 + (tid & 7) * 9]);
-            }
-            {
-                const double2 bf = *reinterpret_cast<const double2*>(&Dt[fo]);
-                for (int I0 = j + 1 + warp; I0 < nt; I0 += 3 * NWARP) {
-                    double2 af[3];
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const int I = I0 + NWARP * u;
-                        if (I < nt) af[u] = *reinterpret_cast<const double2*>(T + tix(I, j) * 64 + fo);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const int I = I0 + NWARP * u;
-                        if (I < nt) {
-                            double2 c = make_double2(0.0, 0.0);
-                            dmma(c.x, c.y, af[u].x, bf.x);
-                            dmma(c.x, c.y, af[u].y, bf.y);
-                            *reinterpret_cast<double2*>(T + tix(I, j) * 64 + fo) = c;
-                        }
-                    }
-                }
-                if (warp == NWARP - 1) {
-                    double* y = (lane & 8) ? S.yb : S.yf;
-                    const int i = lane & 7;
-                    double u0 = 0.0, u1 = 0.0;
-                    if (lane < 16) {
-#pragma unroll
-                        for (int k = 0; k < 8; k += 2) {
-                            u0 = fma(Dt[i * 8 + k], y[c0 + k], u0);
-                            u1 = fma(Dt[i * 8 + k + 1], y[c0 + k + 1], u1);
-                        }
-                        u0 = (u0 + u1) * S.rd[c0 + i];
-                    }
-                    __syncwarp();
-                    if (lane < 16) y[c0 + i] = u0;
-                }
-            }
-            __syncthreads();
-            PROF(1);
-            if (j < nt - 1) {
-#ifdef QP_PROFILE
-                const long long tb0 = clock64();
+        // ---- blocked LDL' (block 8), both right-hand sides riding along as two extra panel rows.
+        // Warp 0 runs the critical path on its own: eliminate the diagonal block j (one thread, registers), form
+        // W(j+1,j), apply it to tile (j+1,j+1), eliminate that ... and only exchanges named-barrier arrivals with
+        // the bulk warps 1-3, which per step j solve the remaining panel rows W(I,j) = A(I,j) L11^-T (one thread
+        // per row, FMA pipe) and apply the trailing update C(I,K) -= W(I,j) D^-1 W(K,j)' on the DMMA pipe
+        // (A fragment reused along a tile row, rows dealt to the warps in snake order).
+        //   BAR_E: warp 0 arrives when L_jj, 1/d_j and W(j+1,j) are in place -> bulk warps may run step j
+        //   BAR_F: bulk warps arrive when step j is applied               -> warp 0 may touch tiles (j+1, .)
+        //   BAR_B: bulk-internal, between the panel rows and the trailing update
+        constexpr int BAR_E = 1, BAR_F = 2, BAR_B = 3;
+        if (warp == 0) {
+            if (lane == 0) elim8(T, &S.ref[0], &S.rd[0], true, false, &S.fail);
+            __syncwarp();
+            for (int j = 0; j < nt; ++j) {
+                const int c0 = j << 3;
+                SUB0();
+                if (j > 0) bar_sync(BAR_F, THREADS);
+                SUB(0);
+                if (j < nt - 1) {
+                    double* Wt = T + tix(j + 1, j) * 64;
+#if QP_ABLATE != 1
+                    if (lane < 8) panel_row(Wt + lane * 8, T + tix(j, j) * 64, nullptr);
 #endif
-                const double nr0 = -S.rd[c0 + 2 * t], nr1 = -S.rd[c0 + 2 * t + 1];
-                if (warp == 0) {
-                    const double2 af = *reinterpret_cast<const double2*>(T + tix(j + 1, j) * 64 + fo);
+                    __syncwarp();
+                }
+                SUB(4);
+                __threadfence_block();
+                SUB(5);
+                bar_arrive(BAR_E, THREADS);
+                SUB(1);
+                if (j < nt - 1) {
+                    const double2 wf = *reinterpret_cast<const double2*>(T + tix(j + 1, j) * 64 + fo);
                     double* Dn = T + tix(j + 1, j + 1) * 64;
                     double2 c = *reinterpret_cast<double2*>(Dn + fo);
-                    dmma(c.x, c.y, af.x * nr0, af.x);
-                    dmma(c.x, c.y, af.y * nr1, af.y);
+                    dmma(c.x, c.y, wf.x * -S.rd[c0 + 2 * t], wf.x);
+                    dmma(c.x, c.y, wf.y * -S.rd[c0 + 2 * t + 1], wf.y);
                     *reinterpret_cast<double2*>(Dn + fo) = c;
                     __syncwarp();
-                    diag_block(Dn, &S.ref[c0 + 8], &S.rd[c0 + 8], j + 1 < NTZ, j + 1 == NTZ, &S.fail, lane);
-                } else {
-                    for (int rr = c0 + 8 + tid - 32; rr < np; rr += THREADS - 32) {
-                        const double2* wrow = reinterpret_cast<const double2*>(T + tix(rr >> 3, j) * 64 + (rr & 7) * 8);
-                        double uf = S.yf[rr], ub = S.yb[rr], uf2 = 0.0, ub2 = 0.0;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const double2 w2 = wrow[q];
-                            uf = fma(-w2.x, S.yf[c0 + 2 * q], uf);
-                            uf2 = fma(-w2.y, S.yf[c0 + 2 * q + 1], uf2);
-                            ub = fma(-w2.x, S.yb[c0 + 2 * q], ub);
-                            ub2 = fma(-w2.y, S.yb[c0 + 2 * q + 1], ub2);
-                        }
-                        S.yf[rr] = uf + uf2;
-                        S.yb[rr] = ub + ub2;
+                    SUB(2);
+#if QP_ABLATE != 2
+                    if (lane == 0) elim8(Dn, &S.ref[c0 + 8], &S.rd[c0 + 8], j + 1 < NTZ, j + 1 == NTZ, &S.fail);
+#endif
+                    __syncwarp();
+                    SUB(3);
+                }
+            }
+        } else {
+            const int bt = tid - 32, bw = warp - 1;  // bulk thread / warp index
+            for (int j = 0; j < nt; ++j) {
+                const int c0 = j << 3;
+                SUB0();
+                bar_sync(BAR_E, THREADS);
+                SUB(0);
+                const double* Ld = T + tix(j, j) * 64;
+                {   // panel rows 8(j+2) .. np-1 and the two right-hand sides (threads 94, 95)
+#if QP_ABLATE != 3
+                    if (bt < 94) {
+                        for (int rr = c0 + 16 + bt; rr < np; rr += 94) panel_row(T + tix(rr >> 3, j) * 64 + (rr & 7) * 8, Ld, nullptr);
+                    } else {
+                        panel_row((bt == 94 ? S.yf : S.yb) + c0, Ld, &S.rd[c0]);
                     }
-                    // tile rows I = nt-1 .. j+2 (row j+1 is warp 0's single tile), dealt in snake order
-                    const int nrows = nt - 2 - j, bw = warp - 1;
-                    const double* const b0p = T + tix(j + 1, j) * 64 + fo;
-                    for (int rnd = 0; 3 * rnd < nrows; ++rnd) {
-                        const int idx = 3 * rnd + ((rnd & 1) ? 2 - bw : bw);
-                        if (idx >= nrows) continue;
-                        const int I = nt - 1 - idx;
-                        double2 af = *reinterpret_cast<const double2*>(T + tix(I, j) * 64 + fo);
-                        af.x *= nr0;
-                        af.y *= nr1;
-                        const double* bp = b0p;
-                        double* cp = T + tix(I, j + 1) * 64 + fo;
-                        int K = j + 1;
-                        for (; K < I; K += 2) {
-                            const double2 b0 = *reinterpret_cast<const double2*>(bp);
-                            const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);
-                            bp += (2 * K + 3) * 64;
-                            double2 ca = *reinterpret_cast<double2*>(cp), cb = *reinterpret_cast<double2*>(cp + 64);
-                            dmma(ca.x, ca.y, af.x, b0.x);
-                            dmma(cb.x, cb.y, af.x, b1.x);
-                            dmma(ca.x, ca.y, af.y, b0.y);
-                            dmma(cb.x, cb.y, af.y, b1.y);
-                            *reinterpret_cast<double2*>(cp) = ca;
-                            *reinterpret_cast<double2*>(cp + 64) = cb;
-                            cp += 128;
-                        }
-                        if (K == I) {
-                            const double2 b0 = *reinterpret_cast<const double2*>(bp);
-                            double2 ca = *reinterpret_cast<double2*>(cp);
-                            dmma(ca.x, ca.y, af.x, b0.x);
-                            dmma(ca.x, ca.y, af.y, b0.y);
-                            *reinterpret_cast<double2*>(cp) = ca;
-                        }
+#endif
+                }
+                if (j == nt - 1) break;
+                SUB(1);
+                bar_sync(BAR_B, THREADS - 32);
+                SUB(2);
+                const double nr0 = -S.rd[c0 + 2 * t], nr1 = -S.rd[c0 + 2 * t + 1];
+                for (int rr = c0 + 8 + bt; rr < np; rr += THREADS - 32) {
+                    const double2* wrow = reinterpret_cast<const double2*>(T + tix(rr >> 3, j) * 64 + (rr & 7) * 8);
+                    double uf = S.yf[rr], ub = S.yb[rr], uf2 = 0.0, ub2 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double2 w2 = wrow[q];
+                        const double2 vf = *reinterpret_cast<const double2*>(&S.yf[c0 + 2 * q]);
+                        const double2 vb2 = *reinterpret_cast<const double2*>(&S.yb[c0 + 2 * q]);
+                        uf = fma(-w2.x, vf.x, uf);
+                        uf2 = fma(-w2.y, vf.y, uf2);
+                        ub = fma(-w2.x, vb2.x, ub);
+                        ub2 = fma(-w2.y, vb2.y, ub2);
+                    }
+                    S.yf[rr] = uf + uf2;
+                    S.yb[rr] = ub + ub2;
+                }
+                SUB(3);
+                // tile rows I = nt-1 .. j+2 (row j+1 is warp 0's single tile), dealt in snake order
+                const int nrows = nt - 2 - j;
+                const double* const b0p = T + tix(j + 1, j) * 64 + fo;
+                for (int rnd = 0; 3 * rnd < nrows; ++rnd) {
+                    const int idx = 3 * rnd + ((rnd & 1) ? 2 - bw : bw);
+#if QP_ABLATE == 4
+                    continue;
+#endif
+                    if (idx >= nrows) continue;
+                    const int I = nt - 1 - idx;
+                    double2 af = *reinterpret_cast<const double2*>(T + tix(I, j) * 64 + fo);
+                    af.x *= nr0;
+                    af.y *= nr1;
+                    const double* bp = b0p;
+                    double* cp = T + tix(I, j + 1) * 64 + fo;
+                    int K = j + 1;
+                    for (; K < I; K += 2) {
+                        const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                        const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);
+                        bp += (2 * K + 3) * 64;
+                        double2 ca = *reinterpret_cast<double2*>(cp), cb = *reinterpret_cast<double2*>(cp + 64);
+                        dmma(ca.x, ca.y, af.x, b0.x);
+                        dmma(cb.x, cb.y, af.x, b1.x);
+                        dmma(ca.x, ca.y, af.y, b0.y);
+                        dmma(cb.x, cb.y, af.y, b1.y);
+                        *reinterpret_cast<double2*>(cp) = ca;
+                        *reinterpret_cast<double2*>(cp + 64) = cb;
+                        cp += 128;
+                    }
+                    if (K == I) {
+                        const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                        double2 ca = *reinterpret_cast<double2*>(cp);
+                        dmma(ca.x, ca.y, af.x, b0.x);
+                        dmma(ca.x, ca.y, af.y, b0.y);
+                        *reinterpret_cast<double2*>(cp) = ca;
+                    }
+                    if (j == NTZ - 1) {  // Schur complement of the z block complete: record the diagonal of tile (I,I)
+                        const double2 dg = *reinterpret_cast<const double2*>(T + tix(I, I) * 64 + fo);
+                        if (g == 2 * t) S.ref[8 * I + g] = fabs(dg.x);
+                        if (g == 2 * t + 1) S.ref[8 * I + g] = fabs(dg.y);
                     }
                 }
-#ifdef QP_PROFILE
-                pc[5] += clock64() - tb0;  // this warp's own phase-B work (before the barrier)
-#endif
+                __threadfence_block();
+                bar_arrive(BAR_F, THREADS);
+                SUB(4);
             }
-            __syncthreads();
-            PROF(2);
         }
+        __syncthreads();
+        PROF(1);
 
         // ---- backward substitution L' x = v.  Right-hand side r (0: forward mode, 1: reverse mode) is owned by the
-        // warp pair (r, r+2): the critical warp r computes x_j = inv(L11)' (v_j - D^-1 (s + s2)_j) and folds
+        // warp pair (r, r+2): the critical warp r computes x_j = L11^-T (v_j - D^-1 (s + s2)_j) and folds
         // W(j, .)' x_j into s for the 32 columns next to the diagonal; its helper warp r+2 folds the remaining
         // columns into s2 one step behind.  The pair meets at a named barrier once per step.
         {
@@ -585,20 +622,30 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                     const int c0 = j << 3;
                     const double* Dt = T + tix(j, j) * 64;
                     pair_barrier(rhs);
-                    double tk = 0.0;
-                    if (lane < 8) tk = fma(-S.rd[c0 + lane], s1[c0 + lane] + s2[c0 + lane], y[c0 + lane]);
-                    double xk = 0.0, xk2 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 8; k += 2) {
-                        const double t0 = __shfl_sync(FULL, tk, k), t1 = __shfl_sync(FULL, tk, k + 1);
-                        xk = fma(Dt[k * 8 + (lane & 7)], t0, xk);
-                        xk2 = fma(Dt[(k + 1) * 8 + (lane & 7)], t1, xk2);
-                    }
-                    xk += xk2;  // every lane: x_j[lane & 7]
-                    if (lane < 8) y[c0 + lane] = xk;
+                    // every lane redundantly: x_j = L11^-T (v_j - D^-1 (s + s2)_j), unit-lower L11 in the diagonal tile
                     double x8[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) x8[k] = __shfl_sync(FULL, xk, k);
+                    for (int k = 0; k < 8; k += 2) {
+                        const double2 yy = *reinterpret_cast<const double2*>(&y[c0 + k]);
+                        const double2 sa = *reinterpret_cast<const double2*>(&s1[c0 + k]);
+                        const double2 sc = *reinterpret_cast<const double2*>(&s2[c0 + k]);
+                        const double2 rr = *reinterpret_cast<const double2*>(&S.rd[c0 + k]);
+                        x8[k] = fma(-rr.x, sa.x + sc.x, yy.x);
+                        x8[k + 1] = fma(-rr.y, sa.y + sc.y, yy.y);
+                    }
+#pragma unroll
+                    for (int k = 7; k >= 1; --k) {
+#pragma unroll
+                        for (int c = 0; c < k; c += 2) {
+                            const double2 l2 = *reinterpret_cast<const double2*>(&Dt[k * 8 + c]);
+                            x8[c] = fma(-l2.x, x8[k], x8[c]);
+                            if (c + 1 < k) x8[c + 1] = fma(-l2.y, x8[k], x8[c + 1]);
+                        }
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(&y[c0 + k]) = make_double2(x8[k], x8[k + 1]);
+                    }
                     const int c = c0 - 1 - lane;
                     if (c >= 0) {
                         const double* wt = T + tix(j, c >> 3) * 64 + (c & 7);
@@ -707,10 +754,14 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         PROF(4);
     }
 #ifdef QP_PROFILE
-    if (a.prof && blockIdx.x == 0 && tid == 0)
+    if (a.prof && blockIdx.x == 0 && tid == 0) {
         for (int i = 0; i < 6; ++i) a.prof[i] = pc[i];
-    if (a.prof && blockIdx.x == 0 && tid == 32) a.prof[6] = pc[5];
-    if (a.prof && blockIdx.x == 0 && tid == 96) a.prof[7] = pc[5];
+        for (int i = 0; i < 4; ++i) a.prof[8 + i] = sub[i];
+        a.prof[17] = sub[4];
+        a.prof[18] = sub[5];
+    }
+    if (a.prof && blockIdx.x == 0 && tid == 32)
+        for (int i = 0; i < 5; ++i) a.prof[12 + i] = sub[i];
 #endif
 }
 
@@ -751,15 +802,15 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
     const bool profile = getenv("DIFFOPT_B200_PROFILE") != nullptr;
     long long* dprof = nullptr;
     if (profile) {
-        DO_CUDA(ctx, cudaMalloc(&dprof, 8 * sizeof(long long)));
-        DO_CUDA(ctx, cudaMemsetAsync(dprof, 0, 8 * sizeof(long long), ctx->stream));
+        DO_CUDA(ctx, cudaMalloc(&dprof, 20 * sizeof(long long)));
+        DO_CUDA(ctx, cudaMemsetAsync(dprof, 0, 20 * sizeof(long long), ctx->stream));
         aa.prof = dprof;
     }
     qp_kkt_sqd_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa, fb_list, fb_count);
     ctx->launches++;
     DO_CUDA(ctx, cudaGetLastError());
     if (profile) {
-        long long h[8];
+        long long h[20];
         int nfb = 0;
         DO_CUDA(ctx, cudaMemcpyAsync(h, dprof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         DO_CUDA(ctx, cudaMemcpyAsync(&nfb, fb_count, sizeof nfb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -768,9 +819,10 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
         long long ninst = (a.B + grid - 1) / grid;
         fprintf(stderr,
                 "[qp_sqd profile, CTA 0, %lld instances, %d CTA/SM, nt_cap %d, smem %zu, %d to LU] clocks/instance: "
-                "assemble+diag0 %lld panel %lld update+diag %lld (own work: warp0 %lld warp1 %lld warp3 %lld) backward %lld output %lld\n",
-                ninst, per_sm, nt_cap, smem, nfb, h[0] / ninst, h[1] / ninst, h[2] / ninst, h[5] / ninst, h[6] / ninst,
-                h[7] / ninst, h[3] / ninst, h[4] / ninst);
+                "assemble %lld factor %lld backward %lld output %lld | warp0: wait F %lld, panel row %lld, fence %lld, arrive %lld, tile update %lld, elim %lld | "
+                "warp1: wait E %lld, panel rows %lld, wait B %lld, rhs update %lld, pairs %lld\n",
+                ninst, per_sm, nt_cap, smem, nfb, h[0] / ninst, h[1] / ninst, h[3] / ninst, h[4] / ninst, h[8] / ninst, h[17] / ninst, h[18] / ninst, h[9] / ninst,
+                h[10] / ninst, h[11] / ninst, h[12] / ninst, h[13] / ninst, h[14] / ninst, h[15] / ninst, h[16] / ninst);
     }
     *handled = true;
     return qp_lu_launch_list(ctx, a, nt_cap, fb_list, fb_count);
