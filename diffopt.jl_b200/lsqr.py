@@ -36,3 +36,22 @@ def lsqr_csc(ctx: Context, M, rhs, trans=False, atol=None, btol=None, conlim=Non
         ptr(x), ptr(stats), HOST)
     ctx.check(rc)
     return x, dict(istop=int(stats[0]), itn=int(stats[1]), rnorm=stats[2], arnorm=stats[3])
+
+
+def solve_csc(ctx: Context, M, rhs, trans=False):
+    """Direct branch of ``solve_system`` (``LHS \\ RHS``, QuadraticProgram.jl:490) through
+    ``diffopt_b200_kkt_solve_csc``: one pivoted LU on the device, ``rhs`` may hold many columns
+    (N x nrhs).  Raises ``SingularException`` on an exactly zero pivot like the reference."""
+    from ._capi import SingularException
+    N = M.shape[0]
+    colptr, rowval, nzval = julia_csc(M)
+    rhs = np.asarray(rhs, dtype=np.float64)
+    one = rhs.ndim == 1
+    R = np.asfortranarray(rhs.reshape(N, -1))
+    X = np.empty_like(R, order="F")
+    rc = ctx.lib.diffopt_b200_kkt_solve_csc(ctx.h, N, ptr(colptr), ptr(rowval), ptr(nzval), int(trans), R.shape[1],
+                                            ptr(R), ptr(X), HOST)
+    ctx.check(rc)
+    if rc > 0:
+        raise SingularException(rc)
+    return X[:, 0].copy() if one else X

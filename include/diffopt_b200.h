@@ -116,6 +116,17 @@ int32_t diffopt_b200_qp_batch_param_grads(
     diffopt_b200_ctx* ctx, const double* rev, int32_t reduce_over_batch,
     double* dQ, double* dq, double* dG, double* dh, double* dA, double* db, int32_t memspace);
 
+/* ---- direct branch of solve_system for one KKT system (QuadraticProgram.jl:486-492: `LHS \ RHS`) --------------
+ *
+ * LHS is Julia's SparseMatrixCSC{Float64,Int} (colptr/rowval 1-based int64, N x N); trans = 1 solves with LHS'
+ * (the `Adjoint` forward_differentiate! passes, QuadraticProgram.jl:438).  rhs / x_out are N x nrhs column-major:
+ * all right-hand sides share ONE partially pivoted LU factorisation (the reference refactorises per call).
+ * Returns 0, or the 1-based elimination step with an exactly zero pivot (reference: SingularException).
+ * N <= 8192 (dense on-device factorisation); larger systems need the sparse path. */
+int32_t diffopt_b200_kkt_solve_csc(
+    diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+    int32_t trans, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace);
+
 /* ---- LSQR (IterativeSolvers.lsqr call sites QuadraticProgram.jl:488, ConicProgram.jl:323,372)
  *
  * min ||M x - rhs|| from x0 = 0 on an explicit sparse matrix in Julia's

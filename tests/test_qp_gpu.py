@@ -160,3 +160,130 @@ def test_full_size_batch_properties(ctx):
     of, orv = _oracle_batch(sub)
     assert rel_err(fwd[sl], of).max() <= RTOL_DIRECT
     assert rel_err(rev[sl], orv).max() <= RTOL_DIRECT
+
+
+# ---- the n=64, m=64, p=16 shape has three kernels: pivot-free LDL' fast path (default), pivoted LU
+# (fallback and DIFFOPT_B200_QP_KERNEL=lu), generic LU (DIFFOPT_B200_QP_KERNEL=generic).
+
+def _solve(ctx, d):
+    qpm = diffopt_b200.submodule("qp")
+    return qpm.solve_batch(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"],
+                           fwd_dir=(d["dQ"], d["dq"], d["dG"], d["dh"], d["dA"], d["db"]), seed=d["seed"])
+
+
+@pytest.mark.parametrize("kernel", ["ldl", "lu", "generic"])
+def test_each_headline_kernel_matches_oracle(ctx, kernel, monkeypatch):
+    monkeypatch.setenv("DIFFOPT_B200_QP_KERNEL", kernel)
+    d = bench_data.qp_batch(48, seed0=4242)
+    fwd, rev, info = _solve(ctx, d)
+    assert not info.any()
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+@pytest.mark.parametrize("na", [0, 1, 7, 8, 9, 31, 40, 48])
+def test_active_set_sizes(ctx, na):
+    """Reduced-system order 80 + na: tile padding, pad pivots, every shared-memory configuration (na + 16 <= 64)."""
+    d = bench_data.qp_batch(20, n_active=na, seed0=900 + na)
+    fwd, rev, info = _solve(ctx, d)
+    assert not info.any()
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+def test_ragged_active_sets_in_one_batch(ctx):
+    parts = [bench_data.qp_batch(6, n_active=na, seed0=300 + na) for na in (0, 3, 16, 29, 45)]
+    d = {k: np.concatenate([q[k] for q in parts]) for k in parts[0]}
+    fwd, rev, info = _solve(ctx, d)
+    assert not info.any()
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+def test_interior_point_style_duals(ctx):
+    """Solver output instead of exact complementarity: inactive rows carry lam = 1e-9 (no exact zeros, so nothing is
+    eliminated and the full N = 144 system is factorised), active rows carry slack -1e-9."""
+    d = bench_data.qp_batch(16, seed0=77)
+    act = d["lam"] > 0
+    d["lam"] = np.where(act, d["lam"], 1e-9)
+    slack = np.einsum("bij,bj->bi", d["G"], d["z"]) - d["h"]
+    d["h"] = np.einsum("bij,bj->bi", d["G"], d["z"]) - np.where(act, -1e-9, slack)
+    fwd, rev, info = _solve(ctx, d)
+    assert not info.any()
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+def test_ldl_rejects_go_to_pivoted_lu(ctx):
+    """Instances outside the LDL' path's assumptions must come back identical to the oracle through the fallback:
+    (a) Q only positive SEMIdefinite (rank 40) but K nonsingular, (b) negative duals (wrong sign: K_s not
+    quasi-definite), mixed with regular instances in one batch."""
+    d = bench_data.qp_batch(24, seed0=555)
+    rng = np.random.default_rng(5)
+    for b in range(0, 24, 3):       # (a)
+        L = rng.standard_normal((64, 40))
+        d["Q"][b] = L @ L.T / 40
+    for b in range(1, 24, 3):       # (b)
+        d["lam"][b] = -d["lam"][b]
+    fwd, rev, info = _solve(ctx, d)
+    assert not info.any()
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+def test_singular_instance_inside_headline_batch(ctx):
+    """LICQ violated in one instance (two identical active rows, K numerically singular): the LDL' path rejects it
+    and the pivoted LU treats it like LAPACK would (info > 0 on an exactly zero pivot, otherwise a huge solution);
+    the other instances of the batch are unaffected."""
+    d = bench_data.qp_batch(8, seed0=31)
+    act = np.flatnonzero(d["lam"][3] > 0)
+    d["G"][3, act[1]] = d["G"][3, act[0]]
+    d["h"][3, act[1]] = d["h"][3, act[0]]
+    fwd, rev, info = _solve(ctx, d)
+    assert not np.delete(info, 3).any()
+    assert info[3] > 0 or not np.isfinite(rev[3]).all() or np.abs(rev[3]).max() > 1e8
+    keep = np.arange(8) != 3
+    of, orv = _oracle_batch({k: v[keep] for k, v in d.items()})
+    assert rel_err(fwd[keep], of).max() <= RTOL_DIRECT
+    assert rel_err(rev[keep], orv).max() <= RTOL_DIRECT
+
+
+@pytest.mark.parametrize("N,nrhs", [(1, 1), (9, 1), (70, 3), (300, 16), (1100, 5)])
+def test_direct_solve_system_csc(ctx, N, nrhs):
+    """`LHS \\ RHS` drop-in (QuadraticProgram.jl:490): CSC and Adjoint{CSC}, one and many right-hand sides."""
+    import scipy.sparse as sp
+    lsq = diffopt_b200.submodule("lsqr")
+    rng = np.random.default_rng(N)
+    M = sp.random(N, N, density=min(1.0, 8.0 / N), random_state=N, format="csc") + sp.diags(rng.uniform(1, 2, N) * rng.choice([-1, 1], N))
+    M = sp.csc_matrix(M)
+    R = rng.standard_normal((N, nrhs))
+    for trans in (False, True):
+        X = lsq.solve_csc(ctx, M, R, trans=trans)
+        ref = np.linalg.solve(M.toarray().T if trans else M.toarray(), R)
+        assert (np.linalg.norm(X - ref, axis=0) / np.linalg.norm(ref, axis=0)).max() <= RTOL_DIRECT
+    x1 = lsq.solve_csc(ctx, M, R[:, 0])
+    assert np.allclose(x1, np.linalg.solve(M.toarray(), R[:, 0]), rtol=1e-9, atol=1e-12)
+
+
+def test_direct_solve_system_kkt_and_singular(ctx, kat):
+    """The reference's KKT matrix (create_LHS_matrix) of a known-answer case through the direct drop-in, both
+    orientations as reverse (:335) and forward (:438) use them; exactly singular LHS -> SingularException."""
+    lsq = diffopt_b200.submodule("lsqr")
+    import scipy.sparse as sp
+    c = kat["qp_moi_examples_2"]
+    n, m, p = len(c["z"]), len(c["lam"]), len(c["nu"])
+    a = lambda k, shape: np.array(c[k], float).reshape(shape)
+    K = oqp.create_lhs(a("z", n), a("lam", m), a("Q", (n, n)), a("G", (m, n)), a("h", m), a("A", (p, n)))
+    rb = np.zeros(n + m + p); rb[:n] = c["seed"]
+    x = -lsq.solve_csc(ctx, sp.csc_matrix(K), rb)
+    dz, dl, dn = oqp.reverse(a("Q", (n, n)), a("G", (m, n)), a("h", m), a("A", (p, n)), a("z", n), a("lam", m), a("nu", p),
+                             np.array(c["seed"], float))
+    assert np.allclose(x, np.concatenate([dz, dl, dn]), rtol=1e-9, atol=1e-12)
+    S = sp.csc_matrix(np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 1.0]]))
+    with pytest.raises(diffopt_b200.SingularException):
+        lsq.solve_csc(ctx, S, np.ones(3))
