@@ -46,6 +46,7 @@ int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {
     ctx->info.release();
     ctx->qp_fb.release();
     ctx->qp_max.release();
+    if (ctx->qp_hmax_host) cudaFreeHost(ctx->qp_hmax_host);
     QpBatchState& q = ctx->qp;
     q.Q.release(); q.G.release(); q.A.release(); q.h.release(); q.z.release(); q.lam.release(); q.nu.release();
     ConicState& c = ctx->conic;

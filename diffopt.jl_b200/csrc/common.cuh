@@ -88,6 +88,8 @@ struct diffopt_b200_ctx {
     DevBuf info;
     DevBuf qp_fb;   // [count, list...] of instances the LDL' fast path hands to the pivoted LU kernel
     DevBuf qp_max;  // device scalar: largest active-set size of the batch
+    int* qp_hmax_host = nullptr;  // pinned copy of it, read at the start of the NEXT call (calls end synchronised)
+    int qp_hint = -1;             // active-set size the next headline-shape launch is configured for (-1: unknown)
     QpBatchState qp;
     ConicState conic;
     LsqrWork lsqr;

@@ -819,7 +819,8 @@ static int32_t lu_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap
 // the pivoted LU kernel over a device-side list of instances (fallback of the LDL' fast path)
 int32_t qp_lu_launch_list(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, const int* list, const int* count) {
     bool handled = false;
-    int32_t rc = lu_launch(ctx, a, nt_cap, list, count, &handled);
+    (void)nt_cap;  // rejected instances may be larger than the fast path's configuration: always worst-case sized
+    int32_t rc = lu_launch(ctx, a, NTMAX, list, count, &handled);
     if (rc == 0 && !handled) {
         ctx->err = "qp_batch: pivoted-LU fallback does not fit in shared memory";
         return -3;
@@ -833,9 +834,15 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
     if (a.n != NV || a.m != MI || a.p != PE) return 0;
     const char* force = getenv("DIFFOPT_B200_QP_KERNEL");
     if (force && strcmp(force, "generic") == 0) return 0;
-    // size the tile matrix by the largest reduced system of the batch
+    // The shared-memory configuration depends on the largest active set of the batch (reduced order 80 + active).
+    // First call: measure it and wait for the answer.  Later calls: launch for the size seen by the PREVIOUS call
+    // (no host round trip in the middle of the call); instances that do not fit that guess are handed to the
+    // pivoted-LU kernel, and the size measured now configures the next call.
     DO_CUDA(ctx, ctx->qp_max.reserve(sizeof(int)));
+    if (!ctx->qp_hmax_host) DO_CUDA(ctx, cudaHostAlloc((void**)&ctx->qp_hmax_host, sizeof(int), cudaHostAllocDefault));
     int* dmax = ctx->qp_max.as<int>();
+    const bool first = ctx->qp_hint < 0;
+    if (!first) ctx->qp_hint = *ctx->qp_hmax_host;
     DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
     {
         int64_t blocks = (a.B + 7) / 8;
@@ -843,13 +850,18 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
         max_active_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a.B, a.lam, dmax);
         ctx->launches++;
     }
-    int hmax = 0;
-    DO_CUDA(ctx, cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int nt_cap = (NV + hmax + PE + 7) / 8;
+    DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (first) {
+        DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->qp_hint = *ctx->qp_hmax_host;
+    }
+    const int nt_cap = (NV + ctx->qp_hint + PE + 7) / 8;
     if (!(force && strcmp(force, "lu") == 0)) {
         int32_t rc = qp_sqd_launch(ctx, a, nt_cap, handled);
         if (rc != 0 || *handled) return rc;
+    }
+    if (!first) {  // the guess may be too small for the plain LU launch: size it for the worst case
+        return lu_launch(ctx, a, NTMAX, nullptr, nullptr, handled);
     }
     return lu_launch(ctx, a, nt_cap, nullptr, nullptr, handled);
 }

@@ -208,7 +208,7 @@ __device__ __forceinline__ void panel_row(double* p, const double* Ld, const dou
 __device__ __forceinline__ void bar_sync(const int id, const int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, int* fb_list, int* fb_count) {
+__global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, int* fb_list, int* fb_count, const int nt_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Hdr& S = *reinterpret_cast<Hdr*>(smem_raw);
     double* const T = reinterpret_cast<double*>(smem_raw + sizeof(Hdr));
@@ -289,6 +289,11 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         __syncthreads();
         const int ma = S.ma, nt = S.nt;
         const int nred = NV + ma + PE, np = nt << 3;
+        if (nt > nt_cap) {  // larger than this launch was configured for: the pivoted-LU kernel takes it
+            if (tid == 0) fb_list[atomicAdd(fb_count, 1)] = (int)inst;
+            __syncthreads();
+            continue;
+        }
         // ---- clear the tile rows below the z block, then fill
         {
             double2* zp = reinterpret_cast<double2*>(T + tix(NTZ, 0) * 64);
@@ -806,7 +811,7 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
         DO_CUDA(ctx, cudaMemsetAsync(dprof, 0, 20 * sizeof(long long), ctx->stream));
         aa.prof = dprof;
     }
-    qp_kkt_sqd_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa, fb_list, fb_count);
+    qp_kkt_sqd_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa, fb_list, fb_count, nt_cap);
     ctx->launches++;
     DO_CUDA(ctx, cudaGetLastError());
     if (profile) {
