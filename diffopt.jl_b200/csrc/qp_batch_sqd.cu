@@ -59,6 +59,12 @@ struct __align__(16) Hdr {
 
 __device__ __forceinline__ int tix(int I, int J) { return ((I * (I + 1)) >> 1) + J; }
 
+// Offset of element (r, c) inside an 8 x 8 tile.  Rows are 64 B; the four 16-byte chunks of row r are stored at
+// chunk ^ ((r >> 1) & 3).  DMMA fragment accesses (lane (g, t) -> chunk t of row g) and whole-row accesses (one lane
+// per row, chunk q of rows 0..7) are then both free of shared-memory bank conflicts.
+__device__ __forceinline__ int el(int r, int c) { return r * 8 + ((((c >> 1) ^ (r >> 1)) & 3) << 1) + (c & 1); }
+__device__ __forceinline__ int swz(int r) { return (r >> 1) & 3; }
+
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
@@ -121,7 +127,7 @@ __device__ __noinline__ void elim8(double* D, double* ref, double* rd, const boo
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
             if (c <= i) {
-                const double2 v = *reinterpret_cast<const double2*>(&D[i * 8 + c]);
+                const double2 v = *reinterpret_cast<const double2*>(&D[el(i, c)]);
                 a[i][c] = v.x;
                 a[i][c + 1] = v.y;
             }
@@ -155,7 +161,7 @@ __device__ __noinline__ void elim8(double* D, double* ref, double* rd, const boo
             for (int i = c; i < 8; ++i) a[i][c] = fma(-lk[i], a[c][k], a[i][c]);
         }
 #pragma unroll
-        for (int i = k + 1; i < 8; ++i) D[i * 8 + k] = lk[i];
+        for (int i = k + 1; i < 8; ++i) D[el(i, k)] = lk[i];
         r = rn;
     }
     bool ok = true;
@@ -165,15 +171,15 @@ __device__ __noinline__ void elim8(double* D, double* ref, double* rd, const boo
 }
 
 // One row w (8 doubles at p) of a panel tile: w <- w L11^-T, i.e. solve x L11' = w with the unit-lower L11 stored
-// in the strict lower triangle of tile Ld (axpy form: one FMA per step on the dependency chain).
+// in the strict lower triangle of tile Ld.  sw = swz(row) for a tile row, 0 for a plain vector.
 // scale != nullptr: the result is also multiplied by scale[0..7] (right-hand side rows: v = D^-1 L^-1 r).
-__device__ __forceinline__ void panel_row(double* p, const double* Ld, const double* scale) {
+__device__ __forceinline__ void panel_row(double* p, const int sw, const double* Ld, const double* scale) {
     double w[8];
     {
         const double2* pp = reinterpret_cast<const double2*>(p);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const double2 v = pp[q];
+            const double2 v = pp[q ^ sw];
             w[2 * q] = v.x;
             w[2 * q + 1] = v.y;
         }
@@ -183,7 +189,7 @@ __device__ __forceinline__ void panel_row(double* p, const double* Ld, const dou
         double l[8];
 #pragma unroll
         for (int k = 0; k < c; k += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(&Ld[c * 8 + k]);
+            const double2 v = *reinterpret_cast<const double2*>(&Ld[el(c, k)]);
             l[k] = v.x;
             l[k + 1] = v.y;
         }
@@ -201,7 +207,7 @@ __device__ __forceinline__ void panel_row(double* p, const double* Ld, const dou
     }
     double2* pp = reinterpret_cast<double2*>(p);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) pp[q] = make_double2(w[2 * q], w[2 * q + 1]);
+    for (int q = 0; q < 4; ++q) pp[q ^ sw] = make_double2(w[2 * q], w[2 * q + 1]);
 }
 
 // named barriers (id 0 is __syncthreads)
@@ -215,11 +221,13 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // g, t: DMMA fragment coordinates; the same pair addresses the tile-shaped global loads (column g, rows 2t, 2t+1)
     const int g = lane >> 2, t = lane & 3;
-    const int fo = g * 8 + 2 * t;  // fragment offset inside a tile
+    const int fo = el(g, 2 * t);  // fragment offset inside a tile
     const bool do_fwd = a.fwd != nullptr, do_rev = a.rev != nullptr;
 #ifdef QP_PROFILE
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long sub[6] = {0, 0, 0, 0, 0, 0};
+    long long asub[6] = {0, 0, 0, 0, 0, 0};
+    long long tprev2 = 0;
     long long tsub = 0;
     long long tprev = clock64();
 #define PROF(i)                  \
@@ -227,6 +235,12 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         long long _n = clock64(); \
         pc[i] += _n - tprev;     \
         tprev = _n;              \
+    } while (0)
+#define ASUB(i)                  \
+    do {                         \
+        long long _n = clock64(); \
+        asub[i] += _n - tprev2;  \
+        tprev2 = _n;             \
     } while (0)
 #define SUB0() tsub = clock64()
 #define SUB(i)                   \
@@ -237,12 +251,16 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
     } while (0)
 #else
 #define PROF(i)
+#define ASUB(i)
 #define SUB0()
 #define SUB(i)
 #endif
 
     for (int64_t inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
         const size_t b = (size_t)inst;
+#ifdef QP_PROFILE
+        tprev2 = clock64();
+#endif
         const double* Q = a.Q + b * NV * NV;
         const double* G = a.G + b * MI * NV;
         const double* A = a.A + b * PE * NV;
@@ -287,6 +305,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
             }
         }
         __syncthreads();
+        ASUB(0);
         const int ma = S.ma, nt = S.nt;
         const int nred = NV + ma + PE, np = nt << 3;
         if (nt > nt_cap) {  // larger than this launch was configured for: the pivoted-LU kernel takes it
@@ -294,11 +313,22 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
             __syncthreads();
             continue;
         }
-        // ---- clear the tile rows below the z block, then fill
+        // ---- clear what the fill below does not overwrite: the tiles of the (2,2) block and the padding rows
         {
-            double2* zp = reinterpret_cast<double2*>(T + tix(NTZ, 0) * 64);
-            const int cnt = (tix(nt, 0) - tix(NTZ, 0)) * 32;
-            for (int i = tid; i < cnt; i += THREADS) zp[i] = make_double2(0.0, 0.0);
+            const int nneg = nt - NTZ;                      // tile rows below the z block
+            const int cnt = ((nneg * (nneg + 1)) >> 1) * 32;  // double2 slots of the tiles (I >= NTZ, NTZ <= J <= I)
+            for (int i = tid; i < cnt; i += THREADS) {
+                const int tl = i >> 5;                        // tile number inside the (2,2) block, row major lower
+                int I = 0;
+                while (((I + 1) * (I + 2)) >> 1 <= tl) ++I;
+                const int J = tl - ((I * (I + 1)) >> 1);
+                reinterpret_cast<double2*>(T + tix(NTZ + I, NTZ + J) * 64)[i & 31] = make_double2(0.0, 0.0);
+            }
+            const int npad = np - nred;                       // rows nred .. np-1 of the last tile row, columns 0 .. NV-1
+            for (int i = tid; i < npad * NV; i += THREADS) {
+                const int r = nred + i / NV, c = i % NV;
+                T[tix(nt - 1, c >> 3) * 64 + el(r & 7, c & 7)] = 0.0;
+            }
         }
         if (tid < np - NV) {
             S.yb[NV + tid] = 0.0;
@@ -314,9 +344,9 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         for (int s9 = 0; s9 < 9; ++s9) {
             const bool first = s9 <= warp;
             const int I = first ? warp : 7 - warp, J = first ? s9 : s9 - warp - 1;
-            double* tp = T + tix(I, J) * 64 + (2 * t) * 8 + g;
-            tp[0] = qv[s9].x;
-            tp[8] = qv[s9].y;
+            double* tp = T + tix(I, J) * 64;
+            tp[el(2 * t, g)] = qv[s9].x;
+            tp[el(2 * t + 1, g)] = qv[s9].y;
             if (J == I) {
                 if (g == 2 * t) S.ref[8 * I + g] = qv[s9].x;
                 if (g == 2 * t + 1) S.ref[8 * I + g] = qv[s9].y;
@@ -327,7 +357,8 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
 #pragma unroll
         for (int q = 0; q < 4; ++q) hv[q] = a.h[b * MI + 8 * (warp + 4 * (q >> 1)) + 2 * t + (q & 1)];
         __syncthreads();
-        if (tid >= nred && tid < np) T[tix(nt - 1, nt - 1) * 64 + (tid & 7) * 9] = -1.0;  // identity padding
+        ASUB(1);
+        if (tid >= nred && tid < np) T[tix(nt - 1, nt - 1) * 64 + el(tid & 7, tid & 7)] = -1.0;  // identity padding
         // ---- G: D = G z - h for every row; active rows go to the matrix; warp w owns tile rows w, w+4
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -342,12 +373,12 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
             }
             const int a0 = S.apos[r0], a1 = S.apos[r0 + 1];
             if (a0 >= 0) {
-                double* tp = T + tix(NTZ + (a0 >> 3), 0) * 64 + (a0 & 7) * 8 + g;
+                double* tp = T + tix(NTZ + (a0 >> 3), 0) * 64 + el(a0 & 7, g);
 #pragma unroll
                 for (int J = 0; J < 8; ++J) tp[J * 64] = gv[J].x;
             }
             if (a1 >= 0) {
-                double* tp = T + tix(NTZ + (a1 >> 3), 0) * 64 + (a1 & 7) * 8 + g;
+                double* tp = T + tix(NTZ + (a1 >> 3), 0) * 64 + el(a1 & 7, g);
 #pragma unroll
                 for (int J = 0; J < 8; ++J) tp[J * 64] = gv[J].y;
             }
@@ -360,12 +391,13 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                 d1 -= hv[2 * hh + 1];
                 S.dvec[r0] = d0;
                 S.dvec[r0 + 1] = d1;
-                if (a0 >= 0) T[tix(NTZ + (a0 >> 3), NTZ + (a0 >> 3)) * 64 + (a0 & 7) * 9] = d0 / S.lams[r0];
+                if (a0 >= 0) T[tix(NTZ + (a0 >> 3), NTZ + (a0 >> 3)) * 64 + el(a0 & 7, a0 & 7)] = d0 * fast_rcp(S.lams[r0]);
                 else if (d0 == 0.0) S.fail = 1;  // lam_i = D_i = 0: singular column, the LU path reports it
-                if (a1 >= 0) T[tix(NTZ + (a1 >> 3), NTZ + (a1 >> 3)) * 64 + (a1 & 7) * 9] = d1 / S.lams[r0 + 1];
+                if (a1 >= 0) T[tix(NTZ + (a1 >> 3), NTZ + (a1 >> 3)) * 64 + el(a1 & 7, a1 & 7)] = d1 * fast_rcp(S.lams[r0 + 1]);
                 else if (d1 == 0.0) S.fail = 1;
             }
         }
+        ASUB(2);
         // ---- A (16 x 64): warp w owns tile columns 2w, 2w+1
 #pragma unroll
         for (int q = 0; q < 4; ++q) av[q] = ldg2(A + (8 * (2 * warp + (q >> 1)) + g) * PE + 8 * (q & 1) + 2 * t);
@@ -382,9 +414,10 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         for (int q = 0; q < 4; ++q) {
             const int J = 2 * warp + (q >> 1), Ia = q & 1;
             const int k0 = NV + ma + 8 * Ia + 2 * t, k1 = k0 + 1;
-            T[tix(k0 >> 3, J) * 64 + (k0 & 7) * 8 + g] = av[q].x;
-            T[tix(k1 >> 3, J) * 64 + (k1 & 7) * 8 + g] = av[q].y;
+            T[tix(k0 >> 3, J) * 64 + el(k0 & 7, g)] = av[q].x;
+            T[tix(k1 >> 3, J) * 64 + el(k1 & 7, g)] = av[q].y;
         }
+        ASUB(3);
         // ---- forward right-hand side (QuadraticProgram.jl:429-433), symmetric-form scaling
         if (do_fwd) {
             if (a.dA) {
@@ -466,6 +499,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
             }
         }
         __syncthreads();
+        ASUB(4);
         if (tid < NV) {
             double v = 0.0;
             if (do_fwd) v = (S.rowq[tid] + vq) + ((S.gcol[0][tid] + S.gcol[1][tid]) + (S.gcol[2][tid] + S.gcol[3][tid])) + S.acol[tid];
@@ -499,7 +533,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                 if (j < nt - 1) {
                     double* Wt = T + tix(j + 1, j) * 64;
 #if QP_ABLATE != 1
-                    if (lane < 8) panel_row(Wt + lane * 8, T + tix(j, j) * 64, nullptr);
+                    if (lane < 8) panel_row(Wt + lane * 8, swz(lane), T + tix(j, j) * 64, nullptr);
 #endif
                     __syncwarp();
                 }
@@ -535,9 +569,9 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                 {   // panel rows 8(j+2) .. np-1 and the two right-hand sides (threads 94, 95)
 #if QP_ABLATE != 3
                     if (bt < 94) {
-                        for (int rr = c0 + 16 + bt; rr < np; rr += 94) panel_row(T + tix(rr >> 3, j) * 64 + (rr & 7) * 8, Ld, nullptr);
+                        for (int rr = c0 + 16 + bt; rr < np; rr += 94) panel_row(T + tix(rr >> 3, j) * 64 + (rr & 7) * 8, swz(rr & 7), Ld, nullptr);
                     } else {
-                        panel_row((bt == 94 ? S.yf : S.yb) + c0, Ld, &S.rd[c0]);
+                        panel_row((bt == 94 ? S.yf : S.yb) + c0, 0, Ld, &S.rd[c0]);
                     }
 #endif
                 }
@@ -551,7 +585,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                     double uf = S.yf[rr], ub = S.yb[rr], uf2 = 0.0, ub2 = 0.0;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const double2 w2 = wrow[q];
+                        const double2 w2 = wrow[q ^ swz(rr & 7)];
                         const double2 vf = *reinterpret_cast<const double2*>(&S.yf[c0 + 2 * q]);
                         const double2 vb2 = *reinterpret_cast<const double2*>(&S.yb[c0 + 2 * q]);
                         uf = fma(-w2.x, vf.x, uf);
@@ -642,7 +676,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                     for (int k = 7; k >= 1; --k) {
 #pragma unroll
                         for (int c = 0; c < k; c += 2) {
-                            const double2 l2 = *reinterpret_cast<const double2*>(&Dt[k * 8 + c]);
+                            const double2 l2 = *reinterpret_cast<const double2*>(&Dt[el(k, c)]);
                             x8[c] = fma(-l2.x, x8[k], x8[c]);
                             if (c + 1 < k) x8[c + 1] = fma(-l2.y, x8[k], x8[c + 1]);
                         }
@@ -653,12 +687,13 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                     }
                     const int c = c0 - 1 - lane;
                     if (c >= 0) {
-                        const double* wt = T + tix(j, c >> 3) * 64 + (c & 7);
+                        const double* wt = T + tix(j, c >> 3) * 64;
+                        const int cc = c & 7;
                         double v = s1[c], v2 = 0.0;
 #pragma unroll
                         for (int k = 0; k < 8; k += 2) {
-                            v = fma(wt[k * 8], x8[k], v);
-                            v2 = fma(wt[(k + 1) * 8], x8[k + 1], v2);
+                            v = fma(wt[el(k, cc)], x8[k], v);
+                            v2 = fma(wt[el(k + 1, cc)], x8[k + 1], v2);
                         }
                         s1[c] = v + v2;
                     }
@@ -681,12 +716,13 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                             x8[k + 1] = xx.y;
                         }
                         for (int c = c1 - 33 - lane; c >= 0; c -= 32) {
-                            const double* wt = T + tix(jj, c >> 3) * 64 + (c & 7);
+                            const double* wt = T + tix(jj, c >> 3) * 64;
+                            const int cc = c & 7;
                             double v = s2[c], v2 = 0.0;
 #pragma unroll
                             for (int k = 0; k < 8; k += 2) {
-                                v = fma(wt[k * 8], x8[k], v);
-                                v2 = fma(wt[(k + 1) * 8], x8[k + 1], v2);
+                                v = fma(wt[el(k, cc)], x8[k], v);
+                                v2 = fma(wt[el(k + 1, cc)], x8[k + 1], v2);
                             }
                             s2[c] = v + v2;
                         }
@@ -706,6 +742,23 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                 for (int l = tid; l < 256; l += THREADS) {
                     if (16 * (l & 3) + 15 >= ((l >> 2) & ~7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(qn + (size_t)l * 128));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)l * 128));
+                }
+                // ... and its vectors (z, lam, nu, h, seed, dq, dh, db): they gate the first barriers of the assembly
+                if (tid < 32) {
+                    const int v = tid >> 2, ln = tid & 3;  // 8 vectors x up to 4 lines of 128 B (plus one for misalignment)
+                    const double* base = nullptr;
+                    int len = 0;
+                    switch (v) {
+                        case 0: base = a.z + (size_t)nxt * NV; len = NV; break;
+                        case 1: base = a.lam + (size_t)nxt * MI; len = MI; break;
+                        case 2: base = a.h + (size_t)nxt * MI; len = MI; break;
+                        case 3: base = a.nu + (size_t)nxt * PE; len = PE; break;
+                        case 4: base = do_rev ? a.seed + (size_t)nxt * NV : nullptr; len = NV; break;
+                        case 5: base = do_fwd && a.dq ? a.dq + (size_t)nxt * NV : nullptr; len = NV; break;
+                        case 6: base = do_fwd && a.dh ? a.dh + (size_t)nxt * MI : nullptr; len = MI; break;
+                        default: base = do_fwd && a.db ? a.db + (size_t)nxt * PE : nullptr; len = PE; break;
+                    }
+                    if (base && ln * 16 < len) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)base + (size_t)ln * 128));
                 }
             }
         }
@@ -764,6 +817,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         for (int i = 0; i < 4; ++i) a.prof[8 + i] = sub[i];
         a.prof[17] = sub[4];
         a.prof[18] = sub[5];
+        for (int i = 0; i < 5; ++i) a.prof[20 + i] = asub[i];
     }
     if (a.prof && blockIdx.x == 0 && tid == 32)
         for (int i = 0; i < 5; ++i) a.prof[12 + i] = sub[i];
@@ -807,15 +861,15 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
     const bool profile = getenv("DIFFOPT_B200_PROFILE") != nullptr;
     long long* dprof = nullptr;
     if (profile) {
-        DO_CUDA(ctx, cudaMalloc(&dprof, 20 * sizeof(long long)));
-        DO_CUDA(ctx, cudaMemsetAsync(dprof, 0, 20 * sizeof(long long), ctx->stream));
+        DO_CUDA(ctx, cudaMalloc(&dprof, 32 * sizeof(long long)));
+        DO_CUDA(ctx, cudaMemsetAsync(dprof, 0, 32 * sizeof(long long), ctx->stream));
         aa.prof = dprof;
     }
     qp_kkt_sqd_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa, fb_list, fb_count, nt_cap);
     ctx->launches++;
     DO_CUDA(ctx, cudaGetLastError());
     if (profile) {
-        long long h[20];
+        long long h[32];
         int nfb = 0;
         DO_CUDA(ctx, cudaMemcpyAsync(h, dprof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         DO_CUDA(ctx, cudaMemcpyAsync(&nfb, fb_count, sizeof nfb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -825,9 +879,11 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
         fprintf(stderr,
                 "[qp_sqd profile, CTA 0, %lld instances, %d CTA/SM, nt_cap %d, smem %zu, %d to LU] clocks/instance: "
                 "assemble %lld factor %lld backward %lld output %lld | warp0: wait F %lld, panel row %lld, fence %lld, arrive %lld, tile update %lld, elim %lld | "
-                "warp1: wait E %lld, panel rows %lld, wait B %lld, rhs update %lld, pairs %lld\n",
+                "warp1: wait E %lld, panel rows %lld, wait B %lld, rhs update %lld, pairs %lld | assemble: to sync1 %lld, to sync2 %lld, G %lld, A %lld, "
+                "fwd rhs %lld\n",
                 ninst, per_sm, nt_cap, smem, nfb, h[0] / ninst, h[1] / ninst, h[3] / ninst, h[4] / ninst, h[8] / ninst, h[17] / ninst, h[18] / ninst, h[9] / ninst,
-                h[10] / ninst, h[11] / ninst, h[12] / ninst, h[13] / ninst, h[14] / ninst, h[15] / ninst, h[16] / ninst);
+                h[10] / ninst, h[11] / ninst, h[12] / ninst, h[13] / ninst, h[14] / ninst, h[15] / ninst, h[16] / ninst, h[20] / ninst, h[21] / ninst, h[22] / ninst,
+                h[23] / ninst, h[24] / ninst);
     }
     *handled = true;
     return qp_lu_launch_list(ctx, a, nt_cap, fb_list, fb_count);
