@@ -71,6 +71,15 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
+// m16n8k8: two vertically adjacent 8 x 8 tiles (rows g and g+8 of the 16-row A / C operands) against one B tile.
+// With the k-slot convention used throughout (slot t <-> tile column 2t, slot t+4 <-> column 2t+1) the operands
+// are exactly the double2 fragments at offset `fo` of the two A tiles, the B tile and the two C tiles.
+__device__ __forceinline__ void dmma16(double2& c_top, double2& c_bot, const double2 a_top, const double2 a_bot, const double2 b) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(c_top.x), "+d"(c_top.y), "+d"(c_bot.x), "+d"(c_bot.y)
+        : "d"(a_top.x), "d"(a_bot.x), "d"(a_top.y), "d"(a_bot.y), "d"(b.x), "d"(b.y));
+}
+
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // 1/x: hardware estimate (rel. error <= 2^-20) + one cubic Newton step r0 (1 + e + e^2), e = 1 - x r0:
@@ -597,46 +606,77 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                     S.yb[rr] = ub + ub2;
                 }
                 SUB(3);
-                // tile rows I = nt-1 .. j+2 (row j+1 is warp 0's single tile), dealt in snake order
-                const int nrows = nt - 2 - j;
+                // tile rows I = nt-1 .. j+2 (row j+1 is warp 0's single tile) taken in PAIRS (I1-1, I1): one m16n8k8 DMMA
+                // updates the two vertically adjacent tiles of a column with a shared B fragment; pairs are dealt to the
+                // warps in snake order
+                const int nrows = nt - 2 - j, nitems = (nrows + 1) >> 1;
                 const double* const b0p = T + tix(j + 1, j) * 64 + fo;
-                for (int rnd = 0; 3 * rnd < nrows; ++rnd) {
+                for (int rnd = 0; 3 * rnd < nitems; ++rnd) {
                     const int idx = 3 * rnd + ((rnd & 1) ? 2 - bw : bw);
 #if QP_ABLATE == 4
                     continue;
 #endif
-                    if (idx >= nrows) continue;
-                    const int I = nt - 1 - idx;
-                    double2 af = *reinterpret_cast<const double2*>(T + tix(I, j) * 64 + fo);
-                    af.x *= nr0;
-                    af.y *= nr1;
+                    if (idx >= nitems) continue;
+                    const int I1 = nt - 1 - 2 * idx, I0 = I1 - 1;
+                    const double2 w1 = *reinterpret_cast<const double2*>(T + tix(I1, j) * 64 + fo);
+                    const double2 a1 = make_double2(w1.x * nr0, w1.y * nr1);
                     const double* bp = b0p;
-                    double* cp = T + tix(I, j + 1) * 64 + fo;
+                    double* c1p = T + tix(I1, j + 1) * 64 + fo;
                     int K = j + 1;
-                    for (; K < I; K += 2) {
+                    if (I0 >= j + 2) {
+                        double2 a0 = *reinterpret_cast<const double2*>(T + tix(I0, j) * 64 + fo);
+                        a0.x *= nr0;
+                        a0.y *= nr1;
+                        double* c0p = T + tix(I0, j + 1) * 64 + fo;
+                        for (; K < I0; K += 2) {  // two columns per iteration
+                            const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                            const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);
+                            bp += (2 * K + 3) * 64;
+                            double2 c00 = *reinterpret_cast<double2*>(c0p), c10 = *reinterpret_cast<double2*>(c1p);
+                            double2 c01 = *reinterpret_cast<double2*>(c0p + 64), c11 = *reinterpret_cast<double2*>(c1p + 64);
+                            dmma16(c00, c10, a0, a1, b0);
+                            dmma16(c01, c11, a0, a1, b1);
+                            *reinterpret_cast<double2*>(c0p) = c00;
+                            *reinterpret_cast<double2*>(c1p) = c10;
+                            *reinterpret_cast<double2*>(c0p + 64) = c01;
+                            *reinterpret_cast<double2*>(c1p + 64) = c11;
+                            c0p += 128;
+                            c1p += 128;
+                        }
+                        if (K == I0) {  // column I0: diagonal tile of row I0 and tile (I1, I0)
+                            const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                            double2 c00 = *reinterpret_cast<double2*>(c0p), c10 = *reinterpret_cast<double2*>(c1p);
+                            dmma16(c00, c10, a0, a1, b0);
+                            *reinterpret_cast<double2*>(c0p) = c00;
+                            *reinterpret_cast<double2*>(c1p) = c10;
+                            c1p += 64;
+                            ++K;
+                        }
+                    } else {  // odd row count: row j+2 alone, column j+1 first
                         const double2 b0 = *reinterpret_cast<const double2*>(bp);
-                        const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);
-                        bp += (2 * K + 3) * 64;
-                        double2 ca = *reinterpret_cast<double2*>(cp), cb = *reinterpret_cast<double2*>(cp + 64);
-                        dmma(ca.x, ca.y, af.x, b0.x);
-                        dmma(cb.x, cb.y, af.x, b1.x);
-                        dmma(ca.x, ca.y, af.y, b0.y);
-                        dmma(cb.x, cb.y, af.y, b1.y);
-                        *reinterpret_cast<double2*>(cp) = ca;
-                        *reinterpret_cast<double2*>(cp + 64) = cb;
-                        cp += 128;
+                        double2 ca = *reinterpret_cast<double2*>(c1p);
+                        dmma(ca.x, ca.y, a1.x, b0.x);
+                        dmma(ca.x, ca.y, a1.y, b0.y);
+                        *reinterpret_cast<double2*>(c1p) = ca;
+                        c1p += 64;
+                        ++K;
                     }
-                    if (K == I) {
-                        const double2 b0 = *reinterpret_cast<const double2*>(bp);
-                        double2 ca = *reinterpret_cast<double2*>(cp);
-                        dmma(ca.x, ca.y, af.x, b0.x);
-                        dmma(ca.x, ca.y, af.y, b0.y);
-                        *reinterpret_cast<double2*>(cp) = ca;
+                    {   // diagonal tile (I1, I1): B = W(I1, j) itself
+                        double2 ca = *reinterpret_cast<double2*>(c1p);
+                        dmma(ca.x, ca.y, a1.x, w1.x);
+                        dmma(ca.x, ca.y, a1.y, w1.y);
+                        *reinterpret_cast<double2*>(c1p) = ca;
                     }
-                    if (j == NTZ - 1) {  // Schur complement of the z block complete: record the diagonal of tile (I,I)
-                        const double2 dg = *reinterpret_cast<const double2*>(T + tix(I, I) * 64 + fo);
-                        if (g == 2 * t) S.ref[8 * I + g] = fabs(dg.x);
-                        if (g == 2 * t + 1) S.ref[8 * I + g] = fabs(dg.y);
+                    if (j == NTZ - 1) {  // Schur complement of the z block complete: record the diagonals of tiles (I,I)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int I = q ? I1 : I0;
+                            if (I >= j + 2) {
+                                const double2 dg = *reinterpret_cast<const double2*>(T + tix(I, I) * 64 + fo);
+                                if (g == 2 * t) S.ref[8 * I + g] = fabs(dg.x);
+                                if (g == 2 * t + 1) S.ref[8 * I + g] = fabs(dg.y);
+                            }
+                        }
                     }
                 }
                 __threadfence_block();
