@@ -628,6 +628,31 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                         a0.x *= nr0;
                         a0.y *= nr1;
                         double* c0p = T + tix(I0, j + 1) * 64 + fo;
+                        for (; K + 3 <= I0; K += 4) {  // four columns per iteration: four independent DMMAs in flight
+                            const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                            const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);
+                            const double2 b2 = *reinterpret_cast<const double2*>(bp + (2 * K + 3) * 64);
+                            const double2 b3 = *reinterpret_cast<const double2*>(bp + (3 * K + 6) * 64);
+                            bp += (4 * K + 10) * 64;
+                            double2 c00 = *reinterpret_cast<double2*>(c0p), c10 = *reinterpret_cast<double2*>(c1p);
+                            double2 c01 = *reinterpret_cast<double2*>(c0p + 64), c11 = *reinterpret_cast<double2*>(c1p + 64);
+                            double2 c02 = *reinterpret_cast<double2*>(c0p + 128), c12 = *reinterpret_cast<double2*>(c1p + 128);
+                            double2 c03 = *reinterpret_cast<double2*>(c0p + 192), c13 = *reinterpret_cast<double2*>(c1p + 192);
+                            dmma16(c00, c10, a0, a1, b0);
+                            dmma16(c01, c11, a0, a1, b1);
+                            dmma16(c02, c12, a0, a1, b2);
+                            dmma16(c03, c13, a0, a1, b3);
+                            *reinterpret_cast<double2*>(c0p) = c00;
+                            *reinterpret_cast<double2*>(c1p) = c10;
+                            *reinterpret_cast<double2*>(c0p + 64) = c01;
+                            *reinterpret_cast<double2*>(c1p + 64) = c11;
+                            *reinterpret_cast<double2*>(c0p + 128) = c02;
+                            *reinterpret_cast<double2*>(c1p + 128) = c12;
+                            *reinterpret_cast<double2*>(c0p + 192) = c03;
+                            *reinterpret_cast<double2*>(c1p + 192) = c13;
+                            c0p += 256;
+                            c1p += 256;
+                        }
                         for (; K < I0; K += 2) {  // two columns per iteration
                             const double2 b0 = *reinterpret_cast<const double2*>(bp);
                             const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);

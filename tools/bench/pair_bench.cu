@@ -75,7 +75,7 @@ __global__ void bench(double* out, long long* t, int reps, int j) {
                 }
             }
         } else {
-            // row-pair oriented m16n8k8: rows (I, I+1) share A fragments (scaled once), loop over K <= I
+            // (V == 2 or 3) row-pair oriented m16n8k8: rows (I, I+1) share A fragments (scaled once), loop over K <= I
             for (int idx = warp; 2 * idx < nrows; idx += nw) {
                 const int I1 = NT - 1 - 2 * idx, I0 = I1 - 1;  // I0 may be j (invalid) when nrows is odd
                 double2 a1 = *reinterpret_cast<const double2*>(T + tix(I1, j) * 64 + fo);
@@ -87,6 +87,28 @@ __global__ void bench(double* out, long long* t, int reps, int j) {
                     double* c0p = T + tix(I0, j + 1) * 64 + fo;
                     double* c1p = T + tix(I1, j + 1) * 64 + fo;
                     int K = j + 1;
+                    if (V == 3) {
+                        for (; K + 3 <= I0; K += 4) {  // four columns per iteration
+                            const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                            const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);
+                            const double2 b2 = *reinterpret_cast<const double2*>(bp + (2 * K + 3) * 64);
+                            const double2 b3 = *reinterpret_cast<const double2*>(bp + (3 * K + 6) * 64);
+                            bp += (4 * K + 10) * 64;
+                            double2 c00 = *reinterpret_cast<double2*>(c0p), c10 = *reinterpret_cast<double2*>(c1p);
+                            double2 c01 = *reinterpret_cast<double2*>(c0p + 64), c11 = *reinterpret_cast<double2*>(c1p + 64);
+                            double2 c02 = *reinterpret_cast<double2*>(c0p + 128), c12 = *reinterpret_cast<double2*>(c1p + 128);
+                            double2 c03 = *reinterpret_cast<double2*>(c0p + 192), c13 = *reinterpret_cast<double2*>(c1p + 192);
+                            dmma16(c00, c10, a0, a1, b0);
+                            dmma16(c01, c11, a0, a1, b1);
+                            dmma16(c02, c12, a0, a1, b2);
+                            dmma16(c03, c13, a0, a1, b3);
+                            *reinterpret_cast<double2*>(c0p) = c00; *reinterpret_cast<double2*>(c1p) = c10;
+                            *reinterpret_cast<double2*>(c0p + 64) = c01; *reinterpret_cast<double2*>(c1p + 64) = c11;
+                            *reinterpret_cast<double2*>(c0p + 128) = c02; *reinterpret_cast<double2*>(c1p + 128) = c12;
+                            *reinterpret_cast<double2*>(c0p + 192) = c03; *reinterpret_cast<double2*>(c1p + 192) = c13;
+                            c0p += 256; c1p += 256;
+                        }
+                    }
                     for (; K + 1 <= I0; K += 2) {  // two columns per iteration
                         const double2 b0 = *reinterpret_cast<const double2*>(bp);
                         const double2 b1 = *reinterpret_cast<const double2*>(bp + (K + 1) * 64);
@@ -136,20 +158,22 @@ int main() {
     cudaFuncSetAttribute(bench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(bench<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(bench<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     for (int j = 0; j <= 6; j += 3)
         for (int nw = 1; nw <= 4; nw += (nw == 1 ? 2 : 1)) {
             const int npairs = (NT - 1 - j) * (NT - j) / 2;
-            long long r[3]; double h[3][1];
-            for (int v = 0; v < 3; ++v) {
+            long long r[4]; double h[4][1];
+            for (int v = 0; v < 4; ++v) {
                 if (v == 0) bench<0><<<1, 32 * nw, smem>>>(out, t, 200, j);
                 if (v == 1) bench<1><<<1, 32 * nw, smem>>>(out, t, 200, j);
                 if (v == 2) bench<2><<<1, 32 * nw, smem>>>(out, t, 200, j);
+                if (v == 3) bench<3><<<1, 32 * nw, smem>>>(out, t, 200, j);
                 cudaDeviceSynchronize();
                 r[v] = t[0];
                 cudaMemcpy(h[v], out, 8, cudaMemcpyDeviceToHost);
             }
-            printf("j=%d warps=%d pairs=%d : m8n8k4 rows %lld clk (%.0f/pair)  m16n8k8 cols %lld clk (%.0f/pair)  m16n8k8 row pairs %lld (%.0f/pair)  chk %.6e %.6e %.6e %s\n", j, nw,
-                   npairs, r[0], (double)r[0] / npairs * nw, r[1], (double)r[1] / npairs * nw, r[2], (double)r[2] / npairs * nw, h[0][0], h[1][0], h[2][0], cudaGetErrorString(cudaGetLastError()));
+            printf("j=%d warps=%d pairs=%d : m8n8k4 rows %lld clk (%.0f/pair)  m16n8k8 cols %lld clk (%.0f/pair)  m16n8k8 row pairs %lld (%.0f/pair)  x4 cols %lld (%.0f/pair)  chk %.6e %.6e %.6e %.6e %s\n", j, nw,
+                   npairs, r[0], (double)r[0] / npairs * nw, r[1], (double)r[1] / npairs * nw, r[2], (double)r[2] / npairs * nw, r[3], (double)r[3] / npairs * nw, h[0][0], h[1][0], h[2][0], h[3][0], cudaGetErrorString(cudaGetLastError()));
         }
     return 0;
 }
