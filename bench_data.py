@@ -123,3 +123,54 @@ def conic_config4(n=5000, n_zero=500, n_nonneg=4000, n_soc=300, soc_dim=10, nnz_
     x = rng.standard_normal(n)
     return dict(A=A, b=A @ x + s, c=-(A.T @ y), x=x, s=s, y=y, cone_types=cone_types, cone_dims=cone_dims,
                 seed=rng.standard_normal(n))
+
+
+def mpc_config3(T=10_000, nx=6, nu=4, active_frac=0.1, seed=3):
+    """Config 3: one sparse MPC QP, solved by construction.  Stage t = 0..T-1 has state x_t (nx) and input u_t (nu);
+    z = (x_0, u_0, x_1, u_1, ...), n = T (nx + nu).  Q = blkdiag(Qx, R) per stage (SPD); dynamics equalities
+    x_{t+1} = Ad x_t + Bd u_t (x_0 fixed: nx rows), p = T nx; input box constraints -1 <= u <= 1 as 2 nu rows per
+    stage, m = 2 T nu, a fraction ``active_frac`` of the inputs sits on a bound (lam > 0, slack 0), the others are
+    strictly inside (lam = 0).  Returns the reference's LHS (scipy CSC, create_LHS_matrix layout) and the pieces."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n, p, m = T * (nx + nu), T * nx, 2 * T * nu
+    Lx = rng.standard_normal((nx, nx)); Qx = Lx @ Lx.T / nx + 0.5 * np.eye(nx)
+    Lr = rng.standard_normal((nu, nu)); R = Lr @ Lr.T / nu + 0.5 * np.eye(nu)
+    Ad = rng.standard_normal((nx, nx)) / np.sqrt(nx)
+    Ad *= 0.95 / np.abs(np.linalg.eigvals(Ad)).max()
+    Bd = rng.standard_normal((nx, nu)) / np.sqrt(nx)
+    Q = sp.block_diag([sp.csc_matrix(np.block([[Qx, np.zeros((nx, nu))], [np.zeros((nu, nx)), R]]))] * T, format="csc")
+    # equality rows: block t couples stage t-1 (Ad, Bd) and x_t (-I); block 0 is x_0 = given
+    rows, cols, vals = [], [], []
+    s = nx + nu
+    for t in range(T):
+        r0 = t * nx
+        for i in range(nx):
+            rows.append(r0 + i); cols.append(t * s + i); vals.append(-1.0)
+        if t > 0:
+            c0 = (t - 1) * s
+            rr, cc = np.meshgrid(np.arange(nx), np.arange(nx), indexing="ij")
+            rows += list(r0 + rr.ravel()); cols += list(c0 + cc.ravel()); vals += list(Ad.ravel())
+            rr, cc = np.meshgrid(np.arange(nx), np.arange(nu), indexing="ij")
+            rows += list(r0 + rr.ravel()); cols += list(c0 + nx + cc.ravel()); vals += list(Bd.ravel())
+    A = sp.csc_matrix((vals, (rows, cols)), shape=(p, n))
+    # inequality rows: for every input, u <= 1 and -u <= 1
+    ucols = (np.arange(T)[:, None] * s + nx + np.arange(nu)[None, :]).ravel()
+    G = sp.vstack([sp.csc_matrix((np.ones(T * nu), (np.arange(T * nu), ucols)), shape=(T * nu, n)),
+                   sp.csc_matrix((-np.ones(T * nu), (np.arange(T * nu), ucols)), shape=(T * nu, n))]).tocsc()
+    z = rng.standard_normal(n) * 0.3
+    u = rng.uniform(-0.9, 0.9, size=T * nu)
+    act = rng.random(T * nu) < active_frac
+    side = rng.random(T * nu) < 0.5
+    u[act & side] = 1.0
+    u[act & ~side] = -1.0
+    z[ucols] = u
+    lam = np.zeros(m)
+    lam[:T * nu][act & side] = rng.uniform(0.5, 1.5, size=int((act & side).sum()))
+    lam[T * nu:][act & ~side] = rng.uniform(0.5, 1.5, size=int((act & ~side).sum()))
+    h = np.ones(m)
+    D = G @ z - h                                   # exactly 0 on the active rows, < 0 elsewhere
+    nu_ = rng.standard_normal(p)
+    K = sp.bmat([[Q, G.T @ sp.diags(lam), A.T], [G, sp.diags(D), None], [A, None, sp.csc_matrix((p, p))]], format="csc")
+    K.sort_indices()
+    return dict(K=K, Q=Q, G=G, A=A, z=z, lam=lam, nu=nu_, h=h, n=n, m=m, p=p)

@@ -69,6 +69,14 @@ struct ConicState {
     DevBuf w1, w2, w3;
 };
 
+// factorisation kept by diffopt_b200_sparse_setup (banded LU after RCM ordering)
+struct SparseBandState {
+    bool valid = false;
+    int64_t N = 0;
+    int kl = 0, ku = 0;
+    DevBuf AB, ipiv, perm, work;
+};
+
 struct LsqrWork {
     DevBuf u, v, w, x, tmp, scal;  // vectors and a small block of device scalars
 };
@@ -94,6 +102,7 @@ struct diffopt_b200_ctx {
     ConicState conic;
     LsqrWork lsqr;
     CsrDev lsqr_mat;
+    SparseBandState sparse;
 };
 
 #define DO_CUDA(ctx, expr)                                                              \

@@ -70,6 +70,55 @@ __device__ __forceinline__ int pick_T(const CsrView& A) {
     return T;
 }
 
+
+// y_row = (sparse row) . x for every row of A, `epi(row, value)` called once per row (by the first lane of the row's
+// lane group).  Each group of T lanes keeps RU rows in flight at once (RU independent rowptr -> (val, colind) -> x gather
+// chains per lane) so that a persistent grid of a few hundred CTAs still covers the HBM latency on large matrices;
+// consecutive groups take consecutive rows, so val / colind accesses of a warp stay contiguous.
+template <int RU, class F>
+__device__ __forceinline__ void spmv_rows(const Dev& d, const CsrView& A, const double* __restrict__ x, F&& epi) {
+    const int T = pick_T(A);
+    const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
+    for (int base = 0; base < A.nrows; base += ngroups * RU) {
+        int s[RU], len[RU];
+        int maxlen = 0;
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+            const int row = base + r * ngroups + g;
+            s[r] = 0;
+            len[r] = 0;
+            if (row < A.nrows) {
+                s[r] = A.rowptr[row];
+                len[r] = A.rowptr[row + 1] - s[r];
+            }
+            maxlen = max(maxlen, len[r]);
+        }
+        maxlen = __reduce_max_sync(0xffffffffu, maxlen);  // keep the warp converged for the shuffles below
+        double acc[RU];
+#pragma unroll
+        for (int r = 0; r < RU; ++r) acc[r] = 0.0;
+        for (int k = lig; k < maxlen; k += T) {
+            double av[RU];
+            int ci[RU];
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+                const bool ok = k < len[r];
+                av[r] = ok ? A.val[s[r] + k] : 0.0;
+                ci[r] = ok ? A.colind[s[r] + k] : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < RU; ++r) acc[r] = fma(av[r], __ldcg(x + ci[r]), acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+            double t = acc[r];
+            for (int o = T >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            const int row = base + r * ngroups + g;
+            if (row < A.nrows && lig == 0) epi(row, t);
+        }
+    }
+}
+
 // ---- SOC block of Dpi applied to y (symmetric block, so it serves Dpi and Dpi') ------------------
 // group of `T` lanes handles cone `c`; writes out[off .. off+dim)
 __device__ void soc_apply(const ConicOpView& op, int c, bool valid, const double* __restrict__ y, double* out,
@@ -214,21 +263,12 @@ __device__ void dpi_apply(Dev& d, const ConicOpView& op, const double* __restric
 
 __device__ void csr_apply(Dev& d, const CsrView& A, const double* __restrict__ src, double s_src, double* dst,
                           double s_dst, int slot) {
-    const int T = pick_T(A);
-    const int lig = d.lane & (T - 1);
-    const int ngroups = d.gthreads / T;
-    const int g = d.gtid / T;
     double acc = 0.0;
-    for (int base = 0; base < A.nrows; base += ngroups) {
-        int row = base + g;
-        bool valid = row < A.nrows;
-        double t = row_dot(A, row, valid, src, lig, T);
-        if (valid && lig == 0) {
-            t = t * s_src + s_dst * dst[row];
-            dst[row] = t;
-            acc += t * t;
-        }
-    }
+    spmv_rows<4>(d, A, src, [&](int row, double t) {
+        t = t * s_src + s_dst * dst[row];
+        dst[row] = t;
+        acc += t * t;
+    });
     block_partial(d, slot, acc);
 }
 
@@ -243,37 +283,21 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         d.grid.sync();
         const double t3 = __ldcg(src + n + m);
         double acc = 0.0;
-        {   // rows 0..n-1:  (A' wc)_j + c_j t3
-            const int T = pick_T(op.At);
-            const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
-            for (int base = 0; base < n; base += ngroups) {
-                int row = base + g;
-                bool valid = row < n;
-                double t = row_dot(op.At, row, valid, op.wc, lig, T);
-                if (valid && lig == 0) {
-                    t = (t + op.c[row] * t3) * s_src + s_dst * dst[row];
-                    dst[row] = t;
-                    acc += t * t;
-                    dotacc += op.c[row] * __ldcg(src + row);
-                }
-            }
-        }
-        {   // rows n..n+m-1:  -(A t1)_i + t2_i - wc_i + b_i t3
-            const int T = pick_T(op.A);
-            const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
-            for (int base = 0; base < m; base += ngroups) {
-                int row = base + g;
-                bool valid = row < m;
-                double t = row_dot(op.A, row, valid, src, lig, T);
-                if (valid && lig == 0) {
-                    double wci = __ldcg(op.wc + row);
-                    t = (-t + __ldcg(src + n + row) - wci + op.b[row] * t3) * s_src + s_dst * dst[n + row];
-                    dst[n + row] = t;
-                    acc += t * t;
-                    dotacc += op.b[row] * wci;
-                }
-            }
-        }
+        // rows 0..n-1:  (A' wc)_j + c_j t3
+        spmv_rows<4>(d, op.At, op.wc, [&](int row, double t) {
+            t = (t + op.c[row] * t3) * s_src + s_dst * dst[row];
+            dst[row] = t;
+            acc += t * t;
+            dotacc += op.c[row] * __ldcg(src + row);
+        });
+        // rows n..n+m-1:  -(A t1)_i + t2_i - wc_i + b_i t3
+        spmv_rows<4>(d, op.A, src, [&](int row, double t) {
+            const double wci = __ldcg(op.wc + row);
+            t = (-t + __ldcg(src + n + row) - wci + op.b[row] * t3) * s_src + s_dst * dst[n + row];
+            dst[n + row] = t;
+            acc += t * t;
+            dotacc += op.b[row] * wci;
+        });
         block_partial(d, slot, acc);
         block_partial(d, slot + 1, dotacc);
         d.grid.sync();
@@ -286,20 +310,11 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
     } else {
         // r = A u1 - u2 - b u3  -> wc
         const double u3 = __ldcg(src + n + m);
-        {
-            const int T = pick_T(op.A);
-            const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
-            for (int base = 0; base < m; base += ngroups) {
-                int row = base + g;
-                bool valid = row < m;
-                double t = row_dot(op.A, row, valid, src, lig, T);
-                if (valid && lig == 0) {
-                    double u2 = __ldcg(src + n + row);
-                    op.wc[row] = t - u2 - op.b[row] * u3;
-                    dotacc += op.b[row] * u2;
-                }
-            }
-        }
+        spmv_rows<4>(d, op.A, src, [&](int row, double t) {
+            const double u2 = __ldcg(src + n + row);
+            op.wc[row] = t - u2 - op.b[row] * u3;
+            dotacc += op.b[row] * u2;
+        });
         d.grid.sync();
         // out2 = Dpi' r + u2 : first Dpi' r into a second scratch = reuse psd-free path by writing to dst later.
         // We need dst's old value (s_dst * dst), so stage Dpi' r in op.wc's partner buffer: the x-part of dst is
@@ -309,21 +324,13 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         dpi_apply(d, op, op.wc, r2, true);
         d.grid.sync();
         double acc = 0.0;
-        {   // rows 0..n-1: -(A' u2)_j - c_j u3
-            const int T = pick_T(op.At);
-            const int lig = d.lane & (T - 1), ngroups = d.gthreads / T, g = d.gtid / T;
-            for (int base = 0; base < n; base += ngroups) {
-                int row = base + g;
-                bool valid = row < n;
-                double t = row_dot(op.At, row, valid, src + n, lig, T);
-                if (valid && lig == 0) {
-                    t = (-t - op.c[row] * u3) * s_src + s_dst * dst[row];
-                    dst[row] = t;
-                    acc += t * t;
-                    dotacc += op.c[row] * __ldcg(src + row);
-                }
-            }
-        }
+        // rows 0..n-1: -(A' u2)_j - c_j u3
+        spmv_rows<4>(d, op.At, src + n, [&](int row, double t) {
+            t = (-t - op.c[row] * u3) * s_src + s_dst * dst[row];
+            dst[row] = t;
+            acc += t * t;
+            dotacc += op.c[row] * __ldcg(src + row);
+        });
         for (int i = d.gtid; i < m; i += d.gthreads) {
             double t = (__ldcg(r2 + i) + __ldcg(src + n + i)) * s_src + s_dst * dst[n + i];
             dst[n + i] = t;
@@ -356,7 +363,7 @@ __device__ void op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* sr
         conic_apply(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot);
 }
 
-__global__ void __launch_bounds__(LSQR_THREADS) lsqr_kernel(OpArgs o, const double* __restrict__ rhs, LsqrParams prm,
+__global__ void __launch_bounds__(LSQR_THREADS, 4) lsqr_kernel(OpArgs o, const double* __restrict__ rhs, LsqrParams prm,
                                                            LsqrVectors vec) {
     __shared__ double red[64];
     Dev d{cg::this_grid(), vec.partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
@@ -551,7 +558,8 @@ static int coop_grid(diffopt_b200_ctx* ctx, const void* kernel, int64_t work) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LSQR_THREADS, 0);
     if (per_sm < 1) per_sm = 1;
     int64_t want = (work + LSQR_THREADS * 4 - 1) / (LSQR_THREADS * 4);
-    int64_t cap = (int64_t)ctx->sm_count;  // one CTA per SM keeps grid.sync cheap
+    // small problems: one CTA per SM keeps grid.sync cheap; large ones (beyond L2) need every resident CTA to cover HBM latency
+    int64_t cap = (int64_t)ctx->sm_count * (work > (int64_t)4 << 20 ? per_sm : 1);
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     return (int)want;

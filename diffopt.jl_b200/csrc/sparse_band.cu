@@ -1,0 +1,470 @@
+// Sparse direct path for ONE large KKT system with many right-hand sides (BASELINE config 3: MPC-structured QP,
+// N = 240 000, 256 forward directions against one factorisation) -- the `LHS \ RHS` of QuadraticProgram.jl:486-492 for
+// systems far beyond the dense kernels.  The reference refactorises for every direction (:438 runs once per
+// forward_differentiate!); here the factorisation stays in the ctx and every block of right-hand sides reuses it.
+//
+// Method: reverse Cuthill-McKee ordering of the symmetrised pattern on the host (KKT matrices of stage-structured
+// problems become narrow banded), LAPACK band storage built on the device, then
+//   * dgbtf2-style LU with partial pivoting inside the band by one persistent CTA (read phase / barrier / write phase
+//     per column, the active window of the band stays L2 resident), and
+//   * dgbtrs-style sweeps with ONE WARP PER RIGHT-HAND SIDE: the warp keeps a sliding window of its column in shared
+//     memory, prefetches the multipliers of the next column from L2 and never synchronises with other warps, so all
+//     right-hand sides advance in parallel.
+// Partial pivoting keeps this valid for the reference's nonsymmetric LHS = [Q G'L A'; G D 0; A 0 0] with its exact
+// zeros on the diagonal.  A matrix whose RCM bandwidth exceeds BAND_MAX is rejected (-3): a fill-reducing supernodal
+// factorisation for general patterns is the next step.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BAND_MAX = 255;   // kl = ku <= BAND_MAX
+constexpr int F_THREADS = 512;  // factorisation CTA (> BAND_MAX: one thread per entry of the pivot column)
+constexpr int S_WARPS = 4;      // right-hand sides per solve CTA
+constexpr int WIN = 1024;       // sliding window (doubles) per warp: power of two >= kl + ku + 1 + 64 (refilled in 32-chunks)
+
+// ---- host: reverse Cuthill-McKee on the symmetrised pattern ---------------------------------------------------------
+void rcm_order(int64_t N, const std::vector<int64_t>& ptr, const std::vector<int32_t>& adj, std::vector<int32_t>& perm) {
+    std::vector<int32_t> deg((size_t)N);
+    for (int64_t i = 0; i < N; ++i) deg[(size_t)i] = (int32_t)(ptr[(size_t)i + 1] - ptr[(size_t)i]);
+    std::vector<char> seen((size_t)N, 0), mark((size_t)N, 0);
+    std::vector<int32_t> q, nbr;
+    perm.clear();
+    perm.reserve((size_t)N);
+    auto bfs_last = [&](int32_t start) {  // a vertex of the last BFS level with small degree (pseudo-peripheral search)
+        q.assign(1, start);
+        mark[(size_t)start] = 1;
+        for (size_t head = 0; head < q.size(); ++head) {
+            const int32_t v = q[head];
+            for (int64_t k = ptr[(size_t)v]; k < ptr[(size_t)v + 1]; ++k) {
+                const int32_t w = adj[(size_t)k];
+                if (!mark[(size_t)w] && !seen[(size_t)w]) {
+                    mark[(size_t)w] = 1;
+                    q.push_back(w);
+                }
+            }
+        }
+        for (int32_t v : q) mark[(size_t)v] = 0;
+        int32_t best = q.back();
+        for (size_t i = q.size() > 32 ? q.size() - 32 : 0; i < q.size(); ++i)
+            if (deg[(size_t)q[i]] < deg[(size_t)best]) best = q[i];
+        return best;
+    };
+    for (int64_t s0 = 0; s0 < N; ++s0) {
+        if (seen[(size_t)s0]) continue;
+        int32_t start = bfs_last((int32_t)s0);
+        start = bfs_last(start);
+        size_t head = perm.size();
+        perm.push_back(start);
+        seen[(size_t)start] = 1;
+        while (head < perm.size()) {
+            const int32_t v = perm[head++];
+            nbr.clear();
+            for (int64_t k = ptr[(size_t)v]; k < ptr[(size_t)v + 1]; ++k) {
+                const int32_t w = adj[(size_t)k];
+                if (!seen[(size_t)w]) {
+                    seen[(size_t)w] = 1;
+                    nbr.push_back(w);
+                }
+            }
+            std::sort(nbr.begin(), nbr.end(), [&](int32_t a, int32_t b) { return deg[(size_t)a] < deg[(size_t)b]; });
+            perm.insert(perm.end(), nbr.begin(), nbr.end());
+        }
+    }
+    std::reverse(perm.begin(), perm.end());
+}
+
+// ---- device -----------------------------------------------------------------------------------------------------------
+// band storage: AB is ldab x N column major, ldab = 2 kl + ku + 1, A(i, j) at AB[kv + i - j + j * ldab], kv = kl + ku
+__global__ void band_scatter_kernel(int64_t N, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                                    const double* __restrict__ nzval, const int32_t* __restrict__ inv, int trans, int kv, int64_t ldab,
+                                    double* __restrict__ AB) {
+    const int64_t col = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;  // 8 lanes per column of the CSC matrix
+    const int l8 = threadIdx.x & 7;
+    if (col >= N) return;
+    for (int64_t k = colptr[col] - 1 + l8; k < colptr[col + 1] - 1; k += 8) {
+        int64_t i = inv[rowval[k] - 1], j = inv[col];
+        if (trans) {
+            const int64_t t = i;
+            i = j;
+            j = t;
+        }
+        atomicAdd(&AB[j * ldab + kv + i - j], nzval[k]);  // duplicates are summed like SparseArrays does
+    }
+}
+
+// LU with partial pivoting in band storage (LAPACK dgbtf2).  Per column: (1) pivot search, (2) everything a write of
+// this step could clobber is read into registers / shared memory, barrier, (3) writes.
+__global__ void __launch_bounds__(F_THREADS, 1) band_lu_kernel(int N, int kl, int ku, double* __restrict__ AB, int* __restrict__ ipiv,
+                                                               int* info) {
+    __shared__ double s_val[F_THREADS / 32];
+    __shared__ int s_idx[F_THREADS / 32];
+    __shared__ int s_jp;
+    __shared__ double s_piv, s_diag;
+    __shared__ double s_l[BAND_MAX + 1];        // multipliers of the current column
+    __shared__ double s_top[2 * BAND_MAX + 2];  // row j+jp of the window columns (the new pivot row)
+    __shared__ double s_bot[2 * BAND_MAX + 2];  // row j of the window columns (moves to row j+jp)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kv = kl + ku;
+    const size_t ldab = (size_t)(2 * kl + ku + 1);
+    int ju = 0;
+    for (int j = 0; j < N; ++j) {
+        double* colj = AB + (size_t)j * ldab;
+        const int km = min(kl, N - 1 - j);
+        double best = -1.0, mine = 0.0;
+        int bi = 0;
+        if (tid <= km) {
+            mine = colj[kv + tid];
+            best = fabs(mine);
+            bi = tid;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) {
+                best = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            s_val[warp] = best;
+            s_idx[warp] = bi;
+        }
+        if (tid == 0) s_diag = mine;
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < F_THREADS / 32 ? s_val[lane] : -1.0;
+            bi = lane < F_THREADS / 32 ? s_idx[lane] : 0;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) {
+                    best = ov;
+                    bi = oi;
+                }
+            }
+            if (lane == 0) {
+                s_jp = bi;
+                ipiv[j] = j + bi;
+            }
+        }
+        __syncthreads();
+        const int jp = s_jp;
+        if (tid == jp) s_piv = mine;
+        ju = max(ju, min(j + ku + jp, N - 1));
+        const int nc = ju - j;  // window columns j+1 .. ju
+        for (int c = 1 + tid; c <= nc; c += F_THREADS) {
+            const double* colc = AB + (size_t)(j + c) * ldab + kv - c;
+            s_top[c] = colc[jp];
+            s_bot[c] = colc[0];
+        }
+        __syncthreads();
+        const double piv = s_piv;
+        if (piv == 0.0) {  // the whole column below the diagonal is exactly zero: singular
+            if (tid == 0) *info = j + 1;
+            return;
+        }
+        const double rinv = 1.0 / piv;
+        if (tid == 0) colj[kv] = piv;
+        if (tid >= 1 && tid <= km) {
+            const double v = (tid == jp ? s_diag : mine) * rinv;
+            s_l[tid] = v;
+            colj[kv + tid] = v;
+        }
+        __syncthreads();
+        if (nc > 0) {
+            const int rows = km + 1, items = rows * nc;
+            for (int it = tid; it < items; it += F_THREADS) {
+                const int c = 1 + it / rows, i = it - (c - 1) * rows;
+                double* colc = AB + (size_t)(j + c) * ldab + kv - c;
+                const double top = s_top[c];
+                if (i == 0) {
+                    colc[0] = top;
+                } else {
+                    const double old = (i == jp) ? s_bot[c] : colc[i];
+                    colc[i] = fma(-s_l[i], top, old);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *info = 0;
+}
+
+// Y[i, r] = B[perm[i], r]: right-hand sides into the RCM ordering (so that the sweeps stream contiguously)
+__global__ void band_gather_kernel(int64_t N, int64_t nrhs, const int32_t* __restrict__ perm, const double* __restrict__ B,
+                                   double* __restrict__ Y) {
+    const int64_t total = N * nrhs;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / N, i = e - r * N;
+        Y[e] = B[r * N + perm[i]];
+    }
+}
+
+// Solve with the factored band for nrhs right-hand sides, one warp per right-hand side, in place in Y (RCM order):
+//   forward : y <- L^-1 P y   (interchanges ipiv, multipliers below the diagonal)
+//   backward: x <- U^-1 y     (U has bandwidth kv = kl + ku), scattered to X in the ORIGINAL order through perm
+// The warp keeps the active part of its column in a circular shared-memory window that is refilled 32 entries at a
+// time one chunk ahead; multipliers are fetched one column ahead into registers behind an L1 prefetch PF columns
+// ahead; pivots and permutation entries are fetched 32 at a time and broadcast by shuffles.
+// QL = number of 32-row chunks of the L band (kl <= 32 QL); the U band (kv = 2 kl) takes 2 QL chunks.
+template <int QL>
+__global__ void __launch_bounds__(32 * S_WARPS) band_solve_kernel(int N, int kl, int ku, const double* __restrict__ AB,
+                                                                  const int* __restrict__ ipiv, const int32_t* __restrict__ perm, int nrhs,
+                                                                  double* __restrict__ Y, double* __restrict__ X) {
+    __shared__ double s_win[S_WARPS][WIN];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * S_WARPS + warp;
+    if (r >= nrhs) return;
+    double* win = s_win[warp];
+    const int kv = kl + ku;
+    const size_t ldab = (size_t)(2 * kl + ku + 1);
+    double* y = Y + (size_t)r * N;
+    double* x = X + (size_t)r * N;
+    constexpr int MSK = WIN - 1;
+    constexpr int PF = 12;  // L1 prefetch distance in columns
+    const int lines_l = (kl * 8 + 8 + 127) / 128 + 1, lines_u = (kv * 8 + 8 + 127) / 128 + 1;
+    // ---- forward sweep: window holds y[j .. j + kl], refilled from y one 32-chunk ahead
+    int filled = min(N, kl + 1 + 32);  // window holds indices < filled
+    for (int i = lane; i < filled; i += 32) win[i & MSK] = y[i];
+    double chunk = (filled + lane < N) ? y[filled + lane] : 0.0;  // next 32 entries, in flight
+    double lnext[QL];
+#pragma unroll
+    for (int q = 0; q < QL; ++q) {
+        const int i = 1 + lane + 32 * q;
+        lnext[q] = (i <= min(kl, N - 1)) ? AB[kv + i] : 0.0;
+    }
+    int pchunk = 0;  // ipiv[32 c + lane]
+    __syncwarp();
+    for (int j = 0; j < N; ++j) {
+        if ((j & 31) == 0) {
+            pchunk = (j + lane < N) ? ipiv[j + lane] : 0;
+            // the chunk loaded 32 steps ago enters the window, the next one is requested
+            if (j > 0) {
+                if (filled + lane < N) win[(filled + lane) & MSK] = chunk;
+                filled = min(N, filled + 32);
+                chunk = (filled + lane < N) ? y[filled + lane] : 0.0;
+            }
+        }
+        const int p = __shfl_sync(0xffffffffu, pchunk, j & 31);
+        const int lm = min(kl, N - 1 - j);
+        double lcur[QL];
+#pragma unroll
+        for (int q = 0; q < QL; ++q) lcur[q] = lnext[q];
+        if (j + 1 < N) {
+            const double* cn = AB + (size_t)(j + 1) * ldab + kv;
+            const int lmn = min(kl, N - 2 - j);
+#pragma unroll
+            for (int q = 0; q < QL; ++q) {
+                const int i = 1 + lane + 32 * q;
+                lnext[q] = (i <= lmn) ? cn[i] : 0.0;
+            }
+            if (j + PF < N && lane < lines_l) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)(AB + (size_t)(j + PF) * ldab + kv) + lane * 128));
+        }
+        if (lane == 0 && p != j) {
+            const double t0 = win[j & MSK], t1 = win[p & MSK];
+            win[j & MSK] = t1;
+            win[p & MSK] = t0;
+        }
+        __syncwarp();
+        const double bj = win[j & MSK];
+#pragma unroll
+        for (int q = 0; q < QL; ++q) {
+            const int i = 1 + lane + 32 * q;
+            if (i <= lm) win[(j + i) & MSK] = fma(-lcur[q], bj, win[(j + i) & MSK]);
+        }
+        if (lane == 0) y[j] = bj;
+        __syncwarp();
+    }
+    // ---- backward sweep: window holds y[j - kv .. j], refilled downwards one 32-chunk ahead
+    int low = max(0, N - (kv + 1 + 32));  // window holds indices >= low
+    for (int i = low + lane; i < N; i += 32) win[i & MSK] = y[i];
+    chunk = (low - 32 + lane >= 0) ? y[low - 32 + lane] : 0.0;
+    constexpr int UQ = 2 * QL;
+    double unext[UQ];
+    double dnext;
+    {
+        const double* cn = AB + (size_t)(N - 1) * ldab;
+        dnext = cn[kv];
+#pragma unroll
+        for (int q = 0; q < UQ; ++q) {
+            const int i = 1 + lane + 32 * q;
+            unext[q] = (i <= min(kv, N - 1)) ? cn[kv - i] : 0.0;
+        }
+    }
+    int permchunk = 0;
+    __syncwarp();
+    for (int j = N - 1, step = 0; j >= 0; --j, ++step) {
+        if ((step & 31) == 0) {
+            permchunk = (j - lane >= 0) ? perm[j - lane] : 0;
+            if (step > 0) {
+                if (low - 32 + lane >= 0) win[(low - 32 + lane) & MSK] = chunk;
+                low = max(0, low - 32);
+                chunk = (low - 32 + lane >= 0) ? y[low - 32 + lane] : 0.0;
+            }
+        }
+        const int pj = __shfl_sync(0xffffffffu, permchunk, step & 31);
+        const int um = min(kv, j);
+        double ucur[UQ];
+#pragma unroll
+        for (int q = 0; q < UQ; ++q) ucur[q] = unext[q];
+        const double dcur = dnext;
+        if (j > 0) {
+            const double* cn = AB + (size_t)(j - 1) * ldab;
+            dnext = cn[kv];
+            const int umn = min(kv, j - 1);
+#pragma unroll
+            for (int q = 0; q < UQ; ++q) {
+                const int i = 1 + lane + 32 * q;
+                unext[q] = (i <= umn) ? cn[kv - i] : 0.0;
+            }
+            if (j - PF >= 0 && lane < lines_u) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)(AB + (size_t)(j - PF) * ldab) + lane * 128));
+        }
+        __syncwarp();
+        const double xj = win[j & MSK] / dcur;
+#pragma unroll
+        for (int q = 0; q < UQ; ++q) {
+            const int i = 1 + lane + 32 * q;
+            if (i <= um) win[(j - i) & MSK] = fma(-ucur[q], xj, win[(j - i) & MSK]);
+        }
+        if (lane == 0) x[pj] = xj;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval,
+                                             const double* nzval, int32_t trans, int64_t* bandwidth_out) {
+    if (!ctx) return -1;
+    SparseBandState& S = ctx->sparse;
+    S.valid = false;
+    if (N <= 0 || !colptr || !rowval || !nzval) BAD_ARG(ctx, "sparse_setup: bad argument");
+    if (colptr[0] != 1) BAD_ARG(ctx, "sparse_setup: colptr must be 1-based (Julia SparseMatrixCSC)");
+    if (N >= (int64_t)1 << 31) BAD_ARG(ctx, "sparse_setup: N too large");
+    cudaSetDevice(ctx->device);
+    const int64_t nnz = colptr[N] - 1;
+    // symmetrised pattern (without the diagonal) as CSR
+    std::vector<int64_t> ptr((size_t)N + 1, 0);
+    for (int64_t c = 0; c < N; ++c)
+        for (int64_t k = colptr[c] - 1; k < colptr[c + 1] - 1; ++k) {
+            const int64_t r = rowval[k] - 1;
+            if (r < 0 || r >= N) BAD_ARG(ctx, "sparse_setup: row index out of range");
+            if (r != c) {
+                ++ptr[(size_t)r + 1];
+                ++ptr[(size_t)c + 1];
+            }
+        }
+    for (int64_t i = 0; i < N; ++i) ptr[(size_t)i + 1] += ptr[(size_t)i];
+    std::vector<int32_t> adj((size_t)ptr[(size_t)N]);
+    {
+        std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+        for (int64_t c = 0; c < N; ++c)
+            for (int64_t k = colptr[c] - 1; k < colptr[c + 1] - 1; ++k) {
+                const int64_t r = rowval[k] - 1;
+                if (r != c) {
+                    adj[(size_t)fill[(size_t)r]++] = (int32_t)c;
+                    adj[(size_t)fill[(size_t)c]++] = (int32_t)r;
+                }
+            }
+    }
+    std::vector<int32_t> perm;
+    rcm_order(N, ptr, adj, perm);
+    std::vector<int32_t> inv((size_t)N);
+    for (int64_t i = 0; i < N; ++i) inv[(size_t)perm[(size_t)i]] = (int32_t)i;
+    int64_t bw = 0;
+    for (int64_t c = 0; c < N; ++c)
+        for (int64_t k = colptr[c] - 1; k < colptr[c + 1] - 1; ++k) {
+            const int64_t d = (int64_t)inv[(size_t)(rowval[k] - 1)] - inv[(size_t)c];
+            bw = std::max(bw, d < 0 ? -d : d);
+        }
+    if (bandwidth_out) *bandwidth_out = bw;
+    if (bw > BAND_MAX) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "sparse_setup: bandwidth %lld after RCM exceeds %d (general supernodal path not built yet)",
+                 (long long)bw, BAND_MAX);
+        ctx->err = buf;
+        return -3;
+    }
+    const int kl = (int)bw, ku = (int)bw;
+    const int64_t ldab = 2 * kl + ku + 1;
+    const size_t abytes = sizeof(double) * (size_t)ldab * (size_t)N;
+    DO_CUDA(ctx, S.AB.reserve(abytes));
+    DO_CUDA(ctx, S.ipiv.reserve(sizeof(int) * (size_t)N));
+    DO_CUDA(ctx, S.perm.reserve(sizeof(int32_t) * (size_t)N));
+    DO_CUDA(ctx, ctx->in[0].reserve(sizeof(int64_t) * (size_t)(N + 1)));
+    DO_CUDA(ctx, ctx->in[1].reserve(sizeof(int64_t) * (size_t)std::max<int64_t>(nnz, 1)));
+    DO_CUDA(ctx, ctx->in[2].reserve(sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
+    DO_CUDA(ctx, ctx->in[4].reserve(sizeof(int32_t) * (size_t)N));
+    DO_CUDA(ctx, ctx->info.reserve(sizeof(int)));
+    DO_CUDA(ctx, cudaMemcpyAsync(ctx->in[0].ptr, colptr, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, ctx->stream));
+    DO_CUDA(ctx, cudaMemcpyAsync(ctx->in[1].ptr, rowval, sizeof(int64_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    DO_CUDA(ctx, cudaMemcpyAsync(ctx->in[2].ptr, nzval, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    DO_CUDA(ctx, cudaMemcpyAsync(ctx->in[4].ptr, inv.data(), sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    DO_CUDA(ctx, cudaMemcpyAsync(S.perm.ptr, perm.data(), sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    DO_CUDA(ctx, cudaMemsetAsync(S.AB.ptr, 0, abytes, ctx->stream));
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    {
+        const int64_t blocks = (N * 8 + 255) / 256;
+        band_scatter_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(N, ctx->in[0].as<int64_t>(), ctx->in[1].as<int64_t>(),
+                                                                       ctx->in[2].as<double>(), ctx->in[4].as<int32_t>(), trans, kl + ku, ldab,
+                                                                       S.AB.as<double>());
+        ctx->launches++;
+    }
+    band_lu_kernel<<<1, F_THREADS, 0, ctx->stream>>>((int)N, kl, ku, S.AB.as<double>(), S.ipiv.as<int>(), ctx->info.as<int>());
+    ctx->launches++;
+    DO_CUDA(ctx, cudaGetLastError());
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    int hinfo = 0;
+    DO_CUDA(ctx, cudaMemcpyAsync(&hinfo, ctx->info.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    if (hinfo != 0) return hinfo;  // exactly singular: the reference throws SingularException
+    S.N = N;
+    S.kl = kl;
+    S.ku = ku;
+    S.valid = true;
+    return 0;
+}
+
+extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace) {
+    if (!ctx) return -1;
+    SparseBandState& S = ctx->sparse;
+    if (!S.valid) BAD_ARG(ctx, "sparse_solve: no factorisation (call diffopt_b200_sparse_setup first)");
+    if (nrhs <= 0 || !rhs || !x_out) BAD_ARG(ctx, "sparse_solve: bad argument");
+    cudaSetDevice(ctx->device);
+    const size_t bytes = sizeof(double) * (size_t)S.N * (size_t)nrhs;
+    const void* dB = nullptr;
+    void* dX = nullptr;
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[5], rhs, bytes, memspace, &dB));
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[2], x_out, bytes, memspace, &dX));
+    DO_CUDA(ctx, S.work.reserve(bytes));
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    {
+        int64_t gb = ((int64_t)S.N * nrhs + 255) / 256;
+        if (gb > (int64_t)ctx->sm_count * 16) gb = (int64_t)ctx->sm_count * 16;
+        band_gather_kernel<<<(unsigned)gb, 256, 0, ctx->stream>>>(S.N, nrhs, S.perm.as<int32_t>(), (const double*)dB, S.work.as<double>());
+        ctx->launches++;
+    }
+    const int64_t blocks = (nrhs + S_WARPS - 1) / S_WARPS;
+#define BAND_SOLVE(QL)                                                                                                             \
+    band_solve_kernel<QL><<<(unsigned)blocks, 32 * S_WARPS, 0, ctx->stream>>>((int)S.N, S.kl, S.ku, S.AB.as<double>(), S.ipiv.as<int>(), \
+                                                                              S.perm.as<int32_t>(), (int)nrhs, S.work.as<double>(),     \
+                                                                              (double*)dX)
+    if (S.kl <= 32) BAND_SOLVE(1);
+    else if (S.kl <= 64) BAND_SOLVE(2);
+    else if (S.kl <= 128) BAND_SOLVE(4);
+    else BAND_SOLVE(8);
+#undef BAND_SOLVE
+    ctx->launches++;
+    DO_CUDA(ctx, cudaGetLastError());
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    DO_CUDA(ctx, stage_out_finish(ctx, dX, x_out, bytes, memspace));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    return 0;
+}

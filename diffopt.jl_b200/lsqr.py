@@ -55,3 +55,31 @@ def solve_csc(ctx: Context, M, rhs, trans=False):
     if rc > 0:
         raise SingularException(rc)
     return X[:, 0].copy() if one else X
+
+
+class SparseFactorization:
+    """``diffopt_b200_sparse_setup`` / ``_sparse_solve``: one factorisation of a large sparse KKT matrix (or of its
+    adjoint) on the device, reused for any number of right-hand sides -- the direct ``LHS \\ RHS`` of
+    QuadraticProgram.jl:490 for systems beyond the dense kernels (BASELINE config 3)."""
+
+    def __init__(self, ctx: Context, M, trans=False):
+        from ._capi import SingularException
+        self.ctx = ctx
+        self.N = M.shape[0]
+        colptr, rowval, nzval = julia_csc(M)
+        bw = np.zeros(1, dtype=np.int64)
+        rc = ctx.lib.diffopt_b200_sparse_setup(ctx.h, self.N, ptr(colptr), ptr(rowval), ptr(nzval), int(trans), ptr(bw))
+        ctx.check(rc)
+        if rc > 0:
+            raise SingularException(rc)
+        self.bandwidth = int(bw[0])
+        self.factor_ms = ctx.last_kernel_ms
+
+    def solve(self, rhs):
+        rhs = np.asarray(rhs, dtype=np.float64)
+        one = rhs.ndim == 1
+        R = np.asfortranarray(rhs.reshape(self.N, -1))
+        X = np.empty_like(R, order="F")
+        self.ctx.check(self.ctx.lib.diffopt_b200_sparse_solve(self.ctx.h, R.shape[1], ptr(R), ptr(X), HOST))
+        self.solve_ms = self.ctx.last_kernel_ms
+        return X[:, 0].copy() if one else X

@@ -127,6 +127,20 @@ int32_t diffopt_b200_kkt_solve_csc(
     diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
     int32_t trans, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace);
 
+/* ---- sparse direct path: one large KKT system, many right-hand sides (BASELINE config 3) ----------------------
+ *
+ * sparse_setup factorises LHS (SparseMatrixCSC{Float64,Int} in HOST memory, 1-based; trans = 1: LHS') once:
+ * reverse Cuthill-McKee ordering on the host, banded LU with partial pivoting on the device.  The factorisation stays
+ * in the ctx; sparse_solve then solves for nrhs columns (rhs / x_out are N x nrhs column-major, host or device per
+ * memspace) -- `LHS \ RHS` of QuadraticProgram.jl:490 without the reference's refactorisation per direction (:438).
+ * Returns 0; > 0: exactly zero pivot (SingularException); -3: bandwidth after RCM above 255 (not a banded problem).
+ * bandwidth_out (may be NULL) receives the half bandwidth found. */
+int32_t diffopt_b200_sparse_setup(
+    diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+    int32_t trans, int64_t* bandwidth_out);
+int32_t diffopt_b200_sparse_solve(
+    diffopt_b200_ctx* ctx, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace);
+
 /* ---- LSQR (IterativeSolvers.lsqr call sites QuadraticProgram.jl:488, ConicProgram.jl:323,372)
  *
  * min ||M x - rhs|| from x0 = 0 on an explicit sparse matrix in Julia's
