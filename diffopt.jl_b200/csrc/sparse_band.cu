@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int BAND_MAX = 255;   // kl = ku <= BAND_MAX
-constexpr int F_THREADS = 512;  // factorisation CTA (> BAND_MAX: one thread per entry of the pivot column)
+constexpr int F_THREADS = 1024;  // factorisation CTA (> BAND_MAX: one thread per entry of the pivot column)
 constexpr int S_WARPS = 4;      // right-hand sides per solve CTA
 constexpr int WIN = 1024;       // sliding window (doubles) per warp: power of two >= kl + ku + 1 + 64 (refilled in 32-chunks)
 
@@ -97,66 +97,81 @@ __global__ void band_scatter_kernel(int64_t N, const int64_t* __restrict__ colpt
 
 // LU with partial pivoting in band storage (LAPACK dgbtf2).  Per column: (1) pivot search, (2) everything a write of
 // this step could clobber is read into registers / shared memory, barrier, (3) writes.
+// SMEM_WINDOW: the kv + 1 columns the elimination can touch live in a circular shared-memory window of WC columns
+// (column c at slot c & (WC - 1)); column j is written back when it retires and column j + kv + 1 is fetched one step
+// ahead, so the per-column dependency chain runs at shared-memory instead of L2 latency.
+template <bool SMEM_WINDOW>
 __global__ void __launch_bounds__(F_THREADS, 1) band_lu_kernel(int N, int kl, int ku, double* __restrict__ AB, int* __restrict__ ipiv,
-                                                               int* info) {
-    __shared__ double s_val[F_THREADS / 32];
-    __shared__ int s_idx[F_THREADS / 32];
-    __shared__ int s_jp;
-    __shared__ double s_piv, s_diag;
+                                                               int* info, int WC) {
+    extern __shared__ __align__(16) double s_dyn[];
+    __shared__ int s_idx[1 + F_THREADS / 32];
+    __shared__ double s_piv, s_diag, s_rinv;
     __shared__ double s_l[BAND_MAX + 1];        // multipliers of the current column
     __shared__ double s_top[2 * BAND_MAX + 2];  // row j+jp of the window columns (the new pivot row)
     __shared__ double s_bot[2 * BAND_MAX + 2];  // row j of the window columns (moves to row j+jp)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthr = blockDim.x, nwarp = nthr >> 5;  // the launch picks the CTA size by band width (fewer warps: cheaper barriers)
     const int kv = kl + ku;
-    const size_t ldab = (size_t)(2 * kl + ku + 1);
+    const int ldab_i = 2 * kl + ku + 1;
+    const size_t ldab = (size_t)ldab_i;
+    const int wmask = WC - 1;
+    auto col = [&](int c) -> double* { return SMEM_WINDOW ? s_dyn + (size_t)(c & wmask) * ldab : AB + (size_t)c * ldab; };
+    constexpr int PD = 6;  // columns kept in flight by cp.async ahead of the window
+    if (SMEM_WINDOW) {
+        const int ncol = min(N, kv + 1 + PD);
+        for (int e = tid; e < ncol * ldab_i; e += nthr) s_dyn[e] = AB[e];  // columns 0 .. kv+PD sit at their slots
+        __syncthreads();
+    }
     int ju = 0;
     for (int j = 0; j < N; ++j) {
-        double* colj = AB + (size_t)j * ldab;
+        double* colj = col(j);
         const int km = min(kl, N - 1 - j);
-        double best = -1.0, mine = 0.0;
-        int bi = 0;
+        // column j + kv + 1 + PD starts its way into the window (its slot was freed PD + ... steps ago); the column needed
+        // next step (j + kv + 1) was requested PD steps ago
+        if (SMEM_WINDOW) {
+            const int cin = j + kv + 1 + PD;
+            if (cin < N && tid < ldab_i) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(col(cin) + tid);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(AB + (size_t)cin * ldab + tid) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        // pivot search on a packed key: high word of |a| (sign 0, exponent, 12 mantissa bits) | (255 - row): one
+        // redux.max picks the largest entry (to 2^-12 relative, i.e. threshold pivoting at 0.9998) and the first row on ties
+        double mine = 0.0;
+        unsigned key = 0u;
         if (tid <= km) {
             mine = colj[kv + tid];
-            best = fabs(mine);
-            bi = tid;
+            key = ((unsigned)__double2hiint(fabs(mine)) & 0xFFFFFF00u) | (unsigned)(255 - tid);
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) {
-                best = ov;
-                bi = oi;
+        if (km < 32) {
+            if (warp == 0) {
+                key = __reduce_max_sync(0xffffffffu, key);
+                if (lane == 0) s_idx[0] = (int)key;
             }
-        }
-        if (lane == 0) {
-            s_val[warp] = best;
-            s_idx[warp] = bi;
+        } else {
+            key = __reduce_max_sync(0xffffffffu, key);
+            if (lane == 0) s_idx[1 + warp] = (int)key;
+            __syncthreads();
+            if (warp == 0) {
+                key = lane < nwarp ? (unsigned)s_idx[1 + lane] : 0u;
+                key = __reduce_max_sync(0xffffffffu, key);
+                if (lane == 0) s_idx[0] = (int)key;
+            }
         }
         if (tid == 0) s_diag = mine;
         __syncthreads();
-        if (warp == 0) {
-            best = lane < F_THREADS / 32 ? s_val[lane] : -1.0;
-            bi = lane < F_THREADS / 32 ? s_idx[lane] : 0;
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) {
-                    best = ov;
-                    bi = oi;
-                }
-            }
-            if (lane == 0) {
-                s_jp = bi;
-                ipiv[j] = j + bi;
-            }
+        const unsigned kbest = (unsigned)s_idx[0];
+        const int jp = 255 - (int)(kbest & 0xFFu);
+        if (tid == jp) {
+            s_piv = (kbest >> 8) ? mine : 0.0;  // zero or denormal column: singular
+            s_rinv = (kbest >> 8) ? 1.0 / mine : 0.0;
+            ipiv[j] = j + jp;
         }
-        __syncthreads();
-        const int jp = s_jp;
-        if (tid == jp) s_piv = mine;
         ju = max(ju, min(j + ku + jp, N - 1));
         const int nc = ju - j;  // window columns j+1 .. ju
-        for (int c = 1 + tid; c <= nc; c += F_THREADS) {
-            const double* colc = AB + (size_t)(j + c) * ldab + kv - c;
+        for (int c = 1 + tid; c <= nc; c += nthr) {
+            const double* colc = col(j + c) + kv - c;
             s_top[c] = colc[jp];
             s_bot[c] = colc[0];
         }
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) band_lu_kernel(int N, int kl, in
             if (tid == 0) *info = j + 1;
             return;
         }
-        const double rinv = 1.0 / piv;
+        const double rinv = s_rinv;
         if (tid == 0) colj[kv] = piv;
         if (tid >= 1 && tid <= km) {
             const double v = (tid == jp ? s_diag : mine) * rinv;
@@ -174,12 +189,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) band_lu_kernel(int N, int kl, in
             colj[kv + tid] = v;
         }
         __syncthreads();
-        if (nc > 0) {
-            const int rows = km + 1, items = rows * nc;
-            for (int it = tid; it < items; it += F_THREADS) {
-                const int c = 1 + it / rows, i = it - (c - 1) * rows;
-                double* colc = AB + (size_t)(j + c) * ldab + kv - c;
-                const double top = s_top[c];
+        for (int c = 1 + warp; c <= nc; c += nwarp) {  // a warp per window column, lanes down the rows
+            double* colc = col(j + c) + kv - c;
+            const double top = s_top[c];
+            for (int i = lane; i <= km; i += 32) {
                 if (i == 0) {
                     colc[0] = top;
                 } else {
@@ -187,6 +200,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) band_lu_kernel(int N, int kl, in
                     colc[i] = fma(-s_l[i], top, old);
                 }
             }
+        }
+        if (SMEM_WINDOW) {
+            // column j is final: write it back (its slot is reused by column j + WC, requested no earlier than next step)
+            if (tid < ldab_i) AB[(size_t)j * ldab + tid] = colj[tid];
+            asm volatile("cp.async.wait_group %0;" ::"n"(PD - 1) : "memory");  // column j + kv + 1 has landed
         }
         __syncthreads();
     }
@@ -413,8 +431,24 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
                                                                        S.AB.as<double>());
         ctx->launches++;
     }
-    band_lu_kernel<<<1, F_THREADS, 0, ctx->stream>>>((int)N, kl, ku, S.AB.as<double>(), S.ipiv.as<int>(), ctx->info.as<int>());
-    ctx->launches++;
+    {
+        // shared-memory window variant when kv + 2 columns of the band fit (narrow bands, the MPC case)
+        int WC = 1;
+        while (WC < kl + ku + 2 + 6 + 1) WC <<= 1;  // window + columns in flight (PD = 6) + the retiring column
+        const size_t wbytes = sizeof(double) * (size_t)WC * (size_t)ldab;
+        if (wbytes + 16 * 1024 <= ctx->smem_optin && ldab <= F_THREADS) {
+            DO_CUDA(ctx, cudaFuncSetAttribute(band_lu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
+            // one warp per window column in the update: as many warps as the window has columns (at least 8)
+            int thr = 32 * std::min(16, std::max(8, kl + ku + 1));  // measured: 16 warps is the sweet spot (barrier cost vs update width)
+            if (getenv("DIFFOPT_B200_BAND_THREADS")) thr = atoi(getenv("DIFFOPT_B200_BAND_THREADS"));
+            band_lu_kernel<true><<<1, thr, wbytes, ctx->stream>>>((int)N, kl, ku, S.AB.as<double>(), S.ipiv.as<int>(),
+                                                                        ctx->info.as<int>(), WC);
+        } else {
+            band_lu_kernel<false><<<1, F_THREADS, 0, ctx->stream>>>((int)N, kl, ku, S.AB.as<double>(), S.ipiv.as<int>(),
+                                                                    ctx->info.as<int>(), 1);
+        }
+        ctx->launches++;
+    }
     DO_CUDA(ctx, cudaGetLastError());
     DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     int hinfo = 0;
