@@ -10,7 +10,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdiffopt_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = (["-DQP_PROFILE"] if os.environ.get("DIFFOPT_B200_BUILD_PROFILE") else []) + \
-    (["-DQP_ABLATE=" + os.environ["DIFFOPT_B200_BUILD_ABLATE"]] if os.environ.get("DIFFOPT_B200_BUILD_ABLATE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    (["-DQP_ABLATE=" + os.environ["DIFFOPT_B200_BUILD_ABLATE"]] if os.environ.get("DIFFOPT_B200_BUILD_ABLATE") else []) + \
+    (os.environ["DIFFOPT_B200_BUILD_DEFS"].split() if os.environ.get("DIFFOPT_B200_BUILD_DEFS") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
 

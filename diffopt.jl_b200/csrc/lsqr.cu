@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "lsqr.cuh"
@@ -516,6 +518,305 @@ __global__ void __launch_bounds__(LSQR_THREADS) conic_dpi_kernel(ConicOpView op,
     dpi_apply(d, op, t, out, transpose != 0);
 }
 
+
+// ================================================================================================================
+// Streaming LSQR for LARGE conic operators (working set beyond L2): the same iteration as lsqr_kernel, but every
+// phase is its own kernel at full occupancy (the persistent kernel is capped at a few hundred CTAs by grid.sync and
+// its register footprint, far too few loads in flight to cover HBM latency).  All Golub-Kahan scalars, the stop
+// tests and the `done` flag live in a device struct: the host only enqueues iterations in batches and looks at the
+// flag between batches; kernels of an iteration after convergence return at once.  Same arithmetic and the same
+// deterministic reductions (per-CTA partials, fixed-order sums) as the persistent kernel.  No PSD cones here.
+struct LsqrState {
+    double alpha, beta, su, sv, rhobar, phibar, rho, t1, t2, tau;
+    double anorm, acond, ddnorm, res2, xnorm, xxnorm, z, sn2, cs2, rnorm, arnorm, bnorm;
+    double op_src, op_dst;  // scalars of the operator application in flight: dst = op_src * OP(src) + op_dst * dst
+    long long itn;
+    int istop, first, pending, done, more, do_op1;
+};
+
+constexpr int ST_THREADS = 256;
+#ifndef ST_RU
+#define ST_RU 2
+#endif
+constexpr int ST_STRIDE = 2048;  // capacity of one partial slot = upper bound of every streaming grid
+
+#define ST_DEV(partials)                                                                                          \
+    __shared__ double red[64];                                                                                    \
+    Dev d{cg::this_grid(), partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),     \
+          (int)(blockDim.x >> 5), ST_STRIDE, (int)(blockIdx.x * blockDim.x + threadIdx.x),                        \
+          (int)(gridDim.x * blockDim.x)}
+
+__device__ double st_total(const double* partials, int slot, int stride, int count, double* red) {
+    // fixed-order sum of `count` CTA partials by one 256-thread block
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += partials[slot * stride + i];
+    s = warp_sum_all(s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(ST_THREADS) st_init_kernel(int nr, int nc, const double* __restrict__ rhs, LsqrVectors vec, LsqrState* S) {
+    ST_DEV(vec.partials);
+    double acc = 0.0;
+    for (int i = d.gtid; i < nr; i += d.gthreads) {
+        const double t = rhs[i];
+        vec.u[i] = t;
+        acc += t * t;
+    }
+    for (int i = d.gtid; i < nc; i += d.gthreads) {
+        vec.x[i] = 0.0;
+        vec.v[i] = 0.0;
+        vec.w[i] = 0.0;
+    }
+    block_partial(d, 0, acc);
+}
+
+// after st_init_kernel: beta, su; sets up v = A' u (op1 with s_dst = 0)
+__global__ void __launch_bounds__(ST_THREADS) st_init_fin_kernel(LsqrVectors vec, int stride, int cnt0, LsqrState* S) {
+    __shared__ double red[64];
+    const double t0 = st_total(vec.partials, 0, stride, cnt0, red);
+    if (threadIdx.x == 0) {
+        LsqrState s{};
+        s.beta = sqrt(t0);
+        s.su = 1.0;
+        s.sv = 1.0;
+        s.cs2 = -1.0;
+        s.rho = 1.0;
+        s.rnorm = s.beta;
+        s.do_op1 = s.beta > 0 ? 1 : 0;
+        if (s.beta > 0) s.su = 1.0 / s.beta;
+        s.op_src = s.su;
+        s.op_dst = 0.0;
+        s.first = 1;
+        *S = s;
+    }
+}
+
+// x, w update of the previous iteration (LSQR's deferred vector update), ||w / rho||^2 into slot 4
+__global__ void __launch_bounds__(ST_THREADS) st_update_kernel(int nc, LsqrVectors vec, LsqrState* S) {
+    if (S->done) return;
+    ST_DEV(vec.partials);
+    const double sv = S->sv, t1 = S->t1, t2 = S->t2;
+    double dd = 0.0;
+    if (S->first) {
+        for (int i = d.gtid; i < nc; i += d.gthreads) vec.w[i] = sv * vec.v[i];
+    } else {
+        const double irho = 1.0 / S->rho;
+        for (int i = d.gtid; i < nc; i += d.gthreads) {
+            const double wi = vec.w[i];
+            const double dk = wi * irho;
+            dd += dk * dk;
+            vec.x[i] += t1 * wi;
+            vec.w[i] = sv * vec.v[i] + t2 * wi;
+        }
+    }
+    block_partial(d, 4, dd);
+}
+
+// ---- M src (non-transposed), phase 1: wc = Dpi src2
+__global__ void __launch_bounds__(ST_THREADS) st_dpi_kernel(ConicOpView op, const double* __restrict__ y, double* out, int transpose,
+                                                            const LsqrState* S, int which) {
+    if (S->done || (which == 0 ? !S->more : !S->do_op1)) return;
+    ST_DEV(nullptr);
+    dpi_apply(d, op, y, out, transpose != 0);
+}
+
+// ---- M src, phase 2: both sparse products, dst updated in place; slots 0 (norm) and 1 (last-row dot)
+__global__ void __launch_bounds__(ST_THREADS) st_M_rows_kernel(ConicOpView op, const double* __restrict__ src, double* dst, double* partials,
+                                                               const LsqrState* S) {
+    if (S->done || !S->more) return;
+    ST_DEV(partials);
+    const int n = op.n, m = op.m;
+    const double s_src = S->op_src, s_dst = S->op_dst;
+    const double t3 = __ldcg(src + n + m);
+    double acc = 0.0, dotacc = 0.0;
+    spmv_rows<ST_RU>(d, op.At, op.wc, [&](int row, double t) {
+        t = (t + op.c[row] * t3) * s_src + s_dst * dst[row];
+        dst[row] = t;
+        acc += t * t;
+        dotacc += op.c[row] * __ldcg(src + row);
+    });
+    spmv_rows<ST_RU>(d, op.A, src, [&](int row, double t) {
+        const double wci = __ldcg(op.wc + row);
+        t = (-t + __ldcg(src + n + row) - wci + op.b[row] * t3) * s_src + s_dst * dst[n + row];
+        dst[n + row] = t;
+        acc += t * t;
+        dotacc += op.b[row] * wci;
+    });
+    block_partial(d, 0, acc);
+    block_partial(d, 1, dotacc);
+}
+
+// ---- after M v: last row of u, pending stop tests, beta, scalars of the transposed application
+__global__ void __launch_bounds__(ST_THREADS) st_mid_kernel(int N, LsqrVectors vec, int stride, int cnt_rows, int cnt_upd, LsqrParams prm,
+                                                            LsqrState* S) {
+    if (S->done) return;
+    __shared__ double red[64];
+    const double tot0 = st_total(vec.partials, 0, stride, cnt_rows, red);
+    const double tot1 = st_total(vec.partials, 1, stride, cnt_rows, red);
+    const double tot4 = st_total(vec.partials, 4, stride, cnt_upd, red);
+    if (threadIdx.x != 0) return;
+    LsqrState s = *S;
+    double unorm2 = tot0;
+    if (s.more) {
+        const double last = -tot1 * s.op_src + s.op_dst * vec.u[N - 1];
+        vec.u[N - 1] = last;
+        unorm2 += last * last;
+    }
+    if (s.pending) {
+        s.ddnorm += tot4;
+        s.acond = s.anorm * sqrt(s.ddnorm);
+        const double test1 = s.rnorm / s.bnorm;
+        const double test2 = s.arnorm / (s.anorm * s.rnorm);
+        const double test3 = 1.0 / s.acond;
+        const double t1_ = test1 / (1.0 + s.anorm * s.xnorm / s.bnorm);
+        const double rtol = prm.btol + prm.atol * s.anorm * s.xnorm / s.bnorm;
+        const double ctol = prm.conlim > 0 ? 1.0 / prm.conlim : 0.0;
+        if (s.itn >= prm.maxiter) s.istop = 7;
+        if (1.0 + test3 <= 1.0) s.istop = 6;
+        if (1.0 + test2 <= 1.0) s.istop = 5;
+        if (1.0 + t1_ <= 1.0) s.istop = 4;
+        if (test3 <= ctol) s.istop = 3;
+        if (test2 <= prm.atol) s.istop = 2;
+        if (test1 <= rtol) s.istop = 1;
+        s.pending = 0;
+    }
+    s.first = 0;
+    if (s.istop > 0 || !s.more) {
+        s.done = 1;
+        *S = s;
+        return;
+    }
+    s.itn += 1;
+    s.beta = sqrt(unorm2);
+    if (s.beta > 0) {
+        s.su = 1.0 / s.beta;
+        s.anorm = sqrt(s.anorm * s.anorm + s.alpha * s.alpha + s.beta * s.beta);
+        s.op_src = s.su;
+        s.op_dst = -s.beta * s.sv;
+        s.do_op1 = 1;
+    } else {
+        s.su = 1.0;
+        s.do_op1 = 0;
+    }
+    *S = s;
+}
+
+// ---- M' src, phase 1: wc = A src1 - src2 - b src3 ; slot 3 = b . src2
+__global__ void __launch_bounds__(ST_THREADS) st_Mt_A_kernel(ConicOpView op, const double* __restrict__ src, double* partials,
+                                                             const LsqrState* S) {
+    if (S->done || !S->do_op1) return;
+    ST_DEV(partials);
+    const int n = op.n, m = op.m;
+    const double u3 = __ldcg(src + n + m);
+    double dotacc = 0.0;
+    spmv_rows<ST_RU>(d, op.A, src, [&](int row, double t) {
+        const double u2 = __ldcg(src + n + row);
+        op.wc[row] = t - u2 - op.b[row] * u3;
+        dotacc += op.b[row] * u2;
+    });
+    block_partial(d, 3, dotacc);
+}
+
+// ---- M' src, phase 3 (after Dpi' wc -> r2): rows of A' and the elementwise block; slots 2 (norm) and 5 (c . src1)
+__global__ void __launch_bounds__(ST_THREADS) st_Mt_rows_kernel(ConicOpView op, const double* __restrict__ src, double* dst, double* partials,
+                                                                const LsqrState* S) {
+    if (S->done || !S->do_op1) return;
+    ST_DEV(partials);
+    const int n = op.n, m = op.m;
+    const double s_src = S->op_src, s_dst = S->op_dst;
+    const double u3 = __ldcg(src + n + m);
+    const double* r2 = op.wc + m;
+    double acc = 0.0, dotacc = 0.0;
+    spmv_rows<ST_RU>(d, op.At, src + n, [&](int row, double t) {
+        t = (-t - op.c[row] * u3) * s_src + s_dst * dst[row];
+        dst[row] = t;
+        acc += t * t;
+        dotacc += op.c[row] * __ldcg(src + row);
+    });
+    for (int i = d.gtid; i < m; i += d.gthreads) {
+        const double t = (__ldcg(r2 + i) + __ldcg(src + n + i)) * s_src + s_dst * dst[n + i];
+        dst[n + i] = t;
+        acc += t * t;
+    }
+    block_partial(d, 2, acc);
+    block_partial(d, 5, dotacc);
+}
+
+// ---- after M' u: last row of v, alpha, plane rotations (or, at start-up, the initial scalars)
+__global__ void __launch_bounds__(ST_THREADS) st_end_kernel(int N, LsqrVectors vec, int stride, int cnt_a, int cnt_rows, LsqrParams prm,
+                                                            LsqrState* S, int startup) {
+    if (S->done) return;
+    __shared__ double red[64];
+    const double tot2 = st_total(vec.partials, 2, stride, cnt_rows, red);
+    const double tot3 = st_total(vec.partials, 3, stride, cnt_a, red);
+    const double tot5 = st_total(vec.partials, 5, stride, cnt_rows, red);
+    if (threadIdx.x != 0) return;
+    LsqrState s = *S;
+    if (s.do_op1) {
+        const double last = (tot3 + tot5) * s.op_src + s.op_dst * vec.v[N - 1];
+        vec.v[N - 1] = last;
+        s.alpha = sqrt(tot2 + last * last);
+        if (startup) {
+            if (s.alpha > 0) s.sv = 1.0 / s.alpha;
+        } else {
+            s.sv = s.alpha > 0 ? 1.0 / s.alpha : 1.0;
+        }
+    }
+    if (startup) {
+        s.arnorm = s.alpha * s.beta;
+        s.bnorm = s.beta;
+        s.rhobar = s.alpha;
+        s.phibar = s.beta;
+        s.more = s.itn < prm.maxiter ? 1 : 0;
+        s.op_src = s.sv;
+        s.op_dst = -s.alpha * s.su;
+        if (s.arnorm == 0.0) s.done = 1;
+        *S = s;
+        return;
+    }
+    const double rhobar1 = s.rhobar;
+    s.rho = hypot(rhobar1, s.beta);
+    const double cs = rhobar1 / s.rho, sn = s.beta / s.rho;
+    const double theta = sn * s.alpha;
+    s.rhobar = -cs * s.alpha;
+    const double phi = cs * s.phibar;
+    s.phibar = sn * s.phibar;
+    s.tau = sn * phi;
+    s.t1 = phi / s.rho;
+    s.t2 = -theta / s.rho;
+    const double delta = s.sn2 * s.rho, gambar = -s.cs2 * s.rho, rhs_ = phi - delta * s.z;
+    const double zbar = rhs_ / gambar;
+    s.xnorm = sqrt(s.xxnorm + zbar * zbar);
+    const double gamma = hypot(gambar, theta);
+    s.cs2 = gambar / gamma;
+    s.sn2 = theta / gamma;
+    s.z = rhs_ / gamma;
+    s.xxnorm += s.z * s.z;
+    s.rnorm = sqrt(s.phibar * s.phibar + s.res2);
+    s.arnorm = s.alpha * fabs(s.tau);
+    s.pending = 1;
+    s.more = s.itn < prm.maxiter ? 1 : 0;
+    s.op_src = s.sv;
+    s.op_dst = -s.alpha * s.su;
+    *S = s;
+}
+
+__global__ void st_stats_kernel(const LsqrState* S, double* stats) {
+    stats[0] = (double)S->istop;
+    stats[1] = (double)S->itn;
+    stats[2] = S->rnorm;
+    stats[3] = S->arnorm;
+    stats[4] = S->anorm;
+    stats[5] = S->acond;
+    stats[6] = S->xnorm;
+}
+
 CsrView view_of(const DevBuf& rp, const DevBuf& ci, const DevBuf& v, int64_t nrows, int64_t ncols) {
     return CsrView{(int)nrows, (int)ncols, rp.as<int>(), ci.as<int>(), v.as<double>()};
 }
@@ -606,6 +907,70 @@ int32_t lsqr_run_csr(diffopt_b200_ctx* ctx, const CsrDev& M, bool trans, const d
     return lsqr_launch(ctx, o, M.nnz + M.nrows + M.ncols, rhs_dev, prm, x_dev, stats_host7);
 }
 
+static int32_t lsqr_stream_conic(diffopt_b200_ctx* ctx, const double* rhs_dev, LsqrParams prm, double* x_dev, double* stats_host7) {
+    ConicState& cs = ctx->conic;
+    LsqrWork& wk = ctx->lsqr;
+    ConicOpView op = conic_view(ctx);
+    const int n = (int)cs.n, m = (int)cs.m, N = n + m + 1;
+    const size_t dsz = sizeof(double);
+    DO_CUDA(ctx, wk.u.reserve(dsz * (size_t)N));
+    DO_CUDA(ctx, wk.v.reserve(dsz * (size_t)N));
+    DO_CUDA(ctx, wk.w.reserve(dsz * (size_t)N));
+    const int stride = ST_STRIDE;
+    DO_CUDA(ctx, wk.tmp.reserve(dsz * (size_t)NSLOTS * (size_t)stride));
+    DO_CUDA(ctx, wk.scal.reserve(dsz * 8 + sizeof(LsqrState) + 64));
+    double* stats = wk.scal.as<double>();
+    LsqrState* S = reinterpret_cast<LsqrState*>(stats + 8);
+    LsqrVectors vec{wk.u.as<double>(), wk.v.as<double>(), wk.w.as<double>(), x_dev, wk.tmp.as<double>(), stats};
+    auto blocks_for = [&](int64_t items) {
+        int64_t b = (items + ST_THREADS - 1) / ST_THREADS;
+        if (b > stride) b = stride;
+        if (b < 1) b = 1;
+        return (unsigned)b;
+    };
+    const unsigned g_vec = blocks_for(N), g_dpi = blocks_for(std::max<int64_t>(m, (int64_t)cs.nsoc * 8));
+    const unsigned g_rows = blocks_for(((int64_t)n + m) * 8), g_a = blocks_for((int64_t)m * 8);
+    cudaStream_t st = ctx->stream;
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    st_init_kernel<<<g_vec, ST_THREADS, 0, st>>>(N, N, rhs_dev, vec, S);
+    st_init_fin_kernel<<<1, ST_THREADS, 0, st>>>(vec, stride, (int)g_vec, S);
+    auto apply_Mt = [&](int startup) {  // v = su M' u + op_dst v
+        st_Mt_A_kernel<<<g_a, ST_THREADS, 0, st>>>(op, vec.u, vec.partials, S);
+        st_dpi_kernel<<<g_dpi, ST_THREADS, 0, st>>>(op, op.wc, op.wc + m, 1, S, 1);
+        st_Mt_rows_kernel<<<g_rows, ST_THREADS, 0, st>>>(op, vec.u, vec.v, vec.partials, S);
+        st_end_kernel<<<1, ST_THREADS, 0, st>>>(N, vec, stride, (int)g_a, (int)g_rows, prm, S, startup);
+        ctx->launches += 4;
+    };
+    apply_Mt(1);
+    ctx->launches += 2;
+    LsqrState hs{};
+    const long long batch = 16;
+    for (long long it = 0; it <= prm.maxiter; it += batch) {
+        for (long long k = 0; k < batch; ++k) {
+            st_update_kernel<<<g_vec, ST_THREADS, 0, st>>>(N, vec, S);
+            st_dpi_kernel<<<g_dpi, ST_THREADS, 0, st>>>(op, vec.v + n, op.wc, 0, S, 0);
+            st_M_rows_kernel<<<g_rows, ST_THREADS, 0, st>>>(op, vec.v, vec.u, vec.partials, S);
+            st_mid_kernel<<<1, ST_THREADS, 0, st>>>(N, vec, stride, (int)g_rows, (int)g_vec, prm, S);
+            ctx->launches += 4;
+            apply_Mt(0);
+        }
+        DO_CUDA(ctx, cudaMemcpyAsync(&hs, S, sizeof hs, cudaMemcpyDeviceToHost, st));
+        DO_CUDA(ctx, cudaStreamSynchronize(st));
+        if (hs.done) break;
+    }
+    st_stats_kernel<<<1, 1, 0, st>>>(S, stats);
+    ctx->launches++;
+    DO_CUDA(ctx, cudaGetLastError());
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    double stv[7];
+    DO_CUDA(ctx, cudaMemcpyAsync(stv, stats, sizeof stv, cudaMemcpyDeviceToHost, st));
+    DO_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    if (stats_host7) memcpy(stats_host7, stv, sizeof stv);
+    return 0;
+}
+
 int32_t lsqr_run_conic(diffopt_b200_ctx* ctx, const double* rhs_dev, LsqrParams prm, double* x_dev,
                        double* stats_host7) {
     ConicState& s = ctx->conic;
@@ -615,6 +980,11 @@ int32_t lsqr_run_conic(diffopt_b200_ctx* ctx, const double* rhs_dev, LsqrParams 
     o.conic_trans = 0;
     o.nrows = o.ncols = (int)(s.n + s.m + 1);
     int64_t work = s.A.nnz * 2 + s.n + 2 * s.m + s.psd_sumd2 * 8;
+    // large operators without PSD cones: one kernel per phase at full occupancy (see lsqr_stream_conic)
+    const char* mode = getenv("DIFFOPT_B200_LSQR");
+    const bool want_stream = mode ? strcmp(mode, "stream") == 0 : work > ((int64_t)4 << 20);
+    if (want_stream && s.npsd == 0 && !(mode && strcmp(mode, "persistent") == 0))
+        return lsqr_stream_conic(ctx, rhs_dev, prm, x_dev, stats_host7);
     return lsqr_launch(ctx, o, work, rhs_dev, prm, x_dev, stats_host7);
 }
 
