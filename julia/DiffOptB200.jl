@@ -85,6 +85,40 @@ function DiffOpt.QuadraticProgram.solve_system(s::B200Solver, LHS, RHS::Abstract
     return x
 end
 
+"""
+    SparseFactorization(ctx, LHS)            # LHS::SparseMatrixCSC or its Adjoint
+
+One device factorisation of a large sparse KKT matrix (RCM ordering + banded LU with partial pivoting), reused for any
+number of right-hand sides: `F \\ RHS` with `RHS::Matrix` (N x nrhs).  Replaces the per-direction `LHS' \\ RHS` of
+`forward_differentiate!` (QuadraticProgram.jl:438) when many directions are differentiated against one solution.
+"""
+struct SparseFactorization
+    ctx::Context
+    n::Int
+    bandwidth::Int
+    function SparseFactorization(ctx::Context, LHS)
+        A, trans = _csc(LHS)
+        bw = Ref{Int64}(0)
+        GC.@preserve A begin
+            rc = ccall((:diffopt_b200_sparse_setup, LIB), Int32,
+                       (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Ptr{Int64}),
+                       ctx.handle, size(A, 1), A.colptr, A.rowval, A.nzval, trans, bw)
+        end
+        check(ctx, rc)
+        return new(ctx, size(A, 1), Int(bw[]))
+    end
+end
+
+function Base.:\(F::SparseFactorization, RHS::StridedVecOrMat{Float64})
+    X = similar(RHS)
+    GC.@preserve RHS X begin
+        rc = ccall((:diffopt_b200_sparse_solve, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int32),
+                   F.ctx.handle, size(RHS, 2), RHS, X, HOST)
+    end
+    check(F.ctx, rc)
+    return X
+end
+
 "ModelConstructor that keeps the B200 solver attached although the wrapper rebuilds the backend (moi_wrapper.jl:619-657)."
 function qp_model_constructor(ctx::Context)
     return () -> begin
