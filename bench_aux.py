@@ -155,6 +155,8 @@ def main():
     if "4x" in todo:
         run_conic(ctx, "4x: config-4 generator scaled 200x (n=1e6, m=1.5e6, nnz(A)=1.5e7): A exceeds L2",
                   bench_data.conic_config4(n=1_000_000, n_zero=100_000, n_nonneg=800_000, n_soc=60_000), iters=200, cpu_iters=0)
+    if "5b" in todo:
+        run_psd_batch(ctx)
     if "5" in todo:
         import scipy.sparse as sp
         from oracle import cones as ocones
@@ -174,6 +176,8 @@ def main():
         x = ocones.vec_symm(X)
         model = cm.ConicModel(ctx, A, A @ x + s, -(A.T @ y), [ocones.ZERO, ocones.PSD], [dd, k])
         model.set_variable_primal(x); model.set_constraint_primal(s); model.set_constraint_dual(y)
+        model.vp()
+        model.gradient_cache = False   # time the second setup: buffers allocated, modules loaded
         model.vp()
         setup_ms = model.setup_ms
         t = rng.normal(size=dd + k)
@@ -197,6 +201,42 @@ def main():
                           "cpu_baseline": {"eigh_ms": cpu_eig_ms, "dpi_apply_ms_incl_eigh": cpu_apply_ms, "kind": "port",
                                            "sample": "numpy eigh + operator-form apply; the reference's dense 20100^2 Jacobian "
                                                      "(3.2 GB, ~1e12 flop) is not formed"}}), flush=True)
+
+
+def run_psd_batch(ctx):
+    """Batched micro-config of SURVEY 8(d) config 5: 512 PSD cones of side 16 / 32, eigendecompositions in one launch."""
+    import scipy.sparse as sp
+    import diffopt_b200
+    from oracle import cones as ocones
+    cm = diffopt_b200.submodule("conic")
+    rng = np.random.default_rng(55)
+    for side in (16, 32):
+        mats = []
+        for _ in range(512):
+            Xm = rng.normal(size=(side, side))
+            mats.append((Xm + Xm.T) / 2)
+        dims = [side * (side + 1) // 2] * 512
+        k = sum(dims)
+        y = np.concatenate([ocones.vec_symm(m) for m in mats])
+        model = cm.ConicModel(ctx, (-sp.identity(k)).tocsc(), np.zeros(k), np.zeros(k), [ocones.PSD] * 512, dims)
+        model.set_variable_primal(np.zeros(k)); model.set_constraint_primal(np.zeros(k)); model.set_constraint_dual(y)
+        model.vp()
+        model.gradient_cache = False   # second setup: buffers allocated, kernels warm
+        model.vp()
+        setup_ms = model.setup_ms
+        t = rng.normal(size=k)
+        model.dpi_apply(t)
+        model.dpi_apply(t)
+        ap = ctx.last_kernel_ms
+        t0 = time.perf_counter()
+        for m_ in mats:
+            np.linalg.eigh(m_)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        print(json.dumps({"config": f"5b: 512 PSD cones of side {side} (batched eigendecomposition + B + pi)",
+                          "setup_ms_incl_eigendecomposition": setup_ms, "eig_per_s": 512 / (setup_ms * 1e-3),
+                          "dpi_apply_ms": ap,
+                          "cpu_baseline": {"eigh_512_ms": cpu_ms, "kind": "port", "cores": 1,
+                                           "sample": "numpy.linalg.eigh in a loop"}}), flush=True)
 
 
 if __name__ == "__main__":

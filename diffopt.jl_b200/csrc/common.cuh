@@ -63,6 +63,7 @@ struct ConicState {
     DevBuf psd_off, psd_d, psd_uoff;  // per PSD cone: row offset, side d, offset into U/B storage
     DevBuf psd_U, psd_Bm, psd_ident;  // eigenvectors (col-major d x d), B matrix, identity flag
     DevBuf psd_work;                  // scratch 3 * sum d^2
+    DevBuf psd_lam, psd_loff;         // eigenvalues (+ shifts) and per-cone offsets into them (+ small-cone list)
     int64_t npsd = 0, psd_maxd = 0, psd_sumd2 = 0;
     std::vector<int64_t> h_psd_off, h_psd_d, h_psd_uoff;
     // work vectors for M apply / LSQR
@@ -171,6 +172,7 @@ struct QpSolveArgs {
     int* info;
     long long* prof;  // optional per-phase clock counters of CTA 0 (DIFFOPT_B200_PROFILE=1)
 };
+int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const std::vector<long long>& h_uoff);
 int32_t qp_batch_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a);
 int32_t qp_param_grads_launch(diffopt_b200_ctx* ctx, int64_t B, int n, int m, int p, const double* z,
                               const double* lam, const double* nu, const double* rev, int reduce,

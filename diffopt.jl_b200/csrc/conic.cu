@@ -59,162 +59,7 @@ __global__ void cone_soc_kernel(int nsoc, const int* __restrict__ off, const int
     }
 }
 
-// ---- PSD cones: one CTA per cone; parallel-order cyclic Jacobi on X = unvec(v) -----------------------
-constexpr int PSD_THREADS = 1024;
-constexpr double PSD_EIG_THRESHOLD = 1e-4;  // MathOptSetDistances' `λ < 1e-4`
-
-__global__ void __launch_bounds__(PSD_THREADS) psd_eig_kernel(const int* __restrict__ poff, const int* __restrict__ pd,
-                                                              const long long* __restrict__ uoff,
-                                                              const double* __restrict__ v, double* Awork, double* U,
-                                                              double* Bm, int* ident, double* vp, double* lam_out,
-                                                              int* sweeps_out) {
-    const int c = blockIdx.x;
-    const int d = pd[c], off = poff[c];
-    double* A = Awork + uoff[c];
-    double* V = U + uoff[c];
-    double* Bc = Bm + uoff[c];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double cs_c[512], cs_s[512];
-    __shared__ int pp[512], qq[512];
-    __shared__ double red[32];
-    __shared__ double s_off, s_tot;
-    __shared__ int s_allpos;
-    const long long dd = (long long)d * d;
-    for (long long e = tid; e < dd; e += nt) {
-        int i = (int)(e % d), j = (int)(e / d);
-        int r = i < j ? i : j, cc = i < j ? j : i;
-        A[e] = v[off + (long long)cc * (cc + 1) / 2 + r];
-        V[e] = i == j ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    const int de = d + (d & 1);     // players (padded to even)
-    const int npairs = de / 2;      // <= 512  (d <= 1024)
-    int sweep = 0;
-    for (; sweep < 40; ++sweep) {
-        // off-diagonal norm
-        double lo = 0.0, lt = 0.0;
-        for (long long e = tid; e < dd; e += nt) {
-            int i = (int)(e % d), j = (int)(e / d);
-            double a = A[e];
-            lt += a * a;
-            if (i != j) lo += a * a;
-        }
-        for (int q = 16; q > 0; q >>= 1) {
-            lo += __shfl_xor_sync(0xffffffffu, lo, q);
-            lt += __shfl_xor_sync(0xffffffffu, lt, q);
-        }
-        if ((tid & 31) == 0) red[tid >> 5] = lo;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0;
-            for (int w = 0; w < nt / 32; ++w) s += red[w];
-            s_off = s;
-        }
-        __syncthreads();
-        if ((tid & 31) == 0) red[tid >> 5] = lt;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0;
-            for (int w = 0; w < nt / 32; ++w) s += red[w];
-            s_tot = s;
-        }
-        __syncthreads();
-        if (s_off <= 1e-30 * s_tot || s_tot == 0.0) break;
-        for (int r = 0; r < de - 1; ++r) {
-            for (int k = tid; k < npairs; k += nt) {
-                int p, q;
-                if (k == 0) {
-                    p = r % (de - 1);
-                    q = de - 1;
-                } else {
-                    p = (r + k) % (de - 1);
-                    q = (r + (de - 1) - k) % (de - 1);
-                }
-                if (p > q) { int t = p; p = q; q = t; }
-                double cr = 1.0, sr = 0.0;
-                if (q < d) {
-                    double apq = A[p + (long long)q * d];
-                    if (apq != 0.0) {
-                        double app = A[p + (long long)p * d], aqq = A[q + (long long)q * d];
-                        double theta = (aqq - app) / (2.0 * apq);
-                        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        cr = 1.0 / sqrt(t * t + 1.0);
-                        sr = t * cr;
-                    }
-                } else {
-                    q = -1;
-                }
-                pp[k] = p; qq[k] = q; cs_c[k] = cr; cs_s[k] = sr;
-            }
-            __syncthreads();
-            // columns: A <- A J, V <- V J
-            for (long long e = tid; e < (long long)npairs * d; e += nt) {
-                int i = (int)(e % d), k = (int)(e / d);
-                int p = pp[k], q = qq[k];
-                if (q < 0) continue;
-                double cr = cs_c[k], sr = cs_s[k];
-                double ap = A[i + (long long)p * d], aq = A[i + (long long)q * d];
-                A[i + (long long)p * d] = cr * ap - sr * aq;
-                A[i + (long long)q * d] = sr * ap + cr * aq;
-                double vp_ = V[i + (long long)p * d], vq = V[i + (long long)q * d];
-                V[i + (long long)p * d] = cr * vp_ - sr * vq;
-                V[i + (long long)q * d] = sr * vp_ + cr * vq;
-            }
-            __syncthreads();
-            // rows: A <- J' A
-            for (long long e = tid; e < (long long)npairs * d; e += nt) {
-                int k = (int)(e % npairs), j = (int)(e / npairs);
-                int p = pp[k], q = qq[k];
-                if (q < 0) continue;
-                double cr = cs_c[k], sr = cs_s[k];
-                double ap = A[p + (long long)j * d], aq = A[q + (long long)j * d];
-                A[p + (long long)j * d] = cr * ap - sr * aq;
-                A[q + (long long)j * d] = sr * ap + cr * aq;
-            }
-            __syncthreads();
-        }
-    }
-    if (tid == 0) {
-        int allpos = 1;
-        for (int i = 0; i < d; ++i)
-            if (!(A[i + (long long)i * d] >= 0.0)) allpos = 0;
-        s_allpos = allpos;
-        ident[c] = allpos;
-        if (sweeps_out) sweeps_out[c] = sweep;
-    }
-    __syncthreads();
-    // B matrix from the eigenvalues (no sorting needed: F is invariant under permuting eigenpairs)
-    for (long long e = tid; e < dd; e += nt) {
-        int i = (int)(e % d), j = (int)(e / d);
-        double li = A[i + (long long)i * d], lj = A[j + (long long)j * d];
-        bool ni = li < PSD_EIG_THRESHOLD, nj = lj < PSD_EIG_THRESHOLD;
-        double b;
-        if (!ni && !nj) b = 1.0;
-        else if (ni && nj) b = 0.0;
-        else {
-            double lp = ni ? fmax(lj, 0.0) : fmax(li, 0.0);      // positive side
-            double lm = ni ? -fmin(li, 0.0) : -fmin(lj, 0.0);    // negative side
-            b = lp / (lm + lp);
-        }
-        Bc[e] = b;
-    }
-    if (lam_out)
-        for (int i = tid; i < d; i += nt) lam_out[off + i] = A[i + (long long)i * d];
-    // vp = vec(U max(L,0) U')
-    const int tri = d * (d + 1) / 2;
-    for (int e = tid; e < tri; e += nt) {
-        int cc = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while ((long long)(cc + 1) * (cc + 2) / 2 <= e) ++cc;
-        while ((long long)cc * (cc + 1) / 2 > e) --cc;
-        int r = e - cc * (cc + 1) / 2;
-        double acc = 0.0;
-        for (int k = 0; k < d; ++k) {
-            double l = A[k + (long long)k * d];
-            if (l > 0.0) acc += V[r + (long long)k * d] * l * V[cc + (long long)k * d];
-        }
-        vp[off + e] = acc;
-    }
-}
+// ---- PSD cones: eigendecomposition, B and pi(v) live in psd_eig.cu ------------------------------------
 
 __global__ void conic_fwd_rhs_kernel(int n, int m, long long nnz, const long long* __restrict__ rows,
                                      const long long* __restrict__ cols, const double* __restrict__ vals,
@@ -481,13 +326,8 @@ int32_t diffopt_b200_conic_setup(diffopt_b200_ctx* ctx, int64_t n, int64_t m, co
                                                           S.vp.as<double>());
         ctx->launches++;
     }
-    if (S.npsd > 0) {
-        psd_eig_kernel<<<(unsigned)S.npsd, PSD_THREADS, 0, ctx->stream>>>(
-            S.psd_off.as<int>(), S.psd_d.as<int>(), S.psd_uoff.as<long long>(), S.v.as<double>(),
-            S.psd_work.as<double>(), S.psd_U.as<double>(), S.psd_Bm.as<double>(), S.psd_ident.as<int>(),
-            S.vp.as<double>(), nullptr, nullptr);
-        ctx->launches++;
-    }
+    if (S.npsd > 0)
+        if (int32_t rc = psd_eig_launch(ctx, psd_d, psd_uoff)) return rc;
     DO_CUDA(ctx, cudaGetLastError());
     DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

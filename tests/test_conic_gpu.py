@@ -234,6 +234,59 @@ def test_psd_maxcut_200(ctx):
         assert rel(model.dpi_apply(t, transpose=tr), want) <= 1e-8
 
 
+def _psd_only_model(ctx, mats):
+    """One PSD cone per matrix in `mats`, A = -I (rows = variables), s = 0, y = vec(mat) => v = vec(mat)."""
+    cm = diffopt_b200.submodule("conic")
+    dims = [m.shape[0] * (m.shape[0] + 1) // 2 for m in mats]
+    k = sum(dims)
+    y = np.concatenate([ocones.vec_symm(m) for m in mats])
+    A = (-sp.identity(k)).tocsc()
+    model = cm.ConicModel(ctx, A, np.zeros(k), np.zeros(k), [ocones.PSD] * len(mats), dims)
+    model.set_variable_primal(np.zeros(k)); model.set_constraint_primal(np.zeros(k)); model.set_constraint_dual(y)
+    return model, y, dims
+
+
+@pytest.mark.parametrize("case", ["pm_pairs", "degenerate", "zero_and_one", "odd_sizes", "block_path", "batch512"])
+def test_psd_eigensolver_edge_cases(ctx, case):
+    """The Jacobi eigensolver behind Dpi for PSD cones (diff_opt.jl:509-519 -> MOSD, eigen): spectra with +l/-l
+    pairs (the reference's own 2x2 case has them), repeated eigenvalues, the zero matrix, side 1, odd sides, sides
+    on both sides of the shared-memory / block-Jacobi switch, and a batch of 512 small cones in one launch."""
+    rng = np.random.default_rng(17)
+
+    def with_spectrum(lams):
+        Qm, _ = np.linalg.qr(rng.normal(size=(len(lams), len(lams))))
+        Xm = (Qm * np.asarray(lams, float)) @ Qm.T
+        return (Xm + Xm.T) / 2
+
+    if case == "pm_pairs":
+        mats = [np.array([[0.0, 1.0], [1.0, 0.0]]), with_spectrum([3, -3, 2, -2, 1, -1, 0.5, -0.5]),
+                with_spectrum([5, -5] * 10)]
+    elif case == "degenerate":
+        mats = [with_spectrum([2.0] * 5 + [-1.0] * 4), with_spectrum([1.0, 1.0, 1.0, -1.0, -1.0, 0.0, 0.0]),
+                np.diag([1.0, -2.0, 3.0, -4.0])]
+    elif case == "zero_and_one":
+        mats = [np.zeros((3, 3)), np.array([[-2.0]]), np.array([[0.7]]), np.eye(4), -np.eye(5)]
+    elif case == "odd_sizes":
+        mats = [with_spectrum(rng.normal(size=d)) for d in (3, 5, 17, 33, 63)]
+    elif case == "block_path":
+        mats = [with_spectrum(rng.normal(size=d)) for d in (119, 121, 150)] + [with_spectrum([4, -4] * 64 + [1e-3, -1e-3])]
+    else:
+        mats = [with_spectrum(rng.normal(size=d)) for d in ([16] * 256 + [32] * 256)]
+    model, v, dims = _psd_only_model(ctx, mats)
+    types = [ocones.PSD] * len(mats)
+    want_vp = ocones.pi(v, types, dims)
+    assert np.linalg.norm(model.vp() - want_vp) <= 1e-11 * max(1.0, np.linalg.norm(want_vp))
+    t = rng.normal(size=v.size)
+    for tr in (False, True):
+        want = ocones.Dpi_apply(v, types, dims, t, transpose=tr)
+        got = model.dpi_apply(t, transpose=tr)
+        # per cone: a +l/-l pair makes B entries depend on l1/(l1+l2) only, so the tolerance can stay tight
+        o = 0
+        for k_ in dims:
+            assert np.linalg.norm(got[o:o + k_] - want[o:o + k_]) <= 1e-9 * max(1.0, np.linalg.norm(want[o:o + k_]))
+            o += k_
+
+
 def test_streaming_lsqr_matches_persistent_kernel(ctx, monkeypatch):
     """Large conic operators use the multi-kernel (streaming) LSQR; it must reproduce the persistent kernel and the
     oracle on the same problem.  This M is singular and LSQR's iterates are sensitive (the persistent kernel and the
