@@ -155,6 +155,11 @@ def main():
     if "4x" in todo:
         run_conic(ctx, "4x: config-4 generator scaled 200x (n=1e6, m=1.5e6, nnz(A)=1.5e7): A exceeds L2",
                   bench_data.conic_config4(n=1_000_000, n_zero=100_000, n_nonneg=800_000, n_soc=60_000), iters=200, cpu_iters=0)
+    if "4xb" in todo:
+        run_conic(ctx, "4xb: scaled 200x like 4x, but stage-structured sparsity (row i touches variables within +-2000 of "
+                       "i n/m, as in MPC / network / PDE-constrained programs): x gathers have locality",
+                  bench_data.conic_config4(n=1_000_000, n_zero=100_000, n_nonneg=800_000, n_soc=60_000, col_window=2000),
+                  iters=200, cpu_iters=0)
     if "5b" in todo:
         run_psd_batch(ctx)
     if "5" in todo:

@@ -92,7 +92,8 @@ def lp_config1(n=200, m=100, n_active=60, seed=1):
                 z=z, lam=lam, nu=np.zeros(0), seed=rng.standard_normal(n))
 
 
-def conic_config4(n=5000, n_zero=500, n_nonneg=4000, n_soc=300, soc_dim=10, nnz_per_row=10, seed=4, psd_sides=()):
+def conic_config4(n=5000, n_zero=500, n_nonneg=4000, n_soc=300, soc_dim=10, nnz_per_row=10, seed=4, psd_sides=(),
+                  col_window=None):
     """Config 4: sparse conic program solved by construction (Moreau decomposition):
     zeta ~ N(0,1)^m, s = Pi_K(zeta), y = s - zeta in K*, x ~ N(0,1)^n, b = A x + s, c = -A'y,
     so v = y - s = -zeta.  Returns A (scipy CSC, the reference's A = -coefficients), b, c, x, s, y,
@@ -106,7 +107,11 @@ def conic_config4(n=5000, n_zero=500, n_nonneg=4000, n_soc=300, soc_dim=10, nnz_
         [d * (d + 1) // 2 for d in psd_sides]
     m = int(sum(cone_dims))
     rows = np.repeat(np.arange(m), nnz_per_row)
-    cols = rng.integers(0, n, size=m * nnz_per_row)
+    if col_window is None:      # uniformly random columns
+        cols = rng.integers(0, n, size=m * nnz_per_row)
+    else:                       # stage-structured variant: row i touches variables within +-col_window of i n / m
+        centre = (rows.astype(np.int64) * n) // m
+        cols = (centre + rng.integers(-col_window, col_window + 1, size=m * nnz_per_row)) % n
     vals = rng.standard_normal(m * nnz_per_row)
     A = sp.csc_matrix((vals, (rows, cols)), shape=(m, n))
     A.sum_duplicates()

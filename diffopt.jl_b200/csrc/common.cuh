@@ -47,6 +47,9 @@ struct CsrDev {  // device CSR (0-based, int32 indices) of a sparse matrix and o
     int64_t nrows = 0, ncols = 0, nnz = 0;
     DevBuf rowptr, colind, val;     // A   (nrows x ncols)
     DevBuf t_rowptr, t_colind, t_val;  // A'  (ncols x nrows)
+    // row blocks for the streaming SpMV (lsqr.cu): block k = rows [blk[k], blk[k+1]) holding <= ST_CHUNK nonzeros
+    DevBuf blk, t_blk;
+    int64_t nblk = 0, t_nblk = 0;
 };
 
 struct ConicState {

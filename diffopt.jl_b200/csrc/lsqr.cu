@@ -535,10 +535,82 @@ struct LsqrState {
 };
 
 constexpr int ST_THREADS = 256;
-#ifndef ST_RU
-#define ST_RU 2
-#endif
+constexpr int SP_THREADS = 128;                   // threads of a streaming-SpMV CTA (8 CTAs per SM)
+constexpr int ST_NPT = 8;                         // nonzeros per thread in flight
+constexpr int ST_CHUNK = SP_THREADS * ST_NPT;     // nonzeros per row block
 constexpr int ST_STRIDE = 2048;  // capacity of one partial slot = upper bound of every streaming grid
+
+// Row-block ("CSR-stream") SpMV for matrices beyond L2.  The host cuts the rows into blocks of <= ST_CHUNK
+// nonzeros (and <= SP_THREADS rows, or one longer row) and stores (first row, first nonzero) per block.  A CTA owns a
+// CONTIGUOUS range of blocks, so the part of x it gathers from slides slowly and stays in L1 when the matrix has any
+// locality (the kernels keep shared memory small to leave L1 its capacity).  Per block: ST_NPT independent, fully
+// coalesced (val, colind) loads per thread -- no dependence on row pointers, so the HBM pipe stays full regardless of
+// the row lengths -- then the x gathers (read-only path) with the row's epilogue operands loaded underneath them
+// (`pre(b, row)`), products parked in shared memory, one row per thread reduced in storage order (deterministic),
+// `epi(b, row, value, operands)` once per row.
+// sel(b, A, x, lb): matrix, gather vector and local block index of global block b.
+template <class Sel, class Pre, class Epi>
+__device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double* red, Sel&& sel, Pre&& pre, Epi&& epi) {
+    const int tid = threadIdx.x;
+    const int per = (nblk_total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int b_end = min(nblk_total, ((int)blockIdx.x + 1) * per);
+    for (int b = blockIdx.x * per; b < b_end; ++b) {
+        const CsrView* A;
+        const double* x;
+        int lb;
+        sel(b, A, x, lb);
+        const int2 d0 = __ldg(reinterpret_cast<const int2*>(A->blk) + lb);
+        const int2 d1 = __ldg(reinterpret_cast<const int2*>(A->blk) + lb + 1);
+        const int r0 = d0.x, s = d0.y, r1 = d1.x, cnt = d1.y - d0.y;
+        if (cnt > ST_CHUNK) {  // one long row: whole CTA, fixed-order reduction
+            double acc = 0.0;
+            for (int k = tid; k < cnt; k += SP_THREADS)
+                acc = fma(__ldcs(A->val + s + k), __ldg(x + __ldcs(A->colind + s + k)), acc);
+            acc = warp_sum_all(acc);
+            if ((tid & 31) == 0) red[32 + (tid >> 5)] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int w = 0; w < SP_THREADS / 32; ++w) t += red[32 + w];
+                epi(b, r0, t, pre(b, r0));
+            }
+        } else {
+            double av[ST_NPT];
+            int ci[ST_NPT];
+#pragma unroll
+            for (int u = 0; u < ST_NPT; ++u) {
+                const int k = tid + u * SP_THREADS;
+                av[u] = 0.0;
+                ci[u] = 0;
+                if (k < cnt) {
+                    av[u] = __ldcs(A->val + s + k);
+                    ci[u] = __ldcs(A->colind + s + k);
+                }
+            }
+            const int row = r0 + tid;
+            int ra = 0, rb = 0;
+            if (row < r1) {
+                ra = __ldg(A->rowptr + row) - s;
+                rb = __ldg(A->rowptr + row + 1) - s;
+            }
+            double xv[ST_NPT];
+#pragma unroll
+            for (int u = 0; u < ST_NPT; ++u) xv[u] = (tid + u * SP_THREADS < cnt) ? __ldg(x + ci[u]) : 0.0;
+            double4 opnd = make_double4(0.0, 0.0, 0.0, 0.0);
+            if (row < r1) opnd = pre(b, row);
+#pragma unroll
+            for (int u = 0; u < ST_NPT; ++u)
+                if (tid + u * SP_THREADS < cnt) prod[tid + u * SP_THREADS] = av[u] * xv[u];
+            __syncthreads();
+            if (row < r1) {
+                double t = 0.0;
+                for (int k = ra; k < rb; ++k) t += prod[k];
+                epi(b, row, t, opnd);
+            }
+        }
+        __syncthreads();  // prod / red are free again
+    }
+}
 
 #define ST_DEV(partials)                                                                                          \
     __shared__ double red[64];                                                                                    \
@@ -627,7 +699,7 @@ __global__ void __launch_bounds__(ST_THREADS) st_dpi_kernel(ConicOpView op, cons
 }
 
 // ---- M src, phase 2: both sparse products, dst updated in place; slots 0 (norm) and 1 (last-row dot)
-__global__ void __launch_bounds__(ST_THREADS) st_M_rows_kernel(ConicOpView op, const double* __restrict__ src, double* dst, double* partials,
+__global__ void __launch_bounds__(SP_THREADS, 8) st_M_rows_kernel(ConicOpView op, const double* __restrict__ src, double* dst, double* partials,
                                                                const LsqrState* S) {
     if (S->done || !S->more) return;
     ST_DEV(partials);
@@ -635,19 +707,31 @@ __global__ void __launch_bounds__(ST_THREADS) st_M_rows_kernel(ConicOpView op, c
     const double s_src = S->op_src, s_dst = S->op_dst;
     const double t3 = __ldcg(src + n + m);
     double acc = 0.0, dotacc = 0.0;
-    spmv_rows<ST_RU>(d, op.At, op.wc, [&](int row, double t) {
-        t = (t + op.c[row] * t3) * s_src + s_dst * dst[row];
-        dst[row] = t;
-        acc += t * t;
-        dotacc += op.c[row] * __ldcg(src + row);
-    });
-    spmv_rows<ST_RU>(d, op.A, src, [&](int row, double t) {
-        const double wci = __ldcg(op.wc + row);
-        t = (-t + __ldcg(src + n + row) - wci + op.b[row] * t3) * s_src + s_dst * dst[n + row];
-        dst[n + row] = t;
-        acc += t * t;
-        dotacc += op.b[row] * wci;
-    });
+    const int nbt = op.At.nblk;
+    __shared__ double prod[ST_CHUNK];
+    spmv_stream(
+        nbt + op.A.nblk, prod, red,
+        [&](int b, const CsrView*& A, const double*& x, int& lb) {
+            if (b < nbt) { A = &op.At; x = op.wc; lb = b; }
+            else { A = &op.A; x = src; lb = b - nbt; }
+        },
+        [&](int b, int row) {
+            return b < nbt ? make_double4(op.c[row], dst[row], __ldcg(src + row), 0.0)
+                           : make_double4(__ldcg(op.wc + row), __ldcg(src + n + row), op.b[row], dst[n + row]);
+        },
+        [&](int b, int row, double t, const double4& o) {
+            if (b < nbt) {  // rows 0..n-1:  (A' wc)_j + c_j t3
+                t = (t + o.x * t3) * s_src + s_dst * o.y;
+                dst[row] = t;
+                acc += t * t;
+                dotacc += o.x * o.z;
+            } else {        // rows n..n+m-1:  -(A t1)_i + t2_i - wc_i + b_i t3
+                t = (-t + o.y - o.x + o.z * t3) * s_src + s_dst * o.w;
+                dst[n + row] = t;
+                acc += t * t;
+                dotacc += o.z * o.x;
+            }
+        });
     block_partial(d, 0, acc);
     block_partial(d, 1, dotacc);
 }
@@ -708,23 +792,27 @@ __global__ void __launch_bounds__(ST_THREADS) st_mid_kernel(int N, LsqrVectors v
 }
 
 // ---- M' src, phase 1: wc = A src1 - src2 - b src3 ; slot 3 = b . src2
-__global__ void __launch_bounds__(ST_THREADS) st_Mt_A_kernel(ConicOpView op, const double* __restrict__ src, double* partials,
+__global__ void __launch_bounds__(SP_THREADS, 8) st_Mt_A_kernel(ConicOpView op, const double* __restrict__ src, double* partials,
                                                              const LsqrState* S) {
     if (S->done || !S->do_op1) return;
     ST_DEV(partials);
     const int n = op.n, m = op.m;
     const double u3 = __ldcg(src + n + m);
     double dotacc = 0.0;
-    spmv_rows<ST_RU>(d, op.A, src, [&](int row, double t) {
-        const double u2 = __ldcg(src + n + row);
-        op.wc[row] = t - u2 - op.b[row] * u3;
-        dotacc += op.b[row] * u2;
-    });
+    __shared__ double prod[ST_CHUNK];
+    spmv_stream(
+        op.A.nblk, prod, red,
+        [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.A; x = src; lb = b; },
+        [&](int, int row) { return make_double4(__ldcg(src + n + row), op.b[row], 0.0, 0.0); },
+        [&](int, int row, double t, const double4& o) {
+            op.wc[row] = t - o.x - o.y * u3;
+            dotacc += o.y * o.x;
+        });
     block_partial(d, 3, dotacc);
 }
 
 // ---- M' src, phase 3 (after Dpi' wc -> r2): rows of A' and the elementwise block; slots 2 (norm) and 5 (c . src1)
-__global__ void __launch_bounds__(ST_THREADS) st_Mt_rows_kernel(ConicOpView op, const double* __restrict__ src, double* dst, double* partials,
+__global__ void __launch_bounds__(SP_THREADS, 8) st_Mt_rows_kernel(ConicOpView op, const double* __restrict__ src, double* dst, double* partials,
                                                                 const LsqrState* S) {
     if (S->done || !S->do_op1) return;
     ST_DEV(partials);
@@ -733,12 +821,17 @@ __global__ void __launch_bounds__(ST_THREADS) st_Mt_rows_kernel(ConicOpView op, 
     const double u3 = __ldcg(src + n + m);
     const double* r2 = op.wc + m;
     double acc = 0.0, dotacc = 0.0;
-    spmv_rows<ST_RU>(d, op.At, src + n, [&](int row, double t) {
-        t = (-t - op.c[row] * u3) * s_src + s_dst * dst[row];
-        dst[row] = t;
-        acc += t * t;
-        dotacc += op.c[row] * __ldcg(src + row);
-    });
+    __shared__ double prod[ST_CHUNK];
+    spmv_stream(
+        op.At.nblk, prod, red,
+        [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.At; x = src + n; lb = b; },
+        [&](int, int row) { return make_double4(op.c[row], dst[row], __ldcg(src + row), 0.0); },
+        [&](int, int row, double t, const double4& o) {
+            t = (-t - o.x * u3) * s_src + s_dst * o.y;
+            dst[row] = t;
+            acc += t * t;
+            dotacc += o.x * o.z;
+        });
     for (int i = d.gtid; i < m; i += d.gthreads) {
         const double t = (__ldcg(r2 + i) + __ldcg(src + n + i)) * s_src + s_dst * dst[n + i];
         dst[n + i] = t;
@@ -817,8 +910,10 @@ __global__ void st_stats_kernel(const LsqrState* S, double* stats) {
     stats[6] = S->xnorm;
 }
 
-CsrView view_of(const DevBuf& rp, const DevBuf& ci, const DevBuf& v, int64_t nrows, int64_t ncols) {
-    return CsrView{(int)nrows, (int)ncols, rp.as<int>(), ci.as<int>(), v.as<double>()};
+CsrView view_of(const DevBuf& rp, const DevBuf& ci, const DevBuf& v, int64_t nrows, int64_t ncols,
+                const DevBuf* blk = nullptr, int64_t nblk = 0) {
+    return CsrView{(int)nrows, (int)ncols, rp.as<int>(), ci.as<int>(), v.as<double>(),
+                   blk ? blk->as<int>() : nullptr, (int)nblk};
 }
 
 }  // namespace
@@ -828,8 +923,8 @@ ConicOpView conic_view(diffopt_b200_ctx* ctx) {
     ConicOpView o{};
     o.n = (int)s.n;
     o.m = (int)s.m;
-    o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n);
-    o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m);
+    o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n, &s.A.blk, s.A.nblk);
+    o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m, &s.A.t_blk, s.A.t_nblk);
     o.b = s.b.as<double>();
     o.c = s.c.as<double>();
     o.diag = s.nn_scale.as<double>();
@@ -929,16 +1024,24 @@ static int32_t lsqr_stream_conic(diffopt_b200_ctx* ctx, const double* rhs_dev, L
         return (unsigned)b;
     };
     const unsigned g_vec = blocks_for(N), g_dpi = blocks_for(std::max<int64_t>(m, (int64_t)cs.nsoc * 8));
-    const unsigned g_rows = blocks_for(((int64_t)n + m) * 8), g_a = blocks_for((int64_t)m * 8);
+    // SpMV kernels: persistent over the row blocks, every resident CTA slot filled exactly once (8 CTAs per SM)
+    auto blocks_spmv = [&](int64_t nblk) {
+        int per_sm = 8;
+        if (const char* e = getenv("DIFFOPT_B200_SPMV_CTAS")) per_sm = std::max(1, atoi(e));
+        int64_t b = std::min<int64_t>(nblk, (int64_t)ctx->sm_count * per_sm);
+        return (unsigned)std::max<int64_t>(1, std::min<int64_t>(b, stride));
+    };
+    const unsigned g_rows = blocks_spmv(cs.A.nblk + cs.A.t_nblk), g_a = blocks_spmv(cs.A.nblk);
+    const unsigned g_trows = blocks_spmv(std::max<int64_t>(cs.A.t_nblk, ((int64_t)m + SP_THREADS * 8 - 1) / (SP_THREADS * 8)));
     cudaStream_t st = ctx->stream;
     DO_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     st_init_kernel<<<g_vec, ST_THREADS, 0, st>>>(N, N, rhs_dev, vec, S);
     st_init_fin_kernel<<<1, ST_THREADS, 0, st>>>(vec, stride, (int)g_vec, S);
     auto apply_Mt = [&](int startup) {  // v = su M' u + op_dst v
-        st_Mt_A_kernel<<<g_a, ST_THREADS, 0, st>>>(op, vec.u, vec.partials, S);
+        st_Mt_A_kernel<<<g_a, SP_THREADS, 0, st>>>(op, vec.u, vec.partials, S);
         st_dpi_kernel<<<g_dpi, ST_THREADS, 0, st>>>(op, op.wc, op.wc + m, 1, S, 1);
-        st_Mt_rows_kernel<<<g_rows, ST_THREADS, 0, st>>>(op, vec.u, vec.v, vec.partials, S);
-        st_end_kernel<<<1, ST_THREADS, 0, st>>>(N, vec, stride, (int)g_a, (int)g_rows, prm, S, startup);
+        st_Mt_rows_kernel<<<g_trows, SP_THREADS, 0, st>>>(op, vec.u, vec.v, vec.partials, S);
+        st_end_kernel<<<1, ST_THREADS, 0, st>>>(N, vec, stride, (int)g_a, (int)g_trows, prm, S, startup);
         ctx->launches += 4;
     };
     apply_Mt(1);
@@ -949,7 +1052,7 @@ static int32_t lsqr_stream_conic(diffopt_b200_ctx* ctx, const double* rhs_dev, L
         for (long long k = 0; k < batch; ++k) {
             st_update_kernel<<<g_vec, ST_THREADS, 0, st>>>(N, vec, S);
             st_dpi_kernel<<<g_dpi, ST_THREADS, 0, st>>>(op, vec.v + n, op.wc, 0, S, 0);
-            st_M_rows_kernel<<<g_rows, ST_THREADS, 0, st>>>(op, vec.v, vec.u, vec.partials, S);
+            st_M_rows_kernel<<<g_rows, SP_THREADS, 0, st>>>(op, vec.v, vec.u, vec.partials, S);
             st_mid_kernel<<<1, ST_THREADS, 0, st>>>(N, vec, stride, (int)g_rows, (int)g_vec, prm, S);
             ctx->launches += 4;
             apply_Mt(0);
@@ -1039,6 +1142,32 @@ int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, c
             colind[(size_t)dst] = (int)j;
             val[(size_t)dst] = nzval[k];
         }
+    // row blocks of the streaming SpMV: <= ST_CHUNK nonzeros and <= SP_THREADS rows each, or one longer row
+    auto row_blocks = [](const std::vector<int>& rp, int64_t nr, std::vector<int>& blk) {
+        blk.clear();
+        blk.push_back(0);
+        int64_t r = 0;
+        while (r < nr) {
+            const int s0 = rp[(size_t)r];
+            int64_t e = r;
+            while (e < nr && rp[(size_t)e + 1] - s0 <= ST_CHUNK && e - r < SP_THREADS) ++e;
+            if (e == r) e = r + 1;
+            blk.push_back((int)e);
+            r = e;
+        }
+        // interleave (first row, first nonzero) per block: one 8-byte load per block end for the issuing thread
+        std::vector<int> d2(blk.size() * 2);
+        for (size_t k = 0; k < blk.size(); ++k) {
+            d2[2 * k] = blk[k];
+            d2[2 * k + 1] = rp[(size_t)blk[k]];
+        }
+        blk.swap(d2);
+    };
+    std::vector<int> blk, t_blk;
+    row_blocks(rowptr, nrows, blk);
+    row_blocks(t_rowptr, ncols, t_blk);
+    out.nblk = (int64_t)blk.size() / 2 - 1;
+    out.t_nblk = (int64_t)t_blk.size() / 2 - 1;
     out.nrows = nrows;
     out.ncols = ncols;
     out.nnz = nnz;
@@ -1053,6 +1182,8 @@ int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, c
     DO_CUDA(ctx, up(out.t_rowptr, t_rowptr.data(), sizeof(int) * t_rowptr.size()));
     DO_CUDA(ctx, up(out.t_colind, t_colind.data(), sizeof(int) * t_colind.size()));
     DO_CUDA(ctx, up(out.t_val, nzval, sizeof(double) * (size_t)nnz));
+    DO_CUDA(ctx, up(out.blk, blk.data(), sizeof(int) * blk.size()));
+    DO_CUDA(ctx, up(out.t_blk, t_blk.data(), sizeof(int) * t_blk.size()));
     DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die at return
     return 0;
 }

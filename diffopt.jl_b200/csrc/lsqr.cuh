@@ -13,6 +13,8 @@ struct CsrView {
     const int* rowptr;
     const int* colind;
     const double* val;
+    const int* blk;  // row blocks of the streaming SpMV (nblk + 1 entries), see CsrDev
+    int nblk;
 };
 
 struct ConicOpView {

@@ -5,7 +5,8 @@ ctx = diffopt_b200.Context(0)
 cm = diffopt_b200.submodule("conic")
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-d = bench_data.conic_config4(n=5000 * scale, n_zero=500 * scale, n_nonneg=4000 * scale, n_soc=300 * scale)
+win = int(sys.argv[3]) if len(sys.argv) > 3 else None
+d = bench_data.conic_config4(n=5000 * scale, n_zero=500 * scale, n_nonneg=4000 * scale, n_soc=300 * scale, col_window=win)
 model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
 model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
 model.tolerances = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=iters)
