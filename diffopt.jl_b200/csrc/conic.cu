@@ -6,7 +6,7 @@
 
 #include "lsqr.cuh"
 
-ConicOpView conic_view(diffopt_b200_ctx* ctx);
+ConicOpView conic_view(diffopt_b200_ctx* ctx, bool stream_blocks);
 
 namespace {
 

@@ -16,11 +16,39 @@ namespace {
 constexpr int LSQR_THREADS = 256;
 constexpr int NSLOTS = 8;
 
+#ifdef LSQR_PROF
+__device__ long long g_prof[8192];
+__device__ int g_prof_n;
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 struct Dev {
     cg::grid_group grid;
     double* partials;  // [NSLOTS][nblk]
     double* red;       // shared scratch (>= 2 * warps doubles)
     int tid, lane, warp, nwarp, nblk, gtid, gthreads;
+    bool cluster = false;  // the whole grid is ONE thread-block cluster: hardware barrier instead of grid.sync()
+    // All-CTA barrier with release/acquire ordering of global memory.  The cluster barrier costs ~0.2 us (and
+    // invalidates L1, so plain loads after it see the other CTAs' stores); cooperative grid.sync() costs 2-3 us.
+    __device__ __forceinline__ void sync() {
+#ifdef LSQR_PROF
+        if (gtid == 0 && g_prof_n < 8190) g_prof[g_prof_n++] = gtimer();
+#endif
+        sync_();
+#ifdef LSQR_PROF
+        if (gtid == 0 && g_prof_n < 8190) g_prof[g_prof_n++] = gtimer();
+#endif
+    }
+    __device__ __forceinline__ void sync_() {
+        if (cluster)
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        else
+            grid.sync();
+    }
 };
 
 __device__ __forceinline__ double warp_sum_all(double v) {
@@ -121,6 +149,97 @@ __device__ __forceinline__ void spmv_rows(const Dev& d, const CsrView& A, const 
     }
 }
 
+constexpr int SP_THREADS = 128;                   // threads of a streaming-SpMV CTA (8 CTAs per SM)
+constexpr int ST_NPT = 8;                         // nonzeros per thread in flight
+constexpr int ST_CHUNK = SP_THREADS * ST_NPT;     // nonzeros per row block
+// cluster-synchronised kernel (small operators): one cluster of CL_THREADS-thread CTAs, same SpMV with bigger blocks
+#ifndef CL_THREADS_DEF
+#define CL_THREADS_DEF 512
+#endif
+constexpr int CL_THREADS = CL_THREADS_DEF;
+constexpr int CL_NPT = 8;
+constexpr int CL_CHUNK = CL_THREADS * CL_NPT;
+constexpr int CL_MAX_CTAS = 16;
+constexpr int ST_STRIDE = 2048;  // capacity of one partial slot = upper bound of every streaming grid
+
+// Row-block ("CSR-stream") SpMV for matrices beyond L2.  The host cuts the rows into blocks of <= ST_CHUNK
+// nonzeros (and <= SP_THREADS rows, or one longer row) and stores (first row, first nonzero) per block.  A CTA owns a
+// CONTIGUOUS range of blocks, so the part of x it gathers from slides slowly and stays in L1 when the matrix has any
+// locality (the kernels keep shared memory small to leave L1 its capacity).  Per block: NPT independent, fully
+// coalesced (val, colind) loads per thread -- no dependence on row pointers, so the HBM pipe stays full regardless of
+// the row lengths -- then the x gathers (read-only path) with the row's epilogue operands loaded underneath them
+// (`pre(b, row)`), products parked in shared memory, one row per thread reduced in storage order (deterministic),
+// `epi(b, row, value, operands)` once per row.
+// sel(b, A, x, lb): matrix, gather vector and local block index of global block b.
+// XCG: x was written earlier in the SAME launch (persistent kernels) -> gather with ld.global.cg, not the read-only path.
+template <int THREADS, int NPT, bool XCG, class Sel, class Pre, class Epi>
+__device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double* red, Sel&& sel, Pre&& pre, Epi&& epi) {
+    constexpr int CHUNK = THREADS * NPT;
+    const int tid = threadIdx.x;
+    const int per = (nblk_total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int b_end = min(nblk_total, ((int)blockIdx.x + 1) * per);
+    for (int b = blockIdx.x * per; b < b_end; ++b) {
+        const CsrView* A;
+        const double* x;
+        int lb;
+        sel(b, A, x, lb);
+        const int2 d0 = __ldg(reinterpret_cast<const int2*>(A->blk) + lb);
+        const int2 d1 = __ldg(reinterpret_cast<const int2*>(A->blk) + lb + 1);
+        const int r0 = d0.x, s = d0.y, r1 = d1.x, cnt = d1.y - d0.y;
+        if (cnt > CHUNK) {  // one long row: whole CTA, fixed-order reduction
+            double acc = 0.0;
+            for (int k = tid; k < cnt; k += THREADS)
+                {
+                const double* xp = x + (XCG ? __ldg(A->colind + s + k) : __ldcs(A->colind + s + k));
+                acc = fma(XCG ? __ldg(A->val + s + k) : __ldcs(A->val + s + k), XCG ? __ldcg(xp) : __ldg(xp), acc);
+            }
+            acc = warp_sum_all(acc);
+            if ((tid & 31) == 0) red[32 + (tid >> 5)] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int w = 0; w < THREADS / 32; ++w) t += red[32 + w];
+                epi(b, r0, t, pre(b, r0));
+            }
+        } else {
+            double av[NPT];
+            int ci[NPT];
+#pragma unroll
+            for (int u = 0; u < NPT; ++u) {
+                const int k = tid + u * THREADS;
+                av[u] = 0.0;
+                ci[u] = 0;
+                if (k < cnt) {  // streamed once per pass (evict-first) unless the operator lives in L2 (XCG kernels)
+                    av[u] = XCG ? __ldg(A->val + s + k) : __ldcs(A->val + s + k);
+                    ci[u] = XCG ? __ldg(A->colind + s + k) : __ldcs(A->colind + s + k);
+                }
+            }
+            const int row = r0 + tid;
+            int ra = 0, rb = 0;
+            if (row < r1) {
+                ra = __ldg(A->rowptr + row) - s;
+                rb = __ldg(A->rowptr + row + 1) - s;
+            }
+            double xv[NPT];
+#pragma unroll
+            for (int u = 0; u < NPT; ++u)
+                xv[u] = (tid + u * THREADS < cnt) ? (XCG ? __ldcg(x + ci[u]) : __ldg(x + ci[u])) : 0.0;
+            double4 opnd = make_double4(0.0, 0.0, 0.0, 0.0);
+            if (row < r1) opnd = pre(b, row);
+#pragma unroll
+            for (int u = 0; u < NPT; ++u)
+                if (tid + u * THREADS < cnt) prod[tid + u * THREADS] = av[u] * xv[u];
+            __syncthreads();
+            if (row < r1) {
+                double t = 0.0;
+                for (int k = ra; k < rb; ++k) t += prod[k];
+                epi(b, row, t, opnd);
+            }
+        }
+        __syncthreads();  // prod / red are free again
+    }
+}
+
 // ---- SOC block of Dpi applied to y (symmetric block, so it serves Dpi and Dpi') ------------------
 // group of `T` lanes handles cone `c`; writes out[off .. off+dim)
 __device__ void soc_apply(const ConicOpView& op, int c, bool valid, const double* __restrict__ y, double* out,
@@ -196,32 +315,32 @@ __device__ void psd_apply_all(Dev& d, const ConicOpView& op, const double* __res
             X[e] = val;
         }
     }
-    d.grid.sync();
+    d.sync();
     for (int c = 0; c < op.npsd; ++c) {  // W1 = U' X
         const int dd = op.psd_d[c];
         const long long uo = op.psd_uoff[c];
         if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_U + uo, true, op.psd_w0 + uo, false, nullptr, op.psd_w1 + uo);
     }
-    d.grid.sync();
+    d.sync();
     for (int c = 0; c < op.npsd; ++c) {  // W2 = (W1 U) o B
         const int dd = op.psd_d[c];
         const long long uo = op.psd_uoff[c];
         if (!op.psd_ident[c])
             psd_gemm_phase(d, dd, op.psd_w1 + uo, false, op.psd_U + uo, false, op.psd_Bm + uo, op.psd_w2 + uo);
     }
-    d.grid.sync();
+    d.sync();
     for (int c = 0; c < op.npsd; ++c) {  // W1 = U W2
         const int dd = op.psd_d[c];
         const long long uo = op.psd_uoff[c];
         if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_U + uo, false, op.psd_w2 + uo, false, nullptr, op.psd_w1 + uo);
     }
-    d.grid.sync();
+    d.sync();
     for (int c = 0; c < op.npsd; ++c) {  // W0 = W1 U'   (identity cones keep X in W0)
         const int dd = op.psd_d[c];
         const long long uo = op.psd_uoff[c];
         if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_w1 + uo, false, op.psd_U + uo, true, nullptr, op.psd_w2 + uo);
     }
-    d.grid.sync();
+    d.sync();
     for (int c = 0; c < op.npsd; ++c) {  // vec
         const int dd = op.psd_d[c], off = op.psd_off[c];
         const double* R = (op.psd_ident[c] ? op.psd_w0 : op.psd_w2) + op.psd_uoff[c];
@@ -263,26 +382,123 @@ __device__ void dpi_apply(Dev& d, const ConicOpView& op, const double* __restric
 // CONIC: OP = M or M'.
 // All functions are called by the whole grid and contain grid syncs.
 
+extern __shared__ double cl_prod[];  // CL_CHUNK products (dynamic shared memory of the cluster launch)
+
+// CL = cluster-synchronised launch: the SpMVs run as row-block streams (every load of a thread's share is issued up
+// front: two L2 latencies per product instead of two per lane-group step), see spmv_stream.
+template <bool CL>
 __device__ void csr_apply(Dev& d, const CsrView& A, const double* __restrict__ src, double s_src, double* dst,
                           double s_dst, int slot) {
     double acc = 0.0;
-    spmv_rows<4>(d, A, src, [&](int row, double t) {
-        t = t * s_src + s_dst * dst[row];
-        dst[row] = t;
-        acc += t * t;
-    });
+    if constexpr (CL) {
+        spmv_stream<CL_THREADS, CL_NPT, true>(
+            A.nblk, cl_prod, d.red, [&](int b, const CsrView*& M, const double*& x, int& lb) { M = &A; x = src; lb = b; },
+            [&](int, int row) { return make_double4(s_dst != 0.0 ? __ldcg(dst + row) : 0.0, 0.0, 0.0, 0.0); },
+            [&](int, int row, double t, const double4& o) {
+                t = t * s_src + s_dst * o.x;
+                dst[row] = t;
+                acc += t * t;
+            });
+    } else {
+        spmv_rows<4>(d, A, src, [&](int row, double t) {
+            t = t * s_src + s_dst * dst[row];
+            dst[row] = t;
+            acc += t * t;
+        });
+    }
     block_partial(d, slot, acc);
 }
 
 // dst = s_src * (M src) + s_dst * dst ; slots: slot (norm), slot+1 (last-row dot)
+// `dst_last` is every thread's private copy of dst[N-1] (all threads compute it identically): with it nobody reads the
+// old last entry from memory, so thread 0 may overwrite it without a second barrier.
+template <bool CL>
 __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const double* __restrict__ src,
-                            double s_src, double* dst, double s_dst, int slot) {
+                            double s_src, double* dst, double s_dst, int slot, double& dst_last) {
     const int n = op.n, m = op.m, N = n + m + 1;
     double dotacc = 0.0;
+    if constexpr (CL) {
+        double* prod = cl_prod;
+        double acc = 0.0;
+        if (!transpose) {
+            dpi_apply(d, op, src + n, op.wc, false);  // wc = Dpi t2
+            d.sync();
+            const double t3 = __ldcg(src + n + m);
+            const int nbt = op.At.nblk;
+            spmv_stream<CL_THREADS, CL_NPT, true>(
+                nbt + op.A.nblk, prod, d.red,
+                [&](int b, const CsrView*& A, const double*& x, int& lb) {
+                    if (b < nbt) { A = &op.At; x = op.wc; lb = b; }
+                    else { A = &op.A; x = src; lb = b - nbt; }
+                },
+                [&](int b, int row) {
+                    return b < nbt ? make_double4(op.c[row], __ldcg(dst + row), __ldcg(src + row), 0.0)
+                                   : make_double4(__ldcg(op.wc + row), __ldcg(src + n + row), op.b[row],
+                                                  __ldcg(dst + n + row));
+                },
+                [&](int b, int row, double t, const double4& o) {
+                    if (b < nbt) {  // rows 0..n-1:  (A' wc)_j + c_j t3
+                        t = (t + o.x * t3) * s_src + s_dst * o.y;
+                        dst[row] = t;
+                        acc += t * t;
+                        dotacc += o.x * o.z;
+                    } else {        // rows n..n+m-1:  -(A t1)_i + t2_i - wc_i + b_i t3
+                        t = (-t + o.y - o.x + o.z * t3) * s_src + s_dst * o.w;
+                        dst[n + row] = t;
+                        acc += t * t;
+                        dotacc += o.z * o.x;
+                    }
+                });
+            block_partial(d, slot, acc);
+            block_partial(d, slot + 1, dotacc);
+            d.sync();
+            const double last = -total_of(d, slot + 1) * s_src + s_dst * dst_last;  // -(c't1 + b'wc)
+            dst_last = last;
+            if (d.gtid == 0) dst[N - 1] = last;
+            if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
+        } else {
+            const double u3 = __ldcg(src + n + m);
+            spmv_stream<CL_THREADS, CL_NPT, true>(  // wc = A u1 - u2 - b u3
+                op.A.nblk, prod, d.red,
+                [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.A; x = src; lb = b; },
+                [&](int, int row) { return make_double4(__ldcg(src + n + row), op.b[row], 0.0, 0.0); },
+                [&](int, int row, double t, const double4& o) {
+                    op.wc[row] = t - o.x - o.y * u3;
+                    dotacc += o.y * o.x;
+                });
+            d.sync();
+            double* r2 = op.wc + m;
+            dpi_apply(d, op, op.wc, r2, true);
+            d.sync();
+            spmv_stream<CL_THREADS, CL_NPT, true>(  // rows 0..n-1: -(A' u2)_j - c_j u3
+                op.At.nblk, prod, d.red,
+                [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.At; x = src + n; lb = b; },
+                [&](int, int row) { return make_double4(op.c[row], __ldcg(dst + row), __ldcg(src + row), 0.0); },
+                [&](int, int row, double t, const double4& o) {
+                    t = (-t - o.x * u3) * s_src + s_dst * o.y;
+                    dst[row] = t;
+                    acc += t * t;
+                    dotacc += o.x * o.z;
+                });
+            for (int i = d.gtid; i < m; i += d.gthreads) {
+                const double t = (__ldcg(r2 + i) + __ldcg(src + n + i)) * s_src + s_dst * __ldcg(dst + n + i);
+                dst[n + i] = t;
+                acc += t * t;
+            }
+            block_partial(d, slot, acc);
+            block_partial(d, slot + 1, dotacc);
+            d.sync();
+            const double last = total_of(d, slot + 1) * s_src + s_dst * dst_last;
+            dst_last = last;
+            if (d.gtid == 0) dst[N - 1] = last;
+            if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
+        }
+        return;
+    }
     if (!transpose) {
         // wc = Dpi t2
         dpi_apply(d, op, src + n, op.wc, false);
-        d.grid.sync();
+        d.sync();
         const double t3 = __ldcg(src + n + m);
         double acc = 0.0;
         // rows 0..n-1:  (A' wc)_j + c_j t3
@@ -302,11 +518,10 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         });
         block_partial(d, slot, acc);
         block_partial(d, slot + 1, dotacc);
-        d.grid.sync();
+        d.sync();
         // last row: -(c't1 + b'wc)
-        double last = -total_of(d, slot + 1) * s_src + s_dst * __ldcg(dst + N - 1);
-        __syncthreads();
-        d.grid.sync();  // everyone has read the old dst[N-1] and the partials
+        const double last = -total_of(d, slot + 1) * s_src + s_dst * dst_last;
+        dst_last = last;
         if (d.gtid == 0) dst[N - 1] = last;
         if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
     } else {
@@ -317,14 +532,14 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
             op.wc[row] = t - u2 - op.b[row] * u3;
             dotacc += op.b[row] * u2;
         });
-        d.grid.sync();
+        d.sync();
         // out2 = Dpi' r + u2 : first Dpi' r into a second scratch = reuse psd-free path by writing to dst later.
         // We need dst's old value (s_dst * dst), so stage Dpi' r in op.wc's partner buffer: the x-part of dst is
         // disjoint, so compute into `tmp = psd_w-independent` region: use op.wc in place is unsafe (SOC reads all
         // entries of its cone) -> stage through dst? no.  Use the dedicated second scratch stored after wc.
         double* r2 = op.wc + m;  // second half of the 2m scratch
         dpi_apply(d, op, op.wc, r2, true);
-        d.grid.sync();
+        d.sync();
         double acc = 0.0;
         // rows 0..n-1: -(A' u2)_j - c_j u3
         spmv_rows<4>(d, op.At, src + n, [&](int row, double t) {
@@ -340,10 +555,9 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         }
         block_partial(d, slot, acc);
         block_partial(d, slot + 1, dotacc);
-        d.grid.sync();
-        double last = total_of(d, slot + 1) * s_src + s_dst * __ldcg(dst + N - 1);
-        __syncthreads();
-        d.grid.sync();
+        d.sync();
+        const double last = total_of(d, slot + 1) * s_src + s_dst * dst_last;
+        dst_last = last;
         if (d.gtid == 0) dst[N - 1] = last;
         if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
     }
@@ -357,23 +571,27 @@ struct OpArgs {
     int nrows, ncols;
 };
 
+template <bool CL>
 __device__ void op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* src, double s_src, double* dst,
-                         double s_dst, int slot) {
+                         double s_dst, int slot, double& dst_last) {
     if (o.kind == 0)
-        csr_apply(d, adjoint ? o.adj : o.fwd, src, s_src, dst, s_dst, slot);
+        csr_apply<CL>(d, adjoint ? o.adj : o.fwd, src, s_src, dst, s_dst, slot);
     else
-        conic_apply(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot);
+        conic_apply<CL>(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot, dst_last);
 }
 
-__global__ void __launch_bounds__(LSQR_THREADS, 4) lsqr_kernel(OpArgs o, const double* __restrict__ rhs, LsqrParams prm,
-                                                           LsqrVectors vec) {
+template <int THREADS, int MINB, bool CLUSTER, bool STREAM>
+__global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const double* __restrict__ rhs, LsqrParams prm,
+                                                               LsqrVectors vec) {
     __shared__ double red[64];
     Dev d{cg::this_grid(), vec.partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
           (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
-          (int)(gridDim.x * blockDim.x)};
+          (int)(gridDim.x * blockDim.x), CLUSTER};
     const int nr = o.nrows, nc = o.ncols;
     double *u = vec.u, *v = vec.v, *w = vec.w, *x = vec.x;
 
+    // private copies of the last entries of u and v (see conic_apply)
+    double u_last = nr > 0 ? rhs[nr - 1] : 0.0, v_last = 0.0;
     // u = b, beta = ||b||
     {
         double acc = 0.0;
@@ -389,7 +607,7 @@ __global__ void __launch_bounds__(LSQR_THREADS, 4) lsqr_kernel(OpArgs o, const d
         }
         block_partial(d, 0, acc);
     }
-    d.grid.sync();
+    d.sync();
     double beta = sqrt(total_of(d, 0));
     double alpha = 0.0;
     double su = 1.0, sv = 1.0;  // true u = su * u_mem, true v = sv * v_mem
@@ -399,8 +617,8 @@ __global__ void __launch_bounds__(LSQR_THREADS, 4) lsqr_kernel(OpArgs o, const d
     double rnorm = beta, arnorm = 0.0;
     if (beta > 0) {
         su = 1.0 / beta;
-        op_apply(d, o, true, u, su, v, 0.0, 2);   // v_mem = A' u_true
-        d.grid.sync();
+        op_apply<STREAM>(d, o, true, u, su, v, 0.0, 2, v_last);   // v_mem = A' u_true
+        d.sync();
         alpha = sqrt(total_of(d, 2));
     }
     if (alpha > 0) sv = 1.0 / alpha;
@@ -431,8 +649,8 @@ __global__ void __launch_bounds__(LSQR_THREADS, 4) lsqr_kernel(OpArgs o, const d
             }
             block_partial(d, 4, dd);
             const bool more = itn < prm.maxiter;
-            if (more) op_apply(d, o, false, v, sv, u, -alpha * su, 0);  // u_mem = A v_true - alpha u_true
-            d.grid.sync();
+            if (more) op_apply<STREAM>(d, o, false, v, sv, u, -alpha * su, 0, u_last);  // u_mem = A v_true - alpha u_true
+            d.sync();
             if (pending) {
                 ddnorm += total_of(d, 4);
                 acond = anorm * sqrt(ddnorm);
@@ -457,8 +675,8 @@ __global__ void __launch_bounds__(LSQR_THREADS, 4) lsqr_kernel(OpArgs o, const d
             if (beta > 0) {
                 su = 1.0 / beta;
                 anorm = sqrt(anorm * anorm + alpha * alpha + beta * beta);
-                op_apply(d, o, true, u, su, v, -beta * sv, 2);  // v_mem = A' u_true - beta v_true
-                d.grid.sync();
+                op_apply<STREAM>(d, o, true, u, su, v, -beta * sv, 2, v_last);  // v_mem = A' u_true - beta v_true
+                d.sync();
                 alpha = sqrt(total_of(d, 2));
                 sv = alpha > 0 ? 1.0 / alpha : 1.0;
             } else {
@@ -488,6 +706,14 @@ __global__ void __launch_bounds__(LSQR_THREADS, 4) lsqr_kernel(OpArgs o, const d
             pending = true;
         }
     }
+#ifdef LSQR_PROF
+    if (d.gtid == 0) {
+        const int n0 = g_prof_n > 400 ? 300 : 0;
+        for (int k = n0; k + 1 < g_prof_n && k < n0 + 44; ++k)
+            printf("%s %lld ns\n", (k & 1) ? "  compute" : "barrier", g_prof[k + 1] - g_prof[k]);
+        g_prof_n = 0;
+    }
+#endif
     if (d.gtid == 0) {
         vec.stats[0] = (double)istop;
         vec.stats[1] = (double)itn;
@@ -506,7 +732,8 @@ __global__ void __launch_bounds__(LSQR_THREADS) conic_M_kernel(ConicOpView op, i
     Dev d{cg::this_grid(), partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
           (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
           (int)(gridDim.x * blockDim.x)};
-    conic_apply(d, op, transpose != 0, t, 1.0, out, 0.0, 0);
+    double last = 0.0;
+    conic_apply<false>(d, op, transpose != 0, t, 1.0, out, 0.0, 0, last);
 }
 
 __global__ void __launch_bounds__(LSQR_THREADS) conic_dpi_kernel(ConicOpView op, int transpose, const double* t, double* out,
@@ -535,83 +762,6 @@ struct LsqrState {
 };
 
 constexpr int ST_THREADS = 256;
-constexpr int SP_THREADS = 128;                   // threads of a streaming-SpMV CTA (8 CTAs per SM)
-constexpr int ST_NPT = 8;                         // nonzeros per thread in flight
-constexpr int ST_CHUNK = SP_THREADS * ST_NPT;     // nonzeros per row block
-constexpr int ST_STRIDE = 2048;  // capacity of one partial slot = upper bound of every streaming grid
-
-// Row-block ("CSR-stream") SpMV for matrices beyond L2.  The host cuts the rows into blocks of <= ST_CHUNK
-// nonzeros (and <= SP_THREADS rows, or one longer row) and stores (first row, first nonzero) per block.  A CTA owns a
-// CONTIGUOUS range of blocks, so the part of x it gathers from slides slowly and stays in L1 when the matrix has any
-// locality (the kernels keep shared memory small to leave L1 its capacity).  Per block: ST_NPT independent, fully
-// coalesced (val, colind) loads per thread -- no dependence on row pointers, so the HBM pipe stays full regardless of
-// the row lengths -- then the x gathers (read-only path) with the row's epilogue operands loaded underneath them
-// (`pre(b, row)`), products parked in shared memory, one row per thread reduced in storage order (deterministic),
-// `epi(b, row, value, operands)` once per row.
-// sel(b, A, x, lb): matrix, gather vector and local block index of global block b.
-template <class Sel, class Pre, class Epi>
-__device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double* red, Sel&& sel, Pre&& pre, Epi&& epi) {
-    const int tid = threadIdx.x;
-    const int per = (nblk_total + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int b_end = min(nblk_total, ((int)blockIdx.x + 1) * per);
-    for (int b = blockIdx.x * per; b < b_end; ++b) {
-        const CsrView* A;
-        const double* x;
-        int lb;
-        sel(b, A, x, lb);
-        const int2 d0 = __ldg(reinterpret_cast<const int2*>(A->blk) + lb);
-        const int2 d1 = __ldg(reinterpret_cast<const int2*>(A->blk) + lb + 1);
-        const int r0 = d0.x, s = d0.y, r1 = d1.x, cnt = d1.y - d0.y;
-        if (cnt > ST_CHUNK) {  // one long row: whole CTA, fixed-order reduction
-            double acc = 0.0;
-            for (int k = tid; k < cnt; k += SP_THREADS)
-                acc = fma(__ldcs(A->val + s + k), __ldg(x + __ldcs(A->colind + s + k)), acc);
-            acc = warp_sum_all(acc);
-            if ((tid & 31) == 0) red[32 + (tid >> 5)] = acc;
-            __syncthreads();
-            if (tid == 0) {
-                double t = 0.0;
-                for (int w = 0; w < SP_THREADS / 32; ++w) t += red[32 + w];
-                epi(b, r0, t, pre(b, r0));
-            }
-        } else {
-            double av[ST_NPT];
-            int ci[ST_NPT];
-#pragma unroll
-            for (int u = 0; u < ST_NPT; ++u) {
-                const int k = tid + u * SP_THREADS;
-                av[u] = 0.0;
-                ci[u] = 0;
-                if (k < cnt) {
-                    av[u] = __ldcs(A->val + s + k);
-                    ci[u] = __ldcs(A->colind + s + k);
-                }
-            }
-            const int row = r0 + tid;
-            int ra = 0, rb = 0;
-            if (row < r1) {
-                ra = __ldg(A->rowptr + row) - s;
-                rb = __ldg(A->rowptr + row + 1) - s;
-            }
-            double xv[ST_NPT];
-#pragma unroll
-            for (int u = 0; u < ST_NPT; ++u) xv[u] = (tid + u * SP_THREADS < cnt) ? __ldg(x + ci[u]) : 0.0;
-            double4 opnd = make_double4(0.0, 0.0, 0.0, 0.0);
-            if (row < r1) opnd = pre(b, row);
-#pragma unroll
-            for (int u = 0; u < ST_NPT; ++u)
-                if (tid + u * SP_THREADS < cnt) prod[tid + u * SP_THREADS] = av[u] * xv[u];
-            __syncthreads();
-            if (row < r1) {
-                double t = 0.0;
-                for (int k = ra; k < rb; ++k) t += prod[k];
-                epi(b, row, t, opnd);
-            }
-        }
-        __syncthreads();  // prod / red are free again
-    }
-}
-
 #define ST_DEV(partials)                                                                                          \
     __shared__ double red[64];                                                                                    \
     Dev d{cg::this_grid(), partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),     \
@@ -709,7 +859,7 @@ __global__ void __launch_bounds__(SP_THREADS, 8) st_M_rows_kernel(ConicOpView op
     double acc = 0.0, dotacc = 0.0;
     const int nbt = op.At.nblk;
     __shared__ double prod[ST_CHUNK];
-    spmv_stream(
+    spmv_stream<SP_THREADS, ST_NPT, false>(
         nbt + op.A.nblk, prod, red,
         [&](int b, const CsrView*& A, const double*& x, int& lb) {
             if (b < nbt) { A = &op.At; x = op.wc; lb = b; }
@@ -800,7 +950,7 @@ __global__ void __launch_bounds__(SP_THREADS, 8) st_Mt_A_kernel(ConicOpView op, 
     const double u3 = __ldcg(src + n + m);
     double dotacc = 0.0;
     __shared__ double prod[ST_CHUNK];
-    spmv_stream(
+    spmv_stream<SP_THREADS, ST_NPT, false>(
         op.A.nblk, prod, red,
         [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.A; x = src; lb = b; },
         [&](int, int row) { return make_double4(__ldcg(src + n + row), op.b[row], 0.0, 0.0); },
@@ -822,7 +972,7 @@ __global__ void __launch_bounds__(SP_THREADS, 8) st_Mt_rows_kernel(ConicOpView o
     const double* r2 = op.wc + m;
     double acc = 0.0, dotacc = 0.0;
     __shared__ double prod[ST_CHUNK];
-    spmv_stream(
+    spmv_stream<SP_THREADS, ST_NPT, false>(
         op.At.nblk, prod, red,
         [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.At; x = src + n; lb = b; },
         [&](int, int row) { return make_double4(op.c[row], dst[row], __ldcg(src + row), 0.0); },
@@ -918,13 +1068,18 @@ CsrView view_of(const DevBuf& rp, const DevBuf& ci, const DevBuf& v, int64_t nro
 
 }  // namespace
 
-ConicOpView conic_view(diffopt_b200_ctx* ctx) {
+ConicOpView conic_view(diffopt_b200_ctx* ctx, bool stream_blocks = false) {
     ConicState& s = ctx->conic;
     ConicOpView o{};
     o.n = (int)s.n;
     o.m = (int)s.m;
-    o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n, &s.A.blk, s.A.nblk);
-    o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m, &s.A.t_blk, s.A.t_nblk);
+    if (stream_blocks) {
+        o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n, &s.A.blk, s.A.nblk);
+        o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m, &s.A.t_blk, s.A.t_nblk);
+    } else {
+        o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n, &s.A.cblk, s.A.ncblk);
+        o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m, &s.A.t_cblk, s.A.t_ncblk);
+    }
     o.b = s.b.as<double>();
     o.c = s.c.as<double>();
     o.diag = s.nn_scale.as<double>();
@@ -961,6 +1116,41 @@ static int coop_grid(diffopt_b200_ctx* ctx, const void* kernel, int64_t work) {
     return (int)want;
 }
 
+// Cluster-synchronised variant for operators that a single cluster can chew through (a few 10^5 nonzeros, everything
+// L2 resident): ONE cluster of 16 (or 8) CTAs x 1024 threads, every phase boundary is a hardware cluster barrier.
+constexpr int64_t CL_MAX_WORK = (int64_t)1 << 20;
+constexpr int64_t CL_CLUSTER_WORK = (int64_t)512 << 10;
+
+static int cluster_size_for(diffopt_b200_ctx* ctx, const void* kernel) {
+    static int cached = -1;  // per process; every B200 in a box is the same part
+    if (cached >= 0) return cached;
+    cached = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+    }
+    for (int cs : {16, 8}) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)cs);
+        cfg.blockDim = dim3(CL_THREADS);
+        cfg.dynamicSmemBytes = CL_CHUNK * sizeof(double);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && n >= 1) {
+            cached = cs;
+            break;
+        }
+        cudaGetLastError();
+    }
+    (void)ctx;
+    return cached;
+}
+
 static int32_t lsqr_launch(diffopt_b200_ctx* ctx, OpArgs& o, int64_t work, const double* rhs_dev, LsqrParams prm,
                            double* x_dev, double* stats_host7) {
     LsqrWork& wk = ctx->lsqr;
@@ -968,7 +1158,44 @@ static int32_t lsqr_launch(diffopt_b200_ctx* ctx, OpArgs& o, int64_t work, const
     DO_CUDA(ctx, wk.u.reserve(d * (size_t)o.nrows));
     DO_CUDA(ctx, wk.v.reserve(d * (size_t)o.ncols));
     DO_CUDA(ctx, wk.w.reserve(d * (size_t)o.ncols));
-    int grid = coop_grid(ctx, (const void*)lsqr_kernel, work);
+    const void* k_grid = (const void*)lsqr_kernel_t<LSQR_THREADS, 4, false, false>;
+    const void* k_cluster = (const void*)lsqr_kernel_t<CL_THREADS, 1, true, true>;
+    const void* k_gstream = (const void*)lsqr_kernel_t<CL_THREADS, 1, false, true>;
+    // Three persistent variants, by size of the operator (`work` ~ nonzeros + vector lengths):
+    //   cluster : <= CL_CLUSTER_WORK  one 16-CTA cluster, hardware barriers, row-block SpMV (16 SMs are enough)
+    //   gstream : <= CL_MAX_WORK      one CTA per SM, grid.sync(), row-block SpMV (L1 gather rate of 16 SMs is not)
+    //   grid    : larger / PSD cones  lane-group SpMV, up to 4 CTAs per SM
+    const char* mode = getenv("DIFFOPT_B200_LSQR");
+    const bool psd = o.kind == 1 && o.conic.npsd > 0;  // PSD applies are GEMM phases written for the lane-group grid
+    int variant = 0;  // 0 grid, 1 cluster, 2 gstream
+    if (!psd && work <= CL_MAX_WORK) variant = work <= CL_CLUSTER_WORK ? 1 : 2;
+    if (mode && strcmp(mode, "grid") == 0) variant = 0;
+    if (mode && strcmp(mode, "cluster") == 0 && !psd) variant = 1;
+    if (mode && strcmp(mode, "gstream") == 0 && !psd) variant = 2;
+    int cs = variant == 1 ? cluster_size_for(ctx, k_cluster) : 0;
+    if (variant == 1 && cs == 0) variant = 2;
+    const size_t dyn = variant ? CL_CHUNK * sizeof(double) : 0;
+    int grid = cs;
+    if (variant == 0) grid = coop_grid(ctx, k_grid, work);
+    if (variant == 2) {
+        DO_CUDA(ctx, cudaFuncSetAttribute(k_gstream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        grid = ctx->sm_count;
+    }
+    {   // the row-block lists that match the launch
+        auto pick = [&](CsrView& v, const CsrDev& M, bool t) {
+            const bool g = variant == 2;
+            v.blk = (t ? (g ? M.t_gblk : M.t_cblk) : (g ? M.gblk : M.cblk)).as<int>();
+            v.nblk = (int)(t ? (g ? M.t_ngblk : M.t_ncblk) : (g ? M.ngblk : M.ncblk));
+        };
+        if (o.kind == 1) {
+            pick(o.conic.A, ctx->conic.A, false);
+            pick(o.conic.At, ctx->conic.A, true);
+        } else {
+            const bool fwd_is_t = o.fwd.rowptr == ctx->lsqr_mat.t_rowptr.as<int>();
+            pick(o.fwd, ctx->lsqr_mat, fwd_is_t);
+            pick(o.adj, ctx->lsqr_mat, !fwd_is_t);
+        }
+    }
     DO_CUDA(ctx, wk.tmp.reserve(d * (size_t)NSLOTS * (size_t)grid));
     DO_CUDA(ctx, wk.scal.reserve(d * 8));
     DO_CUDA(ctx, cudaMemsetAsync(wk.tmp.ptr, 0, d * (size_t)NSLOTS * (size_t)grid, ctx->stream));
@@ -976,8 +1203,25 @@ static int32_t lsqr_launch(diffopt_b200_ctx* ctx, OpArgs& o, int64_t work, const
                     wk.scal.as<double>()};
     void* args[] = {&o, (void*)&rhs_dev, &prm, &vec};
     DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    DO_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)lsqr_kernel, dim3(grid), dim3(LSQR_THREADS), args, 0,
-                                             ctx->stream));
+    if (variant == 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)cs);
+        cfg.blockDim = dim3(CL_THREADS);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        DO_CUDA(ctx, cudaLaunchKernelExC(&cfg, k_cluster, args));
+    } else if (variant == 2) {
+        DO_CUDA(ctx, cudaLaunchCooperativeKernel(k_gstream, dim3(grid), dim3(CL_THREADS), args, dyn, ctx->stream));
+    } else {
+        DO_CUDA(ctx, cudaLaunchCooperativeKernel(k_grid, dim3(grid), dim3(LSQR_THREADS), args, 0, ctx->stream));
+    }
     ctx->launches++;
     DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     double st[7];
@@ -993,8 +1237,8 @@ int32_t lsqr_run_csr(diffopt_b200_ctx* ctx, const CsrDev& M, bool trans, const d
                      double* x_dev, double* stats_host7) {
     OpArgs o{};
     o.kind = 0;
-    CsrView a = view_of(M.rowptr, M.colind, M.val, M.nrows, M.ncols);
-    CsrView at = view_of(M.t_rowptr, M.t_colind, M.t_val, M.ncols, M.nrows);
+    CsrView a = view_of(M.rowptr, M.colind, M.val, M.nrows, M.ncols, &M.cblk, M.ncblk);
+    CsrView at = view_of(M.t_rowptr, M.t_colind, M.t_val, M.ncols, M.nrows, &M.t_cblk, M.t_ncblk);
     o.fwd = trans ? at : a;
     o.adj = trans ? a : at;
     o.nrows = (int)(trans ? M.ncols : M.nrows);
@@ -1005,7 +1249,7 @@ int32_t lsqr_run_csr(diffopt_b200_ctx* ctx, const CsrDev& M, bool trans, const d
 static int32_t lsqr_stream_conic(diffopt_b200_ctx* ctx, const double* rhs_dev, LsqrParams prm, double* x_dev, double* stats_host7) {
     ConicState& cs = ctx->conic;
     LsqrWork& wk = ctx->lsqr;
-    ConicOpView op = conic_view(ctx);
+    ConicOpView op = conic_view(ctx, true);
     const int n = (int)cs.n, m = (int)cs.m, N = n + m + 1;
     const size_t dsz = sizeof(double);
     DO_CUDA(ctx, wk.u.reserve(dsz * (size_t)N));
@@ -1163,9 +1407,47 @@ int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, c
         }
         blk.swap(d2);
     };
-    std::vector<int> blk, t_blk;
+    // the same for the cluster-synchronised kernel: about one block per CTA and round, <= CL_CHUNK nonzeros each
+    auto cluster_blocks = [](const std::vector<int>& rp, int64_t nr, int64_t CTAS, std::vector<int>& blk) {
+        const int64_t nz = nr > 0 ? rp[(size_t)nr] : 0;
+        const int64_t rounds = std::max<int64_t>(1, (nz + CTAS * CL_CHUNK - 1) / (CTAS * CL_CHUNK));
+        const int64_t rows_round = std::max<int64_t>(1, (nr + CTAS * CL_THREADS - 1) / (CTAS * CL_THREADS));
+        const int64_t want = CTAS * std::max(rounds, rows_round);
+        double target = (double)std::max<int64_t>(nz / want + 1, 1);
+        for (int attempt = 0; attempt < 24; ++attempt) {
+            const int cap = (int)std::min<double>(target, (double)CL_CHUNK);
+            blk.clear();
+            blk.push_back(0);
+            int64_t r = 0;
+            while (r < nr) {
+                const int s0 = rp[(size_t)r];
+                int64_t e = r;
+                while (e < nr && rp[(size_t)e + 1] - s0 <= cap && e - r < CL_THREADS) ++e;
+                if (e == r) e = r + 1;
+                blk.push_back((int)e);
+                r = e;
+            }
+            if ((int64_t)blk.size() - 1 <= want || cap >= CL_CHUNK) break;
+            target *= 1.03;
+        }
+        std::vector<int> d2(blk.size() * 2);
+        for (size_t k = 0; k < blk.size(); ++k) {
+            d2[2 * k] = blk[k];
+            d2[2 * k + 1] = rp[(size_t)blk[k]];
+        }
+        blk.swap(d2);
+    };
+    std::vector<int> blk, t_blk, cblk, t_cblk, gblk, t_gblk;
     row_blocks(rowptr, nrows, blk);
     row_blocks(t_rowptr, ncols, t_blk);
+    cluster_blocks(rowptr, nrows, CL_MAX_CTAS, cblk);
+    cluster_blocks(t_rowptr, ncols, CL_MAX_CTAS, t_cblk);
+    cluster_blocks(rowptr, nrows, ctx->sm_count, gblk);
+    cluster_blocks(t_rowptr, ncols, ctx->sm_count, t_gblk);
+    out.ncblk = (int64_t)cblk.size() / 2 - 1;
+    out.t_ncblk = (int64_t)t_cblk.size() / 2 - 1;
+    out.ngblk = (int64_t)gblk.size() / 2 - 1;
+    out.t_ngblk = (int64_t)t_gblk.size() / 2 - 1;
     out.nblk = (int64_t)blk.size() / 2 - 1;
     out.t_nblk = (int64_t)t_blk.size() / 2 - 1;
     out.nrows = nrows;
@@ -1184,6 +1466,10 @@ int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, c
     DO_CUDA(ctx, up(out.t_val, nzval, sizeof(double) * (size_t)nnz));
     DO_CUDA(ctx, up(out.blk, blk.data(), sizeof(int) * blk.size()));
     DO_CUDA(ctx, up(out.t_blk, t_blk.data(), sizeof(int) * t_blk.size()));
+    DO_CUDA(ctx, up(out.cblk, cblk.data(), sizeof(int) * cblk.size()));
+    DO_CUDA(ctx, up(out.t_cblk, t_cblk.data(), sizeof(int) * t_cblk.size()));
+    DO_CUDA(ctx, up(out.gblk, gblk.data(), sizeof(int) * gblk.size()));
+    DO_CUDA(ctx, up(out.t_gblk, t_gblk.data(), sizeof(int) * t_gblk.size()));
     DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die at return
     return 0;
 }
