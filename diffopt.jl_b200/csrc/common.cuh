@@ -70,6 +70,8 @@ struct ConicState {
     DevBuf psd_off, psd_d, psd_uoff;  // per PSD cone: row offset, side d, offset into U/B storage
     DevBuf psd_U, psd_Bm, psd_ident;  // eigenvectors (col-major d x d), B matrix, identity flag
     DevBuf psd_work;                  // scratch 3 * sum d^2
+    DevBuf psd_toff;                  // tile offsets of the PSD apply (lsqr.cu)
+    int64_t psd_ntiles = 0;
     DevBuf psd_lam, psd_loff;         // eigenvalues (+ shifts) and per-cone offsets into them (+ small-cone list)
     int64_t npsd = 0, psd_maxd = 0, psd_sumd2 = 0;
     std::vector<int64_t> h_psd_off, h_psd_d, h_psd_uoff;

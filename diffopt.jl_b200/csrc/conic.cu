@@ -297,6 +297,15 @@ int32_t diffopt_b200_conic_setup(diffopt_b200_ctx* ctx, int64_t n, int64_t m, co
     DO_CUDA(ctx, keep(S.psd_off, psd_off.data(), sizeof(int) * psd_off.size(), cudaMemcpyHostToDevice));
     DO_CUDA(ctx, keep(S.psd_d, psd_d.data(), sizeof(int) * psd_d.size(), cudaMemcpyHostToDevice));
     DO_CUDA(ctx, keep(S.psd_uoff, psd_uoff.data(), sizeof(long long) * psd_uoff.size(), cudaMemcpyHostToDevice));
+    {   // flattened list of 32 x 32 output tiles of the PSD apply
+        std::vector<int> toff(psd_d.size() + 1, 0);
+        for (size_t k = 0; k < psd_d.size(); ++k) {
+            const int nt = (psd_d[k] + 31) / 32;
+            toff[k + 1] = toff[k] + nt * nt;
+        }
+        S.psd_ntiles = toff.back();
+        DO_CUDA(ctx, keep(S.psd_toff, toff.data(), sizeof(int) * toff.size(), cudaMemcpyHostToDevice));
+    }
     DO_CUDA(ctx, S.v.reserve(d8 * (m ? m : 1)));
     DO_CUDA(ctx, S.vp.reserve(d8 * (m ? m : 1)));
     DO_CUDA(ctx, S.nn_scale.reserve(d8 * (m ? m : 1)));

@@ -281,80 +281,134 @@ __device__ void soc_apply(const ConicOpView& op, int c, bool valid, const double
 
 // ---- PSD block: out = Dpi*y (transpose=false) or Dpi'*y (true), whole grid cooperates ------------
 // Dpi' y = vec(F(unvec(y)));  Dpi y = S' F T' y  (diag of unvec doubled on the way in, halved on the way out),
-// F(X) = U (B o (U' X U)) U'.   Three d x d scratch matrices per cone; 5 grid syncs per call.
-__device__ void psd_gemm_phase(Dev& d, int dd, const double* __restrict__ Am, bool transA, const double* __restrict__ Bm_,
-                               bool transB, const double* __restrict__ mask, double* __restrict__ C) {
-    // C = op(A) * op(B) [o mask], column-major d x d, one output element per thread, grid-stride
-    const long long total = (long long)dd * dd;
-    for (long long e = d.gtid; e < total; e += d.gthreads) {
-        int i = (int)(e % dd), j = (int)(e / dd);
-        double acc = 0.0;
-        for (int k = 0; k < dd; ++k) {
-            double a = transA ? __ldcg(Am + k + (long long)i * dd) : __ldcg(Am + i + (long long)k * dd);
-            double b = transB ? __ldcg(Bm_ + j + (long long)k * dd) : __ldcg(Bm_ + k + (long long)j * dd);
-            acc += a * b;
+// F(X) = U (B o (U' X U)) U'.  Four GEMM phases on the FP64 tensor pipe (mma.sync m8n8k4), 3 barriers inside:
+//   W1 = U' X        (X read straight from the triangle y)
+//   W2 = (W1 U) o B
+//   W1 = U W2
+//   out = vec(W1 U') (upper-triangle tiles only, written straight into the triangle)
+// Work unit = one 32 x 32 output tile of one cone (tiles of all cones in one list, so 512 small cones fill the grid as
+// well as one 200 x 200 cone does); a 256-thread CTA stages 32-deep operand panels in shared memory ([k][i] layout,
+// leading dimension 36: fragment reads are bank-conflict free), next panel prefetched into registers under the MMAs.
+constexpr int PT = 32;        // tile side
+constexpr int PLD = PT + 4;   // panel leading dimension (doubles)
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// C(i0.., j0..) = sum_k la(i, k) * lb(k, j); st(i, j, value) for every in-range element of the tile.
+// a_ic / b_kc: which index is contiguous in memory for the A / B operand (chooses the coalesced load mapping).
+template <class LA, class LB, class ST>
+__device__ __forceinline__ void psd_tile_gemm(int dd, int i0, int j0, bool a_ic, bool b_kc, double* As, double* Bs,
+                                              LA&& la, LB&& lb, ST&& st) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int iw = (warp & 3) * 8, jw = (warp >> 2) * 16;
+    const int f = tid & 31, s8 = tid >> 5;  // fast / slow index of the load mapping (slow: s8 + 8 r)
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    double ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int sl = s8 + 8 * r;
+            const int ia = a_ic ? f : sl, ka = a_ic ? sl : f;
+            const int kb = b_kc ? f : sl, jb = b_kc ? sl : f;
+            ra[r] = (i0 + ia < dd && k0 + ka < dd) ? la(i0 + ia, k0 + ka) : 0.0;
+            rb[r] = (k0 + kb < dd && j0 + jb < dd) ? lb(k0 + kb, j0 + jb) : 0.0;
         }
-        if (mask) acc *= mask[e];
-        C[e] = acc;
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < dd; k0 += PT) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int sl = s8 + 8 * r;
+            const int ia = a_ic ? f : sl, ka = a_ic ? sl : f;
+            const int kb = b_kc ? f : sl, jb = b_kc ? sl : f;
+            As[ka * PLD + ia] = ra[r];
+            Bs[kb * PLD + jb] = rb[r];
+        }
+        __syncthreads();
+        if (k0 + PT < dd) fetch(k0 + PT);
+#pragma unroll
+        for (int kk = 0; kk < PT; kk += 4) {
+            const int kr = (kk + (lane & 3)) * PLD;
+            const double av = As[kr + iw + (lane >> 2)];
+            const double b0 = Bs[kr + jw + (lane >> 2)];
+            const double b1 = Bs[kr + jw + 8 + (lane >> 2)];
+            dmma884(c00, c01, av, b0);
+            dmma884(c10, c11, av, b1);
+        }
+        __syncthreads();
+    }
+    const int i = i0 + iw + (lane >> 2), j = j0 + jw + 2 * (lane & 3);
+    if (i < dd) {
+        if (j < dd) st(i, j, c00);
+        if (j + 1 < dd) st(i, j + 1, c01);
+        if (j + 8 < dd) st(i, j + 8, c10);
+        if (j + 9 < dd) st(i, j + 9, c11);
     }
 }
 
 __device__ void psd_apply_all(Dev& d, const ConicOpView& op, const double* __restrict__ y, double* out,
                               bool transpose) {
     if (op.npsd == 0) return;
-    // phase 0: unvec
-    for (int c = 0; c < op.npsd; ++c) {
-        const int dd = op.psd_d[c], off = op.psd_off[c];
-        double* X = op.psd_w0 + op.psd_uoff[c];
-        const long long total = (long long)dd * dd;
-        for (long long e = d.gtid; e < total; e += d.gthreads) {
-            int i = (int)(e % dd), j = (int)(e / dd);
-            int r = i < j ? i : j, cc = i < j ? j : i;
-            double val = __ldcg(y + off + (long long)cc * (cc + 1) / 2 + r);
-            if (!transpose && i == j) val *= 2.0;
-            X[e] = val;
+    __shared__ double As[PT * PLD], Bs[PT * PLD];
+    const double dscale = transpose ? 1.0 : 2.0, oscale = transpose ? 1.0 : 0.5;
+    for (int phase = 0; phase < 4; ++phase) {
+        for (int t = blockIdx.x; t < op.psd_ntiles; t += gridDim.x) {
+            // cone of tile t: last c with toff[c] <= t
+            int lo = 0, hi = op.npsd - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (__ldg(op.psd_toff + mid) <= t) lo = mid; else hi = mid - 1;
+            }
+            const int c = lo, dd = op.psd_d[c], off = op.psd_off[c];
+            const int nt = (dd + PT - 1) / PT, lt = t - __ldg(op.psd_toff + c);
+            const int i0 = (lt % nt) * PT, j0 = (lt / nt) * PT;
+            const long long uo = op.psd_uoff[c];
+            const double* U = op.psd_U + uo;
+            double* W1 = op.psd_w1 + uo;
+            double* W2 = op.psd_w2 + uo;
+            const double* yc = y + off;
+            if (op.psd_ident[c]) {  // Dpi = I on this cone
+                if (phase == 3)
+                    for (int e = threadIdx.x; e < PT * PT; e += blockDim.x) {
+                        const int i = i0 + e % PT, j = j0 + e / PT;
+                        if (i <= j && j < dd) out[off + (long long)j * (j + 1) / 2 + i] = __ldcg(yc + (long long)j * (j + 1) / 2 + i);
+                    }
+                continue;
+            }
+            if (phase == 0) {  // W1 = U' X
+                psd_tile_gemm(dd, i0, j0, false, true, As, Bs,
+                    [&](int i, int k) { return U[k + (long long)i * dd]; },
+                    [&](int k, int j) {
+                        const int r = k < j ? k : j, cc = k < j ? j : k;
+                        const double v = __ldcg(yc + (long long)cc * (cc + 1) / 2 + r);
+                        return k == j ? v * dscale : v;
+                    },
+                    [&](int i, int j, double v) { W1[i + (long long)j * dd] = v; });
+            } else if (phase == 1) {  // W2 = (W1 U) o B
+                const double* Bm = op.psd_Bm + uo;
+                psd_tile_gemm(dd, i0, j0, true, true, As, Bs,
+                    [&](int i, int k) { return __ldcg(W1 + i + (long long)k * dd); },
+                    [&](int k, int j) { return U[k + (long long)j * dd]; },
+                    [&](int i, int j, double v) { W2[i + (long long)j * dd] = v * Bm[i + (long long)j * dd]; });
+            } else if (phase == 2) {  // W1 = U W2
+                psd_tile_gemm(dd, i0, j0, true, true, As, Bs,
+                    [&](int i, int k) { return U[i + (long long)k * dd]; },
+                    [&](int k, int j) { return __ldcg(W2 + k + (long long)j * dd); },
+                    [&](int i, int j, double v) { W1[i + (long long)j * dd] = v; });
+            } else if (i0 <= j0 + PT - 1) {  // out = vec(W1 U'), tiles touching the upper triangle
+                psd_tile_gemm(dd, i0, j0, true, false, As, Bs,
+                    [&](int i, int k) { return __ldcg(W1 + i + (long long)k * dd); },
+                    [&](int k, int j) { return U[j + (long long)k * dd]; },
+                    [&](int i, int j, double v) {
+                        if (i <= j) out[off + (long long)j * (j + 1) / 2 + i] = i == j ? v * oscale : v;
+                    });
+            }
         }
-    }
-    d.sync();
-    for (int c = 0; c < op.npsd; ++c) {  // W1 = U' X
-        const int dd = op.psd_d[c];
-        const long long uo = op.psd_uoff[c];
-        if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_U + uo, true, op.psd_w0 + uo, false, nullptr, op.psd_w1 + uo);
-    }
-    d.sync();
-    for (int c = 0; c < op.npsd; ++c) {  // W2 = (W1 U) o B
-        const int dd = op.psd_d[c];
-        const long long uo = op.psd_uoff[c];
-        if (!op.psd_ident[c])
-            psd_gemm_phase(d, dd, op.psd_w1 + uo, false, op.psd_U + uo, false, op.psd_Bm + uo, op.psd_w2 + uo);
-    }
-    d.sync();
-    for (int c = 0; c < op.npsd; ++c) {  // W1 = U W2
-        const int dd = op.psd_d[c];
-        const long long uo = op.psd_uoff[c];
-        if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_U + uo, false, op.psd_w2 + uo, false, nullptr, op.psd_w1 + uo);
-    }
-    d.sync();
-    for (int c = 0; c < op.npsd; ++c) {  // W0 = W1 U'   (identity cones keep X in W0)
-        const int dd = op.psd_d[c];
-        const long long uo = op.psd_uoff[c];
-        if (!op.psd_ident[c]) psd_gemm_phase(d, dd, op.psd_w1 + uo, false, op.psd_U + uo, true, nullptr, op.psd_w2 + uo);
-    }
-    d.sync();
-    for (int c = 0; c < op.npsd; ++c) {  // vec
-        const int dd = op.psd_d[c], off = op.psd_off[c];
-        const double* R = (op.psd_ident[c] ? op.psd_w0 : op.psd_w2) + op.psd_uoff[c];
-        const int tri = dd * (dd + 1) / 2;
-        for (int e = d.gtid; e < tri; e += d.gthreads) {
-            // e -> (r, cc) with cc(cc+1)/2 + r = e
-            int cc = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-            while ((long long)(cc + 1) * (cc + 2) / 2 <= e) ++cc;
-            while ((long long)cc * (cc + 1) / 2 > e) --cc;
-            int r = e - cc * (cc + 1) / 2;
-            double val = __ldcg(R + r + (long long)cc * dd);
-            if (!transpose && r == cc) val *= 0.5;
-            out[off + e] = val;
-        }
+        if (phase < 3) d.sync();
     }
     // caller syncs
 }
@@ -1097,6 +1151,8 @@ ConicOpView conic_view(diffopt_b200_ctx* ctx, bool stream_blocks = false) {
     o.psd_U = s.psd_U.as<double>();
     o.psd_Bm = s.psd_Bm.as<double>();
     o.psd_ident = s.psd_ident.as<int>();
+    o.psd_toff = s.psd_toff.as<int>();
+    o.psd_ntiles = (int)s.psd_ntiles;
     o.psd_w0 = s.psd_work.as<double>();
     o.psd_w1 = o.psd_w0 + s.psd_sumd2;
     o.psd_w2 = o.psd_w1 + s.psd_sumd2;

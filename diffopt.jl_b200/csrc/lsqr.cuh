@@ -38,6 +38,8 @@ struct ConicOpView {
     const double* psd_U;       // eigenvectors, column-major d x d per cone
     const double* psd_Bm;      // B matrix, d x d per cone
     const int* psd_ident;      // 1 if all eigenvalues >= 0 (Dpi = I)
+    const int* psd_toff;       // first 32 x 32 output tile of each cone in the flattened tile list (npsd + 1 entries)
+    int psd_ntiles;
     double* psd_w0;            // 3 scratch matrices per cone (d x d each)
     double* psd_w1;
     double* psd_w2;

@@ -356,9 +356,10 @@ int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const
         if ((size_t)16 * d * d <= smem_cap) continue;
         int b = (int)(smem_cap / ((size_t)32 * d));  // 2 matrices x 2b columns x d doubles
         if (b > 32) b = 32;
+        if (b > d / 20) b = d / 20 < 4 ? 4 : d / 20;  // measured on B200 (d = 200): 10 CTAs x 10-column blocks beat 4 x 25
         if (const char* e = getenv("DIFFOPT_B200_PSD_BLOCK")) {  // tuning knob: block width of the block Jacobi
             const int w = atoi(e);
-            if (w >= 1 && w < b) b = w;
+            if (w >= 1 && (size_t)32 * w * d <= smem_cap && w <= 32) b = w;
         }
         if (b < 1) BAD_ARG(ctx, "conic_setup: PSD side too large for the block Jacobi eigensolver");
         int nblk = (d + b - 1) / b;
