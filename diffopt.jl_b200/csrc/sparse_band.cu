@@ -352,6 +352,133 @@ __global__ void __launch_bounds__(32 * S_WARPS) band_solve_kernel(int N, int kl,
     }
 }
 
+// Register-window sweeps for narrow bands (kl <= 32, kv = kl + ku <= 64: the MPC case).  Same arithmetic as
+// band_solve_kernel (dgbtrs), but the live part of the right-hand side sits in two (forward) / three (backward)
+// registers per lane, pivot swaps and the broadcast of x_j are warp shuffles, and the multipliers of 32 columns at a
+// time are staged for all warps of the CTA in a 3-slot shared-memory ring by cp.async two blocks ahead -- one
+// __syncthreads per 32 columns, nothing but SHFL -> (select | DMUL) -> DFMA on the per-column dependency chain.
+// U's diagonal is applied as a reciprocal computed off the chain (one rounding apart from dgbtrs's division).
+#ifndef R_WARPS_DEF
+#define R_WARPS_DEF 4
+#endif
+constexpr int R_WARPS = R_WARPS_DEF;
+constexpr int R_LROW = 32, R_UROW = 64;
+constexpr int R_SLOT = 32 * R_UROW + 32;  // doubles per ring slot (backward layout: 32 columns x 64 + 32 diagonals)
+
+__global__ void __launch_bounds__(32 * R_WARPS) band_solve_reg_kernel(int N, int kl, int ku, const double* __restrict__ AB,
+                                                                      const int* __restrict__ ipiv, const int32_t* __restrict__ perm,
+                                                                      int nrhs, double* __restrict__ Y, double* __restrict__ X) {
+    extern __shared__ __align__(16) double ring[];  // 3 * R_SLOT doubles
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x * R_WARPS + warp;
+    const bool active = r < nrhs;
+    const int kv = kl + ku;
+    const size_t ldab = (size_t)(2 * kl + ku + 1);
+    double* y = Y + (size_t)(active ? r : 0) * N;
+    double* x = X + (size_t)(active ? r : 0) * N;
+    const int nblk = (N + 31) >> 5;
+    auto cp8 = [](double* dst, const double* src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    // ---------------- forward: y <- L^-1 P y ----------------
+    auto load_L = [&](int b, int slot) {  // multipliers of columns 32 b .. 32 b + 31 : Ls[c][i - 1], zeros elsewhere
+        double* Ls = ring + (size_t)slot * R_SLOT;
+        if (b < nblk)
+            for (int e = tid; e < 32 * R_LROW; e += 32 * R_WARPS) {
+                const int c = e >> 5, i = e & 31, j = 32 * b + c;
+                if (j < N && i < min(kl, N - 1 - j)) cp8(Ls + e, AB + (size_t)j * ldab + kv + 1 + i);
+                else Ls[e] = 0.0;
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_L(0, 0);
+    load_L(1, 1);
+    double w0 = (active && lane < N) ? y[lane] : 0.0;
+    double w1 = (active && 32 + lane < N) ? y[32 + lane] : 0.0;
+    int pcur = lane < N ? ipiv[lane] : 0;
+    for (int b = 0; b < nblk; ++b) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();  // block b has landed for every warp; everyone is done with block b - 1
+        load_L(b + 2, (b + 2) % 3);
+        const int j0 = 32 * b;
+        const double nxt = (active && j0 + 64 + lane < N) ? y[j0 + 64 + lane] : 0.0;
+        const int pnext = (j0 + 32 + lane < N) ? ipiv[j0 + 32 + lane] : 0;
+        const double* Ls = ring + (size_t)(b % 3) * R_SLOT;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+            if (j0 + jj < N) {
+                const int p = __shfl_sync(0xffffffffu, pcur, jj) - j0;  // jj <= p <= jj + kl < 64
+                const double xj = __shfl_sync(0xffffffffu, w0, jj);
+                const double xp = __shfl_sync(0xffffffffu, p < 32 ? w0 : w1, p & 31);
+                if (p != jj) {
+                    if (lane == jj) w0 = xp;
+                    if (p < 32) {
+                        if (lane == p) w0 = xj;
+                    } else if (lane == p - 32) {
+                        w1 = xj;
+                    }
+                }
+                const double l = Ls[jj * R_LROW + ((lane - jj - 1) & 31)];
+                if (lane > jj) w0 = fma(-l, xp, w0);
+                else w1 = fma(-l, xp, w1);
+            }
+        }
+        if (active && j0 + lane < N) y[j0 + lane] = w0;
+        w0 = w1;
+        w1 = nxt;
+        pcur = pnext;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---------------- backward: x <- U^-1 y, scattered through perm ----------------
+    auto load_U = [&](int b, int slot) {  // Us[c][i - 1] = U(j - i, j), i = 1 .. kv; diagonals behind the 32 columns
+        double* Us = ring + (size_t)slot * R_SLOT;
+        if (b >= 0)
+            for (int e = tid; e < 32 * R_UROW + 32; e += 32 * R_WARPS) {
+                if (e < 32 * R_UROW) {
+                    const int c = e >> 6, i = e & 63, j = 32 * b + c;
+                    if (j < N && i < min(kv, j)) cp8(Us + e, AB + (size_t)j * ldab + kv - 1 - i);
+                    else Us[e] = 0.0;
+                } else {
+                    const int c = e - 32 * R_UROW, j = 32 * b + c;
+                    if (j < N) cp8(Us + e, AB + (size_t)j * ldab + kv);
+                    else Us[e] = 1.0;
+                }
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_U(nblk - 1, 0);
+    load_U(nblk - 2, 1);
+    auto ld = [&](int base) { return (active && base + lane >= 0 && base >= 0 && base + lane < N) ? y[base + lane] : 0.0; };
+    double v2 = ld(32 * (nblk - 1)), v1 = ld(32 * (nblk - 2)), v0 = ld(32 * (nblk - 3));
+    for (int b = nblk - 1, it = 0; b >= 0; --b, ++it) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        load_U(b - 2, (it + 2) % 3);
+        const int j0 = 32 * b;
+        const double nxt = ld(32 * (b - 3));
+        const double* Us = ring + (size_t)(it % 3) * R_SLOT;
+        const double rinv = 1.0 / Us[32 * R_UROW + lane];
+#pragma unroll
+        for (int jj = 31; jj >= 0; --jj) {
+            if (j0 + jj < N) {
+                const double xj = __shfl_sync(0xffffffffu, v2, jj) * __shfl_sync(0xffffffffu, rinv, jj);
+                if (lane == jj) v2 = xj;
+                const double ua = Us[jj * R_UROW + ((jj - lane - 1) & 63)];
+                const double ub = Us[jj * R_UROW + jj + 31 - lane];
+                if (lane < jj) v2 = fma(-ua, xj, v2);
+                else v0 = fma(-ua, xj, v0);
+                v1 = fma(-ub, xj, v1);
+            }
+        }
+        if (active && j0 + lane < N) x[perm[j0 + lane]] = v2;
+        v2 = v1;
+        v1 = v0;
+        v0 = nxt;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 }  // namespace
 
 extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval,
@@ -488,7 +615,12 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
     band_solve_kernel<QL><<<(unsigned)blocks, 32 * S_WARPS, 0, ctx->stream>>>((int)S.N, S.kl, S.ku, S.AB.as<double>(), S.ipiv.as<int>(), \
                                                                               S.perm.as<int32_t>(), (int)nrhs, S.work.as<double>(),     \
                                                                               (double*)dX)
-    if (S.kl <= 32) BAND_SOLVE(1);
+    if (S.kl <= 32 && S.kl + S.ku <= 64 && !getenv("DIFFOPT_B200_BAND_SOLVE_OLD")) {
+        const size_t rbytes = sizeof(double) * 3 * R_SLOT;
+        DO_CUDA(ctx, cudaFuncSetAttribute(band_solve_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rbytes));
+        band_solve_reg_kernel<<<(unsigned)((nrhs + R_WARPS - 1) / R_WARPS), 32 * R_WARPS, rbytes, ctx->stream>>>(
+            (int)S.N, S.kl, S.ku, S.AB.as<double>(), S.ipiv.as<int>(), S.perm.as<int32_t>(), (int)nrhs, S.work.as<double>(), (double*)dX);
+    } else if (S.kl <= 32) BAND_SOLVE(1);
     else if (S.kl <= 64) BAND_SOLVE(2);
     else if (S.kl <= 128) BAND_SOLVE(4);
     else BAND_SOLVE(8);
