@@ -211,6 +211,89 @@ __global__ void __launch_bounds__(F_THREADS, 1) band_lu_kernel(int N, int kl, in
     if (tid == 0) *info = 0;
 }
 
+// Narrow bands (kl <= 31): the same elimination with ONE barrier per column.  Every warp loads the pivot column into
+// registers and runs the pivot search, the Newton-refined reciprocal and the multipliers redundantly (packed-key redux
+// + shuffles: no shared scalars, no extra barriers), then owns whole window columns: it reads a column's kl + 1 live
+// rows into registers, takes the pivot-row and top-row entries by shuffle and writes the swapped + updated column back
+// -- no cross-warp hazard inside a step.  Column j retires straight to global memory (U part from the window, pivot
+// and multipliers from registers), so the window copy of the pivot column is never written while other warps read it.
+// Variants measured on config 3 (N = 240 000, kl = ku = 19), factorisation time: three barriers per column 252 ms; this
+// kernel 164 ms; the same with the retiring column leaving by a bulk (TMA) store one step later 172 ms; named-barrier
+// look-ahead with an owner warp per column 159-176 ms; two warps with lanes = columns in the update 205-240 ms.  The
+// column step (~1300 clk) is bound by the dependent instruction chain of a warp (clock counters: pivot search 120,
+// reciprocal + multipliers 150, one window column ~190 clk), not by arithmetic or memory.
+__device__ __forceinline__ double band_fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, fma(e, e, e), r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1) band_lu_warp_kernel(int N, int kl, int ku, double* __restrict__ AB, int* __restrict__ ipiv,
+                                                                    int* info, int WC) {
+    extern __shared__ __align__(16) double s_dyn[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthr = blockDim.x, nwarp = nthr >> 5;
+    const int kv = kl + ku;
+    const int ldab_i = 2 * kl + ku + 1;
+    const size_t ldab = (size_t)ldab_i;
+    const int wmask = WC - 1;
+    auto col = [&](int c) -> double* { return s_dyn + (size_t)(c & wmask) * ldab; };
+    constexpr int PD = 6;  // columns kept in flight by cp.async ahead of the window
+    {
+        const int ncol = min(N, kv + 1 + PD);
+        for (int e = tid; e < ncol * ldab_i; e += nthr) s_dyn[e] = AB[e];
+        __syncthreads();
+    }
+    int ju = 0;
+    for (int j = 0; j < N; ++j) {
+        const double* colj = col(j);
+        const int km = min(kl, N - 1 - j);
+        {
+            const int cin = j + kv + 1 + PD;
+            if (cin < N && tid < ldab_i) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(col(cin) + tid);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(AB + (size_t)cin * ldab + tid) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        // pivot search (same packed key as band_lu_kernel), redundantly in every warp
+        const double mine = lane <= km ? colj[kv + lane] : 0.0;
+        unsigned key = lane <= km ? (((unsigned)__double2hiint(fabs(mine)) & 0xFFFFFF00u) | (unsigned)(255 - lane)) : 0u;
+        key = __reduce_max_sync(0xffffffffu, key);
+        if (!(key >> 8)) {  // the whole column below the diagonal is zero (or denormal): singular
+            if (tid == 0) *info = j + 1;
+            return;
+        }
+        const int jp = 255 - (int)(key & 0xFFu);
+        const double piv = __shfl_sync(0xffffffffu, mine, jp), diag = __shfl_sync(0xffffffffu, mine, 0);
+        const double l = (lane == jp ? diag : mine) * band_fast_rcp(piv);  // multiplier of window row `lane` (lane >= 1)
+        ju = max(ju, min(j + ku + jp, N - 1));
+        const int nc = ju - j;
+        if (warp == nwarp - 1) {  // column j retires (the last warp has the fewest window columns)
+            double* out = AB + (size_t)j * ldab;
+            for (int i = lane; i < kv; i += 32) out[i] = colj[i];
+            if (lane == 0) {
+                out[kv] = piv;
+                ipiv[j] = j + jp;
+            } else if (lane <= km) {
+                out[kv + lane] = l;
+            }
+        }
+        for (int c = 1 + warp; c <= nc; c += nwarp) {  // a warp per window column, lanes down the rows
+            double* colc = col(j + c) + kv - c;
+            const double old = lane <= km ? colc[lane] : 0.0;
+            const double top = __shfl_sync(0xffffffffu, old, jp), bot = __shfl_sync(0xffffffffu, old, 0);
+            if (lane <= km) colc[lane] = lane == 0 ? top : fma(-l, top, lane == jp ? bot : old);
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(PD - 1) : "memory");  // column j + kv + 1 has landed
+        __syncthreads();
+    }
+    if (tid == 0) *info = 0;
+}
+
 // Y[i, r] = B[perm[i], r]: right-hand sides into the RCM ordering (so that the sweeps stream contiguously)
 __global__ void band_gather_kernel(int64_t N, int64_t nrhs, const int32_t* __restrict__ perm, const double* __restrict__ B,
                                    double* __restrict__ Y) {
@@ -561,15 +644,21 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
     {
         // shared-memory window variant when kv + 2 columns of the band fit (narrow bands, the MPC case)
         int WC = 1;
-        while (WC < kl + ku + 2 + 6 + 1) WC <<= 1;  // window + columns in flight (PD = 6) + the retiring column
+        while (WC < kl + ku + 2 + 8 + 2) WC <<= 1;  // window + columns in flight (PD <= 8) + the retiring column
         const size_t wbytes = sizeof(double) * (size_t)WC * (size_t)ldab;
         if (wbytes + 16 * 1024 <= ctx->smem_optin && ldab <= F_THREADS) {
             DO_CUDA(ctx, cudaFuncSetAttribute(band_lu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
             // one warp per window column in the update: as many warps as the window has columns (at least 8)
             int thr = 32 * std::min(16, std::max(8, kl + ku + 1));  // measured: 16 warps is the sweet spot (barrier cost vs update width)
             if (getenv("DIFFOPT_B200_BAND_THREADS")) thr = atoi(getenv("DIFFOPT_B200_BAND_THREADS"));
-            band_lu_kernel<true><<<1, thr, wbytes, ctx->stream>>>((int)N, kl, ku, S.AB.as<double>(), S.ipiv.as<int>(),
-                                                                        ctx->info.as<int>(), WC);
+            if (kl <= 31 && !getenv("DIFFOPT_B200_BAND_LU_OLD")) {
+                DO_CUDA(ctx, cudaFuncSetAttribute(band_lu_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
+                band_lu_warp_kernel<<<1, thr, wbytes, ctx->stream>>>((int)N, kl, ku, S.AB.as<double>(), S.ipiv.as<int>(),
+                                                                    ctx->info.as<int>(), WC);
+            } else {
+                band_lu_kernel<true><<<1, thr, wbytes, ctx->stream>>>((int)N, kl, ku, S.AB.as<double>(), S.ipiv.as<int>(),
+                                                                      ctx->info.as<int>(), WC);
+            }
         } else {
             band_lu_kernel<false><<<1, F_THREADS, 0, ctx->stream>>>((int)N, kl, ku, S.AB.as<double>(), S.ipiv.as<int>(),
                                                                     ctx->info.as<int>(), 1);
