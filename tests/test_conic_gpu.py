@@ -48,6 +48,44 @@ def test_lsqr_csc_matches_oracle(ctx):
     assert rel(xt, olsqr.lsqr(A.T.tocsc(), bt)) <= RTOL_LSQR
 
 
+@pytest.mark.parametrize("mode", ["cluster", "gstream", "grid"])
+def test_persistent_lsqr_variants_match_oracle(ctx, monkeypatch, mode):
+    """The three persistent LSQR drivers (single cluster with hardware barriers / one CTA per SM with row-block SpMV /
+    lane-group grid) on an explicit CSC matrix and on the conic operator: same iterates as the oracle at matched
+    iteration counts, same answer at convergence."""
+    monkeypatch.setenv("DIFFOPT_B200_LSQR", mode)
+    lsqr = diffopt_b200.submodule("lsqr")
+    cm = diffopt_b200.submodule("conic")
+    rng = np.random.default_rng(8)
+    A = (sp.random(700, 450, density=0.03, random_state=3) + sp.eye(700, 450)).tocsc()
+    A = sp.vstack([A, sp.csc_matrix((3, 450))]).tocsc()          # empty rows
+    A[5, :] = rng.normal(size=450)                                # one dense row (long-row path of the row-block SpMV)
+    A = A.tocsc()
+    b = rng.normal(size=703)
+    for mi in (1, 6, 30):
+        xg, sg = lsqr.lsqr_csc(ctx, A, b, maxiter=mi)
+        xc, ic = olsqr.lsqr(A, b, maxiter=mi, return_info=True)
+        assert sg["itn"] == ic.itn == mi
+        # the dense row makes this matrix ill conditioned: rounding differences (summation order) grow with the
+        # iteration count, so the tight comparison is at small counts
+        assert rel(xg, xc) <= (1e-10 if mi <= 6 else 1e-5), (mi, rel(xg, xc))
+    x, st = lsqr.lsqr_csc(ctx, A, b)
+    assert rel(x, olsqr.lsqr(A, b)) <= RTOL_LSQR
+    bt = rng.normal(size=450)
+    xt, _ = lsqr.lsqr_csc(ctx, A, bt, trans=True, maxiter=4)
+    assert rel(xt, olsqr.lsqr(A.T.tocsc(), bt, maxiter=4)) <= 1e-10
+    d = bench_data.conic_config4(n=300, n_zero=30, n_nonneg=200, n_soc=20, soc_dim=6, nnz_per_row=5, seed=31)
+    model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+    model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
+    cache = _oracle_cache(d)
+    for iters in (1, 2, 3):
+        tol = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=iters)
+        model.tolerances = tol
+        model.reverse_differentiate(d["seed"])
+        assert model.last_stats["itn"] == iters
+        assert rel(model.back_grad_cache["g"], oconic.reverse(cache, d["seed"], **tol)) <= 1e-9
+
+
 def test_lp_config1_lsqr_on_kkt(ctx):
     """BASELINE config 1: LP n=200, m=100 -> rank-deficient KKT, minimum-norm LSQR limit."""
     qpm = diffopt_b200.submodule("qp")

@@ -300,7 +300,7 @@ def _banded_random(N, bw, seed):
     return sp.csc_matrix(M[P][:, P])
 
 
-@pytest.mark.parametrize("N,bw,nrhs", [(1, 0, 1), (50, 3, 2), (400, 17, 9), (3000, 40, 33)])
+@pytest.mark.parametrize("N,bw,nrhs", [(1, 0, 1), (50, 3, 2), (400, 17, 9), (333, 30, 3), (1000, 31, 5), (3000, 40, 33)])
 def test_sparse_band_factorization(ctx, N, bw, nrhs):
     """Sparse direct path (banded LU after RCM): LHS and LHS', many right-hand sides, against a dense/sparse CPU solve."""
     import scipy.sparse.linalg as spla
@@ -331,6 +331,30 @@ def test_sparse_mpc_kkt_forward_directions(ctx):
     assert (np.linalg.norm(X - ref, axis=0) / np.linalg.norm(ref, axis=0)).max() <= RTOL_DIRECT
     res = np.linalg.norm(K.T @ X - R, axis=0) / np.linalg.norm(R, axis=0)
     assert res.max() < 1e-9
+
+
+def test_sparse_band_kernel_variants_agree(ctx, monkeypatch):
+    """Narrow bands run the one-barrier LU and the register-window sweeps; the general kernels (any band up to 255)
+    must give the same factorisation and solutions (same pivots: identical up to the reciprocal-vs-division rounding)."""
+    import scipy.sparse.linalg as spla
+    lsq = diffopt_b200.submodule("lsqr")
+    d = bench_data.mpc_config3(T=150)
+    K = d["K"]
+    R = np.random.default_rng(4).standard_normal((K.shape[0], 7))
+    ref = spla.splu(K.tocsc()).solve(R)
+    sols = {}
+    for name, env in (("new", {}), ("old_lu", {"DIFFOPT_B200_BAND_LU_OLD": "1"}),
+                      ("old_solve", {"DIFFOPT_B200_BAND_SOLVE_OLD": "1"})):
+        for k in ("DIFFOPT_B200_BAND_LU_OLD", "DIFFOPT_B200_BAND_SOLVE_OLD"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        F = lsq.SparseFactorization(ctx, K)
+        assert F.bandwidth <= 31
+        sols[name] = F.solve(R)
+        assert (np.linalg.norm(sols[name] - ref, axis=0) / np.linalg.norm(ref, axis=0)).max() <= RTOL_DIRECT
+    for other in ("old_lu", "old_solve"):
+        assert np.linalg.norm(sols["new"] - sols[other]) <= 1e-12 * np.linalg.norm(sols["new"])
 
 
 def test_sparse_setup_rejects_and_reports(ctx):
