@@ -33,6 +33,8 @@ SIGNATURES = {
     "diffopt_b200_host_free": (C.c_int32, [vp]),
     "diffopt_b200_last_kernel_ms": (C.c_double, [vp]),
     "diffopt_b200_qp_batch_solve": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 17 + [C.c_int32]),
+    "diffopt_b200_qp_batch_solve_async": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 17),
+    "diffopt_b200_synchronize": (C.c_int32, [vp]),
     "diffopt_b200_qp_batch_setup": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 7 + [C.c_int32]),
     "diffopt_b200_qp_batch_reverse": (C.c_int32, [vp, vp, vp, vp, C.c_int32]),
     "diffopt_b200_qp_batch_forward": (C.c_int32, [vp] * 9 + [C.c_int32]),

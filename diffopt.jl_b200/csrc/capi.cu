@@ -113,7 +113,7 @@ static int32_t finish_info(diffopt_b200_ctx* ctx, int64_t B, int* dinfo, int32_t
 }
 
 static int32_t qp_solve_common(diffopt_b200_ctx* ctx, QpSolveArgs a, double* fwd_user, double* rev_user,
-                               int32_t* info_user, int memspace) {
+                               int32_t* info_user, int memspace, bool async = false) {
     const int64_t B = a.B;
     const int N = a.n + a.m + a.p;
     void *dfwd = nullptr, *drev = nullptr;
@@ -135,6 +135,11 @@ static int32_t qp_solve_common(diffopt_b200_ctx* ctx, QpSolveArgs a, double* fwd
     DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     DO_CUDA(ctx, stage_out_finish(ctx, dfwd, fwd_user, sizeof(double) * B * N, memspace));
     DO_CUDA(ctx, stage_out_finish(ctx, drev, rev_user, sizeof(double) * B * N, memspace));
+    if (async) {  // status is collected by diffopt_b200_synchronize
+        ctx->async_B = B;
+        ctx->async_info = dinfo;
+        return 0;
+    }
     std::vector<int> hinfo;
     rc = finish_info(ctx, B, dinfo, info_user, memspace, hinfo);
     float ms = 0.f;
@@ -187,6 +192,45 @@ int32_t diffopt_b200_qp_batch_solve(diffopt_b200_ctx* ctx, int64_t B, int32_t n,
     }
     if (rev_out) { STAGE(13, seed, dl_dz, n) }
     return qp_solve_common(ctx, a, fwd_out, rev_out, info, memspace);
+}
+
+int32_t diffopt_b200_qp_batch_solve_async(diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
+                                          const double* Q, const double* G, const double* A, const double* h,
+                                          const double* z, const double* lam, const double* nu, const double* dQ,
+                                          const double* dq, const double* dG, const double* dh, const double* dA,
+                                          const double* db, const double* dl_dz, double* fwd_out, double* rev_out,
+                                          int32_t* info) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    if (int32_t rc = check_shape(ctx, B, n, m, p)) return rc;
+    if (B == 0) return 0;
+    if (!Q || !z || (m > 0 && (!G || !h || !lam)) || (p > 0 && (!A || !nu)))
+        BAD_ARG(ctx, "qp_batch_solve_async: Q, z (and G, h, lam when m > 0; A, nu when p > 0) are required");
+    if (rev_out && !dl_dz) BAD_ARG(ctx, "qp_batch_solve_async: rev_out requested without dl_dz");
+    if (!fwd_out && !rev_out) BAD_ARG(ctx, "qp_batch_solve_async: nothing to compute (fwd_out and rev_out are NULL)");
+    QpSolveArgs a{};
+    a.B = B; a.n = n; a.m = m; a.p = p;
+    a.Q = Q; a.G = G; a.A = A; a.h = h; a.z = z; a.lam = lam; a.nu = nu;
+    if (fwd_out) { a.dQ = dQ; a.dq = dq; a.dG = dG; a.dh = dh; a.dA = dA; a.db = db; }
+    if (rev_out) a.seed = dl_dz;
+    return qp_solve_common(ctx, a, fwd_out, rev_out, info, DIFFOPT_B200_DEVICE, true);
+}
+
+int32_t diffopt_b200_synchronize(diffopt_b200_ctx* ctx) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    int32_t rc = 0;
+    if (ctx->async_info && ctx->async_B > 0) {
+        std::vector<int> hinfo;
+        rc = finish_info(ctx, ctx->async_B, ctx->async_info, nullptr, DIFFOPT_B200_DEVICE, hinfo);
+        ctx->async_info = nullptr;
+        ctx->async_B = 0;
+    } else {
+        DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    return rc;
 }
 
 int32_t diffopt_b200_qp_batch_setup(diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,

@@ -89,6 +89,20 @@ int32_t diffopt_b200_qp_batch_solve(
     const double* dA, const double* db, const double* dl_dz,
     double* fwd_out, double* rev_out, int32_t* info, int32_t memspace);
 
+/* Stream-ordered form for device-resident pipelines (memspace must be DIFFOPT_B200_DEVICE, e.g. CUDA.jl arrays):
+ * the same work is enqueued on the ctx stream and the call returns without waiting, so consecutive batches run back
+ * to back with no host round trip in between.  `diffopt_b200_synchronize` waits for the stream and returns the status
+ * of the LAST enqueued call (0, or first failing instance + 1) -- the blocking form above is this pair in one call,
+ * which is what the reference's `@elapsed` timing (QuadraticProgram.jl:317,358) needs. */
+int32_t diffopt_b200_qp_batch_solve_async(
+    diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
+    const double* Q, const double* G, const double* A, const double* h,
+    const double* z, const double* lam, const double* nu,
+    const double* dQ, const double* dq, const double* dG, const double* dh,
+    const double* dA, const double* db, const double* dl_dz,
+    double* fwd_out, double* rev_out, int32_t* info);
+int32_t diffopt_b200_synchronize(diffopt_b200_ctx* ctx);
+
 /* Two-phase form mirroring the reference's cache (`_gradient_cache` builds LHS once,
  * QuadraticProgram.jl:182-213; seeds may then change): setup keeps the problem data
  * resident on the device, forward/reverse solve against it. */

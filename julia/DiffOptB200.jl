@@ -162,6 +162,25 @@ function qp_batch_solve(ctx::Context, Q, G, A, h, z, lam, nu;
     return (forward = split(fwd), reverse = split(rev), info = info)
 end
 
+# Stream-ordered form for device-resident batches (pointers of CUDA.jl arrays, `pointer(x)` converted to Ptr{Float64}):
+# enqueue any number of batches, then `synchronize(ctx)` waits and throws for the status of the last one.
+function qp_batch_solve_async(ctx::Context, B::Integer, n::Integer, m::Integer, p::Integer,
+                              Q::Ptr{Float64}, G::Ptr{Float64}, A::Ptr{Float64}, h::Ptr{Float64}, z::Ptr{Float64},
+                              lam::Ptr{Float64}, nu::Ptr{Float64}, dQ::Ptr{Float64}, dq::Ptr{Float64},
+                              dG::Ptr{Float64}, dh::Ptr{Float64}, dA::Ptr{Float64}, db::Ptr{Float64},
+                              dl_dz::Ptr{Float64}, fwd::Ptr{Float64}, rev::Ptr{Float64}, info::Ptr{Int32})
+    rc = ccall((:diffopt_b200_qp_batch_solve_async, LIB), Int32,
+               (Ptr{Cvoid}, Int64, Int32, Int32, Int32,
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+               ctx.handle, B, n, m, p, Q, G, A, h, z, lam, nu, dQ, dq, dG, dh, dA, db, dl_dz, fwd, rev, info)
+    check(ctx, rc)
+    return nothing
+end
+
+synchronize(ctx::Context) = check(ctx, ccall((:diffopt_b200_synchronize, LIB), Int32, (Ptr{Cvoid},), ctx.handle))
+
 # ------------------------------------------------------------------------------------------------
 # (3) ConicProgram backend: _gradient_cache / forward / reverse (src/ConicProgram/ConicProgram.jl:172-394)
 #     cone_type: 0 Zeros, 1 Nonnegatives, 2 SecondOrderCone, 3 PositiveSemidefiniteConeTriangle (row order of A)

@@ -253,6 +253,56 @@ def test_singular_instance_inside_headline_batch(ctx):
     assert rel_err(rev[keep], orv).max() <= RTOL_DIRECT
 
 
+def test_stream_ordered_batch_calls(ctx):
+    """diffopt_b200_qp_batch_solve_async + diffopt_b200_synchronize (device pointers, no host round trip between
+    batches): three different batches enqueued back to back give the blocking call's results; the status of the last
+    call (a batch with an exactly singular instance) surfaces at synchronize."""
+    import torch
+    capi = diffopt_b200.submodule("_capi")
+    qpm = diffopt_b200.submodule("qp")
+    lib = ctx.lib
+    dev = torch.device("cuda", 0)
+    fields = ["Q", "G", "A", "h", "z", "lam", "nu", "dQ", "dq", "dG", "dh", "dA", "db", "seed"]
+    batches, outs = [], []
+    for k in range(3):
+        d = bench_data.qp_batch(40 + 8 * k, seed0=7000 + 100 * k)
+        B = d["z"].shape[0]
+        rows = {"Q": 64, "G": 64, "A": 16, "dQ": 64, "dG": 64, "dA": 16}   # matrices go column-major per instance
+        t = {f: torch.from_numpy(qpm.colmajor(d[f], rows[f], 64, B) if f in rows else np.ascontiguousarray(d[f])).to(dev)
+             for f in fields}
+        o = dict(fwd=torch.empty((B, 144), dtype=torch.float64, device=dev),
+                 rev=torch.empty((B, 144), dtype=torch.float64, device=dev),
+                 info=torch.zeros(B, dtype=torch.int32, device=dev))
+        batches.append((d, t, B))
+        outs.append(o)
+    torch.cuda.synchronize()
+    for (d, t, B), o in zip(batches, outs):
+        rc = lib.diffopt_b200_qp_batch_solve_async(ctx.h, B, 64, 64, 16, *[capi.vp(t[f].data_ptr()) for f in fields],
+                                                   capi.vp(o["fwd"].data_ptr()), capi.vp(o["rev"].data_ptr()),
+                                                   capi.vp(o["info"].data_ptr()))
+        assert rc == 0
+    assert lib.diffopt_b200_synchronize(ctx.h) == 0
+    assert lib.diffopt_b200_synchronize(ctx.h) == 0      # idempotent
+    for (d, t, B), o in zip(batches, outs):
+        of, orv = _oracle_batch(d)
+        assert not o["info"].cpu().numpy().any()
+        assert rel_err(o["fwd"].cpu().numpy(), of).max() <= RTOL_DIRECT
+        assert rel_err(o["rev"].cpu().numpy(), orv).max() <= RTOL_DIRECT
+    # a singular instance: lam_i = D_i = 0 and a zero row of G make column n+i of LHS exactly zero
+    d, t, B = batches[0]
+    G = d["G"].copy(); h = d["h"].copy(); lam = d["lam"].copy()
+    G[5, 2, :] = 0.0; lam[5, 2] = 0.0; h[5, 2] = 0.0
+    tG, th, tl = (torch.from_numpy(x).to(dev) for x in (qpm.colmajor(G, 64, 64, B), h, lam))
+    ptrs = {f: capi.vp(t[f].data_ptr()) for f in fields}
+    ptrs.update(G=capi.vp(tG.data_ptr()), h=capi.vp(th.data_ptr()), lam=capi.vp(tl.data_ptr()))
+    o = outs[0]
+    assert lib.diffopt_b200_qp_batch_solve_async(ctx.h, B, 64, 64, 16, *[ptrs[f] for f in fields],
+                                                 capi.vp(o["fwd"].data_ptr()), capi.vp(o["rev"].data_ptr()),
+                                                 capi.vp(o["info"].data_ptr())) == 0
+    assert lib.diffopt_b200_synchronize(ctx.h) == 6      # first failing instance + 1
+    assert o["info"].cpu().numpy()[5] > 0
+
+
 @pytest.mark.parametrize("N,nrhs", [(1, 1), (9, 1), (70, 3), (300, 16), (1100, 5)])
 def test_direct_solve_system_csc(ctx, N, nrhs):
     """`LHS \\ RHS` drop-in (QuadraticProgram.jl:490): CSC and Adjoint{CSC}, one and many right-hand sides."""
