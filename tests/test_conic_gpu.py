@@ -272,6 +272,25 @@ def test_psd_maxcut_200(ctx):
         assert rel(model.dpi_apply(t, transpose=tr), want) <= 1e-8
 
 
+@pytest.mark.parametrize("col_window", [None, 150])
+def test_streaming_lsqr_mid_size_operators(ctx, monkeypatch, col_window):
+    """The multi-kernel (streaming) LSQR with its row-block SpMV on operators of a few 10^4 rows -- uniformly random
+    columns and a stage-structured pattern -- against the oracle's explicit M at small iteration counts."""
+    cm = diffopt_b200.submodule("conic")
+    d = bench_data.conic_config4(n=9000, n_zero=900, n_nonneg=7000, n_soc=500, soc_dim=8, nnz_per_row=7, seed=77,
+                                 col_window=col_window)
+    cache = _oracle_cache(d)
+    monkeypatch.setenv("DIFFOPT_B200_LSQR", "stream")
+    model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+    model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
+    for iters in (1, 2, 3):
+        tol = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=iters)
+        model.tolerances = tol
+        model.reverse_differentiate(d["seed"])
+        assert model.last_stats["itn"] == iters
+        assert rel(model.back_grad_cache["g"], oconic.reverse(cache, d["seed"], **tol)) <= 1e-9
+
+
 def _psd_only_model(ctx, mats):
     """One PSD cone per matrix in `mats`, A = -I (rows = variables), s = 0, y = vec(mat) => v = vec(mat)."""
     cm = diffopt_b200.submodule("conic")
