@@ -414,6 +414,9 @@ __device__ void psd_apply_all(Dev& d, const ConicOpView& op, const double* __res
 }
 
 // Dpi (or Dpi') applied to y -> out, for all cones; ends WITHOUT a grid sync when there is no PSD cone
+// PSD = false compiles the PSD-cone phases out (the cluster / row-block variants and the streaming driver never run
+// problems with PSD cones; their kernels stay small).
+template <bool PSD>
 __device__ void dpi_apply(Dev& d, const ConicOpView& op, const double* __restrict__ y, double* out, bool transpose) {
     for (int i = d.gtid; i < op.m; i += d.gthreads)
         if (op.kind[i] == 0) out[i] = op.diag[i] * __ldcg(y + i);
@@ -427,7 +430,7 @@ __device__ void dpi_apply(Dev& d, const ConicOpView& op, const double* __restric
             soc_apply(op, c, c < op.nsoc, y, out, lig, T);
         }
     }
-    psd_apply_all(d, op, y, out, transpose);
+    if constexpr (PSD) psd_apply_all(d, op, y, out, transpose);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,20 +467,22 @@ __device__ void csr_apply(Dev& d, const CsrView& A, const double* __restrict__ s
 }
 
 // dst = s_src * (M src) + s_dst * dst ; slots: slot (norm), slot+1 (last-row dot)
-// `dst_last` is every thread's private copy of dst[N-1] (all threads compute it identically): with it nobody reads the
-// old last entry from memory, so thread 0 may overwrite it without a second barrier.
+// `src_last` / `dst_last` are every thread's private copies of src[N-1] / dst[N-1] (all threads compute the last row
+// identically): nobody reads those entries from memory, so thread 0 may store the new one right after the barrier
+// that publishes the partial sums, and ||dst||^2 (returned in `norm2`) is complete without another barrier.
 template <bool CL>
 __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const double* __restrict__ src,
-                            double s_src, double* dst, double s_dst, int slot, double& dst_last) {
+                            double s_src, double* dst, double s_dst, int slot, double src_last, double& dst_last,
+                            double& norm2) {
     const int n = op.n, m = op.m, N = n + m + 1;
     double dotacc = 0.0;
     if constexpr (CL) {
         double* prod = cl_prod;
         double acc = 0.0;
         if (!transpose) {
-            dpi_apply(d, op, src + n, op.wc, false);  // wc = Dpi t2
+            dpi_apply<!CL>(d, op, src + n, op.wc, false);  // wc = Dpi t2
             d.sync();
-            const double t3 = __ldcg(src + n + m);
+            const double t3 = src_last;
             const int nbt = op.At.nblk;
             spmv_stream<CL_THREADS, CL_NPT, true>(
                 nbt + op.A.nblk, prod, d.red,
@@ -509,9 +514,9 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
             const double last = -total_of(d, slot + 1) * s_src + s_dst * dst_last;  // -(c't1 + b'wc)
             dst_last = last;
             if (d.gtid == 0) dst[N - 1] = last;
-            if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
+            norm2 = total_of(d, slot) + last * last;
         } else {
-            const double u3 = __ldcg(src + n + m);
+            const double u3 = src_last;
             spmv_stream<CL_THREADS, CL_NPT, true>(  // wc = A u1 - u2 - b u3
                 op.A.nblk, prod, d.red,
                 [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.A; x = src; lb = b; },
@@ -522,7 +527,7 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
                 });
             d.sync();
             double* r2 = op.wc + m;
-            dpi_apply(d, op, op.wc, r2, true);
+            dpi_apply<!CL>(d, op, op.wc, r2, true);
             d.sync();
             spmv_stream<CL_THREADS, CL_NPT, true>(  // rows 0..n-1: -(A' u2)_j - c_j u3
                 op.At.nblk, prod, d.red,
@@ -545,15 +550,15 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
             const double last = total_of(d, slot + 1) * s_src + s_dst * dst_last;
             dst_last = last;
             if (d.gtid == 0) dst[N - 1] = last;
-            if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
+            norm2 = total_of(d, slot) + last * last;
         }
         return;
     }
     if (!transpose) {
         // wc = Dpi t2
-        dpi_apply(d, op, src + n, op.wc, false);
+        dpi_apply<!CL>(d, op, src + n, op.wc, false);
         d.sync();
-        const double t3 = __ldcg(src + n + m);
+        const double t3 = src_last;
         double acc = 0.0;
         // rows 0..n-1:  (A' wc)_j + c_j t3
         spmv_rows<4>(d, op.At, op.wc, [&](int row, double t) {
@@ -577,10 +582,10 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         const double last = -total_of(d, slot + 1) * s_src + s_dst * dst_last;
         dst_last = last;
         if (d.gtid == 0) dst[N - 1] = last;
-        if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
+        norm2 = total_of(d, slot) + last * last;
     } else {
         // r = A u1 - u2 - b u3  -> wc
-        const double u3 = __ldcg(src + n + m);
+        const double u3 = src_last;
         spmv_rows<4>(d, op.A, src, [&](int row, double t) {
             const double u2 = __ldcg(src + n + row);
             op.wc[row] = t - u2 - op.b[row] * u3;
@@ -592,7 +597,7 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         // disjoint, so compute into `tmp = psd_w-independent` region: use op.wc in place is unsafe (SOC reads all
         // entries of its cone) -> stage through dst? no.  Use the dedicated second scratch stored after wc.
         double* r2 = op.wc + m;  // second half of the 2m scratch
-        dpi_apply(d, op, op.wc, r2, true);
+        dpi_apply<!CL>(d, op, op.wc, r2, true);
         d.sync();
         double acc = 0.0;
         // rows 0..n-1: -(A' u2)_j - c_j u3
@@ -613,7 +618,7 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         const double last = total_of(d, slot + 1) * s_src + s_dst * dst_last;
         dst_last = last;
         if (d.gtid == 0) dst[N - 1] = last;
-        if (blockIdx.x == 0 && d.tid == 0) d.partials[slot * d.nblk] += last * last;
+        norm2 = total_of(d, slot) + last * last;
     }
 }
 
@@ -625,13 +630,19 @@ struct OpArgs {
     int nrows, ncols;
 };
 
+// Returns ||dst||^2 (after the update).  The conic operator ends behind its own barrier; the CSR one needs a barrier
+// here before its partial sums can be read.
 template <bool CL>
-__device__ void op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* src, double s_src, double* dst,
-                         double s_dst, int slot, double& dst_last) {
-    if (o.kind == 0)
+__device__ double op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* src, double s_src, double* dst,
+                           double s_dst, int slot, double src_last, double& dst_last) {
+    if (o.kind == 0) {
         csr_apply<CL>(d, adjoint ? o.adj : o.fwd, src, s_src, dst, s_dst, slot);
-    else
-        conic_apply<CL>(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot, dst_last);
+        d.sync();
+        return total_of(d, slot);
+    }
+    double norm2 = 0.0;
+    conic_apply<CL>(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot, src_last, dst_last, norm2);
+    return norm2;
 }
 
 template <int THREADS, int MINB, bool CLUSTER, bool STREAM>
@@ -671,9 +682,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
     double rnorm = beta, arnorm = 0.0;
     if (beta > 0) {
         su = 1.0 / beta;
-        op_apply<STREAM>(d, o, true, u, su, v, 0.0, 2, v_last);   // v_mem = A' u_true
-        d.sync();
-        alpha = sqrt(total_of(d, 2));
+        alpha = sqrt(op_apply<STREAM>(d, o, true, u, su, v, 0.0, 2, u_last, v_last));   // v_mem = A' u_true
     }
     if (alpha > 0) sv = 1.0 / alpha;
     arnorm = alpha * beta;
@@ -689,8 +698,10 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
             // ---- deferred vector update of the previous iteration (or w = v at start), fused with the next
             //      bidiagonalisation product
             double dd = 0.0;
+            // (conic operator: the last entry of v is read from its register copy, see conic_apply)
+            const int ilast = o.kind == 1 ? nc - 1 : -1;
             if (first) {
-                for (int i = d.gtid; i < nc; i += d.gthreads) w[i] = sv * v[i];
+                for (int i = d.gtid; i < nc; i += d.gthreads) w[i] = sv * (i == ilast ? v_last : v[i]);
             } else {
                 const double irho = 1.0 / rho;
                 for (int i = d.gtid; i < nc; i += d.gthreads) {
@@ -698,13 +709,14 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
                     double dk = wi * irho;
                     dd += dk * dk;
                     x[i] += t1 * wi;
-                    w[i] = sv * v[i] + t2 * wi;
+                    w[i] = sv * (i == ilast ? v_last : v[i]) + t2 * wi;
                 }
             }
             block_partial(d, 4, dd);
             const bool more = itn < prm.maxiter;
-            if (more) op_apply<STREAM>(d, o, false, v, sv, u, -alpha * su, 0, u_last);  // u_mem = A v_true - alpha u_true
-            d.sync();
+            double unorm2 = 0.0;
+            if (more) unorm2 = op_apply<STREAM>(d, o, false, v, sv, u, -alpha * su, 0, v_last, u_last);  // u_mem = A v_true - alpha u_true
+            else d.sync();  // the partial sums of the update above
             if (pending) {
                 ddnorm += total_of(d, 4);
                 acond = anorm * sqrt(ddnorm);
@@ -725,13 +737,11 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
             first = false;
             if (istop > 0 || !more) break;
             itn += 1;
-            beta = sqrt(total_of(d, 0));
+            beta = sqrt(unorm2);
             if (beta > 0) {
                 su = 1.0 / beta;
                 anorm = sqrt(anorm * anorm + alpha * alpha + beta * beta);
-                op_apply<STREAM>(d, o, true, u, su, v, -beta * sv, 2, v_last);  // v_mem = A' u_true - beta v_true
-                d.sync();
-                alpha = sqrt(total_of(d, 2));
+                alpha = sqrt(op_apply<STREAM>(d, o, true, u, su, v, -beta * sv, 2, u_last, v_last));  // v_mem = A' u_true - beta v_true
                 sv = alpha > 0 ? 1.0 / alpha : 1.0;
             } else {
                 su = 1.0;  // u_mem is exactly zero
@@ -786,8 +796,8 @@ __global__ void __launch_bounds__(LSQR_THREADS) conic_M_kernel(ConicOpView op, i
     Dev d{cg::this_grid(), partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
           (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
           (int)(gridDim.x * blockDim.x)};
-    double last = 0.0;
-    conic_apply<false>(d, op, transpose != 0, t, 1.0, out, 0.0, 0, last);
+    double last = 0.0, norm2 = 0.0;
+    conic_apply<false>(d, op, transpose != 0, t, 1.0, out, 0.0, 0, __ldcg(t + op.n + op.m), last, norm2);
 }
 
 __global__ void __launch_bounds__(LSQR_THREADS) conic_dpi_kernel(ConicOpView op, int transpose, const double* t, double* out,
@@ -796,7 +806,7 @@ __global__ void __launch_bounds__(LSQR_THREADS) conic_dpi_kernel(ConicOpView op,
     Dev d{cg::this_grid(), partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
           (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
           (int)(gridDim.x * blockDim.x)};
-    dpi_apply(d, op, t, out, transpose != 0);
+    dpi_apply<true>(d, op, t, out, transpose != 0);
 }
 
 
@@ -899,7 +909,7 @@ __global__ void __launch_bounds__(ST_THREADS) st_dpi_kernel(ConicOpView op, cons
                                                             const LsqrState* S, int which) {
     if (S->done || (which == 0 ? !S->more : !S->do_op1)) return;
     ST_DEV(nullptr);
-    dpi_apply(d, op, y, out, transpose != 0);
+    dpi_apply<false>(d, op, y, out, transpose != 0);
 }
 
 // ---- M src, phase 2: both sparse products, dst updated in place; slots 0 (norm) and 1 (last-row dot)
