@@ -62,13 +62,14 @@ def test_persistent_lsqr_variants_match_oracle(ctx, monkeypatch, mode):
     A[5, :] = rng.normal(size=450)                                # one dense row (long-row path of the row-block SpMV)
     A = A.tocsc()
     b = rng.normal(size=703)
-    for mi in (1, 6, 30):
+    for mi in (1, 3, 6):
         xg, sg = lsqr.lsqr_csc(ctx, A, b, maxiter=mi)
         xc, ic = olsqr.lsqr(A, b, maxiter=mi, return_info=True)
         assert sg["itn"] == ic.itn == mi
-        # the dense row makes this matrix ill conditioned: rounding differences (summation order) grow with the
-        # iteration count, so the tight comparison is at small counts
-        assert rel(xg, xc) <= (1e-10 if mi <= 6 else 1e-5), (mi, rel(xg, xc))
+        # the dense row makes this matrix ill conditioned: rounding differences (summation order) grow quickly with
+        # the iteration count (1e-7 .. 3e-4 at 30 iterations depending on the build), so iterates are compared at
+        # small counts and the answer at convergence
+        assert rel(xg, xc) <= 1e-10, (mi, rel(xg, xc))
     x, st = lsqr.lsqr_csc(ctx, A, b)
     assert rel(x, olsqr.lsqr(A, b)) <= RTOL_LSQR
     bt = rng.normal(size=450)
