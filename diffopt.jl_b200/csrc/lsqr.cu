@@ -214,7 +214,11 @@ __device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double
                     ci[u] = XCG ? __ldg(A->colind + s + k) : __ldcs(A->colind + s + k);
                 }
             }
-            const int row = r0 + tid;
+            // T threads per row (power of two, as many as the block's row count allows): rows of a few hundred nonzeros
+            // (KKT matrices with dense blocks) are not summed by one thread; fixed order either way
+            int T = 1;
+            while (T < 32 && (r1 - r0) * T * 2 <= THREADS) T <<= 1;
+            const int row = r0 + tid / T, sub = tid & (T - 1);
             int ra = 0, rb = 0;
             if (row < r1) {
                 ra = __ldg(A->rowptr + row) - s;
@@ -225,16 +229,15 @@ __device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double
             for (int u = 0; u < NPT; ++u)
                 xv[u] = (tid + u * THREADS < cnt) ? (XCG ? __ldcg(x + ci[u]) : __ldg(x + ci[u])) : 0.0;
             double4 opnd = make_double4(0.0, 0.0, 0.0, 0.0);
-            if (row < r1) opnd = pre(b, row);
+            if (row < r1 && sub == 0) opnd = pre(b, row);
 #pragma unroll
             for (int u = 0; u < NPT; ++u)
                 if (tid + u * THREADS < cnt) prod[tid + u * THREADS] = av[u] * xv[u];
             __syncthreads();
-            if (row < r1) {
-                double t = 0.0;
-                for (int k = ra; k < rb; ++k) t += prod[k];
-                epi(b, row, t, opnd);
-            }
+            double t = 0.0;
+            for (int k = ra + sub; k < rb; k += T) t += prod[k];
+            for (int o = T >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (row < r1 && sub == 0) epi(b, row, t, opnd);
         }
         __syncthreads();  // prod / red are free again
     }
