@@ -33,6 +33,24 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 
+__device__ __forceinline__ double fast_rcp(double x) {  // 1 / x, |relative error| ~ 1 ulp, x normal
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, fma(e, e, e), r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+__device__ __forceinline__ double fast_rsqrt(double x) {  // 1 / sqrt(x), |relative error| ~ 1 ulp, x normal
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);                 // 1 - x y^2
+    y = fma(y, e * fma(0.375, e, 0.5), y);          // third-order step
+    e = fma(-x * y, y, 1.0);
+    return fma(y, 0.5 * e, y);
+}
+
 // Orthogonalises columns (gp, gq) of G and applies the same rotation to (vp, vq) of V.  One warp.
 __device__ __forceinline__ int rotate_pair(double* __restrict__ gp, double* __restrict__ gq, double* __restrict__ vp,
                                            double* __restrict__ vq, int d, int lane, double tol) {
@@ -47,9 +65,22 @@ __device__ __forceinline__ int rotate_pair(double* __restrict__ gp, double* __re
     b = warp_sum(b);
     g = warp_sum(g);
     if (!(g * g > tol * tol * a * b)) return 0;
-    const double zeta = (b - a) / (2.0 * g);
-    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
-    const double c = rsqrt(fma(t, t, 1.0));
+    // t = tan(theta) = 2 g sign(d) / (|d| + sqrt(d^2 + 4 g^2)), d = b - a; c = 1 / sqrt(1 + t^2), s = c t.
+    // The scalar chain is the critical path of a tournament round (one warp retires a dependent instruction every ~10
+    // clk): square root and reciprocals are MUFU seeds + Newton steps (~60 clk each) instead of the IEEE-rounded
+    // library sequences (~250 clk each); c^2 + s^2 = 1 holds to an ulp or two, which is all Jacobi needs.
+    const double dba = b - a, g2 = g + g;
+    const double h2 = fma(dba, dba, g2 * g2);
+    double t, c;
+    if (h2 > 1e-280 && h2 < 1e280) {
+        const double den = fabs(dba) + h2 * fast_rsqrt(h2);
+        t = (dba >= 0.0 ? g2 : -g2) * fast_rcp(den);
+        c = fast_rsqrt(fma(t, t, 1.0));
+    } else {  // out of the range the flush-to-zero seeds cover
+        const double zeta = dba / g2;
+        t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+        c = rsqrt(fma(t, t, 1.0));
+    }
     const double s = c * t;
     for (int i = lane; i < d; i += 32) {
         const double x = gp[i], y = gq[i];
