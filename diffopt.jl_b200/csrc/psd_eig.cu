@@ -211,12 +211,31 @@ __global__ void __launch_bounds__(1024) psd_jacobi_block_kernel(int d, int b, in
             circle_pair(nblk, r, blockIdx.x, bi, bj);
             // stage the two blocks (columns beyond d do not exist)
             const int ci = bi * b, cj = bj * b;
-            for (int e = tid; e < 2 * b * d; e += nt) {
-                const int lc = e / d, i = e - lc * d;
+            // a warp per column, eight independent loads per lane and matrix in flight (the staging was the longest
+            // part of an outer round when every element waited for its own L2 round trip)
+            for (int lc = warp; lc < 2 * b; lc += nw) {
                 const int gc = lc < b ? ci + lc : cj + lc - b;
-                if (gc < d) {
-                    Gs[e] = G[(size_t)gc * d + i];
-                    Vs[e] = V[(size_t)gc * d + i];
+                if (gc >= d) continue;
+                const double* gsrc = G + (size_t)gc * d;
+                const double* vsrc = V + (size_t)gc * d;
+                double* gdst = Gs + (size_t)lc * d;
+                double* vdst = Vs + (size_t)lc * d;
+                for (int i0 = lane; i0 < d; i0 += 256) {
+                    double tg[8], tv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + 32 * u;
+                        tg[u] = i < d ? gsrc[i] : 0.0;
+                        tv[u] = i < d ? vsrc[i] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + 32 * u;
+                        if (i < d) {
+                            gdst[i] = tg[u];
+                            vdst[i] = tv[u];
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -243,12 +262,16 @@ __global__ void __launch_bounds__(1024) psd_jacobi_block_kernel(int d, int b, in
                     __syncthreads();
                 }
             }
-            for (int e = tid; e < 2 * b * d; e += nt) {
-                const int lc = e / d, i = e - lc * d;
+            for (int lc = warp; lc < 2 * b; lc += nw) {
                 const int gc = lc < b ? ci + lc : cj + lc - b;
-                if (gc < d) {
-                    G[(size_t)gc * d + i] = Gs[e];
-                    V[(size_t)gc * d + i] = Vs[e];
+                if (gc >= d) continue;
+                double* gdst = G + (size_t)gc * d;
+                double* vdst = V + (size_t)gc * d;
+                const double* gsrc = Gs + (size_t)lc * d;
+                const double* vsrc = Vs + (size_t)lc * d;
+                for (int i = lane; i < d; i += 32) {
+                    gdst[i] = gsrc[i];
+                    vdst[i] = vsrc[i];
                 }
             }
             if (r == nblk - 2 && lane == 0 && rot) atomicAdd(&counters[sweep], rot);
