@@ -35,7 +35,8 @@ int32_t diffopt_b200_create(int32_t device, diffopt_b200_ctx** out) {
 static void release_csr(CsrDev& c) {
     c.rowptr.release(); c.colind.release(); c.val.release();
     c.t_rowptr.release(); c.t_colind.release(); c.t_val.release();
-    c.blk.release(); c.t_blk.release(); c.cblk.release(); c.t_cblk.release(); c.gblk.release(); c.t_gblk.release();
+    c.blk.release(); c.t_blk.release();
+    for (DevBuf* b : {&c.sval, &c.scol, &c.spos, &c.t_sval, &c.t_scol, &c.t_spos}) b->release(); c.cblk.release(); c.t_cblk.release(); c.gblk.release(); c.t_gblk.release();
 }
 
 int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {

@@ -50,6 +50,8 @@ struct CsrDev {  // device CSR (0-based, int32 indices) of a sparse matrix and o
     // row blocks for the streaming SpMV (lsqr.cu): block k = rows [blk[k], blk[k+1]) holding <= ST_CHUNK nonzeros
     DevBuf blk, t_blk;
     int64_t nblk = 0, t_nblk = 0;
+    bool sorted = false;  // column-ordered copies of the streaming blocks exist
+    DevBuf sval, scol, spos, t_sval, t_scol, t_spos;
     DevBuf cblk, t_cblk;  // coarser blocks for the cluster-synchronised persistent kernel (16 CTAs)
     int64_t ncblk = 0, t_ncblk = 0;
     DevBuf gblk, t_gblk;  // ... and for the one-CTA-per-SM persistent kernel

@@ -2,6 +2,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -204,14 +205,23 @@ __device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double
         } else {
             double av[NPT];
             int ci[NPT];
+            int ps[NPT];  // slot of the product in `prod` (CSR position inside the block)
+            const bool sorted = !XCG && A->spos != nullptr;  // column-ordered copy of the block (large operators)
 #pragma unroll
             for (int u = 0; u < NPT; ++u) {
                 const int k = tid + u * THREADS;
                 av[u] = 0.0;
                 ci[u] = 0;
+                ps[u] = k;
                 if (k < cnt) {  // streamed once per pass (evict-first) unless the operator lives in L2 (XCG kernels)
-                    av[u] = XCG ? __ldg(A->val + s + k) : __ldcs(A->val + s + k);
-                    ci[u] = XCG ? __ldg(A->colind + s + k) : __ldcs(A->colind + s + k);
+                    if (sorted) {
+                        av[u] = __ldcs(A->sval + s + k);
+                        ci[u] = __ldcs(A->scol + s + k);
+                        ps[u] = __ldcs(A->spos + s + k);
+                    } else {
+                        av[u] = XCG ? __ldg(A->val + s + k) : __ldcs(A->val + s + k);
+                        ci[u] = XCG ? __ldg(A->colind + s + k) : __ldcs(A->colind + s + k);
+                    }
                 }
             }
             // T threads per row (power of two, as many as the block's row count allows): rows of a few hundred nonzeros
@@ -232,7 +242,7 @@ __device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double
             if (row < r1 && sub == 0) opnd = pre(b, row);
 #pragma unroll
             for (int u = 0; u < NPT; ++u)
-                if (tid + u * THREADS < cnt) prod[tid + u * THREADS] = av[u] * xv[u];
+                if (tid + u * THREADS < cnt) prod[ps[u]] = av[u] * xv[u];
             __syncthreads();
             double t = 0.0;
             for (int k = ra + sub; k < rb; k += T) t += prod[k];
@@ -1128,9 +1138,12 @@ __global__ void st_stats_kernel(const LsqrState* S, double* stats) {
 }
 
 CsrView view_of(const DevBuf& rp, const DevBuf& ci, const DevBuf& v, int64_t nrows, int64_t ncols,
-                const DevBuf* blk = nullptr, int64_t nblk = 0) {
+                const DevBuf* blk = nullptr, int64_t nblk = 0, const DevBuf* sval = nullptr, const DevBuf* scol = nullptr,
+                const DevBuf* spos = nullptr) {
     return CsrView{(int)nrows, (int)ncols, rp.as<int>(), ci.as<int>(), v.as<double>(),
-                   blk ? blk->as<int>() : nullptr, (int)nblk};
+                   blk ? blk->as<int>() : nullptr, (int)nblk,
+                   sval ? sval->as<double>() : nullptr, scol ? scol->as<int>() : nullptr,
+                   spos ? spos->as<unsigned short>() : nullptr};
 }
 
 }  // namespace
@@ -1141,8 +1154,11 @@ ConicOpView conic_view(diffopt_b200_ctx* ctx, bool stream_blocks = false) {
     o.n = (int)s.n;
     o.m = (int)s.m;
     if (stream_blocks) {
-        o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n, &s.A.blk, s.A.nblk);
-        o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m, &s.A.t_blk, s.A.t_nblk);
+        const bool so = s.A.sorted;
+        o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n, &s.A.blk, s.A.nblk, so ? &s.A.sval : nullptr,
+                      so ? &s.A.scol : nullptr, so ? &s.A.spos : nullptr);
+        o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m, &s.A.t_blk, s.A.t_nblk, so ? &s.A.t_sval : nullptr,
+                       so ? &s.A.t_scol : nullptr, so ? &s.A.t_spos : nullptr);
     } else {
         o.A = view_of(s.A.rowptr, s.A.colind, s.A.val, s.m, s.n, &s.A.cblk, s.A.ncblk);
         o.At = view_of(s.A.t_rowptr, s.A.t_colind, s.A.t_val, s.n, s.m, &s.A.t_cblk, s.A.t_ncblk);
@@ -1519,6 +1535,50 @@ int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, c
     out.t_ngblk = (int64_t)t_gblk.size() / 2 - 1;
     out.nblk = (int64_t)blk.size() / 2 - 1;
     out.t_nblk = (int64_t)t_blk.size() / 2 - 1;
+    // Large operators (the streaming driver): a second copy of (val, colind) with the nonzeros of every row block
+    // ordered by column, plus each nonzero's position inside its block.  The gathers of a warp then fall into few
+    // 128-byte lines when the operator has any locality (the L1TEX takes ~one line request per clock per SM, which is
+    // what bounds the row-block SpMV), the products are scattered back to their CSR positions in shared memory, and the
+    // row sums are unchanged bit for bit.
+    std::vector<double> sval, t_sval;
+    std::vector<int> scol, t_scol;
+    std::vector<unsigned short> spos, t_spos;
+    const char* sort_env = getenv("DIFFOPT_B200_SPMV_SORT");
+    const bool want_sort = sort_env ? atoi(sort_env) != 0 : nnz >= ((int64_t)1 << 21);
+    auto sort_blocks = [](const std::vector<int>& blk2, const std::vector<int>& ci, const double* va,
+                          std::vector<double>& sv, std::vector<int>& sc, std::vector<unsigned short>& sp) {
+        const size_t nb = blk2.size() / 2 - 1;
+        const size_t nz = ci.size();
+        sv.resize(nz); sc.resize(nz); sp.resize(nz);
+        auto work = [&](size_t b0, size_t b1) {
+            std::vector<int> idx;
+            for (size_t b = b0; b < b1; ++b) {
+                const int s0 = blk2[2 * b + 1], s1 = blk2[2 * b + 3], cnt = s1 - s0;
+                if (cnt > ST_CHUNK) {  // one long row: streamed in place
+                    for (int k = s0; k < s1; ++k) { sv[(size_t)k] = va[k]; sc[(size_t)k] = ci[(size_t)k]; sp[(size_t)k] = 0; }
+                    continue;
+                }
+                idx.resize((size_t)cnt);
+                for (int j = 0; j < cnt; ++j) idx[(size_t)j] = j;
+                std::stable_sort(idx.begin(), idx.end(), [&](int a, int c) { return ci[(size_t)(s0 + a)] < ci[(size_t)(s0 + c)]; });
+                for (int j = 0; j < cnt; ++j) {
+                    const int k = s0 + idx[(size_t)j];
+                    sv[(size_t)(s0 + j)] = va[k];
+                    sc[(size_t)(s0 + j)] = ci[(size_t)k];
+                    sp[(size_t)(s0 + j)] = (unsigned short)idx[(size_t)j];
+                }
+            }
+        };
+        const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < hw; ++t) pool.emplace_back(work, nb * t / hw, nb * (t + 1) / hw);
+        for (auto& th : pool) th.join();
+    };
+    if (want_sort && nnz > 0) {
+        sort_blocks(blk, colind, val.data(), sval, scol, spos);
+        sort_blocks(t_blk, t_colind, nzval, t_sval, t_scol, t_spos);
+    }
+    out.sorted = want_sort && nnz > 0;
     out.nrows = nrows;
     out.ncols = ncols;
     out.nnz = nnz;
@@ -1533,6 +1593,14 @@ int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, c
     DO_CUDA(ctx, up(out.t_rowptr, t_rowptr.data(), sizeof(int) * t_rowptr.size()));
     DO_CUDA(ctx, up(out.t_colind, t_colind.data(), sizeof(int) * t_colind.size()));
     DO_CUDA(ctx, up(out.t_val, nzval, sizeof(double) * (size_t)nnz));
+    if (out.sorted) {
+        DO_CUDA(ctx, up(out.sval, sval.data(), sizeof(double) * sval.size()));
+        DO_CUDA(ctx, up(out.scol, scol.data(), sizeof(int) * scol.size()));
+        DO_CUDA(ctx, up(out.spos, spos.data(), sizeof(unsigned short) * spos.size()));
+        DO_CUDA(ctx, up(out.t_sval, t_sval.data(), sizeof(double) * t_sval.size()));
+        DO_CUDA(ctx, up(out.t_scol, t_scol.data(), sizeof(int) * t_scol.size()));
+        DO_CUDA(ctx, up(out.t_spos, t_spos.data(), sizeof(unsigned short) * t_spos.size()));
+    }
     DO_CUDA(ctx, up(out.blk, blk.data(), sizeof(int) * blk.size()));
     DO_CUDA(ctx, up(out.t_blk, t_blk.data(), sizeof(int) * t_blk.size()));
     DO_CUDA(ctx, up(out.cblk, cblk.data(), sizeof(int) * cblk.size()));

@@ -15,6 +15,10 @@ struct CsrView {
     const double* val;
     const int* blk;  // row blocks of the streaming SpMV (nblk + 1 entries), see CsrDev
     int nblk;
+    // column-ordered copy of every streaming block and each nonzero's CSR slot inside its block (or null)
+    const double* sval;
+    const int* scol;
+    const unsigned short* spos;
 };
 
 struct ConicOpView {

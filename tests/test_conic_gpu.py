@@ -273,10 +273,13 @@ def test_psd_maxcut_200(ctx):
         assert rel(model.dpi_apply(t, transpose=tr), want) <= 1e-8
 
 
+@pytest.mark.parametrize("sort", ["0", "1"])
 @pytest.mark.parametrize("col_window", [None, 150])
-def test_streaming_lsqr_mid_size_operators(ctx, monkeypatch, col_window):
+def test_streaming_lsqr_mid_size_operators(ctx, monkeypatch, col_window, sort):
     """The multi-kernel (streaming) LSQR with its row-block SpMV on operators of a few 10^4 rows -- uniformly random
-    columns and a stage-structured pattern -- against the oracle's explicit M at small iteration counts."""
+    columns and a stage-structured pattern, with and without the column-ordered copy of the row blocks that large
+    operators get -- against the oracle's explicit M at small iteration counts."""
+    monkeypatch.setenv("DIFFOPT_B200_SPMV_SORT", sort)
     cm = diffopt_b200.submodule("conic")
     d = bench_data.conic_config4(n=9000, n_zero=900, n_nonneg=7000, n_soc=500, soc_dim=8, nnz_per_row=7, seed=77,
                                  col_window=col_window)
