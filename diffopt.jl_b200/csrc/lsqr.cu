@@ -859,6 +859,38 @@ __device__ double st_total(const double* partials, int slot, int stride, int cou
     return t;
 }
 
+// three totals in one pass (independent loads, one shared-memory exchange): the single-CTA scalar kernels are pure
+// latency, three sequential st_total calls were most of it
+__device__ void st_total3(const double* partials, int stride, int s0, int c0, int s1, int c1, int s2, int c2, double* red,
+                          double& t0, double& t1, double& t2) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    const int cmax = max(c0, max(c1, c2));
+    for (int i = threadIdx.x; i < cmax; i += blockDim.x) {
+        const double x0 = i < c0 ? partials[s0 * stride + i] : 0.0;
+        const double x1 = i < c1 ? partials[s1 * stride + i] : 0.0;
+        const double x2 = i < c2 ? partials[s2 * stride + i] : 0.0;
+        a += x0;
+        b += x1;
+        c += x2;
+    }
+    a = warp_sum_all(a);
+    b = warp_sum_all(b);
+    c = warp_sum_all(c);
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        red[w] = a;
+        red[8 + w] = b;
+        red[16 + w] = c;
+    }
+    __syncthreads();
+    t0 = t1 = t2 = 0.0;
+    for (int k = 0; k < nw; ++k) {
+        t0 += red[k];
+        t1 += red[8 + k];
+        t2 += red[16 + k];
+    }
+}
+
 __global__ void __launch_bounds__(ST_THREADS) st_init_kernel(int nr, int nc, const double* __restrict__ rhs, LsqrVectors vec, LsqrState* S) {
     ST_DEV(vec.partials);
     double acc = 0.0;
@@ -968,9 +1000,8 @@ __global__ void __launch_bounds__(ST_THREADS) st_mid_kernel(int N, LsqrVectors v
                                                             LsqrState* S) {
     if (S->done) return;
     __shared__ double red[64];
-    const double tot0 = st_total(vec.partials, 0, stride, cnt_rows, red);
-    const double tot1 = st_total(vec.partials, 1, stride, cnt_rows, red);
-    const double tot4 = st_total(vec.partials, 4, stride, cnt_upd, red);
+    double tot0, tot1, tot4;
+    st_total3(vec.partials, stride, 0, cnt_rows, 1, cnt_rows, 4, cnt_upd, red, tot0, tot1, tot4);
     if (threadIdx.x != 0) return;
     LsqrState s = *S;
     double unorm2 = tot0;
@@ -1073,9 +1104,8 @@ __global__ void __launch_bounds__(ST_THREADS) st_end_kernel(int N, LsqrVectors v
                                                             LsqrState* S, int startup) {
     if (S->done) return;
     __shared__ double red[64];
-    const double tot2 = st_total(vec.partials, 2, stride, cnt_rows, red);
-    const double tot3 = st_total(vec.partials, 3, stride, cnt_a, red);
-    const double tot5 = st_total(vec.partials, 5, stride, cnt_rows, red);
+    double tot2, tot3, tot5;
+    st_total3(vec.partials, stride, 2, cnt_rows, 3, cnt_a, 5, cnt_rows, red, tot2, tot3, tot5);
     if (threadIdx.x != 0) return;
     LsqrState s = *S;
     if (s.do_op1) {
