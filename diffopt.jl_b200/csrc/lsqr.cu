@@ -483,7 +483,7 @@ __device__ void csr_apply(Dev& d, const CsrView& A, const double* __restrict__ s
 // `src_last` / `dst_last` are every thread's private copies of src[N-1] / dst[N-1] (all threads compute the last row
 // identically): nobody reads those entries from memory, so thread 0 may store the new one right after the barrier
 // that publishes the partial sums, and ||dst||^2 (returned in `norm2`) is complete without another barrier.
-template <bool CL>
+template <bool CL, bool PSD>
 __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const double* __restrict__ src,
                             double s_src, double* dst, double s_dst, int slot, double src_last, double& dst_last,
                             double& norm2) {
@@ -493,7 +493,7 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         double* prod = cl_prod;
         double acc = 0.0;
         if (!transpose) {
-            dpi_apply<!CL>(d, op, src + n, op.wc, false);  // wc = Dpi t2
+            dpi_apply<PSD>(d, op, src + n, op.wc, false);  // wc = Dpi t2
             d.sync();
             const double t3 = src_last;
             const int nbt = op.At.nblk;
@@ -540,7 +540,7 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
                 });
             d.sync();
             double* r2 = op.wc + m;
-            dpi_apply<!CL>(d, op, op.wc, r2, true);
+            dpi_apply<PSD>(d, op, op.wc, r2, true);
             d.sync();
             spmv_stream<CL_THREADS, CL_NPT, true>(  // rows 0..n-1: -(A' u2)_j - c_j u3
                 op.At.nblk, prod, d.red,
@@ -569,7 +569,7 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
     }
     if (!transpose) {
         // wc = Dpi t2
-        dpi_apply<!CL>(d, op, src + n, op.wc, false);
+        dpi_apply<PSD>(d, op, src + n, op.wc, false);
         d.sync();
         const double t3 = src_last;
         double acc = 0.0;
@@ -610,7 +610,7 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         // disjoint, so compute into `tmp = psd_w-independent` region: use op.wc in place is unsafe (SOC reads all
         // entries of its cone) -> stage through dst? no.  Use the dedicated second scratch stored after wc.
         double* r2 = op.wc + m;  // second half of the 2m scratch
-        dpi_apply<!CL>(d, op, op.wc, r2, true);
+        dpi_apply<PSD>(d, op, op.wc, r2, true);
         d.sync();
         double acc = 0.0;
         // rows 0..n-1: -(A' u2)_j - c_j u3
@@ -645,7 +645,7 @@ struct OpArgs {
 
 // Returns ||dst||^2 (after the update).  The conic operator ends behind its own barrier; the CSR one needs a barrier
 // here before its partial sums can be read.
-template <bool CL>
+template <bool CL, bool PSD>
 __device__ double op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* src, double s_src, double* dst,
                            double s_dst, int slot, double src_last, double& dst_last) {
     if (o.kind == 0) {
@@ -654,11 +654,11 @@ __device__ double op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* 
         return total_of(d, slot);
     }
     double norm2 = 0.0;
-    conic_apply<CL>(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot, src_last, dst_last, norm2);
+    conic_apply<CL, PSD>(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot, src_last, dst_last, norm2);
     return norm2;
 }
 
-template <int THREADS, int MINB, bool CLUSTER, bool STREAM>
+template <int THREADS, int MINB, bool CLUSTER, bool STREAM, bool PSD>
 __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const double* __restrict__ rhs, LsqrParams prm,
                                                                LsqrVectors vec) {
     __shared__ double red[64];
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
     double rnorm = beta, arnorm = 0.0;
     if (beta > 0) {
         su = 1.0 / beta;
-        alpha = sqrt(op_apply<STREAM>(d, o, true, u, su, v, 0.0, 2, u_last, v_last));   // v_mem = A' u_true
+        alpha = sqrt(op_apply<STREAM, PSD>(d, o, true, u, su, v, 0.0, 2, u_last, v_last));   // v_mem = A' u_true
     }
     if (alpha > 0) sv = 1.0 / alpha;
     arnorm = alpha * beta;
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
             block_partial(d, 4, dd);
             const bool more = itn < prm.maxiter;
             double unorm2 = 0.0;
-            if (more) unorm2 = op_apply<STREAM>(d, o, false, v, sv, u, -alpha * su, 0, v_last, u_last);  // u_mem = A v_true - alpha u_true
+            if (more) unorm2 = op_apply<STREAM, PSD>(d, o, false, v, sv, u, -alpha * su, 0, v_last, u_last);  // u_mem = A v_true - alpha u_true
             else d.sync();  // the partial sums of the update above
             if (pending) {
                 ddnorm += total_of(d, 4);
@@ -754,7 +754,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
             if (beta > 0) {
                 su = 1.0 / beta;
                 anorm = sqrt(anorm * anorm + alpha * alpha + beta * beta);
-                alpha = sqrt(op_apply<STREAM>(d, o, true, u, su, v, -beta * sv, 2, u_last, v_last));  // v_mem = A' u_true - beta v_true
+                alpha = sqrt(op_apply<STREAM, PSD>(d, o, true, u, su, v, -beta * sv, 2, u_last, v_last));  // v_mem = A' u_true - beta v_true
                 sv = alpha > 0 ? 1.0 / alpha : 1.0;
             } else {
                 su = 1.0;  // u_mem is exactly zero
@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(LSQR_THREADS) conic_M_kernel(ConicOpView op, i
           (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
           (int)(gridDim.x * blockDim.x)};
     double last = 0.0, norm2 = 0.0;
-    conic_apply<false>(d, op, transpose != 0, t, 1.0, out, 0.0, 0, __ldcg(t + op.n + op.m), last, norm2);
+    conic_apply<false, true>(d, op, transpose != 0, t, 1.0, out, 0.0, 0, __ldcg(t + op.n + op.m), last, norm2);
 }
 
 __global__ void __launch_bounds__(LSQR_THREADS) conic_dpi_kernel(ConicOpView op, int transpose, const double* t, double* out,
@@ -1273,9 +1273,9 @@ static int32_t lsqr_launch(diffopt_b200_ctx* ctx, OpArgs& o, int64_t work, const
     DO_CUDA(ctx, wk.u.reserve(d * (size_t)o.nrows));
     DO_CUDA(ctx, wk.v.reserve(d * (size_t)o.ncols));
     DO_CUDA(ctx, wk.w.reserve(d * (size_t)o.ncols));
-    const void* k_grid = (const void*)lsqr_kernel_t<LSQR_THREADS, 4, false, false>;
-    const void* k_cluster = (const void*)lsqr_kernel_t<CL_THREADS, 1, true, true>;
-    const void* k_gstream = (const void*)lsqr_kernel_t<CL_THREADS, 1, false, true>;
+    const void* k_grid = (const void*)lsqr_kernel_t<LSQR_THREADS, 4, false, false, false>;
+    const void* k_cluster = (const void*)lsqr_kernel_t<CL_THREADS, 1, true, true, false>;
+    const void* k_gstream = (const void*)lsqr_kernel_t<CL_THREADS, 1, false, true, false>;
     // Three persistent variants, by size of the operator (`work` ~ nonzeros + vector lengths):
     //   cluster : <= CL_CLUSTER_WORK  one 16-CTA cluster, hardware barriers, row-block SpMV (16 SMs are enough)
     //   gstream : <= CL_MAX_WORK      one CTA per SM, grid.sync(), row-block SpMV (L1 gather rate of 16 SMs is not)
@@ -1290,8 +1290,12 @@ static int32_t lsqr_launch(diffopt_b200_ctx* ctx, OpArgs& o, int64_t work, const
     int cs = variant == 1 ? cluster_size_for(ctx, k_cluster) : 0;
     if (variant == 1 && cs == 0) variant = 2;
     const size_t dyn = variant ? CL_CHUNK * sizeof(double) : 0;
+    // problems with PSD cones: same kernel compiled for 2 CTAs per SM (128 registers: the GEMM phases of the PSD apply
+    // spill badly under the 64-register cap of the 4-CTA build)
+    const void* k_psd = (const void*)lsqr_kernel_t<LSQR_THREADS, 2, false, false, true>;
+    const void* k_lane = psd ? k_psd : k_grid;
     int grid = cs;
-    if (variant == 0) grid = coop_grid(ctx, k_grid, work);
+    if (variant == 0) grid = coop_grid(ctx, k_lane, work);
     if (variant == 2) {
         DO_CUDA(ctx, cudaFuncSetAttribute(k_gstream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         grid = ctx->sm_count;
@@ -1335,7 +1339,7 @@ static int32_t lsqr_launch(diffopt_b200_ctx* ctx, OpArgs& o, int64_t work, const
     } else if (variant == 2) {
         DO_CUDA(ctx, cudaLaunchCooperativeKernel(k_gstream, dim3(grid), dim3(CL_THREADS), args, dyn, ctx->stream));
     } else {
-        DO_CUDA(ctx, cudaLaunchCooperativeKernel(k_grid, dim3(grid), dim3(LSQR_THREADS), args, 0, ctx->stream));
+        DO_CUDA(ctx, cudaLaunchCooperativeKernel(k_lane, dim3(grid), dim3(LSQR_THREADS), args, 0, ctx->stream));
     }
     ctx->launches++;
     DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
