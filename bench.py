@@ -64,7 +64,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -74,6 +74,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout=2.0):
+        """Block until nvidia-smi has produced its first line (so that the timed region is actually sampled)."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
 
     def stop(self, t0, t1):
         if self.proc is None:
@@ -267,10 +273,12 @@ def run_b200(args, rank, world, local_rank):
             ms = float(t.item())
         return ms, kms / steps
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi needs ~0.2 s to come up
     for _ in range(max(args.warmup, 3)):
         step_device()
     finish_device()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
     l0 = ctx.launch_count
     t0 = time.perf_counter()
     ms, _ = timed(step_device, args.steps)
