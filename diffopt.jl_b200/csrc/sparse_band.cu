@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) band_lu_kernel(int N, int kl, in
 // and multipliers from registers), so the window copy of the pivot column is never written while other warps read it.
 // Variants measured on config 3 (N = 240 000, kl = ku = 19), factorisation time: three barriers per column 252 ms; this
 // kernel 164 ms; the same with the retiring column leaving by a bulk (TMA) store one step later 172 ms; named-barrier
-// look-ahead with an owner warp per column 159-176 ms; two warps with lanes = columns in the update 205-240 ms.  The
+// look-ahead with an owner warp per column 159-176 ms; two warps with lanes = columns in the update 205-240 ms; pivot
+// search by warp 0 only, published through shared memory behind a second barrier 164 ms.  The
 // column step (~1300 clk) is bound by the dependent instruction chain of a warp (clock counters: pivot search 120,
 // reciprocal + multipliers 150, one window column ~190 clk), not by arithmetic or memory.
 __device__ __forceinline__ double band_fast_rcp(double x) {
