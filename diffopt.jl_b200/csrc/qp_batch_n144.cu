@@ -774,7 +774,7 @@ __global__ void max_active_kernel(int64_t B, const double* __restrict__ lam, int
 
 }  // namespace
 
-int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled);
+int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled, int* max_active);
 
 static int32_t lu_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, const int* list, const int* count,
                          bool* handled) {
@@ -843,22 +843,36 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
     int* dmax = ctx->qp_max.as<int>();
     const bool first = ctx->qp_hint < 0;
     if (!first) ctx->qp_hint = *ctx->qp_hmax_host;
-    DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
-    {
+    // The largest active set of THIS batch configures the next call.  First call (and when the LDL' kernel does not
+    // run): a small scan kernel; otherwise the LDL' kernel reports it itself while it assembles the instances.
+    const bool want_ldl = !(force && strcmp(force, "lu") == 0);
+    auto scan_active = [&]() -> cudaError_t {
         int64_t blocks = (a.B + 7) / 8;
         if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
         max_active_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a.B, a.lam, dmax);
         ctx->launches++;
-    }
-    DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        return cudaGetLastError();
+    };
+    DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
     if (first) {
+        DO_CUDA(ctx, scan_active());
+        DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->qp_hint = *ctx->qp_hmax_host;
     }
     const int nt_cap = (NV + ctx->qp_hint + PE + 7) / 8;
-    if (!(force && strcmp(force, "lu") == 0)) {
-        int32_t rc = qp_sqd_launch(ctx, a, nt_cap, handled);
-        if (rc != 0 || *handled) return rc;
+    bool reported = first;
+    if (want_ldl) {
+        int32_t rc = qp_sqd_launch(ctx, a, nt_cap, handled, first ? nullptr : dmax);
+        if (rc != 0) return rc;
+        if (*handled) {
+            if (!first) DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            return 0;
+        }
+    }
+    if (!reported) {
+        DO_CUDA(ctx, scan_active());
+        DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (!first) {  // the guess may be too small for the plain LU launch: size it for the worst case
         return lu_launch(ctx, a, NTMAX, nullptr, nullptr, handled);
