@@ -109,6 +109,7 @@ struct diffopt_b200_ctx {
     DevBuf qp_fb;   // [count, list...] of instances the LDL' fast path hands to the pivoted LU kernel
     DevBuf qp_max;  // device scalar: largest active-set size of the batch
     int* qp_hmax_host = nullptr;  // pinned copy of it, read at the start of the NEXT call (calls end synchronised)
+    int qp_seq = 0;               // call number, tags the active-set word written by the LDL' kernel
     int qp_hint = -1;             // active-set size the next headline-shape launch is configured for (-1: unknown)
     int64_t async_B = 0;          // batch size and info array of the last qp_batch_solve_async (status at synchronize)
     int* async_info = nullptr;

@@ -774,7 +774,7 @@ __global__ void max_active_kernel(int64_t B, const double* __restrict__ lam, int
 
 }  // namespace
 
-int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled, int* max_active);
+int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled, int* max_active, int max_tag);
 
 static int32_t lu_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, const int* list, const int* count,
                          bool* handled) {
@@ -842,7 +842,7 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
     if (!ctx->qp_hmax_host) DO_CUDA(ctx, cudaHostAlloc((void**)&ctx->qp_hmax_host, sizeof(int), cudaHostAllocDefault));
     int* dmax = ctx->qp_max.as<int>();
     const bool first = ctx->qp_hint < 0;
-    if (!first) ctx->qp_hint = *ctx->qp_hmax_host;
+    if (!first) ctx->qp_hint = *ctx->qp_hmax_host & 0xFF;  // low byte: active-set size, high bits: call tag
     // The largest active set of THIS batch configures the next call.  First call (and when the LDL' kernel does not
     // run): a small scan kernel; otherwise the LDL' kernel reports it itself while it assembles the instances.
     const bool want_ldl = !(force && strcmp(force, "lu") == 0);
@@ -853,17 +853,20 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
         ctx->launches++;
         return cudaGetLastError();
     };
-    DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
+    // the scan kernel needs a cleared word; the LDL' kernel's tagged values (call number << 8 | size) only grow
+    ctx->qp_seq = (ctx->qp_seq + 1) & 0x3FFFFF;
+    const bool clear = first || !want_ldl || ctx->qp_seq == 0;
+    if (clear) DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
     if (first) {
         DO_CUDA(ctx, scan_active());
         DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->qp_hint = *ctx->qp_hmax_host;
+        ctx->qp_hint = *ctx->qp_hmax_host & 0xFF;
     }
     const int nt_cap = (NV + ctx->qp_hint + PE + 7) / 8;
     bool reported = first;
     if (want_ldl) {
-        int32_t rc = qp_sqd_launch(ctx, a, nt_cap, handled, first ? nullptr : dmax);
+        int32_t rc = qp_sqd_launch(ctx, a, nt_cap, handled, first ? nullptr : dmax, ctx->qp_seq << 8);
         if (rc != 0) return rc;
         if (*handled) {
             if (!first) DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -871,6 +874,7 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
         }
     }
     if (!reported) {
+        if (!clear) DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
         DO_CUDA(ctx, scan_active());
         DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }

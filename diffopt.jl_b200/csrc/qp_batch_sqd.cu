@@ -224,7 +224,7 @@ __device__ __forceinline__ void bar_sync(const int id, const int n) { asm volati
 __device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, int* fb_list, int* fb_count, const int nt_cap,
-                                                                 int* max_active) {
+                                                                 int* max_active, const int max_tag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Hdr& S = *reinterpret_cast<Hdr*>(smem_raw);
     double* const T = reinterpret_cast<double*>(smem_raw + sizeof(Hdr));
@@ -291,7 +291,9 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
             if (lane == 0) {
                 const int ma = __popc(m0) + __popc(m1);
                 S.ma = ma;
-                if (max_active) atomicMax(max_active, ma);  // largest active set of the batch: configures the next call
+                // largest active set of the batch (configures the next call); tagged with the call number in the high
+                // bits so that the word never has to be cleared between calls
+                if (max_active) atomicMax(max_active, max_tag | ma);
                 S.nt = (NV + ma + PE + 7) >> 3;
                 S.fail = 0;
             }
@@ -895,7 +897,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
 
 // Launches the LDL' fast path followed by the pivoted-LU kernel over the instances it rejected (device-side
 // list, no host round trip).  nt_cap = tile order of the largest reduced system of the batch.
-int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled, int* max_active) {
+int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled, int* max_active, int max_tag) {
     *handled = false;
     const size_t smem = sizeof(Hdr) + (size_t)(nt_cap * (nt_cap + 1) / 2) * 64 * sizeof(double);
     if (smem > ctx->smem_optin) return 0;
@@ -932,7 +934,7 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
         DO_CUDA(ctx, cudaMemsetAsync(dprof, 0, 32 * sizeof(long long), ctx->stream));
         aa.prof = dprof;
     }
-    qp_kkt_sqd_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa, fb_list, fb_count, nt_cap, max_active);
+    qp_kkt_sqd_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa, fb_list, fb_count, nt_cap, max_active, max_tag);
     ctx->launches++;
     DO_CUDA(ctx, cudaGetLastError());
     if (profile) {
