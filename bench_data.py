@@ -179,3 +179,28 @@ def mpc_config3(T=10_000, nx=6, nu=4, active_frac=0.1, seed=3):
     K = sp.bmat([[Q, G.T @ sp.diags(lam), A.T], [G, sp.diags(D), None], [A, None, sp.csc_matrix((p, p))]], format="csc")
     K.sort_indices()
     return dict(K=K, Q=Q, G=G, A=A, z=z, lam=lam, nu=nu_, h=h, n=n, m=m, p=p)
+
+
+def maxcut_config5(d=200, r=20, seed=5):
+    """Config 5: max-cut SDP relaxation with a d x d PSD cone, solved by construction.  V ~ N(0,1)^{d x r} with unit
+    rows, X = V V' (unit diagonal, rank r); W = orthonormal basis of range(V)^perp, S = W diag(U(.5,1.5)) W';
+    nu ~ N(0,1)^d; C = S + Diag(nu): a strictly complementary primal-dual pair.  Variables = triangle of X
+    (unscaled, column-wise upper), rows = Zeros(d) (X_ii = 1) + PSD triangle.  Returns A (the reference's
+    A = -coefficients), b, c, x, s, y, cone lists and a reverse seed."""
+    import scipy.sparse as sp
+    from oracle import cones as oc  # vec_symm only: used to *construct* the data set
+    rng = np.random.default_rng(seed)
+    V = rng.normal(size=(d, r))
+    V /= np.linalg.norm(V, axis=1, keepdims=True)
+    X = V @ V.T
+    Qf, _ = np.linalg.qr(np.hstack([V, rng.normal(size=(d, d - r))]))
+    W = Qf[:, r:]
+    S = (W * rng.uniform(0.5, 1.5, size=d - r)) @ W.T
+    k = d * (d + 1) // 2
+    s = np.concatenate([np.zeros(d), oc.vec_symm(X)])
+    y = np.concatenate([rng.normal(size=d), oc.vec_symm(S)])
+    iu = [(i * (i + 1) // 2 + i) for i in range(d)]
+    A = sp.vstack([sp.csc_matrix((np.ones(d), (np.arange(d), iu)), shape=(d, k)), -sp.identity(k)]).tocsc()
+    x = oc.vec_symm(X)
+    return dict(A=A, b=A @ x + s, c=-(A.T @ y), x=x, s=s, y=y, cone_types=[oc.ZERO, oc.PSD], cone_dims=[d, k],
+                seed=rng.normal(size=k), X=X, S=S, d=d)

@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -35,6 +36,7 @@ SIGNATURES = {
     "diffopt_b200_qp_batch_solve": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 17 + [C.c_int32]),
     "diffopt_b200_qp_batch_solve_async": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 17),
     "diffopt_b200_synchronize": (C.c_int32, [vp]),
+    "diffopt_b200_qp_batch_last_stats": (C.c_int32, [vp, vp]),
     "diffopt_b200_qp_batch_setup": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 7 + [C.c_int32]),
     "diffopt_b200_qp_batch_reverse": (C.c_int32, [vp, vp, vp, vp, C.c_int32]),
     "diffopt_b200_qp_batch_forward": (C.c_int32, [vp] * 9 + [C.c_int32]),
@@ -136,6 +138,12 @@ class Context:
     def last_kernel_ms(self):
         return float(self.lib.diffopt_b200_last_kernel_ms(self.h))
 
+    def qp_last_stats(self):
+        """(instances handed to the pivoted-LU fallback, active-set hint, kernel id) of the last qp_batch call."""
+        out = np.zeros(3, dtype=np.int64)
+        self.check(self.lib.diffopt_b200_qp_batch_last_stats(self.h, ptr(out)))
+        return int(out[0]), int(out[1]), int(out[2])
+
     @property
     def stream(self):
         return self.lib.diffopt_b200_stream(self.h)
@@ -151,8 +159,6 @@ def pinned_empty(shape, dtype=np.float64):
         raise DiffOptB200Error(rc, "cudaHostAlloc failed")
     buf = (C.c_char * max(n, 8)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[arr.ctypes.data] = p.value
+    # the ctypes buffer is the base object every view of `arr` keeps alive: free the pinned block when it dies
+    weakref.finalize(buf, lib.diffopt_b200_host_free, p.value)
     return arr
-
-
-_PINNED = {}

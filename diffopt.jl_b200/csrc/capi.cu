@@ -15,7 +15,7 @@ int32_t diffopt_b200_create(int32_t device, diffopt_b200_ctx** out) {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) return -2;  // no CUDA device: there is no CPU fallback
     if (device < 0 || device >= count) return -1;
-    if (cudaSetDevice(device) != cudaSuccess) return -2;
+    DeviceGuard guard_(device);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -2;
     if (prop.major != 10) return -4;  // this library only carries sm_100a code
@@ -41,14 +41,17 @@ static void release_csr(CsrDev& c) {
 
 int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->in) b.release();
     for (auto& b : ctx->out) b.release();
     ctx->info.release();
     ctx->qp_fb.release();
     ctx->qp_max.release();
+    ctx->qp_sticky.release();
     if (ctx->qp_hmax_host) cudaFreeHost(ctx->qp_hmax_host);
+    for (cudaEvent_t ev : ctx->qp_hmax_ev)
+        if (ev) cudaEventDestroy(ev);
     QpBatchState& q = ctx->qp;
     q.Q.release(); q.G.release(); q.A.release(); q.h.release(); q.z.release(); q.lam.release(); q.nu.release();
     ConicState& c = ctx->conic;
@@ -89,6 +92,7 @@ int32_t qp_batch_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a) {
     bool handled = false;
     int32_t rc = qp_batch_launch_tuned(ctx, a, &handled);
     if (handled) return rc;
+    ctx->qp_last_kernel = 0;
     return qp_batch_launch_generic(ctx, a);
 }
 
@@ -130,6 +134,14 @@ static int32_t qp_solve_common(diffopt_b200_ctx* ctx, QpSolveArgs a, double* fwd
     a.fwd = (double*)dfwd;
     a.rev = (double*)drev;
     a.info = dinfo;
+    if (async) {
+        if (!ctx->qp_sticky.ptr) {
+            DO_CUDA(ctx, ctx->qp_sticky.reserve(sizeof(unsigned long long)));
+            DO_CUDA(ctx, cudaMemsetAsync(ctx->qp_sticky.ptr, 0xFF, sizeof(unsigned long long), ctx->stream));
+        }
+        a.sticky = ctx->qp_sticky.as<unsigned long long>();
+        a.call_seq = ctx->async_calls++;
+    }
     DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     int32_t rc = qp_batch_launch(ctx, a);
     if (rc != 0) return rc;
@@ -137,8 +149,7 @@ static int32_t qp_solve_common(diffopt_b200_ctx* ctx, QpSolveArgs a, double* fwd
     DO_CUDA(ctx, stage_out_finish(ctx, dfwd, fwd_user, sizeof(double) * B * N, memspace));
     DO_CUDA(ctx, stage_out_finish(ctx, drev, rev_user, sizeof(double) * B * N, memspace));
     if (async) {  // status is collected by diffopt_b200_synchronize
-        ctx->async_B = B;
-        ctx->async_info = dinfo;
+        ctx->async_pending = true;
         return 0;
     }
     std::vector<int> hinfo;
@@ -162,7 +173,7 @@ int32_t diffopt_b200_qp_batch_solve(diffopt_b200_ctx* ctx, int64_t B, int32_t n,
                                     const double* db, const double* dl_dz, double* fwd_out, double* rev_out,
                                     int32_t* info, int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     if (int32_t rc = check_shape(ctx, B, n, m, p)) return rc;
     if (B == 0) return 0;
     if (!Q || !z || (m > 0 && (!G || !h || !lam)) || (p > 0 && (!A || !nu)))
@@ -202,7 +213,7 @@ int32_t diffopt_b200_qp_batch_solve_async(diffopt_b200_ctx* ctx, int64_t B, int3
                                           const double* db, const double* dl_dz, double* fwd_out, double* rev_out,
                                           int32_t* info) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     if (int32_t rc = check_shape(ctx, B, n, m, p)) return rc;
     if (B == 0) return 0;
     if (!Q || !z || (m > 0 && (!G || !h || !lam)) || (p > 0 && (!A || !nu)))
@@ -217,15 +228,43 @@ int32_t diffopt_b200_qp_batch_solve_async(diffopt_b200_ctx* ctx, int64_t B, int3
     return qp_solve_common(ctx, a, fwd_out, rev_out, info, DIFFOPT_B200_DEVICE, true);
 }
 
+int32_t diffopt_b200_qp_batch_last_stats(diffopt_b200_ctx* ctx, int64_t* out3) {
+    if (!ctx || !out3) return -1;
+    DeviceGuard guard_(ctx->device);
+    out3[0] = 0;
+    out3[1] = ctx->qp_last_hint;
+    out3[2] = ctx->qp_last_kernel;
+    if (ctx->qp_last_kernel == 2 && ctx->qp_fb.ptr) {
+        int nfb = 0;
+        DO_CUDA(ctx, cudaMemcpyAsync(&nfb, ctx->qp_fb.ptr, sizeof nfb, cudaMemcpyDeviceToHost, ctx->stream));
+        DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        out3[0] = nfb;
+    }
+    return 0;
+}
+
 int32_t diffopt_b200_synchronize(diffopt_b200_ctx* ctx) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     int32_t rc = 0;
-    if (ctx->async_info && ctx->async_B > 0) {
-        std::vector<int> hinfo;
-        rc = finish_info(ctx, ctx->async_B, ctx->async_info, nullptr, DIFFOPT_B200_DEVICE, hinfo);
-        ctx->async_info = nullptr;
-        ctx->async_B = 0;
+    if (ctx->async_pending && ctx->qp_sticky.ptr) {
+        unsigned long long first_bad = ~0ull;
+        DO_CUDA(ctx, cudaMemcpyAsync(&first_bad, ctx->qp_sticky.ptr, sizeof first_bad, cudaMemcpyDeviceToHost, ctx->stream));
+        DO_CUDA(ctx, cudaMemsetAsync(ctx->qp_sticky.ptr, 0xFF, sizeof first_bad, ctx->stream));
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("kernel failed: ") + cudaGetErrorString(e);
+            return -100 - (int32_t)e;
+        }
+        if (first_bad != ~0ull) {
+            rc = (int32_t)(first_bad & 0xFFFFFFFFull);
+            char msg[128];
+            snprintf(msg, sizeof msg, "singular KKT matrix: instance %d of stream-ordered call %u since the last synchronize",
+                     rc, (unsigned)(first_bad >> 32));
+            ctx->err = msg;
+        }
+        ctx->async_pending = false;
+        ctx->async_calls = 0;
     } else {
         DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -238,7 +277,7 @@ int32_t diffopt_b200_qp_batch_setup(diffopt_b200_ctx* ctx, int64_t B, int32_t n,
                                     const double* Q, const double* G, const double* A, const double* h,
                                     const double* z, const double* lam, const double* nu, int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     if (int32_t rc = check_shape(ctx, B, n, m, p)) return rc;
     if (!Q || !z || (m > 0 && (!G || !h || !lam)) || (p > 0 && (!A || !nu)))
         BAD_ARG(ctx, "qp_batch_setup: Q, z (and G, h, lam when m > 0; A, nu when p > 0) are required");
@@ -276,7 +315,7 @@ static void fill_from_state(const QpBatchState& s, QpSolveArgs& a) {
 int32_t diffopt_b200_qp_batch_reverse(diffopt_b200_ctx* ctx, const double* dl_dz, double* rev_out, int32_t* info,
                                       int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     if (!ctx->qp.valid) BAD_ARG(ctx, "qp_batch_reverse: call qp_batch_setup first");
     if (!dl_dz || !rev_out) BAD_ARG(ctx, "qp_batch_reverse: dl_dz and rev_out are required");
     if (ctx->qp.B == 0) return 0;
@@ -292,7 +331,7 @@ int32_t diffopt_b200_qp_batch_forward(diffopt_b200_ctx* ctx, const double* dQ, c
                                       const double* dh, const double* dA, const double* db, double* fwd_out,
                                       int32_t* info, int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     if (!ctx->qp.valid) BAD_ARG(ctx, "qp_batch_forward: call qp_batch_setup first");
     if (!fwd_out) BAD_ARG(ctx, "qp_batch_forward: fwd_out is required");
     if (ctx->qp.B == 0) return 0;
@@ -315,7 +354,7 @@ int32_t diffopt_b200_qp_batch_param_grads(diffopt_b200_ctx* ctx, const double* r
                                           double* dQ, double* dq, double* dG, double* dh, double* dA, double* db,
                                           int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     QpBatchState& s = ctx->qp;
     if (!s.valid) BAD_ARG(ctx, "qp_batch_param_grads: call qp_batch_setup first");
     if (!rev) BAD_ARG(ctx, "qp_batch_param_grads: rev is required");

@@ -108,16 +108,42 @@ struct diffopt_b200_ctx {
     DevBuf info;
     DevBuf qp_fb;   // [count, list...] of instances the LDL' fast path hands to the pivoted LU kernel
     DevBuf qp_max;  // device scalar: largest active-set size of the batch
-    int* qp_hmax_host = nullptr;  // pinned copy of it, read at the start of the NEXT call (calls end synchronised)
+    // pinned ring of D2H copies of that word (slot = call number & 3), each followed by an event: a later call only
+    // trusts a slot whose event has completed (stream-ordered calls do not end synchronised), newest call wins
+    int* qp_hmax_host = nullptr;
+    cudaEvent_t qp_hmax_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t qp_hmax_call[4] = {-1, -1, -1, -1};  // host-side call counter of the copy in flight in each slot (-1: none)
+    int64_t qp_calls = 0;
+    int qp_last_kernel = -1;      // kernel of the last qp_batch call: 0 generic pivoted LU, 1 tuned pivoted LU, 2 LDL' fast path
+    int qp_last_hint = -1;        // active-set size that launch was configured for
     int qp_seq = 0;               // call number, tags the active-set word written by the LDL' kernel
     int qp_hint = -1;             // active-set size the next headline-shape launch is configured for (-1: unknown)
-    int64_t async_B = 0;          // batch size and info array of the last qp_batch_solve_async (status at synchronize)
-    int* async_info = nullptr;
+    // stream-ordered calls: every kernel that finds a singular instance lowers this device word with atomicMin to
+    // (call number << 32 | instance + 1); diffopt_b200_synchronize reads it, so a failure in ANY queued call surfaces
+    DevBuf qp_sticky;
+    unsigned async_calls = 0;     // calls enqueued since the last synchronize
+    bool async_pending = false;
     QpBatchState qp;
     ConicState conic;
     LsqrWork lsqr;
     CsrDev lsqr_mat;
     SparseBandState sparse;
+};
+
+// Entry points make the ctx's device current for their duration and restore the caller's device on exit (a host
+// process that drives several GPUs, e.g. through torch or CUDA.jl, keeps its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
 #define DO_CUDA(ctx, expr)                                                              \
@@ -185,7 +211,14 @@ struct QpSolveArgs {
     double *fwd, *rev;
     int* info;
     long long* prof;  // optional per-phase clock counters of CTA 0 (DIFFOPT_B200_PROFILE=1)
+    unsigned long long* sticky;  // optional: first failing (call, instance) of a stream-ordered sequence of calls
+    unsigned call_seq;
 };
+
+// what a kernel does when instance `inst` turned out singular in a stream-ordered call
+__device__ __forceinline__ void qp_report_sticky(const QpSolveArgs& a, long long inst) {
+    if (a.sticky) atomicMin(a.sticky, ((unsigned long long)a.call_seq << 32) | (unsigned)(inst + 1));
+}
 int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const std::vector<long long>& h_uoff);
 int32_t qp_batch_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a);
 int32_t qp_param_grads_launch(diffopt_b200_ctx* ctx, int64_t B, int n, int m, int p, const double* z,

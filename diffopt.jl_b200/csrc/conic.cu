@@ -186,7 +186,7 @@ int32_t diffopt_b200_lsqr_csc(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncol
                               double atol, double btol, double conlim, int64_t maxiter, double* x_out,
                               double* out_stats, int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     if (!colptr || !rowval || !nzval || !rhs || !x_out) BAD_ARG(ctx, "lsqr_csc: null argument");
     std::vector<char> t0, t1, t2;
     const void *hc, *hr, *hv;
@@ -219,7 +219,7 @@ int32_t diffopt_b200_conic_setup(diffopt_b200_ctx* ctx, int64_t n, int64_t m, co
                                  const double* x, const double* s, const double* y, int64_t ncones,
                                  const int32_t* cone_type, const int64_t* cone_dim, int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     ConicState& S = ctx->conic;
     S.valid = false;
     if (n <= 0 || m < 0 || ncones < 0) BAD_ARG(ctx, "conic_setup: bad sizes");
@@ -348,7 +348,7 @@ int32_t diffopt_b200_conic_setup(diffopt_b200_ctx* ctx, int64_t n, int64_t m, co
 
 int32_t diffopt_b200_conic_get_vp(diffopt_b200_ctx* ctx, double* vp_out, int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     if (!ctx->conic.valid) BAD_ARG(ctx, "conic_get_vp: call conic_setup first");
     if (!vp_out) BAD_ARG(ctx, "conic_get_vp: null output");
     DO_CUDA(ctx, cudaMemcpyAsync(vp_out, ctx->conic.vp.ptr, sizeof(double) * (size_t)ctx->conic.m,
@@ -361,7 +361,7 @@ int32_t diffopt_b200_conic_get_vp(diffopt_b200_ctx* ctx, double* vp_out, int32_t
 static int32_t conic_op_call(diffopt_b200_ctx* ctx, const double* t, int32_t transpose, double* out, int32_t memspace,
                              bool full_M) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     ConicState& S = ctx->conic;
     if (!S.valid) BAD_ARG(ctx, "conic operator: call conic_setup first");
     if (!t || !out) BAD_ARG(ctx, "conic operator: null argument");
@@ -397,7 +397,7 @@ int32_t diffopt_b200_conic_forward(diffopt_b200_ctx* ctx, int64_t dA_nnz, const 
                                    double conlim, int64_t maxiter, double* dx_out, double* dz_out, double* out_stats,
                                    int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     ConicState& S = ctx->conic;
     if (!S.valid) BAD_ARG(ctx, "conic_forward: call conic_setup first");
     if (dA_nnz < 0 || (dA_nnz > 0 && (!dA_row || !dA_col || !dA_val))) BAD_ARG(ctx, "conic_forward: bad dA triplets");
@@ -456,7 +456,7 @@ int32_t diffopt_b200_conic_reverse(diffopt_b200_ctx* ctx, const double* dx_seed,
                                    double conlim, int64_t maxiter, double* g_out, double* dc_out, double* db_out,
                                    double* out_stats, int32_t memspace) {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     ConicState& S = ctx->conic;
     if (!S.valid) BAD_ARG(ctx, "conic_reverse: call conic_setup first");
     if (!dx_seed) BAD_ARG(ctx, "conic_reverse: dx_seed is required");

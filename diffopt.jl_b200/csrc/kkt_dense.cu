@@ -129,7 +129,7 @@ extern "C" int32_t diffopt_b200_kkt_solve_csc(diffopt_b200_ctx* ctx, int64_t N, 
     if (!ctx) return -1;
     if (N <= 0 || nrhs <= 0 || !colptr || !rowval || !nzval || !rhs || !x_out) BAD_ARG(ctx, "kkt_solve_csc: bad argument");
     if (N > 8192) BAD_ARG(ctx, "kkt_solve_csc: N > 8192 needs the sparse path (not built yet)");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     int64_t nnz = 0;
     std::vector<int64_t> hcol;
     const void *dcol = nullptr, *drow = nullptr, *dval = nullptr;

@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
         if (do_fwd)
             for (int i = tid; i < N; i += GEN_THREADS) a.fwd[(size_t)inst * N + perm[i]] = -K[N + i * ld];
         if (a.info && tid == 0) a.info[inst] = ipiv[1];
+        if (tid == 0 && ipiv[1] != 0) qp_report_sticky(a, inst);
         __syncthreads();
     }
 }

@@ -749,6 +749,7 @@ __global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a, 
                 } else if (tid < N) rev[tid] = -S.y[NV + ma + (tid - NV - MI)];
             }
             if (a.info && tid == 0) a.info[inst] = S.info;
+            if (tid == 0 && S.info != 0) qp_report_sticky(a, inst);
         }
         __syncthreads();
         PROF(5);
@@ -839,11 +840,41 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
     // (no host round trip in the middle of the call); instances that do not fit that guess are handed to the
     // pivoted-LU kernel, and the size measured now configures the next call.
     DO_CUDA(ctx, ctx->qp_max.reserve(sizeof(int)));
-    if (!ctx->qp_hmax_host) DO_CUDA(ctx, cudaHostAlloc((void**)&ctx->qp_hmax_host, sizeof(int), cudaHostAllocDefault));
+    if (!ctx->qp_hmax_host) {
+        DO_CUDA(ctx, cudaHostAlloc((void**)&ctx->qp_hmax_host, 4 * sizeof(int), cudaHostAllocDefault));
+        for (cudaEvent_t& ev : ctx->qp_hmax_ev) DO_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     int* dmax = ctx->qp_max.as<int>();
     const bool first = ctx->qp_hint < 0;
-    if (!first) ctx->qp_hint = *ctx->qp_hmax_host & 0xFF;  // low byte: active-set size, high bits: call tag
-    // The largest active set of THIS batch configures the next call.  First call (and when the LDL' kernel does not
+    // Hint for this launch: the newest report whose D2H copy has COMPLETED (its event says so).  Stream-ordered calls
+    // (qp_batch_solve_async) return before their copies land, so a slot still in flight is left alone and the
+    // previous hint stays in force -- the hint only sizes the launch, results never depend on it.
+    if (!first) {
+        int64_t newest = -1;
+        for (int s = 0; s < 4; ++s) {
+            if (ctx->qp_hmax_call[s] < 0 || cudaEventQuery(ctx->qp_hmax_ev[s]) != cudaSuccess) continue;
+            if (ctx->qp_hmax_call[s] > newest) {
+                newest = ctx->qp_hmax_call[s];
+                ctx->qp_hint = ctx->qp_hmax_host[s] & 0xFF;  // low byte: active-set size, high bits: call tag
+            }
+            ctx->qp_hmax_call[s] = -1;
+        }
+    }
+    const int64_t call = ctx->qp_calls++;
+    // D2H copy of the word into a free ring slot + its event.  A slot stays taken until its copy has been seen to
+    // complete, so with many calls in flight the ring holds the OLDEST outstanding reports (they complete first as
+    // the stream drains) and newer calls skip the report instead of overwriting an unread one.
+    int slot = -1;
+    for (int s = 0; s < 4 && slot < 0; ++s)
+        if (ctx->qp_hmax_call[s] < 0) slot = s;
+    auto report_to_host = [&]() -> cudaError_t {
+        if (slot < 0) return cudaSuccess;
+        cudaError_t e = cudaMemcpyAsync(ctx->qp_hmax_host + slot, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) return e;
+        ctx->qp_hmax_call[slot] = call;
+        return cudaEventRecord(ctx->qp_hmax_ev[slot], ctx->stream);
+    };
+    // The largest active set of THIS batch configures a later call.  First call (and when the LDL' kernel does not
     // run): a small scan kernel; otherwise the LDL' kernel reports it itself while it assembles the instances.
     const bool want_ldl = !(force && strcmp(force, "lu") == 0);
     auto scan_active = [&]() -> cudaError_t {
@@ -859,9 +890,10 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
     if (clear) DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
     if (first) {
         DO_CUDA(ctx, scan_active());
-        DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        DO_CUDA(ctx, report_to_host());
         DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->qp_hint = *ctx->qp_hmax_host & 0xFF;
+        ctx->qp_hint = ctx->qp_hmax_host[slot] & 0xFF;
+        ctx->qp_hmax_call[slot] = -1;
     }
     const int nt_cap = (NV + ctx->qp_hint + PE + 7) / 8;
     bool reported = first;
@@ -869,15 +901,19 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
         int32_t rc = qp_sqd_launch(ctx, a, nt_cap, handled, first ? nullptr : dmax, ctx->qp_seq << 8);
         if (rc != 0) return rc;
         if (*handled) {
-            if (!first) DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            if (!first) DO_CUDA(ctx, report_to_host());
+            ctx->qp_last_kernel = 2;
+            ctx->qp_last_hint = ctx->qp_hint;
             return 0;
         }
     }
     if (!reported) {
         if (!clear) DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
         DO_CUDA(ctx, scan_active());
-        DO_CUDA(ctx, cudaMemcpyAsync(ctx->qp_hmax_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        DO_CUDA(ctx, report_to_host());
     }
+    ctx->qp_last_kernel = 1;
+    ctx->qp_last_hint = ctx->qp_hint;
     if (!first) {  // the guess may be too small for the plain LU launch: size it for the worst case
         return lu_launch(ctx, a, NTMAX, nullptr, nullptr, handled);
     }

@@ -371,7 +371,10 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         for (int q = 0; q < 4; ++q) hv[q] = a.h[b * MI + 8 * (warp + 4 * (q >> 1)) + 2 * t + (q & 1)];
         __syncthreads();
         ASUB(1);
-        if (tid >= nred && tid < np) T[tix(nt - 1, nt - 1) * 64 + el(tid & 7, tid & 7)] = -1.0;  // identity padding
+        if (tid < np - nred) {  // identity padding of rows nred .. np-1 (indexed from nred: nred may exceed the CTA size)
+            const int r = (nred + tid) & 7;
+            T[tix(nt - 1, nt - 1) * 64 + el(r, r)] = -1.0;
+        }
         // ---- G: D = G z - h for every row; active rows go to the matrix; warp w owns tile rows w, w+4
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {

@@ -573,7 +573,7 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
     if (N <= 0 || !colptr || !rowval || !nzval) BAD_ARG(ctx, "sparse_setup: bad argument");
     if (colptr[0] != 1) BAD_ARG(ctx, "sparse_setup: colptr must be 1-based (Julia SparseMatrixCSC)");
     if (N >= (int64_t)1 << 31) BAD_ARG(ctx, "sparse_setup: N too large");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     const int64_t nnz = colptr[N] - 1;
     // symmetrised pattern (without the diagonal) as CSR
     std::vector<int64_t> ptr((size_t)N + 1, 0);
@@ -686,7 +686,7 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
     SparseBandState& S = ctx->sparse;
     if (!S.valid) BAD_ARG(ctx, "sparse_solve: no factorisation (call diffopt_b200_sparse_setup first)");
     if (nrhs <= 0 || !rhs || !x_out) BAD_ARG(ctx, "sparse_solve: bad argument");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard_(ctx->device);
     const size_t bytes = sizeof(double) * (size_t)S.N * (size_t)nrhs;
     const void* dB = nullptr;
     void* dX = nullptr;

@@ -77,8 +77,10 @@ double diffopt_b200_last_kernel_ms(diffopt_b200_ctx* ctx);
  * db[B][p] in the reference's packed sign convention (db,dh = -constant,
  * QuadraticProgram.jl:374-395).  dl_dz[B][n] is the reverse seed.
  * fwd_out / rev_out [B][N] may be NULL to skip that mode.  info[B] (may be NULL):
- * 0 or the 1-based elimination step with an exactly zero pivot (the reference
- * throws SingularException there).
+ * 0, or nonzero when the factorisation met an exactly zero pivot (the reference throws
+ * SingularException there).  The nonzero value is a 1-based position in the elimination order
+ * of the kernel that served the instance (the tuned kernels eliminate a reduced, reordered
+ * system), so it identifies "singular", not a row of LHS.
  * Return: 0, or (first failing instance + 1) if any info != 0.
  */
 int32_t diffopt_b200_qp_batch_solve(
@@ -91,9 +93,12 @@ int32_t diffopt_b200_qp_batch_solve(
 
 /* Stream-ordered form for device-resident pipelines (memspace must be DIFFOPT_B200_DEVICE, e.g. CUDA.jl arrays):
  * the same work is enqueued on the ctx stream and the call returns without waiting, so consecutive batches run back
- * to back with no host round trip in between.  `diffopt_b200_synchronize` waits for the stream and returns the status
- * of the LAST enqueued call (0, or first failing instance + 1) -- the blocking form above is this pair in one call,
- * which is what the reference's `@elapsed` timing (QuadraticProgram.jl:317,358) needs. */
+ * to back with no host round trip in between.  `diffopt_b200_synchronize` waits for the stream and returns 0, or
+ * (first failing instance + 1) of the EARLIEST call enqueued since the previous synchronize that met a singular
+ * instance (every queued call is covered: the kernels record failures in a device word; the message of
+ * diffopt_b200_last_error names the call) -- the blocking form above is this pair in one call, which is what the
+ * reference's `@elapsed` timing (QuadraticProgram.jl:317,358) needs.  `info`, when given, must be a distinct device
+ * array per queued call. */
 int32_t diffopt_b200_qp_batch_solve_async(
     diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
     const double* Q, const double* G, const double* A, const double* h,
@@ -102,6 +107,11 @@ int32_t diffopt_b200_qp_batch_solve_async(
     const double* dA, const double* db, const double* dl_dz,
     double* fwd_out, double* rev_out, int32_t* info);
 int32_t diffopt_b200_synchronize(diffopt_b200_ctx* ctx);
+/* Diagnostics of the last qp_batch call on this ctx (waits for the stream): out3[0] = instances the pivot-free LDL'
+ * fast path handed to the partially pivoted LU kernel (semidefinite Q, rank-deficient active set, ... -- results are
+ * the same, throughput is not), out3[1] = active-set size the launch was configured for, out3[2] = kernel that served
+ * the call (0 generic pivoted LU, 1 tuned pivoted LU, 2 LDL' fast path). */
+int32_t diffopt_b200_qp_batch_last_stats(diffopt_b200_ctx* ctx, int64_t* out3);
 
 /* Two-phase form mirroring the reference's cache (`_gradient_cache` builds LHS once,
  * QuadraticProgram.jl:182-213; seeds may then change): setup keeps the problem data

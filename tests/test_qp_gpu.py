@@ -193,6 +193,30 @@ def test_active_set_sizes(ctx, na):
     assert rel_err(rev, orv).max() <= RTOL_DIRECT
 
 
+@pytest.mark.parametrize("na", [16, 41, 48, 50, 55, 57, 63])
+def test_ldl_fast_path_serves_every_active_set_size(ctx, na, monkeypatch):
+    """The pivot-free LDL' kernel itself (not its pivoted-LU safety net) must serve regular instances of every
+    active-set size, including reduced orders 80 + na >= 128 that are not multiples of 8 (the identity padding rows
+    are then indexed beyond the CTA size).  LICQ caps the rows with slack 0 at 48 (p = 16, n = 64); beyond that the
+    extra rows get lam > 0 with slack < 0, which keeps the reduced system quasi-definite at order 80 + na."""
+    monkeypatch.setenv("DIFFOPT_B200_QP_KERNEL", "ldl")
+    d = bench_data.qp_batch(12, n_active=min(na, 48), seed0=4100 + na)
+    if na > 48:
+        # more "active" rows than LICQ allows cannot have slack 0; give the extra rows lam > 0 with slack < 0
+        # (D/lam < 0 keeps the reduced system quasi-definite and nonsingular) so that the reduced order is 80 + na
+        for b in range(12):
+            idle = np.flatnonzero(d["lam"][b] == 0)[:na - 48]
+            d["lam"][b, idle] = 0.7
+    _solve(ctx, d)                      # first call of this size: configures the launch for it
+    fwd, rev, info = _solve(ctx, d)
+    assert not info.any()
+    nfb, hint, kern = ctx.qp_last_stats()
+    assert kern == 2 and nfb == 0, (nfb, hint, kern)
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
 def test_ragged_active_sets_in_one_batch(ctx):
     parts = [bench_data.qp_batch(6, n_active=na, seed0=300 + na) for na in (0, 3, 16, 29, 45)]
     d = {k: np.concatenate([q[k] for q in parts]) for k in parts[0]}
@@ -301,6 +325,17 @@ def test_stream_ordered_batch_calls(ctx):
                                                  capi.vp(o["info"].data_ptr())) == 0
     assert lib.diffopt_b200_synchronize(ctx.h) == 6      # first failing instance + 1
     assert o["info"].cpu().numpy()[5] > 0
+    # a failure in an EARLIER queued call is not lost behind later clean calls (info = NULL: every call shares the
+    # library's own info buffer, the device-side sticky word carries the status)
+    null = capi.vp(None)
+    assert lib.diffopt_b200_qp_batch_solve_async(ctx.h, B, 64, 64, 16, *[ptrs[f] for f in fields],
+                                                 capi.vp(o["fwd"].data_ptr()), capi.vp(o["rev"].data_ptr()), null) == 0
+    for (d2, t2, B2), o2 in zip(batches[1:], outs[1:]):
+        assert lib.diffopt_b200_qp_batch_solve_async(ctx.h, B2, 64, 64, 16, *[capi.vp(t2[f].data_ptr()) for f in fields],
+                                                     capi.vp(o2["fwd"].data_ptr()), capi.vp(o2["rev"].data_ptr()), null) == 0
+    assert lib.diffopt_b200_synchronize(ctx.h) == 6
+    assert b"call 0" in lib.diffopt_b200_last_error(ctx.h)
+    assert lib.diffopt_b200_synchronize(ctx.h) == 0
 
 
 @pytest.mark.parametrize("N,nrhs", [(1, 1), (9, 1), (70, 3), (300, 16), (1100, 5)])
