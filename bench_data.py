@@ -93,11 +93,18 @@ def lp_config1(n=200, m=100, n_active=60, seed=1):
 
 
 def conic_config4(n=5000, n_zero=500, n_nonneg=4000, n_soc=300, soc_dim=10, nnz_per_row=10, seed=4, psd_sides=(),
-                  col_window=None):
+                  col_window=None, active_frac=None, solution_scale=1.0):
     """Config 4: sparse conic program solved by construction (Moreau decomposition):
     zeta ~ N(0,1)^m, s = Pi_K(zeta), y = s - zeta in K*, x ~ N(0,1)^n, b = A x + s, c = -A'y,
     so v = y - s = -zeta.  Returns A (scipy CSC, the reference's A = -coefficients), b, c, x, s, y,
-    cone lists and a reverse seed."""
+    cone lists and a reverse seed.
+
+    ``active_frac`` / ``solution_scale`` give the WELL-CONDITIONED variant used for converged parity checks: with
+    zeta ~ N(0,1) half of the nonnegative rows are active and zeros + active rows + SOC rows barely exceed n, so M
+    is close to singular (cond ~ 1e7; default-tolerance LSQR stops after ~1e4 iterations at a rounding-dependent
+    point).  ``active_frac=0.75`` makes that fraction of the nonnegative rows active (sign of zeta chosen, magnitude
+    kept) and ``solution_scale=0.02`` scales (x, s, y) so that |b|, |c| are of the order of |A| -- cond(M) ~ 1e4,
+    LSQR converges in ~1e3 iterations at the default tolerances."""
     import scipy.sparse as sp
     from oracle import cones as oc  # projection only used to *construct* the data set
     rng = np.random.default_rng(seed)
@@ -117,6 +124,11 @@ def conic_config4(n=5000, n_zero=500, n_nonneg=4000, n_soc=300, soc_dim=10, nnz_
     A.sum_duplicates()
     A.sort_indices()
     zeta = rng.standard_normal(m)
+    if active_frac is not None and n_nonneg:
+        lo = n_zero
+        act = rng.permutation(n_nonneg) < int(round(active_frac * n_nonneg))
+        zeta[lo:lo + n_nonneg] = np.abs(zeta[lo:lo + n_nonneg]) * np.where(act, -1.0, 1.0)   # zeta < 0: s = 0, y > 0
+    zeta *= solution_scale
     # primal cone K = product of the MOI sets; s = Pi_K(zeta).  oracle.cones projects on the DUAL of
     # the listed set, which equals the set itself for nonneg/SOC/PSD; for Zeros, K = {0}.
     s = np.empty(m)
@@ -125,9 +137,16 @@ def conic_config4(n=5000, n_zero=500, n_nonneg=4000, n_soc=300, soc_dim=10, nnz_
         sl = slice(off[k], off[k + 1])
         s[sl] = 0.0 if t == oc.ZERO else oc.project(zeta[sl], t)
     y = s - zeta
-    x = rng.standard_normal(n)
+    x = rng.standard_normal(n) * solution_scale
     return dict(A=A, b=A @ x + s, c=-(A.T @ y), x=x, s=s, y=y, cone_types=cone_types, cone_dims=cone_dims,
                 seed=rng.standard_normal(n))
+
+
+def conic_config4_conditioned(**kw):
+    """Config 4 with 75 % of the nonnegative rows active and the solution scaled by 0.02 (see ``conic_config4``)."""
+    kw.setdefault("active_frac", 0.75)
+    kw.setdefault("solution_scale", 0.02)
+    return conic_config4(**kw)
 
 
 def mpc_config3(T=10_000, nx=6, nu=4, active_frac=0.1, seed=3):
@@ -204,3 +223,31 @@ def maxcut_config5(d=200, r=20, seed=5):
     x = oc.vec_symm(X)
     return dict(A=A, b=A @ x + s, c=-(A.T @ y), x=x, s=s, y=y, cone_types=[oc.ZERO, oc.PSD], cone_dims=[d, k],
                 seed=rng.normal(size=k), X=X, S=S, d=d)
+
+
+def portfolio_config3(n=100_000, nfac=100, density=0.1, active_frac=0.3, seed=33):
+    """Config 3, portfolio variant: n assets, ``nfac`` factors, Q = D + F F' in lifted sparse form (variables (x, y) with
+    the equalities F'x - y = 0), one budget equality 1'x = 1, long-only bounds x >= 0.  z = (x, y), n + nfac
+    variables; m = n inequality rows (-x <= 0), p = nfac + 1 equality rows.  ``active_frac`` of the assets sit on the
+    bound (x = 0, lam > 0).  The KKT pattern is an arrowhead: every asset couples to the dense budget row and to the
+    factor rows it loads on -- not banded under any ordering.  Returns the reference's LHS (create_LHS_matrix)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    nv = n + nfac
+    F = sp.random(n, nfac, density=density, random_state=np.random.RandomState(seed), format="csc",
+                  data_rvs=lambda k: rng.standard_normal(k))
+    D = rng.uniform(0.5, 1.5, size=n)
+    Q = sp.diags(np.concatenate([D, np.ones(nfac)]), format="csc")
+    A = sp.vstack([sp.hstack([F.T, -sp.identity(nfac)]), sp.hstack([sp.csr_matrix(np.ones((1, n))), sp.csr_matrix((1, nfac))])]).tocsc()
+    G = sp.hstack([-sp.identity(n), sp.csc_matrix((n, nfac))]).tocsc()
+    act = rng.random(n) < active_frac
+    x = np.where(act, 0.0, rng.uniform(0.1, 1.0, size=n))
+    x /= x.sum()
+    z = np.concatenate([x, F.T @ x])
+    lam = np.where(act, rng.uniform(0.5, 1.5, size=n), 0.0)
+    nu = rng.standard_normal(nfac + 1)
+    h = np.zeros(n)
+    Dg = G @ z - h
+    K = sp.bmat([[Q, G.T @ sp.diags(lam), A.T], [G, sp.diags(Dg), None], [A, None, sp.csc_matrix((nfac + 1, nfac + 1))]], format="csc")
+    K.sort_indices()
+    return dict(K=K, Q=Q, G=G, A=A, z=z, lam=lam, nu=nu, h=h, n=nv, m=n, p=nfac + 1)

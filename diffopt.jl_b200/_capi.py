@@ -44,6 +44,8 @@ SIGNATURES = {
     "diffopt_b200_kkt_solve_csc": (C.c_int32, [vp, C.c_int64, vp, vp, vp, C.c_int32, C.c_int64, vp, vp, C.c_int32]),
     "diffopt_b200_sparse_setup": (C.c_int32, [vp, C.c_int64, vp, vp, vp, C.c_int32, vp]),
     "diffopt_b200_sparse_solve": (C.c_int32, [vp, C.c_int64, vp, vp, C.c_int32]),
+    "diffopt_b200_sparse_stats": (C.c_int32, [vp, vp]),
+    "diffopt_b200_sparse_analyze": (C.c_int32, [C.c_int64, vp, vp, C.c_int32, vp]),
     "diffopt_b200_lsqr_csc": (C.c_int32, [vp, C.c_int64, C.c_int64, vp, vp, vp, C.c_int32, vp, C.c_double,
                                           C.c_double, C.c_double, C.c_int64, vp, vp, C.c_int32]),
     "diffopt_b200_conic_setup": (C.c_int32, [vp, C.c_int64, C.c_int64] + [vp] * 8 + [C.c_int64, vp, vp, C.c_int32]),

@@ -64,6 +64,7 @@ int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {
     for (DevBuf* b : {&l.u, &l.v, &l.w, &l.x, &l.tmp, &l.scal}) b->release();
     release_csr(ctx->lsqr_mat);
     for (DevBuf* b : {&ctx->sparse.AB, &ctx->sparse.ipiv, &ctx->sparse.perm, &ctx->sparse.work}) b->release();
+    sparse_mf_release(ctx);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);

@@ -89,6 +89,9 @@ struct SparseBandState {
     DevBuf AB, ipiv, perm, work;
 };
 
+struct SparseMfImpl;  // multifrontal factorisation kept by diffopt_b200_sparse_setup (sparse_mf.cu)
+void sparse_mf_release(struct diffopt_b200_ctx* ctx);
+
 struct LsqrWork {
     DevBuf u, v, w, x, tmp, scal;  // vectors and a small block of device scalars
 };
@@ -128,6 +131,9 @@ struct diffopt_b200_ctx {
     LsqrWork lsqr;
     CsrDev lsqr_mat;
     SparseBandState sparse;
+    SparseMfImpl* sparse_mf = nullptr;
+    int sparse_method = 0;        // factorisation currently held: 0 none, 1 banded LU (RCM), 2 multifrontal LU
+    int64_t sparse_N = 0;
 };
 
 // Entry points make the ctx's device current for their duration and restore the caller's device on exit (a host

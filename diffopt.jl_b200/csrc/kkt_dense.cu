@@ -5,6 +5,10 @@
 // -> info > 0 (the reference throws SingularException there).  Intended for the reference's problem sizes
 // (N up to a few thousand, the whole matrix stays L2 resident); many right-hand sides share the factorisation,
 // which the reference does not do (it refactorises per direction).
+#include <stdlib.h>
+
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -128,8 +132,35 @@ extern "C" int32_t diffopt_b200_kkt_solve_csc(diffopt_b200_ctx* ctx, int64_t N, 
                                               int32_t memspace) {
     if (!ctx) return -1;
     if (N <= 0 || nrhs <= 0 || !colptr || !rowval || !nzval || !rhs || !x_out) BAD_ARG(ctx, "kkt_solve_csc: bad argument");
-    if (N > 8192) BAD_ARG(ctx, "kkt_solve_csc: N > 8192 needs the sparse path (not built yet)");
     DeviceGuard guard_(ctx->device);
+    // The dense kernel is one CTA: fine for the reference's own problem sizes, hopeless beyond ~1000 unknowns.  Larger
+    // systems go through the sparse factorisation (multifrontal LU, sparse_mf.cu), which is what the reference's sparse
+    // `\` does at any size.  DIFFOPT_B200_DENSE_MAX moves the switch-over.
+    int64_t dense_max = 1024;
+    if (const char* dm = getenv("DIFFOPT_B200_DENSE_MAX")) dense_max = atoll(dm);
+    if (N > dense_max) {
+        std::vector<int64_t> hc, hr;
+        std::vector<double> hv;
+        const int64_t *pc = colptr, *pr = rowval;
+        const double* pvv = nzval;
+        if (memspace == DIFFOPT_B200_DEVICE) {  // the analysis runs on the host: fetch the matrix
+            hc.resize((size_t)N + 1);
+            DO_CUDA(ctx, cudaMemcpy(hc.data(), colptr, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyDeviceToHost));
+            const int64_t nz = hc[(size_t)N] - 1;
+            if (nz < 0) BAD_ARG(ctx, "kkt_solve_csc: colptr must be 1-based");
+            hr.resize((size_t)nz);
+            hv.resize((size_t)nz);
+            DO_CUDA(ctx, cudaMemcpy(hr.data(), rowval, sizeof(int64_t) * (size_t)nz, cudaMemcpyDeviceToHost));
+            DO_CUDA(ctx, cudaMemcpy(hv.data(), nzval, sizeof(double) * (size_t)nz, cudaMemcpyDeviceToHost));
+            pc = hc.data(); pr = hr.data(); pvv = hv.data();
+        }
+        int32_t rc = diffopt_b200_sparse_setup(ctx, N, pc, pr, pvv, trans, nullptr);
+        if (rc != 0) return rc;
+        const double factor_ms = ctx->last_ms;
+        rc = diffopt_b200_sparse_solve(ctx, nrhs, rhs, x_out, memspace);
+        ctx->last_ms += factor_ms;
+        return rc;
+    }
     int64_t nnz = 0;
     std::vector<int64_t> hcol;
     const void *dcol = nullptr, *drow = nullptr, *dval = nullptr;

@@ -565,8 +565,8 @@ __global__ void __launch_bounds__(32 * R_WARPS) band_solve_reg_kernel(int N, int
 
 }  // namespace
 
-extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval,
-                                             const double* nzval, int32_t trans, int64_t* bandwidth_out) {
+int32_t sparse_band_setup(diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                          int32_t trans, int64_t* bandwidth_out) {
     if (!ctx) return -1;
     SparseBandState& S = ctx->sparse;
     S.valid = false;
@@ -612,7 +612,7 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
     if (bandwidth_out) *bandwidth_out = bw;
     if (bw > BAND_MAX) {
         char buf[200];
-        snprintf(buf, sizeof buf, "sparse_setup: bandwidth %lld after RCM exceeds %d (general supernodal path not built yet)",
+        snprintf(buf, sizeof buf, "sparse_setup: bandwidth %lld after RCM exceeds %d (not a banded pattern)",
                  (long long)bw, BAND_MAX);
         ctx->err = buf;
         return -3;
@@ -681,7 +681,7 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
     return 0;
 }
 
-extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace) {
+int32_t sparse_band_solve(diffopt_b200_ctx* ctx, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace) {
     if (!ctx) return -1;
     SparseBandState& S = ctx->sparse;
     if (!S.valid) BAD_ARG(ctx, "sparse_solve: no factorisation (call diffopt_b200_sparse_setup first)");

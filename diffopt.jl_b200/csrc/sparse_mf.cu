@@ -1,0 +1,996 @@
+// Sparse direct path for general patterns: multifrontal LU with partial pivoting inside the fronts, for ONE large KKT
+// system with many right-hand sides -- `LHS \ RHS` of QuadraticProgram.jl:486-492 (UMFPACK in the reference), BASELINE
+// config 3.  The reference refactorises for every direction (:438); here the factorisation stays in the ctx.
+//
+// Host (analysis, once per pattern):
+//   * symmetrised pattern; vertices of very high degree (dense rows/columns such as a budget constraint) are set aside
+//     and eliminated last in one top front;
+//   * nested dissection by BFS level structures (George): a connected region is cut at the smallest level near its
+//     middle, thinned to the vertices that actually touch the far side; regions of <= LEAF vertices become leaf fronts,
+//     tiny components are packed together into one leaf; every separator is one front;
+//   * symbolic factorisation on that supernode partition: row structure of every front, assembly tree, relative
+//     indices child -> parent, destination of every matrix entry, tree levels.
+// Device (numeric):
+//   * factorisation level by level, ONE CTA PER FRONT, fronts of a level batched in one launch: the front is assembled
+//     in shared memory (matrix entries + extend-add of the children's contribution blocks in a fixed order, so the
+//     result is deterministic), its fully-summed block is eliminated with partial pivoting among the fully-summed rows
+//     (threshold test against the whole column; a front that would need a DELAYED pivot is reported, merged into its
+//     parent on the host and the factorisation repeated), the Schur complement is passed up;
+//   * multi-RHS solves level by level, one CTA per (front, tile of 64 right-hand sides), one thread per column of the
+//     tile: leaves gather their rows straight from the caller's column-major block and scatter the solution straight
+//     back, so the N x nrhs block crosses HBM four times in total (read b, write y, read y, write x).
+// Fronts beyond shared memory are processed in place in global memory by the same code (correct, not tuned).
+#include <algorithm>
+#include <chrono>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+int32_t sparse_band_setup(diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                          int32_t trans, int64_t* bandwidth_out);
+int32_t sparse_band_solve(diffopt_b200_ctx* ctx, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace);
+
+namespace {
+
+constexpr int MF_TC = 64;            // right-hand sides per solve CTA (one thread each)
+constexpr int MF_FACT_THREADS = 256;
+constexpr int MF_BIG_THREADS = 1024;
+constexpr double MF_PIV_U = 1e-3;    // threshold: |pivot| >= u * max|column| (rows not yet fully summed included)
+constexpr size_t MF_SMEM_CAP = 200 * 1024;
+
+struct MfFront {
+    int k, s, first, parent;    // fully-summed columns, boundary rows, first permuted position, parent front (-1: root)
+    int soff;                   // offset of the boundary list (permuted positions) and of the relative indices into the parent
+    int c0, c1;                 // children: child_idx[c0 .. c1)
+    int a0, a1;                 // matrix entries: aloc/asrc[a0 .. a1)
+    int leaf;
+    long long lp, up, cb, w;    // offsets: L panel (nf x k), U panel (k x s), contribution block (s x s), solve workspace row
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// numeric factorisation of one front (F: nf x nf column-major with leading dimension ld, in shared or global memory)
+template <int THREADS>
+__device__ void mf_factor_front(const MfFront fr, double* F, const int ld, double* rinv, const MfFront* fronts, const int* child_idx,
+                                const int* rel, const int* aloc, const int* asrc, const double* vals, double* Lp, double* Up,
+                                double* CB, int* piv, int* status, const int fid) {
+    __shared__ int sh_p, sh_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = fr.k, s = fr.s, nf = k + s;
+    for (int i = tid; i < nf * ld; i += THREADS) F[i] = 0.0;
+    if (tid == 0) sh_flag = 0;
+    __syncthreads();
+    for (int e = fr.a0 + tid; e < fr.a1; e += THREADS) {
+        const int loc = aloc[e];
+        atomicAdd(&F[(loc % nf) + (loc / nf) * ld], vals[asrc[e]]);
+    }
+    __syncthreads();
+    for (int ci = fr.c0; ci < fr.c1; ++ci) {  // extend-add, children in list order (deterministic sums)
+        const MfFront ch = fronts[child_idx[ci]];
+        const int sc = ch.s;
+        const int* r = rel + ch.soff;
+        const double* cb = CB + ch.cb;
+        for (int idx = tid; idx < sc * sc; idx += THREADS) {
+            const int a = idx % sc, b = idx / sc;
+            F[r[a] + r[b] * ld] += cb[idx];
+        }
+        __syncthreads();
+    }
+    for (int j = 0; j < k; ++j) {
+        if (warp == 0) {  // pivot search: largest entry among the fully-summed rows, and the column's largest overall
+            double best = -1.0, rest = 0.0;
+            int bi = j;
+            for (int i = j + lane; i < nf; i += 32) {
+                const double a = fabs(F[i + j * ld]);
+                if (i < k) {
+                    if (a > best) { best = a; bi = i; }
+                } else if (a > rest) rest = a;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o), orr = __shfl_xor_sync(0xffffffffu, rest, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                rest = fmax(rest, orr);
+            }
+            if (lane == 0) {
+                sh_p = bi;
+                if (!(best > 0.0)) {
+                    if (rest > 0.0) sh_flag |= 2;   // only rows that are not fully summed could pivot: delayed pivot needed
+                    else sh_flag |= 1;              // the whole column is zero: the matrix is singular
+                } else if (best < MF_PIV_U * rest) sh_flag |= 2;
+            }
+        }
+        __syncthreads();
+        const int p = sh_p;
+        if (p != j)
+            for (int c = tid; c < nf; c += THREADS) {
+                const double t = F[j + c * ld];
+                F[j + c * ld] = F[p + c * ld];
+                F[p + c * ld] = t;
+            }
+        __syncthreads();
+        const double pv = F[j + j * ld];
+        const double ri = pv != 0.0 ? 1.0 / pv : 0.0;
+        if (tid == 0) {
+            rinv[j] = ri;
+            piv[fr.first + j] = p;
+        }
+        const int rem = nf - j - 1;
+        for (int idx = tid; idx < rem * rem; idx += THREADS) {
+            const int i = j + 1 + idx % rem, c = j + 1 + idx / rem;
+            F[i + c * ld] = fma(-(F[i + j * ld] * ri), F[j + c * ld], F[i + c * ld]);
+        }
+        __syncthreads();
+    }
+    // write-back: L panel (unit-lower L11 scaled, U11 on and above the diagonal, L21), U12, contribution block
+    for (int idx = tid; idx < nf * k; idx += THREADS) {
+        const int r = idx % nf, c = idx / nf;
+        Lp[fr.lp + idx] = r > c ? F[r + c * ld] * rinv[c] : F[r + c * ld];
+    }
+    for (int idx = tid; idx < k * s; idx += THREADS) Up[fr.up + idx] = F[(idx % k) + (k + idx / k) * ld];
+    for (int idx = tid; idx < s * s; idx += THREADS) CB[fr.cb + idx] = F[(k + idx % s) + (k + idx / s) * ld];
+    if (tid == 0) status[fid] = sh_flag;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MF_FACT_THREADS) mf_factor_kernel(const int* list, const MfFront* fronts, const int* child_idx, const int* rel,
+                                                                    const int* aloc, const int* asrc, const double* vals, double* Lp,
+                                                                    double* Up, double* CB, int* piv, int* status) {
+    extern __shared__ __align__(16) double mf_smem[];
+    const int fid = list[blockIdx.x];
+    const MfFront fr = fronts[fid];
+    const int nf = fr.k + fr.s, ld = nf | 1;
+    mf_factor_front<MF_FACT_THREADS>(fr, mf_smem, ld, mf_smem + (size_t)nf * ld, fronts, child_idx, rel, aloc, asrc, vals, Lp, Up, CB,
+                                     piv, status, fid);
+}
+
+// fronts beyond shared memory: the same elimination in a global scratch area (scratch[b]: nf * ld + k doubles)
+__global__ void __launch_bounds__(MF_BIG_THREADS) mf_factor_big_kernel(const int* list, const long long* scratch_off, double* scratch,
+                                                                       const MfFront* fronts, const int* child_idx, const int* rel,
+                                                                       const int* aloc, const int* asrc, const double* vals, double* Lp,
+                                                                       double* Up, double* CB, int* piv, int* status) {
+    const int fid = list[blockIdx.x];
+    const MfFront fr = fronts[fid];
+    const int nf = fr.k + fr.s, ld = nf | 1;
+    double* F = scratch + scratch_off[blockIdx.x];
+    mf_factor_front<MF_BIG_THREADS>(fr, F, ld, F + (size_t)nf * ld, fronts, child_idx, rel, aloc, asrc, vals, Lp, Up, CB, piv, status,
+                                    fid);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// solves.  Y: N x nrhs row-major in PERMUTED row order (y after the forward sweep, x of the separator rows after the
+// backward sweep); W: per-front boundary updates (s x nrhs row-major).  SMALL: factor panels and the tile of the
+// right-hand sides in shared memory.  BIG: everything stays in global memory (Y itself is the work area).
+template <bool BIG>
+__global__ void __launch_bounds__(MF_TC) mf_forward_kernel(const int* list, const MfFront* fronts, const int* child_idx, const int* rel,
+                                                           const int* perm, const int* piv, const double* Lp, const double* B,
+                                                           double* Y, double* W, const long long N, const int nrhs) {
+    extern __shared__ __align__(16) double mf_smem[];
+    const int fid = list[blockIdx.x];
+    const MfFront fr = fronts[fid];
+    const int k = fr.k, s = fr.s, nf = k + s;
+    const int c0 = blockIdx.y * MF_TC, tid = threadIdx.x, col = c0 + tid;
+    const int ncol = min(MF_TC, nrhs - c0);
+    const int ldy = (k | 1), ldw = (s | 1);
+    double* Ls = mf_smem;                                   // nf x k            (SMALL)
+    double* Ys = BIG ? nullptr : Ls + (size_t)nf * k;       // [col][r], ld ldy
+    double* Ws = BIG ? nullptr : Ys + (size_t)MF_TC * ldy;  // [col][t], ld ldw
+    const double* L = Lp + fr.lp;
+    if (!BIG) {
+        for (int i = tid; i < nf * k; i += MF_TC) Ls[i] = L[i];
+        // own rows from the caller's column-major block: consecutive threads take consecutive rows of one column
+        for (int idx = tid; idx < k * ncol; idx += MF_TC) {
+            const int r = idx % k, c = idx / k;
+            Ys[c * ldy + r] = B[(size_t)perm[fr.first + r] + (size_t)N * (c0 + c)];
+        }
+        for (int i = tid; i < MF_TC * ldw; i += MF_TC) Ws[i] = 0.0;
+        __syncthreads();
+        L = Ls;
+    } else {
+        for (int idx = tid; idx < k * ncol; idx += MF_TC) {
+            const int r = idx % k, c = idx / k;
+            Y[(size_t)(fr.first + r) * nrhs + c0 + c] = B[(size_t)perm[fr.first + r] + (size_t)N * (c0 + c)];
+        }
+        __syncthreads();
+    }
+    if (tid >= ncol) return;
+    double* y = BIG ? Y + (size_t)fr.first * nrhs + col : Ys + tid * ldy;
+    const size_t ys = BIG ? (size_t)nrhs : 1;
+    double* w = BIG ? W + (size_t)fr.w * nrhs + col : Ws + tid * ldw;
+    const size_t ws = BIG ? (size_t)nrhs : 1;
+    if (BIG)
+        for (int t = 0; t < s; ++t) w[t * ws] = 0.0;
+    for (int ci = fr.c0; ci < fr.c1; ++ci) {  // updates of the children, in list order
+        const MfFront ch = fronts[child_idx[ci]];
+        const int* r = rel + ch.soff;
+        const double* cw = W + (size_t)ch.w * nrhs + col;
+        for (int t = 0; t < ch.s; ++t) {
+            const int loc = r[t];
+            const double v = cw[(size_t)t * nrhs];
+            if (loc < k) y[loc * ys] += v;
+            else w[(loc - k) * ws] += v;
+        }
+    }
+    const int* pv = piv + fr.first;
+    for (int j = 0; j < k; ++j) {
+        const int p = pv[j];
+        if (p != j) {
+            const double t = y[j * ys];
+            y[j * ys] = y[p * ys];
+            y[p * ys] = t;
+        }
+    }
+    for (int i = 1; i < k; ++i) {  // unit-lower L11
+        double acc = y[i * ys], acc2 = 0.0;
+        int j = 0;
+        for (; j + 1 < i; j += 2) {
+            acc = fma(-L[i + (size_t)j * nf], y[j * ys], acc);
+            acc2 = fma(-L[i + (size_t)(j + 1) * nf], y[(j + 1) * ys], acc2);
+        }
+        if (j < i) acc = fma(-L[i + (size_t)j * nf], y[j * ys], acc);
+        y[i * ys] = acc + acc2;
+    }
+    double* wout = W + (size_t)fr.w * nrhs + col;
+    for (int t = 0; t < s; ++t) {  // boundary update  w -= L21 y
+        double acc = w[t * ws], acc2 = 0.0;
+        int j = 0;
+        for (; j + 1 < k; j += 2) {
+            acc = fma(-L[k + t + (size_t)j * nf], y[j * ys], acc);
+            acc2 = fma(-L[k + t + (size_t)(j + 1) * nf], y[(j + 1) * ys], acc2);
+        }
+        if (j < k) acc = fma(-L[k + t + (size_t)j * nf], y[j * ys], acc);
+        wout[(size_t)t * nrhs] = acc + acc2;
+    }
+    if (!BIG) {
+        double* yo = Y + (size_t)fr.first * nrhs + col;
+        for (int r = 0; r < k; ++r) yo[(size_t)r * nrhs] = y[r];
+    }
+}
+
+template <bool BIG>
+__global__ void __launch_bounds__(MF_TC) mf_backward_kernel(const int* list, const MfFront* fronts, const int* strct, const int* perm,
+                                                            const double* Lp, const double* Up, double* Y, double* X, const long long N,
+                                                            const int nrhs) {
+    extern __shared__ __align__(16) double mf_smem[];
+    const int fid = list[blockIdx.x];
+    const MfFront fr = fronts[fid];
+    const int k = fr.k, s = fr.s, nf = k + s;
+    const int c0 = blockIdx.y * MF_TC, tid = threadIdx.x, col = c0 + tid;
+    const int ncol = min(MF_TC, nrhs - c0);
+    const int ldy = (k | 1), ldw = (s | 1);
+    double* U11s = mf_smem;                                   // k x k (upper part of the L panel), ld k
+    double* U12s = BIG ? nullptr : U11s + (size_t)k * k;      // k x s
+    double* Ys = BIG ? nullptr : U12s + (size_t)k * s;        // [col][r]
+    double* Xs = BIG ? nullptr : Ys + (size_t)MF_TC * ldy;    // [col][t]
+    const double* U11 = Lp + fr.lp;
+    const double* U12 = Up + fr.up;
+    int ldu = nf;
+    if (!BIG) {
+        for (int i = tid; i < k * k; i += MF_TC) U11s[i] = U11[(i % k) + (size_t)(i / k) * nf];
+        for (int i = tid; i < k * s; i += MF_TC) U12s[i] = U12[i];
+        __syncthreads();
+        U11 = U11s;
+        U12 = U12s;
+        ldu = k;
+    }
+    if (tid < ncol) {
+        double* y = BIG ? Y + (size_t)fr.first * nrhs + col : Ys + tid * ldy;
+        const size_t ys = BIG ? (size_t)nrhs : 1;
+        const int* sp = strct + fr.soff;
+        if (!BIG) {
+            const double* yi = Y + (size_t)fr.first * nrhs + col;
+            for (int r = 0; r < k; ++r) y[r] = yi[(size_t)r * nrhs];
+            double* x2 = Xs + tid * ldw;
+            for (int t = 0; t < s; ++t) x2[t] = Y[(size_t)sp[t] * nrhs + col];
+        }
+        for (int i = k - 1; i >= 0; --i) {
+            double acc = y[i * ys], acc2 = 0.0;
+            if (!BIG) {
+                const double* x2 = Xs + tid * ldw;
+                int t = 0;
+                for (; t + 1 < s; t += 2) {
+                    acc = fma(-U12[i + (size_t)t * k], x2[t], acc);
+                    acc2 = fma(-U12[i + (size_t)(t + 1) * k], x2[t + 1], acc2);
+                }
+                if (t < s) acc = fma(-U12[i + (size_t)t * k], x2[t], acc);
+            } else {
+                for (int t = 0; t < s; ++t) acc = fma(-U12[i + (size_t)t * k], Y[(size_t)sp[t] * nrhs + col], acc);
+            }
+            int j = i + 1;
+            for (; j + 1 < k; j += 2) {
+                acc = fma(-U11[i + (size_t)j * ldu], y[j * ys], acc);
+                acc2 = fma(-U11[i + (size_t)(j + 1) * ldu], y[(j + 1) * ys], acc2);
+            }
+            if (j < k) acc = fma(-U11[i + (size_t)j * ldu], y[j * ys], acc);
+            y[i * ys] = (acc + acc2) / U11[i + (size_t)i * ldu];
+        }
+        if (!BIG && !fr.leaf) {  // separator rows are read by the fronts below
+            double* yo = Y + (size_t)fr.first * nrhs + col;
+            for (int r = 0; r < k; ++r) yo[(size_t)r * nrhs] = y[r];
+        }
+    }
+    __syncthreads();
+    // solution rows back into the caller's column-major block (consecutive threads: consecutive rows of one column)
+    for (int idx = tid; idx < k * ncol; idx += MF_TC) {
+        const int r = idx % k, c = idx / k;
+        const double v = BIG ? Y[(size_t)(fr.first + r) * nrhs + c0 + c] : Ys[c * ldy + r];
+        X[(size_t)perm[fr.first + r] + (size_t)N * (c0 + c)] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host analysis
+struct Graph {
+    int64_t N;
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> adj;
+};
+
+struct Dissector {
+    const Graph& g;
+    int leaf_max;
+    std::vector<int32_t> region;   // region id of every vertex while it is unassigned, -1 once it is ordered
+    std::vector<int32_t> level;    // BFS scratch
+    std::vector<std::vector<int32_t>> snodes;  // supernodes in elimination order
+    int next_region = 1;
+    std::vector<int32_t> queue;
+
+    Dissector(const Graph& gr, int leaf) : g(gr), leaf_max(leaf), region((size_t)gr.N, 0), level((size_t)gr.N, -1) {}
+
+    // BFS inside region `rid` from `start`; fills queue (visit order) and level[]; returns the number of levels
+    int bfs(int32_t start, int32_t rid) {
+        queue.clear();
+        queue.push_back(start);
+        level[(size_t)start] = 0;
+        int nl = 1;
+        for (size_t head = 0; head < queue.size(); ++head) {
+            const int32_t v = queue[head];
+            for (int64_t e = g.ptr[(size_t)v]; e < g.ptr[(size_t)v + 1]; ++e) {
+                const int32_t w = g.adj[(size_t)e];
+                if (region[(size_t)w] == rid && level[(size_t)w] < 0) {
+                    level[(size_t)w] = level[(size_t)v] + 1;
+                    nl = level[(size_t)w] + 1;
+                    queue.push_back(w);
+                }
+            }
+        }
+        return nl;
+    }
+    void clear_levels() {
+        for (int32_t v : queue) level[(size_t)v] = -1;
+    }
+    void emit(std::vector<int32_t>& verts) {
+        std::sort(verts.begin(), verts.end());
+        for (int32_t v : verts) region[(size_t)v] = -1;
+        snodes.push_back(verts);
+    }
+
+    // orders all vertices of `verts` (all carrying region id rid)
+    void dissect(std::vector<int32_t>& verts, int32_t rid) {
+        // connected components
+        std::vector<std::vector<int32_t>> comps;
+        for (int32_t v0 : verts) {
+            if (level[(size_t)v0] >= 0 || region[(size_t)v0] != rid) continue;
+            bfs(v0, rid);
+            comps.emplace_back(queue);
+            for (int32_t v : queue) level[(size_t)v] = 1 << 30;  // keep them marked until all components are found
+        }
+        for (int32_t v : verts) level[(size_t)v] = -1;
+        std::vector<int32_t> bin;
+        for (auto& comp : comps) {
+            if ((int)comp.size() <= leaf_max) {  // small component: pack with its small siblings into one leaf front
+                if (!bin.empty() && (int)(bin.size() + comp.size()) > leaf_max) {
+                    emit(bin);
+                    bin.clear();
+                }
+                bin.insert(bin.end(), comp.begin(), comp.end());
+                continue;
+            }
+            const int32_t cid = next_region++;
+            for (int32_t v : comp) region[(size_t)v] = cid;
+            split(comp, cid);
+        }
+        if (!bin.empty()) emit(bin);
+    }
+
+    // connected region larger than a leaf: level-structure bisection
+    void split(std::vector<int32_t>& comp, int32_t rid) {
+        // pseudo-peripheral start: repeat BFS from a vertex of the last level
+        int32_t start = comp[0];
+        int nl = 0;
+        for (int it = 0; it < 3; ++it) {
+            nl = bfs(start, rid);
+            int32_t last = queue.back();
+            // smallest degree in the last level
+            int64_t bestdeg = INT64_MAX;
+            for (size_t i = queue.size(); i-- > 0 && level[(size_t)queue[i]] == nl - 1;) {
+                const int64_t d = g.ptr[(size_t)queue[i] + 1] - g.ptr[(size_t)queue[i]];
+                if (d < bestdeg) { bestdeg = d; last = queue[i]; }
+            }
+            if (it == 2) break;
+            clear_levels();
+            start = last;
+        }
+        if (nl < 3) {  // no interior level to cut at (clique-like): one dense front
+            clear_levels();
+            emit(comp);
+            return;
+        }
+        std::vector<int64_t> cnt((size_t)nl, 0);
+        for (int32_t v : queue) ++cnt[(size_t)level[(size_t)v]];
+        const int64_t total = (int64_t)queue.size();
+        int64_t before = cnt[0];
+        int best = -1;
+        double bestscore = 1e300;
+        for (int l = 1; l + 1 < nl; ++l) {
+            const double frac = (double)before / (double)total;
+            const double imbalance = fabs(frac + 0.5 * (double)cnt[(size_t)l] / (double)total - 0.5);
+            // small separators near the middle: size, penalised away from the centre
+            const double score = (double)cnt[(size_t)l] * (1.0 + 8.0 * imbalance * imbalance * 4.0) + (imbalance > 0.3 ? 1e9 * imbalance : 0.0);
+            if (score < bestscore) { bestscore = score; best = l; }
+            before += cnt[(size_t)l];
+        }
+        // thin the separator: a vertex of level `best` without a neighbour in level best + 1 joins the near side
+        std::vector<int32_t> sep, lo, hi;
+        for (int32_t v : queue) {
+            const int lv = level[(size_t)v];
+            if (lv < best) lo.push_back(v);
+            else if (lv > best) hi.push_back(v);
+            else {
+                bool touches = false;
+                for (int64_t e = g.ptr[(size_t)v]; e < g.ptr[(size_t)v + 1] && !touches; ++e) {
+                    const int32_t w = g.adj[(size_t)e];
+                    touches = region[(size_t)w] == rid && level[(size_t)w] == best + 1;
+                }
+                (touches ? sep : lo).push_back(v);
+            }
+        }
+        clear_levels();
+        const int32_t rlo = next_region++, rhi = next_region++, rsep = next_region++;
+        for (int32_t v : lo) region[(size_t)v] = rlo;
+        for (int32_t v : hi) region[(size_t)v] = rhi;
+        for (int32_t v : sep) region[(size_t)v] = rsep;
+        dissect(lo, rlo);
+        dissect(hi, rhi);
+        emit(sep);
+    }
+};
+
+struct MfLaunch {
+    int level, big, offset, count, max_nf, max_k, max_s;
+};
+
+struct MfHost {
+    std::vector<MfFront> fronts;
+    std::vector<int32_t> perm;       // permuted position -> original index
+    std::vector<int32_t> strct, rel, child_idx, aloc, asrc, lists;
+    std::vector<MfLaunch> launches;  // factorisation order (levels ascending)
+    int nlevels = 0;
+    long long lp_total = 0, up_total = 0, cb_total = 0, w_rows = 0, big_scratch = 0;
+    std::vector<long long> big_off;  // per big launch entry
+    double flops = 0.0;
+    long long nnz_lu = 0;
+    int max_front = 0;
+};
+
+// symbolic factorisation on a given supernode partition (snodes in elimination order)
+bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes, int64_t N, const int64_t* colptr, const int64_t* rowval,
+                 int trans, MfHost& H, std::string& err) {
+    const int S = (int)snodes.size();
+    H = MfHost();
+    H.perm.resize((size_t)N);
+    std::vector<int32_t> pos((size_t)N), sn_of_pos((size_t)N);
+    std::vector<int32_t> first((size_t)S + 1, 0);
+    {
+        int32_t q = 0;
+        for (int s = 0; s < S; ++s) {
+            first[(size_t)s] = q;
+            for (int32_t v : snodes[(size_t)s]) {
+                H.perm[(size_t)q] = v;
+                pos[(size_t)v] = q;
+                sn_of_pos[(size_t)q] = s;
+                ++q;
+            }
+        }
+        first[(size_t)S] = q;
+        if (q != N) {
+            err = "sparse_setup: internal error (ordering does not cover all vertices)";
+            return false;
+        }
+    }
+    H.fronts.resize((size_t)S);
+    std::vector<std::vector<int32_t>> children((size_t)S);
+    std::vector<int32_t> stamp((size_t)N, -1);
+    std::vector<int32_t> soff((size_t)S + 1, 0);
+    std::vector<int32_t> tmp;
+    std::vector<int> lvl((size_t)S, 0);
+    for (int s = 0; s < S; ++s) {
+        tmp.clear();
+        const int32_t end = first[(size_t)s + 1];
+        for (int32_t v : snodes[(size_t)s])
+            for (int64_t e = g.ptr[(size_t)v]; e < g.ptr[(size_t)v + 1]; ++e) {
+                const int32_t q = pos[(size_t)g.adj[(size_t)e]];
+                if (q >= end && stamp[(size_t)q] != s) {
+                    stamp[(size_t)q] = s;
+                    tmp.push_back(q);
+                }
+            }
+        for (int32_t c : children[(size_t)s]) {
+            const MfFront& ch = H.fronts[(size_t)c];
+            for (int t = 0; t < ch.s; ++t) {
+                const int32_t q = H.strct[(size_t)ch.soff + t];
+                if (q >= end && stamp[(size_t)q] != s) {
+                    stamp[(size_t)q] = s;
+                    tmp.push_back(q);
+                }
+            }
+            lvl[(size_t)s] = std::max(lvl[(size_t)s], lvl[(size_t)c] + 1);
+        }
+        std::sort(tmp.begin(), tmp.end());
+        MfFront& f = H.fronts[(size_t)s];
+        f.k = (int)snodes[(size_t)s].size();
+        f.s = (int)tmp.size();
+        f.first = first[(size_t)s];
+        f.soff = (int)H.strct.size();
+        f.leaf = children[(size_t)s].empty() ? 1 : 0;
+        f.parent = tmp.empty() ? -1 : sn_of_pos[(size_t)tmp[0]];
+        H.strct.insert(H.strct.end(), tmp.begin(), tmp.end());
+        if (f.parent >= 0) children[(size_t)f.parent].push_back(s);
+        if (H.strct.size() > (size_t)1 << 30) {
+            err = "sparse_setup: factor structure too large";
+            return false;
+        }
+    }
+    // relative indices into the parent, children lists, storage offsets
+    H.rel.assign(H.strct.size(), 0);
+    for (int s = 0; s < S; ++s) {
+        MfFront& f = H.fronts[(size_t)s];
+        f.c0 = (int)H.child_idx.size();
+        for (int32_t c : children[(size_t)s]) H.child_idx.push_back(c);
+        f.c1 = (int)H.child_idx.size();
+        if (f.parent >= 0) {
+            const MfFront& p = H.fronts[(size_t)f.parent];
+            const int32_t pend = p.first + p.k;
+            int t2 = 0;
+            for (int t = 0; t < f.s; ++t) {
+                const int32_t q = H.strct[(size_t)f.soff + t];
+                if (q < pend) H.rel[(size_t)f.soff + t] = q - p.first;
+                else {
+                    while (t2 < p.s && H.strct[(size_t)p.soff + t2] < q) ++t2;
+                    if (t2 >= p.s || H.strct[(size_t)p.soff + t2] != q) {
+                        err = "sparse_setup: internal error (child structure not contained in the parent front)";
+                        return false;
+                    }
+                    H.rel[(size_t)f.soff + t] = p.k + t2;
+                }
+            }
+        }
+        const long long nf = f.k + f.s;
+        f.lp = H.lp_total; H.lp_total += nf * f.k;
+        f.up = H.up_total; H.up_total += (long long)f.k * f.s;
+        f.cb = H.cb_total; H.cb_total += (long long)f.s * f.s;
+        f.w = H.w_rows; H.w_rows += f.s;
+        H.nnz_lu += nf * f.k + (long long)f.k * f.s;
+        const double k = f.k, s2 = f.s;
+        H.flops += 2.0 / 3.0 * k * k * k + 2.0 * k * k * s2 + 2.0 * k * s2 * s2;
+        H.max_front = std::max(H.max_front, (int)nf);
+        if (nf * nf > ((long long)1 << 31) - 1) {
+            err = "sparse_setup: a front is too large";
+            return false;
+        }
+    }
+    // matrix entries -> (front, local offset).  Entry (i, j) lives in the front that eliminates min(pos i, pos j).
+    {
+        std::vector<int32_t> cnt((size_t)S + 1, 0);
+        const int64_t nnz = colptr[N] - 1;
+        std::vector<int32_t> ef((size_t)nnz), el((size_t)nnz);
+        for (int64_t c = 0; c < N; ++c)
+            for (int64_t e = colptr[c] - 1; e < colptr[c + 1] - 1; ++e) {
+                int64_t r = rowval[e] - 1, cc = c;
+                if (trans) std::swap(r, cc);
+                const int32_t pr = pos[(size_t)r], pc = pos[(size_t)cc];
+                const int s = sn_of_pos[(size_t)std::min(pr, pc)];
+                const MfFront& f = H.fronts[(size_t)s];
+                auto loc = [&](int32_t q) -> int {
+                    if (q < f.first + f.k) return q - f.first;
+                    const int32_t* b = H.strct.data() + f.soff;
+                    const int32_t* it = std::lower_bound(b, b + f.s, q);
+                    return f.k + (int)(it - b);
+                };
+                const int nf = f.k + f.s;
+                ef[(size_t)e] = s;
+                el[(size_t)e] = loc(pr) + loc(pc) * nf;
+                ++cnt[(size_t)s + 1];
+            }
+        for (int s = 0; s < S; ++s) cnt[(size_t)s + 1] += cnt[(size_t)s];
+        H.aloc.resize((size_t)nnz);
+        H.asrc.resize((size_t)nnz);
+        std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
+        for (int64_t e = 0; e < nnz; ++e) {
+            const int32_t d = fill[(size_t)ef[(size_t)e]]++;
+            H.aloc[(size_t)d] = el[(size_t)e];
+            H.asrc[(size_t)d] = (int32_t)e;
+        }
+        for (int s = 0; s < S; ++s) {
+            H.fronts[(size_t)s].a0 = cnt[(size_t)s];
+            H.fronts[(size_t)s].a1 = cnt[(size_t)s + 1];
+        }
+    }
+    // launch groups: per tree level, fronts that fit shared memory (sorted by size) and the others
+    H.nlevels = 0;
+    for (int s = 0; s < S; ++s) H.nlevels = std::max(H.nlevels, lvl[(size_t)s] + 1);
+    std::vector<std::vector<int32_t>> bylevel((size_t)H.nlevels);
+    for (int s = 0; s < S; ++s) bylevel[(size_t)lvl[(size_t)s]].push_back(s);
+    for (int l = 0; l < H.nlevels; ++l) {
+        auto& v = bylevel[(size_t)l];
+        std::stable_sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
+            return H.fronts[(size_t)a].k + H.fronts[(size_t)a].s > H.fronts[(size_t)b].k + H.fronts[(size_t)b].s;
+        });
+        // size classes so that one huge front does not size the shared memory of thousands of small ones
+        size_t i = 0;
+        while (i < v.size()) {
+            const MfFront& f0 = H.fronts[(size_t)v[i]];
+            const int nf0 = f0.k + f0.s;
+            const bool big = (size_t)nf0 * (nf0 | 1) * 8 + (size_t)f0.k * 8 > MF_SMEM_CAP;
+            MfLaunch L{l, big ? 1 : 0, (int)H.lists.size(), 0, 0, 0, 0};
+            size_t j = i;
+            for (; j < v.size(); ++j) {
+                const MfFront& f = H.fronts[(size_t)v[j]];
+                const int nf = f.k + f.s;
+                const bool b2 = (size_t)nf * (nf | 1) * 8 + (size_t)f.k * 8 > MF_SMEM_CAP;
+                if (b2 != big) break;
+                if (!big && j > i && nf * 2 < nf0 && nf0 > 24) break;  // next size class
+                H.lists.push_back(v[j]);
+                L.max_nf = std::max(L.max_nf, nf);
+                L.max_k = std::max(L.max_k, f.k);
+                L.max_s = std::max(L.max_s, f.s);
+                if (big) {
+                    H.big_off.push_back(H.big_scratch);
+                    H.big_scratch += (long long)nf * (nf | 1) + f.k;
+                }
+            }
+            L.count = (int)(j - i);
+            H.launches.push_back(L);
+            i = j;
+        }
+    }
+    return true;
+}
+
+// symmetrised pattern + ordering (dense vertices last, nested dissection on the rest) -> supernodes in elimination order
+bool mf_order(int64_t N, const int64_t* colptr, const int64_t* rowval, Graph& g, std::vector<std::vector<int32_t>>& snodes,
+              std::string& err) {
+    // symmetrised pattern without the diagonal, duplicates removed
+    g.N = N;
+    g.ptr.assign((size_t)N + 1, 0);
+    for (int64_t c = 0; c < N; ++c)
+        for (int64_t e = colptr[c] - 1; e < colptr[c + 1] - 1; ++e) {
+            const int64_t r = rowval[e] - 1;
+            if (r < 0 || r >= N) {
+                err = "sparse_setup: row index out of range";
+                return false;
+            }
+            if (r != c) {
+                ++g.ptr[(size_t)r + 1];
+                ++g.ptr[(size_t)c + 1];
+            }
+        }
+    for (int64_t i = 0; i < N; ++i) g.ptr[(size_t)i + 1] += g.ptr[(size_t)i];
+    g.adj.resize((size_t)g.ptr[(size_t)N]);
+    {
+        std::vector<int64_t> fill(g.ptr.begin(), g.ptr.end() - 1);
+        for (int64_t c = 0; c < N; ++c)
+            for (int64_t e = colptr[c] - 1; e < colptr[c + 1] - 1; ++e) {
+                const int64_t r = rowval[e] - 1;
+                if (r != c) {
+                    g.adj[(size_t)fill[(size_t)r]++] = (int32_t)c;
+                    g.adj[(size_t)fill[(size_t)c]++] = (int32_t)r;
+                }
+            }
+        // sort + unique per vertex, compacting in place
+        int64_t w = 0;
+        std::vector<int64_t> nptr((size_t)N + 1, 0);
+        for (int64_t v = 0; v < N; ++v) {
+            int32_t* b = g.adj.data() + g.ptr[(size_t)v];
+            int32_t* e = g.adj.data() + g.ptr[(size_t)v + 1];
+            std::sort(b, e);
+            e = std::unique(b, e);
+            nptr[(size_t)v] = w;
+            for (int32_t* p = b; p < e; ++p) g.adj[(size_t)w++] = *p;
+        }
+        nptr[(size_t)N] = w;
+        g.ptr.swap(nptr);
+        g.adj.resize((size_t)w);
+    }
+    // ordering: dense vertices last, nested dissection on the rest
+    int leaf = 32;
+    if (const char* lf = getenv("DIFFOPT_B200_MF_LEAF")) leaf = std::max(1, atoi(lf));
+    {
+        Dissector D(g, leaf);
+        const double dense_deg = std::max(40.0, 10.0 * std::sqrt((double)N));
+        std::vector<int32_t> dense, rest;
+        for (int64_t v = 0; v < N; ++v) {
+            if ((double)(g.ptr[(size_t)v + 1] - g.ptr[(size_t)v]) > dense_deg) {
+                dense.push_back((int32_t)v);
+                D.region[(size_t)v] = -1;
+            } else rest.push_back((int32_t)v);
+        }
+        D.dissect(rest, 0);
+        if (!dense.empty()) D.emit(dense);
+        snodes.swap(D.snodes);
+    }
+    return true;
+}
+
+}  // namespace
+
+struct SparseMfImpl {
+    MfHost H;
+    std::vector<std::vector<int32_t>> snodes;
+    Graph g;
+    DevBuf fronts, perm, strct, rel, child_idx, aloc, asrc, lists, big_off, big_scratch, vals, Lp, Up, CB, piv, status, Y, W;
+    int retries = 0;
+    double analysis_ms = 0.0;
+    void release() {
+        for (DevBuf* b : {&fronts, &perm, &strct, &rel, &child_idx, &aloc, &asrc, &lists, &big_off, &big_scratch, &vals, &Lp, &Up, &CB, &piv,
+                          &status, &Y, &W})
+            b->release();
+    }
+};
+
+void sparse_mf_release(diffopt_b200_ctx* ctx) {
+    if (ctx->sparse_mf) {
+        ctx->sparse_mf->release();
+        delete ctx->sparse_mf;
+        ctx->sparse_mf = nullptr;
+    }
+}
+
+namespace {
+
+template <class T>
+cudaError_t upload(diffopt_b200_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
+    cudaError_t e = b.reserve(std::max<size_t>(v.size() * sizeof(T), 16));
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(b.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+}
+
+// uploads the symbolic structure and runs the numeric factorisation; returns 0, >0 singular, -5 delayed pivots needed
+// (failed_out lists those fronts), <0 error
+int32_t mf_numeric(diffopt_b200_ctx* ctx, SparseMfImpl& M, int64_t nnz, std::vector<int32_t>& failed_out) {
+    MfHost& H = M.H;
+    DO_CUDA(ctx, upload(ctx, M.fronts, H.fronts));
+    DO_CUDA(ctx, upload(ctx, M.perm, H.perm));
+    DO_CUDA(ctx, upload(ctx, M.strct, H.strct));
+    DO_CUDA(ctx, upload(ctx, M.rel, H.rel));
+    DO_CUDA(ctx, upload(ctx, M.child_idx, H.child_idx));
+    DO_CUDA(ctx, upload(ctx, M.aloc, H.aloc));
+    DO_CUDA(ctx, upload(ctx, M.asrc, H.asrc));
+    DO_CUDA(ctx, upload(ctx, M.lists, H.lists));
+    DO_CUDA(ctx, upload(ctx, M.big_off, H.big_off));
+    DO_CUDA(ctx, M.big_scratch.reserve(std::max<size_t>((size_t)H.big_scratch * 8, 16)));
+    DO_CUDA(ctx, M.Lp.reserve(std::max<size_t>((size_t)H.lp_total * 8, 16)));
+    DO_CUDA(ctx, M.Up.reserve(std::max<size_t>((size_t)H.up_total * 8, 16)));
+    DO_CUDA(ctx, M.CB.reserve(std::max<size_t>((size_t)H.cb_total * 8, 16)));
+    DO_CUDA(ctx, M.piv.reserve(sizeof(int) * H.perm.size()));
+    DO_CUDA(ctx, M.status.reserve(sizeof(int) * H.fronts.size()));
+    (void)nnz;
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    int big_seen = 0;
+    for (const MfLaunch& L : H.launches) {
+        if (L.count == 0) continue;
+        if (!L.big) {
+            const size_t smem = ((size_t)L.max_nf * (L.max_nf | 1) + (size_t)L.max_k) * sizeof(double);
+            DO_CUDA(ctx, cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            mf_factor_kernel<<<(unsigned)L.count, MF_FACT_THREADS, smem, ctx->stream>>>(
+                M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.child_idx.as<int>(), M.rel.as<int>(), M.aloc.as<int>(),
+                M.asrc.as<int>(), M.vals.as<double>(), M.Lp.as<double>(), M.Up.as<double>(), M.CB.as<double>(), M.piv.as<int>(),
+                M.status.as<int>());
+        } else {
+            mf_factor_big_kernel<<<(unsigned)L.count, MF_BIG_THREADS, 0, ctx->stream>>>(
+                M.lists.as<int>() + L.offset, M.big_off.as<long long>() + big_seen, M.big_scratch.as<double>(), M.fronts.as<MfFront>(),
+                M.child_idx.as<int>(), M.rel.as<int>(), M.aloc.as<int>(), M.asrc.as<int>(), M.vals.as<double>(), M.Lp.as<double>(),
+                M.Up.as<double>(), M.CB.as<double>(), M.piv.as<int>(), M.status.as<int>());
+            big_seen += L.count;
+        }
+        ctx->launches++;
+        DO_CUDA(ctx, cudaGetLastError());
+    }
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    std::vector<int> st(H.fronts.size());
+    DO_CUDA(ctx, cudaMemcpyAsync(st.data(), M.status.ptr, sizeof(int) * st.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    failed_out.clear();
+    for (size_t f = 0; f < st.size(); ++f) {
+        if (st[f] & 2) failed_out.push_back((int32_t)f);
+    }
+    if (!failed_out.empty()) return -5;
+    for (size_t f = 0; f < st.size(); ++f)
+        if (st[f] & 1) return (int32_t)H.fronts[f].first + 1;  // a zero column at this elimination step: singular
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval,
+                                             const double* nzval, int32_t trans, int64_t* bandwidth_out) {
+    if (!ctx) return -1;
+    ctx->sparse.valid = false;
+    ctx->sparse_method = 0;
+    if (N <= 0 || !colptr || !rowval || !nzval) BAD_ARG(ctx, "sparse_setup: bad argument");
+    if (colptr[0] != 1) BAD_ARG(ctx, "sparse_setup: colptr must be 1-based (Julia SparseMatrixCSC)");
+    if (N >= (int64_t)1 << 31) BAD_ARG(ctx, "sparse_setup: N too large");
+    const char* force = getenv("DIFFOPT_B200_SPARSE");
+    if (force && strcmp(force, "band") == 0) {
+        int32_t rc = sparse_band_setup(ctx, N, colptr, rowval, nzval, trans, bandwidth_out);
+        if (rc == 0) ctx->sparse_method = 1;
+        return rc;
+    }
+    if (bandwidth_out) *bandwidth_out = -1;
+    DeviceGuard guard_(ctx->device);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t nnz = colptr[N] - 1;
+    if (nnz >= ((int64_t)1 << 31) - 1) BAD_ARG(ctx, "sparse_setup: too many nonzeros");
+    if (!ctx->sparse_mf) ctx->sparse_mf = new SparseMfImpl();
+    SparseMfImpl& M = *ctx->sparse_mf;
+    {
+        std::string err;
+        if (!mf_order(N, colptr, rowval, M.g, M.snodes, err)) BAD_ARG(ctx, err);
+    }
+    Graph& g = M.g;
+    DO_CUDA(ctx, M.vals.reserve(std::max<size_t>(sizeof(double) * (size_t)nnz, 16)));
+    DO_CUDA(ctx, cudaMemcpyAsync(M.vals.ptr, nzval, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    M.retries = 0;
+    int32_t rc = 0;
+    for (;;) {
+        std::string err;
+        if (!mf_symbolic(g, M.snodes, N, colptr, rowval, trans, M.H, err)) {
+            ctx->err = err;
+            return -3;
+        }
+        M.analysis_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::vector<int32_t> failed;
+        rc = mf_numeric(ctx, M, nnz, failed);
+        if (rc != -5) break;
+        // delayed pivots: merge every failing front into its parent (its columns become fully summed there) and repeat
+        if (++M.retries > 8) break;
+        std::vector<char> drop(M.snodes.size(), 0);
+        bool progress = false;
+        for (int32_t f : failed) {
+            const int p = M.H.fronts[(size_t)f].parent;
+            if (p < 0) continue;  // a root cannot delay: the pivot is simply unacceptable
+            auto& dst = M.snodes[(size_t)p];
+            dst.insert(dst.begin(), M.snodes[(size_t)f].begin(), M.snodes[(size_t)f].end());
+            drop[(size_t)f] = 1;
+            progress = true;
+        }
+        if (!progress) break;
+        std::vector<std::vector<int32_t>> kept;
+        for (size_t s = 0; s < M.snodes.size(); ++s)
+            if (!drop[s]) kept.push_back(std::move(M.snodes[s]));
+        M.snodes.swap(kept);
+    }
+    if (rc == -5) {  // pivoting inside the fronts was not enough: banded LU with full partial pivoting if the pattern allows
+        int32_t rb = sparse_band_setup(ctx, N, colptr, rowval, nzval, trans, bandwidth_out);
+        if (rb == 0) ctx->sparse_method = 1;
+        else if (rb == -3) ctx->err = "sparse_setup: no acceptable pivots inside the fronts after merging, and the pattern is not banded";
+        return rb;
+    }
+    if (rc != 0) return rc;
+    ctx->sparse_method = 2;
+    ctx->sparse_N = N;
+    return 0;
+}
+
+extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace) {
+    if (!ctx) return -1;
+    if (ctx->sparse_method == 1) return sparse_band_solve(ctx, nrhs, rhs, x_out, memspace);
+    if (ctx->sparse_method != 2 || !ctx->sparse_mf) BAD_ARG(ctx, "sparse_solve: no factorisation (call diffopt_b200_sparse_setup first)");
+    if (nrhs <= 0 || !rhs || !x_out) BAD_ARG(ctx, "sparse_solve: bad argument");
+    if (nrhs > 65535 * MF_TC) BAD_ARG(ctx, "sparse_solve: too many right-hand sides in one call");
+    DeviceGuard guard_(ctx->device);
+    SparseMfImpl& M = *ctx->sparse_mf;
+    MfHost& H = M.H;
+    const int64_t N = ctx->sparse_N;
+    const size_t bytes = sizeof(double) * (size_t)N * (size_t)nrhs;
+    const void* dB = nullptr;
+    void* dX = nullptr;
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[5], rhs, bytes, memspace, &dB));
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[2], x_out, bytes, memspace, &dX));
+    DO_CUDA(ctx, M.Y.reserve(bytes));
+    DO_CUDA(ctx, M.W.reserve(std::max<size_t>(sizeof(double) * (size_t)H.w_rows * (size_t)nrhs, 16)));
+    const unsigned tiles = (unsigned)((nrhs + MF_TC - 1) / MF_TC);
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    auto smem_fwd = [](const MfLaunch& L) {
+        return ((size_t)L.max_nf * L.max_k + (size_t)MF_TC * (L.max_k | 1) + (size_t)MF_TC * (L.max_s | 1)) * sizeof(double);
+    };
+    auto smem_bwd = [](const MfLaunch& L) {
+        return ((size_t)L.max_k * L.max_k + (size_t)L.max_k * L.max_s + (size_t)MF_TC * (L.max_k | 1) + (size_t)MF_TC * (L.max_s | 1)) *
+               sizeof(double);
+    };
+    for (const MfLaunch& L : H.launches) {
+        if (L.count == 0) continue;
+        const dim3 grid((unsigned)L.count, tiles);
+        const size_t smem = smem_fwd(L);
+        const bool big = L.big || smem > MF_SMEM_CAP;
+        if (!big) {
+            DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            mf_forward_kernel<false><<<grid, MF_TC, smem, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(),
+                                                                         M.child_idx.as<int>(), M.rel.as<int>(), M.perm.as<int>(),
+                                                                         M.piv.as<int>(), M.Lp.as<double>(), (const double*)dB,
+                                                                         M.Y.as<double>(), M.W.as<double>(), N, (int)nrhs);
+        } else {
+            mf_forward_kernel<true><<<grid, MF_TC, 0, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(),
+                                                                     M.child_idx.as<int>(), M.rel.as<int>(), M.perm.as<int>(),
+                                                                     M.piv.as<int>(), M.Lp.as<double>(), (const double*)dB, M.Y.as<double>(),
+                                                                     M.W.as<double>(), N, (int)nrhs);
+        }
+        ctx->launches++;
+    }
+    for (size_t li = H.launches.size(); li-- > 0;) {
+        const MfLaunch& L = H.launches[li];
+        if (L.count == 0) continue;
+        const dim3 grid((unsigned)L.count, tiles);
+        const size_t smem = smem_bwd(L);
+        const bool big = L.big || smem > MF_SMEM_CAP || smem_fwd(L) > MF_SMEM_CAP;
+        if (!big) {
+            DO_CUDA(ctx, cudaFuncSetAttribute(mf_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            mf_backward_kernel<false><<<grid, MF_TC, smem, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(),
+                                                                          M.strct.as<int>(), M.perm.as<int>(), M.Lp.as<double>(),
+                                                                          M.Up.as<double>(), M.Y.as<double>(), (double*)dX, N, (int)nrhs);
+        } else {
+            mf_backward_kernel<true><<<grid, MF_TC, 0, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(),
+                                                                      M.strct.as<int>(), M.perm.as<int>(), M.Lp.as<double>(),
+                                                                      M.Up.as<double>(), M.Y.as<double>(), (double*)dX, N, (int)nrhs);
+        }
+        ctx->launches++;
+    }
+    DO_CUDA(ctx, cudaGetLastError());
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    DO_CUDA(ctx, stage_out_finish(ctx, dX, x_out, bytes, memspace));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    return 0;
+}
+
+// Host-only analysis (no GPU involved): ordering + symbolic factorisation of a pattern, for inspection and tests.
+extern "C" int32_t diffopt_b200_sparse_analyze(int64_t N, const int64_t* colptr, const int64_t* rowval, int32_t trans, double* out8) {
+    if (N <= 0 || !colptr || !rowval || !out8 || colptr[0] != 1) return -1;
+    Graph g;
+    std::vector<std::vector<int32_t>> snodes;
+    MfHost H;
+    std::string err;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!mf_order(N, colptr, rowval, g, snodes, err)) return -1;
+    if (!mf_symbolic(g, snodes, N, colptr, rowval, trans, H, err)) return -3;
+    out8[0] = 2.0;
+    out8[1] = (double)H.fronts.size();
+    out8[2] = (double)H.nlevels;
+    out8[3] = (double)H.max_front;
+    out8[4] = (double)H.nnz_lu;
+    out8[5] = H.flops;
+    out8[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    out8[7] = (double)H.launches.size();
+    return 0;
+}
+
+extern "C" int32_t diffopt_b200_sparse_stats(diffopt_b200_ctx* ctx, double* out8) {
+    if (!ctx || !out8) return -1;
+    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+    out8[0] = (double)ctx->sparse_method;
+    if (ctx->sparse_method == 2 && ctx->sparse_mf) {
+        const SparseMfImpl& M = *ctx->sparse_mf;
+        out8[1] = (double)M.H.fronts.size();
+        out8[2] = (double)M.H.nlevels;
+        out8[3] = (double)M.H.max_front;
+        out8[4] = (double)M.H.nnz_lu;
+        out8[5] = M.H.flops;
+        out8[6] = M.analysis_ms;
+        out8[7] = (double)M.retries;
+    }
+    return 0;
+}

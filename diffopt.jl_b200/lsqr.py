@@ -57,10 +57,22 @@ def solve_csc(ctx: Context, M, rhs, trans=False):
     return X[:, 0].copy() if one else X
 
 
+def sparse_analyze(M, trans=False):
+    """Host-only ordering + symbolic factorisation of a pattern (``diffopt_b200_sparse_analyze``; no GPU needed)."""
+    from ._capi import load
+    colptr, rowval, _ = julia_csc(M)
+    st = np.zeros(8)
+    rc = load().diffopt_b200_sparse_analyze(M.shape[0], ptr(colptr), ptr(rowval), int(trans), ptr(st))
+    if rc != 0:
+        raise RuntimeError(f"sparse_analyze failed ({rc})")
+    return dict(fronts=int(st[1]), levels=int(st[2]), max_front=int(st[3]), nnz_lu=int(st[4]), factor_flops=float(st[5]),
+                analysis_ms=float(st[6]), launches=int(st[7]))
+
+
 class SparseFactorization:
     """``diffopt_b200_sparse_setup`` / ``_sparse_solve``: one factorisation of a large sparse KKT matrix (or of its
-    adjoint) on the device, reused for any number of right-hand sides -- the direct ``LHS \\ RHS`` of
-    QuadraticProgram.jl:490 for systems beyond the dense kernels (BASELINE config 3)."""
+    adjoint) on the device (multifrontal LU; banded LU as fallback), reused for any number of right-hand sides -- the
+    direct ``LHS \\ RHS`` of QuadraticProgram.jl:490 for systems beyond the dense kernels (BASELINE config 3)."""
 
     def __init__(self, ctx: Context, M, trans=False):
         from ._capi import SingularException
@@ -72,8 +84,13 @@ class SparseFactorization:
         ctx.check(rc)
         if rc > 0:
             raise SingularException(rc)
-        self.bandwidth = int(bw[0])
+        self.bandwidth = int(bw[0])          # -1: multifrontal path (no band involved)
         self.factor_ms = ctx.last_kernel_ms
+        st = np.zeros(8)
+        ctx.check(ctx.lib.diffopt_b200_sparse_stats(ctx.h, ptr(st)))
+        self.stats = dict(method={0: "none", 1: "band", 2: "multifrontal"}[int(st[0])], fronts=int(st[1]), levels=int(st[2]),
+                          max_front=int(st[3]), nnz_lu=int(st[4]), factor_flops=float(st[5]), analysis_ms=float(st[6]),
+                          delayed_pivot_retries=int(st[7]))
 
     def solve(self, rhs):
         rhs = np.asarray(rhs, dtype=np.float64)

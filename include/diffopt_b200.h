@@ -145,25 +145,37 @@ int32_t diffopt_b200_qp_batch_param_grads(
  * LHS is Julia's SparseMatrixCSC{Float64,Int} (colptr/rowval 1-based int64, N x N); trans = 1 solves with LHS'
  * (the `Adjoint` forward_differentiate! passes, QuadraticProgram.jl:438).  rhs / x_out are N x nrhs column-major:
  * all right-hand sides share ONE partially pivoted LU factorisation (the reference refactorises per call).
- * Returns 0, or the 1-based elimination step with an exactly zero pivot (reference: SingularException).
- * N <= 8192 (dense on-device factorisation); larger systems need the sparse path. */
+ * Returns 0, or > 0 when the matrix is singular (an exactly zero pivot; reference: SingularException).
+ * Small systems (N <= 1024) are densified and factorised by one CTA; larger ones go through the sparse
+ * factorisation below (setup + solve in one call), as the reference's sparse `\` does at any size. */
 int32_t diffopt_b200_kkt_solve_csc(
     diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
     int32_t trans, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace);
 
 /* ---- sparse direct path: one large KKT system, many right-hand sides (BASELINE config 3) ----------------------
  *
- * sparse_setup factorises LHS (SparseMatrixCSC{Float64,Int} in HOST memory, 1-based; trans = 1: LHS') once:
- * reverse Cuthill-McKee ordering on the host, banded LU with partial pivoting on the device.  The factorisation stays
- * in the ctx; sparse_solve then solves for nrhs columns (rhs / x_out are N x nrhs column-major, host or device per
- * memspace) -- `LHS \ RHS` of QuadraticProgram.jl:490 without the reference's refactorisation per direction (:438).
- * Returns 0; > 0: exactly zero pivot (SingularException); -3: bandwidth after RCM above 255 (not a banded problem).
- * bandwidth_out (may be NULL) receives the half bandwidth found. */
+ * sparse_setup factorises LHS (SparseMatrixCSC{Float64,Int} in HOST memory, 1-based; trans = 1: LHS') once and keeps
+ * the factorisation in the ctx: `LHS \ RHS` of QuadraticProgram.jl:490 (UMFPACK in the reference) without the
+ * reference's refactorisation per direction (:438).  Method: multifrontal LU for general patterns -- nested-dissection
+ * ordering and symbolic factorisation on the host, fronts factorised level by level on the device with partial
+ * pivoting inside each front (a front that needs a delayed pivot is merged into its parent and the factorisation
+ * repeated).  If that still finds no acceptable pivots, a banded LU with full partial pivoting (reverse Cuthill-McKee
+ * ordering) is used when the pattern is banded (DIFFOPT_B200_SPARSE=band forces it).
+ * sparse_solve then solves for nrhs columns (rhs / x_out are N x nrhs column-major, host or device per memspace).
+ * Returns 0; > 0: the matrix is singular (SingularException in the reference); -3: no acceptable pivot order found.
+ * bandwidth_out (may be NULL) receives the half bandwidth when the banded path was used, -1 otherwise. */
 int32_t diffopt_b200_sparse_setup(
     diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
     int32_t trans, int64_t* bandwidth_out);
 int32_t diffopt_b200_sparse_solve(
     diffopt_b200_ctx* ctx, int64_t nrhs, const double* rhs, double* x_out, int32_t memspace);
+/* out8 = {method (0 none, 1 banded, 2 multifrontal), fronts, tree levels, largest front order, nnz(L+U) stored,
+ * factorisation flop, host analysis ms, delayed-pivot repetitions} of the factorisation held by the ctx. */
+int32_t diffopt_b200_sparse_stats(diffopt_b200_ctx* ctx, double* out8);
+/* Host-only analysis of a pattern (ordering + symbolic factorisation, no GPU involved): out8 as above with
+ * out8[7] = number of kernel launches one factorisation takes. */
+int32_t diffopt_b200_sparse_analyze(
+    int64_t N, const int64_t* colptr, const int64_t* rowval, int32_t trans, double* out8);
 
 /* ---- LSQR (IterativeSolvers.lsqr call sites QuadraticProgram.jl:488, ConicProgram.jl:323,372)
  *

@@ -209,3 +209,52 @@ def Dpi_apply(v, cone_types, cone_dims, y, transpose=False):
         s = slice(off[c], off[c + 1])
         out[s] = apply_gradient(v[s], t, y[s], transpose)
     return out
+
+
+class DpiOperator:
+    """``Dpi_apply`` with the per-cone work that does not depend on the argument done once (eigendecompositions,
+    triangle index maps): the form an iterative solve needs on large PSD cones.  Same arithmetic as
+    ``apply_gradient``; ``tests/test_oracle_kat.py`` checks the two against each other."""
+
+    def __init__(self, v, cone_types, cone_dims):
+        v = np.asarray(v, float)
+        self.off = cone_offsets(cone_dims)
+        self.types = list(cone_types)
+        self.v = v
+        self.psd = {}
+        for c, t in enumerate(self.types):
+            if t != PSD:
+                continue
+            vs = v[self.off[c]:self.off[c + 1]]
+            d = psd_side(vs.size)
+            iu = np.triu_indices(d)
+            idx = np.lexsort((iu[0], iu[1]))
+            r, cc = iu[0][idx], iu[1][idx]
+            X = np.zeros((d, d))
+            X[r, cc] = vs
+            X[cc, r] = vs
+            lam, U = np.linalg.eigh(X)
+            self.psd[c] = (d, r, cc, U, None if np.all(lam >= 0) else _psd_B(lam))
+
+    def apply(self, y, transpose=False):
+        y = np.asarray(y, float)
+        out = np.empty(self.off[-1])
+        for c, t in enumerate(self.types):
+            s = slice(self.off[c], self.off[c + 1])
+            if t != PSD:
+                out[s] = apply_gradient(self.v[s], t, y[s], transpose)
+                continue
+            d, r, cc, U, B = self.psd[c]
+            if B is None:
+                out[s] = y[s]
+                continue
+            Y = np.zeros((d, d))
+            Y[r, cc] = y[s]
+            Y[cc, r] = y[s]
+            if not transpose:
+                Y[np.diag_indices(d)] *= 2.0
+            R = U @ (B * (U.T @ Y @ U)) @ U.T
+            if not transpose:
+                R[np.diag_indices(d)] *= 0.5
+            out[s] = R[r, cc]
+        return out

@@ -101,17 +101,41 @@ def reverse_param_grads(cache, g, dense_dA=True):
     return dA, db, dc
 
 
-def M_apply(A, b, c, v, cone_types, cone_dims, t, transpose=False):
+def M_apply(A, b, c, v, cone_types, cone_dims, t, transpose=False, dpi=None):
     """Matrix-free M t / M' t -- the operator the CUDA LSQR uses; checked against the
-    explicit ``gradient_cache().M`` in the tests."""
+    explicit ``gradient_cache().M`` in the tests.  ``dpi``: optional ``cones.DpiOperator(v, ...)``
+    (cached eigendecompositions) for repeated applications."""
     A = sp.csr_matrix(A)
     m, n = A.shape
     t1, t2, t3 = t[:n], t[n:n + m], t[n + m]
+    Dpi = (lambda y, tr=False: cones.Dpi_apply(v, cone_types, cone_dims, y, tr)) if dpi is None else dpi.apply
     if not transpose:
-        w = cones.Dpi_apply(v, cone_types, cone_dims, t2)
+        w = Dpi(t2)
         return np.concatenate([A.T @ w + c * t3, -(A @ t1) + t2 - w + b * t3,
                                [-(c @ t1) - b @ w]])
     r = A @ t1 - t2 - b * t3
-    return np.concatenate([-(A.T @ t2) - c * t3,
-                           cones.Dpi_apply(v, cone_types, cone_dims, r, transpose=True) + t2,
-                           [c @ t1 + b @ t2]])
+    return np.concatenate([-(A.T @ t2) - c * t3, Dpi(r, True) + t2, [c @ t1 + b @ t2]])
+
+
+def matrix_free_ops(A, b, c, x, s, y, cone_types, cone_dims):
+    """(matvec, rmatvec, shape) of M for ``lsqr`` without forming M (large PSD cones: the reference's dense
+    Dpi block of a 200 x 200 cone alone is 3.2 GB)."""
+    A = sp.csr_matrix(A)
+    m, n = A.shape
+    v = np.asarray(y, float) - np.asarray(s, float)
+    op = cones.DpiOperator(v, cone_types, cone_dims)
+    N = n + m + 1
+    return ((lambda t: M_apply(A, b, c, v, cone_types, cone_dims, t, False, op)),
+            (lambda t: M_apply(A, b, c, v, cone_types, cone_dims, t, True, op)), (N, N))
+
+
+def reverse_matrix_free(A, b, c, x, s, y, cone_types, cone_dims, dx_seed, **lsqr_kw):
+    """``reverse`` (:349-373) on the matrix-free operator."""
+    A = sp.csr_matrix(A)
+    m, n = A.shape
+    x = np.asarray(x, float)
+    dx = np.asarray(dx_seed, float)
+    dz = np.concatenate([dx, np.zeros(m), [-(x @ dx)]])
+    if np.linalg.norm(dz) <= 1e-4:
+        return np.zeros_like(dz)
+    return lsqr(matrix_free_ops(A, b, c, x, s, y, cone_types, cone_dims), dz, **lsqr_kw)

@@ -123,6 +123,30 @@ cases["lp_nonactive"] = dict(
     tol=1e-2,
 )
 
+# KAT 8: dispatch LP of test/jump.jl:473-638 (`test_sensitivity_index_issue`).  Variables (v, u, g1, g2, g3, a);
+# HiGHS' solution z = (0, 45, 15, 20, 20, 50) is asserted there (:540-543); the duals follow from stationarity
+# c + G'lam + A'nu = 0 with lam = 0 on the inactive rows (the vertex is nondegenerate: 4 active inequalities + 2
+# equalities = 6 variables, all active multipliers > 0, so the KKT matrix is nonsingular and the solver's duals are these).
+# The reference perturbs the constant of each of the 13 constraints by +1 (ForwardConstraintFunction = 1.0, :606-613) and
+# compares -dz with +-(column i of lsqr(KKT, rhsKKT)) (:624-636).  In the packed convention of
+# QuadraticProgram.jl:374-395 (dh, db = -constant; GreaterThan rows arrive negated, :378-425): rows 1-6 and 11 are
+# `>=` constraints -> dh_i = +1; rows 7-10 are `<=` -> dh_i = -1; the equalities -> db_j = -1.
+_G8 = [[-1, 0, 0, 0, 0, 0], [0, -1, 0, 0, 0, 0], [0, 0, -1, 0, 0, 0], [0, 0, 0, -1, 0, 0], [0, 0, 0, 0, -1, 0],
+       [0, 0, 0, 0, 0, -1], [1, 0, 0, 0, 0, 0], [0, 0, 1, 0, 0, 0], [0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 1, 0],
+       [-1, 0, 0, 0, 0, -1]]
+cases["lp_dispatch_sensitivity"] = dict(
+    cite="test/jump.jl:473-638",
+    Q=np.zeros((6, 6)).tolist(), q=[0, 0, 3, 5, 7, 1], G=_G8, h=[0, 0, 0, 0, 0, 0, 50, 15, 20, 25, -50],
+    A=[[1, 1, 0, 0, 0, 0], [0, 1, 1, 1, 1, 0]], b=[45, 100],
+    z=[0, 45, 15, 20, 20, 50], lam=[6, 0, 0, 0, 0, 0, 0, 4, 2, 0, 1], nu=[7, -7],
+    # per constraint i (reference order xRef, :588-602): packed direction entry and the sign s_i of
+    # `-dprimal_dcons[:, i] ~ s_i * dprimal_dconsKKT[:, i]` (:624-636)
+    directions=[dict(kind="dh", index=i, value=(+1 if i in (0, 1, 2, 3, 4, 5, 10) else -1),
+                     kkt_sign=(-1 if i in (0, 1, 2, 3, 4, 5, 10) else +1)) for i in range(11)] +
+               [dict(kind="db", index=j, value=-1, kkt_sign=+1) for j in range(2)],
+    tol=2e-4,
+)
+
 # ---------------------------------------------------------------- conic (A = -coefficients, b = constants)
 cases["conic_socp"] = dict(
     cite="test/conic_program.jl:29-116 (eq_vec = true)",

@@ -386,9 +386,11 @@ def _banded_random(N, bw, seed):
 
 
 @pytest.mark.parametrize("N,bw,nrhs", [(1, 0, 1), (50, 3, 2), (400, 17, 9), (333, 30, 3), (1000, 31, 5), (3000, 40, 33)])
-def test_sparse_band_factorization(ctx, N, bw, nrhs):
-    """Sparse direct path (banded LU after RCM): LHS and LHS', many right-hand sides, against a dense/sparse CPU solve."""
+def test_sparse_band_factorization(ctx, N, bw, nrhs, monkeypatch):
+    """Banded fallback of the sparse direct path (LU after RCM): LHS and LHS', many right-hand sides, against a
+    dense/sparse CPU solve."""
     import scipy.sparse.linalg as spla
+    monkeypatch.setenv("DIFFOPT_B200_SPARSE", "band")
     lsq = diffopt_b200.submodule("lsqr")
     M = _banded_random(N, bw, seed=N)
     R = np.random.default_rng(1).standard_normal((N, nrhs))
@@ -423,6 +425,7 @@ def test_sparse_band_kernel_variants_agree(ctx, monkeypatch):
     must give the same factorisation and solutions (same pivots: identical up to the reciprocal-vs-division rounding)."""
     import scipy.sparse.linalg as spla
     lsq = diffopt_b200.submodule("lsqr")
+    monkeypatch.setenv("DIFFOPT_B200_SPARSE", "band")
     d = bench_data.mpc_config3(T=150)
     K = d["K"]
     R = np.random.default_rng(4).standard_normal((K.shape[0], 7))
@@ -442,9 +445,10 @@ def test_sparse_band_kernel_variants_agree(ctx, monkeypatch):
         assert np.linalg.norm(sols["new"] - sols[other]) <= 1e-12 * np.linalg.norm(sols["new"])
 
 
-def test_sparse_setup_rejects_and_reports(ctx):
+def test_sparse_setup_rejects_and_reports(ctx, monkeypatch):
     import scipy.sparse as sp
     lsq = diffopt_b200.submodule("lsqr")
+    monkeypatch.setenv("DIFFOPT_B200_SPARSE", "band")
     # exactly singular (two identical rows) -> SingularException like the reference's `\\`
     S = sp.csc_matrix(np.array([[1.0, 2.0, 0.0], [1.0, 2.0, 0.0], [0.0, 1.0, 1.0]]))
     with pytest.raises(diffopt_b200.SingularException):
