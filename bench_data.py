@@ -200,7 +200,7 @@ def mpc_config3(T=10_000, nx=6, nu=4, active_frac=0.1, seed=3):
     return dict(K=K, Q=Q, G=G, A=A, z=z, lam=lam, nu=nu_, h=h, n=n, m=m, p=p)
 
 
-def maxcut_config5(d=200, r=20, seed=5):
+def maxcut_config5(d=200, r=20, seed=5):  # r(r+1)/2 <= d makes the pair nondegenerate (unique dual): r <= 19 at d = 200
     """Config 5: max-cut SDP relaxation with a d x d PSD cone, solved by construction.  V ~ N(0,1)^{d x r} with unit
     rows, X = V V' (unit diagonal, rank r); W = orthonormal basis of range(V)^perp, S = W diag(U(.5,1.5)) W';
     nu ~ N(0,1)^d; C = S + Diag(nu): a strictly complementary primal-dual pair.  Variables = triangle of X

@@ -219,6 +219,7 @@ struct QpSolveArgs {
     long long* prof;  // optional per-phase clock counters of CTA 0 (DIFFOPT_B200_PROFILE=1)
     unsigned long long* sticky;  // optional: first failing (call, instance) of a stream-ordered sequence of calls
     unsigned call_seq;
+    int shared;  // bit 0: Q, G, A are ONE instance shared by the whole batch; bit 1: dQ, dG, dA likewise
 };
 
 // what a kernel does when instance `inst` turned out singular in a stream-ordered call

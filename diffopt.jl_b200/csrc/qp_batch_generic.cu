@@ -69,9 +69,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
     const int lane = tid & 31, warp = tid >> 5;
 
     for (int64_t inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
-        const double* Q = a.Q + (size_t)inst * n * n;
-        const double* G = a.G ? a.G + (size_t)inst * m * n : nullptr;
-        const double* A = a.A ? a.A + (size_t)inst * p * n : nullptr;
+        const size_t bm = (a.shared & 1) ? 0 : (size_t)inst;   // shared Q, G, A: one instance serves the batch
+        const double* Q = a.Q + bm * n * n;
+        const double* G = a.G ? a.G + bm * m * n : nullptr;
+        const double* A = a.A ? a.A + bm * p * n : nullptr;
         const bool do_fwd = a.fwd != nullptr, do_rev = a.rev != nullptr;
 
         // ---- load vectors, clear K
@@ -106,9 +107,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
         // forward RHS (QuadraticProgram.jl:429-433) accumulated into rf via global reads
         if (do_fwd) {
             const size_t b = (size_t)inst;
-            accum_matvecs(a.dQ ? a.dQ + b * n * n : nullptr, n, n, zs, nullptr, rf, nullptr, nullptr);
-            accum_matvecs(a.dG ? a.dG + b * m * n : nullptr, m, n, zs, lams, rf + n, lams, rf);
-            accum_matvecs(a.dA ? a.dA + b * p * n : nullptr, p, n, zs, nus, rf + n + m, nullptr, rf);
+            const size_t bd = (a.shared & 2) ? 0 : b;
+            accum_matvecs(a.dQ ? a.dQ + bd * n * n : nullptr, n, n, zs, nullptr, rf, nullptr, nullptr);
+            accum_matvecs(a.dG ? a.dG + bd * m * n : nullptr, m, n, zs, lams, rf + n, lams, rf);
+            accum_matvecs(a.dA ? a.dA + bd * p * n : nullptr, p, n, zs, nus, rf + n + m, nullptr, rf);
         }
         __syncthreads();
         // diag(Gz - h); finish rf; place the two right-hand sides

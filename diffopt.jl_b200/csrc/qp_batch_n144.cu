@@ -289,9 +289,10 @@ __global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a, 
     const int64_t nwork = list ? (int64_t)*count : a.B;
     for (int64_t work = blockIdx.x; work < nwork; work += gridDim.x) {
         const int64_t inst = list ? (int64_t)list[work] : work;
-        const double* Q = a.Q + (size_t)inst * NV * NV;
-        const double* G = a.G + (size_t)inst * MI * NV;
-        const double* A = a.A + (size_t)inst * PE * NV;
+        const size_t bm = (a.shared & 1) ? 0 : (size_t)inst, bd = (a.shared & 2) ? 0 : (size_t)inst;
+        const double* Q = a.Q + bm * NV * NV;
+        const double* G = a.G + bm * MI * NV;
+        const double* A = a.A + bm * PE * NV;
         // ---- vectors; active set (column-singleton detection)
         if (tid < NV) S.zs[tid] = a.z[(size_t)inst * NV + tid];
         else if (tid < NV + MI) S.lams[tid - NV] = a.lam[(size_t)inst * MI + tid - NV];
@@ -315,11 +316,12 @@ __global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a, 
         {   // L2 prefetch of the next instance of this CTA (inputs are streamed once from HBM)
             const int64_t nxt = list ? a.B : inst + gridDim.x;
             if (nxt < a.B) {
-                const char* bases[6] = {(const char*)(a.Q + (size_t)nxt * NV * NV), (const char*)(a.G + (size_t)nxt * MI * NV),
-                                        (const char*)(a.A + (size_t)nxt * PE * NV),
-                                        do_fwd && a.dQ ? (const char*)(a.dQ + (size_t)nxt * NV * NV) : nullptr,
-                                        do_fwd && a.dG ? (const char*)(a.dG + (size_t)nxt * MI * NV) : nullptr,
-                                        do_fwd && a.dA ? (const char*)(a.dA + (size_t)nxt * PE * NV) : nullptr};
+                const size_t nm = (a.shared & 1) ? 0 : (size_t)nxt, nd = (a.shared & 2) ? 0 : (size_t)nxt;
+                const char* bases[6] = {(const char*)(a.Q + nm * NV * NV), (const char*)(a.G + nm * MI * NV),
+                                        (const char*)(a.A + nm * PE * NV),
+                                        do_fwd && a.dQ ? (const char*)(a.dQ + nd * NV * NV) : nullptr,
+                                        do_fwd && a.dG ? (const char*)(a.dG + nd * MI * NV) : nullptr,
+                                        do_fwd && a.dA ? (const char*)(a.dA + nd * PE * NV) : nullptr};
                 const int lines[6] = {256, 256, 64, 256, 256, 64};  // 128-byte lines
 #pragma unroll
                 for (int q = 0; q < 6; ++q)
@@ -391,12 +393,12 @@ __global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a, 
 #pragma unroll
             for (int i = 0; i < 16; ++i) cv[i] = 0.0;
             if (a.dQ) {
-                const double* Xp = a.dQ + b * NV * NV;
+                const double* Xp = a.dQ + bd * NV * NV;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) rq = fma(__ldg(Xp + (cg + 4 * i) * NV + r), S.zs[cg + 4 * i], rq);
             }
             if (a.dG) {
-                const double* Xp = a.dG + b * MI * NV;
+                const double* Xp = a.dG + bd * MI * NV;
                 const double lr = S.lams[r];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, 2) qp_kkt_n144_kernel(QpSolveArgs a, 
             // dA: 16 x 64, thread element idx = tid + 256 q: row ii = tid & 15, column (tid >> 4) + 16 q
             double ra = 0.0, ca[4] = {0.0, 0.0, 0.0, 0.0};
             if (a.dA) {
-                const double* Xp = a.dA + b * PE * NV;
+                const double* Xp = a.dA + bd * PE * NV;
                 const int ii = tid & 15, c = tid >> 4;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {

@@ -271,9 +271,10 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
 #ifdef QP_PROFILE
         tprev2 = clock64();
 #endif
-        const double* Q = a.Q + b * NV * NV;
-        const double* G = a.G + b * MI * NV;
-        const double* A = a.A + b * PE * NV;
+        const size_t bm = (a.shared & 1) ? 0 : b, bd = (a.shared & 2) ? 0 : b;  // shared matrices: one instance serves the batch
+        const double* Q = a.Q + bm * NV * NV;
+        const double* G = a.G + bm * MI * NV;
+        const double* A = a.A + bm * PE * NV;
         // ---- vectors, active set
         if (tid < NV) {
             S.zs[tid] = a.z[b * NV + tid];
@@ -309,8 +310,8 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         }
         load_row8(G, MI, 8 * warp + 2 * t, g, bufA);
         if (do_fwd) {  // this instance's direction data is consumed a few microseconds from now: pull it into L2
-            const char* bases[3] = {a.dQ ? (const char*)(a.dQ + b * NV * NV) : nullptr, a.dG ? (const char*)(a.dG + b * MI * NV) : nullptr,
-                                    a.dA ? (const char*)(a.dA + b * PE * NV) : nullptr};
+            const char* bases[3] = {a.dQ ? (const char*)(a.dQ + bd * NV * NV) : nullptr, a.dG ? (const char*)(a.dG + bd * MI * NV) : nullptr,
+                                    a.dA ? (const char*)(a.dA + bd * PE * NV) : nullptr};
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 if (!bases[q]) continue;
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
                 for (int J = 0; J < 8; ++J) tp[J * 64] = gv[J].y;
             }
             // next group in flight: dQ tile rows (forward mode)
-            if (do_fwd) load_row8(a.dQ ? a.dQ + b * NV * NV : nullptr, NV, r0, g, gv);
+            if (do_fwd) load_row8(a.dQ ? a.dQ + bd * NV * NV : nullptr, NV, r0, g, gv);
             d0 = sum_over_g(d0);
             d1 = sum_over_g(d1);
             if (g == 0) {
@@ -438,12 +439,12 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         if (do_fwd) {
             if (a.dA) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) av[q] = ldg2(a.dA + b * PE * NV + (8 * (2 * warp + (q >> 1)) + g) * PE + 8 * (q & 1) + 2 * t);
+                for (int q = 0; q < 4; ++q) av[q] = ldg2(a.dA + bd * PE * NV + (8 * (2 * warp + (q >> 1)) + g) * PE + 8 * (q & 1) + 2 * t);
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) av[q] = make_double2(0.0, 0.0);
             }
-            const double* dGp = a.dG ? a.dG + b * MI * NV : nullptr;
+            const double* dGp = a.dG ? a.dG + bd * MI * NV : nullptr;
             // dQ z
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -809,8 +810,9 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_kernel(QpSolveArgs a, i
         {   // pull the next instance's Q (lower-triangle lines) and G towards L2 while this one is written out
             const int64_t nxt = inst + gridDim.x;
             if (nxt < a.B) {
-                const char* qn = (const char*)(a.Q + (size_t)nxt * NV * NV);
-                const char* gn = (const char*)(a.G + (size_t)nxt * MI * NV);
+                const size_t nm = (a.shared & 1) ? 0 : (size_t)nxt;
+                const char* qn = (const char*)(a.Q + nm * NV * NV);
+                const char* gn = (const char*)(a.G + nm * MI * NV);
                 for (int l = tid; l < 256; l += THREADS) {
                     if (16 * (l & 3) + 15 >= ((l >> 2) & ~7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(qn + (size_t)l * 128));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)l * 128));

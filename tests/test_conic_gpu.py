@@ -243,6 +243,148 @@ def test_conic_config4_full_size(ctx):
     assert rel(model.vp(), cache.vp) <= 1e-13
 
 
+def test_conic_config4_conditioned_converged_parity(ctx):
+    """BASELINE config 4 at full size (n=5000, m=7500) on the WELL-CONDITIONED generator (75 % of the nonnegative rows
+    active, solution scaled; cond(M) ~ 1e4 instead of ~1e7, bench_data.conic_config4): LSQR runs to its own stopping
+    rule on the GPU and in the oracle at MATCHED tolerances and the converged answers are compared (north_star: <= 1e-6
+    at a matched residual tolerance).  (a) tight tolerances 1e-13: both stop with istop = 1 after ~2500 iterations,
+    measured agreement 1e-12; (b) the reference's default tolerances (sqrt(eps)): ~1130 iterations, agreement ~6e-7."""
+    cm = diffopt_b200.submodule("conic")
+    d = bench_data.conic_config4_conditioned()
+    model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+    model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
+    cache = _oracle_cache(d)
+    dz = np.concatenate([d["seed"], np.zeros(7500), [-(d["x"] @ d["seed"])]])
+    for tol, bound in ((dict(atol=1e-13, btol=1e-13, conlim=0.0, maxiter=12501), 1e-9),
+                       (dict(atol=olsqr.SQRT_EPS, btol=olsqr.SQRT_EPS, conlim=1 / olsqr.SQRT_EPS, maxiter=12501), 1e-6)):
+        model.tolerances = tol
+        model.reverse_differentiate(d["seed"])
+        g, info = olsqr.lsqr(cache.M, dz, return_info=True, **tol)
+        st = model.last_stats
+        assert st["istop"] == info.istop == 1                       # ||r|| small: both converged by the same test
+        assert abs(st["itn"] - info.itn) <= max(5, info.itn // 100)
+        assert abs(st["rnorm"] - info.rnorm) <= 0.02 * info.rnorm
+        assert rel(model.back_grad_cache["g"], g) <= bound, (tol["atol"], st, info)
+        # the getters the caller reads (ConicProgram.jl:396-428)
+        _, db, dc = oconic.reverse_param_grads(cache, g, dense_dA=False)
+        assert rel(model.reverse_objective_function(), dc) <= bound and rel(model.get_db(), db) <= bound
+        r = model.M_apply(model.back_grad_cache["g"]) - dz
+        assert abs(np.linalg.norm(r) - st["rnorm"]) <= 1e-6 * np.linalg.norm(dz)
+
+
+def test_psd_maxcut_200_full_reverse(ctx):
+    """BASELINE config 5: a full `reverse_differentiate!` (ConicProgram.jl:336-394) on the 200 x 200 max-cut SDP against
+    the oracle's matrix-free LSQR (the reference's dense 20100^2 Dpi block is never formed).
+    r = 20 is dual degenerate (r(r+1)/2 = 210 > 200 constraints): M is singular beyond the embedding's own
+    null direction, LSQR does not converge within N iterations in either implementation and rounding differences
+    between the two grow with the iteration count -- compared iterate by iterate while they are meaningful and by
+    stopping state at the iteration limit.  r = 8 is nondegenerate: both run to istop = 1 at the reference's default
+    tolerances and agree to 1e-4 (the answers of two LSQR runs differ by tolerance x cond(M) ~ 1.5e-8 x 7e5)."""
+    cm = diffopt_b200.submodule("conic")
+    for r, full_iters in ((20, 400), (8, None)):
+        d = bench_data.maxcut_config5(r=r)
+        model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+        model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
+        args = [d[k] for k in ("A", "b", "c", "x", "s", "y", "cone_types", "cone_dims")]
+        m, n = d["A"].shape
+        dz = np.concatenate([d["seed"], np.zeros(m), [-(d["x"] @ d["seed"])]])
+        for iters, bound in ((1, 1e-10), (2, 1e-10), (5, 1e-9)):
+            tol = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=iters)
+            model.tolerances = tol
+            model.reverse_differentiate(d["seed"])
+            g = oconic.reverse_matrix_free(*args, d["seed"], **tol)
+            assert rel(model.back_grad_cache["g"], g) <= bound, (r, iters)
+        tol = dict(atol=olsqr.SQRT_EPS, btol=olsqr.SQRT_EPS, conlim=1 / olsqr.SQRT_EPS, maxiter=full_iters or 3000)
+        model.tolerances = tol
+        model.reverse_differentiate(d["seed"])
+        st = model.last_stats
+        g, info = olsqr.lsqr(oconic.matrix_free_ops(*args), dz, return_info=True, **tol)
+        assert st["istop"] == info.istop == (7 if full_iters else 1)
+        assert abs(st["itn"] - info.itn) <= max(5, info.itn // 50)
+        assert abs(st["rnorm"] - info.rnorm) <= 0.02 * info.rnorm
+        res = np.linalg.norm(model.M_apply(model.back_grad_cache["g"]) - dz)
+        assert abs(res - st["rnorm"]) <= 1e-6 * np.linalg.norm(dz)        # the returned g really has that residual
+        if not full_iters:
+            assert rel(model.back_grad_cache["g"], g) <= 1e-4, (r, st, info)
+
+
+def test_kat8_dispatch_lp_forward_directions(ctx, kat):
+    """KAT 8 (test/jump.jl:473-638) through the reference-shaped model on the GPU: 13 successive forward directions on
+    the degenerate-looking dispatch LP (Q = 0 -> LSQR on the KKT matrix, QuadraticProgram.jl:436-438) against column-wise
+    LSQR on the hand-built KKT system with the reference's sign table and tolerance."""
+    qpm = diffopt_b200.submodule("qp")
+    c = kat["lp_dispatch_sensitivity"]
+    n, m, p = len(c["z"]), len(c["lam"]), len(c["nu"])
+    a = lambda k, shape: np.array(c[k], float).reshape(shape)
+    Q, G, A, z, lam = a("Q", (n, n)), a("G", (m, n)), a("A", (p, n)), a("z", n), a("lam", m)
+    model = qpm.QPModel(ctx, Q, a("q", n), G, a("h", m), A, a("b", p))
+    model.set_variable_primal(z); model.set_constraint_dual_le(-lam); model.set_constraint_dual_eq(-a("nu", p))
+    K = np.block([[Q, G.T, A.T], [np.diag(lam) @ G, np.diag(G @ z - a("h", m)), np.zeros((m, p))],
+                  [A, np.zeros((p, m)), np.zeros((p, p))]])
+    R = np.block([[np.zeros((n, m)), np.zeros((n, p))], [np.diag(lam), np.zeros((m, p))], [np.zeros((p, m)), np.eye(p)]])
+    for i, dct in enumerate(c["directions"]):
+        dh, db = np.zeros(m), np.zeros(p)
+        (dh if dct["kind"] == "dh" else db)[dct["index"]] = dct["value"]
+        model.forward_differentiate(dh=dh, db=db)
+        col = olsqr.lsqr(K, R[:, i])[:n]
+        got = -model.forward_variable_primal()
+        want = dct["kkt_sign"] * col
+        assert np.linalg.norm(got - want) <= max(c["tol"], c["tol"] * max(np.linalg.norm(got), np.linalg.norm(want))), i
+
+
+def test_kat14_qp_cases_through_the_conic_backend(ctx, kat):
+    """KAT 14 (test/utils.jl:369-377: every qp_test also runs with ConicProgram.Model): each QP / LP known-answer case
+    restated as a conic program (tests/qp_as_conic.py: Zeros + Nonnegatives + the SOC epigraph of the quadratic
+    objective) runs forward and reverse through the GPU conic backend.  Checked (1) against the oracle's conic backend
+    on every direction, coefficient directions included (<= 1e-6 at matched tight tolerances) and (2) against the QP
+    backend's own answers where the reference's two backends agree (constants, linear objective; see the CPU twin
+    of this test in test_oracle_kat.py for the sign of coefficient directions)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from qp_as_conic import conic_forward_direction, qp_as_conic
+    cm = diffopt_b200.submodule("conic")
+    tight = dict(atol=1e-14, btol=1e-14, conlim=0.0, maxiter=5000)
+    agree = {"qp_moi_examples_2": ["dq", "db"], "qp_moi_examples_1": ["dq", "dh"], "qp_ineq_eq": ["dh", "db"],
+             "qp_trivial_1": ["dq", "dh"], "lp_simplex_example": ["dh"], "lp_fixed_variable": ["dh", "db"],
+             "lp_nonactive": ["dh"], "lp_dispatch_sensitivity": ["dq", "dh", "db"]}
+    rng = np.random.default_rng(14)
+    for name, keys in agree.items():
+        c = kat[name]
+        n, m, p = len(c["z"]), len(c["lam"]), len(c["nu"])
+        a = lambda k, shape: np.array(c[k], float).reshape(shape)
+        Q, q, G, h, A, b, z, lam, nu = (a("Q", (n, n)), a("q", n), a("G", (m, n)), a("h", m), a("A", (p, n)), a("b", p),
+                                        a("z", n), a("lam", m), a("nu", p))
+        cp = qp_as_conic(Q, q, G, h, A, b, z, lam, nu)
+        model = cm.ConicModel(ctx, cp["A"], cp["b"], cp["c"], cp["cone_types"], cp["cone_dims"])
+        model.set_variable_primal(cp["x"]); model.set_constraint_primal(cp["s"]); model.set_constraint_dual(cp["y"])
+        model.tolerances = tight
+        cache = oconic.gradient_cache(cp["A"], cp["b"], cp["c"], cp["x"], cp["s"], cp["y"], cp["cone_types"], cp["cone_dims"])
+        kw_qp = tight if oqp.is_iterative(Q) else {}
+        sizes = dict(dq=n, dh=m, db=p, dG=(m, n), dA=(p, n))
+        for key in ("dq", "dh", "db", "dG", "dA"):
+            if (key in ("dh", "dG") and m == 0) or (key in ("db", "dA") and p == 0):
+                continue
+            direction = {key: rng.standard_normal(sizes[key])}
+            dAc, dbc, dcc = conic_forward_direction(cp, **direction)
+            model.forward_differentiate(dAc, dbc, dcc)
+            dx, _ = oconic.forward(cache, dAc, dbc, dcc, **tight)
+            assert np.linalg.norm(model.forward_variable_primal() - dx) <= 1e-6 * np.linalg.norm(dx) + 1e-10, (name, key)
+            if key in keys:
+                if key == "dq" and cp["quad"]:
+                    model.forward_differentiate(-dAc, dbc, dcc)   # un-negated dA of the reference flips q's SOC rows
+                full = dict(dQ=np.zeros((n, n)), dq=np.zeros(n), dG=np.zeros((m, n)), dh=np.zeros(m),
+                            dA=np.zeros((p, n)), db=np.zeros(p))
+                full.update(direction)
+                ref = oqp.forward(Q, G, h, A, z, lam, nu, **full, **kw_qp)[0]
+                got = model.forward_variable_primal()[:n]
+                assert np.linalg.norm(got - ref) <= 1e-6 * max(1.0, np.linalg.norm(ref)), (name, key, "vs QP backend")
+        seed = np.concatenate([np.array(c["seed"], float), np.zeros(cp["x"].size - n)])
+        model.reverse_differentiate(seed)
+        g = oconic.reverse(cache, seed, **tight)
+        assert np.linalg.norm(model.back_grad_cache["g"] - g) <= 1e-6 * np.linalg.norm(g) + 1e-10, name
+
+
 def test_psd_maxcut_200(ctx):
     """BASELINE config 5: 200 x 200 PSD cone (max-cut SDP shape).  pi and the Dpi operator vs the oracle
     (eigh + 4 GEMMs); the reference's literal dense 20100^2 Jacobian is never formed."""

@@ -197,16 +197,14 @@ def test_active_set_sizes(ctx, na):
 def test_ldl_fast_path_serves_every_active_set_size(ctx, na, monkeypatch):
     """The pivot-free LDL' kernel itself (not its pivoted-LU safety net) must serve regular instances of every
     active-set size, including reduced orders 80 + na >= 128 that are not multiples of 8 (the identity padding rows
-    are then indexed beyond the CTA size).  LICQ caps the rows with slack 0 at 48 (p = 16, n = 64); beyond that the
-    extra rows get lam > 0 with slack < 0, which keeps the reduced system quasi-definite at order 80 + na."""
+    are then indexed beyond the CTA size).  40 rows are active with slack 0 (with the 16 equalities: 56 < n = 64
+    constraints, a well-conditioned KKT matrix); the other na - 40 rows of the reduced system carry lam > 0 with
+    slack < 0, which keeps it quasi-definite at order 80 + na."""
     monkeypatch.setenv("DIFFOPT_B200_QP_KERNEL", "ldl")
-    d = bench_data.qp_batch(12, n_active=min(na, 48), seed0=4100 + na)
-    if na > 48:
-        # more "active" rows than LICQ allows cannot have slack 0; give the extra rows lam > 0 with slack < 0
-        # (D/lam < 0 keeps the reduced system quasi-definite and nonsingular) so that the reduced order is 80 + na
-        for b in range(12):
-            idle = np.flatnonzero(d["lam"][b] == 0)[:na - 48]
-            d["lam"][b, idle] = 0.7
+    d = bench_data.qp_batch(12, n_active=min(na, 40), seed0=4100 + na)
+    for b in range(12):
+        idle = np.flatnonzero(d["lam"][b] == 0)[:max(0, na - 40)]
+        d["lam"][b, idle] = 0.7
     _solve(ctx, d)                      # first call of this size: configures the launch for it
     fwd, rev, info = _solve(ctx, d)
     assert not info.any()
