@@ -6,8 +6,9 @@
 Workload (config 2 of BASELINE.json): a batch of 4096 dense random QPs, n=64, m_eq=16,
 m_ineq=64 (KKT order N=144).  One *solve* = KKT assembly + one LU factorisation + one forward
 (LHS') and one reverse (LHS) sensitivity solve for one instance; one *step* = one pass over the
-batch.  With N GPUs every rank owns its own 4096-instance batch (weak scaling, no data-path
-collective; the whole-job value is the sum).  Prints ONE JSON line on rank 0.
+batch.  With N GPUs the SAME 4096 instances are split into contiguous shards, one per rank (strong
+scaling, no data-path collective; `weak` carries the 4096-per-rank companion number, `shared_variant`
+the OptNet-shared form with its NCCL all-reduce).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -118,97 +119,204 @@ def fp64_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm on host cores (oracle port; Julia/UMFPACK are not in the image)
 
+def _kkt_pattern():
+    """CSC index arrays of LHS = [Q G'L A'; G D 0; A 0 0] for dense blocks (identical for every instance): the
+    reference holds LHS as a SparseMatrixCSC built once per problem by sparse hcat/vcat (QuadraticProgram.jl:256-282);
+    here only the value vector is assembled per instance, never a dense N x N detour."""
+    n, m, p = N_VAR, M_INEQ, P_EQ
+    N = n + m + p
+    mask = np.zeros((N, N), dtype=bool)
+    mask[:n, :n] = True; mask[:n, n:n + m] = True; mask[:n, n + m:] = True
+    mask[n:n + m, :n] = True; mask[n + m:, :n] = True
+    mask[np.arange(n, n + m), np.arange(n, n + m)] = True
+    import scipy.sparse as sp
+    P = sp.csc_matrix(mask.astype(np.float64))
+    P.sort_indices()
+    PT = sp.csc_matrix(mask.T.astype(np.float64))
+    PT.sort_indices()
+    return P.indices.copy(), P.indptr.copy(), PT.indices.copy(), PT.indptr.copy(), mask
+
+
+_PATTERN = None
+
+
 def _cpu_chunk(args):
-    """Reference-faithful per-instance work: sparse KKT (create_LHS_matrix) and one sparse LU
-    factorisation PER differentiate call (QuadraticProgram.jl:335 and :438 both call `\\`)."""
+    r"""Per-instance work of one worker.  variant:
+    'faithful'    -- what the reference does: LHS assembled once as CSC (_gradient_cache), then one sparse LU factorisation
+                     PER differentiate call: `LHS' \ RHS` in forward_differentiate! (:438) and `LHS \ RHS` in
+                     reverse_differentiate! (:335);
+    'factor_once' -- one sparse LU of LHS serving both solves (what a caching reimplementation would do);
+    'dense'       -- LAPACK getrf once + two getrs on the dense 144 x 144 matrix (strongest simple CPU variant)."""
+    import scipy.linalg as sla
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     from oracle import qp as oqp
-    lo, hi = args
+    global _PATTERN
+    lo, hi, variant = args
     d = _CPU_DATA
-    n, m = N_VAR, M_INEQ
+    n = N_VAR
+    if _PATTERN is None:
+        _PATTERN = _kkt_pattern()
+    ind, ptr, indT, ptrT, mask = _PATTERN
     for b in range(lo, hi):
-        K = sp.csc_matrix(oqp.create_lhs(d["z"][b], d["lam"][b], d["Q"][b], d["G"][b], d["h"][b], d["A"][b]))
+        Kd = oqp.create_lhs(d["z"][b], d["lam"][b], d["Q"][b], d["G"][b], d["h"][b], d["A"][b])
         rf = oqp.forward_rhs(d["z"][b], d["lam"][b], d["nu"][b], d["dQ"][b], d["dq"][b], d["dG"][b], d["dh"][b],
                              d["dA"][b], d["db"][b])
         rb = np.zeros(KKT_N)
         rb[:n] = d["seed"][b]
-        spla.splu(K.T.tocsc()).solve(rf)      # forward_differentiate!: LHS' \ RHS
-        spla.splu(K).solve(rb)                # reverse_differentiate!: LHS \ RHS
+        if variant == "dense":
+            lu = sla.lu_factor(Kd, check_finite=False)
+            sla.lu_solve(lu, rf, trans=1, check_finite=False)
+            sla.lu_solve(lu, rb, check_finite=False)
+            continue
+        K = sp.csc_matrix((Kd.T[mask.T], ind, ptr), shape=Kd.shape)       # values in CSC order of the fixed pattern
+        if variant == "factor_once":
+            lu = spla.splu(K)
+            lu.solve(rf, trans="T")
+            lu.solve(rb)
+        else:
+            KT = sp.csc_matrix((Kd[mask], indT, ptrT), shape=Kd.shape)
+            spla.splu(KT).solve(rf)      # forward_differentiate!: LHS' \ RHS
+            spla.splu(K).solve(rb)       # reverse_differentiate!: LHS \ RHS
     return hi - lo
 
 
 _CPU_DATA = None
 
 
-def cpu_reference_rate(d, sample, procs):
-    """solves/s of the CPU port on `sample` instances using `procs` worker processes (fork: the
-    workers inherit the inputs, nothing is pickled inside the timed region)."""
+def cpu_reference_rate(d, sample, procs, variant="faithful"):
+    """solves/s of the CPU port on `sample` instances using `procs` single-threaded worker processes (fork: the workers
+    inherit the inputs, nothing is pickled inside the timed region; BLAS/OpenMP pinned to one thread per worker so the
+    pool is not oversubscribed)."""
     import multiprocessing as mp
     global _CPU_DATA
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     _CPU_DATA = {k: v[:sample] for k, v in d.items()}
     bounds = np.linspace(0, sample, procs + 1).astype(int)
-    chunks = [(int(bounds[i]), int(bounds[i + 1])) for i in range(procs) if bounds[i + 1] > bounds[i]]
+    chunks = [(int(bounds[i]), int(bounds[i + 1]), variant) for i in range(procs) if bounds[i + 1] > bounds[i]]
     if procs == 1:
-        _cpu_chunk((0, min(4, sample)))
+        _cpu_chunk((0, min(4, sample), variant))
         t0 = time.perf_counter()
         _cpu_chunk(chunks[0])
         return sample / (time.perf_counter() - t0)
     with mp.get_context("fork").Pool(procs) as pool:
-        pool.map(_cpu_chunk, [(0, min(4, sample))] * procs)  # warm the workers (imports)
+        pool.map(_cpu_chunk, [(0, min(4, sample), variant)] * procs)  # warm the workers (imports)
         t0 = time.perf_counter()
         pool.map(_cpu_chunk, chunks)
         dt = time.perf_counter() - t0
     return sample / dt
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+CPU_SAMPLE_TXT = ("all {sample} instances of the step; per instance the reference's work: LHS assembled once as CSC, then one "
+                  "sparse LU factorisation + solve for forward_differentiate! (LHS') and another for reverse_differentiate! "
+                  "(LHS), QuadraticProgram.jl:335,438; SuperLU (scipy) stands in for UMFPACK; {procs} single-threaded worker "
+                  "processes (OMP/OPENBLAS/MKL threads = 1)")
+
+
+def cpu_baseline_block(d, sample, procs):
+    rate = cpu_reference_rate(d, sample, procs, "faithful")
+    once = cpu_reference_rate(d, sample, procs, "factor_once")
+    dense = cpu_reference_rate(d, sample, procs, "dense")
+    return {"value": rate, "unit": "solves/s", "cores": procs, "kind": "port",
+            "sample": CPU_SAMPLE_TXT.format(sample=sample, procs=procs), "same_config": sample == 4096,
+            "variants": {"reference_faithful_two_sparse_lu_per_instance": rate,
+                         "factor_once_sparse_lu": once, "dense_lapack_getrf_getrs": dense}}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     import bench_data
-    procs = os.cpu_count() or 1
-    sample = int(os.environ.get("DIFFOPT_BENCH_CPU_SAMPLE", 1024))
+    procs = host_cores()
+    sample = int(os.environ.get("DIFFOPT_BENCH_CPU_SAMPLE", 4096))
     d = bench_data.qp_batch_fast(sample, N_VAR, M_INEQ, P_EQ, seed=2026)
     for _ in range(args.warmup):
-        cpu_reference_rate(d, min(sample, 64 * procs), procs)
+        cpu_reference_rate(d, min(sample, 16 * procs), procs)
     dt = 0.0
     done = 0
-    for _ in range(args.steps):
+    steps = min(args.steps, 20)   # each step is the full 4096-instance batch (~0.2 s on 32 cores)
+    for _ in range(steps):
         dt += sample / cpu_reference_rate(d, sample, procs)   # times the worker map only, not pool start-up
         done += sample
     val = done / dt
-    sample_txt = (f"{sample} of 4096 instances per step; per instance: sparse KKT build + splu factorisation and "
-                  f"solve for the forward call (LHS') and again for the reverse call (LHS), like "
-                  f"QuadraticProgram.jl:335,438; SuperLU (scipy) stands in for UMFPACK; {procs} worker processes")
+    base = cpu_baseline_block(d, sample, procs)
+    base["value"] = val
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * (4096 / sample),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps * (4096 / sample),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "4096 x dense QP n=64 m_ineq=64 m_eq=16 (KKT N=144), forward + reverse "
-                                   "sensitivities; CPU arm runs a bounded sample", "batch_per_gpu": 4096},
-            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": procs, "kind": "port", "sample": sample_txt},
+                                   "sensitivities (BASELINE.json configs[1]); CPU arm: the reference's algorithm on the "
+                                   "host cores of rank 0", "global_batch": 4096},
+            "cpu_baseline": base,
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this process (and therefore the pinned host buffers it allocates next: first touch) to the CPUs of the NUMA
+    node the GPU hangs off.  Without it every rank of a multi-GPU run stages through node 0 (r1: e2e efficiency 0.43 at 8
+    GPUs).  Returns a description for the JSON line."""
+    try:
+        q = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                           capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = q[-12:] if len(q) >= 12 else q           # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": node, "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:  # pragma: no cover
+        return {"bound": False, "why": str(e)[:80]}
+
 
 def run_b200(args, rank, world, local_rank):
+    numa = bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as dist
 
     import diffopt_b200
     capi = diffopt_b200.submodule("_capi")
+    sharding = diffopt_b200.submodule("sharding")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = diffopt_b200.Context(local_rank)
     lib = ctx.lib
-    B = args.batch
+    BT = args.batch                                   # the whole job: 4096 instances
+    lo, hi = sharding.shard_range(BT, rank, world)    # strong scaling: this rank's contiguous shard
+    B = hi - lo
     N = KKT_N
 
-    hb, logical = host_buffers(B, seed=2026 + rank, pinned_alloc=capi.pinned_empty)
+    # every rank generates the full batch (same seed) and keeps its shard: the job is the SAME 4096 problems at any N
+    hb_full, logical_full = host_buffers(BT, seed=2026)
+    logical = {k: v[lo:hi] for k, v in logical_full.items()}
+    hb = {}
+    for k in FIELDS:
+        buf = capi.pinned_empty(hb_full[k][lo:hi].shape)
+        np.copyto(buf, hb_full[k][lo:hi])
+        hb[k] = buf
     db = {k: torch.from_numpy(v).to(dev) for k, v in hb.items()}     # resident inputs (torch = device memory)
     fwd = torch.empty((B, N), dtype=torch.float64, device=dev)
     rev = torch.empty((B, N), dtype=torch.float64, device=dev)
@@ -222,31 +330,27 @@ def run_b200(args, rank, world, local_rank):
     def dptr(t):
         return capi.vp(t.data_ptr())
 
+    def check(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} rc={rc}: {lib.diffopt_b200_last_error(ctx.h).decode()}")
+
     dev_args = [dptr(db[k]) for k in FIELDS] + [dptr(fwd), dptr(rev), dptr(info)]
 
     def step_device():
         # stream-ordered form of the call (device-resident inputs): batches run back to back on the ctx stream, the
-        # status of the last one is collected by diffopt_b200_synchronize after the timed region
-        rc = lib.diffopt_b200_qp_batch_solve_async(ctx.h, B, N_VAR, M_INEQ, P_EQ, *dev_args)
-        if rc != 0:
-            raise RuntimeError(f"qp_batch_solve_async rc={rc}: {lib.diffopt_b200_last_error(ctx.h).decode()}")
+        # status of every queued call is collected by diffopt_b200_synchronize after the timed region
+        check(lib.diffopt_b200_qp_batch_solve_async(ctx.h, B, N_VAR, M_INEQ, P_EQ, *dev_args), "qp_batch_solve_async")
 
     def step_device_blocking():
-        rc = lib.diffopt_b200_qp_batch_solve(ctx.h, B, N_VAR, M_INEQ, P_EQ, *dev_args, capi.DEVICE)
-        if rc != 0:
-            raise RuntimeError(f"qp_batch_solve rc={rc}: {lib.diffopt_b200_last_error(ctx.h).decode()}")
+        check(lib.diffopt_b200_qp_batch_solve(ctx.h, B, N_VAR, M_INEQ, P_EQ, *dev_args, capi.DEVICE), "qp_batch_solve")
 
     def finish_device():
-        rc = lib.diffopt_b200_synchronize(ctx.h)
-        if rc != 0:
-            raise RuntimeError(f"qp_batch_solve_async status {rc}: {lib.diffopt_b200_last_error(ctx.h).decode()}")
+        check(lib.diffopt_b200_synchronize(ctx.h), "diffopt_b200_synchronize")
 
     def step_e2e():
-        rc = lib.diffopt_b200_qp_batch_solve(
+        check(lib.diffopt_b200_qp_batch_solve(
             ctx.h, B, N_VAR, M_INEQ, P_EQ, *[capi.ptr(hb[k]) for k in FIELDS], capi.ptr(fwd_h), capi.ptr(rev_h),
-            capi.ptr(info_h), capi.HOST)
-        if rc != 0:
-            raise RuntimeError(f"qp_batch_solve(host) rc={rc}: {lib.diffopt_b200_last_error(ctx.h).decode()}")
+            capi.ptr(info_h), capi.HOST), "qp_batch_solve(host)")
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
@@ -255,8 +359,8 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """CUDA events on the library's own stream, barrier + synchronize on both sides."""
+    def timed(fn, steps, finish=None):
+        """CUDA events on the library's own stream, barrier + synchronize on both sides, max over ranks."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kms = 0.0
         barrier()
@@ -266,6 +370,8 @@ def run_b200(args, rank, world, local_rank):
             kms += ctx.last_kernel_ms
         e1.record(stream)
         barrier()
+        if finish:
+            finish()
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -281,8 +387,7 @@ def run_b200(args, rank, world, local_rank):
         sampler.wait_first()
     l0 = ctx.launch_count
     t0 = time.perf_counter()
-    ms, _ = timed(step_device, args.steps)
-    finish_device()
+    ms, _ = timed(step_device, args.steps, finish_device)
     t1 = time.perf_counter()
     launches = ctx.launch_count - l0
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -292,18 +397,15 @@ def run_b200(args, rank, world, local_rank):
     ms_blocking, call_kernel_ms = timed(step_device_blocking, 5)
 
     # parity spot-check of what was just timed (oracle as checker only)
-    if rank == 0:
-        from oracle import qp as oqp
-        sl = slice(0, 8)
-        of, orv = oqp.batch_forward_reverse(*[logical[k][sl] for k in ["Q", "G", "A", "h", "z", "lam", "nu", "seed",
-                                                                       "dQ", "dq", "dG", "dh", "dA", "db"]])
-        gf, gr = fwd[sl].cpu().numpy(), rev[sl].cpu().numpy()
-        err = max((np.linalg.norm(gf - of, axis=1) / np.linalg.norm(of, axis=1)).max(),
-                  (np.linalg.norm(gr - orv, axis=1) / np.linalg.norm(orv, axis=1)).max())
-        if not err <= 1e-8:
-            raise RuntimeError(f"parity check failed inside bench: rel err {err:.3e}")
-    else:
-        err = None
+    from oracle import qp as oqp
+    sl = slice(0, min(8, B))
+    of, orv = oqp.batch_forward_reverse(*[logical[k][sl] for k in ["Q", "G", "A", "h", "z", "lam", "nu", "seed",
+                                                                   "dQ", "dq", "dG", "dh", "dA", "db"]])
+    gf, gr = fwd[sl].cpu().numpy(), rev[sl].cpu().numpy()
+    err = max((np.linalg.norm(gf - of, axis=1) / np.linalg.norm(of, axis=1)).max(),
+              (np.linalg.norm(gr - orv, axis=1) / np.linalg.norm(orv, axis=1)).max())
+    if not err <= 1e-8:
+        raise RuntimeError(f"parity check failed inside bench (rank {rank}): rel err {err:.3e}")
 
     # end-to-end through the C ABI with host (pinned) buffers: H2D + kernel + D2H every step
     for _ in range(2):
@@ -311,12 +413,35 @@ def run_b200(args, rank, world, local_rank):
     e2e_steps = max(2, min(args.steps, 10))
     ms_e2e, _ = timed(step_e2e, e2e_steps)
 
+    # weak-scaling companion number (second field): every rank a full 4096-instance batch of its own
+    weak = None
+    if world > 1:
+        dbw = {k: torch.from_numpy(np.ascontiguousarray(hb_full[k])).to(dev) for k in FIELDS}
+        fw = torch.empty((BT, N), dtype=torch.float64, device=dev)
+        rw = torch.empty((BT, N), dtype=torch.float64, device=dev)
+        iw = torch.zeros(BT, dtype=torch.int32, device=dev)
+        wargs = [dptr(dbw[k]) for k in FIELDS] + [dptr(fw), dptr(rw), dptr(iw)]
+
+        def step_weak():
+            check(lib.diffopt_b200_qp_batch_solve_async(ctx.h, BT, N_VAR, M_INEQ, P_EQ, *wargs), "qp_batch_solve_async")
+        for _ in range(3):
+            step_weak()
+        finish_device()
+        wsteps = min(args.steps, 50)
+        ms_w, _ = timed(step_weak, wsteps, finish_device)
+        weak = {"value": world * BT * wsteps / (ms_w * 1e-3), "unit": "solves/s", "ms_per_step": ms_w / wsteps,
+                "batch_per_gpu": BT, "scaling": "weak"}
+        del dbw, fw, rw, iw
+
+    shared = shared_variant(args, rank, world, ctx, lib, capi, sharding, dev, db, logical, B, BT, timed, check, dptr)
+    aux = active_set_sweep(args, ctx, lib, capi, dev, timed, check, dptr) if world == 1 and not args.no_aux else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    value = world * B * args.steps / (ms * 1e-3)
-    e2e_val = world * B * e2e_steps / (ms_e2e * 1e-3)
+    value = BT * args.steps / (ms * 1e-3)
+    e2e_val = BT * e2e_steps / (ms_e2e * 1e-3)
     peaks = fp64_peaks() if world == 1 else {}
     achieved = B * FLOP_PER_SOLVE / (kernel_ms * 1e-3) / 1e12
     peak = peaks.get("dgemm8192_tflops_sustained")
@@ -327,14 +452,15 @@ def run_b200(args, rank, world, local_rank):
                 "frac": (achieved / peak) if peak else None, "traffic": prof.get("dram_bytes_per_launch"),
                 "kernel": "qp_kkt_sqd_kernel (KKT assembly + blocked LDL' on DMMA + 2 solves; pivoted-LU fallback kernel "
                           "launched behind it, plus the active-set scan), avg device time per launch %.3f ms over the "
-                          "timed region; blocking call: %.3f ms per call (%.3f ms of it between the library's own "
-                          "events)" % (kernel_ms, ms_blocking / 5, call_kernel_ms),
+                          "timed region (%d instances per launch on this rank); blocking call: %.3f ms per call (%.3f ms "
+                          "of it between the library's own events)" % (kernel_ms, B, ms_blocking / 5, call_kernel_ms),
                 "algorithmic_flop_per_solve": FLOP_PER_SOLVE, "algorithmic_bytes_per_solve": BYTES_PER_SOLVE,
                 "executed_flop_per_solve_estimate": prof.get("executed_flop_per_solve"),
                 "note": "achieved = SURVEY.md 8(d) algorithmic flop (LU of the N=144 KKT + 2x2 triangular solves) / device "
                         "time; the kernel reaches it by eliminating column singletons and factorising the symmetric "
-                        "quasi-definite reduced system with LDL' (fewer executed flop, see DESIGN.md); traffic from "
-                        "profiles/ (ncu capture of the same kernel, per launch)",
+                        "quasi-definite reduced system with LDL' (fewer executed flop, see DESIGN.md), so the binding "
+                        "roofline of the reformulated kernel is HBM (hbm_secondary); traffic from profiles/ (ncu capture of "
+                        "the same kernel, per 4096-instance launch)",
                 "peak_source": "measured in this run: cuBLAS DGEMM 8192^3 sustained 4 s (tools/fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "fp64_peaks": peaks,
@@ -342,29 +468,148 @@ def run_b200(args, rank, world, local_rank):
                                   "frac": hbm_ach / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"}}
     line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "4096 x dense QP n=64 m_ineq=64 m_eq=16 (KKT N=144), forward + reverse "
                                    "sensitivities (BASELINE.json configs[1])",
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instances sharded x{world}",
-                       "l2_policy": "inputs (627 MB/step) larger than the 126 MB L2",
+                       "global_batch": BT, "batch_per_gpu": B,
+                       "parallelism": f"4096 instances split into contiguous shards over {world} GPU(s), no collective on "
+                                      f"the data path (SURVEY.md 8e)",
+                       "l2_policy": "per-rank inputs (%.0f MB/step) %s the 126 MB L2%s" % (
+                           B * BYTES_PER_SOLVE / 1e6, "larger than" if B * BYTES_PER_SOLVE > 126e6 else "SMALLER than",
+                           "" if B * BYTES_PER_SOLVE > 126e6 else
+                           " (strong scaling shrinks the shard); see `weak` for the HBM-streaming number"),
                        "call": "diffopt_b200_qp_batch_solve_async x K + diffopt_b200_synchronize (stream-ordered, "
-                               "device-resident inputs); e2e uses the blocking host-buffer call"},
-            "roofline": roofline, "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": in_bytes,
-                                          "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e / e2e_steps},
+                               "device-resident inputs); e2e uses the blocking host-buffer call",
+                       "host_numa": numa},
+            "roofline": roofline, "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": in_bytes * world,
+                                          "d2h_bytes_per_step": out_bytes * world, "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "parity_rel_err": err}
+    if weak:
+        line["weak"] = weak
+    if shared:
+        line["shared_variant"] = shared
+    if aux:
+        line["aux"] = aux
     if world == 1 and not args.no_cpu:
-        procs = os.cpu_count() or 1
-        sample = int(os.environ.get("DIFFOPT_BENCH_CPU_SAMPLE", 1024))
-        sub = {k: logical[k][:sample] for k in logical}
-        rate = cpu_reference_rate(sub, sample, procs)
-        line["cpu_baseline"] = {
-            "value": rate, "unit": "solves/s", "cores": procs, "kind": "port",
-            "sample": f"first {sample} of the 4096 instances; per instance sparse KKT build + splu factorise+solve "
-                      f"for forward (LHS') and again for reverse (LHS) as QuadraticProgram.jl:335,438 do; "
-                      f"SuperLU stands in for UMFPACK; {procs} worker processes"}
+        procs = host_cores()
+        sample = int(os.environ.get("DIFFOPT_BENCH_CPU_SAMPLE", 4096))
+        line["cpu_baseline"] = cpu_baseline_block({k: logical_full[k][:sample] for k in logical_full}, sample, procs)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def shared_variant(args, rank, world, ctx, lib, capi, sharding, dev, db, logical, B, BT, timed, check, dptr):
+    """OptNet-shared variant of config 2: Q, G, A are ONE instance shared by the 4096 problems (read once,
+    L2 resident), only z, lam, nu, h and the seeds vary.  One step = reverse sensitivities of this rank's shard + the
+    device-side batch sum of the shared-parameter gradients (dQ, dq, dG, dh, dA, db) + ONE device-resident fp64
+    ncclAllReduce of the 9360 sums over the ranks, all stream-ordered inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        sharding.nccl_init(ctx, rank, world)
+    n, m = N_VAR, M_INEQ
+    per = N_VAR * N_VAR + N_VAR + M_INEQ * N_VAR + M_INEQ + P_EQ * N_VAR + P_EQ
+    rev = torch.empty((B, KKT_N), dtype=torch.float64, device=dev)
+    grads = torch.empty(per, dtype=torch.float64, device=dev)
+    # the shared weights: instance 0 of the full job on every rank (same seed everywhere)
+    import bench_data
+    w = bench_data.qp_batch_fast(1, N_VAR, M_INEQ, P_EQ, seed=4242)
+    sh = {k: torch.from_numpy(np.ascontiguousarray(w[k].transpose(0, 2, 1))).to(dev) for k in ("Q", "G", "A")}
+    null = capi.vp(None)
+    flags = capi.QP_SHARED_MATRICES | capi.QP_ASYNC
+    gflags = capi.QP_ASYNC | (capi.QP_ALLREDUCE if world > 1 else 0)
+
+    def step():
+        check(lib.diffopt_b200_qp_batch_solve_ex(
+            ctx.h, B, N_VAR, M_INEQ, P_EQ, dptr(sh["Q"]), dptr(sh["G"]), dptr(sh["A"]), dptr(db["h"]), dptr(db["z"]),
+            dptr(db["lam"]), dptr(db["nu"]), null, null, null, null, null, null, dptr(db["seed"]), null, dptr(rev), null,
+            capi.DEVICE, flags), "qp_batch_solve_ex(shared)")
+        check(lib.diffopt_b200_qp_batch_shared_grads(
+            ctx.h, B, N_VAR, M_INEQ, P_EQ, dptr(db["z"]), dptr(db["lam"]), dptr(db["nu"]), dptr(rev), dptr(grads),
+            capi.DEVICE, gflags), "qp_batch_shared_grads")
+
+    def finish():
+        check(lib.diffopt_b200_synchronize(ctx.h), "diffopt_b200_synchronize")
+    for _ in range(3):
+        step()
+    finish()
+    steps = min(args.steps, 100)
+    ms, _ = timed(step, steps, finish)
+    # post-timing checks (oracle / host arithmetic as checker only).  (1) the reverse solves against the oracle on a few
+    # instances; the (z, lam, nu, h) of this variant are not a KKT point of the shared matrices, which is irrelevant for
+    # the arithmetic exercised (LHS assembly, factorisation, solve).  (2) batch sum + all-reduce: the getters evaluated
+    # on the host from this rank's device results, summed over the ranks by torch.distributed as an independent path.
+    from oracle import qp as oqp
+    r = rev.cpu().numpy()
+    z, lam, nu = logical["z"], logical["lam"], logical["nu"]
+    serr = 0.0
+    for b in range(min(4, B)):
+        want_b = np.concatenate(oqp.reverse(w["Q"][0], w["G"][0], logical["h"][b], w["A"][0], z[b], lam[b], nu[b],
+                                            logical["seed"][b]))
+        serr = max(serr, float(np.linalg.norm(r[b] - want_b) / np.linalg.norm(want_b)))
+    if not serr <= 1e-8:
+        raise RuntimeError(f"shared-variant reverse solve check failed on rank {rank}: {serr:.3e}")
+    dQ = 0.5 * (np.einsum("bi,bj->ij", r[:, :n], z) + np.einsum("bi,bj->ij", z, r[:, :n]))
+    dG = np.einsum("bi,bj->ij", lam * r[:, n:n + m], z) + np.einsum("bi,bj->ij", lam, r[:, :n])
+    dA = np.einsum("bi,bj->ij", r[:, n + m:], z) + np.einsum("bi,bj->ij", nu, r[:, :n])
+    loc = np.concatenate([dQ.T.ravel(), r[:, :n].sum(0), dG.T.ravel(), -(lam * r[:, n:n + m]).sum(0), dA.T.ravel(),
+                          -r[:, n + m:].sum(0)])
+    tot = torch.from_numpy(loc).to(dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    got, want = grads.cpu().numpy(), tot.cpu().numpy()
+    cerr = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    if not cerr <= 1e-10:
+        raise RuntimeError(f"shared-variant gradient sum / all-reduce check failed on rank {rank}: {cerr:.3e}")
+    if world > 1:
+        lib.diffopt_b200_nccl_destroy(ctx.h)
+    return {"value": BT * steps / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms / steps, "steps": steps,
+            "workload": "config 2, OptNet-shared: Q, G, A one instance for all 4096 problems; reverse sensitivities + "
+                        "batch-summed shared-parameter gradients",
+            "collective": ("ncclAllReduce(sum, f64, %d values = %d B) on the ctx stream, device resident, once per step"
+                           % (per, 8 * per)) if world > 1 else "none (1 GPU): device batch sum only",
+            "kernels_per_step": "qp_kkt_sqd_kernel + fallback list kernel + shared_grads_partial + shared_grads_final"
+                                + (" + NCCL all-reduce" if world > 1 else ""),
+            "allreduced_grads_rel_err_vs_host_sum": cerr, "reverse_rel_err_vs_oracle": serr}
+
+
+def active_set_sweep(args, ctx, lib, capi, dev, timed, check, dptr):
+    """Throughput of the headline call away from the benchmark's fixed 16 active rows (r1 review): 0 / 16 / 32 / 48 active
+    inequalities, and interior-point style duals (inactive rows carry lam = 1e-9, active rows slack -1e-9: nothing is an
+    exact zero)."""
+    import torch
+
+    import bench_data
+    out = {}
+    B = 4096
+    cases = [("active_0", 0, False), ("active_16", 16, False), ("active_32", 32, False), ("active_48", 48, False),
+             ("ipm_duals_16_active", 16, True)]
+    for name, na, ipm in cases:
+        d = bench_data.qp_batch_fast(B, N_VAR, M_INEQ, P_EQ, n_active=na, seed=77 + na)
+        if ipm:
+            act = d["lam"] > 0
+            Gz = np.einsum("bij,bj->bi", d["G"], d["z"])
+            d["lam"] = np.where(act, d["lam"], 1e-9)
+            d["h"] = Gz - np.where(act, -1e-9, Gz - d["h"])
+        t = {k: torch.from_numpy(np.ascontiguousarray(d[k].transpose(0, 2, 1) if k in SHAPES else d[k])).to(dev) for k in FIELDS}
+        fo = torch.empty((B, KKT_N), dtype=torch.float64, device=dev)
+        ro = torch.empty_like(fo)
+        io = torch.zeros(B, dtype=torch.int32, device=dev)
+        a = [dptr(t[k]) for k in FIELDS] + [dptr(fo), dptr(ro), dptr(io)]
+        for _ in range(3):   # blocking calls first: they let the launch configuration follow the new active-set size
+            check(lib.diffopt_b200_qp_batch_solve(ctx.h, B, N_VAR, M_INEQ, P_EQ, *a, capi.DEVICE), "qp_batch_solve")
+
+        def step():
+            check(lib.diffopt_b200_qp_batch_solve_async(ctx.h, B, N_VAR, M_INEQ, P_EQ, *a), "qp_batch_solve_async")
+        steps = 20
+        ms, _ = timed(step, steps, lambda: check(lib.diffopt_b200_synchronize(ctx.h), "synchronize"))
+        nfb, hint, kern = ctx.qp_last_stats()
+        out[name] = {"solves_per_s": B * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+                     "kernel": {0: "generic LU", 1: "pivoted LU", 2: "LDL' fast path"}.get(kern, "?"),
+                     "instances_sent_to_pivoted_lu": nfb, "configured_active_rows": hint}
+        del t, fo, ro, io
+    return out
 
 
 def _profile_facts():
@@ -392,6 +637,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-aux", action="store_true", help="skip the active-set sweep")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

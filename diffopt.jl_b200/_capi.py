@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libdiffopt_b200.so")
 
 HOST, DEVICE = 0, 1
+QP_SHARED_MATRICES, QP_SHARED_DIRECTION, QP_PACKED_Q, QP_ASYNC, QP_ALLREDUCE = 1, 2, 4, 8, 16
 CONE_ZERO, CONE_NONNEG, CONE_SOC, CONE_PSD = 0, 1, 2, 3
 
 _lib = None
@@ -37,6 +38,11 @@ SIGNATURES = {
     "diffopt_b200_qp_batch_solve_async": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 17),
     "diffopt_b200_synchronize": (C.c_int32, [vp]),
     "diffopt_b200_qp_batch_last_stats": (C.c_int32, [vp, vp]),
+    "diffopt_b200_qp_batch_solve_ex": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 17 + [C.c_int32, C.c_int32]),
+    "diffopt_b200_qp_batch_shared_grads": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 5 + [C.c_int32, C.c_int32]),
+    "diffopt_b200_nccl_unique_id": (C.c_int32, [vp]),
+    "diffopt_b200_nccl_init": (C.c_int32, [vp, C.c_int32, C.c_int32, vp]),
+    "diffopt_b200_nccl_destroy": (C.c_int32, [vp]),
     "diffopt_b200_qp_batch_setup": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 7 + [C.c_int32]),
     "diffopt_b200_qp_batch_reverse": (C.c_int32, [vp, vp, vp, vp, C.c_int32]),
     "diffopt_b200_qp_batch_forward": (C.c_int32, [vp] * 9 + [C.c_int32]),
@@ -45,7 +51,7 @@ SIGNATURES = {
     "diffopt_b200_sparse_setup": (C.c_int32, [vp, C.c_int64, vp, vp, vp, C.c_int32, vp]),
     "diffopt_b200_sparse_solve": (C.c_int32, [vp, C.c_int64, vp, vp, C.c_int32]),
     "diffopt_b200_sparse_stats": (C.c_int32, [vp, vp]),
-    "diffopt_b200_sparse_analyze": (C.c_int32, [C.c_int64, vp, vp, C.c_int32, vp]),
+    "diffopt_b200_sparse_analyze": (C.c_int32, [C.c_int64, vp, vp, vp, C.c_int32, vp]),
     "diffopt_b200_lsqr_csc": (C.c_int32, [vp, C.c_int64, C.c_int64, vp, vp, vp, C.c_int32, vp, C.c_double,
                                           C.c_double, C.c_double, C.c_int64, vp, vp, C.c_int32]),
     "diffopt_b200_conic_setup": (C.c_int32, [vp, C.c_int64, C.c_int64] + [vp] * 8 + [C.c_int64, vp, vp, C.c_int32]),

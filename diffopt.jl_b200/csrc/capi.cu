@@ -65,6 +65,9 @@ int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {
     release_csr(ctx->lsqr_mat);
     for (DevBuf* b : {&ctx->sparse.AB, &ctx->sparse.ipiv, &ctx->sparse.perm, &ctx->sparse.work}) b->release();
     sparse_mf_release(ctx);
+    nccl_release(ctx);
+    ctx->qp_unpacked[0].release();
+    ctx->qp_unpacked[1].release();
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -118,8 +121,8 @@ static int32_t finish_info(diffopt_b200_ctx* ctx, int64_t B, int* dinfo, int32_t
     return rc;
 }
 
-static int32_t qp_solve_common(diffopt_b200_ctx* ctx, QpSolveArgs a, double* fwd_user, double* rev_user,
-                               int32_t* info_user, int memspace, bool async = false) {
+int32_t qp_solve_common(diffopt_b200_ctx* ctx, QpSolveArgs a, double* fwd_user, double* rev_user, int32_t* info_user, int memspace,
+                        bool async) {
     const int64_t B = a.B;
     const int N = a.n + a.m + a.p;
     void *dfwd = nullptr, *drev = nullptr;
@@ -204,7 +207,7 @@ int32_t diffopt_b200_qp_batch_solve(diffopt_b200_ctx* ctx, int64_t B, int32_t n,
         STAGE(12, db, db, p)
     }
     if (rev_out) { STAGE(13, seed, dl_dz, n) }
-    return qp_solve_common(ctx, a, fwd_out, rev_out, info, memspace);
+    return qp_solve_common(ctx, a, fwd_out, rev_out, info, memspace, false);
 }
 
 int32_t diffopt_b200_qp_batch_solve_async(diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
@@ -325,7 +328,7 @@ int32_t diffopt_b200_qp_batch_reverse(diffopt_b200_ctx* ctx, const double* dl_dz
     const void* ptr;
     DO_CUDA(ctx, stage_in(ctx, ctx->in[13], dl_dz, sizeof(double) * a.B * a.n, memspace, &ptr));
     a.seed = (const double*)ptr;
-    return qp_solve_common(ctx, a, nullptr, rev_out, info, memspace);
+    return qp_solve_common(ctx, a, nullptr, rev_out, info, memspace, false);
 }
 
 int32_t diffopt_b200_qp_batch_forward(diffopt_b200_ctx* ctx, const double* dQ, const double* dq, const double* dG,
@@ -348,7 +351,7 @@ int32_t diffopt_b200_qp_batch_forward(diffopt_b200_ctx* ctx, const double* dQ, c
     STAGE(10, dh, dh, m)
     STAGE(11, dA, dA, (size_t)p * n)
     STAGE(12, db, db, p)
-    return qp_solve_common(ctx, a, fwd_out, nullptr, info, memspace);
+    return qp_solve_common(ctx, a, fwd_out, nullptr, info, memspace, false);
 }
 
 int32_t diffopt_b200_qp_batch_param_grads(diffopt_b200_ctx* ctx, const double* rev, int32_t reduce_over_batch,

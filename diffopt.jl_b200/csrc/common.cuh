@@ -89,6 +89,9 @@ struct SparseBandState {
     DevBuf AB, ipiv, perm, work;
 };
 
+struct NcclUniqueIdBytes { char internal[128]; };  // ncclUniqueId (nccl.h), passed by value to ncclCommInitRank
+void nccl_release(struct diffopt_b200_ctx* ctx);
+
 struct SparseMfImpl;  // multifrontal factorisation kept by diffopt_b200_sparse_setup (sparse_mf.cu)
 void sparse_mf_release(struct diffopt_b200_ctx* ctx);
 
@@ -131,6 +134,9 @@ struct diffopt_b200_ctx {
     LsqrWork lsqr;
     CsrDev lsqr_mat;
     SparseBandState sparse;
+    void* nccl_comm = nullptr;    // ncclComm_t of diffopt_b200_nccl_init (one rank per ctx)
+    int nccl_ranks = 0, nccl_rank = 0;
+    DevBuf qp_unpacked[2];        // Q / dQ expanded from packed lower triangles (qp_batch_solve_ex)
     SparseMfImpl* sparse_mf = nullptr;
     int sparse_method = 0;        // factorisation currently held: 0 none, 1 banded LU (RCM), 2 multifrontal LU
     int64_t sparse_N = 0;

@@ -320,6 +320,138 @@ __global__ void __launch_bounds__(MF_TC) mf_backward_kernel(const int* list, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Leaf fronts (tree level 0: no children, k <= KMAX) hold most rows of the matrix, so their sweeps carry the N x nrhs
+// block through HBM.  One thread per right-hand side column with ITS k entries in registers (all loops unrolled to
+// KMAX, panels zero-padded in shared memory and read as broadcast 16-byte loads), the row interchanges folded into
+// the gather, no work area: forward reads the caller's b and writes y / the boundary update, backward reads y and the
+// separator solutions and writes the caller's x.
+constexpr int MF_KMAX = 32;
+constexpr int MF_LEAF_TC = 128;
+
+__global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* list, const MfFront* fronts, const int* perm,
+                                                                     const int* piv, const double* Lp, const double* B, double* Y,
+                                                                     double* W, const long long N, const int nrhs) {
+    extern __shared__ __align__(16) double mf_smem[];
+    __shared__ int rows[MF_KMAX];
+    const int fid = list[blockIdx.x];
+    const MfFront fr = fronts[fid];
+    const int k = fr.k, s = fr.s, nf = k + s;
+    const int tid = threadIdx.x, col = blockIdx.y * MF_LEAF_TC + tid;
+    double* Ls = mf_smem;  // row r of the L panel at Ls[r * KMAX .. ], columns >= k zero
+    for (int i = tid; i < nf * MF_KMAX; i += MF_LEAF_TC) {
+        const int r = i / MF_KMAX, c = i % MF_KMAX;
+        Ls[i] = (c < k && (r >= k || c < r)) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
+    }
+    if (tid == 0) {  // net effect of the row interchanges: position r of P b comes from row src[r]
+        int src[MF_KMAX];
+        for (int r = 0; r < k; ++r) src[r] = r;
+        for (int j = 0; j < k; ++j) {
+            const int p = piv[fr.first + j];
+            const int t = src[j];
+            src[j] = src[p];
+            src[p] = t;
+        }
+        for (int r = 0; r < k; ++r) rows[r] = perm[fr.first + src[r]];
+    }
+    __syncthreads();
+    if (col >= nrhs) return;
+    double y[MF_KMAX];
+    const double* b = B + (size_t)N * col;
+#pragma unroll
+    for (int r = 0; r < MF_KMAX; ++r) y[r] = r < k ? b[rows[r]] : 0.0;
+#pragma unroll
+    for (int i = 1; i < MF_KMAX; ++i) {  // unit-lower L11 (block-uniform guard: rows >= k belong to L21)
+        if (i >= k) break;
+        double acc = y[i], acc2 = 0.0;
+        const double2* l2 = reinterpret_cast<const double2*>(Ls + i * MF_KMAX);
+#pragma unroll
+        for (int j = 0; j + 1 < i; j += 2) {
+            const double2 l = l2[j >> 1];
+            acc = fma(-l.x, y[j], acc);
+            acc2 = fma(-l.y, y[j + 1], acc2);
+        }
+        if (i & 1) acc = fma(-Ls[i * MF_KMAX + i - 1], y[i - 1], acc);
+        y[i] = acc + acc2;
+    }
+    double* yo = Y + (size_t)fr.first * nrhs + col;
+#pragma unroll
+    for (int r = 0; r < MF_KMAX; ++r)
+        if (r < k) yo[(size_t)r * nrhs] = y[r];
+    double* wo = W + (size_t)fr.w * nrhs + col;
+    for (int t = 0; t < s; ++t) {  // boundary update  w = -L21 y
+        const double2* l2 = reinterpret_cast<const double2*>(Ls + (k + t) * MF_KMAX);
+        double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < MF_KMAX; j += 2) {
+            const double2 l = l2[j >> 1];
+            acc = fma(-l.x, y[j], acc);
+            acc2 = fma(-l.y, y[j + 1], acc2);
+        }
+        wo[(size_t)t * nrhs] = acc + acc2;
+    }
+}
+
+__global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int* list, const MfFront* fronts, const int* strct,
+                                                                      const int* perm, const double* Lp, const double* Up,
+                                                                      const double* Y, double* X, const long long N, const int nrhs) {
+    extern __shared__ __align__(16) double mf_smem[];
+    __shared__ int rows[MF_KMAX];
+    __shared__ double rdiag[MF_KMAX];
+    const int fid = list[blockIdx.x];
+    const MfFront fr = fronts[fid];
+    const int k = fr.k, s = fr.s, nf = k + s;
+    const int tid = threadIdx.x, col = blockIdx.y * MF_LEAF_TC + tid;
+    double* U11s = mf_smem;                      // row i at U11s[i * KMAX ..], strictly upper part, zero elsewhere
+    double* U12s = U11s + MF_KMAX * MF_KMAX;     // boundary column t at U12s[t * KMAX ..] (entries i < k)
+    for (int i = tid; i < MF_KMAX * MF_KMAX; i += MF_LEAF_TC) {
+        const int r = i / MF_KMAX, c = i % MF_KMAX;
+        U11s[i] = (r < k && c < k && c > r) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
+    }
+    for (int i = tid; i < s * MF_KMAX; i += MF_LEAF_TC) {
+        const int t = i / MF_KMAX, r = i % MF_KMAX;
+        U12s[i] = r < k ? Up[fr.up + r + (size_t)t * k] : 0.0;
+    }
+    if (tid < MF_KMAX) {
+        rdiag[tid] = tid < k ? 1.0 / Lp[fr.lp + tid + (size_t)tid * nf] : 0.0;
+        if (tid < k) rows[tid] = perm[fr.first + tid];
+    }
+    __syncthreads();
+    if (col >= nrhs) return;
+    double y[MF_KMAX];
+    const double* yi = Y + (size_t)fr.first * nrhs + col;
+#pragma unroll
+    for (int r = 0; r < MF_KMAX; ++r) y[r] = r < k ? yi[(size_t)r * nrhs] : 0.0;
+    const int* sp = strct + fr.soff;
+    for (int t = 0; t < s; ++t) {  // y -= U12 x2
+        const double x2 = Y[(size_t)sp[t] * nrhs + col];
+        const double2* u2 = reinterpret_cast<const double2*>(U12s + t * MF_KMAX);
+#pragma unroll
+        for (int i = 0; i < MF_KMAX; i += 2) {
+            const double2 u = u2[i >> 1];
+            y[i] = fma(-u.x, x2, y[i]);
+            y[i + 1] = fma(-u.y, x2, y[i + 1]);
+        }
+    }
+#pragma unroll
+    for (int i = MF_KMAX - 1; i >= 0; --i) {
+        double acc = y[i], acc2 = 0.0;
+        const double* ur = U11s + i * MF_KMAX;
+        if (!(i & 1)) acc = fma(-ur[i + 1], y[i + 1], acc);   // first entry right of the diagonal sits at an odd column
+#pragma unroll
+        for (int j = (i + 2) & ~1; j < MF_KMAX; j += 2) {
+            const double2 u = *reinterpret_cast<const double2*>(ur + j);
+            acc = fma(-u.x, y[j], acc);
+            acc2 = fma(-u.y, y[j + 1], acc2);
+        }
+        y[i] = (acc + acc2) * rdiag[i];
+    }
+    double* x = X + (size_t)N * col;
+#pragma unroll
+    for (int r = 0; r < MF_KMAX; ++r)
+        if (r < k) x[rows[r]] = y[r];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host analysis
 struct Graph {
     int64_t N;
@@ -335,8 +467,15 @@ struct Dissector {
     std::vector<std::vector<int32_t>> snodes;  // supernodes in elimination order
     int next_region = 1;
     std::vector<int32_t> queue;
+    const std::vector<int32_t>* weight = nullptr;  // original vertices behind every (contracted) vertex; nullptr: 1 each
 
     Dissector(const Graph& gr, int leaf) : g(gr), leaf_max(leaf), region((size_t)gr.N, 0), level((size_t)gr.N, -1) {}
+    int64_t wsum(const std::vector<int32_t>& vs) const {
+        if (!weight) return (int64_t)vs.size();
+        int64_t w = 0;
+        for (int32_t v : vs) w += (*weight)[(size_t)v];
+        return w;
+    }
 
     // BFS inside region `rid` from `start`; fills queue (visit order) and level[]; returns the number of levels
     int bfs(int32_t start, int32_t rid) {
@@ -378,13 +517,17 @@ struct Dissector {
         }
         for (int32_t v : verts) level[(size_t)v] = -1;
         std::vector<int32_t> bin;
+        int64_t binw = 0;
         for (auto& comp : comps) {
-            if ((int)comp.size() <= leaf_max) {  // small component: pack with its small siblings into one leaf front
-                if (!bin.empty() && (int)(bin.size() + comp.size()) > leaf_max) {
+            const int64_t cw = wsum(comp);
+            if (cw <= leaf_max) {  // small component: pack with its small siblings into one leaf front
+                if (!bin.empty() && binw + cw > leaf_max) {
                     emit(bin);
                     bin.clear();
+                    binw = 0;
                 }
                 bin.insert(bin.end(), comp.begin(), comp.end());
+                binw += cw;
                 continue;
             }
             const int32_t cid = next_region++;
@@ -659,8 +802,8 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
 }
 
 // symmetrised pattern + ordering (dense vertices last, nested dissection on the rest) -> supernodes in elimination order
-bool mf_order(int64_t N, const int64_t* colptr, const int64_t* rowval, Graph& g, std::vector<std::vector<int32_t>>& snodes,
-              std::string& err) {
+bool mf_order(int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval, Graph& g,
+              std::vector<std::vector<int32_t>>& snodes, std::string& err) {
     // symmetrised pattern without the diagonal, duplicates removed
     g.N = N;
     g.ptr.assign((size_t)N + 1, 0);
@@ -703,22 +846,114 @@ bool mf_order(int64_t N, const int64_t* colptr, const int64_t* rowval, Graph& g,
         g.ptr.swap(nptr);
         g.adj.resize((size_t)w);
     }
+    // Weak diagonals (KKT matrices: the multiplier rows) cannot be pivoted inside a front unless a partner row sits in
+    // the same front.  Symmetric matching: every vertex whose diagonal is (numerically) zero is paired with the
+    // unmatched neighbour u that maximises |a_uv a_vu|; pairs are contracted to one vertex for the ordering, so the
+    // dissection never separates them (the compressed-graph ordering of symmetric indefinite solvers).
+    std::vector<int32_t> mate((size_t)N, -1);
+    if (nzval) {
+        std::vector<double> dmag((size_t)N, 0.0), omax((size_t)N, 0.0);
+        for (int64_t c = 0; c < N; ++c)
+            for (int64_t e = colptr[c] - 1; e < colptr[c + 1] - 1; ++e) {
+                const int64_t r = rowval[e] - 1;
+                const double a = fabs(nzval[e]);
+                if (r == c) dmag[(size_t)c] += a;
+                else {
+                    omax[(size_t)c] = std::max(omax[(size_t)c], a);
+                    omax[(size_t)r] = std::max(omax[(size_t)r], a);
+                }
+            }
+        auto entry = [&](int64_t r, int64_t c) -> double {  // |a_rc| (rows of a column are sorted in Julia's CSC; else linear scan)
+            const int64_t* b = rowval + (colptr[c] - 1);
+            const int64_t* e = rowval + (colptr[c + 1] - 1);
+            const int64_t* it = std::lower_bound(b, e, r + 1);
+            if (it != e && *it == r + 1) return fabs(nzval[it - rowval]);
+            for (it = b; it != e; ++it)
+                if (*it == r + 1) return fabs(nzval[it - rowval]);
+            return 0.0;
+        };
+        std::vector<int32_t> weak;
+        for (int64_t v = 0; v < N; ++v)
+            if (omax[(size_t)v] > 0.0 && dmag[(size_t)v] <= 1e-8 * omax[(size_t)v]) weak.push_back((int32_t)v);
+        std::stable_sort(weak.begin(), weak.end(), [&](int32_t a, int32_t b) {
+            return g.ptr[(size_t)a + 1] - g.ptr[(size_t)a] < g.ptr[(size_t)b + 1] - g.ptr[(size_t)b];
+        });
+        for (int32_t v : weak) {
+            if (mate[(size_t)v] >= 0) continue;
+            double best = 0.0;
+            int32_t bu = -1;
+            for (int64_t e = g.ptr[(size_t)v]; e < g.ptr[(size_t)v + 1]; ++e) {
+                const int32_t u = g.adj[(size_t)e];
+                if (mate[(size_t)u] >= 0) continue;
+                const double w = entry(u, v) * entry(v, u);
+                if (w > best) {
+                    best = w;
+                    bu = u;
+                }
+            }
+            if (bu >= 0) {
+                mate[(size_t)v] = bu;
+                mate[(size_t)bu] = v;
+            }
+        }
+    }
+    // contracted graph
+    std::vector<int32_t> cmap((size_t)N, -1), cw;
+    std::vector<std::vector<int32_t>> members;
+    for (int64_t v = 0; v < N; ++v) {
+        if (cmap[(size_t)v] >= 0) continue;
+        const int32_t id = (int32_t)members.size();
+        cmap[(size_t)v] = id;
+        members.push_back({(int32_t)v});
+        const int32_t u = mate[(size_t)v];
+        if (u >= 0) {
+            cmap[(size_t)u] = id;
+            members.back().push_back(u);
+        }
+        cw.push_back((int32_t)members.back().size());
+    }
+    Graph gc;
+    gc.N = (int64_t)members.size();
+    gc.ptr.assign((size_t)gc.N + 1, 0);
+    {
+        std::vector<int32_t> tmp;
+        for (int64_t c = 0; c < gc.N; ++c) {
+            tmp.clear();
+            for (int32_t v : members[(size_t)c])
+                for (int64_t e = g.ptr[(size_t)v]; e < g.ptr[(size_t)v + 1]; ++e) {
+                    const int32_t d = cmap[(size_t)g.adj[(size_t)e]];
+                    if (d != c) tmp.push_back(d);
+                }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            gc.adj.insert(gc.adj.end(), tmp.begin(), tmp.end());
+            gc.ptr[(size_t)c + 1] = (int64_t)gc.adj.size();
+        }
+    }
     // ordering: dense vertices last, nested dissection on the rest
     int leaf = 32;
     if (const char* lf = getenv("DIFFOPT_B200_MF_LEAF")) leaf = std::max(1, atoi(lf));
     {
-        Dissector D(g, leaf);
+        Dissector D(gc, leaf);
+        D.weight = &cw;
         const double dense_deg = std::max(40.0, 10.0 * std::sqrt((double)N));
         std::vector<int32_t> dense, rest;
-        for (int64_t v = 0; v < N; ++v) {
-            if ((double)(g.ptr[(size_t)v + 1] - g.ptr[(size_t)v]) > dense_deg) {
-                dense.push_back((int32_t)v);
-                D.region[(size_t)v] = -1;
-            } else rest.push_back((int32_t)v);
+        for (int64_t c = 0; c < gc.N; ++c) {
+            if ((double)(gc.ptr[(size_t)c + 1] - gc.ptr[(size_t)c]) > dense_deg) {
+                dense.push_back((int32_t)c);
+                D.region[(size_t)c] = -1;
+            } else rest.push_back((int32_t)c);
         }
         D.dissect(rest, 0);
         if (!dense.empty()) D.emit(dense);
-        snodes.swap(D.snodes);
+        snodes.clear();
+        snodes.reserve(D.snodes.size());
+        for (auto& sn : D.snodes) {
+            std::vector<int32_t> verts;
+            for (int32_t c : sn) verts.insert(verts.end(), members[(size_t)c].begin(), members[(size_t)c].end());
+            std::sort(verts.begin(), verts.end());
+            snodes.push_back(std::move(verts));
+        }
     }
     return true;
 }
@@ -838,7 +1073,7 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
     SparseMfImpl& M = *ctx->sparse_mf;
     {
         std::string err;
-        if (!mf_order(N, colptr, rowval, M.g, M.snodes, err)) BAD_ARG(ctx, err);
+        if (!mf_order(N, colptr, rowval, nzval, M.g, M.snodes, err)) BAD_ARG(ctx, err);
     }
     Graph& g = M.g;
     DO_CUDA(ctx, M.vals.reserve(std::max<size_t>(sizeof(double) * (size_t)nnz, 16)));
@@ -904,6 +1139,11 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
     DO_CUDA(ctx, M.W.reserve(std::max<size_t>(sizeof(double) * (size_t)H.w_rows * (size_t)nrhs, 16)));
     const unsigned tiles = (unsigned)((nrhs + MF_TC - 1) / MF_TC);
     DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const unsigned ltiles = (unsigned)((nrhs + MF_LEAF_TC - 1) / MF_LEAF_TC);
+    const bool use_leaf = getenv("DIFFOPT_B200_MF_NO_LEAF_KERNELS") == nullptr;
+    auto leaf_group = [&](const MfLaunch& L) {
+        return use_leaf && L.level == 0 && !L.big && L.max_k <= MF_KMAX && sizeof(double) * (size_t)(MF_KMAX + L.max_nf) * MF_KMAX <= MF_SMEM_CAP;
+    };
     auto smem_fwd = [](const MfLaunch& L) {
         return ((size_t)L.max_nf * L.max_k + (size_t)MF_TC * (L.max_k | 1) + (size_t)MF_TC * (L.max_s | 1)) * sizeof(double);
     };
@@ -916,7 +1156,13 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
         const dim3 grid((unsigned)L.count, tiles);
         const size_t smem = smem_fwd(L);
         const bool big = L.big || smem > MF_SMEM_CAP;
-        if (!big) {
+        if (leaf_group(L)) {
+            const size_t ls = sizeof(double) * (size_t)L.max_nf * MF_KMAX;
+            DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ls, 1024)));
+            mf_forward_leaf_kernel<<<dim3((unsigned)L.count, ltiles), MF_LEAF_TC, ls, ctx->stream>>>(
+                M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.perm.as<int>(), M.piv.as<int>(), M.Lp.as<double>(),
+                (const double*)dB, M.Y.as<double>(), M.W.as<double>(), N, (int)nrhs);
+        } else if (!big) {
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
             mf_forward_kernel<false><<<grid, MF_TC, smem, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(),
                                                                          M.child_idx.as<int>(), M.rel.as<int>(), M.perm.as<int>(),
@@ -936,7 +1182,13 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
         const dim3 grid((unsigned)L.count, tiles);
         const size_t smem = smem_bwd(L);
         const bool big = L.big || smem > MF_SMEM_CAP || smem_fwd(L) > MF_SMEM_CAP;
-        if (!big) {
+        if (leaf_group(L)) {
+            const size_t ls = sizeof(double) * (size_t)(MF_KMAX + L.max_s) * MF_KMAX;
+            DO_CUDA(ctx, cudaFuncSetAttribute(mf_backward_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ls, 1024)));
+            mf_backward_leaf_kernel<<<dim3((unsigned)L.count, ltiles), MF_LEAF_TC, ls, ctx->stream>>>(
+                M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.strct.as<int>(), M.perm.as<int>(), M.Lp.as<double>(),
+                M.Up.as<double>(), M.Y.as<double>(), (double*)dX, N, (int)nrhs);
+        } else if (!big) {
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
             mf_backward_kernel<false><<<grid, MF_TC, smem, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(),
                                                                           M.strct.as<int>(), M.perm.as<int>(), M.Lp.as<double>(),
@@ -958,14 +1210,15 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
 }
 
 // Host-only analysis (no GPU involved): ordering + symbolic factorisation of a pattern, for inspection and tests.
-extern "C" int32_t diffopt_b200_sparse_analyze(int64_t N, const int64_t* colptr, const int64_t* rowval, int32_t trans, double* out8) {
+extern "C" int32_t diffopt_b200_sparse_analyze(int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                                               int32_t trans, double* out8) {
     if (N <= 0 || !colptr || !rowval || !out8 || colptr[0] != 1) return -1;
     Graph g;
     std::vector<std::vector<int32_t>> snodes;
     MfHost H;
     std::string err;
     const auto t0 = std::chrono::steady_clock::now();
-    if (!mf_order(N, colptr, rowval, g, snodes, err)) return -1;
+    if (!mf_order(N, colptr, rowval, nzval, g, snodes, err)) return -1;
     if (!mf_symbolic(g, snodes, N, colptr, rowval, trans, H, err)) return -3;
     out8[0] = 2.0;
     out8[1] = (double)H.fronts.size();

@@ -60,9 +60,9 @@ def solve_csc(ctx: Context, M, rhs, trans=False):
 def sparse_analyze(M, trans=False):
     """Host-only ordering + symbolic factorisation of a pattern (``diffopt_b200_sparse_analyze``; no GPU needed)."""
     from ._capi import load
-    colptr, rowval, _ = julia_csc(M)
+    colptr, rowval, nzval = julia_csc(M)
     st = np.zeros(8)
-    rc = load().diffopt_b200_sparse_analyze(M.shape[0], ptr(colptr), ptr(rowval), int(trans), ptr(st))
+    rc = load().diffopt_b200_sparse_analyze(M.shape[0], ptr(colptr), ptr(rowval), ptr(nzval), int(trans), ptr(st))
     if rc != 0:
         raise RuntimeError(f"sparse_analyze failed ({rc})")
     return dict(fronts=int(st[1]), levels=int(st[2]), max_front=int(st[3]), nnz_lu=int(st[4]), factor_flops=float(st[5]),

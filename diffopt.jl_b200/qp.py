@@ -134,6 +134,90 @@ def solve_batch(ctx, Q, G, A, h, z, lam, nu, fwd_dir=None, seed=None):
     return fwd, rev, info
 
 
+def pack_lower(X):
+    """(B, n, n) symmetric matrices -> (B, n(n+1)/2) packed lower triangles, column by column (DIFFOPT_QP_PACKED_Q)."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[-1]
+    r, c = np.tril_indices(n)
+    order = np.lexsort((r, c))           # column-major order of the lower triangle
+    return np.ascontiguousarray(X.reshape(-1, n, n)[:, r[order], c[order]])
+
+
+def solve_batch_ex(ctx, Q, G, A, h, z, lam, nu, fwd_dir=None, seed=None, shared_matrices=False, shared_direction=False,
+                   packed_q=False):
+    """``diffopt_b200_qp_batch_solve_ex``: like ``solve_batch`` with batch-invariant Q, G, A (``shared_matrices``: pass ONE
+    instance, shape (n, n) / (m, n) / (p, n)), a batch-invariant forward direction dQ, dG, dA (``shared_direction``) and
+    Q / dQ sent as packed lower triangles (``packed_q``)."""
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    B, n = z.shape
+    m = 0 if lam is None else np.asarray(lam).reshape(B, -1).shape[1]
+    p = 0 if nu is None else np.asarray(nu).reshape(B, -1).shape[1]
+    N = n + m + p
+    def mat(X, r, shared, sym=False):
+        if X is None or r == 0:
+            return None
+        k = 1 if shared else B
+        if sym and packed_q:
+            return pack_lower(np.asarray(X, float).reshape(k, n, n))
+        return colmajor(np.asarray(X, float).reshape(k, r, n), r, n, k)
+    vec = lambda v, k: None if v is None or k == 0 else np.ascontiguousarray(np.asarray(v, float).reshape(B, k))
+    args = [mat(Q, n, shared_matrices, True), mat(G, m, shared_matrices), mat(A, p, shared_matrices), vec(h, m), z,
+            vec(lam, m), vec(nu, p)]
+    fwd = rev = sd = None
+    if fwd_dir is not None:
+        dQ, dq, dG, dh, dA, db = fwd_dir
+        args += [mat(dQ, n, shared_direction, True), vec(dq, n), mat(dG, m, shared_direction), vec(dh, m),
+                 mat(dA, p, shared_direction), vec(db, p)]
+        fwd = np.empty((B, N))
+    else:
+        args += [None] * 6
+    if seed is not None:
+        sd = vec(seed, n)
+        rev = np.empty((B, N))
+    info = np.zeros(B, dtype=np.int32)
+    flags = (_capi.QP_SHARED_MATRICES if shared_matrices else 0) | (_capi.QP_SHARED_DIRECTION if shared_direction else 0) | \
+        (_capi.QP_PACKED_Q if packed_q else 0)
+    rc = ctx.lib.diffopt_b200_qp_batch_solve_ex(ctx.h, B, n, m, p, *[ptr(a) for a in args], ptr(sd), ptr(fwd), ptr(rev),
+                                                ptr(info), HOST, flags)
+    ctx.check(rc)
+    return fwd, rev, info
+
+
+def shared_param_grads(ctx, z, lam, nu, rev, allreduce=False):
+    """``diffopt_b200_qp_batch_shared_grads``: batch sums of the reverse-mode parameter gradients (dQ, dq, dG, dh, dA, db)
+    for parameters shared by all instances; ``allreduce`` adds the NCCL all-reduce over the ranks of
+    ``sharding.nccl_init``.  Returns logical (row-major) arrays like ``QPBatch.param_grads(reduce_over_batch=True)``."""
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    B, n = z.shape
+    m = 0 if lam is None else np.asarray(lam).reshape(B, -1).shape[1]
+    p = 0 if nu is None else np.asarray(nu).reshape(B, -1).shape[1]
+    vec = lambda v, k: None if v is None or k == 0 else np.ascontiguousarray(np.asarray(v, float).reshape(B, k))
+    rev = np.ascontiguousarray(np.asarray(rev, float).reshape(B, n + m + p))
+    per = n * n + n + m * n + m + p * n + p
+    out = np.empty(per)
+    rc = ctx.lib.diffopt_b200_qp_batch_shared_grads(ctx.h, B, n, m, p, ptr(z), ptr(vec(lam, m)), ptr(vec(nu, p)), ptr(rev),
+                                                    ptr(out), HOST, _capi.QP_ALLREDUCE if allreduce else 0)
+    ctx.check(rc)
+    return unflatten_param_grads(out, n, m, p)
+
+
+def unflatten_param_grads(flat, n, m, p):
+    """[dQ | dq | dG | dh | dA | db] (matrices column-major) -> logical arrays."""
+    o = 0
+    def take(k):
+        nonlocal o
+        v = flat[o:o + k]
+        o += k
+        return v
+    dQ = take(n * n).reshape(n, n).T
+    dq = take(n)
+    dG = take(m * n).reshape(n, m).T
+    dh = take(m)
+    dA = take(p * n).reshape(n, p).T
+    db = take(p)
+    return dQ, dq, dG, dh, dA, db
+
+
 class QPModel:
     """Single-problem backend with the reference's ``AbstractModel`` surface (array level).
 

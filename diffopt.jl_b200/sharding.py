@@ -72,3 +72,26 @@ def sharded_reverse_shared_params(make_batch, data, seed, rank, world, group=Non
         n, m, p = batch.n, batch.m, batch.p
         local = (np.zeros((n, n)), np.zeros(n), np.zeros((m, n)), np.zeros(m), np.zeros((p, n)), np.zeros(p))
     return rev, allreduce_shared_param_grads(local, group=group, device=device)
+
+
+def nccl_init(ctx, rank, world, group=None):
+    """Creates the ctx-owned NCCL communicator (``diffopt_b200_nccl_init``): rank 0 draws the unique id, the id travels
+    through ``torch.distributed`` (any backend -- it is 128 bytes of host data), every rank joins.  After this,
+    ``diffopt_b200_qp_batch_shared_grads(..., DIFFOPT_QP_ALLREDUCE)`` reduces on the device without the host."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        rc = ctx.lib.diffopt_b200_nccl_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise RuntimeError(f"diffopt_b200_nccl_unique_id failed ({rc})")
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    if world > 1:
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0, group=group)
+        t = t.cpu()
+    ident = bytes(t.numpy().tobytes())
+    ctx.check(ctx.lib.diffopt_b200_nccl_init(ctx.h, world, rank, C.c_char_p(ident)))

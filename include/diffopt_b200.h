@@ -113,6 +113,49 @@ int32_t diffopt_b200_synchronize(diffopt_b200_ctx* ctx);
  * the call (0 generic pivoted LU, 1 tuned pivoted LU, 2 LDL' fast path). */
 int32_t diffopt_b200_qp_batch_last_stats(diffopt_b200_ctx* ctx, int64_t* out3);
 
+/* Extended form of qp_batch_solve.  flags (OR of):
+ *   DIFFOPT_QP_SHARED_MATRICES  Q, G, A are ONE instance ([n*n], [m*n], [p*n]) shared by all B problems -- an OptNet-style
+ *                               layer whose weights do not depend on the sample (docs/src/examples/polyhedral_project.jl,
+ *                               custom-relu.jl); h, z, lam, nu and the seeds stay per instance;
+ *   DIFFOPT_QP_SHARED_DIRECTION dQ, dG, dA are one instance shared by the batch (a perturbation of the shared weights);
+ *   DIFFOPT_QP_PACKED_Q         Q and dQ hold only their lower triangles, packed column by column (n(n+1)/2 doubles per
+ *                               instance: column j = rows j..n-1) -- both are symmetric (utils.jl:46-69), so half of their
+ *                               bytes over PCIe are redundant;
+ *   DIFFOPT_QP_ASYNC            stream-ordered like qp_batch_solve_async (memspace must be DIFFOPT_B200_DEVICE). */
+#define DIFFOPT_QP_SHARED_MATRICES 1
+#define DIFFOPT_QP_SHARED_DIRECTION 2
+#define DIFFOPT_QP_PACKED_Q 4
+#define DIFFOPT_QP_ASYNC 8
+#define DIFFOPT_QP_ALLREDUCE 16
+int32_t diffopt_b200_qp_batch_solve_ex(
+    diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
+    const double* Q, const double* G, const double* A, const double* h,
+    const double* z, const double* lam, const double* nu,
+    const double* dQ, const double* dq, const double* dG, const double* dh,
+    const double* dA, const double* db, const double* dl_dz,
+    double* fwd_out, double* rev_out, int32_t* info, int32_t memspace, int32_t flags);
+
+/* Reverse-mode gradients of parameters SHARED by the B instances (the getters of QuadraticProgram.jl:307-314, :448-473
+ * accumulated over the samples as docs/src/examples/polyhedral_project.jl:95-104 and src/parameters.jl:355-360 do):
+ * out_flat = [dQ (n*n, column-major) | dq (n) | dG (m*n) | dh (m) | dA (p*n) | db (p)], each the SUM over the batch of
+ *   dQ = (dz z' + z dz')/2, dq = dz, dG_i = lam_i dlam_i z + lam_i dz, dh = -lam.dlam, dA_i = dnu_i z + nu_i dz, db = -dnu
+ * from rev[B][n+m+p] = (dz, dlam, dnu) (the rev_out of a qp_batch call) and z, lam, nu of the same instances.  The sum is
+ * formed on the device in a fixed order (bitwise reproducible).  flags: DIFFOPT_QP_ALLREDUCE adds ONE fp64 ncclAllReduce
+ * (sum) of out_flat over the ranks of diffopt_b200_nccl_init -- every rank owns a shard of the batch, the buffer never
+ * leaves the GPUs; DIFFOPT_QP_ASYNC enqueues on the ctx stream without waiting (device memory only). */
+int32_t diffopt_b200_qp_batch_shared_grads(
+    diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
+    const double* z, const double* lam, const double* nu, const double* rev,
+    double* out_flat, int32_t memspace, int32_t flags);
+
+/* NCCL communicator owned by the ctx (one rank per ctx / GPU).  Rank 0 obtains a 128-byte ncclUniqueId with
+ * nccl_unique_id and hands it to the other ranks by whatever means the host program has (MPI, torch.distributed,
+ * a file); every rank then calls nccl_init.  NCCL is bound at run time (libnccl.so.2 of the host process, or
+ * DIFFOPT_B200_NCCL_LIB); -6 = not available. */
+int32_t diffopt_b200_nccl_unique_id(void* id128);
+int32_t diffopt_b200_nccl_init(diffopt_b200_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+int32_t diffopt_b200_nccl_destroy(diffopt_b200_ctx* ctx);
+
 /* Two-phase form mirroring the reference's cache (`_gradient_cache` builds LHS once,
  * QuadraticProgram.jl:182-213; seeds may then change): setup keeps the problem data
  * resident on the device, forward/reverse solve against it. */
@@ -172,10 +215,10 @@ int32_t diffopt_b200_sparse_solve(
 /* out8 = {method (0 none, 1 banded, 2 multifrontal), fronts, tree levels, largest front order, nnz(L+U) stored,
  * factorisation flop, host analysis ms, delayed-pivot repetitions} of the factorisation held by the ctx. */
 int32_t diffopt_b200_sparse_stats(diffopt_b200_ctx* ctx, double* out8);
-/* Host-only analysis of a pattern (ordering + symbolic factorisation, no GPU involved): out8 as above with
- * out8[7] = number of kernel launches one factorisation takes. */
+/* Host-only analysis (ordering + symbolic factorisation, no GPU involved): out8 as above with out8[7] = number of
+ * kernel launches one factorisation takes.  nzval may be NULL (no pairing of weak diagonals with a partner row). */
 int32_t diffopt_b200_sparse_analyze(
-    int64_t N, const int64_t* colptr, const int64_t* rowval, int32_t trans, double* out8);
+    int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval, int32_t trans, double* out8);
 
 /* ---- LSQR (IterativeSolvers.lsqr call sites QuadraticProgram.jl:488, ConicProgram.jl:323,372)
  *

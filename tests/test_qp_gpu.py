@@ -456,3 +456,50 @@ def test_sparse_setup_rejects_and_reports(ctx, monkeypatch):
     Aw = sp.lil_matrix((N, N)); Aw.setdiag(2.0); Aw[0, :] = 1.0; Aw[:, 0] = 1.0
     with pytest.raises(diffopt_b200.DiffOptB200Error):
         lsq.SparseFactorization(ctx, sp.csc_matrix(Aw))
+
+
+def test_extended_entry_shared_matrices_and_packed_triangles(ctx):
+    """diffopt_b200_qp_batch_solve_ex: (a) Q, G, A (and the direction dQ, dG, dA) given once for the whole batch
+    (OptNet layer with shared weights) and (b) Q / dQ as packed lower triangles give exactly the results of
+    the plain call on the expanded data -- headline shape (tuned kernels) and a generic shape."""
+    qpm = diffopt_b200.submodule("qp")
+    for (n, m, p, na) in ((64, 64, 16, 16), (12, 9, 3, 4)):
+        d = bench_data.qp_batch(20, n, m, p, n_active=na, seed0=8800 + n, shared=True)
+        fd = (d["dQ"], d["dq"], d["dG"], d["dh"], d["dA"], d["db"])
+        f0, r0, i0 = qpm.solve_batch(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], fwd_dir=fd, seed=d["seed"])
+        assert not i0.any()
+        of, orv = _oracle_batch(d)
+        assert rel_err(f0, of).max() <= RTOL_DIRECT and rel_err(r0, orv).max() <= RTOL_DIRECT
+        # (a) one instance of Q, G, A
+        f1, r1, i1 = qpm.solve_batch_ex(ctx, d["Q"][0], d["G"][0], d["A"][0], d["h"], d["z"], d["lam"], d["nu"], fwd_dir=fd,
+                                        seed=d["seed"], shared_matrices=True)
+        assert not i1.any() and np.array_equal(f1, f0) and np.array_equal(r1, r0)
+        # (b) packed triangles (per instance), and both together with a shared direction
+        f2, r2, _ = qpm.solve_batch_ex(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], fwd_dir=fd,
+                                       seed=d["seed"], packed_q=True)
+        assert np.array_equal(f2, f0) and np.array_equal(r2, r0)
+        fd_sh = (d["dQ"][0], d["dq"], d["dG"][0], d["dh"], d["dA"][0], d["db"])
+        f3, r3, _ = qpm.solve_batch_ex(ctx, d["Q"][0], d["G"][0], d["A"][0], d["h"], d["z"], d["lam"], d["nu"], fwd_dir=fd_sh,
+                                       seed=d["seed"], shared_matrices=True, shared_direction=True, packed_q=True)
+        B = d["z"].shape[0]
+        d3 = dict(d, dQ=np.repeat(d["dQ"][:1], B, 0), dG=np.repeat(d["dG"][:1], B, 0), dA=np.repeat(d["dA"][:1], B, 0))
+        of3, orv3 = _oracle_batch(d3)
+        assert rel_err(f3, of3).max() <= RTOL_DIRECT and rel_err(r3, orv3).max() <= RTOL_DIRECT
+
+
+@pytest.mark.parametrize("B,n,m,p", [(1, 3, 2, 1), (37, 64, 64, 16), (700, 10, 25, 0), (5, 7, 0, 2)])
+def test_shared_parameter_gradients_batch_sum(ctx, B, n, m, p):
+    """diffopt_b200_qp_batch_shared_grads (no collective: one rank): the device batch sum of the getters
+    (QuadraticProgram.jl:307-314, :448-473) equals the sum of the oracle's per-instance gradients, and is bitwise
+    reproducible from call to call (fixed summation order)."""
+    qpm = diffopt_b200.submodule("qp")
+    rng = np.random.default_rng(B + n)
+    z, lam, nu = rng.standard_normal((B, n)), rng.uniform(0, 1, (B, m)), rng.standard_normal((B, p))
+    rev = rng.standard_normal((B, n + m + p))
+    got = qpm.shared_param_grads(ctx, z, lam if m else None, nu if p else None, rev)
+    again = qpm.shared_param_grads(ctx, z, lam if m else None, nu if p else None, rev)
+    refs = [oqp.reverse_param_grads(z[b], lam[b], nu[b], rev[b, :n], rev[b, n:n + m], rev[b, n + m:]) for b in range(B)]
+    for k in range(6):
+        want = sum(r[k] for r in refs)
+        assert np.allclose(got[k], want, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(want).max(initial=0.0))), k
+        assert np.array_equal(got[k], again[k])
