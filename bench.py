@@ -512,10 +512,13 @@ def shared_variant(args, rank, world, ctx, lib, capi, sharding, dev, db, logical
     per = N_VAR * N_VAR + N_VAR + M_INEQ * N_VAR + M_INEQ + P_EQ * N_VAR + P_EQ
     rev = torch.empty((B, KKT_N), dtype=torch.float64, device=dev)
     grads = torch.empty(per, dtype=torch.float64, device=dev)
-    # the shared weights: instance 0 of the full job on every rank (same seed everywhere)
+    # the shared weights and the per-instance solutions: the same job on every rank (same seed), each keeps its shard
     import bench_data
-    w = bench_data.qp_batch_fast(1, N_VAR, M_INEQ, P_EQ, seed=4242)
-    sh = {k: torch.from_numpy(np.ascontiguousarray(w[k].transpose(0, 2, 1))).to(dev) for k in ("Q", "G", "A")}
+    w = bench_data.qp_batch_shared_fast(BT, N_VAR, M_INEQ, P_EQ, seed=4242)
+    lo, hi = sharding.shard_range(BT, rank, world)
+    sh = {k: torch.from_numpy(np.ascontiguousarray(w[k].T)).to(dev) for k in ("Q", "G", "A")}     # column-major
+    logical = {k: w[k][lo:hi] for k in ("h", "z", "lam", "nu", "seed")}
+    db = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in logical.items()}
     null = capi.vp(None)
     flags = capi.QP_SHARED_MATRICES | capi.QP_ASYNC
     gflags = capi.QP_ASYNC | (capi.QP_ALLREDUCE if world > 1 else 0)
@@ -537,16 +540,14 @@ def shared_variant(args, rank, world, ctx, lib, capi, sharding, dev, db, logical
     steps = min(args.steps, 100)
     ms, _ = timed(step, steps, finish)
     # post-timing checks (oracle / host arithmetic as checker only).  (1) the reverse solves against the oracle on a few
-    # instances; the (z, lam, nu, h) of this variant are not a KKT point of the shared matrices, which is irrelevant for
-    # the arithmetic exercised (LHS assembly, factorisation, solve).  (2) batch sum + all-reduce: the getters evaluated
+    # instances.  (2) batch sum + all-reduce: the getters evaluated
     # on the host from this rank's device results, summed over the ranks by torch.distributed as an independent path.
     from oracle import qp as oqp
     r = rev.cpu().numpy()
     z, lam, nu = logical["z"], logical["lam"], logical["nu"]
     serr = 0.0
     for b in range(min(4, B)):
-        want_b = np.concatenate(oqp.reverse(w["Q"][0], w["G"][0], logical["h"][b], w["A"][0], z[b], lam[b], nu[b],
-                                            logical["seed"][b]))
+        want_b = np.concatenate(oqp.reverse(w["Q"], w["G"], logical["h"][b], w["A"], z[b], lam[b], nu[b], logical["seed"][b]))
         serr = max(serr, float(np.linalg.norm(r[b] - want_b) / np.linalg.norm(want_b)))
     if not serr <= 1e-8:
         raise RuntimeError(f"shared-variant reverse solve check failed on rank {rank}: {serr:.3e}")

@@ -77,6 +77,25 @@ def qp_batch_fast(B, n=64, m=64, p=16, n_active=16, seed=2026):
                 seed=rng.standard_normal((B, n)))
 
 
+def qp_batch_shared_fast(B, n=64, m=64, p=16, n_active=16, seed=4242):
+    """OptNet-shared variant of config 2: ONE (Q, G, A) for the whole batch, per-instance (z, lam, nu) with
+    h = G z - slack, b = A z, q = -(Q z + G'lam + A'nu): every instance is an exact KKT point of the shared matrices.
+    Returns Q (n, n), G (m, n), A (p, n) and per-instance h, z, lam, nu, seed."""
+    rng = np.random.default_rng(seed)
+    L = rng.standard_normal((n, n))
+    Q = L @ L.T / n + 0.1 * np.eye(n)
+    G = rng.standard_normal((m, n))
+    A = rng.standard_normal((p, n))
+    z = rng.standard_normal((B, n))
+    order = np.argsort(rng.random((B, m)), axis=1)
+    active = np.zeros((B, m), dtype=bool)
+    np.put_along_axis(active, order[:, :n_active], True, axis=1)
+    lam = np.where(active, rng.uniform(0.5, 1.5, size=(B, m)), 0.0)
+    slack = np.where(active, 0.0, -rng.uniform(0.5, 1.5, size=(B, m)))
+    nu = rng.standard_normal((B, p))
+    return dict(Q=Q, G=G, A=A, h=z @ G.T - slack, b=z @ A.T, z=z, lam=lam, nu=nu, seed=rng.standard_normal((B, n)))
+
+
 def lp_config1(n=200, m=100, n_active=60, seed=1):
     """Config 1: random LP, Q == 0 -> the reference's LSQR-on-KKT branch.  Vertex-like solution:
     ``n_active`` active rows; K = [0 G'L; G D] is rank deficient by design (min-norm answer)."""

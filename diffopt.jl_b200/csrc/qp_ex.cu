@@ -238,7 +238,7 @@ int32_t diffopt_b200_qp_batch_shared_grads(diffopt_b200_ctx* ctx, int64_t B, int
         per, G, ctx->out[3].as<double>(), (double*)dout);
     ctx->launches += 2;
     DO_CUDA(ctx, cudaGetLastError());
-    if (allreduce && ctx->nccl_ranks > 1) {
+    if (allreduce) {  // also with a single rank: the collective path is the same code at any communicator size
         const int rc = nccl_api().AllReduce(dout, dout, (size_t)per, NCCL_DOUBLE, NCCL_SUM, ctx->nccl_comm, ctx->stream);
         if (rc != 0) return nccl_fail(ctx, "ncclAllReduce", rc);
     }

@@ -95,3 +95,19 @@ def nccl_init(ctx, rank, world, group=None):
         t = t.cpu()
     ident = bytes(t.numpy().tobytes())
     ctx.check(ctx.lib.diffopt_b200_nccl_init(ctx.h, world, rank, C.c_char_p(ident)))
+
+
+def sharded_reverse_shared_params_device(ctx, Q, G, A, h, z, lam, nu, seed, rank, world):
+    """The GPU form of ``sharded_reverse_shared_params``: Q, G, A are ONE instance shared by all B problems.  This rank
+    solves its contiguous shard (``diffopt_b200_qp_batch_solve_ex`` with DIFFOPT_QP_SHARED_MATRICES), sums the
+    shared-parameter gradients over the shard on the device and -- after ``nccl_init(ctx, rank, world)`` -- all-reduces
+    the 75 KB of sums with NCCL without leaving the GPUs.  Returns (rev_local, (dQ, dq, dG, dh, dA, db) totals)."""
+    from . import qp as qpm
+    B = len(z)
+    lo, hi = shard_range(B, rank, world)
+    sl = slice(lo, hi)
+    _, rev, info = qpm.solve_batch_ex(ctx, Q, G, A, h[sl], z[sl], lam[sl], nu[sl], seed=seed[sl], shared_matrices=True)
+    if info.any():
+        raise ArithmeticError(f"singular instance {int(np.flatnonzero(info)[0]) + lo}")
+    total = qpm.shared_param_grads(ctx, z[sl], lam[sl], nu[sl], rev, allreduce=world > 1)
+    return rev, total

@@ -75,7 +75,7 @@ function DiffOpt.QuadraticProgram.solve_system(s::B200Solver, LHS, RHS::Abstract
                   s.ctx.handle, size(A, 1), size(A, 2), A.colptr, A.rowval, A.nzval, trans, rhs,
                   s.atol, s.btol, s.conlim, max(size(A)...), x, C_NULL, HOST)
         else
-            # `LHS \ RHS`: pivoted LU on the device
+            # `LHS \ RHS`: pivoted LU on the device (dense kernel up to N = 1024, multifrontal sparse LU beyond)
             ccall((:diffopt_b200_kkt_solve_csc, LIB), Int32,
                   (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Int32),
                   s.ctx.handle, n, A.colptr, A.rowval, A.nzval, trans, 1, rhs, x, HOST)
@@ -88,8 +88,8 @@ end
 """
     SparseFactorization(ctx, LHS)            # LHS::SparseMatrixCSC or its Adjoint
 
-One device factorisation of a large sparse KKT matrix (RCM ordering + banded LU with partial pivoting), reused for any
-number of right-hand sides: `F \\ RHS` with `RHS::Matrix` (N x nrhs).  Replaces the per-direction `LHS' \\ RHS` of
+One device factorisation of a large sparse KKT matrix (multifrontal LU: nested dissection + partial pivoting inside the
+fronts; banded LU as fallback), reused for any number of right-hand sides: `F \\ RHS` with `RHS::Matrix` (N x nrhs).  Replaces the per-direction `LHS' \\ RHS` of
 `forward_differentiate!` (QuadraticProgram.jl:438) when many directions are differentiated against one solution.
 """
 struct SparseFactorization
@@ -128,6 +128,26 @@ function qp_model_constructor(ctx::Context)
     end
 end
 # usage:  MOI.set(model, DiffOpt.ModelConstructor(), DiffOptB200.qp_model_constructor(ctx))
+
+# Process-wide default context (device from ENV["DIFFOPT_B200_DEVICE"], default 0) for the zero-argument constructors
+# that `DiffOpt.ModelConstructor` needs (`MOI.instantiate(ctor)` calls it without arguments, moi_wrapper.jl:619-657).
+const _DEFAULT_CTX = Ref{Union{Nothing,Context}}(nothing)
+function default_context()
+    if _DEFAULT_CTX[] === nothing
+        _DEFAULT_CTX[] = Context(parse(Int, get(ENV, "DIFFOPT_B200_DEVICE", "0")))
+    end
+    return _DEFAULT_CTX[]::Context
+end
+
+"""
+    DiffOptB200.QPModel()
+
+Backend for `MOI.set(model, DiffOpt.ModelConstructor(), DiffOptB200.QPModel)`: the reference's own
+`DiffOpt.QuadraticProgram.Model` (a `DiffOpt.AbstractModel`; all of its MOI plumbing, caches and getters are kept as
+they are, QuadraticProgram.jl:60-473) with its linear algebra -- the only part that costs time,
+`solve_system` at :335 and :438 -- bound to the GPU through `B200Solver`.
+"""
+QPModel() = qp_model_constructor(default_context())()
 
 # ------------------------------------------------------------------------------------------------
 # (2) Batched QP sensitivities (OptNet-style layers): B independent instances, dense column-major
@@ -223,6 +243,182 @@ function conic_forward(ctx::Context, n::Int, m::Int, dA_rows::Vector{Int64}, dA_
     end
     check(ctx, rc)
     return (dx = dx, dz = dz, iterations = Int(stats[2]))
+end
+
+# ------------------------------------------------------------------------------------------------
+# (4) ConicModel <: DiffOpt.AbstractModel -- the conic backend behind `DiffOpt.ModelConstructor`
+#     (no narrow hook exists for ConicProgram, so the backend type itself is provided).  Same stored quantities as
+#     DiffOpt.ConicProgram.Model (ConicProgram.jl:78-101): the geometric-form MOI model, the input cache, x, s, y;
+#     `_gradient_cache` (:172-255), the LSQR solves (:323, :372) and pi / Dpi run on the device.
+#     usage:  MOI.set(model, DiffOpt.ModelConstructor(), DiffOptB200.ConicModel)
+# ------------------------------------------------------------------------------------------------
+const CP = DiffOpt.ConicProgram
+
+mutable struct ConicModel <: DiffOpt.AbstractModel
+    model::CP.Form{Float64}                      # constraints in matrix form (MatrixOfConstraints, ProductOfSets)
+    ctx::Context
+    cache_valid::Bool                            # device-side gradient cache matches (model, x, s, y)
+    vp::Vector{Float64}                          # pi(y - s), fetched once per cache (getters :396-443 need it)
+    forw_grad_cache::Union{Nothing,CP.ForwCache}
+    back_grad_cache::Union{Nothing,CP.ReverseCache}
+    input_cache::DiffOpt.InputCache
+    x::Vector{Float64}
+    s::Vector{Float64}
+    y::Vector{Float64}
+    diff_time::Float64
+    lsqr_atol::Float64
+    lsqr_btol::Float64
+    lsqr_conlim::Float64
+end
+
+function ConicModel(ctx::Context = default_context())
+    return ConicModel(CP.Form{Float64}(), ctx, false, Float64[], nothing, nothing, DiffOpt.InputCache(),
+                      Float64[], Float64[], Float64[], NaN, sqrt(eps()), sqrt(eps()), 1 / sqrt(eps()))
+end
+
+MOI.is_empty(model::ConicModel) = MOI.is_empty(model.model)
+
+function MOI.empty!(model::ConicModel)
+    MOI.empty!(model.model)
+    model.cache_valid = false
+    model.forw_grad_cache = nothing
+    model.back_grad_cache = nothing
+    empty!(model.input_cache)
+    empty!(model.x); empty!(model.s); empty!(model.y); empty!(model.vp)
+    model.diff_time = NaN
+    return
+end
+
+MOI.get(model::ConicModel, ::DiffOpt.DifferentiateTimeSec) = model.diff_time
+
+# set types are registered in the ProductOfSets on first sight, as ConicProgram.jl:132-142 does
+function MOI.supports_constraint(model::ConicModel, F::Type{MOI.VectorAffineFunction{Float64}},
+                                 ::Type{S}) where {S<:MOI.AbstractVectorSet}
+    if DiffOpt.add_set_types(model.model.constraints.sets, S)
+        push!(model.model.constraints.caches, Tuple{F,S}[])
+        push!(model.model.constraints.are_indices_mapped, BitSet())
+    end
+    return MOI.supports_constraint(model.model, F, S)
+end
+
+function MOI.set(model::ConicModel, ::MOI.ConstraintPrimalStart, ci::MOI.ConstraintIndex, value)
+    MOI.throw_if_not_valid(model, ci)
+    model.cache_valid = false
+    return DiffOpt._enlarge_set(model.s, MOI.Utilities.rows(model.model.constraints, ci), value)
+end
+
+function MOI.set(model::ConicModel, ::MOI.ConstraintDualStart, ci::MOI.ConstraintIndex, value)
+    MOI.throw_if_not_valid(model, ci)
+    model.cache_valid = false
+    return DiffOpt._enlarge_set(model.y, MOI.Utilities.rows(model.model.constraints, ci), value)
+end
+
+_cone_code(::Type{MOI.Zeros}) = Int32(0)
+_cone_code(::Type{MOI.Nonnegatives}) = Int32(1)
+_cone_code(::Type{MOI.SecondOrderCone}) = Int32(2)
+_cone_code(::Type{MOI.PositiveSemidefiniteConeTriangle}) = Int32(3)
+_cone_code(::Type{S}) where {S} = error("DiffOptB200.ConicModel: unsupported set $S")
+
+"cone list in row order (cone_type, cone_dim) from the ProductOfSets -- what `Dπ` / `π` iterate over (diff_opt.jl:491-519)"
+function _cone_list(model::ConicModel)
+    entries = Tuple{Int,Int32,Int64}[]
+    for (F, S) in MOI.get(model.model, MOI.ListOfConstraintTypesPresent())
+        for ci in MOI.get(model.model, MOI.ListOfConstraintIndices{F,S}())
+            r = MOI.Utilities.rows(model.model.constraints, ci)
+            push!(entries, (first(r), _cone_code(S), Int64(length(r))))
+        end
+    end
+    sort!(entries; by = first)
+    return Int32[e[2] for e in entries], Int64[e[3] for e in entries]
+end
+
+# _gradient_cache (ConicProgram.jl:172-255): A = -coefficients, b = constants, c (negated for MAX, zero for FEASIBILITY)
+function _gradient_cache(model::ConicModel)
+    model.cache_valid && return
+    A = -convert(SparseArrays.SparseMatrixCSC{Float64,Int}, model.model.constraints.coefficients)
+    b = model.model.constraints.constants
+    if any(isnan, model.y) || length(model.y) < length(b)
+        error("Some constraints are missing a value for the `ConstraintDualStart` attribute.")
+    end
+    if any(isnan, model.s) || length(model.s) < length(b)
+        error("Some constraints are missing a value for the `ConstraintPrimalStart` attribute.")
+    end
+    n = size(A, 2)
+    c = if MOI.get(model, MOI.ObjectiveSense()) == MOI.FEASIBILITY_SENSE
+        zeros(n)
+    else
+        obj = MOI.get(model, MOI.ObjectiveFunction{MOI.ScalarAffineFunction{Float64}}())
+        cc = Vector{Float64}(DiffOpt.sparse_array_representation(obj, n).terms)
+        MOI.get(model, MOI.ObjectiveSense()) == MOI.MAX_SENSE ? -cc : cc
+    end
+    cone_type, cone_dim = _cone_list(model)
+    conic_setup(model.ctx, A, Vector{Float64}(b), c, model.x, model.s, model.y, cone_type, cone_dim)
+    model.vp = Vector{Float64}(undef, length(b))
+    rc = ccall((:diffopt_b200_conic_get_vp, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), model.ctx.handle, model.vp, HOST)
+    check(model.ctx, rc)
+    model.cache_valid = true
+    return
+end
+
+function DiffOpt.forward_differentiate!(model::ConicModel)
+    model.diff_time = @elapsed begin
+        _gradient_cache(model)
+        m, n = size(model.model.constraints.coefficients)
+        objective_function = DiffOpt._convert(MOI.ScalarAffineFunction{Float64}, model.input_cache.objective)
+        dc = Vector{Float64}(DiffOpt.sparse_array_representation(objective_function, n).terms)
+        db = zeros(m)
+        DiffOpt._fill(S -> false, nothing, model.input_cache, model.model.constraints.sets, db)
+        dAi = Int[]; dAj = Int[]; dAv = Float64[]
+        DiffOpt._fill(S -> false, nothing, model.input_cache, model.model.constraints.sets, dAi, dAj, dAv)
+        # (dA packed un-negated exactly as ConicProgram.jl:296-305 does; duplicates are summed on the device)
+        r = conic_forward(model.ctx, n, m, Vector{Int64}(dAi), Vector{Int64}(dAj), dAv, db, dc;
+                          atol = model.lsqr_atol, btol = model.lsqr_btol, conlim = model.lsqr_conlim)
+        model.forw_grad_cache = CP.ForwCache(r.dz[1:n], r.dz[n+1:n+m], [r.dz[n+m+1]])
+    end
+    return nothing
+end
+
+function DiffOpt.reverse_differentiate!(model::ConicModel)
+    model.diff_time = @elapsed begin
+        _gradient_cache(model)
+        m, n = size(model.model.constraints.coefficients)
+        dx = zeros(n)
+        for (vi, value) in model.input_cache.dx
+            dx[vi.value] = value
+        end
+        r = conic_reverse(model.ctx, n, m, dx; atol = model.lsqr_atol, btol = model.lsqr_btol, conlim = model.lsqr_conlim)
+        model.back_grad_cache = CP.ReverseCache(r.g, [model.x; model.vp; 1.0])
+    end
+    return nothing
+end
+
+# getters: same arithmetic as ConicProgram.jl:396-443 on the vectors that came back from the device
+function MOI.get(model::ConicModel, ::DiffOpt.ReverseObjectiveFunction)
+    g = model.back_grad_cache.g
+    πz = model.back_grad_cache.πz
+    dc = DiffOpt.lazy_combination(-, πz, g, length(g), eachindex(model.x))
+    return DiffOpt.VectorScalarAffineFunction(dc, 0.0)
+end
+
+function MOI.get(model::ConicModel, ::DiffOpt.ForwardVariablePrimal, vi::MOI.VariableIndex)
+    i = vi.value
+    return -(model.forw_grad_cache.du[i] - model.x[i] * model.forw_grad_cache.dw[])
+end
+
+function DiffOpt._get_db(model::ConicModel, ci::MOI.ConstraintIndex{F,S}) where {F<:MOI.AbstractVectorFunction,S}
+    i = MOI.Utilities.rows(model.model.constraints, ci)
+    n = length(model.x)
+    g = model.back_grad_cache.g
+    πz = model.back_grad_cache.πz
+    return DiffOpt.lazy_combination(-, πz, g, length(g), n .+ i)
+end
+
+function DiffOpt._get_dA(model::ConicModel, ci::MOI.ConstraintIndex{<:MOI.AbstractVectorFunction})
+    i = MOI.Utilities.rows(model.model.constraints, ci)
+    n = length(model.x)
+    g = model.back_grad_cache.g
+    πz = model.back_grad_cache.πz
+    return g[n.+i] * πz[1:n]' - πz[n.+i] * g[1:n]'
 end
 
 end # module

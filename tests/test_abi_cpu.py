@@ -65,3 +65,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("oracle/", "").replace("the oracle", "") or f == "__init__.py", f
+
+
+def _build_c99_client(tmpdir):
+    capi = diffopt_b200.submodule("_capi")
+    capi.load()
+    exe = os.path.join(str(tmpdir), "c99_client")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi", "c99_client.c"), "-o", exe, "-L", libdir, "-ldiffopt_b200",
+           f"-Wl,-rpath,{libdir}", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c99_and_a_c_client_links(tmp_path):
+    """include/diffopt_b200.h compiled as C99 (-pedantic -Werror) in a translation unit that calls
+    create -> qp_batch_solve -> destroy and links against the shared library.  On a box without a GPU the client runs up
+    to the clean refusal of diffopt_b200_create (no CPU fallback); the GPU run of the same binary is in test_qp_gpu.py."""
+    exe = _build_c99_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -379,7 +379,7 @@ def test_kat14_qp_cases_through_the_conic_backend(ctx, kat):
                 ref = oqp.forward(Q, G, h, A, z, lam, nu, **full, **kw_qp)[0]
                 got = model.forward_variable_primal()[:n]
                 assert np.linalg.norm(got - ref) <= 1e-6 * max(1.0, np.linalg.norm(ref)), (name, key, "vs QP backend")
-        seed = np.concatenate([np.array(c["seed"], float), np.zeros(cp["x"].size - n)])
+        seed = np.concatenate([np.array(c.get("seed", np.ones(n)), float), np.zeros(cp["x"].size - n)])
         model.reverse_differentiate(seed)
         g = oconic.reverse(cache, seed, **tight)
         assert np.linalg.norm(model.back_grad_cache["g"] - g) <= 1e-6 * np.linalg.norm(g) + 1e-10, name

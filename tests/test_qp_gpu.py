@@ -503,3 +503,40 @@ def test_shared_parameter_gradients_batch_sum(ctx, B, n, m, p):
         want = sum(r[k] for r in refs)
         assert np.allclose(got[k], want, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(want).max(initial=0.0))), k
         assert np.array_equal(got[k], again[k])
+
+
+def test_nccl_path_on_a_single_rank_communicator(ctx):
+    """The ctx-owned NCCL communicator (diffopt_b200_nccl_unique_id / _nccl_init) and the device-resident all-reduce of
+    the shared-parameter gradients, exercised on ONE GPU (communicator of size 1: the all-reduce is the identity, but
+    NCCL is bound, initialised and launched on the ctx stream exactly as with N ranks; the N = 2 check against the
+    oracle is tests/test_multi_gpu.py and bench.py --gpus N)."""
+    qpm = diffopt_b200.submodule("qp")
+    sharding = diffopt_b200.submodule("sharding")
+    d = bench_data.qp_batch(24, shared=True, seed0=99)
+    sharding.nccl_init(ctx, 0, 1)
+    try:
+        rev, total = sharding.sharded_reverse_shared_params_device(ctx, d["Q"][0], d["G"][0], d["A"][0], d["h"], d["z"], d["lam"],
+                                                                   d["nu"], d["seed"], 0, 1)
+        plain = qpm.shared_param_grads(ctx, d["z"], d["lam"], d["nu"], rev, allreduce=True)
+    finally:
+        assert ctx.lib.diffopt_b200_nccl_destroy(ctx.h) == 0
+    want = [0.0] * 6
+    for b in range(24):
+        dz, dl, dn = oqp.reverse(d["Q"][b], d["G"][b], d["h"][b], d["A"][b], d["z"][b], d["lam"][b], d["nu"][b], d["seed"][b])
+        assert rel_err(rev[b], np.concatenate([dz, dl, dn])) <= RTOL_DIRECT
+        want = [w + x for w, x in zip(want, oqp.reverse_param_grads(d["z"][b], d["lam"][b], d["nu"][b], dz, dl, dn))]
+    for got, again, w in zip(total, plain, want):
+        assert np.allclose(got, w, rtol=1e-8, atol=1e-9) and np.array_equal(got, again)
+    # without a communicator the flag is refused, not ignored
+    with pytest.raises(diffopt_b200.DiffOptB200Error):
+        qpm.shared_param_grads(ctx, d["z"], d["lam"], d["nu"], rev, allreduce=True)
+
+
+def test_c99_client_runs_the_reference_known_answer(tmp_path):
+    """The plain-C client of tests/c_abi/c99_client.c (gcc -std=c99) drives create -> qp_batch_solve -> destroy on the GPU
+    and reproduces the reference's literals of test/quadratic_program.jl:232-293."""
+    import subprocess
+    from test_abi_cpu import _build_c99_client
+    exe = _build_c99_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "(ok)" in r.stdout, r.stdout + r.stderr

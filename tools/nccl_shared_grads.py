@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node N tools/nccl_shared_grads.py : shared-parameter reverse gradients over N GPUs.
-Each rank solves its instance shard with the CUDA library, reduces its shard's parameter gradients on the device
-and all-reduces them with NCCL; rank 0 checks the total against the CPU oracle (checker only)."""
+Each rank solves its instance shard with the CUDA library (shared Q, G, A), sums its shard's parameter gradients on the
+device and all-reduces them with the ctx-owned NCCL communicator (device resident, diffopt_b200_qp_batch_shared_grads
+with DIFFOPT_QP_ALLREDUCE); rank 0 checks the total against the CPU oracle (checker only)."""
 import os
 import sys
 
@@ -22,9 +23,9 @@ qpm = diffopt_b200.submodule("qp")
 ctx = diffopt_b200.Context(local)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 d = bench_data.qp_batch(B, shared=True, seed0=17)
-data = {k: d[k] for k in ("Q", "G", "A", "h", "z", "lam", "nu")}
-make = lambda s: qpm.QPBatch(ctx, s["Q"], s["G"], s["A"], s["h"], s["z"], s["lam"], s["nu"])
-rev, total = sh.sharded_reverse_shared_params(make, data, d["seed"], rank, world, device=dev)
+sh.nccl_init(ctx, rank, world)
+rev, total = sh.sharded_reverse_shared_params_device(ctx, d["Q"][0], d["G"][0], d["A"][0], d["h"], d["z"], d["lam"], d["nu"],
+                                                     d["seed"], rank, world)
 lo, hi = sh.shard_range(B, rank, world)
 ok = torch.ones(1, device=dev)
 if rank == 0:
