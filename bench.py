@@ -435,6 +435,13 @@ def run_b200(args, rank, world, local_rank):
 
     shared = shared_variant(args, rank, world, ctx, lib, capi, sharding, dev, db, logical, B, BT, timed, check, dptr)
     aux = active_set_sweep(args, ctx, lib, capi, dev, timed, check, dptr) if world == 1 and not args.no_aux else None
+    if aux is not None:
+        # second half of the BASELINE.json metric ("sparse solve ms"): config 3, one sparse KKT system with 256 right-hand sides
+        try:
+            import bench_aux
+            aux["sparse_config3"] = bench_aux.config3(ctx, cpu=not args.no_cpu)
+        except Exception as e:  # the headline line must survive a failure here
+            aux["sparse_config3"] = {"error": str(e)[:300]}
 
     if rank != 0:
         if world > 1:

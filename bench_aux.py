@@ -42,8 +42,14 @@ def run_conic(ctx, name, d, iters, cpu_iters):
     cm = diffopt_b200.submodule("conic")
     model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
     model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
-    model.tolerances = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=iters)
+    if iters is None:      # the reference's defaults, to convergence
+        sq = float(np.sqrt(np.finfo(float).eps))
+        model.tolerances = dict(atol=sq, btol=sq, conlim=1 / sq, maxiter=None)
+    else:
+        model.tolerances = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=iters)
     model.reverse_differentiate(d["seed"])            # warm-up (includes setup)
+    if iters is None:
+        iters = model.last_stats["itn"]
     setup_ms = model.setup_ms
     ms = []
     for _ in range(3):
@@ -62,7 +68,19 @@ def run_conic(ctx, name, d, iters, cpu_iters):
             "istop": model.last_stats["istop"], "rnorm": model.last_stats["rnorm"]}
     line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
     line["working_set_MB"] = (12 * 2 * nnzA + 8 * 8 * N) / 1e6
-    if cpu_iters:
+    if cpu_iters is None:
+        cache = oconic.gradient_cache(d["A"], d["b"], d["c"], d["x"], d["s"], d["y"], d["cone_types"], d["cone_dims"])
+        dz = np.concatenate([d["seed"], np.zeros(m), [-(d["x"] @ d["seed"])]])
+        t0 = time.perf_counter()
+        ref = spla.lsqr(sp.csr_matrix(cache.M), dz, atol=model.tolerances["atol"], btol=model.tolerances["btol"],
+                        conlim=model.tolerances["conlim"], iter_lim=N)
+        dt = time.perf_counter() - t0
+        g = model.back_grad_cache["g"]
+        line["converged"] = {"gpu_iterations": iters, "cpu_iterations": int(ref[2]), "gpu_istop": model.last_stats["istop"],
+                             "cpu_istop": int(ref[1]), "rel_err_vs_cpu_lsqr": float(np.linalg.norm(g - ref[0]) / np.linalg.norm(ref[0]))}
+        line["cpu_baseline"] = {"ms": 1e3 * dt, "us_per_iteration": 1e6 * dt / max(int(ref[2]), 1), "kind": "port", "cores": 1,
+                                "sample": "scipy.sparse.linalg.lsqr on the explicit M to convergence at the same tolerances"}
+    elif cpu_iters:
         cache = oconic.gradient_cache(d["A"], d["b"], d["c"], d["x"], d["s"], d["y"], d["cone_types"], d["cone_dims"]) \
             if hasattr(oconic, "gradient_cache") else None
         if cache is not None:
@@ -76,9 +94,76 @@ def run_conic(ctx, name, d, iters, cpu_iters):
     print(json.dumps(line), flush=True)
 
 
+def config3(ctx, portfolio=False, nrhs=256, cpu=True):
+    """BASELINE config 3: ONE sparse KKT system (MPC QP, N = 240 000; or the portfolio arrowhead, N = 200 201), 256
+    forward directions against one factorisation.  Device times are the library's own CUDA-event brackets
+    (factorisation: all level launches; solve: both sweeps, right-hand sides resident in HBM)."""
+    import scipy.sparse.linalg as spla
+    import torch
+    import diffopt_b200
+    import bench_data
+    lsq = diffopt_b200.submodule("lsqr")
+    capi = diffopt_b200.submodule("_capi")
+    if portfolio:
+        d = bench_data.portfolio_config3()
+        name = f"3p: sparse portfolio QP (n={d['n']}, m={d['m']}, p={d['p']}): arrowhead KKT"
+    else:
+        T = int(os.environ.get("DIFFOPT_AUX_MPC_T", 10_000))
+        d = bench_data.mpc_config3(T=T)
+        name = f"3: sparse MPC QP T={T} (n={d['n']}, m={d['m']}, p={d['p']})"
+    K = d["K"]
+    N = K.shape[0]
+    rng = np.random.default_rng(33)
+    R = np.zeros((N, nrhs), order="F")
+    R[rng.integers(0, N, size=8 * nrhs), np.repeat(np.arange(nrhs), 8)] = rng.standard_normal(8 * nrhs)   # sparse directions
+    t0 = time.perf_counter()
+    F = lsq.SparseFactorization(ctx, K, trans=True)           # forward mode solves with LHS' (:438)
+    setup_wall_ms = 1e3 * (time.perf_counter() - t0)
+    F2 = lsq.SparseFactorization(ctx, K, trans=True)          # second run: buffers allocated, kernels loaded
+    factor_ms = F2.factor_ms
+    dev = torch.device("cuda", ctx.device)
+    Rd = torch.from_numpy(np.ascontiguousarray(R.T)).to(dev)  # (nrhs, N) row-major == N x nrhs column-major
+    Xd = torch.empty_like(Rd)
+    ms = []
+    for _ in range(5):
+        ctx.check(ctx.lib.diffopt_b200_sparse_solve(ctx.h, nrhs, capi.vp(Rd.data_ptr()), capi.vp(Xd.data_ptr()), capi.DEVICE))
+        ms.append(ctx.last_kernel_ms)
+    solve_ms = min(ms[1:])
+    X = np.asfortranarray(Xd.cpu().numpy().T)
+    res = float((np.linalg.norm(K.T @ X[:, :8] - R[:, :8], axis=0) / np.linalg.norm(R[:, :8], axis=0)).max())
+    st = F2.stats
+    solve_bytes = 2 * 12 * st["nnz_lu"] + 2 * N * nrhs * 8      # SURVEY 8(d): (nnz L + nnz U) * 12 per sweep pair + 2 N nrhs 8
+    line = {"config": name + f", N={N}, nnz={K.nnz}, {nrhs} forward directions, one factorisation",
+            "method": st["method"], "fronts": st["fronts"], "tree_levels": st["levels"], "largest_front": st["max_front"],
+            "nnz_LU_stored": st["nnz_lu"], "factor_flop": st["factor_flops"], "delayed_pivot_repeats": st["delayed_pivot_retries"],
+            "analysis_host_ms": st["analysis_ms"], "factor_device_ms": factor_ms, "solve_device_ms": solve_ms,
+            "total_device_ms": factor_ms + solve_ms, "first_setup_wall_ms_incl_host_analysis_and_h2d": setup_wall_ms,
+            "factor_tflops": st["factor_flops"] / (factor_ms * 1e-3) / 1e12,
+            "max_rel_residual_first_8_columns": res,
+            "roofline": {"bound": "hbm", "kernel": "multi-RHS solve (both sweeps)", "achieved": solve_bytes / (solve_ms * 1e-3) / 1e9,
+                         "peak": hbm_peak(), "unit": "GB/s", "algorithmic_bytes": solve_bytes,
+                         "note": "SURVEY 8(d) bytes: factors once per sweep pair + the N x nrhs block read and written once; "
+                                 "the implementation moves the block four times (b -> y -> x), so 0.5 is its ceiling"}}
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+    if cpu:
+        # CPU: factor once + 256 columns; reference-faithful (refactorise per direction) extrapolated from 4 directions
+        Kt = K.T.tocsc()
+        t0 = time.perf_counter(); lu = spla.splu(Kt); f_ms = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter(); Xc = lu.solve(np.ascontiguousarray(R[:, :32])); s_ms = 1e3 * (time.perf_counter() - t0) * (nrhs / 32)
+        t0 = time.perf_counter()
+        for k in range(2):
+            spla.splu(Kt).solve(R[:, k])
+        faithful_ms = 1e3 * (time.perf_counter() - t0) / 2 * nrhs
+        line["rel_err_vs_superlu_32_columns"] = float((np.linalg.norm(X[:, :32] - Xc, axis=0) / np.linalg.norm(Xc, axis=0)).max())
+        line["cpu_baseline"] = {"factor_ms": f_ms, "solve_256_ms_extrapolated_from_32": s_ms, "total_ms": f_ms + s_ms,
+                                "reference_faithful_ms_extrapolated_from_2": faithful_ms, "kind": "port", "cores": 1,
+                                "sample": "scipy splu (SuperLU stands in for UMFPACK); faithful = one factorisation per direction as QuadraticProgram.jl:438"}
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,3,4,4x,5")
+    ap.add_argument("--configs", default="1,3,3p,4,4c,4x,5")
     args = ap.parse_args()
     import bench_data
     import diffopt_b200
@@ -112,46 +197,16 @@ def main():
                                            "sample": "scipy.sparse.linalg.lsqr on the CSC KKT matrix"},
                           "note": "N=300: launch/grid-sync latency bound, no roofline claim"}), flush=True)
     if "3" in todo:
-        import scipy.sparse.linalg as spla
-        lsq = diffopt_b200.submodule("lsqr")
-        T, nrhs = int(os.environ.get("DIFFOPT_AUX_MPC_T", 10_000)), 256
-        d = bench_data.mpc_config3(T=T)
-        K = d["K"]
-        N = K.shape[0]
-        rng = np.random.default_rng(33)
-        R = np.zeros((N, nrhs), order="F")
-        R[rng.integers(0, N, size=8 * nrhs), np.repeat(np.arange(nrhs), 8)] = rng.standard_normal(8 * nrhs)   # sparse directions
-        t0 = time.perf_counter()
-        F = lsq.SparseFactorization(ctx, K, trans=True)           # forward mode solves with LHS' (:438)
-        setup_wall_ms = 1e3 * (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        X = F.solve(R)
-        solve_wall_ms = 1e3 * (time.perf_counter() - t0)
-        res = float((np.linalg.norm(K.T @ X[:, :8] - R[:, :8], axis=0) / np.linalg.norm(R[:, :8], axis=0)).max())
-        ldab = 3 * F.bandwidth + 1
-        line = {"config": f"3: sparse MPC QP T={T} (n={d['n']}, m={d['m']}, p={d['p']}, N={N}, nnz={K.nnz}), {nrhs} forward directions, one factorisation",
-                "bandwidth_after_rcm": F.bandwidth, "factor_device_ms": F.factor_ms, "solve_device_ms": F.solve_ms,
-                "total_device_ms": F.factor_ms + F.solve_ms, "setup_wall_ms_incl_host_rcm_and_h2d": setup_wall_ms,
-                "solve_wall_ms_incl_h2d_d2h": solve_wall_ms, "max_rel_residual_first_8_columns": res,
-                "solve_bytes": {"algorithmic": 2 * N * ldab * 8 * ((nrhs + 7) // 8) + 4 * N * nrhs * 8,
-                                "note": "band factors are re-read from L2/HBM once per CTA of 8 right-hand sides per sweep"}}
-        line["solve_hbm_gbs"] = line["solve_bytes"]["algorithmic"] / (F.solve_ms * 1e-3) / 1e9
-        # CPU: factor once + 256 columns; reference-faithful (refactorise per direction) extrapolated from 4 directions
-        Kt = K.T.tocsc()
-        t0 = time.perf_counter(); lu = spla.splu(Kt); f_ms = 1e3 * (time.perf_counter() - t0)
-        t0 = time.perf_counter(); Xc = lu.solve(np.ascontiguousarray(R[:, :32])); s_ms = 1e3 * (time.perf_counter() - t0) * (nrhs / 32)
-        t0 = time.perf_counter()
-        for k in range(4):
-            spla.splu(Kt).solve(R[:, k])
-        faithful_ms = 1e3 * (time.perf_counter() - t0) / 4 * nrhs
-        line["rel_err_vs_superlu_32_columns"] = float((np.linalg.norm(X[:, :32] - Xc, axis=0) / np.linalg.norm(Xc, axis=0)).max())
-        line["cpu_baseline"] = {"factor_ms": f_ms, "solve_256_ms_extrapolated_from_32": s_ms, "total_ms": f_ms + s_ms,
-                                "reference_faithful_ms_extrapolated_from_4": faithful_ms, "kind": "port", "cores": 1,
-                                "sample": "scipy splu (SuperLU stands in for UMFPACK); faithful = one factorisation per direction as QuadraticProgram.jl:438"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(config3(ctx)), flush=True)
+    if "3p" in todo:
+        print(json.dumps(config3(ctx, portfolio=True)), flush=True)
     if "4" in todo:
         run_conic(ctx, "4: conic n=5000 m=7500 (zeros 500 + nonneg 4000 + 300 x SOC(10)), reverse, matrix-free M",
                   bench_data.conic_config4(), iters=2000, cpu_iters=300)
+    if "4c" in todo:
+        d = bench_data.conic_config4_conditioned()
+        run_conic(ctx, "4c: config 4 on the well-conditioned generator (75 % of the nonnegative rows active, solution scaled 0.02: "
+                       "cond(M) ~ 1e4), reverse, the reference's default LSQR tolerances to convergence", d, iters=None, cpu_iters=None)
     if "4x" in todo:
         run_conic(ctx, "4x: config-4 generator scaled 200x (n=1e6, m=1.5e6, nnz(A)=1.5e7): A exceeds L2",
                   bench_data.conic_config4(n=1_000_000, n_zero=100_000, n_nonneg=800_000, n_soc=60_000), iters=200, cpu_iters=0)

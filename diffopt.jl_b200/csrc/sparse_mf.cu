@@ -337,11 +337,9 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
     const MfFront fr = fronts[fid];
     const int k = fr.k, s = fr.s, nf = k + s;
     const int tid = threadIdx.x, col = blockIdx.y * MF_LEAF_TC + tid;
-    double* Ls = mf_smem;  // row r of the L panel at Ls[r * KMAX .. ], columns >= k zero
-    for (int i = tid; i < nf * MF_KMAX; i += MF_LEAF_TC) {
-        const int r = i / MF_KMAX, c = i % MF_KMAX;
-        Ls[i] = (c < k && (r >= k || c < r)) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
-    }
+    constexpr int LDT = MF_KMAX + 1;       // tile leading dimension: conflict-free both ways
+    double* Ts = mf_smem;                  // [column][row] tile of b (first), then the L panel (same storage)
+    double* Ls = mf_smem;                  // row r of the L panel at Ls[r * KMAX .. ], columns >= k zero
     if (tid == 0) {  // net effect of the row interchanges: position r of P b comes from row src[r]
         int src[MF_KMAX];
         for (int r = 0; r < k; ++r) src[r] = r;
@@ -354,11 +352,24 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
         for (int r = 0; r < k; ++r) rows[r] = perm[fr.first + src[r]];
     }
     __syncthreads();
-    if (col >= nrhs) return;
+    // rows of this front from the caller's column-major block: consecutive threads take consecutive rows of one
+    // column (the front's rows are sorted runs of the original numbering), transposed through shared memory
+    const int c0 = blockIdx.y * MF_LEAF_TC, ncol = min(MF_LEAF_TC, nrhs - c0);
+    for (int idx = tid; idx < k * ncol; idx += MF_LEAF_TC) {
+        const int r = idx % k, c = idx / k;
+        Ts[c * LDT + r] = B[(size_t)rows[r] + (size_t)N * (c0 + c)];
+    }
+    __syncthreads();
     double y[MF_KMAX];
-    const double* b = B + (size_t)N * col;
 #pragma unroll
-    for (int r = 0; r < MF_KMAX; ++r) y[r] = r < k ? b[rows[r]] : 0.0;
+    for (int r = 0; r < MF_KMAX; ++r) y[r] = (r < k && tid < ncol) ? Ts[tid * LDT + r] : 0.0;
+    __syncthreads();
+    for (int i = tid; i < nf * MF_KMAX; i += MF_LEAF_TC) {
+        const int r = i / MF_KMAX, c = i % MF_KMAX;
+        Ls[i] = (c < k && (r >= k || c < r)) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
+    }
+    __syncthreads();
+    if (col >= nrhs) return;
 #pragma unroll
     for (int i = 1; i < MF_KMAX; ++i) {  // unit-lower L11 (block-uniform guard: rows >= k belong to L21)
         if (i >= k) break;
@@ -416,8 +427,8 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int*
         if (tid < k) rows[tid] = perm[fr.first + tid];
     }
     __syncthreads();
-    if (col >= nrhs) return;
     double y[MF_KMAX];
+    if (col < nrhs) {
     const double* yi = Y + (size_t)fr.first * nrhs + col;
 #pragma unroll
     for (int r = 0; r < MF_KMAX; ++r) y[r] = r < k ? yi[(size_t)r * nrhs] : 0.0;
@@ -445,10 +456,23 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int*
         }
         y[i] = (acc + acc2) * rdiag[i];
     }
-    double* x = X + (size_t)N * col;
+    }
+    // solution rows back into the caller's column-major block through a shared-memory transpose (same access shape
+    // as the gather of the forward sweep)
+    constexpr int LDT = MF_KMAX + 1;
+    double* Ts = mf_smem;
+    __syncthreads();   // every thread is done with the panels
+    if (col < nrhs) {
 #pragma unroll
-    for (int r = 0; r < MF_KMAX; ++r)
-        if (r < k) x[rows[r]] = y[r];
+        for (int r = 0; r < MF_KMAX; ++r)
+            if (r < k) Ts[tid * LDT + r] = y[r];
+    }
+    __syncthreads();
+    const int c0 = blockIdx.y * MF_LEAF_TC, ncol = min(MF_LEAF_TC, nrhs - c0);
+    for (int idx = tid; idx < k * ncol; idx += MF_LEAF_TC) {
+        const int r = idx % k, c = idx / k;
+        X[(size_t)rows[r] + (size_t)N * (c0 + c)] = Ts[c * LDT + r];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -505,8 +529,14 @@ struct Dissector {
         snodes.push_back(verts);
     }
 
+    // Separators of `group_levels` consecutive dissection levels are collected into ONE front (relaxed amalgamation of
+    // the small separator fronts: a tree level costs a kernel launch per sweep, the extra fill is a few dense blocks of
+    // separator size).  `sink`: the collecting front of the enclosing group (nullptr: the next cut opens a new group),
+    // `remaining`: dissection levels the enclosing group still absorbs.
+    int group_levels = 3;
+
     // orders all vertices of `verts` (all carrying region id rid)
-    void dissect(std::vector<int32_t>& verts, int32_t rid) {
+    void dissect(std::vector<int32_t>& verts, int32_t rid, std::vector<int32_t>* sink = nullptr, int remaining = 0) {
         // connected components
         std::vector<std::vector<int32_t>> comps;
         for (int32_t v0 : verts) {
@@ -532,13 +562,13 @@ struct Dissector {
             }
             const int32_t cid = next_region++;
             for (int32_t v : comp) region[(size_t)v] = cid;
-            split(comp, cid);
+            split(comp, cid, sink, remaining);
         }
         if (!bin.empty()) emit(bin);
     }
 
     // connected region larger than a leaf: level-structure bisection
-    void split(std::vector<int32_t>& comp, int32_t rid) {
+    void split(std::vector<int32_t>& comp, int32_t rid, std::vector<int32_t>* sink, int remaining) {
         // pseudo-peripheral start: repeat BFS from a vertex of the last level
         int32_t start = comp[0];
         int nl = 0;
@@ -594,9 +624,19 @@ struct Dissector {
         for (int32_t v : lo) region[(size_t)v] = rlo;
         for (int32_t v : hi) region[(size_t)v] = rhi;
         for (int32_t v : sep) region[(size_t)v] = rsep;
-        dissect(lo, rlo);
-        dissect(hi, rhi);
-        emit(sep);
+        if (sink && remaining > 0) {  // inside a group: the separator joins the group's front
+            for (int32_t v : sep) region[(size_t)v] = -1;
+            sink->insert(sink->end(), sep.begin(), sep.end());
+            dissect(lo, rlo, sink, remaining - 1);
+            dissect(hi, rhi, sink, remaining - 1);
+            return;
+        }
+        std::vector<int32_t> group;   // this cut opens a group: its separator + those of the next group_levels - 1 levels
+        for (int32_t v : sep) region[(size_t)v] = -1;
+        dissect(lo, rlo, &group, group_levels - 1);
+        dissect(hi, rhi, &group, group_levels - 1);
+        group.insert(group.end(), sep.begin(), sep.end());
+        emit(group);
     }
 };
 
@@ -936,6 +976,7 @@ bool mf_order(int64_t N, const int64_t* colptr, const int64_t* rowval, const dou
     {
         Dissector D(gc, leaf);
         D.weight = &cw;
+        if (const char* gl = getenv("DIFFOPT_B200_MF_GROUP")) D.group_levels = std::max(1, atoi(gl));
         const double dense_deg = std::max(40.0, 10.0 * std::sqrt((double)N));
         std::vector<int32_t> dense, rest;
         for (int64_t c = 0; c < gc.N; ++c) {
@@ -1157,7 +1198,7 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
         const size_t smem = smem_fwd(L);
         const bool big = L.big || smem > MF_SMEM_CAP;
         if (leaf_group(L)) {
-            const size_t ls = sizeof(double) * (size_t)L.max_nf * MF_KMAX;
+            const size_t ls = sizeof(double) * std::max<size_t>((size_t)L.max_nf * MF_KMAX, (size_t)MF_LEAF_TC * (MF_KMAX + 1));
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ls, 1024)));
             mf_forward_leaf_kernel<<<dim3((unsigned)L.count, ltiles), MF_LEAF_TC, ls, ctx->stream>>>(
                 M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.perm.as<int>(), M.piv.as<int>(), M.Lp.as<double>(),
@@ -1183,7 +1224,7 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
         const size_t smem = smem_bwd(L);
         const bool big = L.big || smem > MF_SMEM_CAP || smem_fwd(L) > MF_SMEM_CAP;
         if (leaf_group(L)) {
-            const size_t ls = sizeof(double) * (size_t)(MF_KMAX + L.max_s) * MF_KMAX;
+            const size_t ls = sizeof(double) * std::max<size_t>((size_t)(MF_KMAX + L.max_s) * MF_KMAX, (size_t)MF_LEAF_TC * (MF_KMAX + 1));
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_backward_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ls, 1024)));
             mf_backward_leaf_kernel<<<dim3((unsigned)L.count, ltiles), MF_LEAF_TC, ls, ctx->stream>>>(
                 M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.strct.as<int>(), M.perm.as<int>(), M.Lp.as<double>(),
