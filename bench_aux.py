@@ -94,6 +94,54 @@ def run_conic(ctx, name, d, iters, cpu_iters):
     print(json.dumps(line), flush=True)
 
 
+def run_conic_batch(ctx, B=512, iters=100, ctas=1):
+    """SURVEY 8(d) config 4 in its HBM-meaningful form: a lock-step batch of B independent config-4-sized problems (own
+    sparsity, solution and seed each) advanced by one persistent kernel.  Fixed iteration count so the algorithmic bytes
+    are exact; parity of the batch against single-problem solves is tests/test_conic_gpu.py's business."""
+    import bench_data
+    import diffopt_b200
+    cm = diffopt_b200.submodule("conic")
+    t0 = time.perf_counter()
+    models, seeds, nnzA = [], [], 0
+    for k in range(B):
+        d = bench_data.conic_config4(seed=4000 + k)
+        mdl = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+        mdl.set_variable_primal(d["x"]); mdl.set_constraint_primal(d["s"]); mdl.set_constraint_dual(d["y"])
+        models.append(mdl); seeds.append(d["seed"]); nnzA += d["A"].nnz
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    batch = cm.ConicBatch(ctx, models, ctas_per_problem=ctas)
+    setup_s = time.perf_counter() - t0
+    batch.tolerances = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=iters)
+    seeds = np.stack(seeds)
+    out = batch.reverse_differentiate(seeds)
+    ms = []
+    for _ in range(3):
+        out = batch.reverse_differentiate(seeds)
+        ms.append(batch.kernel_ms)
+    ms = min(ms)
+    n, m = batch.n, batch.m
+    N = n + m + 1
+    nnzM = 2 * nnzA + B * (2 * n + 3 * m)
+    by = 2 * (12 * nnzM + 4 * B * (N + 1)) + 88 * N * B
+    # spot parity: problem 0 through the single-problem path at the same iteration count
+    mdl = models[0]
+    mdl.tolerances = batch.tolerances
+    mdl.reverse_differentiate(seeds[0])
+    g1 = mdl.back_grad_cache["g"]
+    line = {"config": f"4b: lock-step batch of {B} independent config-4 problems (n=5000, m=7500 each), reverse, {iters} LSQR "
+                      f"iterations each, one persistent kernel, {ctas} CTA(s) per problem",
+            "B": B, "lsqr_iterations": iters, "device_ms": ms, "us_per_lockstep_iteration": 1e3 * ms / iters,
+            "problem_iterations_per_s": B * iters / (ms * 1e-3), "single_problem_us_per_iteration": 1e3 * mdl.last_stats["kernel_ms"] / iters,
+            "roofline": {"bound": "hbm", "achieved": by * iters / (ms * 1e-3) / 1e9, "peak": hbm_peak(), "unit": "GB/s",
+                         "algorithmic_bytes_per_lockstep_iteration": by},
+            "working_set_MB": (12 * 2 * nnzA + 8 * 8 * N * B) / 1e6,
+            "rel_diff_problem0_vs_single_problem_path": float(np.linalg.norm(out["g"][0] - g1) / np.linalg.norm(g1)),
+            "host_generate_s": gen_s, "batch_setup_s": setup_s}
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+    print(json.dumps(line), flush=True)
+
+
 def config3(ctx, portfolio=False, nrhs=256, cpu=True):
     """BASELINE config 3: ONE sparse KKT system (MPC QP, N = 240 000; or the portfolio arrowhead, N = 200 201), 256
     forward directions against one factorisation.  Device times are the library's own CUDA-event brackets
@@ -207,6 +255,10 @@ def main():
         d = bench_data.conic_config4_conditioned()
         run_conic(ctx, "4c: config 4 on the well-conditioned generator (75 % of the nonnegative rows active, solution scaled 0.02: "
                        "cond(M) ~ 1e4), reverse, the reference's default LSQR tolerances to convergence", d, iters=None, cpu_iters=None)
+    for key in todo:
+        if key.startswith("4b"):      # 4b, 4b:B, 4b:B:ctas
+            parts = key.split(":")
+            run_conic_batch(ctx, B=int(parts[1]) if len(parts) > 1 else 512, ctas=int(parts[2]) if len(parts) > 2 else 1)
     if "4x" in todo:
         run_conic(ctx, "4x: config-4 generator scaled 200x (n=1e6, m=1.5e6, nnz(A)=1.5e7): A exceeds L2",
                   bench_data.conic_config4(n=1_000_000, n_zero=100_000, n_nonneg=800_000, n_soc=60_000), iters=200, cpu_iters=0)

@@ -161,3 +161,39 @@ class ConicModel:
         vp = self.vp()
         rows = np.atleast_1d(rows)
         return np.outer(g[n + rows], self.x) - np.outer(vp[rows], g[:n])
+
+
+class ConicBatch:
+    """Lock-step batch of ``ConicModel``s of equal size (``diffopt_b200_conic_batch_*``): the reference differentiates one
+    problem per ``reverse_differentiate!`` call (ConicProgram.jl:336-394); a training loop makes that call once per
+    sample of a minibatch.  Here every problem is analysed as usual and ONE persistent kernel advances all the LSQR
+    solves -- each with its own operator, stop tests and iteration count."""
+
+    def __init__(self, ctx: Context, models, ctas_per_problem=1):
+        self.ctx = ctx
+        self.models = list(models)
+        self.B = len(self.models)
+        self.n, self.m = self.models[0].n, self.models[0].m
+        self.tolerances = dict(DEFAULTS, maxiter=None)
+        ctx.check(ctx.lib.diffopt_b200_conic_batch_begin(ctx.h, self.B, int(ctas_per_problem)))
+        for mdl in self.models:
+            colptr, rowval, nzval = julia_csc(mdl.A)
+            ctx.check(ctx.lib.diffopt_b200_conic_batch_add(
+                ctx.h, mdl.n, mdl.m, ptr(colptr), ptr(rowval), ptr(nzval), ptr(mdl.b), ptr(mdl.c), ptr(mdl.x), ptr(mdl.s),
+                ptr(mdl.y), len(mdl.cone_types), ptr(mdl.cone_types), ptr(mdl.cone_dims), HOST))
+
+    def reverse_differentiate(self, dx_seeds):
+        """dx_seeds: (B, n).  Returns dict(g (B, n+m+1), dc (B, n), db (B, m), stats (B, 4))."""
+        B, n, m = self.B, self.n, self.m
+        seeds = np.ascontiguousarray(dx_seeds, dtype=np.float64).reshape(B, n)
+        g = np.empty((B, n + m + 1))
+        dc = np.empty((B, n))
+        db = np.empty((B, m))
+        stats = np.zeros((B, 4))
+        t = self.tolerances
+        rc = self.ctx.lib.diffopt_b200_conic_batch_reverse(
+            self.ctx.h, ptr(seeds), t["atol"], t["btol"], t["conlim"], 0 if t["maxiter"] is None else int(t["maxiter"]),
+            ptr(g), ptr(dc), ptr(db), ptr(stats), HOST)
+        self.ctx.check(rc)
+        self.kernel_ms = self.ctx.last_kernel_ms
+        return dict(g=g, dc=dc, db=db, stats=stats)

@@ -39,6 +39,18 @@ static void release_csr(CsrDev& c) {
     for (DevBuf* b : {&c.sval, &c.scol, &c.spos, &c.t_sval, &c.t_scol, &c.t_spos}) b->release(); c.cblk.release(); c.t_cblk.release(); c.gblk.release(); c.t_gblk.release();
 }
 
+}  // extern "C"
+
+void conic_state_release(ConicState& c) {
+    release_csr(c.A);
+    for (DevBuf* b : {&c.b, &c.c, &c.x, &c.s, &c.y, &c.v, &c.vp, &c.row_kind, &c.nn_scale, &c.soc_off, &c.soc_dim,
+                      &c.soc_case, &c.soc_nx, &c.psd_off, &c.psd_d, &c.psd_uoff, &c.psd_U, &c.psd_Bm, &c.psd_ident,
+                      &c.psd_work, &c.psd_lam, &c.psd_loff, &c.psd_toff, &c.w1, &c.w2, &c.w3})
+        b->release();
+}
+
+extern "C" {
+
 int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {
     if (!ctx) return -1;
     DeviceGuard guard_(ctx->device);
@@ -54,17 +66,13 @@ int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {
         if (ev) cudaEventDestroy(ev);
     QpBatchState& q = ctx->qp;
     q.Q.release(); q.G.release(); q.A.release(); q.h.release(); q.z.release(); q.lam.release(); q.nu.release();
-    ConicState& c = ctx->conic;
-    release_csr(c.A);
-    for (DevBuf* b : {&c.b, &c.c, &c.x, &c.s, &c.y, &c.v, &c.vp, &c.row_kind, &c.nn_scale, &c.soc_off, &c.soc_dim,
-                      &c.soc_case, &c.soc_nx, &c.psd_off, &c.psd_d, &c.psd_uoff, &c.psd_U, &c.psd_Bm, &c.psd_ident,
-                      &c.psd_work, &c.psd_lam, &c.psd_loff, &c.psd_toff, &c.w1, &c.w2, &c.w3})
-        b->release();
+    conic_state_release(ctx->conic);
     LsqrWork& l = ctx->lsqr;
     for (DevBuf* b : {&l.u, &l.v, &l.w, &l.x, &l.tmp, &l.scal}) b->release();
     release_csr(ctx->lsqr_mat);
     for (DevBuf* b : {&ctx->sparse.AB, &ctx->sparse.ipiv, &ctx->sparse.perm, &ctx->sparse.work}) b->release();
     sparse_mf_release(ctx);
+    conic_batch_release(ctx);
     nccl_release(ctx);
     ctx->qp_unpacked[0].release();
     ctx->qp_unpacked[1].release();

@@ -92,6 +92,10 @@ struct SparseBandState {
 struct NcclUniqueIdBytes { char internal[128]; };  // ncclUniqueId (nccl.h), passed by value to ncclCommInitRank
 void nccl_release(struct diffopt_b200_ctx* ctx);
 
+void conic_state_release(struct ConicState& c);
+struct ConicBatchImpl;  // lock-step batch of conic problems (conic.cu)
+void conic_batch_release(struct diffopt_b200_ctx* ctx);
+
 struct SparseMfImpl;  // multifrontal factorisation kept by diffopt_b200_sparse_setup (sparse_mf.cu)
 void sparse_mf_release(struct diffopt_b200_ctx* ctx);
 
@@ -137,6 +141,8 @@ struct diffopt_b200_ctx {
     void* nccl_comm = nullptr;    // ncclComm_t of diffopt_b200_nccl_init (one rank per ctx)
     int nccl_ranks = 0, nccl_rank = 0;
     DevBuf qp_unpacked[2];        // Q / dQ expanded from packed lower triangles (qp_batch_solve_ex)
+    ConicBatchImpl* conic_batch = nullptr;
+    int csr_cluster_ctas = 0;     // CTAs the cluster-kernel row blocks of csr_from_csc_host are cut for (0: default 16)
     SparseMfImpl* sparse_mf = nullptr;
     int sparse_method = 0;        // factorisation currently held: 0 none, 1 banded LU (RCM), 2 multifrontal LU
     int64_t sparse_N = 0;

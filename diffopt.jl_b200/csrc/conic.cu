@@ -165,6 +165,62 @@ __global__ void conic_rev_getters_kernel(int n, int m, const double* __restrict_
     }
 }
 
+// ---- lock-step batch (diffopt_b200_conic_batch_*) ----------------------------------------------------------------
+// Per-problem pointers the batched right-hand-side / getter kernels need (the operator itself travels as OpArgs).
+struct ConicBatchPtrs {
+    const double* x;
+    const double* vp;
+};
+
+// One CTA per problem: rhs_p = [dx_p; 0; -x_p'dx_p]  (ConicProgram.jl:363-367 with dy = ds = 0) at the head of the
+// problem's work region; the norm test of :369 is made by the LSQR kernel itself (zero_below).
+__global__ void conic_rev_rhs_batch_kernel(int n, int m, const double* __restrict__ seeds, const ConicBatchPtrs* __restrict__ pp,
+                                           double* work, size_t stride) {
+    __shared__ double red[32];
+    const int p = blockIdx.x;
+    const double* dx = seeds + (size_t)p * n;
+    const double* x = pp[p].x;
+    double* dz = work + (size_t)p * stride;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = dx[i];
+        dz[i] = d;
+        acc -= x[i] * d;
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) dz[n + i] = 0.0;
+    for (int q = 16; q > 0; q >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < blockDim.x / 32; ++w) s += red[w];
+        dz[n + m] = s;
+    }
+}
+
+// g_p (the problem's x region), getters dc_p = g[1:n] - g[N] x, db_p = g[n+I] - g[N] vp (:396-428) and the LSQR
+// statistics, gathered into the caller's instance-major arrays.
+__global__ void conic_rev_out_batch_kernel(int n, int m, const ConicBatchPtrs* __restrict__ pp, const double* __restrict__ work,
+                                           size_t stride, size_t stats_off, double* g_out, double* dc, double* db, double* stats) {
+    const int p = blockIdx.y;
+    const int N = n + m + 1;
+    const double* g = work + (size_t)p * stride + (size_t)(N + 1);
+    const double gN = g[n + m];
+    const double* x = pp[p].x;
+    const double* vp = pp[p].vp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const double gi = g[i];
+        if (g_out) g_out[(size_t)p * N + i] = gi;
+        if (i < n) {
+            if (dc) dc[(size_t)p * n + i] = gi - gN * x[i];
+        } else if (i < n + m) {
+            if (db) db[(size_t)p * m + (i - n)] = gi - gN * vp[i - n];
+        }
+    }
+    if (stats && blockIdx.x == 0 && threadIdx.x < 4)
+        stats[(size_t)p * 4 + threadIdx.x] = work[(size_t)p * stride + stats_off + threadIdx.x];
+}
+
 int32_t to_host_copy(diffopt_b200_ctx* ctx, const void* src, size_t bytes, int memspace, std::vector<char>& tmp,
                      const void** host) {
     if (memspace == DIFFOPT_B200_HOST) {
@@ -498,6 +554,126 @@ int32_t diffopt_b200_conic_reverse(diffopt_b200_ctx* ctx, const double* dx_seed,
         if (memspace == DIFFOPT_B200_HOST) memcpy(out_stats, st, d8 * 4);
         else DO_CUDA(ctx, cudaMemcpy(out_stats, st, d8 * 4, cudaMemcpyHostToDevice));
     }
+    return 0;
+}
+
+}  // extern "C"
+
+// Problems of a lock-step batch (every one a full conic_setup state) and the launch's work area.
+struct ConicBatchImpl {
+    std::vector<ConicState> states;
+    int64_t B = 0, n = 0, m = 0;
+    int C = 1;
+    DevBuf work, ops, vecs, rhs, ptrs;
+};
+
+void conic_batch_release(diffopt_b200_ctx* ctx) {
+    ConicBatchImpl* b = ctx->conic_batch;
+    if (!b) return;
+    for (ConicState& s : b->states) conic_state_release(s);
+    for (DevBuf* d : {&b->work, &b->ops, &b->vecs, &b->rhs, &b->ptrs}) d->release();
+    delete b;
+    ctx->conic_batch = nullptr;
+}
+
+extern "C" {
+
+int32_t diffopt_b200_conic_batch_begin(diffopt_b200_ctx* ctx, int64_t B, int32_t ctas_per_problem) {
+    if (!ctx) return -1;
+    DeviceGuard guard_(ctx->device);
+    if (B <= 0) BAD_ARG(ctx, "conic_batch_begin: the batch must hold at least one problem");
+    if (ctas_per_problem < 0 || ctas_per_problem > 16) BAD_ARG(ctx, "conic_batch_begin: ctas_per_problem must be 0 (default) .. 16");
+    conic_batch_release(ctx);
+    ctx->conic_batch = new ConicBatchImpl();
+    ctx->conic_batch->B = B;
+    ctx->conic_batch->C = ctas_per_problem > 0 ? ctas_per_problem : 1;
+    ctx->conic_batch->states.reserve((size_t)B);
+    return 0;
+}
+
+int32_t diffopt_b200_conic_batch_add(diffopt_b200_ctx* ctx, int64_t n, int64_t m, const int64_t* A_colptr,
+                                     const int64_t* A_rowval, const double* A_nzval, const double* b, const double* c,
+                                     const double* x, const double* s, const double* y, int64_t ncones,
+                                     const int32_t* cone_type, const int64_t* cone_dim, int32_t memspace) {
+    if (!ctx) return -1;
+    ConicBatchImpl* bt = ctx->conic_batch;
+    if (!bt) BAD_ARG(ctx, "conic_batch_add: call conic_batch_begin first");
+    if ((int64_t)bt->states.size() >= bt->B) BAD_ARG(ctx, "conic_batch_add: the batch is full");
+    if (!bt->states.empty() && (n != bt->n || m != bt->m))
+        BAD_ARG(ctx, "conic_batch_add: every problem of a batch must have the same n and m");
+    // the single-problem state is parked while this problem is analysed by the ordinary setup, with the row blocks of
+    // its CSR copies cut for the CTAs one problem gets in the batched kernel
+    ConicState parked = ctx->conic;
+    ctx->conic = ConicState{};
+    const int prev_ctas = ctx->csr_cluster_ctas;
+    ctx->csr_cluster_ctas = bt->C;
+    int32_t rc = diffopt_b200_conic_setup(ctx, n, m, A_colptr, A_rowval, A_nzval, b, c, x, s, y, ncones, cone_type, cone_dim, memspace);
+    ctx->csr_cluster_ctas = prev_ctas;
+    ConicState fresh = ctx->conic;
+    ctx->conic = parked;
+    if (rc == 0 && fresh.npsd > 0) {
+        ctx->err = "conic_batch_add: problems with PSD cones are not batched (use conic_setup / conic_reverse)";
+        rc = -1;
+    }
+    if (rc) {
+        conic_state_release(fresh);
+        return rc;
+    }
+    bt->n = n;
+    bt->m = m;
+    bt->states.push_back(fresh);
+    return 0;
+}
+
+int32_t diffopt_b200_conic_batch_reverse(diffopt_b200_ctx* ctx, const double* dx_seeds, double atol, double btol,
+                                         double conlim, int64_t maxiter, double* g_out, double* dc_out, double* db_out,
+                                         double* out_stats, int32_t memspace) {
+    if (!ctx) return -1;
+    DeviceGuard guard_(ctx->device);
+    ConicBatchImpl* bt = ctx->conic_batch;
+    if (!bt || (int64_t)bt->states.size() != bt->B) BAD_ARG(ctx, "conic_batch_reverse: the batch is not complete (conic_batch_add)");
+    if (!dx_seeds) BAD_ARG(ctx, "conic_batch_reverse: dx_seeds is required");
+    const int n = (int)bt->n, m = (int)bt->m, N = n + m + 1, C = bt->C;
+    const int64_t B = bt->B;
+    const size_t d8 = sizeof(double);
+    // per problem: rhs (N + 1) | x, u, v, w (N each) | partial sums | statistics
+    const size_t stats_off = (size_t)(N + 1) + 4 * (size_t)N + (size_t)LSQR_NSLOTS * C;
+    const size_t stride = (stats_off + 8 + 1) & ~(size_t)1;
+    DO_CUDA(ctx, bt->work.reserve(d8 * stride * (size_t)B));
+    if (!bt->ptrs.ptr) {
+        std::vector<ConicBatchPtrs> hp((size_t)B);
+        for (int64_t p = 0; p < B; ++p) hp[(size_t)p] = ConicBatchPtrs{bt->states[(size_t)p].x.as<double>(), bt->states[(size_t)p].vp.as<double>()};
+        DO_CUDA(ctx, bt->ptrs.reserve(sizeof(ConicBatchPtrs) * (size_t)B));
+        DO_CUDA(ctx, cudaMemcpy(bt->ptrs.ptr, hp.data(), sizeof(ConicBatchPtrs) * (size_t)B, cudaMemcpyHostToDevice));
+    }
+    const void* dseed;
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[0], dx_seeds, d8 * (size_t)n * (size_t)B, memspace, &dseed));
+    conic_rev_rhs_batch_kernel<<<(unsigned)B, 512, 0, ctx->stream>>>(n, m, (const double*)dseed, bt->ptrs.as<ConicBatchPtrs>(),
+                                                                    bt->work.as<double>(), stride);
+    ctx->launches++;
+    LsqrParams prm{atol, btol, conlim, maxiter > 0 ? maxiter : (int64_t)N};
+    const char* env = getenv("DIFFOPT_B200_CONIC_BATCH_STAGE");
+    const bool stage = !(env && env[0] == '0');
+    if (int32_t rc = lsqr_run_conic_batch(ctx, bt->states, C, stage, bt->work.as<double>(), stride, prm, 1e-4 /* :369 */,
+                                          bt->ops, bt->vecs, bt->rhs))
+        return rc;
+    void *dg, *ddc, *ddb, *dst;
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[0], g_out, d8 * (size_t)N * (size_t)B, memspace, &dg));
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[1], dc_out, d8 * (size_t)n * (size_t)B, memspace, &ddc));
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[2], db_out, d8 * (size_t)m * (size_t)B, memspace, &ddb));
+    DO_CUDA(ctx, stage_out_prepare(ctx->out[3], out_stats, d8 * 4 * (size_t)B, memspace, &dst));
+    conic_rev_out_batch_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, ctx->stream>>>(
+        n, m, bt->ptrs.as<ConicBatchPtrs>(), bt->work.as<double>(), stride, stats_off, (double*)dg, (double*)ddc, (double*)ddb,
+        (double*)dst);
+    ctx->launches++;
+    DO_CUDA(ctx, cudaGetLastError());
+    DO_CUDA(ctx, stage_out_finish(ctx, dg, g_out, d8 * (size_t)N * (size_t)B, memspace));
+    DO_CUDA(ctx, stage_out_finish(ctx, ddc, dc_out, d8 * (size_t)n * (size_t)B, memspace));
+    DO_CUDA(ctx, stage_out_finish(ctx, ddb, db_out, d8 * (size_t)m * (size_t)B, memspace));
+    DO_CUDA(ctx, stage_out_finish(ctx, dst, out_stats, d8 * 4 * (size_t)B, memspace));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;   // ev0 / ev1 bracket the LSQR kernel (lsqr_run_conic_batch)
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
     return 0;
 }
 

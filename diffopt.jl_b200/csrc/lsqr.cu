@@ -33,6 +33,11 @@ struct Dev {
     double* red;       // shared scratch (>= 2 * warps doubles)
     int tid, lane, warp, nwarp, nblk, gtid, gthreads;
     bool cluster = false;  // the whole grid is ONE thread-block cluster: hardware barrier instead of grid.sync()
+    // batched launches (one problem per cluster of `nblk` CTAs, lsqr_batch_kernel): rank of this CTA inside its problem
+    // (-1: the grid is one problem, rank = blockIdx.x) and whether the problem lives in a single CTA (barrier = bar.sync)
+    int cta = -1;
+    bool cta_only = false;
+    __device__ __forceinline__ int rank() const { return cta >= 0 ? cta : (int)blockIdx.x; }
     // All-CTA barrier with release/acquire ordering of global memory.  The cluster barrier costs ~0.2 us (and
     // invalidates L1, so plain loads after it see the other CTAs' stores); cooperative grid.sync() costs 2-3 us.
     __device__ __forceinline__ void sync() {
@@ -45,7 +50,9 @@ struct Dev {
 #endif
     }
     __device__ __forceinline__ void sync_() {
-        if (cluster)
+        if (cta_only)
+            __syncthreads();
+        else if (cluster)
             asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
         else
             grid.sync();
@@ -66,7 +73,7 @@ __device__ void block_partial(Dev& d, int slot, double v) {
     if (d.tid == 0) {
         double s = 0.0;
         for (int w = 0; w < d.nwarp; ++w) s += d.red[w];
-        d.partials[slot * d.nblk + blockIdx.x] = s;
+        d.partials[slot * d.nblk + d.rank()] = s;
     }
     __syncthreads();
 }
@@ -173,13 +180,20 @@ constexpr int ST_STRIDE = 2048;  // capacity of one partial slot = upper bound o
 // `epi(b, row, value, operands)` once per row.
 // sel(b, A, x, lb): matrix, gather vector and local block index of global block b.
 // XCG: x was written earlier in the SAME launch (persistent kernels) -> gather with ld.global.cg, not the read-only path.
-template <int THREADS, int NPT, bool XCG, class Sel, class Pre, class Epi>
-__device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double* red, Sel&& sel, Pre&& pre, Epi&& epi) {
+// XM: how x is gathered.  0: read-only path (x constant during the launch); 1: ld.global.cg (x was written earlier in the
+// SAME launch by other CTAs: persistent kernels); 2: plain generic loads -- x is a copy staged in SHARED memory by the
+// caller (one problem per CTA: the whole gather vector fits, and shared-memory gathers are not bound by the one-sector-
+// per-request rate of L1TEX that caps the global-memory forms at ~50 % of HBM).  The matrix streams evict-first for 0, 2.
+// cta / ncta: this CTA's rank among the CTAs that share the blocks.
+template <int THREADS, int NPT, int XM, class Sel, class Pre, class Epi>
+__device__ __forceinline__ void spmv_stream(int cta, int ncta, int nblk_total, double* prod, double* red, Sel&& sel, Pre&& pre,
+                                            Epi&& epi) {
     constexpr int CHUNK = THREADS * NPT;
+    constexpr bool XCG = XM == 1;
     const int tid = threadIdx.x;
-    const int per = (nblk_total + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int b_end = min(nblk_total, ((int)blockIdx.x + 1) * per);
-    for (int b = blockIdx.x * per; b < b_end; ++b) {
+    const int per = (nblk_total + ncta - 1) / ncta;
+    const int b_end = min(nblk_total, (cta + 1) * per);
+    for (int b = cta * per; b < b_end; ++b) {
         const CsrView* A;
         const double* x;
         int lb;
@@ -192,7 +206,7 @@ __device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double
             for (int k = tid; k < cnt; k += THREADS)
                 {
                 const double* xp = x + (XCG ? __ldg(A->colind + s + k) : __ldcs(A->colind + s + k));
-                acc = fma(XCG ? __ldg(A->val + s + k) : __ldcs(A->val + s + k), XCG ? __ldcg(xp) : __ldg(xp), acc);
+                acc = fma(XCG ? __ldg(A->val + s + k) : __ldcs(A->val + s + k), XM == 2 ? *xp : (XCG ? __ldcg(xp) : __ldg(xp)), acc);
             }
             acc = warp_sum_all(acc);
             if ((tid & 31) == 0) red[32 + (tid >> 5)] = acc;
@@ -206,7 +220,7 @@ __device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double
             double av[NPT];
             int ci[NPT];
             int ps[NPT];  // slot of the product in `prod` (CSR position inside the block)
-            const bool sorted = !XCG && A->spos != nullptr;  // column-ordered copy of the block (large operators)
+            const bool sorted = XM == 0 && A->spos != nullptr;  // column-ordered copy of the block (large operators)
 #pragma unroll
             for (int u = 0; u < NPT; ++u) {
                 const int k = tid + u * THREADS;
@@ -237,7 +251,7 @@ __device__ __forceinline__ void spmv_stream(int nblk_total, double* prod, double
             double xv[NPT];
 #pragma unroll
             for (int u = 0; u < NPT; ++u)
-                xv[u] = (tid + u * THREADS < cnt) ? (XCG ? __ldcg(x + ci[u]) : __ldg(x + ci[u])) : 0.0;
+                xv[u] = (tid + u * THREADS < cnt) ? (XM == 2 ? x[ci[u]] : (XCG ? __ldcg(x + ci[u]) : __ldg(x + ci[u]))) : 0.0;
             double4 opnd = make_double4(0.0, 0.0, 0.0, 0.0);
             if (row < r1 && sub == 0) opnd = pre(b, row);
 #pragma unroll
@@ -461,8 +475,8 @@ __device__ void csr_apply(Dev& d, const CsrView& A, const double* __restrict__ s
                           double s_dst, int slot) {
     double acc = 0.0;
     if constexpr (CL) {
-        spmv_stream<CL_THREADS, CL_NPT, true>(
-            A.nblk, cl_prod, d.red, [&](int b, const CsrView*& M, const double*& x, int& lb) { M = &A; x = src; lb = b; },
+        spmv_stream<CL_THREADS, CL_NPT, 1>(
+            d.rank(), d.nblk, A.nblk, cl_prod, d.red, [&](int b, const CsrView*& M, const double*& x, int& lb) { M = &A; x = src; lb = b; },
             [&](int, int row) { return make_double4(s_dst != 0.0 ? __ldcg(dst + row) : 0.0, 0.0, 0.0, 0.0); },
             [&](int, int row, double t, const double4& o) {
                 t = t * s_src + s_dst * o.x;
@@ -483,7 +497,9 @@ __device__ void csr_apply(Dev& d, const CsrView& A, const double* __restrict__ s
 // `src_last` / `dst_last` are every thread's private copies of src[N-1] / dst[N-1] (all threads compute the last row
 // identically): nobody reads those entries from memory, so thread 0 may store the new one right after the barrier
 // that publishes the partial sums, and ||dst||^2 (returned in `norm2`) is complete without another barrier.
-template <bool CL, bool PSD>
+// SM (batched launches, one problem per CTA): the vectors the products gather from are first copied into shared memory
+// (behind the CL_CHUNK products: n + m doubles), see spmv_stream XM = 2.
+template <bool CL, bool PSD, bool SM = false>
 __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const double* __restrict__ src,
                             double s_src, double* dst, double s_dst, int slot, double src_last, double& dst_last,
                             double& norm2) {
@@ -491,17 +507,28 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
     double dotacc = 0.0;
     if constexpr (CL) {
         double* prod = cl_prod;
+        double* xs_m = cl_prod + CL_CHUNK;  // staged gather vectors (SM): m entries, then n entries
+        double* xs_n = xs_m + m;
+        constexpr int XM = SM ? 2 : 1;
+        auto stage = [&](double* to, const double* from, int len) {
+            for (int i = d.tid; i < len; i += CL_THREADS) to[i] = __ldcg(from + i);
+        };
         double acc = 0.0;
         if (!transpose) {
             dpi_apply<PSD>(d, op, src + n, op.wc, false);  // wc = Dpi t2
             d.sync();
+            if constexpr (SM) {
+                stage(xs_m, op.wc, m);
+                stage(xs_n, src, n);
+                __syncthreads();
+            }
             const double t3 = src_last;
             const int nbt = op.At.nblk;
-            spmv_stream<CL_THREADS, CL_NPT, true>(
-                nbt + op.A.nblk, prod, d.red,
+            spmv_stream<CL_THREADS, CL_NPT, XM>(
+                d.rank(), d.nblk, nbt + op.A.nblk, prod, d.red,
                 [&](int b, const CsrView*& A, const double*& x, int& lb) {
-                    if (b < nbt) { A = &op.At; x = op.wc; lb = b; }
-                    else { A = &op.A; x = src; lb = b - nbt; }
+                    if (b < nbt) { A = &op.At; x = SM ? xs_m : op.wc; lb = b; }
+                    else { A = &op.A; x = SM ? xs_n : src; lb = b - nbt; }
                 },
                 [&](int b, int row) {
                     return b < nbt ? make_double4(op.c[row], __ldcg(dst + row), __ldcg(src + row), 0.0)
@@ -530,9 +557,13 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
             norm2 = total_of(d, slot) + last * last;
         } else {
             const double u3 = src_last;
-            spmv_stream<CL_THREADS, CL_NPT, true>(  // wc = A u1 - u2 - b u3
-                op.A.nblk, prod, d.red,
-                [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.A; x = src; lb = b; },
+            if constexpr (SM) {
+                stage(xs_n, src, n);
+                __syncthreads();
+            }
+            spmv_stream<CL_THREADS, CL_NPT, XM>(  // wc = A u1 - u2 - b u3
+                d.rank(), d.nblk, op.A.nblk, prod, d.red,
+                [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.A; x = SM ? xs_n : src; lb = b; },
                 [&](int, int row) { return make_double4(__ldcg(src + n + row), op.b[row], 0.0, 0.0); },
                 [&](int, int row, double t, const double4& o) {
                     op.wc[row] = t - o.x - o.y * u3;
@@ -541,10 +572,11 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
             d.sync();
             double* r2 = op.wc + m;
             dpi_apply<PSD>(d, op, op.wc, r2, true);
+            if constexpr (SM) stage(xs_m, src + n, m);   // (src is not touched by dpi_apply: no barrier needed before)
             d.sync();
-            spmv_stream<CL_THREADS, CL_NPT, true>(  // rows 0..n-1: -(A' u2)_j - c_j u3
-                op.At.nblk, prod, d.red,
-                [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.At; x = src + n; lb = b; },
+            spmv_stream<CL_THREADS, CL_NPT, XM>(  // rows 0..n-1: -(A' u2)_j - c_j u3
+                d.rank(), d.nblk, op.At.nblk, prod, d.red,
+                [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.At; x = SM ? xs_m : src + n; lb = b; },
                 [&](int, int row) { return make_double4(op.c[row], __ldcg(dst + row), __ldcg(src + row), 0.0); },
                 [&](int, int row, double t, const double4& o) {
                     t = (-t - o.x * u3) * s_src + s_dst * o.y;
@@ -645,7 +677,7 @@ struct OpArgs {
 
 // Returns ||dst||^2 (after the update).  The conic operator ends behind its own barrier; the CSR one needs a barrier
 // here before its partial sums can be read.
-template <bool CL, bool PSD>
+template <bool CL, bool PSD, bool SM = false>
 __device__ double op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* src, double s_src, double* dst,
                            double s_dst, int slot, double src_last, double& dst_last) {
     if (o.kind == 0) {
@@ -654,17 +686,16 @@ __device__ double op_apply(Dev& d, const OpArgs& o, bool adjoint, const double* 
         return total_of(d, slot);
     }
     double norm2 = 0.0;
-    conic_apply<CL, PSD>(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot, src_last, dst_last, norm2);
+    conic_apply<CL, PSD, SM>(d, o.conic, adjoint != (o.conic_trans != 0), src, s_src, dst, s_dst, slot, src_last, dst_last, norm2);
     return norm2;
 }
 
-template <int THREADS, int MINB, bool CLUSTER, bool STREAM, bool PSD>
-__global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const double* __restrict__ rhs, LsqrParams prm,
-                                                               LsqrVectors vec) {
-    __shared__ double red[64];
-    Dev d{cg::this_grid(), vec.partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
-          (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
-          (int)(gridDim.x * blockDim.x), CLUSTER};
+// The whole LSQR iteration (Paige-Saunders) for one operator; called by every thread of the CTAs that share the problem
+// (the whole grid, one cluster, or -- batched launches -- one cluster / CTA per problem).  zero_below: right-hand sides of
+// norm <= zero_below give x = 0 without iterating (ConicProgram.jl:369 tests 1e-4 on the reverse seed; -1 disables).
+template <bool STREAM, bool PSD, bool SM>
+__device__ void lsqr_body(Dev& d, const OpArgs& o, const double* __restrict__ rhs, const LsqrParams prm, const LsqrVectors vec,
+                          const double zero_below) {
     const int nr = o.nrows, nc = o.ncols;
     double *u = vec.u, *v = vec.v, *w = vec.w, *x = vec.x;
 
@@ -687,6 +718,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
     }
     d.sync();
     double beta = sqrt(total_of(d, 0));
+    if (beta <= zero_below) beta = 0.0;
     double alpha = 0.0;
     double su = 1.0, sv = 1.0;  // true u = su * u_mem, true v = sv * v_mem
     int istop = 0;
@@ -695,7 +727,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
     double rnorm = beta, arnorm = 0.0;
     if (beta > 0) {
         su = 1.0 / beta;
-        alpha = sqrt(op_apply<STREAM, PSD>(d, o, true, u, su, v, 0.0, 2, u_last, v_last));   // v_mem = A' u_true
+        alpha = sqrt(op_apply<STREAM, PSD, SM>(d, o, true, u, su, v, 0.0, 2, u_last, v_last));   // v_mem = A' u_true
     }
     if (alpha > 0) sv = 1.0 / alpha;
     arnorm = alpha * beta;
@@ -728,7 +760,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
             block_partial(d, 4, dd);
             const bool more = itn < prm.maxiter;
             double unorm2 = 0.0;
-            if (more) unorm2 = op_apply<STREAM, PSD>(d, o, false, v, sv, u, -alpha * su, 0, v_last, u_last);  // u_mem = A v_true - alpha u_true
+            if (more) unorm2 = op_apply<STREAM, PSD, SM>(d, o, false, v, sv, u, -alpha * su, 0, v_last, u_last);  // u_mem = A v_true - alpha u_true
             else d.sync();  // the partial sums of the update above
             if (pending) {
                 ddnorm += total_of(d, 4);
@@ -754,7 +786,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
             if (beta > 0) {
                 su = 1.0 / beta;
                 anorm = sqrt(anorm * anorm + alpha * alpha + beta * beta);
-                alpha = sqrt(op_apply<STREAM, PSD>(d, o, true, u, su, v, -beta * sv, 2, u_last, v_last));  // v_mem = A' u_true - beta v_true
+                alpha = sqrt(op_apply<STREAM, PSD, SM>(d, o, true, u, su, v, -beta * sv, 2, u_last, v_last));  // v_mem = A' u_true - beta v_true
                 sv = alpha > 0 ? 1.0 / alpha : 1.0;
             } else {
                 su = 1.0;  // u_mem is exactly zero
@@ -800,6 +832,37 @@ __global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const d
         vec.stats[5] = acond;
         vec.stats[6] = xnorm;
     }
+}
+
+template <int THREADS, int MINB, bool CLUSTER, bool STREAM, bool PSD>
+__global__ void __launch_bounds__(THREADS, MINB) lsqr_kernel_t(OpArgs o, const double* __restrict__ rhs, LsqrParams prm,
+                                                               LsqrVectors vec) {
+    __shared__ double red[64];
+    Dev d{cg::this_grid(), vec.partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
+          (int)(blockDim.x >> 5), (int)gridDim.x, (int)(blockIdx.x * blockDim.x + threadIdx.x),
+          (int)(gridDim.x * blockDim.x), CLUSTER};
+    lsqr_body<STREAM, PSD, false>(d, o, rhs, prm, vec, -1.0);
+}
+
+// Lock-step batch: problem p = blockIdx.x / C is solved by the C CTAs of one cluster (C = 1: one CTA, the gather vectors
+// staged in shared memory); every problem has its own operator, right-hand side and work vectors.  No barrier spans
+// problems: a problem that converges early simply retires its CTAs.
+template <bool SM>
+__global__ void __launch_bounds__(CL_THREADS, 1) lsqr_batch_kernel(const OpArgs* __restrict__ ops, const double* const* __restrict__ rhs,
+                                                                   LsqrParams prm, const LsqrVectors* __restrict__ vecs, const int C,
+                                                                   const double zero_below) {
+    __shared__ double red[64];
+    __shared__ OpArgs so;
+    __shared__ LsqrVectors sv;
+    const int p = blockIdx.x / C, cta = blockIdx.x - p * C;
+    for (int i = threadIdx.x; i < (int)(sizeof(OpArgs) / sizeof(int)); i += blockDim.x)
+        reinterpret_cast<int*>(&so)[i] = reinterpret_cast<const int*>(ops + p)[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(LsqrVectors) / sizeof(int)); i += blockDim.x)
+        reinterpret_cast<int*>(&sv)[i] = reinterpret_cast<const int*>(vecs + p)[i];
+    __syncthreads();
+    Dev d{cg::this_grid(), sv.partials, red, (int)threadIdx.x, (int)(threadIdx.x & 31), (int)(threadIdx.x >> 5),
+          (int)(blockDim.x >> 5), C, (int)(cta * blockDim.x + threadIdx.x), (int)(C * blockDim.x), true, cta, C == 1};
+    lsqr_body<true, false, SM>(d, so, rhs[p], prm, sv, zero_below);
 }
 
 // stand-alone operator kernels (C-ABI conic_M_apply / conic_dpi_apply; also used by tests)
@@ -968,7 +1031,8 @@ __global__ void __launch_bounds__(SP_THREADS, 8) st_M_rows_kernel(ConicOpView op
     double acc = 0.0, dotacc = 0.0;
     const int nbt = op.At.nblk;
     __shared__ double prod[ST_CHUNK];
-    spmv_stream<SP_THREADS, ST_NPT, false>(
+    spmv_stream<SP_THREADS, ST_NPT, 0>(
+        (int)blockIdx.x, (int)gridDim.x,
         nbt + op.A.nblk, prod, red,
         [&](int b, const CsrView*& A, const double*& x, int& lb) {
             if (b < nbt) { A = &op.At; x = op.wc; lb = b; }
@@ -1058,7 +1122,8 @@ __global__ void __launch_bounds__(SP_THREADS, 8) st_Mt_A_kernel(ConicOpView op, 
     const double u3 = __ldcg(src + n + m);
     double dotacc = 0.0;
     __shared__ double prod[ST_CHUNK];
-    spmv_stream<SP_THREADS, ST_NPT, false>(
+    spmv_stream<SP_THREADS, ST_NPT, 0>(
+        (int)blockIdx.x, (int)gridDim.x,
         op.A.nblk, prod, red,
         [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.A; x = src; lb = b; },
         [&](int, int row) { return make_double4(__ldcg(src + n + row), op.b[row], 0.0, 0.0); },
@@ -1080,7 +1145,8 @@ __global__ void __launch_bounds__(SP_THREADS, 8) st_Mt_rows_kernel(ConicOpView o
     const double* r2 = op.wc + m;
     double acc = 0.0, dotacc = 0.0;
     __shared__ double prod[ST_CHUNK];
-    spmv_stream<SP_THREADS, ST_NPT, false>(
+    spmv_stream<SP_THREADS, ST_NPT, 0>(
+        (int)blockIdx.x, (int)gridDim.x,
         op.At.nblk, prod, red,
         [&](int b, const CsrView*& A, const double*& x, int& lb) { A = &op.At; x = src + n; lb = b; },
         [&](int, int row) { return make_double4(op.c[row], dst[row], __ldcg(src + row), 0.0); },
@@ -1476,6 +1542,67 @@ int32_t conic_apply_dpi(diffopt_b200_ctx* ctx, const double* t_dev, bool transpo
     return conic_small_launch(ctx, (const void*)conic_dpi_kernel, t_dev, transpose, out_dev);
 }
 
+// Lock-step batch of conic problems (diffopt_b200_conic_batch_reverse): one persistent kernel, problem p on the C CTAs of
+// cluster p.  `work` holds one region of `stride` doubles per problem: [rhs (N+1) | x (N) | u (N) | v (N) | w (N) |
+// partials (NSLOTS * C) | stats (8)].  With C == 1 and `stage` the gather vectors are staged in shared memory.
+int32_t lsqr_run_conic_batch(diffopt_b200_ctx* ctx, std::vector<ConicState>& states, int C, bool stage, double* work, size_t stride,
+                             LsqrParams prm, double zero_below, DevBuf& ops_buf, DevBuf& vecs_buf, DevBuf& rhs_buf) {
+    const int B = (int)states.size();
+    if (B == 0) return 0;
+    const int n = (int)states[0].n, m = (int)states[0].m, N = n + m + 1;
+    std::vector<OpArgs> ops((size_t)B);
+    std::vector<LsqrVectors> vecs((size_t)B);
+    std::vector<const double*> rhs((size_t)B);
+    for (int p = 0; p < B; ++p) {
+        std::swap(ctx->conic, states[(size_t)p]);
+        OpArgs o{};
+        o.kind = 1;
+        o.conic = conic_view(ctx);
+        o.conic_trans = 0;
+        o.nrows = o.ncols = N;
+        ops[(size_t)p] = o;
+        std::swap(ctx->conic, states[(size_t)p]);
+        double* base = work + (size_t)p * stride;
+        rhs[(size_t)p] = base;
+        vecs[(size_t)p] = LsqrVectors{base + (N + 1) + N, base + (N + 1) + 2 * (size_t)N, base + (N + 1) + 3 * (size_t)N, base + (N + 1),
+                                      base + (N + 1) + 4 * (size_t)N, base + (N + 1) + 4 * (size_t)N + (size_t)NSLOTS * C};
+    }
+    DO_CUDA(ctx, ops_buf.reserve(sizeof(OpArgs) * (size_t)B));
+    DO_CUDA(ctx, vecs_buf.reserve(sizeof(LsqrVectors) * (size_t)B));
+    DO_CUDA(ctx, rhs_buf.reserve(sizeof(double*) * (size_t)B));
+    DO_CUDA(ctx, cudaMemcpyAsync(ops_buf.ptr, ops.data(), sizeof(OpArgs) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+    DO_CUDA(ctx, cudaMemcpyAsync(vecs_buf.ptr, vecs.data(), sizeof(LsqrVectors) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+    DO_CUDA(ctx, cudaMemcpyAsync(rhs_buf.ptr, rhs.data(), sizeof(double*) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+    DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die at return
+    stage = stage && C == 1;
+    const size_t dyn = sizeof(double) * ((size_t)CL_CHUNK + (stage ? (size_t)(n + m) : 0));
+    if (dyn > ctx->smem_optin) stage = false;
+    const size_t dyn2 = sizeof(double) * ((size_t)CL_CHUNK + (stage ? (size_t)(n + m) : 0));
+    const void* kern = stage ? (const void*)lsqr_batch_kernel<true> : (const void*)lsqr_batch_kernel<false>;
+    DO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+    const OpArgs* dops = ops_buf.as<OpArgs>();
+    const double* const* drhs = rhs_buf.as<const double*>();
+    const LsqrVectors* dvecs = vecs_buf.as<LsqrVectors>();
+    void* args[] = {(void*)&dops, (void*)&drhs, &prm, (void*)&dvecs, &C, &zero_below};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(B * C));
+    cfg.blockDim = dim3(CL_THREADS);
+    cfg.dynamicSmemBytes = dyn2;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    DO_CUDA(ctx, cudaLaunchKernelExC(&cfg, kern, args));
+    ctx->launches++;
+    DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    return 0;
+}
+
 // Host: Julia CSC (1-based int64) -> device CSR of the matrix and of its transpose (0-based int32).
 int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, const int64_t* colptr,
                           const int64_t* rowval, const double* nzval, CsrDev& out) {
@@ -1559,8 +1686,9 @@ int32_t csr_from_csc_host(diffopt_b200_ctx* ctx, int64_t nrows, int64_t ncols, c
     std::vector<int> blk, t_blk, cblk, t_cblk, gblk, t_gblk;
     row_blocks(rowptr, nrows, blk);
     row_blocks(t_rowptr, ncols, t_blk);
-    cluster_blocks(rowptr, nrows, CL_MAX_CTAS, cblk);
-    cluster_blocks(t_rowptr, ncols, CL_MAX_CTAS, t_cblk);
+    const int64_t cl_ctas = ctx->csr_cluster_ctas > 0 ? ctx->csr_cluster_ctas : CL_MAX_CTAS;
+    cluster_blocks(rowptr, nrows, cl_ctas, cblk);
+    cluster_blocks(t_rowptr, ncols, cl_ctas, t_cblk);
     cluster_blocks(rowptr, nrows, ctx->sm_count, gblk);
     cluster_blocks(t_rowptr, ncols, ctx->sm_count, t_gblk);
     out.ncblk = (int64_t)cblk.size() / 2 - 1;

@@ -271,6 +271,24 @@ int32_t diffopt_b200_conic_reverse(
     double atol, double btol, double conlim, int64_t maxiter,
     double* g_out, double* dc_out, double* db_out, double* out_stats, int32_t memspace);
 
+/* Lock-step batch of conic problems: B independent problems of equal size (n, m; any sparsity / solution / cone
+ * list without PSD cones), each analysed like conic_setup, then ALL reverse solves advanced by ONE persistent kernel
+ * (problem p on its own CTA -- or cluster of `ctas_per_problem` CTAs -- with the gather vectors staged in shared
+ * memory).  This is how a training loop calls the reference's one-problem-per-call `reverse_differentiate!`
+ * (ConicProgram.jl:336-394) over a minibatch; every problem runs exactly the single-problem iteration (same
+ * arithmetic, same stop tests, own iteration count).  Arrays are instance-major: dx_seeds[n,B], g_out[n+m+1,B],
+ * dc_out[n,B], db_out[m,B], out_stats[4,B] = (istop, iterations, rnorm, arnorm) per problem. */
+int32_t diffopt_b200_conic_batch_begin(diffopt_b200_ctx* ctx, int64_t B, int32_t ctas_per_problem);
+int32_t diffopt_b200_conic_batch_add(
+    diffopt_b200_ctx* ctx, int64_t n, int64_t m,
+    const int64_t* A_colptr, const int64_t* A_rowval, const double* A_nzval,
+    const double* b, const double* c, const double* x, const double* s, const double* y,
+    int64_t ncones, const int32_t* cone_type, const int64_t* cone_dim, int32_t memspace);
+int32_t diffopt_b200_conic_batch_reverse(
+    diffopt_b200_ctx* ctx, const double* dx_seeds,
+    double atol, double btol, double conlim, int64_t maxiter,
+    double* g_out, double* dc_out, double* db_out, double* out_stats, int32_t memspace);
+
 #ifdef __cplusplus
 }
 #endif

@@ -520,3 +520,44 @@ def test_streaming_lsqr_matches_persistent_kernel(ctx, monkeypatch):
         if k in (1, 2, 3, 4):
             assert rel(a[0], b[0]) <= 1e-9
         assert a[1] == pytest.approx(b[1], rel=1e-5 if k in (1, 2, 3, 4, 10) else 5e-2), (k, a[1], b[1])
+
+
+@pytest.mark.parametrize("ctas", [1, 4])
+@pytest.mark.parametrize("stage", ["1", "0"])
+def test_conic_lockstep_batch_matches_single_problem_solves(ctx, monkeypatch, ctas, stage):
+    """Lock-step batch (diffopt_b200_conic_batch_*): B problems of equal size but different sparsity, solutions and
+    seeds, advanced by one persistent kernel -- one CTA per problem with the gather vectors staged in shared memory, or
+    one 4-CTA cluster per problem.  Every problem must reproduce its own single-problem `reverse_differentiate!`
+    (ConicProgram.jl:336-394): same iteration count and stop code as the oracle's LSQR, g / dc / db <= 1e-6; a problem
+    whose seed is below the 1e-4 threshold (:369) returns zeros while its neighbours iterate."""
+    monkeypatch.setenv("DIFFOPT_B200_CONIC_BATCH_STAGE", stage)
+    cm = diffopt_b200.submodule("conic")
+    B = 6
+    kw = dict(TIGHT, maxiter=20000)
+    ds, models = [], []
+    for k in range(B):
+        d = bench_data.conic_config4_conditioned(n=150, n_zero=15, n_nonneg=130, n_soc=9, soc_dim=8, nnz_per_row=5 + k % 3,
+                                                 seed=100 + k)
+        mdl = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+        mdl.set_variable_primal(d["x"]); mdl.set_constraint_primal(d["s"]); mdl.set_constraint_dual(d["y"])
+        ds.append(d); models.append(mdl)
+    seeds = np.stack([d["seed"] for d in ds])
+    seeds[3] = 1e-7                                       # below the reverse zero test
+    batch = cm.ConicBatch(ctx, models, ctas_per_problem=ctas)
+    batch.tolerances = kw
+    out = batch.reverse_differentiate(seeds)
+    for k, d in enumerate(ds):
+        if k == 3:
+            assert not out["g"][k].any() and out["stats"][k][1] == 0
+            continue
+        cache = _oracle_cache(d)
+        dz = np.concatenate([seeds[k], np.zeros(d["A"].shape[0]), [-(d["x"] @ seeds[k])]])
+        g, info = olsqr.lsqr(cache.M, dz, return_info=True, **kw)
+        _, db, dc = oconic.reverse_param_grads(cache, g, dense_dA=False)
+        assert int(out["stats"][k][0]) == info.istop
+        assert abs(int(out["stats"][k][1]) - info.itn) <= max(3, info.itn // 50)
+        assert rel(out["g"][k], g) <= RTOL_LSQR
+        assert rel(out["dc"][k], dc) <= RTOL_LSQR and rel(out["db"][k], db) <= RTOL_LSQR
+    # a second call on the same batch (work area reused) gives the same answer bit for bit
+    out2 = batch.reverse_differentiate(seeds)
+    assert np.array_equal(out["g"], out2["g"])

@@ -52,7 +52,7 @@ def test_mpc_kkt_forward_directions(ctx):
     LHS' (QuadraticProgram.jl:438); 16 directions against one factorisation."""
     d = bench_data.mpc_config3(T=300)
     F = _check(ctx, d["K"], 16, True, seed=2)
-    assert F.stats["levels"] >= 5 and F.stats["max_front"] <= 128
+    assert F.stats["levels"] >= 3 and F.stats["max_front"] <= 128   # levels of GROUPED separators (3 dissection levels each)
     X = F.solve(np.eye(d["K"].shape[0])[:, :3])
     assert np.abs(d["K"].T @ X - np.eye(d["K"].shape[0])[:, :3]).max() < 1e-9
 
@@ -78,20 +78,24 @@ def test_grid_pattern_with_large_fronts(ctx):
     assert F.stats["max_front"] > 60
 
 
-def test_delayed_pivots_are_merged_into_the_parent(ctx):
-    """Tridiagonal matrix with an exactly zero diagonal (KKT-like: every pivot must come from off the diagonal).  Fronts
-    whose last column can only be pivoted with a row of the separator report it; the host merges them into their
-    parents and the factorisation is repeated."""
+@pytest.mark.parametrize("diag", [0.0, 1e-5])
+def test_delayed_pivots_are_merged_into_the_parent(ctx, diag):
+    """Tridiagonal matrix whose pivots must come from off the diagonal (KKT-like).  diag = 0: the exactly zero diagonal is
+    seen by the analysis, which pairs every such vertex with a neighbour (matching-compressed ordering) so that the pivot
+    row sits in the same front.  diag = 1e-5 (weak, but above the analysis' 1e-8 test): no pairing, so a leaf whose last
+    column can only be pivoted with a row of its separator fails the threshold test (|pivot| >= 1e-3 max|column|) and
+    REPORTS it; the host merges such fronts into their parents and the factorisation is repeated."""
     N = 1000
     rng = np.random.default_rng(6)
-    K = sp.diags([rng.uniform(1, 2, N - 1), rng.uniform(1, 2, N - 1)], [-1, 1], format="csc")
+    K = sp.diags([rng.uniform(1, 2, N - 1), diag * rng.uniform(1, 2, N), rng.uniform(1, 2, N - 1)], [-1, 0, 1], format="csc")
     lsq = diffopt_b200.submodule("lsqr")
     F = lsq.SparseFactorization(ctx, K)
     R = rng.standard_normal((N, 4))
     X = F.solve(R)
     ref = spla.splu(K).solve(R)
     assert (np.linalg.norm(X - ref, axis=0) / np.linalg.norm(ref, axis=0)).max() <= RTOL_DIRECT
-    assert F.stats["method"] == "band" or F.stats["delayed_pivot_retries"] >= 1
+    if diag:
+        assert F.stats["method"] == "band" or F.stats["delayed_pivot_retries"] >= 1, F.stats
 
 
 def test_singular_matrix_is_reported(ctx):
