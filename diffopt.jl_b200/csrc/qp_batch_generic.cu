@@ -26,29 +26,40 @@ __device__ __forceinline__ double warp_sum(double v) {
 //   rowacc[r] += sum_j X[r,j] * zc[j]      (length R)
 //   colacc[j] += sum_r X[r,j] * wr[r]      (length n)        (wr == nullptr -> skipped)
 // rowscale (optional) multiplies the row sums' contribution: rowacc[r] += rowscale[r] * (...)
+// Every output has ONE owner and a fixed summation order (results are reproducible bit for bit): rows are owned by the
+// lanes of a warp (32 consecutive rows per warp, columns in order, four interleaved partial sums), columns by whole warps
+// (lanes over the rows, fixed shuffle tree).  Called by all threads; the caller separates calls that share an
+// accumulator with __syncthreads().
 __device__ void accum_matvecs(const double* __restrict__ X, int R, int n, const double* zc, const double* wr,
                               double* rowacc, const double* rowscale, double* colacc) {
     if (X == nullptr || R == 0) return;
-    const int tid = threadIdx.x;
-    const int Rp = (R + 31) & ~31;           // rows padded to a warp multiple
-    const int ngroups = GEN_THREADS / Rp;    // column groups processed concurrently
-    if (ngroups == 0) {                      // R > 512 never happens (N <= 165)
-        return;
-    }
-    const int r = tid % Rp;
-    const int g = tid / Rp;
-    if (g >= ngroups) return;                // whole warps only (Rp multiple of 32)
-    double racc = 0.0;
-    const double wv = (wr != nullptr && r < R) ? wr[r] : 0.0;
-    for (int j = g; j < n; j += ngroups) {
-        double v = (r < R) ? X[(size_t)j * R + r] : 0.0;
-        racc += v * zc[j];
-        if (colacc != nullptr) {
-            double c = warp_sum(v * wv);
-            if ((tid & 31) == 0) atomicAdd(&colacc[j], c);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = GEN_THREADS / 32;
+    if (rowacc != nullptr) {
+        for (int r0 = 32 * warp; r0 < R; r0 += 32 * NW) {
+            const int r = r0 + lane;
+            if (r >= R) continue;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int j = 0;
+            for (; j + 3 < n; j += 4) {
+                s0 = fma(X[(size_t)j * R + r], zc[j], s0);
+                s1 = fma(X[(size_t)(j + 1) * R + r], zc[j + 1], s1);
+                s2 = fma(X[(size_t)(j + 2) * R + r], zc[j + 2], s2);
+                s3 = fma(X[(size_t)(j + 3) * R + r], zc[j + 3], s3);
+            }
+            for (; j < n; ++j) s0 = fma(X[(size_t)j * R + r], zc[j], s0);
+            const double racc = (s0 + s1) + (s2 + s3);
+            rowacc[r] += rowscale ? rowscale[r] * racc : racc;
         }
     }
-    if (rowacc != nullptr && r < R) atomicAdd(&rowacc[r], rowscale ? rowscale[r] * racc : racc);
+    if (colacc != nullptr && wr != nullptr) {
+        for (int j = warp; j < n; j += NW) {
+            double c = 0.0;
+            for (int r = lane; r < R; r += 32) c = fma(X[(size_t)j * R + r], wr[r], c);
+            c = warp_sum(c);
+            if (lane == 0) colacc[j] += c;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveArgs a) {
@@ -109,7 +120,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
             const size_t b = (size_t)inst;
             const size_t bd = (a.shared & 2) ? 0 : b;
             accum_matvecs(a.dQ ? a.dQ + bd * n * n : nullptr, n, n, zs, nullptr, rf, nullptr, nullptr);
+            __syncthreads();   // rf[0..n) changes owner between the calls
             accum_matvecs(a.dG ? a.dG + bd * m * n : nullptr, m, n, zs, lams, rf + n, lams, rf);
+            __syncthreads();
             accum_matvecs(a.dA ? a.dA + bd * p * n : nullptr, p, n, zs, nus, rf + n + m, nullptr, rf);
         }
         __syncthreads();

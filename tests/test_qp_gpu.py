@@ -471,13 +471,14 @@ def test_extended_entry_shared_matrices_and_packed_triangles(ctx):
         # configured alike)
         for _ in range(2):
             f0, r0, i0 = qpm.solve_batch(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], fwd_dir=fd, seed=d["seed"])
+        st0 = ctx.qp_last_stats()
         assert not i0.any()
         of, orv = _oracle_batch(d)
         assert rel_err(f0, of).max() <= RTOL_DIRECT and rel_err(r0, orv).max() <= RTOL_DIRECT
         # (a) one instance of Q, G, A
         f1, r1, i1 = qpm.solve_batch_ex(ctx, d["Q"][0], d["G"][0], d["A"][0], d["h"], d["z"], d["lam"], d["nu"], fwd_dir=fd,
                                         seed=d["seed"], shared_matrices=True)
-        assert not i1.any() and np.array_equal(f1, f0) and np.array_equal(r1, r0)
+        assert not i1.any() and np.array_equal(f1, f0) and np.array_equal(r1, r0), (st0, ctx.qp_last_stats())
         # (b) packed triangles (per instance), and both together with a shared direction
         f2, r2, _ = qpm.solve_batch_ex(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], fwd_dir=fd,
                                        seed=d["seed"], packed_q=True)
