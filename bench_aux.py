@@ -246,6 +246,8 @@ def main():
                           "note": "N=300: launch/grid-sync latency bound, no roofline claim"}), flush=True)
     if "3" in todo:
         print(json.dumps(config3(ctx)), flush=True)
+    if "3nocpu" in todo:
+        print(json.dumps(config3(ctx, cpu=False)), flush=True)
     if "3p" in todo:
         print(json.dumps(config3(ctx, portfolio=True)), flush=True)
     if "4" in todo:

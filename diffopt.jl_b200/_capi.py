@@ -66,6 +66,8 @@ SIGNATURES = {
     "diffopt_b200_conic_batch_add": (C.c_int32, [vp, C.c_int64, C.c_int64] + [vp] * 8 + [C.c_int64, vp, vp, C.c_int32]),
     "diffopt_b200_conic_batch_reverse": (C.c_int32, [vp, vp, C.c_double, C.c_double, C.c_double, C.c_int64, vp, vp, vp, vp,
                                                      C.c_int32]),
+    "diffopt_b200_sparse_setup_inertia": (C.c_int32, [vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, vp]),
+    "diffopt_b200_param_pullback": (C.c_int32, [vp, C.c_int64, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int32]),
 }
 
 

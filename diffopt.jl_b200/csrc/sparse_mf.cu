@@ -320,6 +320,257 @@ __global__ void __launch_bounds__(MF_TC) mf_backward_kernel(const int* list, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Separator fronts that fit shared memory: one CTA per (front, tile of 64 right-hand sides), 256 threads = 64 columns x
+// 4 row groups.  The tile of the right-hand sides lives in shared memory as YW[row][column] (rows 0..k-1: the front's
+// own unknowns, rows k..nf-1: its boundary), the factor panel streams through shared memory in blocks of MF_NB columns
+// (next block in flight in registers while the current one is applied).  Per block every thread solves the MF_NB x MF_NB
+// diagonal block for its column redundantly in registers and then updates the rows it owns (row groups interleaved),
+// so a front of order k costs k / MF_NB short steps instead of one thread walking k^2 / 2 + k s dependent FMAs.
+// Row interchanges enter as the NET permutation of the front (psrc / pdst, mf_netperm_kernel).
+constexpr int MF_TT = 256;
+constexpr int MF_RG = MF_TT / MF_TC;   // row groups
+constexpr int MF_NB = 8;
+constexpr int MF_LDT = MF_TC + 1;      // leading dimension of YW: conflict-free by row and by column
+
+// one CTA per front: net effect of the front's row interchanges.  psrc[first + r] = row (0..k-1, before the interchanges)
+// that ends at position r; pdst = inverse.
+__global__ void __launch_bounds__(64) mf_netperm_kernel(const MfFront* fronts, const int nfronts, const int* piv, int* psrc, int* pdst) {
+    extern __shared__ int np_smem[];
+    for (int fid = blockIdx.x; fid < nfronts; fid += gridDim.x) {
+        const MfFront fr = fronts[fid];
+        const int k = fr.k;
+        int* src = np_smem;
+        int* pv = np_smem + k;
+        for (int r = threadIdx.x; r < k; r += blockDim.x) {
+            src[r] = r;
+            pv[r] = piv[fr.first + r];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int j = 0; j < k; ++j) {
+                const int p = pv[j];
+                const int t = src[j];
+                src[j] = src[p];
+                src[p] = t;
+            }
+        __syncthreads();
+        for (int r = threadIdx.x; r < k; r += blockDim.x) {
+            psrc[fr.first + r] = src[r];
+            pdst[fr.first + src[r]] = r;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list, const MfFront* fronts, const int* child_idx, const int* rel,
+                                                                 const int* perm, const int* psrc, const int* pdst, const double* Lp,
+                                                                 const double* B, double* Y, double* W, const long long N, const int nrhs) {
+    extern __shared__ __align__(16) double mf_smem[];
+    const int fid = list[blockIdx.x];
+    const MfFront fr = fronts[fid];
+    const int k = fr.k, s = fr.s, nf = k + s;
+    const int tid = threadIdx.x, c = tid & (MF_TC - 1), q = tid >> 6, lane = tid & 31, wid = tid >> 5;
+    const int c0 = blockIdx.y * MF_TC, col = c0 + c;
+    const int ncol = min(MF_TC, nrhs - c0);
+    const bool live = col < nrhs;
+    double* YW = mf_smem;                                  // [nf][MF_LDT]
+    double* Lb = YW + (size_t)nf * MF_LDT;                 // [nf][MF_NB]: rows jb.. of the current column block (16-byte aligned:
+    Lb += ((size_t)nf * MF_LDT) & 1;                       //  odd offsets are bumped)
+    int* rows = reinterpret_cast<int*>(Lb + (size_t)nf * MF_NB);  // original row of position r
+    int* posmap = rows + k;                                // position of (pre-interchange) row r
+    const double* L = Lp + fr.lp;
+    double lreg[MF_NB];
+    auto prefetch = [&](const int jb) {
+        const int nbk = min(MF_NB, k - jb);
+        const int i = jb + tid;
+#pragma unroll
+        for (int jj = 0; jj < MF_NB; ++jj) lreg[jj] = (i < nf && jj < nbk) ? L[i + (size_t)(jb + jj) * nf] : 0.0;
+    };
+    prefetch(0);   // first panel block in flight under the gathers below
+    for (int r = tid; r < k; r += MF_TT) {
+        rows[r] = perm[fr.first + psrc[fr.first + r]];
+        posmap[r] = pdst[fr.first + r];
+    }
+    __syncthreads();
+    // own rows from the caller's column-major block (lanes: consecutive positions of one column), boundary rows zero
+    for (int cc = wid; cc < ncol; cc += MF_TT / 32)
+        for (int r = lane; r < k; r += 32) YW[r * MF_LDT + cc] = B[(size_t)rows[r] + (size_t)N * (c0 + cc)];
+    for (int t = q; t < s; t += MF_RG) YW[(k + t) * MF_LDT + c] = 0.0;
+    __syncthreads();
+    for (int ci = fr.c0; ci < fr.c1; ++ci) {  // updates of the children, in list order (rows of one child are distinct)
+        const MfFront ch = fronts[child_idx[ci]];
+        const int* r = rel + ch.soff;
+        const double* cw = W + (size_t)ch.w * nrhs + col;
+        if (live)
+            for (int t = q; t < ch.s; t += MF_RG) {
+                const int loc = r[t];
+                const int pos = loc < k ? posmap[loc] : loc;
+                YW[pos * MF_LDT + c] += cw[(size_t)t * nrhs];
+            }
+        __syncthreads();
+    }
+    // blocked forward substitution with the unit-lower L11 and the boundary update w -= L21 y in one sweep over the rows
+    for (int jb = 0; jb < k; jb += MF_NB) {
+        const int nbk = min(MF_NB, k - jb);
+        __syncthreads();   // the previous block's reads of Lb and its row updates are complete
+        if (jb + tid < nf) {
+            double2* dst = reinterpret_cast<double2*>(Lb + (size_t)tid * MF_NB);
+#pragma unroll
+            for (int jj = 0; jj < MF_NB; jj += 2) dst[jj >> 1] = make_double2(lreg[jj], lreg[jj + 1]);
+        }
+        __syncthreads();
+        if (jb + MF_NB < k) prefetch(jb + MF_NB);
+        double yb[MF_NB];
+#pragma unroll
+        for (int jj = 0; jj < MF_NB; ++jj) yb[jj] = jj < nbk ? YW[(jb + jj) * MF_LDT + c] : 0.0;
+#pragma unroll
+        for (int ii = 1; ii < MF_NB; ++ii) {   // diagonal block (block-uniform guard: a short last block stops early)
+            if (ii >= nbk) break;
+            const double2* l2 = reinterpret_cast<const double2*>(Lb + (size_t)ii * MF_NB);
+            double acc = yb[ii], acc2 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj + 1 < ii; jj += 2) {
+                const double2 l = l2[jj >> 1];
+                acc = fma(-l.x, yb[jj], acc);
+                acc2 = fma(-l.y, yb[jj + 1], acc2);
+            }
+            if (ii & 1) acc = fma(-Lb[ii * MF_NB + ii - 1], yb[ii - 1], acc);
+            yb[ii] = acc + acc2;
+        }
+        if (q == 0 && live) {   // these rows of y are final
+            double* yo = Y + (size_t)(fr.first + jb) * nrhs + col;
+#pragma unroll
+            for (int ii = 0; ii < MF_NB; ++ii)
+                if (ii < nbk) yo[(size_t)ii * nrhs] = yb[ii];
+        }
+        for (int i = jb + nbk + q; i < nf; i += MF_RG) {
+            const double2* l2 = reinterpret_cast<const double2*>(Lb + (size_t)(i - jb) * MF_NB);
+            double acc = YW[i * MF_LDT + c], acc2 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < MF_NB; jj += 2) {
+                const double2 l = l2[jj >> 1];
+                acc = fma(-l.x, yb[jj], acc);
+                acc2 = fma(-l.y, yb[jj + 1], acc2);
+            }
+            YW[i * MF_LDT + c] = acc + acc2;
+        }
+    }
+    __syncthreads();
+    if (live) {
+        double* wout = W + (size_t)fr.w * nrhs + col;
+        for (int t = q; t < s; t += MF_RG) wout[(size_t)t * nrhs] = YW[(k + t) * MF_LDT + c];
+    }
+}
+
+__global__ void __launch_bounds__(MF_TT) mf_backward_tiled_kernel(const int* list, const MfFront* fronts, const int* strct, const int* perm,
+                                                                  const double* Lp, const double* Up, double* Y, double* X,
+                                                                  const long long N, const int nrhs) {
+    extern __shared__ __align__(16) double mf_smem[];
+    const int fid = list[blockIdx.x];
+    const MfFront fr = fronts[fid];
+    const int k = fr.k, s = fr.s, nf = k + s;
+    const int tid = threadIdx.x, c = tid & (MF_TC - 1), q = tid >> 6, lane = tid & 31, wid = tid >> 5;
+    const int c0 = blockIdx.y * MF_TC, col = c0 + c;
+    const int ncol = min(MF_TC, nrhs - c0);
+    const bool live = col < nrhs;
+    double* YW = mf_smem;                                  // rows 0..k-1: y -> x; rows k..nf-1: boundary solutions
+    double* Ub = YW + (size_t)nf * MF_LDT;                 // [k][MF_NB]: rows of the current column block of [U11 U12]
+    Ub += ((size_t)nf * MF_LDT) & 1;
+    const double* L = Lp + fr.lp;
+    const double* U12 = Up + fr.up;
+    const int* sp = strct + fr.soff;
+    if (live) {
+        for (int r = q; r < k; r += MF_RG) YW[r * MF_LDT + c] = Y[(size_t)(fr.first + r) * nrhs + col];
+        for (int t = q; t < s; t += MF_RG) YW[(k + t) * MF_LDT + c] = Y[(size_t)sp[t] * nrhs + col];
+    }
+    // column blocks of [U11 U12] from the right: boundary blocks (plain updates), then the blocks of U11 (solve + update)
+    const int nbb = (s + MF_NB - 1) / MF_NB, npb = (k + MF_NB - 1) / MF_NB;
+    double ureg[MF_NB];
+    auto block_col0 = [&](const int b) { return b < nbb ? k + b * MF_NB : (npb - 1 - (b - nbb)) * MF_NB; };
+    auto prefetch = [&](const int b) {
+        const int jb = block_col0(b);
+        const int lim = jb >= k ? nf : k;          // last column of this kind
+        const int rows_needed = jb >= k ? k : min(jb + MF_NB, k);
+#pragma unroll
+        for (int jj = 0; jj < MF_NB; ++jj) {
+            const int j = jb + jj;
+            double v = 0.0;
+            if (tid < rows_needed && j < lim) v = j < k ? L[tid + (size_t)j * nf] : U12[tid + (size_t)(j - k) * k];
+            ureg[jj] = v;
+        }
+    };
+    double pend[MF_NB];
+    int pend_jb = -1;
+    const int nblocks = nbb + npb;
+    prefetch(0);
+    for (int b = 0; b < nblocks; ++b) {
+        const int jb = block_col0(b);
+        const bool pivot_block = jb < k;
+        const int nbk = pivot_block ? min(MF_NB, k - jb) : min(MF_NB, nf - jb);
+        __syncthreads();   // the previous block is applied: its solved rows may be published, Ub may be overwritten
+        if (pend_jb >= 0 && q == 0) {
+#pragma unroll
+            for (int ii = 0; ii < MF_NB; ++ii)
+                if (pend_jb + ii < k) YW[(pend_jb + ii) * MF_LDT + c] = pend[ii];
+        }
+        pend_jb = -1;
+        if (tid < k) {
+            double2* dst = reinterpret_cast<double2*>(Ub + (size_t)tid * MF_NB);
+#pragma unroll
+            for (int jj = 0; jj < MF_NB; jj += 2) dst[jj >> 1] = make_double2(ureg[jj], ureg[jj + 1]);
+        }
+        __syncthreads();
+        if (b + 1 < nblocks) prefetch(b + 1);
+        double xb[MF_NB];
+#pragma unroll
+        for (int jj = 0; jj < MF_NB; ++jj) xb[jj] = jj < nbk ? YW[(jb + jj) * MF_LDT + c] : 0.0;
+        int top = k;   // rows [0, top) receive this block's update
+        if (pivot_block) {
+#pragma unroll
+            for (int ii = MF_NB - 1; ii >= 0; --ii) {
+                if (ii < nbk) {
+                    const double* ur = Ub + (size_t)(jb + ii) * MF_NB;
+                    double acc = xb[ii], acc2 = 0.0;
+#pragma unroll
+                    for (int jj = ii + 1; jj < MF_NB; ++jj) {   // columns beyond nbk are zero-padded
+                        if ((jj - ii) & 1) acc = fma(-ur[jj], xb[jj], acc);
+                        else acc2 = fma(-ur[jj], xb[jj], acc2);
+                    }
+                    xb[ii] = (acc + acc2) / ur[ii];
+                }
+            }
+#pragma unroll
+            for (int ii = 0; ii < MF_NB; ++ii) pend[ii] = xb[ii];
+            pend_jb = jb;
+            top = jb;
+        }
+        for (int i = q; i < top; i += MF_RG) {
+            const double2* u2 = reinterpret_cast<const double2*>(Ub + (size_t)i * MF_NB);
+            double acc = YW[i * MF_LDT + c], acc2 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < MF_NB; jj += 2) {
+                const double2 u = u2[jj >> 1];
+                acc = fma(-u.x, xb[jj], acc);
+                acc2 = fma(-u.y, xb[jj + 1], acc2);
+            }
+            YW[i * MF_LDT + c] = acc + acc2;
+        }
+    }
+    __syncthreads();
+    if (pend_jb >= 0 && q == 0) {
+#pragma unroll
+        for (int ii = 0; ii < MF_NB; ++ii)
+            if (pend_jb + ii < k) YW[(pend_jb + ii) * MF_LDT + c] = pend[ii];
+    }
+    __syncthreads();
+    if (!fr.leaf && live)   // separator rows are read by the fronts below
+        for (int r = q; r < k; r += MF_RG) Y[(size_t)(fr.first + r) * nrhs + col] = YW[r * MF_LDT + c];
+    // solution rows back into the caller's column-major block (lanes: consecutive rows of one column)
+    for (int cc = wid; cc < ncol; cc += MF_TT / 32)
+        for (int r = lane; r < k; r += 32) X[(size_t)perm[fr.first + r] + (size_t)N * (c0 + cc)] = YW[r * MF_LDT + cc];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Leaf fronts (tree level 0: no children, k <= KMAX) hold most rows of the matrix, so their sweeps carry the N x nrhs
 // block through HBM.  One thread per right-hand side column with ITS k entries in registers (all loops unrolled to
 // KMAX, panels zero-padded in shared memory and read as broadcast 16-byte loads), the row interchanges folded into
@@ -355,9 +606,12 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
     // rows of this front from the caller's column-major block: consecutive threads take consecutive rows of one
     // column (the front's rows are sorted runs of the original numbering), transposed through shared memory
     const int c0 = blockIdx.y * MF_LEAF_TC, ncol = min(MF_LEAF_TC, nrhs - c0);
-    for (int idx = tid; idx < k * ncol; idx += MF_LEAF_TC) {
-        const int r = idx % k, c = idx / k;
-        Ts[c * LDT + r] = B[(size_t)rows[r] + (size_t)N * (c0 + c)];
+    {   // (k <= 32: lane = position, one warp per column, eight columns in flight per warp)
+        const int lane = tid & 31, wid = tid >> 5;
+        const size_t row = lane < k ? (size_t)rows[lane] : 0;
+#pragma unroll 8
+        for (int c = wid; c < ncol; c += MF_LEAF_TC / 32)
+            if (lane < k) Ts[c * LDT + lane] = __ldcs(B + row + (size_t)N * (c0 + c));
     }
     __syncthreads();
     double y[MF_KMAX];
@@ -469,9 +723,12 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int*
     }
     __syncthreads();
     const int c0 = blockIdx.y * MF_LEAF_TC, ncol = min(MF_LEAF_TC, nrhs - c0);
-    for (int idx = tid; idx < k * ncol; idx += MF_LEAF_TC) {
-        const int r = idx % k, c = idx / k;
-        X[(size_t)rows[r] + (size_t)N * (c0 + c)] = Ts[c * LDT + r];
+    {
+        const int lane = tid & 31, wid = tid >> 5;
+        const size_t row = lane < k ? (size_t)rows[lane] : 0;
+#pragma unroll 8
+        for (int c = wid; c < ncol; c += MF_LEAF_TC / 32)
+            if (lane < k) __stcs(X + row + (size_t)N * (c0 + c), Ts[c * LDT + lane]);
     }
 }
 
@@ -533,7 +790,7 @@ struct Dissector {
     // the small separator fronts: a tree level costs a kernel launch per sweep, the extra fill is a few dense blocks of
     // separator size).  `sink`: the collecting front of the enclosing group (nullptr: the next cut opens a new group),
     // `remaining`: dissection levels the enclosing group still absorbs.
-    int group_levels = 3;
+    int group_levels = 2;
 
     // orders all vertices of `verts` (all carrying region id rid)
     void dissect(std::vector<int32_t>& verts, int32_t rid, std::vector<int32_t>* sink = nullptr, int remaining = 0) {
@@ -1005,12 +1262,13 @@ struct SparseMfImpl {
     MfHost H;
     std::vector<std::vector<int32_t>> snodes;
     Graph g;
-    DevBuf fronts, perm, strct, rel, child_idx, aloc, asrc, lists, big_off, big_scratch, vals, Lp, Up, CB, piv, status, Y, W;
+    DevBuf fronts, perm, strct, rel, child_idx, aloc, asrc, lists, big_off, big_scratch, vals, Lp, Up, CB, piv, status, Y, W, psrc, pdst;
     int retries = 0;
+    bool netperm = false;
     double analysis_ms = 0.0;
     void release() {
         for (DevBuf* b : {&fronts, &perm, &strct, &rel, &child_idx, &aloc, &asrc, &lists, &big_off, &big_scratch, &vals, &Lp, &Up, &CB, &piv,
-                          &status, &Y, &W})
+                          &status, &Y, &W, &psrc, &pdst})
             b->release();
     }
 };
@@ -1072,6 +1330,22 @@ int32_t mf_numeric(diffopt_b200_ctx* ctx, SparseMfImpl& M, int64_t nnz, std::vec
         }
         ctx->launches++;
         DO_CUDA(ctx, cudaGetLastError());
+    }
+    {   // net row permutation of every front (used by the tiled solve kernels)
+        DO_CUDA(ctx, M.psrc.reserve(sizeof(int) * H.perm.size()));
+        DO_CUDA(ctx, M.pdst.reserve(sizeof(int) * H.perm.size()));
+        int maxk = 1;
+        for (const MfFront& f : H.fronts) maxk = std::max(maxk, f.k);
+        const size_t smem = sizeof(int) * 2 * (size_t)maxk;
+        if (smem <= MF_SMEM_CAP) {
+            DO_CUDA(ctx, cudaFuncSetAttribute(mf_netperm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            const int nfr = (int)H.fronts.size();
+            mf_netperm_kernel<<<(unsigned)std::min(nfr, ctx->sm_count * 32), 64, smem, ctx->stream>>>(M.fronts.as<MfFront>(), nfr, M.piv.as<int>(),
+                                                                                                      M.psrc.as<int>(), M.pdst.as<int>());
+            ctx->launches++;
+            DO_CUDA(ctx, cudaGetLastError());
+            M.netperm = true;
+        } else M.netperm = false;
     }
     DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     std::vector<int> st(H.fronts.size());
@@ -1192,12 +1466,26 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
         return ((size_t)L.max_k * L.max_k + (size_t)L.max_k * L.max_s + (size_t)MF_TC * (L.max_k | 1) + (size_t)MF_TC * (L.max_s | 1)) *
                sizeof(double);
     };
+    const bool use_tiled = M.netperm && getenv("DIFFOPT_B200_MF_OLD_SOLVE") == nullptr;
+    auto tiled_smem = [](const MfLaunch& L, bool fwd) {
+        return sizeof(double) * ((size_t)L.max_nf * MF_LDT + 1 + (size_t)(fwd ? L.max_nf : L.max_k) * MF_NB) + (fwd ? sizeof(int) * 2 * (size_t)L.max_k : 0);
+    };
+    auto tiled_group = [&](const MfLaunch& L) {
+        return use_tiled && !L.big && L.max_nf <= MF_TT && tiled_smem(L, true) <= MF_SMEM_CAP && smem_fwd(L) <= MF_SMEM_CAP && smem_bwd(L) <= MF_SMEM_CAP;
+    };
     for (const MfLaunch& L : H.launches) {
         if (L.count == 0) continue;
         const dim3 grid((unsigned)L.count, tiles);
         const size_t smem = smem_fwd(L);
         const bool big = L.big || smem > MF_SMEM_CAP;
-        if (leaf_group(L)) {
+        if (!leaf_group(L) && tiled_group(L)) {
+            const size_t ts = tiled_smem(L, true);
+            DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ts, 1024)));
+            mf_forward_tiled_kernel<<<grid, MF_TT, ts, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.child_idx.as<int>(),
+                                                                      M.rel.as<int>(), M.perm.as<int>(), M.psrc.as<int>(), M.pdst.as<int>(),
+                                                                      M.Lp.as<double>(), (const double*)dB, M.Y.as<double>(), M.W.as<double>(), N,
+                                                                      (int)nrhs);
+        } else if (leaf_group(L)) {
             const size_t ls = sizeof(double) * std::max<size_t>((size_t)L.max_nf * MF_KMAX, (size_t)MF_LEAF_TC * (MF_KMAX + 1));
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ls, 1024)));
             mf_forward_leaf_kernel<<<dim3((unsigned)L.count, ltiles), MF_LEAF_TC, ls, ctx->stream>>>(
@@ -1223,7 +1511,13 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
         const dim3 grid((unsigned)L.count, tiles);
         const size_t smem = smem_bwd(L);
         const bool big = L.big || smem > MF_SMEM_CAP || smem_fwd(L) > MF_SMEM_CAP;
-        if (leaf_group(L)) {
+        if (!leaf_group(L) && tiled_group(L)) {
+            const size_t ts = tiled_smem(L, false);
+            DO_CUDA(ctx, cudaFuncSetAttribute(mf_backward_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ts, 1024)));
+            mf_backward_tiled_kernel<<<grid, MF_TT, ts, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.strct.as<int>(),
+                                                                       M.perm.as<int>(), M.Lp.as<double>(), M.Up.as<double>(), M.Y.as<double>(),
+                                                                       (double*)dX, N, (int)nrhs);
+        } else if (leaf_group(L)) {
             const size_t ls = sizeof(double) * std::max<size_t>((size_t)(MF_KMAX + L.max_s) * MF_KMAX, (size_t)MF_LEAF_TC * (MF_KMAX + 1));
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_backward_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ls, 1024)));
             mf_backward_leaf_kernel<<<dim3((unsigned)L.count, ltiles), MF_LEAF_TC, ls, ctx->stream>>>(

@@ -183,7 +183,7 @@ def solve_batch_ex(ctx, Q, G, A, h, z, lam, nu, fwd_dir=None, seed=None, shared_
     return fwd, rev, info
 
 
-def shared_param_grads(ctx, z, lam, nu, rev, allreduce=False):
+def shared_param_grads(ctx, z, lam, nu, rev, allreduce=False, flat=False):
     """``diffopt_b200_qp_batch_shared_grads``: batch sums of the reverse-mode parameter gradients (dQ, dq, dG, dh, dA, db)
     for parameters shared by all instances; ``allreduce`` adds the NCCL all-reduce over the ranks of
     ``sharding.nccl_init``.  Returns logical (row-major) arrays like ``QPBatch.param_grads(reduce_over_batch=True)``."""
@@ -198,7 +198,40 @@ def shared_param_grads(ctx, z, lam, nu, rev, allreduce=False):
     rc = ctx.lib.diffopt_b200_qp_batch_shared_grads(ctx.h, B, n, m, p, ptr(z), ptr(vec(lam, m)), ptr(vec(nu, p)), ptr(rev),
                                                     ptr(out), HOST, _capi.QP_ALLREDUCE if allreduce else 0)
     ctx.check(rc)
-    return unflatten_param_grads(out, n, m, p)
+    return out if flat else unflatten_param_grads(out, n, m, p)
+
+
+def flat_index(n, m, p, block, i=0, j=0):
+    """1-based position of a gradient entry inside the flat block [dQ | dq | dG | dh | dA | db] (matrices column-major):
+    ``block`` in "dQ" (i, j), "dq" (i), "dG" (row i, variable j), "dh" (i), "dA" (row i, variable j), "db" (i); i, j 0-based."""
+    off = {"dQ": 0, "dq": n * n, "dG": n * n + n, "dh": n * n + n + m * n, "dA": n * n + n + m * n + m,
+           "db": n * n + n + m * n + m + p * n}[block]
+    rows = {"dQ": n, "dG": m, "dA": p}.get(block)
+    return off + (i + j * rows if rows is not None else i) + 1
+
+
+def parameter_pullback(ctx, terms, flat, nparams):
+    """``diffopt_b200_param_pullback``: reverse-mode accumulation into parameters (src/parameters.jl:341-534).  ``terms``:
+    iterable of (parameter (0-based), flat index (1-based, ``flat_index``), coefficient); ``flat``: the gradient block of
+    ``shared_param_grads(..., flat=True)`` (numpy array, or a device tensor consumed in place)."""
+    terms = list(terms)
+    tp = np.ascontiguousarray([t[0] + 1 for t in terms], dtype=np.int64)
+    ti = np.ascontiguousarray([t[1] for t in terms], dtype=np.int64)
+    tc = np.ascontiguousarray([t[2] for t in terms], dtype=np.float64)
+    out = np.empty(nparams)
+    on_device = hasattr(flat, "data_ptr")
+    nflat = int(flat.numel()) if on_device else int(np.asarray(flat).size)
+    if not on_device:
+        flat = np.ascontiguousarray(flat, dtype=np.float64)
+    if on_device:
+        import torch
+        dout = torch.empty(nparams, dtype=torch.float64, device=flat.device)
+        rc = ctx.lib.diffopt_b200_param_pullback(ctx.h, len(terms), ptr(tp), ptr(ti), ptr(tc), nflat, ptr(flat), nparams, ptr(dout), 1)
+        ctx.check(rc)
+        return dout
+    rc = ctx.lib.diffopt_b200_param_pullback(ctx.h, len(terms), ptr(tp), ptr(ti), ptr(tc), nflat, ptr(flat), nparams, ptr(out), HOST)
+    ctx.check(rc)
+    return out
 
 
 def unflatten_param_grads(flat, n, m, p):
@@ -339,3 +372,28 @@ class QPModel:
         dz, dlam, _ = self.back_grad_cache
         l = self.lam[i]
         return l * dlam[i] * self.x + l * dz                       # :467-473
+
+
+def poi_terms(n, m, p, constraints, objective=None, param_values=None):
+    """Term triplets for ``parameter_pullback`` from parametric functions as ParametricOptInterface holds them
+    (src/parameters.jl:341-534).  ``constraints``: list of dicts with ``row`` = ("ineq", i) or ("eq", i) (row of G / A the
+    inner constraint became, already in LessThan / EqualTo form) and the term lists ``p`` [(param, coef)], ``pp``
+    [(param1, param2, coef)], ``pv`` [(param, variable, coef)]; ``objective``: dict with the same lists (only its p v
+    terms reach the solution: the constant of ReverseObjectiveFunction is zero).  Parameters 0-based."""
+    out = []
+    for c in constraints:
+        kind, i = c["row"]
+        cte = flat_index(n, m, p, "dh" if kind == "ineq" else "db", i)
+        blk = "dG" if kind == "ineq" else "dA"
+        for (prm, coef) in c.get("p", []):                        # coef * grad_cte, grad_cte = -dh_i / -db_i  (:349-360)
+            out.append((prm, cte, -coef))
+        for (p1, p2, coef) in c.get("pp", []):                    # :410-430 (a squared parameter lands once: both reads
+            out.append((p1, cte, -coef * param_values[p2]))       #  happen before either write)
+            if p2 != p1:
+                out.append((p2, cte, -coef * param_values[p1]))
+        for (prm, v, coef) in c.get("pv", []):                    # coef * coefficient(grad_pf, v)  (:431-437)
+            out.append((prm, flat_index(n, m, p, blk, i, v), coef))
+    if objective is not None:
+        for (prm, v, coef) in objective.get("pv", []):            # :513-518
+            out.append((prm, flat_index(n, m, p, "dq", v), coef))
+    return out

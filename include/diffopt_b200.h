@@ -289,6 +289,29 @@ int32_t diffopt_b200_conic_batch_reverse(
     double atol, double btol, double conlim, int64_t maxiter,
     double* g_out, double* dc_out, double* db_out, double* out_stats, int32_t memspace);
 
+/* ---- callers next to the hot path ------------------------------------------------------------------
+ *
+ * NonLinearProgram backend, `_lu_with_inertia_correction` (NonLinearProgram.jl:356-435): factorise M (host CSC, 1-based);
+ * if the factorisation reports a singular matrix (`K.status == 1`), factorise J = M + c st D for c = 1, 2, ... until it
+ * succeeds, D = diag(+1 on rows 1..num_w, -1 on the next num_cons rows, +1 on the rest), at most max_corrections
+ * corrected factorisations.  corrections_out = c (0: M itself was fine).  Returns 0, or > 0 when the last attempt was
+ * still singular (the reference warns "Inertia correction failed." and returns zeros).  The factorisation stays in the
+ * ctx: `K \ N` for all parameter columns at once (nlp_utilities.jl:436-444, caller negates) is diffopt_b200_sparse_solve. */
+int32_t diffopt_b200_sparse_setup_inertia(
+    diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+    int64_t num_w, int64_t num_cons, double st, int32_t max_corrections, int32_t* corrections_out);
+
+/* Reverse-mode accumulation into parameters (src/parameters.jl:341-534): out[param] = sum over terms of
+ * coef * flat[index], param / index 1-based, term lists in HOST memory (they describe the model), terms of one
+ * parameter summed in the order given.  `flat` is a gradient block as diffopt_b200_qp_batch_shared_grads lays it out
+ * ([dQ | dq | dG | dh | dA | db], host or device per memspace; device: the batch-summed, all-reduced block is consumed
+ * in place).  How the reference's term kinds map to (index, coef): affine p term in constraint row i with coefficient c:
+ * (dh_i or db_i, -c) -- the constant of ReverseConstraintFunction is -dh_i (QuadraticProgram.jl:307-314); p v term:
+ * (dG_iv / dA_iv / dq_v, c); p p term: (dh_i or db_i, -c * value of the other parameter), once per parameter. */
+int32_t diffopt_b200_param_pullback(
+    diffopt_b200_ctx* ctx, int64_t nterms, const int64_t* term_param, const int64_t* term_index, const double* term_coef,
+    int64_t nflat, const double* flat, int64_t nparams, double* out, int32_t memspace);
+
 #ifdef __cplusplus
 }
 #endif

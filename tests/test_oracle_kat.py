@@ -236,3 +236,62 @@ def test_psd_gradient_is_transposed_jacobian():
         J[:, j] = (cones.project(v + e, cones.PSD) - cones.project(v - e, cones.PSD)) / (2 * eps)
     assert np.allclose(D.T, J, atol=1e-6)
     assert not np.allclose(D, D.T, atol=1e-3)
+
+
+# ---- NLP factorisation with inertia correction, parameter pull-back -------------------------------
+
+def nlp_inertia_kat_matrix():
+    """The reference's own case, test/nlp_program.jl:767-795 (KAT 15): a KKT Jacobian whose first two columns are
+    parallel (lambda2 = 0, mu = 0), so `lu(M; check = false)` reports status 1."""
+    x1, x2 = 0.33, 0.33
+    lambda1, lambda2 = 0.333, 0.00
+    mu_val = 0.00
+    return np.array([
+        [0, 0, -1, -2, -1],
+        [0, 0, -2, -1, 0],
+        [-lambda1, -2 * lambda1, (1 - x1 - 2 * x2), 0, 0],
+        [-2 * lambda2, -lambda2, 0, (1 - 2 * x1 - x2), 0],
+        [mu_val, 0, 0, 0, x1]], dtype=float)
+
+
+def test_kat15_inertia_correction():
+    from oracle import nlp
+    import scipy.sparse as sp
+    M = sp.csc_matrix(nlp_inertia_kat_matrix())
+    K, status = nlp._lu(M)
+    assert status == 1                                   # `@assert K.status == 1 # Fail`
+    K, nc = nlp.inertia_correction(M, 3, 2, st=1e-6, max_corrections=50)
+    assert K is not None and nc == 1                     # `@test K.status == 0 # Success`
+    K2, nc2 = nlp.lu_with_inertia_correction(M, 2, 3)
+    assert K2 is not None and nc2 == 1
+    # a regular matrix is factorised as it is
+    R = sp.csc_matrix(nlp_inertia_kat_matrix() + np.eye(5))
+    assert nlp.lu_with_inertia_correction(R, 2, 3)[1] == 0
+
+
+def quadratic_rhs_case(pv, qv, rv, sv, tv, dir_x):
+    """test/parameters.jl:317-445 (KAT 16):  min 2x  s.t.  11 t x >= 1 + 3 p q + 5 r^2 + 7 s.  Inner problem in the QP
+    backend's form (n = 1, one inequality G z <= h): G = -11 t, h = -(1 + 3pq + 5r^2 + 7s).  Returns the QP data, the
+    parametric terms of the constraint as POI holds them (function 11 t x - 3 p q - 5 r^2 - 7 s - 1 in GreaterThan(0),
+    flipped to LessThan: -11 t x + 3 p q + 5 r^2 + 7 s + 1 <= 0; MOI's quadratic coefficient of r^2 is 2 x 5) and the
+    expected parameter sensitivities."""
+    c = 1 + 3 * pv * qv + 5 * rv ** 2 + 7 * sv
+    d = dict(Q=np.zeros((1, 1, 1)), q=np.array([[2.0]]), G=np.array([[[-11.0 * tv]]]), h=np.array([[-c]]),
+             A=np.zeros((1, 0, 1)), b=np.zeros((1, 0)), z=np.array([[c / (11 * tv)]]), lam=np.array([[2 / (11 * tv)]]),
+             nu=np.zeros((1, 0)), seed=np.array([[float(dir_x)]]))
+    terms = dict(p=[(3, 7.0)], pp=[(0, 1, 3.0), (2, 2, 10.0)], pv=[(4, 0, -11.0)])   # parameters p, q, r, s, t = 0..4
+    expect = dir_x * np.array([3 * qv / (11 * tv), 3 * pv / (11 * tv), 10 * rv / (11 * tv), 7 / (11 * tv), -c / (11 * tv ** 2)])
+    return d, terms, expect
+
+
+@pytest.mark.parametrize("vals", [(2, 2, 2, 2, 2), (2, 3, 2, 3, 3), (3, 2, 3, 2, 2)])
+def test_kat16_parameter_pullback(vals):
+    from oracle import nlp
+    for dir_x in range(4):
+        d, terms, expect = quadratic_rhs_case(*vals, dir_x)
+        dz, dlam, dnu = qp.reverse(d["Q"][0], d["G"][0], d["h"][0], d["A"][0], d["z"][0], d["lam"][0], d["nu"][0], d["seed"][0])
+        dQ, dq, dG, dh, dA, db = qp.reverse_param_grads(d["z"][0], d["lam"][0], d["nu"][0], dz, dlam, dnu)
+        # ReverseConstraintFunction of the LessThan row: coefficients dG, constant -dh (QuadraticProgram.jl:307-314)
+        con = dict(grad_cte=-dh[0], grad_coef={0: dG[0, 0]}, **terms)
+        got = nlp.reverse_parameters(5, [con], None, np.array(vals, float))
+        assert np.allclose(got, expect, atol=1e-10), (vals, dir_x, got, expect)
