@@ -412,6 +412,7 @@ def run_b200(args, rank, world, local_rank):
         step_e2e()
     e2e_steps = max(2, min(args.steps, 10))
     ms_e2e, _ = timed(step_e2e, e2e_steps)
+    e2e_variants = e2e_byte_variants(args, ctx, lib, capi, hb, logical, B, BT, world, timed, check, fwd_h, rev_h, info_h, e2e_steps)
 
     # weak-scaling companion number (second field): every rank a full 4096-instance batch of its own
     weak = None
@@ -437,11 +438,22 @@ def run_b200(args, rank, world, local_rank):
     aux = active_set_sweep(args, ctx, lib, capi, dev, timed, check, dptr) if world == 1 and not args.no_aux else None
     if aux is not None:
         # second half of the BASELINE.json metric ("sparse solve ms"): config 3, one sparse KKT system with 256 right-hand sides
+        import bench_aux
         try:
-            import bench_aux
             aux["sparse_config3"] = bench_aux.config3(ctx, cpu=not args.no_cpu)
         except Exception as e:  # the headline line must survive a failure here
             aux["sparse_config3"] = {"error": str(e)[:300]}
+        # conic side of the path (configs 4, 5): lock-step batch of config-4 problems (the HBM-meaningful form),
+        # config 4 converged on the conditioned generator, the 200 x 200 PSD cone
+        for key, fn in (("conic_batch_config4", lambda: bench_aux.run_conic_batch(ctx, B=296, iters=100, emit=False)),
+                        ("conic_config4_converged", lambda: bench_aux.run_conic(
+                            ctx, "4c", __import__("bench_data").conic_config4_conditioned(), iters=None,
+                            cpu_iters=None if not args.no_cpu else 0, emit=False)),
+                        ("psd_config5", lambda: bench_aux.config5(ctx, emit=False))):
+            try:
+                aux[key] = fn()
+            except Exception as e:
+                aux[key] = {"error": str(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -490,6 +502,7 @@ def run_b200(args, rank, world, local_rank):
                        "host_numa": numa},
             "roofline": roofline, "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": in_bytes * world,
                                           "d2h_bytes_per_step": out_bytes * world, "ms_per_step": ms_e2e / e2e_steps},
+            "e2e_variants": e2e_variants,
             "gpu_launches": launches, "clocks": clocks, "parity_rel_err": err}
     if weak:
         line["weak"] = weak
@@ -504,6 +517,55 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_byte_variants(args, ctx, lib, capi, hb, logical, B, BT, world, timed, check, fwd_h, rev_h, info_h, steps):
+    """The end-to-end call is PCIe bound (r1: 97 % of the step is the host-to-device copy), so the boundary accepts the
+    same problem in fewer bytes (diffopt_b200_qp_batch_solve_ex).  Same metric, host (pinned) buffers, H2D + kernels + D2H
+    inside the timed region:
+      packed_triangles  Q and dQ as packed lower triangles (both are symmetric: utils.jl:46-69)
+      shared_matrices   OptNet layer: Q, G, A and the direction dQ, dG, dA are ONE instance for the whole batch"""
+    import diffopt_b200
+    qpm = diffopt_b200.submodule("qp")
+    out = {}
+    pk = {k: capi.pinned_empty((B, N_VAR * (N_VAR + 1) // 2)) for k in ("Q", "dQ")}
+    for k in pk:
+        np.copyto(pk[k], qpm.pack_lower(logical[k]))
+
+    def args_for(sub):
+        return [capi.ptr(sub.get(k, hb[k])) for k in FIELDS]
+
+    def step_packed():
+        check(lib.diffopt_b200_qp_batch_solve_ex(ctx.h, B, N_VAR, M_INEQ, P_EQ, *args_for(pk), capi.ptr(fwd_h), capi.ptr(rev_h),
+                                                 capi.ptr(info_h), capi.HOST, capi.QP_PACKED_Q), "qp_batch_solve_ex(packed)")
+    ref_f, ref_r = fwd_h.copy(), rev_h.copy()      # results of the plain end-to-end call on the same data
+    for _ in range(2):
+        step_packed()
+    if not (np.array_equal(fwd_h, ref_f) and np.array_equal(rev_h, ref_r)):
+        raise RuntimeError("packed-triangle end-to-end call differs from the plain call")
+    ms, _ = timed(step_packed, steps)
+    nb = sum((pk[k] if k in pk else hb[k]).nbytes for k in FIELDS)
+    out["packed_triangles"] = {"value": BT * steps / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms / steps,
+                               "h2d_bytes_per_step": nb * world, "check": "bitwise equal to the plain call"}
+    sh = {k: capi.pinned_empty(hb[k][:1].shape) for k in ("Q", "G", "A", "dQ", "dG", "dA")}
+    for k in sh:
+        np.copyto(sh[k], hb[k][:1])
+
+    def step_shared():
+        check(lib.diffopt_b200_qp_batch_solve_ex(ctx.h, B, N_VAR, M_INEQ, P_EQ, *args_for(sh), capi.ptr(fwd_h), capi.ptr(rev_h),
+                                                 capi.ptr(info_h), capi.HOST, capi.QP_SHARED_MATRICES | capi.QP_SHARED_DIRECTION),
+              "qp_batch_solve_ex(shared)")
+    for _ in range(2):
+        step_shared()
+    if info_h.any() or not np.isfinite(fwd_h).all():
+        raise RuntimeError("shared-matrix end-to-end call failed")
+    ms, _ = timed(step_shared, steps)
+    nb = sum((sh[k] if k in sh else hb[k]).nbytes for k in FIELDS)
+    out["shared_matrices"] = {"value": BT * steps / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms / steps,
+                              "h2d_bytes_per_step": nb * world,
+                              "note": "Q, G, A, dQ, dG, dA of instance 0 serve the whole batch (a different problem set than the "
+                                      "headline: the OptNet-shared form); parity of this entry: tests/test_qp_gpu.py"}
+    return out
 
 
 def shared_variant(args, rank, world, ctx, lib, capi, sharding, dev, db, logical, B, BT, timed, check, dptr):

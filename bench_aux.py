@@ -34,7 +34,7 @@ def lsqr_bytes_per_iter(nnzM, N):
     return 2 * (12 * nnzM + 4 * (N + 1)) + 88 * N
 
 
-def run_conic(ctx, name, d, iters, cpu_iters):
+def run_conic(ctx, name, d, iters, cpu_iters, emit=True):
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     import diffopt_b200
@@ -91,10 +91,12 @@ def run_conic(ctx, name, d, iters, cpu_iters):
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"us_per_iteration": 1e6 * dt / cpu_iters, "kind": "port", "cores": 1,
                                     "sample": f"scipy.sparse.linalg.lsqr on the explicit M (reference construction), {cpu_iters} iterations"}
-    print(json.dumps(line), flush=True)
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
-def run_conic_batch(ctx, B=512, iters=100, ctas=1):
+def run_conic_batch(ctx, B=512, iters=100, ctas=1, emit=True):
     """SURVEY 8(d) config 4 in its HBM-meaningful form: a lock-step batch of B independent config-4-sized problems (own
     sparsity, solution and seed each) advanced by one persistent kernel.  Fixed iteration count so the algorithmic bytes
     are exact; parity of the batch against single-problem solves is tests/test_conic_gpu.py's business."""
@@ -139,7 +141,9 @@ def run_conic_batch(ctx, B=512, iters=100, ctas=1):
             "rel_diff_problem0_vs_single_problem_path": float(np.linalg.norm(out["g"][0] - g1) / np.linalg.norm(g1)),
             "host_generate_s": gen_s, "batch_setup_s": setup_s}
     line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
-    print(json.dumps(line), flush=True)
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def config3(ctx, portfolio=False, nrhs=256, cpu=True):
@@ -272,49 +276,58 @@ def main():
     if "5b" in todo:
         run_psd_batch(ctx)
     if "5" in todo:
-        import scipy.sparse as sp
-        from oracle import cones as ocones
-        cm = diffopt_b200.submodule("conic")
-        dd, r = 200, 20
-        rng = np.random.default_rng(5)
-        V = rng.normal(size=(dd, r)); V /= np.linalg.norm(V, axis=1, keepdims=True)
-        X = V @ V.T
-        Qf, _ = np.linalg.qr(np.hstack([V, rng.normal(size=(dd, dd - r))]))
-        W = Qf[:, r:]
-        Smat = (W * rng.uniform(0.5, 1.5, size=dd - r)) @ W.T
-        k = dd * (dd + 1) // 2
-        s = np.concatenate([np.zeros(dd), ocones.vec_symm(X)])
-        y = np.concatenate([rng.normal(size=dd), ocones.vec_symm(Smat)])
-        iu = [(i * (i + 1) // 2 + i) for i in range(dd)]
-        A = sp.vstack([sp.csc_matrix((np.ones(dd), (np.arange(dd), iu)), shape=(dd, k)), -sp.identity(k)]).tocsc()
-        x = ocones.vec_symm(X)
-        model = cm.ConicModel(ctx, A, A @ x + s, -(A.T @ y), [ocones.ZERO, ocones.PSD], [dd, k])
-        model.set_variable_primal(x); model.set_constraint_primal(s); model.set_constraint_dual(y)
-        model.vp()
-        model.gradient_cache = False   # time the second setup: buffers allocated, modules loaded
-        model.vp()
-        setup_ms = model.setup_ms
-        t = rng.normal(size=dd + k)
+        config5(ctx)
+
+
+def config5(ctx, emit=True):
+    """BASELINE config 5: max-cut SDP with one 200 x 200 PSD cone -- eigendecomposition (setup), one Dpi apply, 50 LSQR iterations."""
+    import diffopt_b200
+    import scipy.sparse as sp
+    from oracle import cones as ocones
+    cm = diffopt_b200.submodule("conic")
+    dd, r = 200, 20
+    rng = np.random.default_rng(5)
+    V = rng.normal(size=(dd, r)); V /= np.linalg.norm(V, axis=1, keepdims=True)
+    X = V @ V.T
+    Qf, _ = np.linalg.qr(np.hstack([V, rng.normal(size=(dd, dd - r))]))
+    W = Qf[:, r:]
+    Smat = (W * rng.uniform(0.5, 1.5, size=dd - r)) @ W.T
+    k = dd * (dd + 1) // 2
+    s = np.concatenate([np.zeros(dd), ocones.vec_symm(X)])
+    y = np.concatenate([rng.normal(size=dd), ocones.vec_symm(Smat)])
+    iu = [(i * (i + 1) // 2 + i) for i in range(dd)]
+    A = sp.vstack([sp.csc_matrix((np.ones(dd), (np.arange(dd), iu)), shape=(dd, k)), -sp.identity(k)]).tocsc()
+    x = ocones.vec_symm(X)
+    model = cm.ConicModel(ctx, A, A @ x + s, -(A.T @ y), [ocones.ZERO, ocones.PSD], [dd, k])
+    model.set_variable_primal(x); model.set_constraint_primal(s); model.set_constraint_dual(y)
+    model.vp()
+    model.gradient_cache = False   # time the second setup: buffers allocated, modules loaded
+    model.vp()
+    setup_ms = model.setup_ms
+    t = rng.normal(size=dd + k)
+    model.dpi_apply(t)
+    ap_ms = []
+    for _ in range(3):
         model.dpi_apply(t)
-        ap_ms = []
-        for _ in range(3):
-            model.dpi_apply(t)
-            ap_ms.append(ctx.last_kernel_ms)
-        model.tolerances = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=50)
-        model.reverse_differentiate(rng.normal(size=k))
-        t0 = time.perf_counter()
-        w, U = np.linalg.eigh(X - Smat)
-        cpu_eig_ms = 1e3 * (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        ocones.Dpi_apply(y - s, [ocones.ZERO, ocones.PSD], [dd, k], t)
-        cpu_apply_ms = 1e3 * (time.perf_counter() - t0)
-        print(json.dumps({"config": "5: max-cut SDP, 200 x 200 PSD cone (20 100 triangle rows + 200 zero rows)",
-                          "setup_ms_incl_eigendecomposition": setup_ms, "dpi_apply_ms": min(ap_ms),
-                          "dpi_apply_gflops": 4 * 2 * dd ** 3 / (min(ap_ms) * 1e-3) / 1e9,
-                          "reverse_50_lsqr_iterations_ms": model.last_stats["kernel_ms"],
-                          "cpu_baseline": {"eigh_ms": cpu_eig_ms, "dpi_apply_ms_incl_eigh": cpu_apply_ms, "kind": "port",
-                                           "sample": "numpy eigh + operator-form apply; the reference's dense 20100^2 Jacobian "
-                                                     "(3.2 GB, ~1e12 flop) is not formed"}}), flush=True)
+        ap_ms.append(ctx.last_kernel_ms)
+    model.tolerances = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=50)
+    model.reverse_differentiate(rng.normal(size=k))
+    t0 = time.perf_counter()
+    w, U = np.linalg.eigh(X - Smat)
+    cpu_eig_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    ocones.Dpi_apply(y - s, [ocones.ZERO, ocones.PSD], [dd, k], t)
+    cpu_apply_ms = 1e3 * (time.perf_counter() - t0)
+    line = ({"config": "5: max-cut SDP, 200 x 200 PSD cone (20 100 triangle rows + 200 zero rows)",
+                      "setup_ms_incl_eigendecomposition": setup_ms, "dpi_apply_ms": min(ap_ms),
+                      "dpi_apply_gflops": 4 * 2 * dd ** 3 / (min(ap_ms) * 1e-3) / 1e9,
+                      "reverse_50_lsqr_iterations_ms": model.last_stats["kernel_ms"],
+                      "cpu_baseline": {"eigh_ms": cpu_eig_ms, "dpi_apply_ms_incl_eigh": cpu_apply_ms, "kind": "port",
+                                       "sample": "numpy eigh + operator-form apply; the reference's dense 20100^2 Jacobian "
+                                                 "(3.2 GB, ~1e12 flop) is not formed"}})
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def run_psd_batch(ctx):
