@@ -421,4 +421,127 @@ function DiffOpt._get_dA(model::ConicModel, ci::MOI.ConstraintIndex{<:MOI.Abstra
     return g[n.+i] * πz[1:n]' - πz[n.+i] * g[1:n]'
 end
 
+# ------------------------------------------------------------------------------------------------
+# (5) Batch-level entries used by training loops: shared weights, shared-parameter gradients, a lock-step batch of
+#     conic problems, parameter pull-back (src/parameters.jl:341-534)
+# ------------------------------------------------------------------------------------------------
+const QP_SHARED_MATRICES = Int32(1)
+const QP_SHARED_DIRECTION = Int32(2)
+const QP_PACKED_Q = Int32(4)
+const QP_ASYNC = Int32(8)
+const QP_ALLREDUCE = Int32(16)
+
+"reverse sensitivities of B problems that share Q, G, A (ONE instance each; an OptNet layer): `rev[n+m+p, B]`"
+function qp_batch_reverse_shared(ctx::Context, Q::Matrix{Float64}, G::Matrix{Float64}, A::Matrix{Float64},
+                                 h::Matrix{Float64}, z::Matrix{Float64}, lam::Matrix{Float64}, nu::Matrix{Float64},
+                                 dl_dz::Matrix{Float64})
+    n, B = size(z); m = size(G, 1); p = size(A, 1)
+    rev = Matrix{Float64}(undef, n + m + p, B)
+    info = zeros(Int32, B)
+    rc = ccall((:diffopt_b200_qp_batch_solve_ex, LIB), Int32,
+               (Ptr{Cvoid}, Int64, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32, Int32),
+               ctx.handle, B, n, m, p, Q, G, A, h, z, lam, nu, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, dl_dz, C_NULL, rev,
+               info, HOST, QP_SHARED_MATRICES)
+    check(ctx, rc)
+    return rev
+end
+
+"batch sum of the getters (QuadraticProgram.jl:307-314, :448-473) as one flat block [dQ | dq | dG | dh | dA | db]; `allreduce`: summed over the ranks of nccl_init"
+function qp_batch_shared_grads(ctx::Context, z::Matrix{Float64}, lam::Matrix{Float64}, nu::Matrix{Float64}, rev::Matrix{Float64};
+                               allreduce::Bool = false)
+    n, B = size(z); m = size(lam, 1); p = size(nu, 1)
+    out = Vector{Float64}(undef, n * n + n + m * n + m + p * n + p)
+    rc = ccall((:diffopt_b200_qp_batch_shared_grads, LIB), Int32,
+               (Ptr{Cvoid}, Int64, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32),
+               ctx.handle, B, n, m, p, z, lam, nu, rev, out, HOST, allreduce ? QP_ALLREDUCE : Int32(0))
+    check(ctx, rc)
+    return out
+end
+
+"""
+    param_pullback(ctx, term_param, term_index, term_coef, flat, nparams)
+
+`reverse_differentiate!(::POI.Optimizer)` in array form (src/parameters.jl:341-534): `out[p] = sum coef * flat[index]` over the
+parametric terms, `flat` the gradient block of `qp_batch_shared_grads`.  Index / coefficient of each term kind: see the header.
+"""
+function param_pullback(ctx::Context, term_param::Vector{Int64}, term_index::Vector{Int64}, term_coef::Vector{Float64},
+                        flat::Vector{Float64}, nparams::Integer)
+    out = Vector{Float64}(undef, nparams)
+    rc = ccall((:diffopt_b200_param_pullback, LIB), Int32,
+               (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int32),
+               ctx.handle, length(term_param), term_param, term_index, term_coef, length(flat), flat, nparams, out, HOST)
+    check(ctx, rc)
+    return out
+end
+
+"""
+    conic_batch_reverse(ctx, problems, dx; atol, btol, conlim, maxiter)
+
+`reverse_differentiate!` (ConicProgram.jl:336-394) of B conic problems of equal size in ONE persistent kernel.  `problems`:
+vector of named tuples `(A, b, c, x, s, y, cone_type, cone_dim)`; `dx[n, B]`.  Returns `(g[n+m+1, B], dc[n, B], db[m, B], stats[4, B])`.
+"""
+function conic_batch_reverse(ctx::Context, problems::Vector, dx::Matrix{Float64};
+                             atol = sqrt(eps()), btol = sqrt(eps()), conlim = 1 / sqrt(eps()), maxiter = 0)
+    B = length(problems)
+    rc = ccall((:diffopt_b200_conic_batch_begin, LIB), Int32, (Ptr{Cvoid}, Int64, Int32), ctx.handle, B, 1)
+    check(ctx, rc)
+    m, n = size(problems[1].A)
+    for pr in problems
+        A = pr.A::SparseArrays.SparseMatrixCSC{Float64,Int}
+        rc = ccall((:diffopt_b200_conic_batch_add, LIB), Int32,
+                   (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                    Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Int64}, Int32),
+                   ctx.handle, n, m, A.colptr, A.rowval, A.nzval, pr.b, pr.c, pr.x, pr.s, pr.y, length(pr.cone_type), pr.cone_type,
+                   pr.cone_dim, HOST)
+        check(ctx, rc)
+    end
+    g = Matrix{Float64}(undef, n + m + 1, B); dc = Matrix{Float64}(undef, n, B); db = Matrix{Float64}(undef, m, B)
+    stats = zeros(4, B)
+    rc = ccall((:diffopt_b200_conic_batch_reverse, LIB), Int32,
+               (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Float64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32),
+               ctx.handle, dx, atol, btol, conlim, maxiter, g, dc, db, stats, HOST)
+    check(ctx, rc)
+    return (g = g, dc = dc, db = db, stats = stats)
+end
+
+# ------------------------------------------------------------------------------------------------
+# (6) NonLinearProgram backend: the factorisation hook `model.input_cache.factorization(M, model)`
+#     (nlp_utilities.jl:436-444; default `_lu_with_inertia_correction`, NonLinearProgram.jl:402-435).  The returned object
+#     only has to support `ldiv!(ds, K, N)`; `nothing` means the correction failed.
+#     usage:  MOI.set(model, DiffOpt.NonLinearKKTJacobianFactorization(), DiffOptB200.nlp_factorization(ctx))
+# ------------------------------------------------------------------------------------------------
+struct InertiaCorrectedLU
+    ctx::Context
+    N::Int
+    corrections::Int
+end
+
+function nlp_factorization(ctx::Context; st = 1e-6, max_corrections = 50)
+    return function (M::SparseArrays.SparseMatrixCSC{Float64,Int}, model)
+        NLP = DiffOpt.NonLinearProgram
+        num_w = NLP._get_num_primal_vars(model) + length(model.cache.leq_locations) + length(model.cache.geq_locations)
+        num_cons = NLP._get_num_constraints(model)
+        nc = Ref{Int32}(0)
+        rc = ccall((:diffopt_b200_sparse_setup_inertia, LIB), Int32,
+                   (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Float64, Int32, Ptr{Int32}),
+                   ctx.handle, size(M, 1), M.colptr, M.rowval, M.nzval, num_w, num_cons, st, max_corrections, nc)
+        rc < 0 && check(ctx, rc)
+        if rc > 0
+            @warn "Inertia correction failed."
+            return nothing
+        end
+        return InertiaCorrectedLU(ctx, size(M, 1), Int(nc[]))
+    end
+end
+
+function LinearAlgebra.ldiv!(ds::Matrix{Float64}, K::InertiaCorrectedLU, N::AbstractMatrix)
+    Nd = Matrix{Float64}(N)
+    rc = ccall((:diffopt_b200_sparse_solve, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int32),
+               K.ctx.handle, size(Nd, 2), Nd, ds, HOST)
+    check(K.ctx, rc)
+    return ds
+end
+
 end # module

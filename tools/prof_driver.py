@@ -1,5 +1,6 @@
 """One driver for the ncu captures under profiles/ (run from the repo root on a GPU box):
-    python tools/prof_driver.py qp [B] | sparse [T] [nrhs] | lsqr_small [iters] | lsqr_big [scale] [iters] [window] | psd
+    python tools/prof_driver.py qp [B] | sparse [T] [nrhs] | lsqr_small [iters] | lsqr_big [scale] [iters] [window] | psd |
+                                conic_batch [B] [iters]
 Each case runs the library call a couple of times (first call warms buffers) and prints the library's own device time."""
 import os
 import sys
@@ -69,5 +70,17 @@ elif case == "psd":
     for _ in range(3):
         model.dpi_apply(t)
     print("apply ms", ctx.last_kernel_ms)
+elif case == "conic_batch":
+    cm = diffopt_b200.submodule("conic")
+    B, iters = arg(2, 148), arg(3, 20)
+    models, seeds = [], []
+    for k in range(B):
+        d = bench_data.conic_config4(seed=4000 + k)
+        models.append(conic_model(d)); seeds.append(d["seed"])
+    batch = cm.ConicBatch(ctx, models)
+    batch.tolerances = dict(atol=0.0, btol=0.0, conlim=0.0, maxiter=iters)
+    for _ in range(2):
+        batch.reverse_differentiate(np.stack(seeds))
+    print("B", B, "iters", iters, "ms", batch.kernel_ms)
 else:
     raise SystemExit(__doc__)
