@@ -45,6 +45,8 @@ struct MfFront {
     int c0, c1;                 // children: child_idx[c0 .. c1)
     int a0, a1;                 // matrix entries: aloc/asrc[a0 .. a1)
     int leaf;
+    int u0, un;                 // forward sweep: uptr[u0 .. u0 + nf] delimits, per row of the front (before interchanges), the
+                                // workspace rows of the children that are added to it (usrc, un entries in total)
     long long lp, up, cb, w;    // offsets: L panel (nf x k), U panel (k x s), contribution block (s x s), solve workspace row
 };
 
@@ -362,8 +364,8 @@ __global__ void __launch_bounds__(64) mf_netperm_kernel(const MfFront* fronts, c
     }
 }
 
-__global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list, const MfFront* fronts, const int* child_idx, const int* rel,
-                                                                 const int* perm, const int* psrc, const int* pdst, const double* Lp,
+__global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list, const MfFront* fronts, const int* uptr, const int* usrc,
+                                                                 const int* perm, const int* psrc, const double* Lp,
                                                                  const double* B, double* Y, double* W, const long long N, const int nrhs) {
     extern __shared__ __align__(16) double mf_smem[];
     const int fid = list[blockIdx.x];
@@ -377,7 +379,9 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
     double* Lb = YW + (size_t)nf * MF_LDT;                 // [nf][MF_NB]: rows jb.. of the current column block (16-byte aligned:
     Lb += ((size_t)nf * MF_LDT) & 1;                       //  odd offsets are bumped)
     int* rows = reinterpret_cast<int*>(Lb + (size_t)nf * MF_NB);  // original row of position r
-    int* posmap = rows + k;                                // position of (pre-interchange) row r
+    int* locs = rows + k;                                  // row of the front (before the interchanges) at position r
+    int* up = locs + k;                                    // nf + 1 offsets into us (children's updates per row)
+    int* us = up + nf + 1;                                 // workspace rows of the children, fr.un entries
     const double* L = Lp + fr.lp;
     double lreg[MF_NB];
     auto prefetch = [&](const int jb) {
@@ -388,27 +392,38 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
     };
     prefetch(0);   // first panel block in flight under the gathers below
     for (int r = tid; r < k; r += MF_TT) {
-        rows[r] = perm[fr.first + psrc[fr.first + r]];
-        posmap[r] = pdst[fr.first + r];
+        const int loc = psrc[fr.first + r];
+        locs[r] = loc;
+        rows[r] = perm[fr.first + loc];
+    }
+    {
+        const int ub = uptr[fr.u0];
+        for (int r = tid; r <= nf; r += MF_TT) up[r] = uptr[fr.u0 + r] - ub;
+        for (int e = tid; e < fr.un; e += MF_TT) us[e] = usrc[ub + e];
     }
     __syncthreads();
     // own rows from the caller's column-major block (lanes: consecutive positions of one column), boundary rows zero
-    for (int cc = wid; cc < ncol; cc += MF_TT / 32)
-        for (int r = lane; r < k; r += 32) YW[r * MF_LDT + cc] = B[(size_t)rows[r] + (size_t)N * (c0 + cc)];
-    for (int t = q; t < s; t += MF_RG) YW[(k + t) * MF_LDT + c] = 0.0;
-    __syncthreads();
-    for (int ci = fr.c0; ci < fr.c1; ++ci) {  // updates of the children, in list order (rows of one child are distinct)
-        const MfFront ch = fronts[child_idx[ci]];
-        const int* r = rel + ch.soff;
-        const double* cw = W + (size_t)ch.w * nrhs + col;
-        if (live)
-            for (int t = q; t < ch.s; t += MF_RG) {
-                const int loc = r[t];
-                const int pos = loc < k ? posmap[loc] : loc;
-                YW[pos * MF_LDT + c] += cw[(size_t)t * nrhs];
-            }
-        __syncthreads();
+    for (int r = lane; r < k; r += 32) {   // eight columns in flight per lane
+        const double* src = B + (size_t)rows[r] + (size_t)N * c0;
+        double* dst = YW + r * MF_LDT;
+#pragma unroll
+        for (int u = 0; u < MF_TC / (MF_TT / 32); ++u) {
+            const int cc = wid + u * (MF_TT / 32);
+            if (cc < ncol) dst[cc] = __ldcs(src + (size_t)N * cc);
+        }
     }
+    __syncthreads();
+    // extend-add as a gather: every row of the tile is owned by one thread per column, which adds the children's
+    // workspace rows that land on it in the children's list order (deterministic; no barrier per child)
+    if (live)
+        for (int pos = q; pos < nf; pos += MF_RG) {
+            const int loc = pos < k ? locs[pos] : pos;
+            const int e0 = up[loc], e1 = up[loc + 1];
+            double acc = pos < k ? YW[pos * MF_LDT + c] : 0.0;
+#pragma unroll 4
+            for (int e = e0; e < e1; ++e) acc += W[(size_t)us[e] * nrhs + col];
+            YW[pos * MF_LDT + c] = acc;
+        }
     // blocked forward substitution with the unit-lower L11 and the boundary update w -= L21 y in one sweep over the rows
     for (int jb = 0; jb < k; jb += MF_NB) {
         const int nbk = min(MF_NB, k - jb);
@@ -480,7 +495,9 @@ __global__ void __launch_bounds__(MF_TT) mf_backward_tiled_kernel(const int* lis
     const double* U12 = Up + fr.up;
     const int* sp = strct + fr.soff;
     if (live) {
+#pragma unroll 4
         for (int r = q; r < k; r += MF_RG) YW[r * MF_LDT + c] = Y[(size_t)(fr.first + r) * nrhs + col];
+#pragma unroll 4
         for (int t = q; t < s; t += MF_RG) YW[(k + t) * MF_LDT + c] = Y[(size_t)sp[t] * nrhs + col];
     }
     // column blocks of [U11 U12] from the right: boundary blocks (plain updates), then the blocks of U11 (solve + update)
@@ -898,13 +915,13 @@ struct Dissector {
 };
 
 struct MfLaunch {
-    int level, big, offset, count, max_nf, max_k, max_s;
+    int level, big, offset, count, max_nf, max_k, max_s, max_u;
 };
 
 struct MfHost {
     std::vector<MfFront> fronts;
     std::vector<int32_t> perm;       // permuted position -> original index
-    std::vector<int32_t> strct, rel, child_idx, aloc, asrc, lists;
+    std::vector<int32_t> strct, rel, child_idx, aloc, asrc, lists, uptr, usrc;
     std::vector<MfLaunch> launches;  // factorisation order (levels ascending)
     int nlevels = 0;
     long long lp_total = 0, up_total = 0, cb_total = 0, w_rows = 0, big_scratch = 0;
@@ -1057,6 +1074,35 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
             H.fronts[(size_t)s].a1 = cnt[(size_t)s + 1];
         }
     }
+    // forward-sweep update lists: for every row of a front (numbering before the interchanges), the workspace rows of its
+    // children that land on it, children in list order (the order the sums are formed in).  uptr holds absolute offsets
+    // into usrc.
+    if (H.w_rows >= ((long long)1 << 31) - 1) {
+        err = "sparse_setup: factor structure too large";
+        return false;
+    }
+    {
+        std::vector<int32_t> cnt;
+        for (int s = 0; s < S; ++s) {
+            MfFront& f = H.fronts[(size_t)s];
+            const int nf = f.k + f.s;
+            f.u0 = (int)H.uptr.size();
+            cnt.assign((size_t)nf + 1, 0);
+            for (int ci = f.c0; ci < f.c1; ++ci) {
+                const MfFront& ch = H.fronts[(size_t)H.child_idx[(size_t)ci]];
+                for (int t = 0; t < ch.s; ++t) ++cnt[(size_t)H.rel[(size_t)ch.soff + t] + 1];
+            }
+            for (int r = 0; r < nf; ++r) cnt[(size_t)r + 1] += cnt[(size_t)r];
+            f.un = cnt[(size_t)nf];
+            const int32_t base = (int32_t)H.usrc.size();
+            for (int r = 0; r <= nf; ++r) H.uptr.push_back(base + cnt[(size_t)r]);
+            H.usrc.resize((size_t)base + (size_t)f.un);
+            for (int ci = f.c0; ci < f.c1; ++ci) {
+                const MfFront& ch = H.fronts[(size_t)H.child_idx[(size_t)ci]];
+                for (int t = 0; t < ch.s; ++t) H.usrc[(size_t)base + (size_t)cnt[(size_t)H.rel[(size_t)ch.soff + t]]++] = (int32_t)(ch.w + t);
+            }
+        }
+    }
     // launch groups: per tree level, fronts that fit shared memory (sorted by size) and the others
     H.nlevels = 0;
     for (int s = 0; s < S; ++s) H.nlevels = std::max(H.nlevels, lvl[(size_t)s] + 1);
@@ -1073,7 +1119,7 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
             const MfFront& f0 = H.fronts[(size_t)v[i]];
             const int nf0 = f0.k + f0.s;
             const bool big = (size_t)nf0 * (nf0 | 1) * 8 + (size_t)f0.k * 8 > MF_SMEM_CAP;
-            MfLaunch L{l, big ? 1 : 0, (int)H.lists.size(), 0, 0, 0, 0};
+            MfLaunch L{l, big ? 1 : 0, (int)H.lists.size(), 0, 0, 0, 0, 0};
             size_t j = i;
             for (; j < v.size(); ++j) {
                 const MfFront& f = H.fronts[(size_t)v[j]];
@@ -1085,6 +1131,7 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
                 L.max_nf = std::max(L.max_nf, nf);
                 L.max_k = std::max(L.max_k, f.k);
                 L.max_s = std::max(L.max_s, f.s);
+                L.max_u = std::max(L.max_u, f.un);
                 if (big) {
                     H.big_off.push_back(H.big_scratch);
                     H.big_scratch += (long long)nf * (nf | 1) + f.k;
@@ -1262,13 +1309,13 @@ struct SparseMfImpl {
     MfHost H;
     std::vector<std::vector<int32_t>> snodes;
     Graph g;
-    DevBuf fronts, perm, strct, rel, child_idx, aloc, asrc, lists, big_off, big_scratch, vals, Lp, Up, CB, piv, status, Y, W, psrc, pdst;
+    DevBuf fronts, perm, strct, rel, child_idx, aloc, asrc, lists, big_off, big_scratch, vals, Lp, Up, CB, piv, status, Y, W, psrc, pdst, uptr, usrc;
     int retries = 0;
     bool netperm = false;
     double analysis_ms = 0.0;
     void release() {
         for (DevBuf* b : {&fronts, &perm, &strct, &rel, &child_idx, &aloc, &asrc, &lists, &big_off, &big_scratch, &vals, &Lp, &Up, &CB, &piv,
-                          &status, &Y, &W, &psrc, &pdst})
+                          &status, &Y, &W, &psrc, &pdst, &uptr, &usrc})
             b->release();
     }
 };
@@ -1299,6 +1346,8 @@ int32_t mf_numeric(diffopt_b200_ctx* ctx, SparseMfImpl& M, int64_t nnz, std::vec
     DO_CUDA(ctx, upload(ctx, M.strct, H.strct));
     DO_CUDA(ctx, upload(ctx, M.rel, H.rel));
     DO_CUDA(ctx, upload(ctx, M.child_idx, H.child_idx));
+    DO_CUDA(ctx, upload(ctx, M.uptr, H.uptr));
+    DO_CUDA(ctx, upload(ctx, M.usrc, H.usrc));
     DO_CUDA(ctx, upload(ctx, M.aloc, H.aloc));
     DO_CUDA(ctx, upload(ctx, M.asrc, H.asrc));
     DO_CUDA(ctx, upload(ctx, M.lists, H.lists));
@@ -1468,7 +1517,7 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
     };
     const bool use_tiled = M.netperm && getenv("DIFFOPT_B200_MF_OLD_SOLVE") == nullptr;
     auto tiled_smem = [](const MfLaunch& L, bool fwd) {
-        return sizeof(double) * ((size_t)L.max_nf * MF_LDT + 1 + (size_t)(fwd ? L.max_nf : L.max_k) * MF_NB) + (fwd ? sizeof(int) * 2 * (size_t)L.max_k : 0);
+        return sizeof(double) * ((size_t)L.max_nf * MF_LDT + 1 + (size_t)(fwd ? L.max_nf : L.max_k) * MF_NB) + (fwd ? sizeof(int) * (2 * (size_t)L.max_k + (size_t)L.max_nf + 1 + (size_t)L.max_u) : 0);
     };
     auto tiled_group = [&](const MfLaunch& L) {
         return use_tiled && !L.big && L.max_nf <= MF_TT && tiled_smem(L, true) <= MF_SMEM_CAP && smem_fwd(L) <= MF_SMEM_CAP && smem_bwd(L) <= MF_SMEM_CAP;
@@ -1481,8 +1530,8 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
         if (!leaf_group(L) && tiled_group(L)) {
             const size_t ts = tiled_smem(L, true);
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ts, 1024)));
-            mf_forward_tiled_kernel<<<grid, MF_TT, ts, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.child_idx.as<int>(),
-                                                                      M.rel.as<int>(), M.perm.as<int>(), M.psrc.as<int>(), M.pdst.as<int>(),
+            mf_forward_tiled_kernel<<<grid, MF_TT, ts, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.uptr.as<int>(),
+                                                                      M.usrc.as<int>(), M.perm.as<int>(), M.psrc.as<int>(),
                                                                       M.Lp.as<double>(), (const double*)dB, M.Y.as<double>(), M.W.as<double>(), N,
                                                                       (int)nrhs);
         } else if (leaf_group(L)) {
