@@ -510,8 +510,13 @@ __device__ void conic_apply(Dev& d, const ConicOpView& op, bool transpose, const
         double* xs_m = cl_prod + CL_CHUNK;  // staged gather vectors (SM): m entries, then n entries
         double* xs_n = xs_m + m;
         constexpr int XM = SM ? 2 : 1;
+        // (one problem per CTA: every producer of these vectors ran on this SM, so the L1-allocating cp.async sees them;
+        // the copies are in flight together, each thread waits for its own and the caller's barrier publishes them)
         auto stage = [&](double* to, const double* from, int len) {
-            for (int i = d.tid; i < len; i += CL_THREADS) to[i] = __ldcg(from + i);
+            for (int i = d.tid; i < len; i += CL_THREADS)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(to + i)), "l"(from + i)
+                             : "memory");
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
         };
         double acc = 0.0;
         if (!transpose) {
@@ -749,7 +754,26 @@ __device__ void lsqr_body(Dev& d, const OpArgs& o, const double* __restrict__ rh
                 for (int i = d.gtid; i < nc; i += d.gthreads) w[i] = sv * (i == ilast ? v_last : v[i]);
             } else {
                 const double irho = 1.0 / rho;
-                for (int i = d.gtid; i < nc; i += d.gthreads) {
+                int i = d.gtid;
+                for (; i + 3 * d.gthreads < nc; i += 4 * d.gthreads) {   // four independent elements in flight per thread
+                    double wi[4], vi[4], xi[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = i + q * d.gthreads;
+                        wi[q] = w[k];
+                        vi[q] = k == ilast ? v_last : v[k];
+                        xi[q] = x[k];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = i + q * d.gthreads;
+                        const double dk = wi[q] * irho;
+                        dd += dk * dk;
+                        x[k] = xi[q] + t1 * wi[q];
+                        w[k] = sv * vi[q] + t2 * wi[q];
+                    }
+                }
+                for (; i < nc; i += d.gthreads) {
                     double wi = w[i];
                     double dk = wi * irho;
                     dd += dk * dk;
