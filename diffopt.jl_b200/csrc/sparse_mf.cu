@@ -594,11 +594,12 @@ __global__ void __launch_bounds__(MF_TT) mf_backward_tiled_kernel(const int* lis
 // the gather, no work area: forward reads the caller's b and writes y / the boundary update, backward reads y and the
 // separator solutions and writes the caller's x.
 constexpr int MF_KMAX = 32;
+constexpr int MF_LLD = MF_KMAX + 2;   // row stride of the panels in shared memory: 16-byte aligned rows, transposing stores 4-way (not 32-way) conflicted
 constexpr int MF_LEAF_TC = 128;
 
 __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* list, const MfFront* fronts, const int* perm,
-                                                                     const int* piv, const double* Lp, const double* B, double* Y,
-                                                                     double* W, const long long N, const int nrhs) {
+                                                                     const int* piv, const int* psrc, const double* Lp, const double* B,
+                                                                     double* Y, double* W, const long long N, const int nrhs) {
     extern __shared__ __align__(16) double mf_smem[];
     __shared__ int rows[MF_KMAX];
     const int fid = list[blockIdx.x];
@@ -608,7 +609,9 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
     constexpr int LDT = MF_KMAX + 1;       // tile leading dimension: conflict-free both ways
     double* Ts = mf_smem;                  // [column][row] tile of b (first), then the L panel (same storage)
     double* Ls = mf_smem;                  // row r of the L panel at Ls[r * KMAX .. ], columns >= k zero
-    if (tid == 0) {  // net effect of the row interchanges: position r of P b comes from row src[r]
+    if (psrc) {      // net effect of the row interchanges, precomputed per front (mf_netperm_kernel)
+        if (tid < k) rows[tid] = perm[fr.first + psrc[fr.first + tid]];
+    } else if (tid == 0) {  // ... or worked out here: position r of P b comes from row src[r]
         int src[MF_KMAX];
         for (int r = 0; r < k; ++r) src[r] = r;
         for (int j = 0; j < k; ++j) {
@@ -635,9 +638,12 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
 #pragma unroll
     for (int r = 0; r < MF_KMAX; ++r) y[r] = (r < k && tid < ncol) ? Ts[tid * LDT + r] : 0.0;
     __syncthreads();
-    for (int i = tid; i < nf * MF_KMAX; i += MF_LEAF_TC) {
-        const int r = i / MF_KMAX, c = i % MF_KMAX;
-        Ls[i] = (c < k && (r >= k || c < r)) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
+    {   // panel: global reads run down the columns (coalesced), rows of the transposed copy are MF_LLD apart
+        const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll 4
+        for (int c = wid; c < MF_KMAX; c += MF_LEAF_TC / 32)
+            for (int r = lane; r < nf; r += 32)
+                Ls[r * MF_LLD + c] = (c < k && (r >= k || c < r)) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
     }
     __syncthreads();
     if (col >= nrhs) return;
@@ -645,14 +651,14 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
     for (int i = 1; i < MF_KMAX; ++i) {  // unit-lower L11 (block-uniform guard: rows >= k belong to L21)
         if (i >= k) break;
         double acc = y[i], acc2 = 0.0;
-        const double2* l2 = reinterpret_cast<const double2*>(Ls + i * MF_KMAX);
+        const double2* l2 = reinterpret_cast<const double2*>(Ls + i * MF_LLD);
 #pragma unroll
         for (int j = 0; j + 1 < i; j += 2) {
             const double2 l = l2[j >> 1];
             acc = fma(-l.x, y[j], acc);
             acc2 = fma(-l.y, y[j + 1], acc2);
         }
-        if (i & 1) acc = fma(-Ls[i * MF_KMAX + i - 1], y[i - 1], acc);
+        if (i & 1) acc = fma(-Ls[i * MF_LLD + i - 1], y[i - 1], acc);
         y[i] = acc + acc2;
     }
     double* yo = Y + (size_t)fr.first * nrhs + col;
@@ -661,7 +667,7 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
         if (r < k) yo[(size_t)r * nrhs] = y[r];
     double* wo = W + (size_t)fr.w * nrhs + col;
     for (int t = 0; t < s; ++t) {  // boundary update  w = -L21 y
-        const double2* l2 = reinterpret_cast<const double2*>(Ls + (k + t) * MF_KMAX);
+        const double2* l2 = reinterpret_cast<const double2*>(Ls + (k + t) * MF_LLD);
         double acc = 0.0, acc2 = 0.0;
 #pragma unroll
         for (int j = 0; j < MF_KMAX; j += 2) {
@@ -684,10 +690,10 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int*
     const int k = fr.k, s = fr.s, nf = k + s;
     const int tid = threadIdx.x, col = blockIdx.y * MF_LEAF_TC + tid;
     double* U11s = mf_smem;                      // row i at U11s[i * KMAX ..], strictly upper part, zero elsewhere
-    double* U12s = U11s + MF_KMAX * MF_KMAX;     // boundary column t at U12s[t * KMAX ..] (entries i < k)
-    for (int i = tid; i < MF_KMAX * MF_KMAX; i += MF_LEAF_TC) {
-        const int r = i / MF_KMAX, c = i % MF_KMAX;
-        U11s[i] = (r < k && c < k && c > r) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
+    double* U12s = U11s + MF_KMAX * MF_LLD;      // boundary column t at U12s[t * KMAX ..] (entries i < k)
+    for (int i = tid; i < MF_KMAX * MF_KMAX; i += MF_LEAF_TC) {   // global reads run down the columns (coalesced)
+        const int c = i / MF_KMAX, r = i % MF_KMAX;
+        U11s[r * MF_LLD + c] = (r < k && c < k && c > r) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
     }
     for (int i = tid; i < s * MF_KMAX; i += MF_LEAF_TC) {
         const int t = i / MF_KMAX, r = i % MF_KMAX;
@@ -697,27 +703,34 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int*
         rdiag[tid] = tid < k ? 1.0 / Lp[fr.lp + tid + (size_t)tid * nf] : 0.0;
         if (tid < k) rows[tid] = perm[fr.first + tid];
     }
+    int* sps = reinterpret_cast<int*>(U12s + (size_t)s * MF_KMAX);   // boundary positions (behind the panels)
+    for (int t = tid; t < s; t += MF_LEAF_TC) sps[t] = strct[fr.soff + t];
     __syncthreads();
     double y[MF_KMAX];
     if (col < nrhs) {
     const double* yi = Y + (size_t)fr.first * nrhs + col;
 #pragma unroll
     for (int r = 0; r < MF_KMAX; ++r) y[r] = r < k ? yi[(size_t)r * nrhs] : 0.0;
-    const int* sp = strct + fr.soff;
-    for (int t = 0; t < s; ++t) {  // y -= U12 x2
-        const double x2 = Y[(size_t)sp[t] * nrhs + col];
-        const double2* u2 = reinterpret_cast<const double2*>(U12s + t * MF_KMAX);
+    for (int t0 = 0; t0 < s; t0 += 4) {  // y -= U12 x2, four boundary solutions in flight
+        double x2[4];
 #pragma unroll
-        for (int i = 0; i < MF_KMAX; i += 2) {
-            const double2 u = u2[i >> 1];
-            y[i] = fma(-u.x, x2, y[i]);
-            y[i + 1] = fma(-u.y, x2, y[i + 1]);
+        for (int u4 = 0; u4 < 4; ++u4) x2[u4] = t0 + u4 < s ? Y[(size_t)sps[t0 + u4] * nrhs + col] : 0.0;
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+            if (t0 + u4 >= s) break;
+            const double2* u2 = reinterpret_cast<const double2*>(U12s + (t0 + u4) * MF_KMAX);
+#pragma unroll
+            for (int i = 0; i < MF_KMAX; i += 2) {
+                const double2 u = u2[i >> 1];
+                y[i] = fma(-u.x, x2[u4], y[i]);
+                y[i + 1] = fma(-u.y, x2[u4], y[i + 1]);
+            }
         }
     }
 #pragma unroll
     for (int i = MF_KMAX - 1; i >= 0; --i) {
         double acc = y[i], acc2 = 0.0;
-        const double* ur = U11s + i * MF_KMAX;
+        const double* ur = U11s + i * MF_LLD;
         if (!(i & 1)) acc = fma(-ur[i + 1], y[i + 1], acc);   // first entry right of the diagonal sits at an odd column
 #pragma unroll
         for (int j = (i + 2) & ~1; j < MF_KMAX; j += 2) {
@@ -1506,7 +1519,7 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
     const unsigned ltiles = (unsigned)((nrhs + MF_LEAF_TC - 1) / MF_LEAF_TC);
     const bool use_leaf = getenv("DIFFOPT_B200_MF_NO_LEAF_KERNELS") == nullptr;
     auto leaf_group = [&](const MfLaunch& L) {
-        return use_leaf && L.level == 0 && !L.big && L.max_k <= MF_KMAX && sizeof(double) * (size_t)(MF_KMAX + L.max_nf) * MF_KMAX <= MF_SMEM_CAP;
+        return use_leaf && L.level == 0 && !L.big && L.max_k <= MF_KMAX && sizeof(double) * (size_t)(MF_KMAX + L.max_nf) * MF_LLD <= MF_SMEM_CAP;
     };
     auto smem_fwd = [](const MfLaunch& L) {
         return ((size_t)L.max_nf * L.max_k + (size_t)MF_TC * (L.max_k | 1) + (size_t)MF_TC * (L.max_s | 1)) * sizeof(double);
@@ -1535,11 +1548,12 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
                                                                       M.Lp.as<double>(), (const double*)dB, M.Y.as<double>(), M.W.as<double>(), N,
                                                                       (int)nrhs);
         } else if (leaf_group(L)) {
-            const size_t ls = sizeof(double) * std::max<size_t>((size_t)L.max_nf * MF_KMAX, (size_t)MF_LEAF_TC * (MF_KMAX + 1));
+            const size_t ls = sizeof(double) * std::max<size_t>((size_t)L.max_nf * MF_LLD, (size_t)MF_LEAF_TC * (MF_KMAX + 1));
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ls, 1024)));
             mf_forward_leaf_kernel<<<dim3((unsigned)L.count, ltiles), MF_LEAF_TC, ls, ctx->stream>>>(
-                M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.perm.as<int>(), M.piv.as<int>(), M.Lp.as<double>(),
-                (const double*)dB, M.Y.as<double>(), M.W.as<double>(), N, (int)nrhs);
+                M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.perm.as<int>(), M.piv.as<int>(),
+                M.netperm ? M.psrc.as<int>() : nullptr, M.Lp.as<double>(), (const double*)dB, M.Y.as<double>(), M.W.as<double>(), N,
+                (int)nrhs);
         } else if (!big) {
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
             mf_forward_kernel<false><<<grid, MF_TC, smem, ctx->stream>>>(M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(),
@@ -1567,7 +1581,8 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
                                                                        M.perm.as<int>(), M.Lp.as<double>(), M.Up.as<double>(), M.Y.as<double>(),
                                                                        (double*)dX, N, (int)nrhs);
         } else if (leaf_group(L)) {
-            const size_t ls = sizeof(double) * std::max<size_t>((size_t)(MF_KMAX + L.max_s) * MF_KMAX, (size_t)MF_LEAF_TC * (MF_KMAX + 1));
+            const size_t ls = sizeof(double) * std::max<size_t>((size_t)MF_KMAX * MF_LLD + (size_t)L.max_s * MF_KMAX + (size_t)(L.max_s + 1) / 2 + 1,
+                                                                (size_t)MF_LEAF_TC * (MF_KMAX + 1));
             DO_CUDA(ctx, cudaFuncSetAttribute(mf_backward_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ls, 1024)));
             mf_backward_leaf_kernel<<<dim3((unsigned)L.count, ltiles), MF_LEAF_TC, ls, ctx->stream>>>(
                 M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.strct.as<int>(), M.perm.as<int>(), M.Lp.as<double>(),

@@ -561,3 +561,24 @@ def test_conic_lockstep_batch_matches_single_problem_solves(ctx, monkeypatch, ct
     # a second call on the same batch (work area reused) gives the same answer bit for bit
     out2 = batch.reverse_differentiate(seeds)
     assert np.array_equal(out["g"], out2["g"])
+
+
+@pytest.mark.parametrize("sides", [(121, 200), (230, 300)])
+def test_psd_block_jacobi_sides(ctx, sides):
+    """Sides beyond one CTA's shared memory (block Jacobi over a cooperative grid), with a rank-deficient part as max-cut
+    solutions have: projection and Dpi must match the oracle's eigh-based ones."""
+    rng = np.random.default_rng(23)
+    for d in sides:
+        Qm, _ = np.linalg.qr(rng.normal(size=(d, d)))
+        lam = rng.normal(size=d)
+        lam[: d // 10] = 0.0
+        Xm = (Qm * lam) @ Qm.T
+        model, v, dims = _psd_only_model(ctx, [(Xm + Xm.T) / 2])
+        types = [ocones.PSD]
+        want_vp = ocones.pi(v, types, dims)
+        assert np.linalg.norm(model.vp() - want_vp) <= 1e-11 * max(1.0, np.linalg.norm(want_vp))
+        t = rng.normal(size=v.size)
+        for tr in (False, True):
+            want = ocones.Dpi_apply(v, types, dims, t, transpose=tr)
+            got = model.dpi_apply(t, transpose=tr)
+            assert np.linalg.norm(got - want) <= 1e-9 * max(1.0, np.linalg.norm(want))
