@@ -95,12 +95,22 @@ __device__ void mf_factor_front(const MfFront fr, double* F, const int ld, doubl
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
                 rest = fmax(rest, orr);
             }
+            // a pivot that fails the threshold test is still taken when its ROW has nothing else left (a row singleton,
+            // e.g. the row of an inactive inequality in LHS': x = r / D exactly): its multipliers only ever meet zeros
+            bool weak = best > 0.0 && best < MF_PIV_U * rest;
+            if (weak) {
+                double rmax = 0.0;
+                for (int c = j + 1 + lane; c < nf; c += 32) rmax = fmax(rmax, fabs(F[bi + c * ld]));
+#pragma unroll
+                for (int o = 16; o; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+                if (rmax == 0.0) weak = false;
+            }
             if (lane == 0) {
                 sh_p = bi;
                 if (!(best > 0.0)) {
                     if (rest > 0.0) sh_flag |= 2;   // only rows that are not fully summed could pivot: delayed pivot needed
                     else sh_flag |= 1;              // the whole column is zero: the matrix is singular
-                } else if (best < MF_PIV_U * rest) sh_flag |= 2;
+                } else if (weak) sh_flag |= 2;
             }
         }
         __syncthreads();
@@ -333,6 +343,7 @@ constexpr int MF_TT = 256;
 constexpr int MF_RG = MF_TT / MF_TC;   // row groups
 constexpr int MF_NB = 8;
 constexpr int MF_LDT = MF_TC + 1;      // leading dimension of YW: conflict-free by row and by column
+constexpr int MF_US_CAP = 8192;        // update lists up to this many entries are staged in shared memory
 
 // one CTA per front: net effect of the front's row interchanges.  psrc[first + r] = row (0..k-1, before the interchanges)
 // that ends at position r; pdst = inverse.
@@ -399,8 +410,11 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
     {
         const int ub = uptr[fr.u0];
         for (int r = tid; r <= nf; r += MF_TT) up[r] = uptr[fr.u0 + r] - ub;
-        for (int e = tid; e < fr.un; e += MF_TT) us[e] = usrc[ub + e];
+        if (fr.un <= MF_US_CAP)
+            for (int e = tid; e < fr.un; e += MF_TT) us[e] = usrc[ub + e];
     }
+    // (a front with thousands of children -- the top front of an arrowhead -- reads its list from global memory)
+    const int* const ulist = fr.un <= MF_US_CAP ? us : usrc + uptr[fr.u0];
     __syncthreads();
     // own rows from the caller's column-major block (lanes: consecutive positions of one column), boundary rows zero
     for (int r = lane; r < k; r += 32) {   // eight columns in flight per lane
@@ -420,8 +434,15 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
             const int loc = pos < k ? locs[pos] : pos;
             const int e0 = up[loc], e1 = up[loc + 1];
             double acc = pos < k ? YW[pos * MF_LDT + c] : 0.0;
-#pragma unroll 4
-            for (int e = e0; e < e1; ++e) acc += W[(size_t)us[e] * nrhs + col];
+            int e = e0;
+            for (; e + 8 <= e1; e += 8) {   // eight loads in flight, added in list order
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = W[(size_t)ulist[e + u] * nrhs + col];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u];
+            }
+            for (; e < e1; ++e) acc += W[(size_t)ulist[e] * nrhs + col];
             YW[pos * MF_LDT + c] = acc;
         }
     // blocked forward substitution with the unit-lower L11 and the boundary update w -= L21 y in one sweep over the rows
@@ -1467,6 +1488,11 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
         std::vector<int32_t> failed;
         rc = mf_numeric(ctx, M, nnz, failed);
         if (rc != -5) break;
+        if (getenv("DIFFOPT_B200_MF_DEBUG")) {
+            const MfFront& f0 = M.H.fronts[(size_t)failed[0]];
+            fprintf(stderr, "sparse_setup: pass %d, %zu of %zu fronts need a delayed pivot (first: front %d, k %d, s %d, level-0 leaf %d)\n",
+                    M.retries, failed.size(), M.H.fronts.size(), failed[0], f0.k, f0.s, f0.leaf);
+        }
         // delayed pivots: merge every failing front into its parent (its columns become fully summed there) and repeat
         if (++M.retries > 8) break;
         std::vector<char> drop(M.snodes.size(), 0);
@@ -1530,10 +1556,10 @@ extern "C" int32_t diffopt_b200_sparse_solve(diffopt_b200_ctx* ctx, int64_t nrhs
     };
     const bool use_tiled = M.netperm && getenv("DIFFOPT_B200_MF_OLD_SOLVE") == nullptr;
     auto tiled_smem = [](const MfLaunch& L, bool fwd) {
-        return sizeof(double) * ((size_t)L.max_nf * MF_LDT + 1 + (size_t)(fwd ? L.max_nf : L.max_k) * MF_NB) + (fwd ? sizeof(int) * (2 * (size_t)L.max_k + (size_t)L.max_nf + 1 + (size_t)L.max_u) : 0);
+        return sizeof(double) * ((size_t)L.max_nf * MF_LDT + 1 + (size_t)(fwd ? L.max_nf : L.max_k) * MF_NB) + (fwd ? sizeof(int) * (2 * (size_t)L.max_k + (size_t)L.max_nf + 1 + (size_t)std::min(L.max_u, MF_US_CAP)) : 0);
     };
     auto tiled_group = [&](const MfLaunch& L) {
-        return use_tiled && !L.big && L.max_nf <= MF_TT && tiled_smem(L, true) <= MF_SMEM_CAP && smem_fwd(L) <= MF_SMEM_CAP && smem_bwd(L) <= MF_SMEM_CAP;
+        return use_tiled && L.max_nf <= MF_TT && tiled_smem(L, true) <= MF_SMEM_CAP && tiled_smem(L, false) <= MF_SMEM_CAP;
     };
     for (const MfLaunch& L : H.launches) {
         if (L.count == 0) continue;
