@@ -582,3 +582,20 @@ def test_psd_block_jacobi_sides(ctx, sides):
             want = ocones.Dpi_apply(v, types, dims, t, transpose=tr)
             got = model.dpi_apply(t, transpose=tr)
             assert np.linalg.norm(got - want) <= 1e-9 * max(1.0, np.linalg.norm(want))
+
+
+def test_kat13_psd_and_pos_forward(ctx):
+    """test/conic_program.jl:378-579 (PSD + POS problem against diffcp): forward mode through the device vs the oracle
+    (<= 1e-6 at matched tolerances) and vs the reference's literals at its own atol 0.3 / rtol 0.01."""
+    from test_oracle_kat import kat13_psd_pos_problem
+    cm = diffopt_b200.submodule("conic")
+    d = kat13_psd_pos_problem()
+    model = cm.ConicModel(ctx, d["A"], d["b"], d["c"], d["cone_types"], d["cone_dims"])
+    model.set_variable_primal(d["x"]); model.set_constraint_primal(d["s"]); model.set_constraint_dual(d["y"])
+    model.tolerances = dict(TIGHT, maxiter=2000)
+    model.forward_differentiate(d["dA"], d["db"], d["dc"])
+    got = model.forward_variable_primal()
+    cache = _oracle_cache(d)
+    want, _ = oconic.forward(cache, d["dA"], d["db"], d["dc"], **dict(TIGHT, maxiter=2000))
+    assert rel(got, want) <= RTOL_LSQR
+    assert np.allclose(got, d["dx"], atol=0.3, rtol=0.01)

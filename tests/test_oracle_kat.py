@@ -295,3 +295,34 @@ def test_kat16_parameter_pullback(vals):
         con = dict(grad_cte=-dh[0], grad_coef={0: dG[0, 0]}, **terms)
         got = nlp.reverse_parameters(5, [con], None, np.array(vals, float))
         assert np.allclose(got, expect, atol=1e-10), (vals, dir_x, got, expect)
+
+
+def kat13_psd_pos_problem():
+    """test/conic_program.jl:378-579 (KAT 13): 7 variables, Zeros(1) + Nonnegatives(1) + Nonnegatives(6) + PSD triangle(2)
+    in the row order the reference's ProductOfSets gives them, MAX sense (c negated, :206-208), the solution literals the
+    test asserts (:488-517) and the forward perturbation dA = ones(11, 7), db = ones(11), dc = ones(7) (:452-487, packed
+    un-negated).  Expected dx: the diffcp values of :523, compared at atol 0.3 / rtol 0.01 as the reference does."""
+    import scipy.sparse as sp
+    de, al, r2 = 0.9, 0.8, np.sqrt(2.0)
+    coef = np.zeros((11, 7))
+    const = np.zeros(11)
+    coef[1, :6] = -1.0
+    const[1] = 10.0                                             # c1: eta - sum(x[1:6]) >= 0
+    coef[2:8, :6] = np.eye(6)                                   # c2: x[1:6] >= 0
+    coef[8, :] = [de / 2, al, de, de / 4, de / 8, 0.0, -1.0]    # c3: PSD triangle (1,1), (1,2), (2,2)
+    coef[9, [0, 1, 2, 4, 5]] = [-de / (2 * r2), -de / 4, 0.0, -de / (8 * r2), 0.0]
+    coef[10, [0, 1, 2, 4, 5, 6]] = [de / 2, de - al, 0.0, de / 8, de / 4, -1.0]
+    x = np.array([20 / 3.0, 0.0, 10 / 3.0, 0.0, 0.0, 0.0, 1.90192379])
+    s = np.array([0.0, 0.0, 20 / 3.0, 0.0, 10 / 3.0, 0.0, 0.0, 0.0, 4.09807621, -2.12132, 1.09807621])
+    y = np.array([0.0, 0.19019238, 0.0, 0.12597667, 0.0, 0.14264428, 0.14264428, 0.01274047, 0.21132487, 0.408248, 0.78867513])
+    return dict(A=-sp.csc_matrix(coef), b=const, c=-np.array([0, 0, 0, 0, 0, 0, 1.0]), x=x, s=s, y=y,
+                cone_types=[cones.ZERO, cones.NONNEG, cones.NONNEG, cones.PSD], cone_dims=[1, 1, 6, 3],
+                dA=np.ones((11, 7)), db=np.ones(11), dc=np.ones(7),
+                dx=np.array([-39.6066, 10.8953, -14.9189, 10.9054, 10.883, 10.9118, -21.7508]))
+
+
+def test_kat13_psd_and_pos_forward_vs_diffcp_literals():
+    d = kat13_psd_pos_problem()
+    cache = conic.gradient_cache(d["A"], d["b"], d["c"], d["x"], d["s"], d["y"], d["cone_types"], d["cone_dims"])
+    dx, _ = conic.forward(cache, d["dA"], d["db"], d["dc"], atol=1e-12, btol=1e-12, conlim=1e12)
+    assert np.allclose(dx, d["dx"], atol=0.3, rtol=0.01)
