@@ -440,6 +440,10 @@ def run_b200(args, rank, world, local_rank):
         # second half of the BASELINE.json metric ("sparse solve ms"): config 3, one sparse KKT system with 256 right-hand sides
         import bench_aux
         try:
+            aux["other_shapes"] = other_shapes_sweep(ctx, lib, capi, dev, timed, check, dptr)
+        except Exception as e:
+            aux["other_shapes"] = {"error": str(e)[:300]}
+        try:
             aux["sparse_config3"] = bench_aux.config3(ctx, cpu=not args.no_cpu)
         except Exception as e:  # the headline line must survive a failure here
             aux["sparse_config3"] = {"error": str(e)[:300]}
@@ -679,6 +683,54 @@ def active_set_sweep(args, ctx, lib, capi, dev, timed, check, dptr):
                      "kernel": {0: "generic LU", 1: "pivoted LU", 2: "LDL' fast path"}.get(kern, "?"),
                      "instances_sent_to_pivoted_lu": nfb, "configured_active_rows": hint}
         del t, fo, ro, io
+    return out
+
+
+def other_shapes_sweep(ctx, lib, capi, dev, timed, check, dptr):
+    """Batched QPs of shapes other than the headline's (r1 review: the fast kernel was hard-wired to 64/64/16): the
+    shape-generic LDL' fast path against the generic pivoted-LU kernel (DIFFOPT_B200_QP_KERNEL=generic) on the same batch,
+    forward + reverse sensitivities, device-resident inputs, stream-ordered calls."""
+    import torch
+
+    import bench_data
+    out = {}
+    for n, m, p, na, B in [(100, 50, 0, 10, 4096), (32, 32, 8, 8, 8192), (16, 16, 4, 4, 16384), (50, 100, 10, 20, 4096)]:
+        d = bench_data.qp_batch_fast(B, n, m, p, n_active=na, seed=500 + n)
+        t = {k: torch.from_numpy(np.ascontiguousarray(d[k].transpose(0, 2, 1) if k in SHAPES else d[k])).to(dev) for k in FIELDS}
+        N = n + m + p
+        res = {}
+        for label, force in (("ldl_fast_path", None), ("generic_pivoted_lu", "generic")):
+            fo = torch.empty((B, N), dtype=torch.float64, device=dev)
+            ro = torch.empty_like(fo)
+            io = torch.zeros(B, dtype=torch.int32, device=dev)
+            a = [dptr(t[k]) for k in FIELDS] + [dptr(fo), dptr(ro), dptr(io)]
+            if force:
+                os.environ["DIFFOPT_B200_QP_KERNEL"] = force
+            try:
+                for _ in range(3):
+                    check(lib.diffopt_b200_qp_batch_solve(ctx.h, B, n, m, p, *a, capi.DEVICE), "qp_batch_solve")
+
+                def step():
+                    check(lib.diffopt_b200_qp_batch_solve_async(ctx.h, B, n, m, p, *a), "qp_batch_solve_async")
+                steps = 10 if force else 20
+                ms, _ = timed(step, steps, lambda: check(lib.diffopt_b200_synchronize(ctx.h), "synchronize"))
+            finally:
+                os.environ.pop("DIFFOPT_B200_QP_KERNEL", None)
+            nfb, hint, kern = ctx.qp_last_stats()
+            res[label] = {"solves_per_s": B * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+                          "kernel": {0: "generic LU", 1: "pivoted LU", 2: "LDL' fast path"}.get(kern, "?"),
+                          "instances_sent_to_pivoted_lu": nfb}
+            res[label + "_out"] = (fo.cpu().numpy(), ro.cpu().numpy())
+        f0, r0 = res.pop("ldl_fast_path_out")
+        f1, r1 = res.pop("generic_pivoted_lu_out")
+        rel = lambda x, y: float((np.linalg.norm(x - y, axis=1) / np.linalg.norm(y, axis=1)).max())
+        res["max_rel_diff_between_kernels"] = max(rel(f0, f1), rel(r0, r1))
+        res["speedup"] = res["ldl_fast_path"]["solves_per_s"] / res["generic_pivoted_lu"]["solves_per_s"]
+        bytes_per = 8 * (2 * (n * n + m * n + p * n) + 3 * n + 3 * m + 3 * p + 2 * N)
+        res["hbm_gbs_algorithmic"] = bytes_per * res["ldl_fast_path"]["solves_per_s"] / 1e9
+        res["batch"] = B
+        out[f"n{n}_m{m}_p{p}_active{na}"] = res
+        del t
     return out
 
 

@@ -127,7 +127,8 @@ struct diffopt_b200_ctx {
     int qp_last_kernel = -1;      // kernel of the last qp_batch call: 0 generic pivoted LU, 1 tuned pivoted LU, 2 LDL' fast path
     int qp_last_hint = -1;        // active-set size that launch was configured for
     int qp_seq = 0;               // call number, tags the active-set word written by the LDL' kernel
-    int qp_hint = -1;             // active-set size the next headline-shape launch is configured for (-1: unknown)
+    int qp_hint = -1;             // active-set size the next launch of the LDL' fast path is configured for (-1: unknown)
+    int64_t qp_hint_shape = -1;   // (n, m, p) that hint belongs to
     // stream-ordered calls: every kernel that finds a singular instance lowers this device word with atomicMin to
     // (call number << 32 | instance + 1); diffopt_b200_synchronize reads it, so a failure in ANY queued call surfaces
     DevBuf qp_sticky;

@@ -62,7 +62,8 @@ __device__ void accum_matvecs(const double* __restrict__ X, int R, int n, const 
     }
 }
 
-__global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveArgs a) {
+// list / count: optional device-side list of the instances to solve (the rejects of the LDL' fast path)
+__global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveArgs a, const int* __restrict__ list, const int* __restrict__ count) {
     extern __shared__ double smem[];
     const int n = a.n, m = a.m, p = a.p;
     const int N = n + m + p;
@@ -79,7 +80,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
-    for (int64_t inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
+    const int64_t todo = list ? (int64_t)*count : a.B;
+    for (int64_t it = blockIdx.x; it < todo; it += gridDim.x) {
+        const int64_t inst = list ? (int64_t)list[it] : it;
         const size_t bm = (a.shared & 1) ? 0 : (size_t)inst;   // shared Q, G, A: one instance serves the batch
         const double* Q = a.Q + bm * n * n;
         const double* G = a.G ? a.G + bm * m * n : nullptr;
@@ -308,7 +311,7 @@ size_t qp_generic_smem_bytes(int n, int m, int p) {
     return d * sizeof(double) + (size_t)(N + 1 + 4) * sizeof(int);
 }
 
-int32_t qp_batch_launch_generic(diffopt_b200_ctx* ctx, const QpSolveArgs& a) {
+static int32_t generic_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, const int* list, const int* count) {
     size_t smem = qp_generic_smem_bytes(a.n, a.m, a.p);
     if (smem > ctx->smem_optin) {
         char buf[160];
@@ -319,10 +322,18 @@ int32_t qp_batch_launch_generic(diffopt_b200_ctx* ctx, const QpSolveArgs& a) {
     }
     DO_CUDA(ctx, cudaFuncSetAttribute(qp_kkt_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = a.B < (int64_t)ctx->sm_count * 4 ? a.B : (int64_t)ctx->sm_count * 4;
-    qp_kkt_generic_kernel<<<(unsigned)grid, GEN_THREADS, smem, ctx->stream>>>(a);
+    if (grid < 1) grid = 1;
+    qp_kkt_generic_kernel<<<(unsigned)grid, GEN_THREADS, smem, ctx->stream>>>(a, list, count);
     ctx->launches++;
     DO_CUDA(ctx, cudaGetLastError());
     return 0;
+}
+
+int32_t qp_batch_launch_generic(diffopt_b200_ctx* ctx, const QpSolveArgs& a) { return generic_launch(ctx, a, nullptr, nullptr); }
+
+// the generic pivoted-LU kernel over a device-side list of instances (fallback of the shape-generic LDL' fast path)
+int32_t qp_generic_launch_list(diffopt_b200_ctx* ctx, const QpSolveArgs& a, const int* list, const int* count) {
+    return generic_launch(ctx, a, list, count);
 }
 
 int32_t qp_param_grads_launch(diffopt_b200_ctx* ctx, int64_t B, int n, int m, int p, const double* z,

@@ -778,6 +778,11 @@ __global__ void max_active_kernel(int64_t B, const double* __restrict__ lam, int
 }  // namespace
 
 int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled, int* max_active, int max_tag);
+// shape-generic LDL' fast path (qp_batch_sqd_any.cu)
+int32_t qp_sqd_any_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled, int* max_active, int max_tag);
+bool qp_sqd_any_supported(diffopt_b200_ctx* ctx, const QpSolveArgs& a);
+int qp_sqd_any_nt(const QpSolveArgs& a, int active);
+int32_t qp_max_active_any_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int* dmax);
 
 static int32_t lu_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, const int* list, const int* count,
                          bool* handled) {
@@ -831,12 +836,26 @@ int32_t qp_lu_launch_list(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_ca
     return rc;
 }
 
-// DIFFOPT_B200_QP_KERNEL = generic | lu | (default) ldl : which kernel serves the n=64, m=64, p=16 shape
+// DIFFOPT_B200_QP_KERNEL = generic | lu | (default) ldl : which kernel serves the batch.  The headline shape n=64, m=64,
+// p=16 has its own LDL' and pivoted-LU kernels; every other shape whose worst case fits shared memory runs the
+// shape-generic LDL' kernel with the generic pivoted-LU kernel behind it.
 int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool* handled) {
     *handled = false;
-    if (a.n != NV || a.m != MI || a.p != PE) return 0;
+    const bool headline = a.n == NV && a.m == MI && a.p == PE;
     const char* force = getenv("DIFFOPT_B200_QP_KERNEL");
     if (force && strcmp(force, "generic") == 0) return 0;
+    if (!headline) {
+        if (force && strcmp(force, "lu") == 0) return 0;
+        if (!qp_sqd_any_supported(ctx, a)) return 0;
+    }
+    // the active-set hint below belongs to one shape: a new shape starts over (outstanding reports are drained first)
+    const int64_t shape_key = ((int64_t)a.n << 40) | ((int64_t)a.m << 20) | (int64_t)a.p;
+    if (shape_key != ctx->qp_hint_shape) {
+        if (ctx->qp_hint_shape != -1) DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t& c : ctx->qp_hmax_call) c = -1;
+        ctx->qp_hint = -1;
+        ctx->qp_hint_shape = shape_key;
+    }
     // The shared-memory configuration depends on the largest active set of the batch (reduced order 80 + active).
     // First call: measure it and wait for the answer.  Later calls: launch for the size seen by the PREVIOUS call
     // (no host round trip in the middle of the call); instances that do not fit that guess are handed to the
@@ -882,6 +901,7 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
     auto scan_active = [&]() -> cudaError_t {
         int64_t blocks = (a.B + 7) / 8;
         if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        if (!headline) return qp_max_active_any_launch(ctx, a, dmax) == 0 ? cudaSuccess : cudaErrorUnknown;
         max_active_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a.B, a.lam, dmax);
         ctx->launches++;
         return cudaGetLastError();
@@ -897,10 +917,11 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
         ctx->qp_hint = ctx->qp_hmax_host[slot] & 0xFF;
         ctx->qp_hmax_call[slot] = -1;
     }
-    const int nt_cap = (NV + ctx->qp_hint + PE + 7) / 8;
+    const int nt_cap = headline ? (NV + ctx->qp_hint + PE + 7) / 8 : qp_sqd_any_nt(a, ctx->qp_hint);
     bool reported = first;
     if (want_ldl) {
-        int32_t rc = qp_sqd_launch(ctx, a, nt_cap, handled, first ? nullptr : dmax, ctx->qp_seq << 8);
+        int32_t rc = headline ? qp_sqd_launch(ctx, a, nt_cap, handled, first ? nullptr : dmax, ctx->qp_seq << 8)
+                              : qp_sqd_any_launch(ctx, a, nt_cap, handled, first ? nullptr : dmax, ctx->qp_seq << 8);
         if (rc != 0) return rc;
         if (*handled) {
             if (!first) DO_CUDA(ctx, report_to_host());
@@ -909,6 +930,7 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
             return 0;
         }
     }
+    if (!headline) return 0;  // (not reached: qp_sqd_any_supported covers the launch) the generic kernel takes the batch
     if (!reported) {
         if (!clear) DO_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(int), ctx->stream));
         DO_CUDA(ctx, scan_active());

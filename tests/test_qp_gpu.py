@@ -545,3 +545,69 @@ def test_c99_client_runs_the_reference_known_answer(tmp_path):
     exe = _build_c99_client(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "(ok)" in r.stdout, r.stdout + r.stderr
+
+
+# ---- every other shape: the shape-generic LDL' fast path (qp_batch_sqd_any.cu) with the generic pivoted LU behind it
+
+ANY_SHAPES = [(10, 25, 10, 0), (5, 0, 2, 0), (7, 9, 0, 3), (3, 0, 0, 0), (33, 47, 5, 11), (1, 1, 0, 1), (80, 60, 20, 30),
+              (100, 50, 0, 12), (32, 32, 8, 8), (50, 100, 10, 20), (17, 130, 3, 9), (64, 64, 8, 16)]
+
+
+@pytest.mark.parametrize("n,m,p,na", ANY_SHAPES)
+def test_any_shape_ldl_fast_path_matches_oracle(ctx, n, m, p, na):
+    """Regular instances of any (n, m, p) are served by the pivot-free LDL' kernel itself (kernel id 2, nothing handed to
+    the pivoted LU): n not a multiple of 8 (identity padding of the z block), no inequalities, no equalities, m > 128."""
+    B = 37
+    d = bench_data.qp_batch(B, n, m, p, n_active=na, seed0=7000 + n + m)
+    _solve(ctx, d)                      # first call of this shape: measures the active sets, configures the launch
+    fwd, rev, info = _solve(ctx, d)
+    assert not info.any()
+    nfb, hint, kern = ctx.qp_last_stats()
+    assert kern == 2 and nfb == 0 and hint == na, (nfb, hint, kern)
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+def test_any_shape_growing_active_set_and_interior_point_duals(ctx):
+    """A batch whose active sets outgrow the configuration of the previous call is still solved correctly (the oversize
+    instances go to the pivoted LU), the next call is configured for it; duals without exact zeros make every row active."""
+    n, m, p = 40, 30, 6
+    small = bench_data.qp_batch(16, n, m, p, n_active=4, seed0=8100)
+    large = bench_data.qp_batch(16, n, m, p, n_active=20, seed0=8200)
+    _solve(ctx, small); _solve(ctx, small)
+    for d in (large, large):
+        fwd, rev, info = _solve(ctx, d)
+        assert not info.any()
+        of, orv = _oracle_batch(d)
+        assert rel_err(fwd, of).max() <= RTOL_DIRECT and rel_err(rev, orv).max() <= RTOL_DIRECT
+    nfb, hint, kern = ctx.qp_last_stats()
+    assert kern == 2 and nfb == 0 and hint == 20, (nfb, hint, kern)
+    ipm = {k: v.copy() for k, v in large.items()}
+    ipm["lam"][ipm["lam"] == 0] = 1e-9
+    for _ in range(2):
+        fwd, rev, info = _solve(ctx, ipm)
+    assert not info.any()
+    nfb, hint, kern = ctx.qp_last_stats()
+    assert kern == 2 and hint == m, (nfb, hint, kern)
+    of, orv = _oracle_batch(ipm)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT and rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+def test_any_shape_rejects_go_to_the_pivoted_lu(ctx):
+    """Instances outside the fast path's assumptions (indefinite Q, singular KKT) inside a regular batch: the regular ones
+    keep their fast-path results, the indefinite one is re-solved by the pivoted LU, the singular one reports info > 0."""
+    n, m, p = 12, 10, 4
+    d = bench_data.qp_batch(9, n, m, p, n_active=3, seed0=8300)
+    d["Q"][2] = np.diag(np.r_[-1.0, np.ones(n - 1)]) + 0.0     # indefinite but nonsingular KKT
+    d["A"][5][1] = d["A"][5][0]                                  # duplicated equality row: exactly singular
+    _solve(ctx, d)
+    fwd, rev, info = _solve(ctx, d)
+    nfb, hint, kern = ctx.qp_last_stats()
+    assert kern == 2 and nfb >= 2
+    assert info[5] > 0 and not np.delete(info, 5).any()
+    keep = np.delete(np.arange(9), 5)
+    sub = {k: v[keep] for k, v in d.items()}
+    of, orv = _oracle_batch(sub)
+    assert rel_err(fwd[keep], of).max() <= RTOL_DIRECT
+    assert rel_err(rev[keep], orv).max() <= RTOL_DIRECT
