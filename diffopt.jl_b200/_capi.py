@@ -39,6 +39,7 @@ SIGNATURES = {
     "diffopt_b200_synchronize": (C.c_int32, [vp]),
     "diffopt_b200_qp_batch_last_stats": (C.c_int32, [vp, vp]),
     "diffopt_b200_qp_batch_solve_ex": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 17 + [C.c_int32, C.c_int32]),
+    "diffopt_b200_qp_batch_solve_coo": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 17 + [C.c_int32, C.c_int32]),
     "diffopt_b200_qp_batch_shared_grads": (C.c_int32, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [vp] * 5 + [C.c_int32, C.c_int32]),
     "diffopt_b200_nccl_unique_id": (C.c_int32, [vp]),
     "diffopt_b200_nccl_init": (C.c_int32, [vp, C.c_int32, C.c_int32, vp]),
@@ -69,6 +70,11 @@ SIGNATURES = {
     "diffopt_b200_sparse_setup_inertia": (C.c_int32, [vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, vp]),
     "diffopt_b200_param_pullback": (C.c_int32, [vp, C.c_int64, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int32]),
 }
+
+
+class CooBatch(C.Structure):
+    """diffopt_b200_coo_batch: per-instance sparse triplets (0-based offsets ptr, 1-based I, J) of a direction matrix."""
+    _fields_ = [("ptr", vp), ("I", vp), ("J", vp), ("V", vp)]
 
 
 def load():

@@ -142,6 +142,7 @@ struct diffopt_b200_ctx {
     void* nccl_comm = nullptr;    // ncclComm_t of diffopt_b200_nccl_init (one rank per ctx)
     int nccl_ranks = 0, nccl_rank = 0;
     DevBuf qp_unpacked[2];        // Q / dQ expanded from packed lower triangles (qp_batch_solve_ex)
+    DevBuf qp_coo[4];             // staged triplets of dQ, dG, dA and the assembled right-hand side (qp_batch_solve_coo)
     ConicBatchImpl* conic_batch = nullptr;
     int csr_cluster_ctas = 0;     // CTAs the cluster-kernel row blocks of csr_from_csc_host are cut for (0: default 16)
     SparseMfImpl* sparse_mf = nullptr;
@@ -233,6 +234,9 @@ struct QpSolveArgs {
     unsigned long long* sticky;  // optional: first failing (call, instance) of a stream-ordered sequence of calls
     unsigned call_seq;
     int shared;  // bit 0: Q, G, A are ONE instance shared by the whole batch; bit 1: dQ, dG, dA likewise
+    // optional: forward right-hand side already assembled on the device from sparse triplets (qp_batch_solve_coo),
+    // [B][n+m+p] = [dQ z + dq + dG'lam + dA'nu; dG z - dh; dA z - db]; dQ .. db are then unused
+    const double* rhs_pre;
 };
 
 // what a kernel does when instance `inst` turned out singular in a stream-ordered call

@@ -119,7 +119,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
             K[j + (n + m + i) * ld] = v;
         }
         // forward RHS (QuadraticProgram.jl:429-433) accumulated into rf via global reads
-        if (do_fwd) {
+        if (do_fwd && a.rhs_pre) {  // assembled from sparse triplets (dq, dh, db already folded in)
+            for (int i = tid; i < N; i += GEN_THREADS) {
+                const double v = a.rhs_pre[(size_t)inst * N + i];
+                rf[i] = (i >= n && i < n + m) ? lams[i - n] * v : v;
+            }
+        } else if (do_fwd) {
             const size_t b = (size_t)inst;
             const size_t bd = (a.shared & 2) ? 0 : b;
             accum_matvecs(a.dQ ? a.dQ + bd * n * n : nullptr, n, n, zs, nullptr, rf, nullptr, nullptr);
@@ -138,7 +143,8 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
         if (do_fwd) {
             for (int i = tid; i < N; i += GEN_THREADS) {
                 double v = rf[i];
-                if (i < n) {
+                if (a.rhs_pre) {
+                } else if (i < n) {
                     if (a.dq) v += a.dq[(size_t)inst * n + i];
                 } else if (i < n + m) {
                     if (a.dh) v -= lams[i - n] * a.dh[(size_t)inst * m + (i - n)];

@@ -221,7 +221,15 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
             }
         }
         // ---- forward right-hand side (QuadraticProgram.jl:429-433), symmetric-form scaling
-        if (do_fwd) {
+        if (do_fwd && a.rhs_pre) {  // assembled from sparse triplets by qp_coo_rhs_kernel
+            const double* r = a.rhs_pre + b * N;
+            for (int i = tid; i < n; i += THREADS) V.yf[i] = r[i];
+            for (int i = tid; i < m; i += THREADS) {
+                const int ar = apos[i];
+                if (ar >= 0) V.yf[n8 + ar] = r[n + i];
+            }
+            for (int i = tid; i < p; i += THREADS) V.yf[n8 + ma + i] = r[n + m + i];
+        } else if (do_fwd) {
             const double* dQp = a.dQ ? a.dQ + bd * n * n : nullptr;
             const double* dGp = (a.dG && m) ? a.dG + bd * m * n : nullptr;
             const double* dAp = (a.dA && p) ? a.dA + bd * p * n : nullptr;

@@ -34,6 +34,52 @@ __global__ void unpack_lower_kernel(const double* __restrict__ packed, double* _
     }
 }
 
+// Forward right-hand side [dQ z + dq + dG'lam + dA'nu; dG z - dh; dA z - db] (QuadraticProgram.jl:429-433, the middle block
+// before its scaling by lam) from the direction's sparse triplets -- what the reference holds after diff_opt.jl:594-656 and
+// SparseArrays.sparse (duplicates add up).  One thread per instance walks its triplets in storage order (a fixed
+// summation order); an index outside its matrix raises *err and is skipped.
+struct CooDev {
+    const int64_t *ptr, *I, *J;
+    const double* V;
+};
+
+__global__ void qp_coo_rhs_kernel(const int64_t B, const int n, const int m, const int p, const double* __restrict__ z,
+                                  const double* __restrict__ lam, const double* __restrict__ nu, const CooDev cq, const CooDev cg,
+                                  const CooDev ca, const double* __restrict__ dq, const double* __restrict__ dh,
+                                  const double* __restrict__ db, const int shared_dir, double* __restrict__ rhs, int* err) {
+    const int N = n + m + p;
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+        double* r = rhs + b * N;
+        const double* zb = z + b * n;
+        const int64_t bt = shared_dir ? 0 : b;
+        for (int i = 0; i < n; ++i) r[i] = dq ? dq[b * n + i] : 0.0;
+        for (int i = 0; i < m; ++i) r[n + i] = dh ? -dh[b * m + i] : 0.0;
+        for (int i = 0; i < p; ++i) r[n + m + i] = db ? -db[b * p + i] : 0.0;
+        if (cq.ptr)
+            for (int64_t k = cq.ptr[bt]; k < cq.ptr[bt + 1]; ++k) {
+                const int64_t i = cq.I[k] - 1, j = cq.J[k] - 1;
+                if (i < 0 || i >= n || j < 0 || j >= n) { *err = 1; continue; }
+                r[i] += cq.V[k] * zb[j];
+            }
+        if (cg.ptr && m)
+            for (int64_t k = cg.ptr[bt]; k < cg.ptr[bt + 1]; ++k) {
+                const int64_t i = cg.I[k] - 1, j = cg.J[k] - 1;
+                if (i < 0 || i >= m || j < 0 || j >= n) { *err = 1; continue; }
+                const double v = cg.V[k];
+                r[n + i] += v * zb[j];
+                r[j] += v * lam[b * m + i];
+            }
+        if (ca.ptr && p)
+            for (int64_t k = ca.ptr[bt]; k < ca.ptr[bt + 1]; ++k) {
+                const int64_t i = ca.I[k] - 1, j = ca.J[k] - 1;
+                if (i < 0 || i >= p || j < 0 || j >= n) { *err = 1; continue; }
+                const double v = ca.V[k];
+                r[n + m + i] += v * zb[j];
+                r[j] += v * nu[b * p + i];
+            }
+    }
+}
+
 constexpr int GR_THREADS = 256;
 constexpr int GR_STAGE = 16;  // instances whose vectors one CTA keeps in shared memory at a time
 
@@ -311,6 +357,95 @@ int32_t diffopt_b200_qp_batch_solve_ex(diffopt_b200_ctx* ctx, int64_t B, int32_t
         DO_CUDA(ctx, cudaGetLastError());
     }
     return qp_solve_common(ctx, a, fwd_out, rev_out, info, memspace, async);
+}
+
+int32_t diffopt_b200_qp_batch_solve_coo(diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p, const double* Q,
+                                        const double* G, const double* A, const double* h, const double* z, const double* lam,
+                                        const double* nu, const diffopt_b200_coo_batch* dQ, const double* dq,
+                                        const diffopt_b200_coo_batch* dG, const double* dh, const diffopt_b200_coo_batch* dA,
+                                        const double* db, const double* dl_dz, double* fwd_out, double* rev_out, int32_t* info,
+                                        int32_t memspace, int32_t flags) {
+    if (!ctx) return -1;
+    DeviceGuard guard_(ctx->device);
+    if (B < 0 || n <= 0 || m < 0 || p < 0) BAD_ARG(ctx, "qp_batch_solve_coo: need B >= 0, n > 0, m >= 0, p >= 0");
+    if (B == 0) return 0;
+    if (!Q || !z || (m > 0 && (!G || !h || !lam)) || (p > 0 && (!A || !nu)))
+        BAD_ARG(ctx, "qp_batch_solve_coo: Q, z (and G, h, lam when m > 0; A, nu when p > 0) are required");
+    if (!fwd_out) BAD_ARG(ctx, "qp_batch_solve_coo: fwd_out is required (use qp_batch_solve for reverse mode alone)");
+    if (rev_out && !dl_dz) BAD_ARG(ctx, "qp_batch_solve_coo: rev_out requested without dl_dz");
+    if (flags & ~(DIFFOPT_QP_SHARED_MATRICES | DIFFOPT_QP_SHARED_DIRECTION | DIFFOPT_QP_ASYNC))
+        BAD_ARG(ctx, "qp_batch_solve_coo: flags may hold SHARED_MATRICES, SHARED_DIRECTION, ASYNC");
+    const bool async = (flags & DIFFOPT_QP_ASYNC) != 0;
+    if (async && memspace != DIFFOPT_B200_DEVICE) BAD_ARG(ctx, "qp_batch_solve_coo: DIFFOPT_QP_ASYNC needs device memory");
+    const bool shm = (flags & DIFFOPT_QP_SHARED_MATRICES) != 0, shd = (flags & DIFFOPT_QP_SHARED_DIRECTION) != 0;
+    QpSolveArgs a{};
+    a.B = B; a.n = n; a.m = m; a.p = p;
+    a.shared = shm ? 1 : 0;
+    const size_t d = sizeof(double);
+    const int64_t Bm = shm ? 1 : B, Bd = shd ? 1 : B;
+    const void* ptr;
+    const double *ddq = nullptr, *ddh = nullptr, *ddb = nullptr;
+#define STAGE_COO(slot, dst, src, count)                                                             \
+    DO_CUDA(ctx, stage_in(ctx, ctx->in[slot], src, d * (size_t)(count), memspace, &ptr)); \
+    dst = (const double*)ptr;
+    STAGE_COO(0, a.Q, Q, (size_t)Bm * n * n)
+    STAGE_COO(1, a.G, G, (size_t)Bm * m * n)
+    STAGE_COO(2, a.A, A, (size_t)Bm * p * n)
+    STAGE_COO(3, a.h, h, (size_t)B * m)
+    STAGE_COO(4, a.z, z, (size_t)B * n)
+    STAGE_COO(5, a.lam, lam, (size_t)B * m)
+    STAGE_COO(6, a.nu, nu, (size_t)B * p)
+    STAGE_COO(8, ddq, dq, (size_t)B * n)
+    STAGE_COO(10, ddh, dh, (size_t)B * m)
+    STAGE_COO(12, ddb, db, (size_t)B * p)
+    if (rev_out) { STAGE_COO(13, a.seed, dl_dz, (size_t)B * n) }
+#undef STAGE_COO
+    // triplets: one staging buffer per matrix holding ptr | I | J | V back to back (host memspace), or used in place
+    CooDev dev[3] = {};
+    const diffopt_b200_coo_batch* src[3] = {dQ, dG, dA};
+    const int lim_rows[3] = {n, m, p};
+    for (int q = 0; q < 3; ++q) {
+        const diffopt_b200_coo_batch* c = src[q];
+        if (!c || !c->ptr || lim_rows[q] == 0) continue;
+        if (memspace == DIFFOPT_B200_DEVICE) {
+            dev[q] = CooDev{c->ptr, c->I, c->J, c->V};
+            continue;
+        }
+        const int64_t nnz = c->ptr[Bd];
+        if (c->ptr[0] != 0 || nnz < 0 || (nnz > 0 && (!c->I || !c->J || !c->V)))
+            BAD_ARG(ctx, "qp_batch_solve_coo: triplet offsets must start at 0 and I, J, V must be given");
+        for (int64_t b = 0; b < Bd; ++b)
+            if (c->ptr[b + 1] < c->ptr[b]) BAD_ARG(ctx, "qp_batch_solve_coo: triplet offsets must be nondecreasing");
+        const size_t np8 = sizeof(int64_t) * (size_t)(Bd + 1), nz8 = sizeof(int64_t) * (size_t)nnz;
+        DevBuf& buf = ctx->qp_coo[q];
+        DO_CUDA(ctx, buf.reserve(np8 + 3 * nz8 + 8));
+        char* base = buf.as<char>();
+        DO_CUDA(ctx, cudaMemcpyAsync(base, c->ptr, np8, cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz > 0) {
+            DO_CUDA(ctx, cudaMemcpyAsync(base + np8, c->I, nz8, cudaMemcpyHostToDevice, ctx->stream));
+            DO_CUDA(ctx, cudaMemcpyAsync(base + np8 + nz8, c->J, nz8, cudaMemcpyHostToDevice, ctx->stream));
+            DO_CUDA(ctx, cudaMemcpyAsync(base + np8 + 2 * nz8, c->V, nz8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        dev[q] = CooDev{(const int64_t*)base, (const int64_t*)(base + np8), (const int64_t*)(base + np8 + nz8),
+                        (const double*)(base + np8 + 2 * nz8)};
+    }
+    const int N = n + m + p;
+    DO_CUDA(ctx, ctx->qp_coo[3].reserve(d * (size_t)B * N + sizeof(int)));
+    double* rhs = ctx->qp_coo[3].as<double>();
+    int* derr = reinterpret_cast<int*>(rhs + (size_t)B * N);
+    DO_CUDA(ctx, cudaMemsetAsync(derr, 0, sizeof(int), ctx->stream));
+    const int64_t blocks = std::min<int64_t>((B + 63) / 64, (int64_t)ctx->sm_count * 8);
+    qp_coo_rhs_kernel<<<(unsigned)blocks, 64, 0, ctx->stream>>>(B, n, m, p, a.z, a.lam, a.nu, dev[0], dev[1], dev[2], ddq, ddh, ddb,
+                                                              shd ? 1 : 0, rhs, derr);
+    ctx->launches++;
+    DO_CUDA(ctx, cudaGetLastError());
+    a.rhs_pre = rhs;
+    int32_t rc = qp_solve_common(ctx, a, fwd_out, rev_out, info, memspace, async);
+    if (rc < 0 || async) return rc;
+    int herr = 0;  // the blocking call has synchronised: out-of-range triplet indices are an argument error
+    DO_CUDA(ctx, cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) BAD_ARG(ctx, "qp_batch_solve_coo: a triplet index lies outside its matrix (1-based I, J expected)");
+    return rc;
 }
 
 }  // extern "C"

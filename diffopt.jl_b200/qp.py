@@ -134,6 +134,57 @@ def solve_batch(ctx, Q, G, A, h, z, lam, nu, fwd_dir=None, seed=None):
     return fwd, rev, info
 
 
+def coo_batch(mats, B, shared=False):
+    """Per-instance sparse matrices (a list of B scipy.sparse matrices, or ONE matrix with ``shared``) -> the arrays of a
+    ``diffopt_b200_coo_batch``: 0-based offsets, 1-based (I, J) triplets, values -- what the reference's ``_fill`` collects
+    (src/diff_opt.jl:594-656).  ``None`` -> None (a zero matrix)."""
+    if mats is None:
+        return None
+    import scipy.sparse as sp
+    mats = [mats] if shared else list(mats)
+    assert len(mats) == (1 if shared else B)
+    coos = [sp.coo_matrix(M) for M in mats]
+    ptr = np.zeros(len(coos) + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([c.nnz for c in coos])
+    cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs).astype(dt)) if xs else np.zeros(0, dt)
+    return (ptr, cat([c.row + 1 for c in coos], np.int64), cat([c.col + 1 for c in coos], np.int64),
+            cat([c.data for c in coos], np.float64))
+
+
+def solve_batch_coo(ctx, Q, G, A, h, z, lam, nu, dQ=None, dq=None, dG=None, dh=None, dA=None, db=None, seed=None,
+                    shared_direction=False):
+    """``diffopt_b200_qp_batch_solve_coo``: forward (and optionally reverse) sensitivities with the direction matrices given
+    as sparse triplets (lists of scipy.sparse matrices, one per instance; see ``coo_batch``)."""
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    B, n = z.shape
+    m = 0 if lam is None else np.asarray(lam).reshape(B, -1).shape[1]
+    p = 0 if nu is None else np.asarray(nu).reshape(B, -1).shape[1]
+    N = n + m + p
+    cm = lambda X, r: None if X is None or r == 0 else colmajor(X, r, n, B)
+    vec = lambda v, k: None if v is None or k == 0 else np.ascontiguousarray(np.asarray(v, float).reshape(B, k))
+    args = [cm(Q, n), cm(G, m), cm(A, p), vec(h, m), z, vec(lam, m), vec(nu, p)]
+    keep = []
+
+    def coo(mats, rows):
+        arrs = coo_batch(mats, B, shared_direction) if rows else None
+        if arrs is None:
+            return None
+        keep.append(arrs)
+        st = _capi.CooBatch(*[a.ctypes.data for a in arrs])
+        keep.append(st)
+        return _capi.C.addressof(st)
+    dvecs = [vec(dq, n), vec(dh, m), vec(db, p)]
+    sd = vec(seed, n) if seed is not None else None
+    fwd = np.empty((B, N))
+    rev = np.empty((B, N)) if seed is not None else None
+    info = np.zeros(B, dtype=np.int32)
+    rc = ctx.lib.diffopt_b200_qp_batch_solve_coo(
+        ctx.h, B, n, m, p, *[ptr(a) for a in args], coo(dQ, n), ptr(dvecs[0]), coo(dG, m), ptr(dvecs[1]), coo(dA, p),
+        ptr(dvecs[2]), ptr(sd), ptr(fwd), ptr(rev), ptr(info), HOST, _capi.QP_SHARED_DIRECTION if shared_direction else 0)
+    ctx.check(rc)
+    return fwd, rev, info
+
+
 def pack_lower(X):
     """(B, n, n) symmetric matrices -> (B, n(n+1)/2) packed lower triangles, column by column (DIFFOPT_QP_PACKED_Q)."""
     X = np.asarray(X, dtype=np.float64)
@@ -344,8 +395,20 @@ class QPModel:
         t0 = time.perf_counter()
         n, m, p = self.n, self.m, self.p
         z = lambda v, shape: np.zeros(shape) if v is None else np.asarray(v, float).reshape(shape)
-        d = (z(dQ, (n, n)), z(dq, n), z(dG, (m, n)), z(dh, m), z(dA, (p, n)), z(db, p))
-        x = self._solve(fwd_dir=d)
+        sparse = any(hasattr(M, "tocoo") for M in (dQ, dG, dA))
+        if sparse and not self._iterative():
+            # the reference's own packing: sparse(I, J, V) per matrix (QuadraticProgram.jl:396-424) -> triplets to the device
+            fwd, _, info = solve_batch_coo(self.ctx, self.Q[None], self.G[None] if m else None, self.A[None] if p else None,
+                                           self.h[None], self.x[None], self.lam[None], self.nu[None],
+                                           dQ=None if dQ is None else [dQ], dq=z(dq, n)[None], dG=None if dG is None else [dG],
+                                           dh=z(dh, m)[None], dA=None if dA is None else [dA], db=z(db, p)[None])
+            if info[0] != 0:
+                raise SingularException(int(info[0]))
+            x = fwd[0]
+        else:
+            dense = lambda M: M.toarray() if hasattr(M, "toarray") else M
+            d = (z(dense(dQ), (n, n)), z(dq, n), z(dense(dG), (m, n)), z(dh, m), z(dense(dA), (p, n)), z(db, p))
+            x = self._solve(fwd_dir=d)
         self.forw_grad_cache = (x[:n], x[n:n + m], x[n + m:])
         self.diff_time = time.perf_counter() - t0
 

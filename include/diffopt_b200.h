@@ -135,6 +135,31 @@ int32_t diffopt_b200_qp_batch_solve_ex(
     const double* dA, const double* db, const double* dl_dz,
     double* fwd_out, double* rev_out, int32_t* info, int32_t memspace, int32_t flags);
 
+/* Forward direction given as SPARSE TRIPLETS, the way the reference holds it: src/diff_opt.jl:594-656 collects (I, J, V)
+ * per matrix from the perturbed constraint / objective functions and QuadraticProgram.jl:396-424 turns them into
+ * SparseArrays.sparse(I, J, V, rows, n) (duplicates add up) before forming the right-hand side (:429-433).  The dense form
+ * above moves n*n + m*n + p*n doubles per instance for a direction that usually has a handful of entries; here the
+ * right-hand side is assembled on the device from the triplets and the dense matrices never exist.
+ *   ptr[b] .. ptr[b+1]-1 (0-based offsets, ptr[0] = 0, B+1 entries; 2 entries with DIFFOPT_QP_SHARED_DIRECTION) are the
+ *   triplets of instance b; I, J are 1-based (Julia's); dQ triplets name the full symmetric matrix (both triangles), as the
+ *   reference's sparse dQ does.  A NULL struct pointer or NULL ptr means the matrix is zero.  The struct lives in host
+ *   memory; the arrays it points to live in `memspace`.
+ * flags: DIFFOPT_QP_SHARED_MATRICES, DIFFOPT_QP_SHARED_DIRECTION, DIFFOPT_QP_ASYNC.  fwd_out is required; rev_out / dl_dz
+ * optional as in qp_batch_solve.  Returns as qp_batch_solve; -1 when a triplet index lies outside its matrix. */
+typedef struct diffopt_b200_coo_batch {
+    const int64_t* ptr;
+    const int64_t* I;
+    const int64_t* J;
+    const double* V;
+} diffopt_b200_coo_batch;
+int32_t diffopt_b200_qp_batch_solve_coo(
+    diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
+    const double* Q, const double* G, const double* A, const double* h,
+    const double* z, const double* lam, const double* nu,
+    const diffopt_b200_coo_batch* dQ, const double* dq, const diffopt_b200_coo_batch* dG, const double* dh,
+    const diffopt_b200_coo_batch* dA, const double* db, const double* dl_dz,
+    double* fwd_out, double* rev_out, int32_t* info, int32_t memspace, int32_t flags);
+
 /* Reverse-mode gradients of parameters SHARED by the B instances (the getters of QuadraticProgram.jl:307-314, :448-473
  * accumulated over the samples as docs/src/examples/polyhedral_project.jl:95-104 and src/parameters.jl:355-360 do):
  * out_flat = [dQ (n*n, column-major) | dq (n) | dG (m*n) | dh (m) | dA (p*n) | db (p)], each the SUM over the batch of

@@ -611,3 +611,91 @@ def test_any_shape_rejects_go_to_the_pivoted_lu(ctx):
     of, orv = _oracle_batch(sub)
     assert rel_err(fwd[keep], of).max() <= RTOL_DIRECT
     assert rel_err(rev[keep], orv).max() <= RTOL_DIRECT
+
+
+# ---- forward directions as sparse triplets (diffopt_b200_qp_batch_solve_coo): the reference's own packing of dQ, dG, dA
+
+def _sparse_direction(d, density, seed):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    out = {}
+    for k in ("dQ", "dG", "dA"):
+        X = d[k] * (rng.random(d[k].shape) < density)
+        if k == "dQ":
+            X = (X + X.transpose(0, 2, 1)) / 2
+        out[k] = X
+    return out, {k: [sp.coo_matrix(M) for M in X] for k, X in out.items()}
+
+
+@pytest.mark.parametrize("n,m,p,na", [(64, 64, 16, 16), (33, 47, 5, 11), (5, 0, 2, 0), (80, 60, 20, 30)])
+def test_sparse_triplet_directions_match_dense_call_and_oracle(ctx, n, m, p, na):
+    """Sparse (I, J, V) directions (src/diff_opt.jl:594-656, QuadraticProgram.jl:396-424) give the dense call's answer."""
+    qpm = diffopt_b200.submodule("qp")
+    d = bench_data.qp_batch(19, n, m, p, n_active=na, seed0=9100 + n)
+    dense, coo = _sparse_direction(d, 0.05, 1 + n)
+    d.update(dense)
+    for _ in range(2):
+        fwd, rev, info = qpm.solve_batch_coo(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], dQ=coo["dQ"],
+                                             dq=d["dq"], dG=coo["dG"], dh=d["dh"], dA=coo["dA"], db=d["db"], seed=d["seed"])
+    assert not info.any()
+    nfb, hint, kern = ctx.qp_last_stats()
+    assert kern == 2 and nfb == 0
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
+    f2, _, _ = _solve(ctx, d)
+    assert rel_err(fwd, f2).max() <= 1e-12
+
+
+def test_sparse_triplet_edge_cases(ctx, monkeypatch):
+    """Empty directions, duplicated triplets (added up like SparseArrays.sparse), one direction shared by the batch, an
+    out-of-range index (argument error), and the generic pivoted-LU kernel consuming the assembled right-hand side."""
+    import scipy.sparse as sp
+    qpm = diffopt_b200.submodule("qp")
+    n, m, p = 12, 9, 3
+    d = bench_data.qp_batch(6, n, m, p, n_active=3, seed0=9300)
+    z0 = {k: np.zeros_like(d[k]) for k in ("dQ", "dG", "dA")}
+    base = dict(d); base.update(z0)
+    fwd, _, _ = qpm.solve_batch_coo(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], dq=d["dq"], dh=d["dh"], db=d["db"])
+    of, _ = _oracle_batch(base)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    # duplicates: the same entry twice with half the value each
+    dG1 = np.zeros((m, n)); dG1[2, 5] = 1.5; dG1[7, 0] = -2.0
+    dup = sp.coo_matrix((np.array([0.75, 0.75, -2.0]), (np.array([2, 2, 7]), np.array([5, 5, 0]))), shape=(m, n))
+    shared = dict(base); shared["dG"] = np.broadcast_to(dG1, (6, m, n)).copy()
+    fwd, _, _ = qpm.solve_batch_coo(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], dq=d["dq"], dG=dup, dh=d["dh"],
+                                    db=d["db"], shared_direction=True)
+    of, _ = _oracle_batch(shared)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    monkeypatch.setenv("DIFFOPT_B200_QP_KERNEL", "generic")
+    f3, _, _ = qpm.solve_batch_coo(ctx, d["Q"], d["G"], d["A"], d["h"], d["z"], d["lam"], d["nu"], dq=d["dq"], dG=dup, dh=d["dh"],
+                                   db=d["db"], shared_direction=True)
+    monkeypatch.delenv("DIFFOPT_B200_QP_KERNEL")
+    assert ctx.qp_last_stats()[2] == 0 and rel_err(f3, of).max() <= RTOL_DIRECT
+    bad = (np.array([0, 1], np.int64), np.array([m + 1], np.int64), np.array([1], np.int64), np.array([1.0]))
+    capi = diffopt_b200.submodule("_capi")
+    st = capi.CooBatch(*[a.ctypes.data for a in bad])
+    B = 6
+    cm = lambda X, r: qpm.colmajor(X, r, n, B)
+    out = np.empty((B, n + m + p)); info = np.zeros(B, np.int32)
+    rc = ctx.lib.diffopt_b200_qp_batch_solve_coo(
+        ctx.h, B, n, m, p, capi.ptr(cm(d["Q"], n)), capi.ptr(cm(d["G"], m)), capi.ptr(cm(d["A"], p)), capi.ptr(d["h"]), capi.ptr(d["z"]),
+        capi.ptr(d["lam"]), capi.ptr(d["nu"]), None, None, capi.C.addressof(st), None, None, None, None, capi.ptr(out), None,
+        capi.ptr(info), capi.HOST, capi.QP_SHARED_DIRECTION)
+    assert rc == -1
+    with pytest.raises(diffopt_b200.DiffOptB200Error, match="outside"):
+        ctx.check(rc)
+
+
+def test_qpmodel_takes_sparse_directions(ctx):
+    import scipy.sparse as sp
+    qpm = diffopt_b200.submodule("qp")
+    n, m, p = 10, 7, 2
+    d = bench_data.qp_batch(1, n, m, p, n_active=2, seed0=9400)
+    model = qpm.QPModel(ctx, d["Q"][0], d["q"][0], d["G"][0], d["h"][0], d["A"][0], d["b"][0])
+    model.set_variable_primal(d["z"][0]); model.set_constraint_dual_le(-d["lam"][0]); model.set_constraint_dual_eq(-d["nu"][0])
+    dG = np.zeros((m, n)); dG[1, 3] = 1.0
+    model.forward_differentiate(dG=sp.csr_matrix(dG), dh=d["dh"][0])
+    got = model.forward_variable_primal().copy()
+    model.forward_differentiate(dG=dG, dh=d["dh"][0])
+    assert np.allclose(got, model.forward_variable_primal(), rtol=1e-10, atol=1e-13)
