@@ -75,6 +75,7 @@ struct ConicState {
     DevBuf psd_toff;                  // tile offsets of the PSD apply (lsqr.cu)
     int64_t psd_ntiles = 0;
     DevBuf psd_lam, psd_loff;         // eigenvalues (+ shifts) and per-cone offsets into them (+ small-cone list)
+    DevBuf psd_tri;                   // tau, diagonal, off-diagonal, scale, cluster flags of the tridiagonal route (psd_tridiag.cu)
     int64_t npsd = 0, psd_maxd = 0, psd_sumd2 = 0;
     std::vector<int64_t> h_psd_off, h_psd_d, h_psd_uoff;
     // work vectors for M apply / LSQR
@@ -243,7 +244,8 @@ struct QpSolveArgs {
 __device__ __forceinline__ void qp_report_sticky(const QpSolveArgs& a, long long inst) {
     if (a.sticky) atomicMin(a.sticky, ((unsigned long long)a.call_seq << 32) | (unsigned)(inst + 1));
 }
-int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const std::vector<long long>& h_uoff);
+int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const std::vector<long long>& h_uoff,
+                       const std::vector<int>& h_off);
 int32_t qp_batch_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a);
 int32_t qp_param_grads_launch(diffopt_b200_ctx* ctx, int64_t B, int n, int m, int p, const double* z,
                               const double* lam, const double* nu, const double* rev, int reduce,

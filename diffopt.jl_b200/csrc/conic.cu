@@ -392,7 +392,7 @@ int32_t diffopt_b200_conic_setup(diffopt_b200_ctx* ctx, int64_t n, int64_t m, co
         ctx->launches++;
     }
     if (S.npsd > 0)
-        if (int32_t rc = psd_eig_launch(ctx, psd_d, psd_uoff)) return rc;
+        if (int32_t rc = psd_eig_launch(ctx, psd_d, psd_uoff, psd_off)) return rc;
     DO_CUDA(ctx, cudaGetLastError());
     DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "lsqr.cuh"
 
@@ -302,7 +303,7 @@ __global__ void psd_lambda_kernel(const int* __restrict__ pd, const long long* _
 __global__ void psd_finish_kernel(const int* __restrict__ poff, const int* __restrict__ pd,
                                   const long long* __restrict__ uoff, const long long* __restrict__ loff,
                                   const double* __restrict__ lam, const double* __restrict__ Vall,
-                                  double* __restrict__ Bm, int* __restrict__ ident, double* __restrict__ vp) {
+                                  double* __restrict__ Bm, int* __restrict__ ident, double* __restrict__ vp, const int vp_max_d) {
     extern __shared__ double ls[];  // eigenvalues of this cone
     const int c = blockIdx.y, d = pd[c], off = poff[c];
     const double* V = Vall + uoff[c];
@@ -331,6 +332,7 @@ __global__ void psd_finish_kernel(const int* __restrict__ poff, const int* __res
         }
         Bc[e] = bv;
     }
+    if (d > vp_max_d) return;  // larger cones: pi(v) by the tiled product of psd_projection_launch
     const long long tri = (long long)d * (d + 1) / 2;
     for (long long e = first; e < tri; e += stride) {
         int cc = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
@@ -349,7 +351,22 @@ __global__ void psd_finish_kernel(const int* __restrict__ poff, const int* __res
 }  // namespace
 
 // Host driver, called from diffopt_b200_conic_setup after v = y - s is on the device.
-int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const std::vector<long long>& h_uoff) {
+bool psd_tridiag_supported(diffopt_b200_ctx* ctx, int d);
+int32_t psd_tridiag_eig_launch(diffopt_b200_ctx* ctx, int d, const double* xtri, double* w0, double* w1, double* w2, double* small,
+                               double* U, double* lam);
+int32_t psd_projection_launch(diffopt_b200_ctx* ctx, int d, const double* U, const double* lam, double* vp);
+
+// Which eigensolver takes a cone of side d: 0 one-CTA Jacobi (d <= 111), 1 tridiagonalisation + bisection + inverse iteration
+// (psd_tridiag.cu), 2 block Jacobi over a cooperative grid.  DIFFOPT_B200_PSD=jacobi keeps every larger cone on the block Jacobi.
+static int psd_method(diffopt_b200_ctx* ctx, int d, size_t smem_cap) {
+    if ((size_t)16 * d * d <= smem_cap) return 0;
+    const char* force = getenv("DIFFOPT_B200_PSD");
+    if (!(force && strcmp(force, "jacobi") == 0) && psd_tridiag_supported(ctx, d)) return 1;
+    return 2;
+}
+
+int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const std::vector<long long>& h_uoff,
+                       const std::vector<int>& h_off) {
     ConicState& S = ctx->conic;
     const int npsd = (int)h_d.size();
     if (npsd == 0) return 0;
@@ -376,7 +393,13 @@ int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const
     if (!small.empty())
         DO_CUDA(ctx, cudaMemcpyAsync(d_small, small.data(), sizeof(int) * small.size(), cudaMemcpyHostToDevice,
                                      ctx->stream));
-    const int nlarge = npsd - (int)small.size();
+    int nlarge = 0, ntri = 0, maxd_tri = 0;
+    for (int c = 0; c < npsd; ++c) {
+        const int meth = psd_method(ctx, h_d[(size_t)c], smem_cap);
+        nlarge += meth == 2;
+        ntri += meth == 1;
+        if (meth == 1 && h_d[(size_t)c] > maxd_tri) maxd_tri = h_d[(size_t)c];
+    }
     DO_CUDA(ctx, ctx->in[14].reserve(sizeof(int) * (size_t)(nlarge + 1) * (PSD_MAX_SWEEPS + 2)));
     DO_CUDA(ctx, cudaMemsetAsync(ctx->in[14].ptr, 0, sizeof(int) * (size_t)(nlarge + 1) * (PSD_MAX_SWEEPS + 2),
                                  ctx->stream));
@@ -388,12 +411,17 @@ int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const
     const int* pd = S.psd_d.as<int>();
     const long long* uoff = S.psd_uoff.as<long long>();
 
-    psd_sigma_kernel<<<npsd, 256, 0, ctx->stream>>>(poff, pd, S.v.as<double>(), sigma);
-    int chunks = (int)(((long long)maxd * maxd + 255) / 256);
-    if (chunks > 64) chunks = 64;
-    psd_init_kernel<<<dim3((unsigned)chunks, (unsigned)npsd), 256, 0, ctx->stream>>>(poff, pd, uoff, S.v.as<double>(),
-                                                                                      sigma, G, V);
-    ctx->launches += 2;
+    const bool any_jacobi = !small.empty() || nlarge > 0;  // the Jacobi kernels work on G = (X + sigma I) V, V = I
+    // cones of the one-CTA Jacobi form pi(v) inside psd_finish_kernel, larger ones by the tiled product
+    const int vp_max_d = (int)floor(sqrt((double)smem_cap / 16.0));
+    if (any_jacobi) {
+        psd_sigma_kernel<<<npsd, 256, 0, ctx->stream>>>(poff, pd, S.v.as<double>(), sigma);
+        int chunks = (int)(((long long)maxd * maxd + 255) / 256);
+        if (chunks > 64) chunks = 64;
+        psd_init_kernel<<<dim3((unsigned)chunks, (unsigned)npsd), 256, 0, ctx->stream>>>(poff, pd, uoff, S.v.as<double>(),
+                                                                                          sigma, G, V);
+        ctx->launches += 2;
+    }
     if (!small.empty()) {
         const size_t smem = (size_t)16 * maxd_small * maxd_small;
         int warps = (maxd_small + 1) / 2;
@@ -407,7 +435,7 @@ int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const
     int li = 0;
     for (int c = 0; c < npsd; ++c) {
         const int d = h_d[(size_t)c];
-        if ((size_t)16 * d * d <= smem_cap) continue;
+        if (psd_method(ctx, d, smem_cap) != 2) continue;
         int b = (int)(smem_cap / ((size_t)32 * d));  // 2 matrices x 2b columns x d doubles
         if (b > 32) b = 32;
         if (b > d / 20) b = d / 20 < 4 ? 4 : d / 20;  // measured on B200 (d = 200): 10 CTAs x 10-column blocks beat 4 x 25
@@ -436,14 +464,34 @@ int32_t psd_eig_launch(diffopt_b200_ctx* ctx, const std::vector<int>& h_d, const
         ctx->launches++;
         ++li;
     }
-    psd_lambda_kernel<<<dim3((unsigned)((maxd + 7) / 8), (unsigned)npsd), 256, 0, ctx->stream>>>(
-        pd, uoff, S.psd_loff.as<long long>(), G, V, sigma, lam);
+    if (any_jacobi) {
+        psd_lambda_kernel<<<dim3((unsigned)((maxd + 7) / 8), (unsigned)npsd), 256, 0, ctx->stream>>>(
+            pd, uoff, S.psd_loff.as<long long>(), G, V, sigma, lam);
+        ctx->launches++;
+    }
+    if (ntri > 0) {  // after the Rayleigh quotients above (which cover every cone): these cones get their own lam and U
+        DO_CUDA(ctx, S.psd_tri.reserve(sizeof(double) * (size_t)(5 * maxd_tri + 8)));
+        double* work = S.psd_work.as<double>();
+        for (int c = 0; c < npsd; ++c) {
+            const int d = h_d[(size_t)c];
+            if (psd_method(ctx, d, smem_cap) != 1) continue;
+            const long long uo = h_uoff[(size_t)c];
+            if (int32_t rc = psd_tridiag_eig_launch(ctx, d, S.v.as<double>() + h_off[(size_t)c], work + uo, work + S.psd_sumd2 + uo,
+                                                    work + 2 * S.psd_sumd2 + uo, S.psd_tri.as<double>(), V + uo, lam + loff[(size_t)c]))
+                return rc;
+        }
+    }
     int fchunks = (int)(((long long)maxd * maxd + 255) / 256);
     if (fchunks > 2 * ctx->sm_count) fchunks = 2 * ctx->sm_count;
     psd_finish_kernel<<<dim3((unsigned)fchunks, (unsigned)npsd), 256, sizeof(double) * (size_t)maxd, ctx->stream>>>(
         poff, pd, uoff, S.psd_loff.as<long long>(), lam, V, S.psd_Bm.as<double>(), S.psd_ident.as<int>(),
-        S.vp.as<double>());
-    ctx->launches += 2;
+        S.vp.as<double>(), vp_max_d);
+    ctx->launches += 1;
+    for (int c = 0; c < npsd; ++c)
+        if (h_d[(size_t)c] > vp_max_d)
+            if (int32_t rc = psd_projection_launch(ctx, h_d[(size_t)c], V + h_uoff[(size_t)c], lam + loff[(size_t)c],
+                                                   S.vp.as<double>() + h_off[(size_t)c]))
+                return rc;
     if (getenv("DIFFOPT_B200_PSD_DEBUG") && nlarge > 0) {  // sweeps and rotations per sweep of the block Jacobi
         std::vector<int> h((size_t)nlarge * (PSD_MAX_SWEEPS + 2));
         DO_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->in[14].ptr, sizeof(int) * h.size(), cudaMemcpyDeviceToHost,
