@@ -448,6 +448,52 @@ function qp_batch_reverse_shared(ctx::Context, Q::Matrix{Float64}, G::Matrix{Flo
     return rev
 end
 
+"C layout of `diffopt_b200_coo_batch`: per-instance sparse triplets (0-based offsets `ptr`, Julia's 1-based `I`, `J`)"
+struct CooBatch
+    ptr::Ptr{Int64}
+    I::Ptr{Int64}
+    J::Ptr{Int64}
+    V::Ptr{Float64}
+end
+
+"""
+    qp_batch_forward_sparse(ctx, Q, G, A, h, z, lam, nu; dQ, dq, dG, dh, dA, db)
+
+Forward sensitivities of B QPs whose direction matrices are the sparse triplets the reference itself builds: `dQ[b]`, `dG[b]`,
+`dA[b]` are `SparseMatrixCSC` (QuadraticProgram.jl:396-424: `sparse(dGi, dGj, dGv, m, nv)` from the `_fill` of
+src/diff_opt.jl:594-656) or `nothing`.  The right-hand side of :429-433 is assembled on the device; no dense direction exists.
+"""
+function qp_batch_forward_sparse(ctx::Context, Q::Array{Float64,3}, G::Array{Float64,3}, A::Array{Float64,3}, h::Matrix{Float64},
+                                 z::Matrix{Float64}, lam::Matrix{Float64}, nu::Matrix{Float64};
+                                 dQ = nothing, dq = nothing, dG = nothing, dh = nothing, dA = nothing, db = nothing)
+    n, B = size(z); m = size(G, 1); p = size(A, 1)
+    function triplets(mats)
+        mats === nothing && return nothing
+        ptr = zeros(Int64, B + 1); I = Int64[]; J = Int64[]; V = Float64[]
+        for b in 1:B
+            i, j, v = SparseArrays.findnz(mats[b])
+            append!(I, i); append!(J, j); append!(V, v)
+            ptr[b + 1] = length(V)
+        end
+        return (ptr, I, J, V)
+    end
+    tq, tg, ta = triplets(dQ), triplets(dG), triplets(dA)
+    fwd = Matrix{Float64}(undef, n + m + p, B)
+    info = zeros(Int32, B)
+    ref(t) = t === nothing ? nothing : Ref(CooBatch(pointer(t[1]), pointer(t[2]), pointer(t[3]), pointer(t[4])))
+    rq, rg, ra = ref(tq), ref(tg), ref(ta)
+    cptr(r) = r === nothing ? Ptr{CooBatch}(C_NULL) : Base.unsafe_convert(Ptr{CooBatch}, r)
+    vptr(v) = v === nothing ? Ptr{Float64}(C_NULL) : pointer(v)
+    rc = GC.@preserve tq tg ta rq rg ra dq dh db ccall((:diffopt_b200_qp_batch_solve_coo, LIB), Int32,
+               (Ptr{Cvoid}, Int64, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{CooBatch}, Ptr{Float64}, Ptr{CooBatch}, Ptr{Float64}, Ptr{CooBatch}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32, Int32),
+               ctx.handle, B, n, m, p, Q, G, A, h, z, lam, nu, cptr(rq), vptr(dq), cptr(rg), vptr(dh), cptr(ra), vptr(db),
+               C_NULL, fwd, C_NULL, info, HOST, Int32(0))
+    check(ctx, rc)
+    return fwd
+end
+
 "batch sum of the getters (QuadraticProgram.jl:307-314, :448-473) as one flat block [dQ | dq | dG | dh | dA | db]; `allreduce`: summed over the ranks of nccl_init"
 function qp_batch_shared_grads(ctx::Context, z::Matrix{Float64}, lam::Matrix{Float64}, nu::Matrix{Float64}, rev::Matrix{Float64};
                                allreduce::Bool = false)
