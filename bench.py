@@ -749,12 +749,14 @@ def other_shapes_sweep(ctx, lib, capi, dev, timed, check, dptr):
 
     import bench_data
     out = {}
-    for n, m, p, na, B in [(100, 50, 0, 10, 4096), (32, 32, 8, 8, 8192), (16, 16, 4, 4, 16384), (50, 100, 10, 20, 4096)]:
+    for n, m, p, na, B in [(100, 50, 0, 10, 4096), (32, 32, 8, 8, 8192), (16, 16, 4, 4, 16384), (50, 100, 10, 20, 4096),
+                           (N_VAR, M_INEQ, P_EQ, 16, 4096)]:   # last: the headline shape through the shape-generic kernel
         d = bench_data.qp_batch_fast(B, n, m, p, n_active=na, seed=500 + n)
         t = {k: torch.from_numpy(np.ascontiguousarray(d[k].transpose(0, 2, 1) if k in SHAPES else d[k])).to(dev) for k in FIELDS}
         N = n + m + p
         res = {}
-        for label, force in (("ldl_fast_path", None), ("generic_pivoted_lu", "generic")):
+        headline = (n, m, p) == (N_VAR, M_INEQ, P_EQ)
+        for label, force in (("ldl_fast_path", "ldl_any" if headline else None), ("generic_pivoted_lu", "generic")):
             fo = torch.empty((B, N), dtype=torch.float64, device=dev)
             ro = torch.empty_like(fo)
             io = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -767,7 +769,7 @@ def other_shapes_sweep(ctx, lib, capi, dev, timed, check, dptr):
 
                 def step():
                     check(lib.diffopt_b200_qp_batch_solve_async(ctx.h, B, n, m, p, *a), "qp_batch_solve_async")
-                steps = 10 if force else 20
+                steps = 10 if force == "generic" else 20
                 ms, _ = timed(step, steps, lambda: check(lib.diffopt_b200_synchronize(ctx.h), "synchronize"))
             finally:
                 os.environ.pop("DIFFOPT_B200_QP_KERNEL", None)

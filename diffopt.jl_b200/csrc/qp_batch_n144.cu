@@ -841,8 +841,9 @@ int32_t qp_lu_launch_list(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_ca
 // shape-generic LDL' kernel with the generic pivoted-LU kernel behind it.
 int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool* handled) {
     *handled = false;
-    const bool headline = a.n == NV && a.m == MI && a.p == PE && !a.rhs_pre;  // the tuned kernels stream dense directions
     const char* force = getenv("DIFFOPT_B200_QP_KERNEL");
+    // the tuned kernels stream dense directions; `ldl_any` runs the shape-generic pair on the headline shape too (measurement)
+    const bool headline = a.n == NV && a.m == MI && a.p == PE && !a.rhs_pre && !(force && strcmp(force, "ldl_any") == 0);
     if (force && strcmp(force, "generic") == 0) return 0;
     if (!headline) {
         if (force && strcmp(force, "lu") == 0) return 0;

@@ -70,11 +70,18 @@ __device__ void rows_times(const double* __restrict__ X, const int R, const int 
         if (X && r < R) {
             const double* x = X + r;
             int j = grp;
-            for (; j + 3 * ngrp < n; j += 4 * ngrp) {
-                s0 = fma(__ldg(x + (size_t)j * R), zc[j], s0);
-                s1 = fma(__ldg(x + (size_t)(j + ngrp) * R), zc[j + ngrp], s1);
-                s2 = fma(__ldg(x + (size_t)(j + 2 * ngrp) * R), zc[j + 2 * ngrp], s2);
-                s3 = fma(__ldg(x + (size_t)(j + 3 * ngrp) * R), zc[j + 3 * ngrp], s3);
+            for (; j + 7 * ngrp < n; j += 8 * ngrp) {  // eight independent loads in flight per thread
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(x + (size_t)(j + u * ngrp) * R);
+                s0 = fma(v[0], zc[j], s0);
+                s1 = fma(v[1], zc[j + ngrp], s1);
+                s2 = fma(v[2], zc[j + 2 * ngrp], s2);
+                s3 = fma(v[3], zc[j + 3 * ngrp], s3);
+                s0 = fma(v[4], zc[j + 4 * ngrp], s0);
+                s1 = fma(v[5], zc[j + 5 * ngrp], s1);
+                s2 = fma(v[6], zc[j + 6 * ngrp], s2);
+                s3 = fma(v[7], zc[j + 7 * ngrp], s3);
             }
             for (; j < n; j += ngrp) s0 = fma(__ldg(x + (size_t)j * R), zc[j], s0);
         }
@@ -92,13 +99,29 @@ __device__ void rows_times(const double* __restrict__ X, const int R, const int 
 // out[j] = sum_r X[r + j R] wr[r], j < n: one warp per column, lanes over the rows, fixed shuffle tree
 __device__ void cols_times(const double* __restrict__ X, const int R, const int n, const double* wr, double* out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int j = warp; j < n; j += NWARP) {
-        double c = 0.0;
+    for (int j0 = 4 * warp; j0 < n; j0 += 4 * NWARP) {  // four columns per pass: their loads and shuffle trees overlap
+        double c[4] = {0.0, 0.0, 0.0, 0.0};
         if (X)
-            for (int r = lane; r < R; r += 32) c = fma(__ldg(X + (size_t)j * R + r), wr[r], c);
-        c = warp_sum(c);
-        if (lane == 0) out[j] = c;
+            for (int r = lane; r < R; r += 32) {
+                const double w = wr[r];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j0 + u < n) c[u] = fma(__ldg(X + (size_t)(j0 + u) * R + r), w, c[u]);
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] += __shfl_xor_sync(FULL, c[u], o);
+        }
+        if (lane < 4 && j0 + lane < n) out[j0 + lane] = lane == 0 ? c[0] : (lane == 1 ? c[1] : (lane == 2 ? c[2] : c[3]));
     }
+}
+
+// pull a range of global memory towards L2 (128-byte lines dealt to the CTA's threads)
+__device__ __forceinline__ void prefetch_l2(const void* p, const size_t bytes) {
+    if (!p) return;
+    const char* c = reinterpret_cast<const char*>(p);
+    for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
 }
 
 __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs a, int* fb_list, int* fb_count, const int nt_cap,
@@ -128,6 +151,11 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
         const double* Q = a.Q + bm * n * n;
         const double* G = m ? a.G + bm * m * n : nullptr;
         const double* A = p ? a.A + bm * p * n : nullptr;
+        if (do_fwd && !a.rhs_pre) {  // this instance's direction is consumed a few microseconds from now: pull it into L2
+            if (a.dQ) prefetch_l2(a.dQ + bd * n * n, sizeof(double) * n * n);
+            if (a.dG && m) prefetch_l2(a.dG + bd * m * n, sizeof(double) * m * n);
+            if (a.dA && p) prefetch_l2(a.dA + bd * p * n, sizeof(double) * p * n);
+        }
         // ---- vectors, active set
         for (int i = tid; i < n8; i += THREADS) {
             zs[i] = i < n ? a.z[b * n + i] : 0.0;
@@ -177,13 +205,23 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
         }
         __syncthreads();
         // ---- Q (lower triangle), identity padding, active rows of G, A
-        for (int c = warp; c < n; c += NWARP) {
+#pragma unroll 2
+        for (int c = warp; c < n; c += NWARP) {  // a warp per column; all row chunks of the column loaded before the first store
             const double* qc = Q + (size_t)c * n;
-            for (int r = (c & ~31) + lane; r < n; r += 32) {
-                if (r < c) continue;
-                const double v = __ldg(qc + r);
-                T[tix(r >> 3, c >> 3) * 64 + el(r & 7, c & 7)] = v;
-                if (r == c) V.ref[c] = fabs(v);
+            const int rb = (c & ~31) + lane;
+            double v[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int r = rb + 32 * u;
+                v[u] = (r >= c && r < n) ? __ldg(qc + r) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int r = rb + 32 * u;
+                if (r >= c && r < n) {
+                    T[tix(r >> 3, c >> 3) * 64 + el(r & 7, c & 7)] = v[u];
+                    if (r == c) V.ref[c] = fabs(v[u]);
+                }
             }
         }
         if (tid < n8 - n) {
@@ -195,6 +233,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
             const int r = nred + tid;
             T[tix(nt - 1, nt - 1) * 64 + el(r & 7, r & 7)] = -1.0;
         }
+#pragma unroll 4
         for (int c = warp; c < n; c += NWARP) {
             for (int i = lane; i < m; i += 32) {
                 const int ar = apos[i];
@@ -248,6 +287,21 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
         }
         __syncthreads();
 
+        {   // the next instance's problem data travel to L2 under this instance's factorisation
+            const int64_t nxt = inst + gridDim.x;
+            if (nxt < a.B) {
+                if (!(a.shared & 1)) {
+                    prefetch_l2(a.Q + (size_t)nxt * n * n, sizeof(double) * n * n);
+                    if (m) prefetch_l2(a.G + (size_t)nxt * m * n, sizeof(double) * m * n);
+                    if (p) prefetch_l2(a.A + (size_t)nxt * p * n, sizeof(double) * p * n);
+                }
+                prefetch_l2(a.z + (size_t)nxt * n, sizeof(double) * n);
+                if (m) prefetch_l2(a.lam + (size_t)nxt * m, sizeof(double) * m);
+                if (m) prefetch_l2(a.h + (size_t)nxt * m, sizeof(double) * m);
+                if (p) prefetch_l2(a.nu + (size_t)nxt * p, sizeof(double) * p);
+                if (do_rev) prefetch_l2(a.seed + (size_t)nxt * n, sizeof(double) * n);
+            }
+        }
         factor<0>(T, V, nt, np, ntz, tid, lane, warp, g, t, fo SQD_SUB_ARG);
         __syncthreads();
         {
