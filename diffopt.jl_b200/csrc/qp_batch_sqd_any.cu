@@ -60,7 +60,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 // out[r] = sum_j X[r + j R] zc[j], r < R, for a column-major R x n matrix in global memory.  One owner per row and a fixed
 // summation order (bitwise reproducible): rows go to threads, the columns are dealt to 128 / RP thread groups whose
 // partial sums meet in shared memory.  Called by all threads; synchronises.
-__device__ void rows_times(const double* __restrict__ X, const int R, const int n, const double* zc, double* out, double* part) {
+// Optional scatter (T != nullptr): row r with apos[r] >= 0 is also written to row n8 + apos[r] of the tile grid T while it
+// passes through the registers (the active rows of G), so G is not read a second time for that.
+__device__ void rows_times(const double* __restrict__ X, const int R, const int n, const double* zc, double* out, double* part,
+                           double* T = nullptr, const int* apos = nullptr, const int n8 = 0) {
     const int tid = threadIdx.x;
     const int RP = R >= 96 ? 128 : (R > 32 ? 64 : 32), ngrp = THREADS / RP;
     const int ri = tid % RP, grp = tid / RP;
@@ -69,6 +72,10 @@ __device__ void rows_times(const double* __restrict__ X, const int R, const int 
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         if (X && r < R) {
             const double* x = X + r;
+            const int ar = T ? apos[r] : -1;
+            double* trow = nullptr;  // element (n8 + ar, 0) of the tile grid; column c adds (c >> 3) * 64 + the swizzled in-tile offset
+            const int Rt = n8 + ar;
+            if (ar >= 0) trow = T + tix(Rt >> 3, 0) * 64;
             int j = grp;
             for (; j + 7 * ngrp < n; j += 8 * ngrp) {  // eight independent loads in flight per thread
                 double v[8];
@@ -82,8 +89,19 @@ __device__ void rows_times(const double* __restrict__ X, const int R, const int 
                 s1 = fma(v[5], zc[j + 5 * ngrp], s1);
                 s2 = fma(v[6], zc[j + 6 * ngrp], s2);
                 s3 = fma(v[7], zc[j + 7 * ngrp], s3);
+                if (trow) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int c = j + u * ngrp;
+                        trow[(c >> 3) * 64 + el(Rt & 7, c & 7)] = v[u];
+                    }
+                }
             }
-            for (; j < n; j += ngrp) s0 = fma(__ldg(x + (size_t)j * R), zc[j], s0);
+            for (; j < n; j += ngrp) {
+                const double v = __ldg(x + (size_t)j * R);
+                s0 = fma(v, zc[j], s0);
+                if (trow) trow[(j >> 3) * 64 + el(Rt & 7, j & 7)] = v;
+            }
         }
         part[tid] = (s0 + s1) + (s2 + s3);
         __syncthreads();
@@ -143,6 +161,16 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
     const bool do_fwd = a.fwd != nullptr, do_rev = a.rev != nullptr;
 #ifdef QP_PROFILE
     long long sub[6] = {0, 0, 0, 0, 0, 0};
+    long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define APROF(i)                  \
+    do {                          \
+        long long _n = clock64(); \
+        pc[i] += _n - tprev;      \
+        tprev = _n;               \
+    } while (0)
+#else
+#define APROF(i)
 #endif
 
     for (int64_t inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
@@ -204,7 +232,8 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
             }
         }
         __syncthreads();
-        // ---- Q (lower triangle), identity padding, active rows of G, A
+        APROF(0);
+        // ---- Q (lower triangle), identity padding, A
 #pragma unroll 2
         for (int c = warp; c < n; c += NWARP) {  // a warp per column; all row chunks of the column loaded before the first store
             const double* qc = Q + (size_t)c * n;
@@ -233,21 +262,23 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
             const int r = nred + tid;
             T[tix(nt - 1, nt - 1) * 64 + el(r & 7, r & 7)] = -1.0;
         }
-#pragma unroll 4
-        for (int c = warp; c < n; c += NWARP) {
-            for (int i = lane; i < m; i += 32) {
-                const int ar = apos[i];
-                if (ar < 0) continue;
-                const int R = n8 + ar;
-                T[tix(R >> 3, c >> 3) * 64 + el(R & 7, c & 7)] = __ldg(G + (size_t)c * m + i);
-            }
-            for (int i = lane; i < p; i += 32) {
-                const int R = n8 + ma + i;
-                T[tix(R >> 3, c >> 3) * 64 + el(R & 7, c & 7)] = __ldg(A + (size_t)c * p + i);
+        for (int e0 = tid; e0 < p * n; e0 += 4 * THREADS) {  // A: p x n entries, four loads in flight per thread
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = e0 + u * THREADS < p * n ? __ldg(A + e0 + u * THREADS) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * THREADS;
+                if (e < p * n) {
+                    const int c = e / p, R = n8 + ma + (e - c * p);
+                    T[tix(R >> 3, c >> 3) * 64 + el(R & 7, c & 7)] = v[u];
+                }
             }
         }
+        APROF(1);
         // ---- D = G z - h; the (2,2) diagonal D_a / lam_a
-        rows_times(G, m, n, zs, dvec, part);
+        rows_times(G, m, n, zs, dvec, part, T, apos, n8);  // ... and the active rows of G into the tile grid
+        APROF(2);
         for (int i = tid; i < m; i += THREADS) {
             const double d = dvec[i] - a.h[b * m + i];
             dvec[i] = d;
@@ -287,6 +318,7 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
         }
         __syncthreads();
 
+        APROF(3);
         {   // the next instance's problem data travel to L2 under this instance's factorisation
             const int64_t nxt = inst + gridDim.x;
             if (nxt < a.B) {
@@ -304,11 +336,13 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
         }
         factor<0>(T, V, nt, np, ntz, tid, lane, warp, g, t, fo SQD_SUB_ARG);
         __syncthreads();
+        APROF(4);
         {
             const int lines = (int)(((size_t)m * n * sizeof(double) + 127) / 128);
             backward(T, V, nt, lane, warp, (do_rev && G) ? (const char*)G : nullptr, lines < 1024 ? lines : 1024);
         }
         __syncthreads();
+        APROF(5);
 
         // ---- outputs (dz, dlam, dnu) = -x; inactive inequalities recovered from their singleton columns
         if (scal[2] == 0) {
@@ -336,7 +370,12 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
             fb_list[atomicAdd(fb_count, 1)] = (int)inst;
         }
         __syncthreads();
+        APROF(6);
     }
+#ifdef QP_PROFILE
+    if (a.prof && blockIdx.x == 0 && tid == 0)
+        for (int i = 0; i < 7; ++i) a.prof[i] = pc[i];
+#endif
 }
 
 __global__ void max_active_any_kernel(int64_t B, int m, const double* __restrict__ lam, int* out) {
@@ -392,9 +431,27 @@ int32_t qp_sqd_any_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_ca
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > a.B) grid = a.B;
     if (grid < 1) grid = 1;
-    qp_kkt_sqd_any_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a, fb_list, fb_count, nt_cap, max_active, max_tag);
+    QpSolveArgs aa = a;
+    long long* dprof = nullptr;
+    const bool profile = getenv("DIFFOPT_B200_PROFILE") != nullptr;
+    if (profile) {
+        DO_CUDA(ctx, cudaMalloc(&dprof, 16 * sizeof(long long)));
+        DO_CUDA(ctx, cudaMemsetAsync(dprof, 0, 16 * sizeof(long long), ctx->stream));
+        aa.prof = dprof;
+    }
+    qp_kkt_sqd_any_kernel<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(aa, fb_list, fb_count, nt_cap, max_active, max_tag);
     ctx->launches++;
     DO_CUDA(ctx, cudaGetLastError());
+    if (profile) {  // per-phase clocks of CTA 0 (profile build: DIFFOPT_B200_BUILD_PROFILE=1)
+        long long h[16];
+        DO_CUDA(ctx, cudaMemcpyAsync(h, dprof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        DO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(dprof);
+        const long long ninst = (a.B + grid - 1) / grid;
+        fprintf(stderr, "[qp_sqd_any profile, CTA 0, %lld instances, %d CTA/SM, nt_cap %d, smem %zu] clocks/instance: vectors+clear %lld, "
+                        "scatter Q/G/A %lld, G z %lld, forward rhs %lld, factor %lld, backward %lld, output %lld\n",
+                ninst, per_sm, nt_cap, smem, h[0] / ninst, h[1] / ninst, h[2] / ninst, h[3] / ninst, h[4] / ninst, h[5] / ninst, h[6] / ninst);
+    }
     *handled = true;
     return qp_generic_launch_list(ctx, a, fb_list, fb_count);
 }

@@ -1,5 +1,5 @@
 """One driver for the ncu captures under profiles/ (run from the repo root on a GPU box):
-    python tools/prof_driver.py qp [B] | sparse [T] [nrhs] | lsqr_small [iters] | lsqr_big [scale] [iters] [window] | psd |
+    python tools/prof_driver.py qp [B] [n m p active] | sparse [T] [nrhs] | lsqr_small [iters] | lsqr_big [scale] [iters] [window] | psd |
                                 conic_batch [B] [iters]
 Each case runs the library call a couple of times (first call warms buffers) and prints the library's own device time."""
 import os
@@ -27,15 +27,16 @@ if case == "qp":
     import torch
     capi = diffopt_b200.submodule("_capi")
     B = arg(2, 4096)
-    d = bench_data.qp_batch_fast(B, n_active=int(os.environ.get("ACTIVE", 16)))
+    n, m, p = arg(3, 64), arg(4, 64), arg(5, 16)   # other shapes run the shape-generic LDL' kernel
+    d = bench_data.qp_batch_fast(B, n, m, p, n_active=arg(6, int(os.environ.get("ACTIVE", 16))))
     keys = ["Q", "G", "A", "h", "z", "lam", "nu", "dQ", "dq", "dG", "dh", "dA", "db", "seed"]
     mats = {"Q", "G", "A", "dQ", "dG", "dA"}
     dev = {k: torch.from_numpy(np.ascontiguousarray(d[k].transpose(0, 2, 1) if k in mats else d[k])).cuda() for k in keys}
-    fo = torch.empty((B, 144), dtype=torch.float64, device="cuda"); ro = torch.empty_like(fo)
+    fo = torch.empty((B, n + m + p), dtype=torch.float64, device="cuda"); ro = torch.empty_like(fo)
     io = torch.zeros(B, dtype=torch.int32, device="cuda")
     ms = []
     for rep in range(int(os.environ.get("REPS", 4))):
-        rc = ctx.lib.diffopt_b200_qp_batch_solve(ctx.h, B, 64, 64, 16, *[capi.vp(dev[k].data_ptr()) for k in keys],
+        rc = ctx.lib.diffopt_b200_qp_batch_solve(ctx.h, B, n, m, p, *[capi.vp(dev[k].data_ptr()) for k in keys],
                                                  capi.vp(fo.data_ptr()), capi.vp(ro.data_ptr()), capi.vp(io.data_ptr()), capi.DEVICE)
         assert rc == 0
         ms.append(ctx.last_kernel_ms)
