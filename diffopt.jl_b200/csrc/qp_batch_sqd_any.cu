@@ -319,7 +319,18 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
         __syncthreads();
 
         APROF(3);
-        {   // the next instance's problem data travel to L2 under this instance's factorisation
+        factor<0>(T, V, nt, np, ntz, tid, lane, warp, g, t, fo SQD_SUB_ARG);
+        __syncthreads();
+        APROF(4);
+        {
+            const int lines = (int)(((size_t)m * n * sizeof(double) + 127) / 128);
+            backward(T, V, nt, lane, warp, (do_rev && G) ? (const char*)G : nullptr, lines < 1024 ? lines : 1024);
+        }
+        __syncthreads();
+        APROF(5);
+
+        {   // the next instance's problem data travel to L2 while this one is written out (any earlier and the resident CTAs'
+            // prefetched lines evict each other: 444 CTAs x 360 KB exceed L2 at n = 100)
             const int64_t nxt = inst + gridDim.x;
             if (nxt < a.B) {
                 if (!(a.shared & 1)) {
@@ -334,16 +345,6 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
                 if (do_rev) prefetch_l2(a.seed + (size_t)nxt * n, sizeof(double) * n);
             }
         }
-        factor<0>(T, V, nt, np, ntz, tid, lane, warp, g, t, fo SQD_SUB_ARG);
-        __syncthreads();
-        APROF(4);
-        {
-            const int lines = (int)(((size_t)m * n * sizeof(double) + 127) / 128);
-            backward(T, V, nt, lane, warp, (do_rev && G) ? (const char*)G : nullptr, lines < 1024 ? lines : 1024);
-        }
-        __syncthreads();
-        APROF(5);
-
         // ---- outputs (dz, dlam, dnu) = -x; inactive inequalities recovered from their singleton columns
         if (scal[2] == 0) {
             double* rev = do_rev ? a.rev + b * N : nullptr;
