@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
     double* pr = ww + ldc;
     double* red = pr + ldc;            // TD_WARPS
     double* colpart = red + TD_WARPS;  // TD_WARPS x ldc
-    int* ro = reinterpret_cast<int*>(colpart + TD_WARPS * ldc);  // row offsets
+    double* colbuf = colpart + TD_WARPS * ldc;  // ldc: the next step's column as it leaves the update
+    double* red2 = colbuf + ldc;                // TD_WARPS: its sums of squares per warp
+    int* ro = reinterpret_cast<int*>(red2 + TD_WARPS);  // row offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n; i += TD_THREADS) ro[i] = roff(i);
     for (int i = warp; i < n; i += TD_WARPS) {
@@ -90,16 +92,34 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
         for (int j = lane; j <= (i | 1); j += 32) dst[j] = j <= i ? src[j] : 0.0;
     }
     __syncthreads();
+#ifdef PSD_PROFILE
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, tp = clock64();
+#define TPROF(i)                  \
+    do {                          \
+        long long _n = clock64(); \
+        pc[i] += _n - tp;         \
+        tp = _n;                  \
+    } while (0)
+#else
+#define TPROF(i)
+#endif
+    bool have_col = false;  // column k below the diagonal (colbuf) and its partial sums of squares (red2) left by the last update
     for (int k = 0; k + 2 < n; ++k) {
         const int r0 = k + 1, j0 = r0 & ~1;
-        // Householder vector of column k (every warp computes the norm redundantly: no block reduction)
-        double ss = 0.0;
-        for (int i = r0 + 1 + lane; i < n; i += 32) {
-            const double x = A[ro[i] + k];
-            ss = fma(x, x, ss);
+        // ---- Householder vector of column k.  The update of step k-1 left the column in colbuf and per-warp sums of squares
+        //      in red2 as it passed through the registers; without one (first step, skipped update) it is read from A.
+        double ss = 0.0, alpha;
+        if (have_col) {
+            for (int w = 0; w < TD_WARPS; ++w) ss += red2[w];
+            alpha = colbuf[r0];
+        } else {
+            for (int i = r0 + 1 + lane; i < n; i += 32) {
+                const double x = A[ro[i] + k];
+                ss = fma(x, x, ss);
+            }
+            ss = warp_sum(ss);
+            alpha = A[ro[r0] + k];
         }
-        ss = warp_sum(ss);
-        const double alpha = A[ro[r0] + k];
         double beta = alpha, t = 0.0, scal = 0.0;
         if (ss != 0.0) {
             const double h = fma(alpha, alpha, ss);
@@ -113,19 +133,22 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
                 scal = 1.0 / (alpha - beta);
             }
         }
-        if (warp == 0) {
-            for (int i = j0 + lane; i < n + (n & 1); i += 32) {  // v, zero outside rows r0 .. n-1 (the pair grid starts at j0)
-                const double v = (i < r0 || i >= n) ? 0.0 : (i == r0 ? 1.0 : A[ro[i] + k] * scal);
+        {   // v, zero outside rows r0 .. n-1 (the pair grid starts at j0 and ends at an even index)
+            const int i = j0 + tid;
+            if (i < n + (n & 1)) {
+                const double v = (i < r0 || i >= n) ? 0.0 : (i == r0 ? 1.0 : (have_col ? colbuf[i] : A[ro[i] + k]) * scal);
                 vv[i] = v;
                 if (i >= r0 && i < n) H[(size_t)k * n + i] = v;
             }
-            if (lane == 0) {
+            if (tid == 0) {
                 tau[k] = t;
                 eb[k] = beta;
                 da[k] = A[ro[k] + k];
             }
         }
         __syncthreads();
+        TPROF(0);
+        have_col = t != 0.0;
         if (t != 0.0) {
             const int nq = (n - j0 + 63) >> 6;  // pair columns in use
             double2 vj[NQ2];
@@ -134,58 +157,57 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
                 const int jp = j0 + 2 * lane + 64 * q;
                 vj[q] = (q < nq && jp < n) ? *reinterpret_cast<const double2*>(vv + jp) : make_double2(0.0, 0.0);
             }
-            {   // row sums and (per lane) column sums of A22 v; the diagonal lands in both and is taken out again below
+            {   // row sums and (per lane) column sums of A22 v; the diagonal lands in both and is taken out again below.
+                // Four rows at a time: their loads are issued together (a pair beyond a row's end is read and masked) and
+                // their four sums share one transposing shuffle reduction.
                 double2 cacc[NQ2];
 #pragma unroll
                 for (int q = 0; q < NQ2; ++q) cacc[q] = make_double2(0.0, 0.0);
-                for (int ib = r0 + warp; ib < n; ib += 8 * TD_WARPS) {  // eight rows at a time share one reduction
-                    double racc[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        racc[u] = 0.0;
-                        const int i = ib + u * TD_WARPS;
-                        if (i < n) {
-                            const double vi = vv[i];
-                            const double2* row = reinterpret_cast<const double2*>(A + ro[i] + j0) + lane;
-#pragma unroll
-                            for (int q = 0; q < NQ2; ++q) {
-                                const int jb = j0 + 64 * q;
-                                if (jb > i) break;
-                                const int jp = jb + 2 * lane;
-                                if (jp + 1 <= i) {
-                                    const double2 a = row[32 * q];
-                                    racc[u] = fma(a.x, vj[q].x, fma(a.y, vj[q].y, racc[u]));
-                                    cacc[q].x = fma(a.x, vi, cacc[q].x);
-                                    cacc[q].y = fma(a.y, vi, cacc[q].y);
-                                } else if (jp == i) {
-                                    const double ax = reinterpret_cast<const double*>(row + 32 * q)[0];
-                                    racc[u] = fma(ax, vj[q].x, racc[u]);
-                                    cacc[q].x = fma(ax, vi, cacc[q].x);
-                                }
-                            }
-                        }
-                    }
-                    // transposing reduction: 8 row sums over 32 lanes with 9 shuffles; lane 4 r holds the sum of row r
-                    double r4[4], r2[2];
+                for (int ib = r0 + warp; ib < n; ib += 4 * TD_WARPS) {
+                    int iu[4];
+                    const double* rowp[4];
+                    double vi[4], racc[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const bool hi = lane & 16;
-                        r4[u] = (hi ? racc[u + 4] : racc[u]) + __shfl_xor_sync(FULL, hi ? racc[u] : racc[u + 4], 16);
+                        const int i = ib + u * TD_WARPS;
+                        iu[u] = i < n ? i : -1;
+                        rowp[u] = A + (i < n ? ro[i] : 0) + 2 * lane;
+                        vi[u] = i < n ? vv[i] : 0.0;
+                        racc[u] = 0.0;
                     }
+                    const int imax = min(n - 1, ib + 3 * TD_WARPS);
+#pragma unroll
+                    for (int q = 0; q < NQ2; ++q) {
+                        const int jb = j0 + 64 * q;
+                        if (jb > imax) break;
+                        const int jp = jb + 2 * lane;
+                        double2 av[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) av[u] = *reinterpret_cast<const double2*>(rowp[u] + jb);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double ax = jp <= iu[u] ? av[u].x : 0.0, ay = jp + 1 <= iu[u] ? av[u].y : 0.0;
+                            racc[u] = fma(ax, vj[q].x, fma(ay, vj[q].y, racc[u]));
+                            cacc[q].x = fma(ax, vi[u], cacc[q].x);
+                            cacc[q].y = fma(ay, vi[u], cacc[q].y);
+                        }
+                    }
+                    double r2[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const bool hi = lane & 8;
-                        r2[u] = (hi ? r4[u + 2] : r4[u]) + __shfl_xor_sync(FULL, hi ? r4[u] : r4[u + 2], 8);
+                        const bool hi = lane & 16;
+                        r2[u] = (hi ? racc[u + 2] : racc[u]) + __shfl_xor_sync(FULL, hi ? racc[u] : racc[u + 2], 16);
                     }
                     double r1;
                     {
-                        const bool hi = lane & 4;
-                        r1 = (hi ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, hi ? r2[0] : r2[1], 4);
+                        const bool hi = lane & 8;
+                        r1 = (hi ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, hi ? r2[0] : r2[1], 8);
                     }
+                    r1 += __shfl_xor_sync(FULL, r1, 4);
                     r1 += __shfl_xor_sync(FULL, r1, 2);
                     r1 += __shfl_xor_sync(FULL, r1, 1);
-                    const int i = ib + (lane >> 2) * TD_WARPS;
-                    if ((lane & 3) == 0 && i < n) pr[i] = r1;
+                    const int i = ib + (lane >> 3) * TD_WARPS;  // lane 8 r holds the sum of row r of the group
+                    if ((lane & 7) == 0 && i < n) pr[i] = r1;
                 }
 #pragma unroll
                 for (int q = 0; q < NQ2; ++q) {
@@ -194,6 +216,7 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
                 }
             }
             __syncthreads();
+            TPROF(1);
             const int i = r0 + tid;
             double pi_ = 0.0, part = 0.0;
             if (i < n) {
@@ -206,42 +229,66 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
             part = warp_sum(part);
             if (lane == 0) red[warp] = part;
             __syncthreads();
+            TPROF(2);
             double dot = 0.0;
             for (int w = 0; w < TD_WARPS; ++w) dot += red[w];
             if (i < n) ww[i] = fma(-0.5 * t * dot, vv[i], pi_);
             if (tid < 2) ww[tid ? n : j0] = tid ? 0.0 : (j0 < r0 ? 0.0 : ww[j0]);  // zero outside the live range
             __syncthreads();
-            {   // A22 -= v w' + w v'
+            TPROF(3);
+            {   // A22 -= v w' + w v', four rows at a time; column r0 (the next step's column) goes to colbuf on its way
                 double2 wj[NQ2];
 #pragma unroll
                 for (int q = 0; q < NQ2; ++q) {
                     const int jp = j0 + 2 * lane + 64 * q;
                     wj[q] = (q < nq && jp < n) ? *reinterpret_cast<const double2*>(ww + jp) : make_double2(0.0, 0.0);
                 }
-#pragma unroll 2
-                for (int i2 = r0 + warp; i2 < n; i2 += TD_WARPS) {
-                    const double vi = vv[i2], wi = ww[i2];
-                    double2* row = reinterpret_cast<double2*>(A + ro[i2] + j0) + lane;
+                double ssp = 0.0;
+                const bool odd = r0 & 1;
+                for (int ib = r0 + warp; ib < n; ib += 4 * TD_WARPS) {
+                    int iu[4];
+                    double* rowp[4];
+                    double vi[4], wi[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i2 = ib + u * TD_WARPS;
+                        iu[u] = i2 < n ? i2 : -1;
+                        rowp[u] = A + (i2 < n ? ro[i2] : 0) + 2 * lane;
+                        vi[u] = i2 < n ? vv[i2] : 0.0;
+                        wi[u] = i2 < n ? ww[i2] : 0.0;
+                    }
+                    const int imax = min(n - 1, ib + 3 * TD_WARPS);
 #pragma unroll
                     for (int q = 0; q < NQ2; ++q) {
                         const int jb = j0 + 64 * q;
-                        if (jb > i2) break;
+                        if (jb > imax) break;
                         const int jp = jb + 2 * lane;
-                        if (jp + 1 <= i2) {
-                            double2 a = row[32 * q];
-                            a.x -= fma(vi, wj[q].x, wi * vj[q].x);
-                            a.y -= fma(vi, wj[q].y, wi * vj[q].y);
-                            row[32 * q] = a;
-                        } else if (jp == i2) {
-                            double* ax = reinterpret_cast<double*>(row + 32 * q);
-                            ax[0] -= fma(vi, wj[q].x, wi * vj[q].x);
+                        double2 av[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) av[u] = *reinterpret_cast<const double2*>(rowp[u] + jb);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double nx = av[u].x - fma(vi[u], wj[q].x, wi[u] * vj[q].x);
+                            const double ny = av[u].y - fma(vi[u], wj[q].y, wi[u] * vj[q].y);
+                            if (jp + 1 <= iu[u]) *reinterpret_cast<double2*>(rowp[u] + jb) = make_double2(nx, ny);
+                            else if (jp == iu[u]) rowp[u][jb] = nx;
+                            if (q == 0 && lane == 0 && iu[u] > r0) {
+                                const double val = odd ? ny : nx;
+                                colbuf[iu[u]] = val;
+                                if (iu[u] > r0 + 1) ssp = fma(val, val, ssp);
+                            }
                         }
                     }
                 }
+                if (lane == 0) red2[warp] = ssp;
             }
         }
         __syncthreads();
+        TPROF(4);
     }
+#ifdef PSD_PROFILE
+    if (tid == 0) printf("[psd_tridiag profile] clocks per step: vector %lld, symv %lld, p+dot %lld, w %lld, update %lld\n", pc[0] / (n - 2), pc[1] / (n - 2), pc[2] / (n - 2), pc[3] / (n - 2), pc[4] / (n - 2));
+#endif
     if (tid == 0) {
         if (n >= 2) {
             da[n - 2] = A[ro[n - 2] + n - 2];
@@ -597,7 +644,7 @@ size_t psd_tridiag_smem_bytes(int d) {
     const size_t h = (size_t)d >> 1;
     const size_t nst = (d & 1) ? 2 * (h + 1) * (h + 1) : 2 * h * (h + 1);  // roff(d)
     const size_t ldc = ((size_t)d + 3) & ~(size_t)1;
-    return sizeof(double) * (nst + 3 * ldc + TD_WARPS + (size_t)TD_WARPS * ldc) + sizeof(int) * ((size_t)d + 2);
+    return sizeof(double) * (nst + 4 * ldc + 2 * TD_WARPS + (size_t)TD_WARPS * ldc) + sizeof(int) * ((size_t)d + 2);
 }
 
 // the direct route serves sides the Jacobi kernel of one CTA cannot hold and whose packed triangle fits shared memory
