@@ -33,6 +33,31 @@ int main(void) {
         if (fabs(rev[i] - want[i]) > 1e-9) bad = 1;
     printf("c99 client: rev = %.6f %.6f %.6f %.6f %.6f (%s), %lld kernel launches\n", rev[0], rev[1], rev[2], rev[3], rev[4],
            bad ? "WRONG" : "ok", (long long)diffopt_b200_launch_count(ctx));
+    /* forward mode with the direction as sparse triplets (diffopt_b200_coo_batch is a plain C struct): dG = e_1 e_2' given
+     * once as (1, 2, 1.0) and once split into two duplicates that must add up -- both calls must agree */
+    {
+        const int64_t ptr1[2] = {0, 1}, I1[1] = {1}, J1[1] = {2};
+        const double V1[1] = {1.0};
+        const int64_t ptr2[2] = {0, 2}, I2[2] = {1, 1}, J2[2] = {2, 2};
+        const double V2[2] = {0.25, 0.75};
+        diffopt_b200_coo_batch g1, g2;
+        double f1[5], f2[5];
+        g1.ptr = ptr1; g1.I = I1; g1.J = J1; g1.V = V1;
+        g2.ptr = ptr2; g2.I = I2; g2.J = J2; g2.V = V2;
+        rc = diffopt_b200_qp_batch_solve_coo(ctx, 1, 2, 2, 1, Q, G, A, h, z, lam, nu, NULL, NULL, &g1, NULL, NULL, NULL, NULL, f1, NULL,
+                                             info, DIFFOPT_B200_HOST, 0);
+        if (rc == 0)
+            rc = diffopt_b200_qp_batch_solve_coo(ctx, 1, 2, 2, 1, Q, G, A, h, z, lam, nu, NULL, NULL, &g2, NULL, NULL, NULL, NULL, f2,
+                                                 NULL, info, DIFFOPT_B200_HOST, 0);
+        if (rc != 0) {
+            printf("qp_batch_solve_coo failed: rc = %d (%s)\n", (int)rc, diffopt_b200_last_error(ctx));
+            diffopt_b200_destroy(ctx);
+            return 2;
+        }
+        for (i = 0; i < 5; ++i)
+            if (fabs(f1[i] - f2[i]) > 1e-12) bad = 1;
+        printf("c99 client: sparse-triplet forward dz = %.6f %.6f (%s)\n", f1[0], f1[1], bad ? "WRONG" : "ok");
+    }
     diffopt_b200_destroy(ctx);
     return bad;
 }

@@ -87,3 +87,21 @@ def test_header_is_plain_c99_and_a_c_client_links(tmp_path):
     exe = _build_c99_client(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_coo_batch_packing_matches_the_references_triplets():
+    """qp.coo_batch: per-instance scipy.sparse matrices -> 0-based offsets + Julia's 1-based (I, J, V), duplicates kept as
+    separate triplets (the device adds them up like SparseArrays.sparse, QuadraticProgram.jl:396-424)."""
+    import scipy.sparse as sp
+    qp = diffopt_b200.submodule("qp")
+    m0 = sp.coo_matrix((np.array([1.5, -2.0]), (np.array([0, 2]), np.array([1, 0]))), shape=(3, 4))
+    m1 = sp.coo_matrix((np.array([0.25, 0.75]), (np.array([1, 1]), np.array([3, 3]))), shape=(3, 4))   # a duplicated entry
+    m2 = sp.csr_matrix((3, 4))
+    ptr, I, J, V = qp.coo_batch([m0, m1, m2], 3)
+    assert ptr.dtype == np.int64 and I.dtype == np.int64 and J.dtype == np.int64 and V.dtype == np.float64
+    assert ptr.tolist() == [0, 2, 4, 4]
+    assert sorted(zip(I[:2].tolist(), J[:2].tolist(), V[:2].tolist())) == [(1, 2, 1.5), (3, 1, -2.0)]
+    assert I[2:].tolist() == [2, 2] and J[2:].tolist() == [4, 4] and V[2:].tolist() == [0.25, 0.75]
+    ptr, I, J, V = qp.coo_batch(m0, 5, shared=True)
+    assert ptr.tolist() == [0, 2]
+    assert qp.coo_batch(None, 3) is None

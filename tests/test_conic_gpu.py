@@ -599,3 +599,44 @@ def test_kat13_psd_and_pos_forward(ctx):
     want, _ = oconic.forward(cache, d["dA"], d["db"], d["dc"], **dict(TIGHT, maxiter=2000))
     assert rel(got, want) <= RTOL_LSQR
     assert np.allclose(got, d["dx"], atol=0.3, rtol=0.01)
+
+
+@pytest.mark.parametrize("route", ["tridiagonal", "jacobi"])
+def test_psd_mid_size_routes_and_hard_spectra(ctx, route, monkeypatch):
+    """Sides 112-218 have two eigensolvers: tridiagonalisation + multisection + inverse iteration (default) and the block
+    Jacobi (DIFFOPT_B200_PSD=jacobi).  Both must reproduce the oracle's projection and Dpi on spectra that stress the direct
+    route: exact multiplicities (clusters orthogonalised inside inverse iteration), eigenvalues 1e-10 and 1e-6 apart (close
+    but separate shifts; the Newton-Schulz step restores orthogonality), +-pairs, a rank-one matrix, the zero matrix, an
+    already diagonal matrix and a matrix that decouples into blocks (zero off-diagonals in T)."""
+    if route == "jacobi":
+        monkeypatch.setenv("DIFFOPT_B200_PSD", "jacobi")
+    rng = np.random.default_rng(29)
+
+    def with_spectrum(lams):
+        Qm, _ = np.linalg.qr(rng.normal(size=(len(lams), len(lams))))
+        Xm = (Qm * np.asarray(lams, float)) @ Qm.T
+        return (Xm + Xm.T) / 2
+
+    d = 128
+    blocks = np.zeros((d, d))
+    blocks[:60, :60] = with_spectrum(rng.normal(size=60))
+    blocks[60:, 60:] = with_spectrum(rng.normal(size=d - 60))
+    u = rng.normal(size=d)
+    mats = [with_spectrum([2.0] * 50 + [-1.0] * 40 + list(rng.normal(size=d - 90))),
+            with_spectrum(list(1.0 + 1e-10 * np.arange(30)) + list(-0.5 + 1e-6 * np.arange(30)) + list(rng.normal(size=d - 60))),
+            with_spectrum([3, -3] * (d // 2)),
+            np.outer(u, u) / (u @ u),
+            np.zeros((d, d)),
+            np.diag(rng.normal(size=d)),
+            blocks,
+            with_spectrum(rng.normal(size=218) * 10.0 ** rng.integers(-3, 3, size=218))]
+    for X in mats:
+        model, v, dims = _psd_only_model(ctx, [X])
+        types = [ocones.PSD]
+        want_vp = ocones.pi(v, types, dims)
+        assert np.linalg.norm(model.vp() - want_vp) <= 1e-10 * max(1.0, np.linalg.norm(want_vp))
+        t = rng.normal(size=v.size)
+        for tr in (False, True):
+            want = ocones.Dpi_apply(v, types, dims, t, transpose=tr)
+            got = model.dpi_apply(t, transpose=tr)
+            assert np.linalg.norm(got - want) <= 1e-8 * max(1.0, np.linalg.norm(want))
