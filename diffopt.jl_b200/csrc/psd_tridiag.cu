@@ -65,10 +65,13 @@ __device__ __forceinline__ int roff(int i) {
 constexpr int NQ2 = (MAX_SIDE + 63) / 64;  // a lane owns the column pairs j0 + 2 lane + 64 q, q < NQ2
 
 // H (n x n, column major): column k holds the Householder vector v_k in rows k+1 .. n-1 (v_k[k+1] = 1); tau[k];
-// da[n] / eb[n-1]: diagonal and off-diagonal of T.  One step k (dsytd2): v from column k, p = tau A22 v,
-// w = p - (tau/2)(p'v) v, A22 -= v w' + w v'.  A warp takes rows, its lanes the column pairs of a row; the mirrored half
-// of the symmetric product accumulates per lane (column sums), so A22 is read once for p and once more for the update.
-// The kernel is bound by FP64 issue on its one SM: predicated-off work is skipped with uniform early exits.
+// da[n] / eb[n-1]: diagonal and off-diagonal of T.  One step k (dsytd2): v_k from column k, p = tau A22 v_k,
+// w_k = p - (tau/2)(p'v_k) v_k, A22 -= v_k w_k' + w_k v_k'.  The rank-2 update of step k-1 is DEFERRED into step k: column k is
+// brought up to date on its own (a thread per row), which gives v_k; then ONE pass over the trailing triangle applies the
+// pending update and accumulates A22 v_k on the updated entries while they are in registers -- the matrix crosses shared
+// memory once per step instead of twice.  A warp takes rows, four at a time, its lanes the column pairs of a row; the
+// mirrored half of the symmetric product accumulates per lane (column sums).  The kernel is bound by the dependent chain
+// of its 5 block barriers per step on ONE SM.
 __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, const double* __restrict__ xtri, double* __restrict__ H,
                                                                  double* __restrict__ tau, double* __restrict__ da,
                                                                  double* __restrict__ eb) {
@@ -76,16 +79,17 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
     const int nst = roff(n);
     double* A = sm;
     const int ldc = (n + 3) & ~1;      // vector length: n + one zero on either side of the live range, kept even
-    double* vv = A + nst;
-    double* ww = vv + ldc;
-    double* pr = ww + ldc;
+    double* vbuf = A + nst;            // 2 x ldc: v of the reflector being built / of the pending one
+    double* wbuf = vbuf + 2 * ldc;     // 2 x ldc: w likewise
+    double* pr = wbuf + 2 * ldc;       // ldc: row sums
     double* red = pr + ldc;            // TD_WARPS
-    double* colpart = red + TD_WARPS;  // TD_WARPS x ldc
-    double* colbuf = colpart + TD_WARPS * ldc;  // ldc: the next step's column as it leaves the update
-    double* red2 = colbuf + ldc;                // TD_WARPS: its sums of squares per warp
-    int* ro = reinterpret_cast<int*>(red2 + TD_WARPS);  // row offsets
+    double* red2 = red + TD_WARPS;     // TD_WARPS
+    double* sc = red2 + TD_WARPS;      // 2: diagonal and first sub-diagonal entry of the current column
+    double* colpart = sc + 2;          // TD_WARPS x ldc
+    int* ro = reinterpret_cast<int*>(colpart + TD_WARPS * ldc);  // row offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n; i += TD_THREADS) ro[i] = roff(i);
+    for (int i = tid; i < 2 * ldc; i += TD_THREADS) vbuf[i] = wbuf[i] = 0.0;
     for (int i = warp; i < n; i += TD_WARPS) {
         const double* src = xtri + (size_t)i * (i + 1) / 2;
         double* dst = A + roff(i);
@@ -103,23 +107,36 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
 #else
 #define TPROF(i)
 #endif
-    bool have_col = false;  // column k below the diagonal (colbuf) and its partial sums of squares (red2) left by the last update
+    int cur = 0;           // vbuf / wbuf half of the reflector being built; the other half holds the pending one
+    bool pending = false;  // reflector k-1 not yet applied to rows and columns >= k
     for (int k = 0; k + 2 < n; ++k) {
         const int r0 = k + 1, j0 = r0 & ~1;
-        // ---- Householder vector of column k.  The update of step k-1 left the column in colbuf and per-warp sums of squares
-        //      in red2 as it passed through the registers; without one (first step, skipped update) it is read from A.
-        double ss = 0.0, alpha;
-        if (have_col) {
-            for (int w = 0; w < TD_WARPS; ++w) ss += red2[w];
-            alpha = colbuf[r0];
-        } else {
-            for (int i = r0 + 1 + lane; i < n; i += 32) {
-                const double x = A[ro[i] + k];
-                ss = fma(x, x, ss);
+        double* const vn = vbuf + cur * ldc;
+        double* const wn = wbuf + cur * ldc;
+        const double* const vp = vbuf + (cur ^ 1) * ldc;
+        const double* const wp = wbuf + (cur ^ 1) * ldc;
+        // ---- column k brought up to date (pending reflector: v_{k-1}[k] = 1), its norm below the first sub-diagonal
+        const int ic = k + tid;
+        double xcol = 0.0;
+        {
+            double sq = 0.0;
+            if (ic < n) {
+                double* pa = A + ro[ic] + k;
+                xcol = *pa;
+                if (pending) {
+                    xcol -= fma(vp[ic], wp[k], wp[ic] * vp[k]);
+                    *pa = xcol;
+                }
+                if (ic >= k + 2) sq = xcol * xcol;
+                else sc[ic - k] = xcol;
             }
-            ss = warp_sum(ss);
-            alpha = A[ro[r0] + k];
+            sq = warp_sum(sq);
+            if (lane == 0) red2[warp] = sq;
         }
+        __syncthreads();
+        double ss = 0.0;
+        for (int w = 0; w < TD_WARPS; ++w) ss += red2[w];
+        const double alpha = sc[1];
         double beta = alpha, t = 0.0, scal = 0.0;
         if (ss != 0.0) {
             const double h = fma(alpha, alpha, ss);
@@ -133,161 +150,131 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
                 scal = 1.0 / (alpha - beta);
             }
         }
-        {   // v, zero outside rows r0 .. n-1 (the pair grid starts at j0 and ends at an even index)
-            const int i = j0 + tid;
-            if (i < n + (n & 1)) {
-                const double v = (i < r0 || i >= n) ? 0.0 : (i == r0 ? 1.0 : (have_col ? colbuf[i] : A[ro[i] + k]) * scal);
-                vv[i] = v;
-                if (i >= r0 && i < n) H[(size_t)k * n + i] = v;
-            }
-            if (tid == 0) {
-                tau[k] = t;
-                eb[k] = beta;
-                da[k] = A[ro[k] + k];
-            }
+        if (ic < n + (n & 1)) {  // v_k, zero outside rows r0 .. n-1 (the pair grid starts at j0 >= k and ends at an even index)
+            const double v = (ic < r0 || ic >= n) ? 0.0 : (ic == r0 ? 1.0 : xcol * scal);
+            vn[ic] = v;
+            if (ic >= r0 && ic < n) H[(size_t)k * n + ic] = v;
+        }
+        if (tid == 0) {
+            tau[k] = t;
+            eb[k] = beta;
+            da[k] = sc[0];
         }
         __syncthreads();
         TPROF(0);
-        have_col = t != 0.0;
-        if (t != 0.0) {
-            const int nq = (n - j0 + 63) >> 6;  // pair columns in use
-            double2 vj[NQ2];
+        const int nq = (n - j0 + 63) >> 6;  // pair columns in use
+        {   // ---- one pass over rows >= r0, columns r0 .. row: pending update applied, then row sums and (per lane) column sums
+            //      of A22 v_k on the updated entries; the diagonal lands in both sums and is taken out again below.  Four rows
+            //      at a time: their loads are issued together (a pair beyond a row's end is read and masked), their sums share
+            //      one transposing shuffle reduction.
+            double2 cacc[NQ2];
+#pragma unroll
+            for (int q = 0; q < NQ2; ++q) cacc[q] = make_double2(0.0, 0.0);
+            for (int ib = r0 + warp; ib < n; ib += 4 * TD_WARPS) {
+                int iu[4];
+                double* rowp[4];
+                double vin[4], vip[4], wip[4], racc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = ib + u * TD_WARPS;
+                    const bool ok = i < n;
+                    iu[u] = ok ? i : -1;
+                    rowp[u] = A + (ok ? ro[i] : 0) + 2 * lane;
+                    vin[u] = ok ? vn[i] : 0.0;
+                    vip[u] = (ok && pending) ? vp[i] : 0.0;
+                    wip[u] = (ok && pending) ? wp[i] : 0.0;
+                    racc[u] = 0.0;
+                }
+                const int imax = min(n - 1, ib + 3 * TD_WARPS);
+#pragma unroll
+                for (int q = 0; q < NQ2; ++q) {
+                    const int jb = j0 + 64 * q;
+                    if (jb > imax) break;
+                    const int jp = jb + 2 * lane;
+                    const bool in_range = jp < n;
+                    const double2 vjn = in_range ? *reinterpret_cast<const double2*>(vn + jp) : make_double2(0.0, 0.0);
+                    double2 vjp = make_double2(0.0, 0.0), wjp = make_double2(0.0, 0.0);
+                    if (pending && in_range) {
+                        vjp = *reinterpret_cast<const double2*>(vp + jp);
+                        wjp = *reinterpret_cast<const double2*>(wp + jp);
+                        if (jp < r0) vjp.x = wjp.x = 0.0;  // column k is already up to date
+                    }
+                    double2 av[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) av[u] = *reinterpret_cast<const double2*>(rowp[u] + jb);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double nx = av[u].x - fma(vip[u], wjp.x, wip[u] * vjp.x);
+                        const double ny = av[u].y - fma(vip[u], wjp.y, wip[u] * vjp.y);
+                        if (pending) {
+                            if (jp + 1 <= iu[u]) *reinterpret_cast<double2*>(rowp[u] + jb) = make_double2(nx, ny);
+                            else if (jp == iu[u]) rowp[u][jb] = nx;
+                        }
+                        const double ax = jp <= iu[u] ? nx : 0.0, ay = jp + 1 <= iu[u] ? ny : 0.0;
+                        racc[u] = fma(ax, vjn.x, fma(ay, vjn.y, racc[u]));
+                        cacc[q].x = fma(ax, vin[u], cacc[q].x);
+                        cacc[q].y = fma(ay, vin[u], cacc[q].y);
+                    }
+                }
+                double r2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const bool hi = lane & 16;
+                    r2[u] = (hi ? racc[u + 2] : racc[u]) + __shfl_xor_sync(FULL, hi ? racc[u] : racc[u + 2], 16);
+                }
+                double r1;
+                {
+                    const bool hi = lane & 8;
+                    r1 = (hi ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, hi ? r2[0] : r2[1], 8);
+                }
+                r1 += __shfl_xor_sync(FULL, r1, 4);
+                r1 += __shfl_xor_sync(FULL, r1, 2);
+                r1 += __shfl_xor_sync(FULL, r1, 1);
+                const int i = ib + (lane >> 3) * TD_WARPS;  // lane 8 r holds the sum of row r of the group
+                if ((lane & 7) == 0 && i < n) pr[i] = r1;
+            }
 #pragma unroll
             for (int q = 0; q < NQ2; ++q) {
                 const int jp = j0 + 2 * lane + 64 * q;
-                vj[q] = (q < nq && jp < n) ? *reinterpret_cast<const double2*>(vv + jp) : make_double2(0.0, 0.0);
-            }
-            {   // row sums and (per lane) column sums of A22 v; the diagonal lands in both and is taken out again below.
-                // Four rows at a time: their loads are issued together (a pair beyond a row's end is read and masked) and
-                // their four sums share one transposing shuffle reduction.
-                double2 cacc[NQ2];
-#pragma unroll
-                for (int q = 0; q < NQ2; ++q) cacc[q] = make_double2(0.0, 0.0);
-                for (int ib = r0 + warp; ib < n; ib += 4 * TD_WARPS) {
-                    int iu[4];
-                    const double* rowp[4];
-                    double vi[4], racc[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = ib + u * TD_WARPS;
-                        iu[u] = i < n ? i : -1;
-                        rowp[u] = A + (i < n ? ro[i] : 0) + 2 * lane;
-                        vi[u] = i < n ? vv[i] : 0.0;
-                        racc[u] = 0.0;
-                    }
-                    const int imax = min(n - 1, ib + 3 * TD_WARPS);
-#pragma unroll
-                    for (int q = 0; q < NQ2; ++q) {
-                        const int jb = j0 + 64 * q;
-                        if (jb > imax) break;
-                        const int jp = jb + 2 * lane;
-                        double2 av[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) av[u] = *reinterpret_cast<const double2*>(rowp[u] + jb);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const double ax = jp <= iu[u] ? av[u].x : 0.0, ay = jp + 1 <= iu[u] ? av[u].y : 0.0;
-                            racc[u] = fma(ax, vj[q].x, fma(ay, vj[q].y, racc[u]));
-                            cacc[q].x = fma(ax, vi[u], cacc[q].x);
-                            cacc[q].y = fma(ay, vi[u], cacc[q].y);
-                        }
-                    }
-                    double r2[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const bool hi = lane & 16;
-                        r2[u] = (hi ? racc[u + 2] : racc[u]) + __shfl_xor_sync(FULL, hi ? racc[u] : racc[u + 2], 16);
-                    }
-                    double r1;
-                    {
-                        const bool hi = lane & 8;
-                        r1 = (hi ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, hi ? r2[0] : r2[1], 8);
-                    }
-                    r1 += __shfl_xor_sync(FULL, r1, 4);
-                    r1 += __shfl_xor_sync(FULL, r1, 2);
-                    r1 += __shfl_xor_sync(FULL, r1, 1);
-                    const int i = ib + (lane >> 3) * TD_WARPS;  // lane 8 r holds the sum of row r of the group
-                    if ((lane & 7) == 0 && i < n) pr[i] = r1;
-                }
-#pragma unroll
-                for (int q = 0; q < NQ2; ++q) {
-                    const int jp = j0 + 2 * lane + 64 * q;
-                    if (q < nq && jp < n + (n & 1)) *reinterpret_cast<double2*>(colpart + warp * ldc + jp) = cacc[q];
-                }
-            }
-            __syncthreads();
-            TPROF(1);
-            const int i = r0 + tid;
-            double pi_ = 0.0, part = 0.0;
-            if (i < n) {
-                const double vi = vv[i];
-                double sum = fma(-A[ro[i] + i], vi, pr[i]);
-                for (int w = 0; w < TD_WARPS; ++w) sum += colpart[w * ldc + i];
-                pi_ = t * sum;
-                part = pi_ * vi;
-            }
-            part = warp_sum(part);
-            if (lane == 0) red[warp] = part;
-            __syncthreads();
-            TPROF(2);
-            double dot = 0.0;
-            for (int w = 0; w < TD_WARPS; ++w) dot += red[w];
-            if (i < n) ww[i] = fma(-0.5 * t * dot, vv[i], pi_);
-            if (tid < 2) ww[tid ? n : j0] = tid ? 0.0 : (j0 < r0 ? 0.0 : ww[j0]);  // zero outside the live range
-            __syncthreads();
-            TPROF(3);
-            {   // A22 -= v w' + w v', four rows at a time; column r0 (the next step's column) goes to colbuf on its way
-                double2 wj[NQ2];
-#pragma unroll
-                for (int q = 0; q < NQ2; ++q) {
-                    const int jp = j0 + 2 * lane + 64 * q;
-                    wj[q] = (q < nq && jp < n) ? *reinterpret_cast<const double2*>(ww + jp) : make_double2(0.0, 0.0);
-                }
-                double ssp = 0.0;
-                const bool odd = r0 & 1;
-                for (int ib = r0 + warp; ib < n; ib += 4 * TD_WARPS) {
-                    int iu[4];
-                    double* rowp[4];
-                    double vi[4], wi[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i2 = ib + u * TD_WARPS;
-                        iu[u] = i2 < n ? i2 : -1;
-                        rowp[u] = A + (i2 < n ? ro[i2] : 0) + 2 * lane;
-                        vi[u] = i2 < n ? vv[i2] : 0.0;
-                        wi[u] = i2 < n ? ww[i2] : 0.0;
-                    }
-                    const int imax = min(n - 1, ib + 3 * TD_WARPS);
-#pragma unroll
-                    for (int q = 0; q < NQ2; ++q) {
-                        const int jb = j0 + 64 * q;
-                        if (jb > imax) break;
-                        const int jp = jb + 2 * lane;
-                        double2 av[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) av[u] = *reinterpret_cast<const double2*>(rowp[u] + jb);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const double nx = av[u].x - fma(vi[u], wj[q].x, wi[u] * vj[q].x);
-                            const double ny = av[u].y - fma(vi[u], wj[q].y, wi[u] * vj[q].y);
-                            if (jp + 1 <= iu[u]) *reinterpret_cast<double2*>(rowp[u] + jb) = make_double2(nx, ny);
-                            else if (jp == iu[u]) rowp[u][jb] = nx;
-                            if (q == 0 && lane == 0 && iu[u] > r0) {
-                                const double val = odd ? ny : nx;
-                                colbuf[iu[u]] = val;
-                                if (iu[u] > r0 + 1) ssp = fma(val, val, ssp);
-                            }
-                        }
-                    }
-                }
-                if (lane == 0) red2[warp] = ssp;
+                if (q < nq && jp < n + (n & 1)) *reinterpret_cast<double2*>(colpart + warp * ldc + jp) = cacc[q];
             }
         }
         __syncthreads();
-        TPROF(4);
+        TPROF(1);
+        const int i = r0 + tid;
+        double pi_ = 0.0, part = 0.0;
+        if (i < n) {
+            const double vi = vn[i];
+            double sum = fma(-A[ro[i] + i], vi, pr[i]);
+            for (int w = 0; w < TD_WARPS; ++w) sum += colpart[w * ldc + i];
+            pi_ = t * sum;
+            part = pi_ * vi;
+        }
+        part = warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        TPROF(2);
+        double dot = 0.0;
+        for (int w = 0; w < TD_WARPS; ++w) dot += red[w];
+        if (i < n) wn[i] = fma(-0.5 * t * dot, vn[i], pi_);
+        if (tid < 2) {  // zero outside the live range
+            if (tid) wn[n] = 0.0;
+            else if (j0 < r0) wn[j0] = 0.0;
+        }
+        __syncthreads();
+        TPROF(3);
+        pending = true;  // (t == 0 leaves w_k = 0: a pending update that changes nothing)
+        cur ^= 1;
     }
+    if (tid < 3 && n >= 3) {  // the last reflector (k = n-3) still has to reach the trailing 2 x 2 block
+        const double* const vp = vbuf + (cur ^ 1) * ldc;
+        const double* const wp = wbuf + (cur ^ 1) * ldc;
+        const int i = tid == 0 ? n - 2 : n - 1, j = tid == 2 ? n - 1 : n - 2;
+        if (pending) A[ro[i] + j] -= fma(vp[i], wp[j], wp[i] * vp[j]);
+    }
+    __syncthreads();
 #ifdef PSD_PROFILE
-    if (tid == 0) printf("[psd_tridiag profile] clocks per step: vector %lld, symv %lld, p+dot %lld, w %lld, update %lld\n", pc[0] / (n - 2), pc[1] / (n - 2), pc[2] / (n - 2), pc[3] / (n - 2), pc[4] / (n - 2));
+    if (tid == 0) printf("[psd_tridiag profile] clocks per step: column + vector %lld, fused pass %lld, p+dot %lld, w %lld\n", pc[0] / (n - 2), pc[1] / (n - 2), pc[2] / (n - 2), pc[3] / (n - 2));
 #endif
     if (tid == 0) {
         if (n >= 2) {
@@ -644,7 +631,7 @@ size_t psd_tridiag_smem_bytes(int d) {
     const size_t h = (size_t)d >> 1;
     const size_t nst = (d & 1) ? 2 * (h + 1) * (h + 1) : 2 * h * (h + 1);  // roff(d)
     const size_t ldc = ((size_t)d + 3) & ~(size_t)1;
-    return sizeof(double) * (nst + 4 * ldc + 2 * TD_WARPS + (size_t)TD_WARPS * ldc) + sizeof(int) * ((size_t)d + 2);
+    return sizeof(double) * (nst + 5 * ldc + 2 * TD_WARPS + 2 + (size_t)TD_WARPS * ldc) + sizeof(int) * ((size_t)d + 2);
 }
 
 // the direct route serves sides the Jacobi kernel of one CTA cannot hold and whose packed triangle fits shared memory
