@@ -287,29 +287,30 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
 
 // ---- 2. eigenvalues of T ---------------------------------------------------------------------------------------------
 // Number of eigenvalues of the scaled T (|a| + |b| row sums <= 1) below x: sign changes of the Sturm sequence
-// p_k = (a_k - x) p_{k-1} - b_{k-1}^2 p_{k-2} (growth <= 3 per step), rescaled by a power of two every second step when
-// both neighbours have left [1e-100, 1e100].
+// p_k = (a_k - x) p_{k-1} - b_{k-1}^2 p_{k-2} (growth <= 3 per step).  b^2 is floored at 1e-100 by the caller (a relative
+// perturbation of 1e-50 of T: the sequence then never stays at an exact zero, which it would where T decouples and x hits
+// a diagonal entry), and the pair is rescaled by a power of two every second step when it has left [1e-100, 1e100]: two
+// steps shrink it by at most 1e-200, so it never underflows.  A zero p_k counts as positive; its successor -b^2 p_{k-1} has
+// the opposite sign of p_{k-1}, which gives the right number of sign changes.
 __device__ __forceinline__ int sturm_count(const int n, const double* a, const double* b2, const double x) {
     double p2 = 1.0, p1 = a[0] - x;
-    if (p1 == 0.0) p1 = -1e-300;
-    int cnt = p1 < 0.0;
+    int cnt = __double2hiint(p1) >> 31 & 1;
     const double up = 0x1p+332, down = 0x1p-332;
     int k = 1;
+#pragma unroll 4
     for (; k + 1 < n; k += 2) {
-        double pa = fma(a[k] - x, p1, -(b2[k - 1] * p2));
-        if (pa == 0.0) pa = p1 < 0.0 ? 1e-300 : -1e-300;
-        double pb = fma(a[k + 1] - x, pa, -(b2[k] * p1));
-        if (pb == 0.0) pb = pa < 0.0 ? 1e-300 : -1e-300;
-        cnt += ((pa < 0.0) != (p1 < 0.0)) + ((pb < 0.0) != (pa < 0.0));
+        const double pa = fma(a[k] - x, p1, -(b2[k - 1] * p2));
+        const double pb = fma(a[k + 1] - x, pa, -(b2[k] * p1));
+        const int h1 = __double2hiint(p1), ha = __double2hiint(pa), hb = __double2hiint(pb);
+        cnt += (((h1 ^ ha) >> 31) & 1) + (((ha ^ hb) >> 31) & 1);
         const double m = fmax(fabs(pa), fabs(pb));
         const double f = m < 1e-100 ? up : (m > 1e100 ? down : 1.0);
         p2 = pa * f;
         p1 = pb * f;
     }
     if (k < n) {
-        double pa = fma(a[k] - x, p1, -(b2[k - 1] * p2));
-        if (pa == 0.0) pa = p1 < 0.0 ? 1e-300 : -1e-300;
-        cnt += (pa < 0.0) != (p1 < 0.0);
+        const double pa = fma(a[k] - x, p1, -(b2[k - 1] * p2));
+        cnt += ((__double2hiint(p1) ^ __double2hiint(pa)) >> 31) & 1;
     }
     return cnt;
 }
@@ -346,12 +347,13 @@ __global__ void __launch_bounds__(BS_WARPS * 32) psd_bisect_kernel(const int n, 
     for (int q = tid; q < n; q += blockDim.x) {
         a[q] = da[q] * rs;
         const double e = q + 1 < n ? eb[q] * rs : 0.0;
-        b2[q] = e * e;
+        b2[q] = fmax(e * e, 1e-100);
     }
     __syncthreads();
     if (i >= n) return;
     double lo = -1.0 - 1e-3, hi = 1.0 + 1e-3;
     for (int it = 0; it < 11; ++it) {
+        if (hi - lo <= 4.0 * EPS) break;  // (uniform across the warp) the interval is down to rounding level
         const double x = lo + (lane + 1) * ((hi - lo) * (1.0 / 33.0));
         const int c = sturm_count(n, a, b2, x);
         const unsigned above = __ballot_sync(FULL, c > i);  // lanes whose point has more than i eigenvalues below it
@@ -421,6 +423,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) psd_invit_kernel(const int n, c
             // P L U = T - xj I with partial pivoting (dlagtf); pivots below tol are pushed to +-tol (dlagts, job -1) and kept
             // as reciprocals.  The running row (ak, bk) stays in registers: one reciprocal per step on the chain.
             double ak = ta[0] - xj, bk = te[0];
+#pragma unroll 2
             for (int k = 0; k + 1 < n; ++k) {
                 const double ck = te[k], an = ta[k + 1] - xj, bn = te[k + 1];
                 if (fabs(ck) <= fabs(ak) || fabs(ck) < 1e-200) {
@@ -459,6 +462,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) psd_invit_kernel(const int n, c
             __syncwarp();
             if (lane == 0) {
                 double prev = x[0];  // the entry the next step still changes, carried in a register
+#pragma unroll 4
                 for (int k = 1; k < n; ++k) {
                     const double xk = x[k], m = fc[k - 1];
                     if (!in[k - 1]) {
@@ -471,6 +475,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) psd_invit_kernel(const int n, c
                 }
                 x[n - 1] = prev;
                 double y1 = 0.0, y2 = 0.0;  // x[k+1], x[k+2]
+#pragma unroll 4
                 for (int k = n - 1; k >= 0; --k) {
                     const double xk = fma(-fd[k], y2, fma(-fb[k], y1, x[k])) * fr[k];
                     x[k] = xk;
@@ -568,58 +573,73 @@ __global__ void __launch_bounds__(256) psd_backtransform_kernel(const int n, con
 }
 
 // ---- 5. Newton-Schulz polish, projection ---------------------------------------------------------------------------------
-// C (n x n, column major) = alpha D + beta op(A) diag(w) op(B), 32 x 32 tile per CTA, 256 threads x (2 x 2), operands staged
-// in shared memory 32 deep.  TA: op(A) = A'; TB: op(B) = B'; w (optional): max(w_k, 0) scales the inner index;
+// C (n x n, column major) = alpha D + beta op(A) diag(w) op(B) on the FP64 tensor pipe: 32 x 32 tile per CTA, 8 warps x two
+// 8 x 8 blocks (mma.sync m8n8k4), operands staged in shared memory 32 deep (row stride 40: fragment loads take the minimum
+// of two wavefronts).  TA: op(A) = A'; TB: op(B) = B'; w (optional): max(w_k, 0) scales the inner index;
 // TRI: only the tiles on and above the diagonal are computed and C is the packed triangle (i <= j at j (j + 1) / 2 + i).
 template <bool TA, bool TB, bool TRI>
 __global__ void __launch_bounds__(256) psd_gemm_kernel(const int n, const double* __restrict__ A, const double* __restrict__ B,
                                                        const double* __restrict__ w, const double* __restrict__ D, const double alpha,
                                                        const double beta, double* __restrict__ C) {
-    __shared__ double As[32][33], Bs[32][33];  // As[k][i], Bs[k][j]
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    __shared__ double As[32][40], Bs[32][40];  // As[k][i], Bs[k][j]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     if (TRI && i0 > j0) return;
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const int bi = warp >> 1, bj = (warp & 1) * 2;  // this warp: blocks (bi, bj) and (bi, bj + 1) of the 4 x 4 block grid
+    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
     for (int k0 = 0; k0 < n; k0 += 32) {
-        for (int e = tid; e < 1024; e += 256) {
-            const int r = e & 31, c = e >> 5;
+        double va[4], vb[4];  // all eight loads of this thread in flight before the first store
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + 256 * u, r = e & 31, c = e >> 5;
             if (TA) {  // op(A)(i, k) = A[k + i n]: r runs over k (contiguous)
                 const int kk = k0 + r, ii = i0 + c;
-                As[r][c] = (kk < n && ii < n) ? A[(size_t)ii * n + kk] * (w ? fmax(w[kk], 0.0) : 1.0) : 0.0;
+                va[u] = (kk < n && ii < n) ? A[(size_t)ii * n + kk] * (w ? fmax(w[kk], 0.0) : 1.0) : 0.0;
             } else {   // A(i, k) = A[i + k n]: r runs over i (contiguous)
                 const int ii = i0 + r, kk = k0 + c;
-                As[c][r] = (kk < n && ii < n) ? A[(size_t)kk * n + ii] * (w ? fmax(w[kk], 0.0) : 1.0) : 0.0;
+                va[u] = (kk < n && ii < n) ? A[(size_t)kk * n + ii] * (w ? fmax(w[kk], 0.0) : 1.0) : 0.0;
             }
             if (TB) {  // op(B)(k, j) = B[j + k n]: r runs over j (contiguous)
                 const int jj = j0 + r, kb = k0 + c;
-                Bs[c][r] = (kb < n && jj < n) ? B[(size_t)kb * n + jj] : 0.0;
+                vb[u] = (kb < n && jj < n) ? B[(size_t)kb * n + jj] : 0.0;
             } else {   // B(k, j) = B[k + j n]: r runs over k
                 const int kb = k0 + r, jj = j0 + c;
-                Bs[r][c] = (kb < n && jj < n) ? B[(size_t)jj * n + kb] : 0.0;
+                vb[u] = (kb < n && jj < n) ? B[(size_t)jj * n + kb] : 0.0;
             }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + 256 * u, r = e & 31, c = e >> 5;
+            if (TA) As[r][c] = va[u];
+            else As[c][r] = va[u];
+            if (TB) Bs[c][r] = vb[u];
+            else Bs[r][c] = vb[u];
+        }
         __syncthreads();
-#pragma unroll 8
-        for (int kk = 0; kk < 32; ++kk) {
-            const double a0 = As[kk][tx], a1 = As[kk][tx + 16], b0 = Bs[kk][ty], b1 = Bs[kk][ty + 16];
-            acc[0][0] = fma(a0, b0, acc[0][0]);
-            acc[0][1] = fma(a0, b1, acc[0][1]);
-            acc[1][0] = fma(a1, b0, acc[1][0]);
-            acc[1][1] = fma(a1, b1, acc[1][1]);
+#pragma unroll
+        for (int kk = 0; kk < 32; kk += 4) {
+            const double a = As[kk + t][8 * bi + g];       // A fragment: row g, k-slot t
+            const double b0 = Bs[kk + t][8 * bj + g];      // B fragments: k-slot t, column g
+            const double b1 = Bs[kk + t][8 * bj + 8 + g];
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[0]), "+d"(c0[1]) : "d"(a), "d"(b0));
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c1[0]), "+d"(c1[1]) : "d"(a), "d"(b1));
         }
         __syncthreads();
     }
+    // accumulator fragment: row g, columns 2t and 2t + 1 of the 8 x 8 block
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-            const int i = i0 + tx + 16 * u, j = j0 + ty + 16 * v;
+            const int i = i0 + 8 * bi + g, j = j0 + 8 * (bj + blk) + 2 * t + v;
+            const double acc = blk ? c1[v] : c0[v];
             if (i < n && j < n) {
                 if (TRI) {
-                    if (i <= j) C[(size_t)j * (j + 1) / 2 + i] = beta * acc[u][v];
+                    if (i <= j) C[(size_t)j * (j + 1) / 2 + i] = beta * acc;
                 } else {
                     const size_t o = (size_t)j * n + i;
-                    C[o] = (D ? alpha * D[o] : 0.0) + beta * acc[u][v];
+                    C[o] = (D ? alpha * D[o] : 0.0) + beta * acc;
                 }
             }
         }
