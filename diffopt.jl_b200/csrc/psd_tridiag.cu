@@ -287,30 +287,35 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
 
 // ---- 2. eigenvalues of T ---------------------------------------------------------------------------------------------
 // Number of eigenvalues of the scaled T (|a| + |b| row sums <= 1) below x: sign changes of the Sturm sequence
-// p_k = (a_k - x) p_{k-1} - b_{k-1}^2 p_{k-2} (growth <= 3 per step).  b^2 is floored at 1e-100 by the caller (a relative
-// perturbation of 1e-50 of T: the sequence then never stays at an exact zero, which it would where T decouples and x hits
-// a diagonal entry), and the pair is rescaled by a power of two every second step when it has left [1e-100, 1e100]: two
-// steps shrink it by at most 1e-200, so it never underflows.  A zero p_k counts as positive; its successor -b^2 p_{k-1} has
-// the opposite sign of p_{k-1}, which gives the right number of sign changes.
+// p_k = (a_k - x) p_{k-1} - b_{k-1}^2 p_{k-2} (growth <= 3 per step).  b^2 is floored at 1e-60 by the caller (a relative
+// perturbation of 1e-30 of T: the sequence then never stays at an exact zero, which it would where T decouples and x hits
+// a diagonal entry), and the pair is rescaled by a power of two every FOURTH step when it has left [1e-60, 1e100]: four
+// steps shrink it by at most 1e-240, so it never underflows, and the rescaling leaves the dependent chain of one FMA per
+// step almost alone.  A zero p_k counts as positive; its successor -b^2 p_{k-1} has the opposite sign of p_{k-1}, which
+// gives the right number of sign changes.  Signs are counted on the integer pipe.
 __device__ __forceinline__ int sturm_count(const int n, const double* a, const double* b2, const double x) {
     double p2 = 1.0, p1 = a[0] - x;
-    int cnt = __double2hiint(p1) >> 31 & 1;
+    int cnt = (__double2hiint(p1) >> 31) & 1;
     const double up = 0x1p+332, down = 0x1p-332;
     int k = 1;
-#pragma unroll 4
-    for (; k + 1 < n; k += 2) {
+#pragma unroll 2
+    for (; k + 3 < n; k += 4) {
         const double pa = fma(a[k] - x, p1, -(b2[k - 1] * p2));
         const double pb = fma(a[k + 1] - x, pa, -(b2[k] * p1));
-        const int h1 = __double2hiint(p1), ha = __double2hiint(pa), hb = __double2hiint(pb);
-        cnt += (((h1 ^ ha) >> 31) & 1) + (((ha ^ hb) >> 31) & 1);
-        const double m = fmax(fabs(pa), fabs(pb));
-        const double f = m < 1e-100 ? up : (m > 1e100 ? down : 1.0);
-        p2 = pa * f;
-        p1 = pb * f;
+        const double pc = fma(a[k + 2] - x, pb, -(b2[k + 1] * pa));
+        const double pd = fma(a[k + 3] - x, pc, -(b2[k + 2] * pb));
+        const int h1 = __double2hiint(p1), ha = __double2hiint(pa), hb = __double2hiint(pb), hc = __double2hiint(pc), hd = __double2hiint(pd);
+        cnt += (((h1 ^ ha) >> 31) & 1) + (((ha ^ hb) >> 31) & 1) + (((hb ^ hc) >> 31) & 1) + (((hc ^ hd) >> 31) & 1);
+        const double m = fmax(fabs(pc), fabs(pd));
+        const double f = m < 1e-60 ? up : (m > 1e100 ? down : 1.0);
+        p2 = pc * f;
+        p1 = pd * f;
     }
-    if (k < n) {
+    for (; k < n; ++k) {
         const double pa = fma(a[k] - x, p1, -(b2[k - 1] * p2));
         cnt += ((__double2hiint(p1) ^ __double2hiint(pa)) >> 31) & 1;
+        p2 = p1;
+        p1 = pa;
     }
     return cnt;
 }
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(BS_WARPS * 32) psd_bisect_kernel(const int n, 
     for (int q = tid; q < n; q += blockDim.x) {
         a[q] = da[q] * rs;
         const double e = q + 1 < n ? eb[q] * rs : 0.0;
-        b2[q] = fmax(e * e, 1e-100);
+        b2[q] = fmax(e * e, 1e-60);
     }
     __syncthreads();
     if (i >= n) return;
@@ -523,21 +528,19 @@ __global__ void __launch_bounds__(256) psd_backtransform_kernel(const int n, con
         const int i = lane + 32 * q;
         x[q] = (j < n && i < n) ? Z[(size_t)j * n + i] : 0.0;
     }
-    constexpr int PER = (BT_PANEL * MAX_SIDE + 255) / 256;  // panel entries per thread
-    double stage[PER];
+    double stage[BT_PANEL];  // thread i < n carries entry i of every reflector of the panel (coalesced, no index arithmetic)
     // panel p holds reflectors k = khi - BT_PANEL + 1 .. khi (those < 0 do not exist), applied from khi downwards
     auto fetch = [&](int khi) {
 #pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const int e = tid + 256 * u, r = e / n, i = e - r * n, k = khi - r;
-            stage[u] = (r < BT_PANEL && k >= 0 && i > k) ? H[(size_t)k * n + i] : 0.0;
+        for (int r = 0; r < BT_PANEL; ++r) {
+            const int k = khi - r;
+            stage[r] = (tid < n && k >= 0 && tid > k) ? H[(size_t)k * n + tid] : 0.0;
         }
     };
     auto commit = [&]() {
+        if (tid < n) {
 #pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const int e = tid + 256 * u;
-            if (e < BT_PANEL * n) pan[e] = stage[u];
+            for (int r = 0; r < BT_PANEL; ++r) pan[r * n + tid] = stage[r];
         }
     };
     int khi = n - 3;
@@ -551,14 +554,15 @@ __global__ void __launch_bounds__(256) psd_backtransform_kernel(const int n, con
             const double t = st[khi - r];
             if (t == 0.0) continue;
             const double* v = pan + r * n;
-            double vq[NQ], dot = 0.0;
+            double vq[NQ], dot = 0.0, dot2 = 0.0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 const int i = lane + 32 * q;
                 vq[q] = i < n ? v[i] : 0.0;
-                dot = fma(vq[q], x[q], dot);
+                if (q & 1) dot2 = fma(vq[q], x[q], dot2);
+                else dot = fma(vq[q], x[q], dot);
             }
-            dot = warp_sum(dot) * t;
+            dot = warp_sum(dot + dot2) * t;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) x[q] = fma(-dot, vq[q], x[q]);
         }
