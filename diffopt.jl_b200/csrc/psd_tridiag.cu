@@ -135,7 +135,12 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
         }
         __syncthreads();
         double ss = 0.0;
-        for (int w = 0; w < TD_WARPS; ++w) ss += red2[w];
+        {
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};  // four short chains instead of one of TD_WARPS additions
+#pragma unroll
+            for (int w = 0; w < TD_WARPS; ++w) s4[w & 3] += red2[w];
+            ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
         const double alpha = sc[1];
         double beta = alpha, t = 0.0, scal = 0.0;
         if (ss != 0.0) {
@@ -204,8 +209,8 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
                     for (int u = 0; u < 4; ++u) av[u] = *reinterpret_cast<const double2*>(rowp[u] + jb);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const double nx = av[u].x - fma(vip[u], wjp.x, wip[u] * vjp.x);
-                        const double ny = av[u].y - fma(vip[u], wjp.y, wip[u] * vjp.y);
+                        const double nx = fma(-vip[u], wjp.x, fma(-wip[u], vjp.x, av[u].x));
+                        const double ny = fma(-vip[u], wjp.y, fma(-wip[u], vjp.y, av[u].y));
                         if (pending) {
                             if (jp + 1 <= iu[u]) *reinterpret_cast<double2*>(rowp[u] + jb) = make_double2(nx, ny);
                             else if (jp == iu[u]) rowp[u][jb] = nx;
@@ -245,9 +250,10 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
         double pi_ = 0.0, part = 0.0;
         if (i < n) {
             const double vi = vn[i];
-            double sum = fma(-A[ro[i] + i], vi, pr[i]);
-            for (int w = 0; w < TD_WARPS; ++w) sum += colpart[w * ldc + i];
-            pi_ = t * sum;
+            double s4[4] = {fma(-A[ro[i] + i], vi, pr[i]), 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int w = 0; w < TD_WARPS; ++w) s4[w & 3] += colpart[w * ldc + i];
+            pi_ = t * ((s4[0] + s4[1]) + (s4[2] + s4[3]));
             part = pi_ * vi;
         }
         part = warp_sum(part);
@@ -255,7 +261,12 @@ __global__ void __launch_bounds__(TD_THREADS) psd_tridiag_kernel(const int n, co
         __syncthreads();
         TPROF(2);
         double dot = 0.0;
-        for (int w = 0; w < TD_WARPS; ++w) dot += red[w];
+        {
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int w = 0; w < TD_WARPS; ++w) s4[w & 3] += red[w];
+            dot = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
         if (i < n) wn[i] = fma(-0.5 * t * dot, vn[i], pi_);
         if (tid < 2) {  // zero outside the live range
             if (tid) wn[n] = 0.0;
