@@ -77,6 +77,7 @@ int32_t diffopt_b200_destroy(diffopt_b200_ctx* ctx) {
     ctx->qp_unpacked[0].release();
     ctx->qp_unpacked[1].release();
     for (DevBuf& b : ctx->qp_coo) b.release();
+    ctx->qp_scratch.release();
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);

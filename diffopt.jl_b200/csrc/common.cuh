@@ -143,6 +143,7 @@ struct diffopt_b200_ctx {
     void* nccl_comm = nullptr;    // ncclComm_t of diffopt_b200_nccl_init (one rank per ctx)
     int nccl_ranks = 0, nccl_rank = 0;
     DevBuf qp_unpacked[2];        // Q / dQ expanded from packed lower triangles (qp_batch_solve_ex)
+    DevBuf qp_scratch;            // KKT matrices of the generic pivoted-LU kernel when they exceed shared memory
     DevBuf qp_coo[4];             // staged triplets of dQ, dG, dA and the assembled right-hand side (qp_batch_solve_coo)
     ConicBatchImpl* conic_batch = nullptr;
     int csr_cluster_ctas = 0;     // CTAs the cluster-kernel row blocks of csr_from_csc_host are cut for (0: default 16)

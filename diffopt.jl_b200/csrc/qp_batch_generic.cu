@@ -1,5 +1,7 @@
-// Generic batched KKT sensitivity kernel: any (n, m, p) whose augmented KKT matrix fits in
-// one CTA's shared memory (N = n+m+p <= 165).  One CTA per QP instance:
+// Generic batched KKT sensitivity kernel: any (n, m, p).  One CTA per QP instance; the augmented KKT matrix lives in the
+// CTA's shared memory when it fits (N = n+m+p <= 165) and in a per-CTA slice of a global scratch buffer otherwise (BIG:
+// the same algorithm with strided loops -- correct for any N, slow, the safety net behind the LDL' fast path for larger
+// problems):
 //
 //   assemble  LHS = [Q G'diag(lam) A'; G diag(Gz-h) 0; A 0 0]   (QuadraticProgram.jl:256-282)
 //   augment   column N = reverse RHS [dl_dz;0;0]                 (:324-329)
@@ -63,13 +65,15 @@ __device__ void accum_matvecs(const double* __restrict__ X, int R, int n, const 
 }
 
 // list / count: optional device-side list of the instances to solve (the rejects of the LDL' fast path)
-__global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveArgs a, const int* __restrict__ list, const int* __restrict__ count) {
+template <bool BIG>
+__global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveArgs a, const int* __restrict__ list, const int* __restrict__ count,
+                                                                         double* __restrict__ gscratch) {
     extern __shared__ double smem[];
     const int n = a.n, m = a.m, p = a.p;
     const int N = n + m + p;
     const int ld = (N + 1) | 1;  // odd leading dimension: conflict-free row AND column access
-    double* K = smem;                       // (N+1) x (N+1) augmented, column-major, ld
-    double* zs = K + (size_t)ld * (N + 1);  // n
+    double* K = BIG ? gscratch + (size_t)blockIdx.x * ld * (N + 1) : smem;  // (N+1) x (N+1) augmented, column-major, ld
+    double* zs = BIG ? smem : K + (size_t)ld * (N + 1);                       // n
     double* lams = zs + n;                  // m
     double* nus = lams + m;                 // p
     double* rf = nus + p;                   // N   forward RHS accumulator
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
             rf[i] = 0.0;
             perm[i] = i;
         }
-        for (int i = tid; i < ld * (N + 1); i += GEN_THREADS) K[i] = 0.0;
+        for (int i = tid; i < ld * (N + 1); i += GEN_THREADS) K[i] = 0.0;  // (ld (N+1) < 2^31 for any N the scratch can hold)
         if (tid == 0) ipiv[1] = 0;
         __syncthreads();
 
@@ -200,7 +204,20 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
             const int pr = ipiv[0];
             const double rinv = scal[0];
             // swap rows k <-> pr in every column but k; scale column k (rows k+1..N)
-            if (tid <= N) {
+            if (BIG) {
+                if (pr != k)
+                    for (int j = tid; j <= N; j += GEN_THREADS)
+                        if (j != k) {
+                            double t = K[k + (size_t)j * ld];
+                            K[k + (size_t)j * ld] = K[pr + (size_t)j * ld];
+                            K[pr + (size_t)j * ld] = t;
+                        }
+                for (int i = k + 1 + tid; i <= N; i += GEN_THREADS) {
+                    double src = (i == pr) ? scal[1] : K[i + (size_t)k * ld];
+                    K[i + (size_t)k * ld] = src * rinv;
+                }
+                if (tid == 0) K[k + (size_t)k * ld] = scal[2];
+            } else if (tid <= N) {
                 int j = tid;
                 if (j != k && pr != k) {
                     double t = K[k + j * ld];
@@ -216,7 +233,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
             }
             __syncthreads();
             // trailing update including the augmented row/column
-            {
+            if (BIG) {
+                for (int j = k + 1 + warp; j <= N; j += GEN_THREADS / 32) {
+                    const double u = K[k + (size_t)j * ld];
+                    for (int i = k + 1 + lane; i <= N; i += 32) K[i + (size_t)j * ld] -= K[i + (size_t)k * ld] * u;
+                }
+            } else {
                 double l[6];
                 const int i0 = k + 1 + lane;
 #pragma unroll
@@ -238,7 +260,17 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) qp_kkt_generic_kernel(QpSolveA
 
         // ---- backward sweeps:  U x_b = y (column N)   and   L' v = w (row N)
         for (int k = N - 1; k >= 0; --k) {
-            if (tid < 256) {
+            if (BIG) {
+                if (do_rev) {
+                    const double xb = K[k + (size_t)N * ld] / K[k + (size_t)k * ld];
+                    for (int i = tid; i < k; i += GEN_THREADS) K[i + (size_t)N * ld] -= K[i + (size_t)k * ld] * xb;
+                    if (tid == 0) rf[k] = xb;
+                }
+                if (do_fwd) {
+                    const double vk = K[N + (size_t)k * ld];
+                    for (int j = tid; j < k; j += GEN_THREADS) K[N + (size_t)j * ld] -= K[k + (size_t)j * ld] * vk;
+                }
+            } else if (tid < 256) {
                 if (do_rev) {
                     double xb = K[k + N * ld] / K[k + k * ld];
                     if (tid < k) K[tid + N * ld] -= K[tid + k * ld] * xb;
@@ -319,17 +351,31 @@ size_t qp_generic_smem_bytes(int n, int m, int p) {
 
 static int32_t generic_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, const int* list, const int* count) {
     size_t smem = qp_generic_smem_bytes(a.n, a.m, a.p);
-    if (smem > ctx->smem_optin) {
-        char buf[160];
-        snprintf(buf, sizeof buf, "qp_batch: N = n+m+p = %d needs %zu B shared memory > %zu available",
-                 a.n + a.m + a.p, smem, ctx->smem_optin);
-        ctx->err = buf;
-        return -3;
-    }
-    DO_CUDA(ctx, cudaFuncSetAttribute(qp_kkt_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int N = a.n + a.m + a.p;
+    const bool big = smem > ctx->smem_optin;
     int64_t grid = a.B < (int64_t)ctx->sm_count * 4 ? a.B : (int64_t)ctx->sm_count * 4;
     if (grid < 1) grid = 1;
-    qp_kkt_generic_kernel<<<(unsigned)grid, GEN_THREADS, smem, ctx->stream>>>(a, list, count);
+    double* scratch = nullptr;
+    if (big) {  // the matrix of every resident CTA in a global scratch buffer (<= 1 GiB), the vectors stay in shared memory
+        const size_t ld = (size_t)((N + 1) | 1), per = ld * (size_t)(N + 1) * sizeof(double);
+        smem = ((size_t)a.n + a.m + a.p + N + 4) * sizeof(double) + (size_t)(N + 1 + 4) * sizeof(int);
+        if (smem > ctx->smem_optin || per > ((size_t)1 << 30) || ld * (size_t)(N + 1) >= ((size_t)1 << 31)) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "qp_batch: N = n+m+p = %d is beyond the batched kernels (use diffopt_b200_sparse_setup / kkt_solve_csc)", N);
+            ctx->err = buf;
+            return -3;
+        }
+        const int64_t fit = (int64_t)(((size_t)1 << 30) / per);
+        if (grid > fit) grid = fit < 1 ? 1 : fit;
+        if (grid > (int64_t)ctx->sm_count * 2) grid = (int64_t)ctx->sm_count * 2;
+        DO_CUDA(ctx, ctx->qp_scratch.reserve(per * (size_t)grid));
+        scratch = ctx->qp_scratch.as<double>();
+        DO_CUDA(ctx, cudaFuncSetAttribute(qp_kkt_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        qp_kkt_generic_kernel<true><<<(unsigned)grid, GEN_THREADS, smem, ctx->stream>>>(a, list, count, scratch);
+    } else {
+        DO_CUDA(ctx, cudaFuncSetAttribute(qp_kkt_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        qp_kkt_generic_kernel<false><<<(unsigned)grid, GEN_THREADS, smem, ctx->stream>>>(a, list, count, nullptr);
+    }
     ctx->launches++;
     DO_CUDA(ctx, cudaGetLastError());
     return 0;

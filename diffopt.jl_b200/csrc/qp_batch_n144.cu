@@ -25,6 +25,8 @@
 // The KKT matrix and its factors never touch HBM: algorithmic traffic is inputs + outputs only.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -782,6 +784,7 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
 int32_t qp_sqd_any_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, bool* handled, int* max_active, int max_tag);
 bool qp_sqd_any_supported(diffopt_b200_ctx* ctx, const QpSolveArgs& a);
 int qp_sqd_any_nt(const QpSolveArgs& a, int active);
+int qp_sqd_any_nt_limit(diffopt_b200_ctx* ctx, const QpSolveArgs& a);
 int32_t qp_max_active_any_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int* dmax);
 
 static int32_t lu_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, const int* list, const int* count,
@@ -918,7 +921,8 @@ int32_t qp_batch_launch_tuned(diffopt_b200_ctx* ctx, const QpSolveArgs& a, bool*
         ctx->qp_hint = ctx->qp_hmax_host[slot] & 0xFF;
         ctx->qp_hmax_call[slot] = -1;
     }
-    const int nt_cap = headline ? (NV + ctx->qp_hint + PE + 7) / 8 : qp_sqd_any_nt(a, ctx->qp_hint);
+    // (a shape whose worst case does not fit shared memory is configured for what fits: larger active sets go to the LU kernel)
+    const int nt_cap = headline ? (NV + ctx->qp_hint + PE + 7) / 8 : std::min(qp_sqd_any_nt(a, ctx->qp_hint), qp_sqd_any_nt_limit(ctx, a));
     bool reported = first;
     if (want_ldl) {
         int32_t rc = headline ? qp_sqd_launch(ctx, a, nt_cap, handled, first ? nullptr : dmax, ctx->qp_seq << 8)

@@ -235,21 +235,22 @@ __global__ void __launch_bounds__(THREADS, 4) qp_kkt_sqd_any_kernel(QpSolveArgs 
         APROF(0);
         // ---- Q (lower triangle), identity padding, A
 #pragma unroll 2
-        for (int c = warp; c < n; c += NWARP) {  // a warp per column; all row chunks of the column loaded before the first store
+        for (int c = warp; c < n; c += NWARP) {  // a warp per column; six row chunks loaded before their first store
             const double* qc = Q + (size_t)c * n;
-            const int rb = (c & ~31) + lane;
-            double v[6];
+            for (int rb = (c & ~31) + lane; rb < n; rb += 192) {
+                double v[6];
 #pragma unroll
-            for (int u = 0; u < 6; ++u) {
-                const int r = rb + 32 * u;
-                v[u] = (r >= c && r < n) ? __ldg(qc + r) : 0.0;
-            }
+                for (int u = 0; u < 6; ++u) {
+                    const int r = rb + 32 * u;
+                    v[u] = (r >= c && r < n) ? __ldg(qc + r) : 0.0;
+                }
 #pragma unroll
-            for (int u = 0; u < 6; ++u) {
-                const int r = rb + 32 * u;
-                if (r >= c && r < n) {
-                    T[tix(r >> 3, c >> 3) * 64 + el(r & 7, c & 7)] = v[u];
-                    if (r == c) V.ref[c] = fabs(v[u]);
+                for (int u = 0; u < 6; ++u) {
+                    const int r = rb + 32 * u;
+                    if (r >= c && r < n) {
+                        T[tix(r >> 3, c >> 3) * 64 + el(r & 7, c & 7)] = v[u];
+                        if (r == c) V.ref[c] = fabs(v[u]);
+                    }
                 }
             }
         }
@@ -396,13 +397,21 @@ __global__ void max_active_any_kernel(int64_t B, int m, const double* __restrict
 // tile order of the reduced system when `active` inequalities are active
 int qp_sqd_any_nt(const QpSolveArgs& a, int active) { return (((a.n + 7) & ~7) + active + a.p + 7) / 8; }
 
-// The fast path serves a shape when the pivoted-LU kernel behind it can take every instance it rejects and the worst case
-// (all inequalities active) fits one CTA's shared memory.
+// Largest tile order whose shared-memory layout fits one CTA (0: not even the z block plus one constraint tile fits).
+int qp_sqd_any_nt_limit(diffopt_b200_ctx* ctx, const QpSolveArgs& a) {
+    const int ntz = (a.n + 7) / 8;
+    int nt = qp_sqd_any_nt(a, a.m);  // all inequalities active
+    while (nt > ntz && (size_t)Layout(a.n, a.m, a.p, nt).total * sizeof(double) > ctx->smem_optin) --nt;
+    if ((size_t)Layout(a.n, a.m, a.p, nt).total * sizeof(double) > ctx->smem_optin) return 0;
+    return nt;
+}
+
+// The fast path serves a shape when the reduced system of an instance with no active inequality fits one CTA's shared
+// memory; instances whose active set outgrows what fits are handed to the pivoted-LU kernel like any other reject (that
+// kernel keeps the matrix in shared memory up to N = 165 and in global memory beyond).
 bool qp_sqd_any_supported(diffopt_b200_ctx* ctx, const QpSolveArgs& a) {
     if (a.m > 255) return false;  // the active-set report carries the size in one byte
-    if (qp_generic_smem_bytes(a.n, a.m, a.p) > ctx->smem_optin) return false;
-    const Layout lay(a.n, a.m, a.p, qp_sqd_any_nt(a, a.m));
-    return (size_t)lay.total * sizeof(double) <= ctx->smem_optin;
+    return qp_sqd_any_nt_limit(ctx, a) >= qp_sqd_any_nt(a, 0);
 }
 
 int32_t qp_max_active_any_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int* dmax) {

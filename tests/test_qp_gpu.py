@@ -699,3 +699,24 @@ def test_qpmodel_takes_sparse_directions(ctx):
     got = model.forward_variable_primal().copy()
     model.forward_differentiate(dG=dG, dh=d["dh"][0])
     assert np.allclose(got, model.forward_variable_primal(), rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("n,m,p,na,fast", [(100, 100, 10, 15, True), (150, 60, 20, 25, True), (200, 150, 0, 10, True),
+                                           (200, 150, 0, 40, False), (120, 260, 4, 12, False)])
+def test_problems_beyond_the_shared_memory_lu(ctx, n, m, p, na, fast):
+    """N = n + m + p > 165: the pivoted-LU kernel keeps its matrix in global memory (the safety net), the LDL' fast path still
+    serves instances whose reduced system fits shared memory.  `fast`: every instance is expected on the fast path; otherwise
+    the active set (or m > 255) is beyond it and the whole batch runs the global-memory LU -- same answers either way."""
+    B = 6
+    d = bench_data.qp_batch(B, n, m, p, n_active=na, seed0=9700 + n + m)
+    _solve(ctx, d)
+    fwd, rev, info = _solve(ctx, d)
+    assert not info.any()
+    nfb, hint, kern = ctx.qp_last_stats()
+    if fast:
+        assert kern == 2 and nfb == 0, (nfb, hint, kern)
+    else:
+        assert kern == 0 or nfb == B, (nfb, hint, kern)
+    of, orv = _oracle_batch(d)
+    assert rel_err(fwd, of).max() <= RTOL_DIRECT
+    assert rel_err(rev, orv).max() <= RTOL_DIRECT
