@@ -82,6 +82,11 @@ double diffopt_b200_last_kernel_ms(diffopt_b200_ctx* ctx);
  * of the kernel that served the instance (the tuned kernels eliminate a reduced, reordered
  * system), so it identifies "singular", not a row of LHS.
  * Return: 0, or (first failing instance + 1) if any info != 0.
+ * Any shape is accepted.  Regular instances (Q positive definite, strict complementarity, independent active rows) run the
+ * pivot-free LDL' fast path when their reduced system -- n variables + active inequalities + p equalities, at most about
+ * 216 unknowns -- fits one CTA's shared memory; every other instance is solved by a partially pivoted LU of the full
+ * KKT matrix (in shared memory up to n+m+p = 165, in global memory beyond: correct, slow).  -3: the KKT matrix of one
+ * instance exceeds the 1 GiB scratch buffer (use diffopt_b200_sparse_setup / kkt_solve_csc for one large system).
  */
 int32_t diffopt_b200_qp_batch_solve(
     diffopt_b200_ctx* ctx, int64_t B, int32_t n, int32_t m, int32_t p,
