@@ -7,6 +7,8 @@
 // which the reference does not do (it refactorises per direction).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include <vector>
 
 #include "common.cuh"
@@ -125,6 +127,218 @@ __global__ void __launch_bounds__(LU_THREADS, 1) dense_lu_solve_kernel(int N, in
     if (tid == 0) *info = 0;
 }
 
+// ---- blocked LU for one mid-size dense system (N of a few hundred to a few thousand) on the whole GPU -------------------
+// Right-looking, block width 32, partial pivoting: per block a one-CTA panel factorisation, one kernel that applies the
+// panel's row interchanges to every other column and forms U12 = L11^-1 A12, and the trailing update A22 -= L21 U12 on the
+// FP64 tensor pipe (32 x 32 tiles, mma.sync m8n8k4).  The right-hand sides ride along as extra columns (so the forward
+// substitution is part of the factorisation); the backward substitution is the same two kernels per block, bottom up.
+constexpr int BL_NB = 32;
+
+__global__ void __launch_bounds__(1024, 1) bl_panel_kernel(const int N, const int k0, const int kb, double* __restrict__ M, int* __restrict__ ipiv,
+                                                           int* __restrict__ info) {
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv;
+    __shared__ double s_rinv;
+    __shared__ double s_row[BL_NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t ld = (size_t)N;
+    for (int j = 0; j < kb; ++j) {
+        const int col = k0 + j;
+        double best = -1.0;
+        int bi = col;
+        for (int i = col + tid; i < N; i += 1024) {
+            const double v = fabs(M[col * ld + i]);
+            if (v > best) {
+                best = v;
+                bi = i;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) {
+                best = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            s_val[warp] = best;
+            s_idx[warp] = bi;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            best = s_val[lane];
+            bi = s_idx[lane];
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) {
+                    best = ov;
+                    bi = oi;
+                }
+            }
+            if (lane == 0) {
+                s_piv = bi;
+                if (best == 0.0 || !(best == best)) {
+                    if (*info == 0) *info = col + 1;  // exactly zero pivot: the reference's SingularException
+                    s_rinv = 0.0;
+                } else {
+                    s_rinv = 1.0 / M[col * ld + bi];
+                }
+                ipiv[col] = bi;
+            }
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        const double rinv = s_rinv;
+        if (tid < kb) {  // interchange inside the panel; the pivot row's entries right of the diagonal go to shared memory
+            const size_t c = (size_t)(k0 + tid) * ld;
+            const double a = M[c + col], b = M[c + piv];
+            if (piv != col) {
+                M[c + col] = b;
+                M[c + piv] = a;
+            }
+            s_row[tid] = piv != col ? b : a;
+        }
+        __syncthreads();
+        for (int r = col + 1 + tid; r < N; r += 1024) {
+            const double l = M[col * ld + r] * rinv;
+            M[col * ld + r] = l;
+            for (int c = j + 1; c < kb; ++c) M[(size_t)(k0 + c) * ld + r] -= l * s_row[c];
+        }
+        __syncthreads();
+    }
+}
+
+// one thread per column outside the panel (W = N + nrhs columns): the panel's interchanges, then U12 = L11^-1 A12
+__global__ void __launch_bounds__(128) bl_swap_trsm_kernel(const int N, const int W, const int k0, const int kb, double* __restrict__ M,
+                                                           const int* __restrict__ ipiv) {
+    __shared__ double L11[BL_NB * BL_NB];
+    __shared__ int piv[BL_NB];
+    const size_t ld = (size_t)N;
+    for (int e = threadIdx.x; e < kb * kb; e += blockDim.x) L11[e] = M[(size_t)(k0 + e / kb) * ld + k0 + e % kb];  // L11[i + j kb]
+    if (threadIdx.x < kb) piv[threadIdx.x] = ipiv[k0 + threadIdx.x];
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = t < k0 ? t : t + kb;
+    if (c >= W) return;
+    double* col = M + (size_t)c * ld;
+    for (int j = 0; j < kb; ++j) {
+        const int p = piv[j];
+        if (p != k0 + j) {
+            const double a = col[k0 + j];
+            col[k0 + j] = col[p];
+            col[p] = a;
+        }
+    }
+    if (c < k0 + kb) return;  // columns left of the panel only take the interchanges
+    double u[BL_NB];
+#pragma unroll
+    for (int j = 0; j < BL_NB; ++j) u[j] = j < kb ? col[k0 + j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < BL_NB; ++j) {
+#pragma unroll
+        for (int i = j + 1; i < BL_NB; ++i)
+            if (i < kb) u[i] = fma(-L11[i + j * kb], u[j], u[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < BL_NB; ++j)
+        if (j < kb) col[k0 + j] = u[j];
+}
+
+// C(i, j) -= sum_k A(i, k) B(k, j) inside M: C = M[rowA0 + i, colB0 + j], A = M[rowA0 + i, k0 + k], B = M[k0 + k, colB0 + j],
+// k < kb <= 32; 32 x 32 tile per CTA, 8 warps x two 8 x 8 blocks on the FP64 tensor pipe
+__global__ void __launch_bounds__(256) bl_gemm_kernel(double* __restrict__ M, const size_t ld, const int rowA0, const int nrows, const int colB0,
+                                                      const int ncols, const int k0, const int kb) {
+    __shared__ double As[32][40], Bs[32][40];  // As[k][i], Bs[k][j]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    double va[4], vb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = tid + 256 * u, r = e & 31, c = e >> 5;
+        va[u] = (c < kb && i0 + r < nrows) ? M[(size_t)(k0 + c) * ld + rowA0 + i0 + r] : 0.0;
+        vb[u] = (r < kb && j0 + c < ncols) ? M[(size_t)(colB0 + j0 + c) * ld + k0 + r] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = tid + 256 * u, r = e & 31, c = e >> 5;
+        As[c][r] = va[u];
+        Bs[r][c] = vb[u];
+    }
+    __syncthreads();
+    const int bi = warp >> 1, bj = (warp & 1) * 2;
+    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+#pragma unroll
+    for (int kk = 0; kk < 32; kk += 4) {
+        const double a = As[kk + t][8 * bi + g];
+        const double b0 = Bs[kk + t][8 * bj + g];
+        const double b1 = Bs[kk + t][8 * bj + 8 + g];
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[0]), "+d"(c0[1]) : "d"(a), "d"(b0));
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c1[0]), "+d"(c1[1]) : "d"(a), "d"(b1));
+    }
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int i = i0 + 8 * bi + g, j = j0 + 8 * (bj + blk) + 2 * t + v;
+            if (i < nrows && j < ncols) M[(size_t)(colB0 + j) * ld + rowA0 + i] -= blk ? c1[v] : c0[v];
+        }
+}
+
+// backward substitution, diagonal block: one thread per right-hand-side column solves U11 x = y (U11 upper, non-unit)
+__global__ void __launch_bounds__(128) bl_back_diag_kernel(const int N, const int nrhs, const int k0, const int kb, double* __restrict__ M) {
+    __shared__ double U11[BL_NB * BL_NB];
+    const size_t ld = (size_t)N;
+    for (int e = threadIdx.x; e < kb * kb; e += blockDim.x) U11[e] = M[(size_t)(k0 + e / kb) * ld + k0 + e % kb];  // U11[i + j kb]
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nrhs) return;
+    double* col = M + (size_t)(N + c) * ld;
+    double x[BL_NB];
+#pragma unroll
+    for (int j = 0; j < BL_NB; ++j) x[j] = j < kb ? col[k0 + j] : 0.0;
+#pragma unroll
+    for (int j = BL_NB - 1; j >= 0; --j) {
+        if (j < kb) {
+            x[j] = x[j] / U11[j + j * kb];
+#pragma unroll
+            for (int i = 0; i < j; ++i) x[i] = fma(-U11[i + j * kb], x[j], x[i]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < BL_NB; ++j)
+        if (j < kb) col[k0 + j] = x[j];
+}
+
+// M: N x (N + nrhs) column-major; on exit its last nrhs columns hold the solutions, *info the first zero pivot (1-based) or 0
+int32_t dense_blocked_lu_solve(diffopt_b200_ctx* ctx, const int N, const int nrhs, double* M, int* ipiv, int* info) {
+    const int W = N + nrhs;
+    const size_t ld = (size_t)N;
+    DO_CUDA(ctx, cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
+    for (int k0 = 0; k0 < N; k0 += BL_NB) {
+        const int kb = std::min(BL_NB, N - k0);
+        bl_panel_kernel<<<1, 1024, 0, ctx->stream>>>(N, k0, kb, M, ipiv, info);
+        const int others = W - kb;
+        if (others > 0) bl_swap_trsm_kernel<<<(others + 127) / 128, 128, 0, ctx->stream>>>(N, W, k0, kb, M, ipiv);
+        const int nr = N - k0 - kb, nc = W - k0 - kb;
+        if (nr > 0 && nc > 0)
+            bl_gemm_kernel<<<dim3((unsigned)((nr + 31) / 32), (unsigned)((nc + 31) / 32)), 256, 0, ctx->stream>>>(M, ld, k0 + kb, nr, k0 + kb, nc, k0, kb);
+        ctx->launches += 3;
+    }
+    for (int k0 = ((N - 1) / BL_NB) * BL_NB; k0 >= 0; k0 -= BL_NB) {
+        const int kb = std::min(BL_NB, N - k0);
+        bl_back_diag_kernel<<<(nrhs + 127) / 128, 128, 0, ctx->stream>>>(N, nrhs, k0, kb, M);
+        if (k0 > 0)
+            bl_gemm_kernel<<<dim3((unsigned)((k0 + 31) / 32), (unsigned)((nrhs + 31) / 32)), 256, 0, ctx->stream>>>(M, ld, 0, k0, N, nrhs, k0, kb);
+        ctx->launches += 2;
+    }
+    DO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int32_t diffopt_b200_kkt_solve_csc(diffopt_b200_ctx* ctx, int64_t N, const int64_t* colptr, const int64_t* rowval,
@@ -133,37 +347,7 @@ extern "C" int32_t diffopt_b200_kkt_solve_csc(diffopt_b200_ctx* ctx, int64_t N, 
     if (!ctx) return -1;
     if (N <= 0 || nrhs <= 0 || !colptr || !rowval || !nzval || !rhs || !x_out) BAD_ARG(ctx, "kkt_solve_csc: bad argument");
     DeviceGuard guard_(ctx->device);
-    // The dense kernel is one CTA: fine for the reference's own problem sizes, hopeless beyond ~1000 unknowns.  Larger
-    // systems go through the sparse factorisation (multifrontal LU, sparse_mf.cu), which is what the reference's sparse
-    // `\` does at any size.  DIFFOPT_B200_DENSE_MAX moves the switch-over.
-    int64_t dense_max = 1024;
-    if (const char* dm = getenv("DIFFOPT_B200_DENSE_MAX")) dense_max = atoll(dm);
-    if (N > dense_max) {
-        std::vector<int64_t> hc, hr;
-        std::vector<double> hv;
-        const int64_t *pc = colptr, *pr = rowval;
-        const double* pvv = nzval;
-        if (memspace == DIFFOPT_B200_DEVICE) {  // the analysis runs on the host: fetch the matrix
-            hc.resize((size_t)N + 1);
-            DO_CUDA(ctx, cudaMemcpy(hc.data(), colptr, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyDeviceToHost));
-            const int64_t nz = hc[(size_t)N] - 1;
-            if (nz < 0) BAD_ARG(ctx, "kkt_solve_csc: colptr must be 1-based");
-            hr.resize((size_t)nz);
-            hv.resize((size_t)nz);
-            DO_CUDA(ctx, cudaMemcpy(hr.data(), rowval, sizeof(int64_t) * (size_t)nz, cudaMemcpyDeviceToHost));
-            DO_CUDA(ctx, cudaMemcpy(hv.data(), nzval, sizeof(double) * (size_t)nz, cudaMemcpyDeviceToHost));
-            pc = hc.data(); pr = hr.data(); pvv = hv.data();
-        }
-        int32_t rc = diffopt_b200_sparse_setup(ctx, N, pc, pr, pvv, trans, nullptr);
-        if (rc != 0) return rc;
-        const double factor_ms = ctx->last_ms;
-        rc = diffopt_b200_sparse_solve(ctx, nrhs, rhs, x_out, memspace);
-        ctx->last_ms += factor_ms;
-        return rc;
-    }
     int64_t nnz = 0;
-    std::vector<int64_t> hcol;
-    const void *dcol = nullptr, *drow = nullptr, *dval = nullptr;
     if (memspace == DIFFOPT_B200_HOST) {
         nnz = colptr[N] - 1;
     } else {
@@ -173,6 +357,35 @@ extern "C" int32_t diffopt_b200_kkt_solve_csc(diffopt_b200_ctx* ctx, int64_t N, 
         nnz = last - 1;
     }
     if (nnz < 0) BAD_ARG(ctx, "kkt_solve_csc: colptr must be 1-based");
+    // Three routes.  N <= 128: one persistent CTA (lowest latency at the reference's own test sizes).  Larger and DENSE
+    // (a KKT matrix with dense Q, G, A: more than 2 % of the entries, up to N = 16384): blocked LU over the whole GPU.
+    // Larger and sparse: the multifrontal factorisation (sparse_mf.cu), which is what the reference's sparse `\` does at any
+    // size.  DIFFOPT_B200_DENSE_MAX moves the switch-over below which every matrix counts as dense.
+    int64_t dense_max = 1024;
+    if (const char* dm = getenv("DIFFOPT_B200_DENSE_MAX")) dense_max = atoll(dm);
+    const bool dense_enough = (double)nnz >= 0.02 * (double)N * (double)N && N <= 16384;
+    if (N > dense_max && !dense_enough) {
+        std::vector<int64_t> hc, hr;
+        std::vector<double> hv;
+        const int64_t *pc = colptr, *pr = rowval;
+        const double* pvv = nzval;
+        if (memspace == DIFFOPT_B200_DEVICE) {  // the analysis runs on the host: fetch the matrix
+            hc.resize((size_t)N + 1);
+            DO_CUDA(ctx, cudaMemcpy(hc.data(), colptr, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyDeviceToHost));
+            hr.resize((size_t)nnz);
+            hv.resize((size_t)nnz);
+            DO_CUDA(ctx, cudaMemcpy(hr.data(), rowval, sizeof(int64_t) * (size_t)nnz, cudaMemcpyDeviceToHost));
+            DO_CUDA(ctx, cudaMemcpy(hv.data(), nzval, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost));
+            pc = hc.data(); pr = hr.data(); pvv = hv.data();
+        }
+        int32_t rc = diffopt_b200_sparse_setup(ctx, N, pc, pr, pvv, trans, nullptr);
+        if (rc != 0) return rc;
+        const double factor_ms = ctx->last_ms;
+        rc = diffopt_b200_sparse_solve(ctx, nrhs, rhs, x_out, memspace);
+        ctx->last_ms += factor_ms;
+        return rc;
+    }
+    const void *dcol = nullptr, *drow = nullptr, *dval = nullptr;
     DO_CUDA(ctx, stage_in(ctx, ctx->in[0], colptr, sizeof(int64_t) * (size_t)(N + 1), memspace, &dcol));
     DO_CUDA(ctx, stage_in(ctx, ctx->in[1], rowval, sizeof(int64_t) * (size_t)nnz, memspace, &drow));
     DO_CUDA(ctx, stage_in(ctx, ctx->in[2], nzval, sizeof(double) * (size_t)nnz, memspace, &dval));
@@ -191,8 +404,14 @@ extern "C" int32_t diffopt_b200_kkt_solve_csc(diffopt_b200_ctx* ctx, int64_t N, 
                                                                       (const double*)dval, trans, M);
         ctx->launches++;
     }
-    dense_lu_solve_kernel<<<1, LU_THREADS, 0, ctx->stream>>>((int)N, (int)nrhs, M, dinfo);
-    ctx->launches++;
+    if (N > 128 && !getenv("DIFFOPT_B200_DENSE_ONE_CTA")) {
+        DO_CUDA(ctx, ctx->in[4].reserve(sizeof(int) * (size_t)N));
+        if (int32_t rc = dense_blocked_lu_solve(ctx, (int)N, (int)nrhs, M, ctx->in[4].as<int>(), dinfo)) return rc;
+    } else {
+        DO_CUDA(ctx, cudaMemsetAsync(dinfo, 0, sizeof(int), ctx->stream));
+        dense_lu_solve_kernel<<<1, LU_THREADS, 0, ctx->stream>>>((int)N, (int)nrhs, M, dinfo);
+        ctx->launches++;
+    }
     DO_CUDA(ctx, cudaGetLastError());
     DO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     int hinfo = 0;

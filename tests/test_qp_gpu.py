@@ -720,3 +720,26 @@ def test_problems_beyond_the_shared_memory_lu(ctx, n, m, p, na, fast):
     of, orv = _oracle_batch(d)
     assert rel_err(fwd, of).max() <= RTOL_DIRECT
     assert rel_err(rev, orv).max() <= RTOL_DIRECT
+
+
+@pytest.mark.parametrize("n,m,p,na,nrhs", [(60, 60, 15, 15, 3), (120, 120, 31, 30, 1), (250, 250, 60, 60, 40), (400, 400, 100, 100, 5)])
+def test_direct_solve_of_one_dense_kkt_system_blocked_lu(ctx, n, m, p, na, nrhs):
+    """`LHS \\ RHS` for ONE QP with dense Q, G, A (N = 135 .. 900: block sizes that are and are not multiples of 32): the
+    blocked partially pivoted LU over the whole GPU (kkt_dense.cu), both orientations, one and many right-hand sides, against
+    a dense LAPACK solve; a structurally singular matrix of that size raises SingularException (numerically singular ones give a
+    rounding-level pivot in any blocked LU, LAPACK's included)."""
+    import scipy.sparse as sp
+    lsq = diffopt_b200.submodule("lsqr")
+    d = bench_data.qp_batch(1, n, m, p, n_active=na, seed0=9900 + n)
+    K = oqp.create_lhs(d["z"][0], d["lam"][0], d["Q"][0], d["G"][0], d["h"][0], d["A"][0])
+    N = K.shape[0]
+    R = np.random.default_rng(n).standard_normal((N, nrhs))
+    Kc = sp.csc_matrix(K)
+    for trans in (False, True):
+        X = lsq.solve_csc(ctx, Kc, R, trans=trans)
+        ref = np.linalg.solve(K.T if trans else K, R)
+        assert (np.linalg.norm(X - ref, axis=0) / np.linalg.norm(ref, axis=0)).max() <= RTOL_DIRECT
+    Ks = K.copy()
+    Ks[n + m + 1] = 0.0                # an equality row without entries: structurally singular, the zero pivot is exact
+    with pytest.raises(diffopt_b200.SingularException):
+        lsq.solve_csc(ctx, sp.csc_matrix(Ks), R)
