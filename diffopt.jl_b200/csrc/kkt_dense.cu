@@ -134,24 +134,34 @@ __global__ void __launch_bounds__(LU_THREADS, 1) dense_lu_solve_kernel(int N, in
 // substitution is part of the factorisation); the backward substitution is the same two kernels per block, bottom up.
 constexpr int BL_NB = 32;
 
+// The panel (rows k0 .. N-1, kb columns) is worked on in shared memory when it fits (`staged`), else in place.
 __global__ void __launch_bounds__(1024, 1) bl_panel_kernel(const int N, const int k0, const int kb, double* __restrict__ M, int* __restrict__ ipiv,
-                                                           int* __restrict__ info) {
+                                                           int* __restrict__ info, const int staged) {
+    extern __shared__ double bl_smem[];
     __shared__ double s_val[32];
     __shared__ int s_idx[32];
     __shared__ int s_piv;
     __shared__ double s_rinv;
     __shared__ double s_row[BL_NB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t ld = (size_t)N;
+    const int mr = N - k0;
+    // element (row k0 + r, panel column c) lives at P[c * pld + r]
+    double* const G0 = M + (size_t)k0 * N + k0;
+    double* const P = staged ? bl_smem : G0;
+    const size_t pld = staged ? (size_t)mr : (size_t)N;
+    if (staged) {
+        for (int c = 0; c < kb; ++c)
+            for (int r = tid; r < mr; r += 1024) P[c * pld + r] = G0[(size_t)c * N + r];
+        __syncthreads();
+    }
     for (int j = 0; j < kb; ++j) {
-        const int col = k0 + j;
         double best = -1.0;
-        int bi = col;
-        for (int i = col + tid; i < N; i += 1024) {
-            const double v = fabs(M[col * ld + i]);
+        int bi = j;
+        for (int r = j + tid; r < mr; r += 1024) {
+            const double v = fabs(P[j * pld + r]);
             if (v > best) {
                 best = v;
-                bi = i;
+                bi = r;
             }
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -181,66 +191,95 @@ __global__ void __launch_bounds__(1024, 1) bl_panel_kernel(const int N, const in
             if (lane == 0) {
                 s_piv = bi;
                 if (best == 0.0 || !(best == best)) {
-                    if (*info == 0) *info = col + 1;  // exactly zero pivot: the reference's SingularException
+                    if (*info == 0) *info = k0 + j + 1;  // exactly zero pivot: the reference's SingularException
                     s_rinv = 0.0;
                 } else {
-                    s_rinv = 1.0 / M[col * ld + bi];
+                    s_rinv = 1.0 / P[j * pld + bi];
                 }
-                ipiv[col] = bi;
+                ipiv[k0 + j] = k0 + bi;
             }
         }
         __syncthreads();
         const int piv = s_piv;
         const double rinv = s_rinv;
-        if (tid < kb) {  // interchange inside the panel; the pivot row's entries right of the diagonal go to shared memory
-            const size_t c = (size_t)(k0 + tid) * ld;
-            const double a = M[c + col], b = M[c + piv];
-            if (piv != col) {
-                M[c + col] = b;
-                M[c + piv] = a;
+        if (tid < kb) {  // interchange inside the panel; the pivot row's entries go to shared memory
+            const double a = P[tid * pld + j], b = P[tid * pld + piv];
+            if (piv != j) {
+                P[tid * pld + j] = b;
+                P[tid * pld + piv] = a;
             }
-            s_row[tid] = piv != col ? b : a;
+            s_row[tid] = piv != j ? b : a;
         }
         __syncthreads();
-        for (int r = col + 1 + tid; r < N; r += 1024) {
-            const double l = M[col * ld + r] * rinv;
-            M[col * ld + r] = l;
-            for (int c = j + 1; c < kb; ++c) M[(size_t)(k0 + c) * ld + r] -= l * s_row[c];
+        for (int r = j + 1 + tid; r < mr; r += 1024) {
+            const double l = P[j * pld + r] * rinv;
+            P[j * pld + r] = l;
+            for (int c = j + 1; c < kb; ++c) P[c * pld + r] -= l * s_row[c];
         }
         __syncthreads();
     }
+    if (staged)
+        for (int c = 0; c < kb; ++c)
+            for (int r = tid; r < mr; r += 1024) G0[(size_t)c * N + r] = P[c * pld + r];
 }
 
-// one thread per column outside the panel (W = N + nrhs columns): the panel's interchanges, then U12 = L11^-1 A12
+// one thread per column outside the panel (W = N + nrhs columns): the panel's interchanges, then U12 = L11^-1 A12.
+// The kb interchanges touch at most 2 kb rows; their net effect is worked out once per CTA (which original row ends up in
+// each of them), so a column thread issues all its loads together instead of kb dependent swaps.
 __global__ void __launch_bounds__(128) bl_swap_trsm_kernel(const int N, const int W, const int k0, const int kb, double* __restrict__ M,
                                                            const int* __restrict__ ipiv) {
     __shared__ double L11[BL_NB * BL_NB];
-    __shared__ int piv[BL_NB];
+    __shared__ int srow[2 * BL_NB];  // rows touched: k0 + j (j < kb), then the pivot rows
+    __shared__ int from[2 * BL_NB];  // original row whose entry ends up in srow[q] (canonical q: first occurrence of the row)
+    __shared__ int canon[2 * BL_NB]; // 1 when q is the first occurrence of its row
+    __shared__ int cpos[2 * BL_NB];  // position of that first occurrence
     const size_t ld = (size_t)N;
     for (int e = threadIdx.x; e < kb * kb; e += blockDim.x) L11[e] = M[(size_t)(k0 + e / kb) * ld + k0 + e % kb];  // L11[i + j kb]
-    if (threadIdx.x < kb) piv[threadIdx.x] = ipiv[k0 + threadIdx.x];
+    if (threadIdx.x < kb) {
+        srow[threadIdx.x] = k0 + threadIdx.x;
+        srow[kb + threadIdx.x] = ipiv[k0 + threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kb) {  // first occurrence of every touched row
+        const int q = threadIdx.x;
+        int first = q;
+        for (int r = 0; r < q; ++r)
+            if (srow[r] == srow[q]) {
+                first = r;
+                break;
+            }
+        cpos[q] = first;
+        canon[q] = first == q;
+        from[q] = srow[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int j = 0; j < kb; ++j) {  // the interchanges in order, on the row labels
+            const int b = cpos[kb + j], tmp = from[j];
+            from[j] = from[b];
+            from[b] = tmp;
+        }
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = t < k0 ? t : t + kb;
     if (c >= W) return;
     double* col = M + (size_t)c * ld;
-    for (int j = 0; j < kb; ++j) {
-        const int p = piv[j];
-        if (p != k0 + j) {
-            const double a = col[k0 + j];
-            col[k0 + j] = col[p];
-            col[p] = a;
-        }
-    }
-    if (c < k0 + kb) return;  // columns left of the panel only take the interchanges
-    double u[BL_NB];
-#pragma unroll
-    for (int j = 0; j < BL_NB; ++j) u[j] = j < kb ? col[k0 + j] : 0.0;
+    double u[BL_NB], dsp[BL_NB];
 #pragma unroll
     for (int j = 0; j < BL_NB; ++j) {
+        u[j] = j < kb ? col[from[j]] : 0.0;
+        dsp[j] = (j < kb && canon[kb + j]) ? col[from[kb + j]] : 0.0;
+    }
 #pragma unroll
-        for (int i = j + 1; i < BL_NB; ++i)
-            if (i < kb) u[i] = fma(-L11[i + j * kb], u[j], u[i]);
+    for (int j = 0; j < BL_NB; ++j)
+        if (j < kb && canon[kb + j]) col[srow[kb + j]] = dsp[j];
+    if (c >= k0 + kb) {  // columns left of the panel only take the interchanges
+#pragma unroll
+        for (int j = 0; j < BL_NB; ++j) {
+#pragma unroll
+            for (int i = j + 1; i < BL_NB; ++i)
+                if (i < kb) u[i] = fma(-L11[i + j * kb], u[j], u[i]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < BL_NB; ++j)
@@ -318,9 +357,17 @@ int32_t dense_blocked_lu_solve(diffopt_b200_ctx* ctx, const int N, const int nrh
     const int W = N + nrhs;
     const size_t ld = (size_t)N;
     DO_CUDA(ctx, cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
-    for (int k0 = 0; k0 < N; k0 += BL_NB) {
-        const int kb = std::min(BL_NB, N - k0);
-        bl_panel_kernel<<<1, 1024, 0, ctx->stream>>>(N, k0, kb, M, ipiv, info);
+    DO_CUDA(ctx, cudaFuncSetAttribute(bl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 2048)));
+    std::vector<int> starts;  // block starts (the backward sweep walks them in reverse)
+    for (int k0 = 0, kb = 0; k0 < N; k0 += kb) {
+        kb = std::min(BL_NB, N - k0);
+        starts.push_back(k0);
+        // the panel is factorised in shared memory when it fits; a tall panel is narrowed to 16 columns if that makes it fit
+        auto fits = [&](int w) { return sizeof(double) * (size_t)(N - k0) * w + 2048 <= ctx->smem_optin; };
+        if (!fits(kb) && kb > 16 && fits(16)) kb = 16;
+        const size_t pbytes = sizeof(double) * (size_t)(N - k0) * kb;
+        const int staged = fits(kb);
+        bl_panel_kernel<<<1, 1024, staged ? pbytes : 0, ctx->stream>>>(N, k0, kb, M, ipiv, info, staged);
         const int others = W - kb;
         if (others > 0) bl_swap_trsm_kernel<<<(others + 127) / 128, 128, 0, ctx->stream>>>(N, W, k0, kb, M, ipiv);
         const int nr = N - k0 - kb, nc = W - k0 - kb;
@@ -328,8 +375,8 @@ int32_t dense_blocked_lu_solve(diffopt_b200_ctx* ctx, const int N, const int nrh
             bl_gemm_kernel<<<dim3((unsigned)((nr + 31) / 32), (unsigned)((nc + 31) / 32)), 256, 0, ctx->stream>>>(M, ld, k0 + kb, nr, k0 + kb, nc, k0, kb);
         ctx->launches += 3;
     }
-    for (int k0 = ((N - 1) / BL_NB) * BL_NB; k0 >= 0; k0 -= BL_NB) {
-        const int kb = std::min(BL_NB, N - k0);
+    for (size_t bidx = starts.size(); bidx-- > 0;) {
+        const int k0 = starts[bidx], kb = (bidx + 1 < starts.size() ? starts[bidx + 1] : N) - k0;
         bl_back_diag_kernel<<<(nrhs + 127) / 128, 128, 0, ctx->stream>>>(N, nrhs, k0, kb, M);
         if (k0 > 0)
             bl_gemm_kernel<<<dim3((unsigned)((k0 + 31) / 32), (unsigned)((nrhs + 31) / 32)), 256, 0, ctx->stream>>>(M, ld, 0, k0, N, nrhs, k0, kb);
