@@ -453,7 +453,8 @@ def run_b200(args, rank, world, local_rank):
                         ("conic_config4_converged", lambda: bench_aux.run_conic(
                             ctx, "4c", __import__("bench_data").conic_config4_conditioned(), iters=None,
                             cpu_iters=None if not args.no_cpu else 0, emit=False)),
-                        ("psd_config5", lambda: bench_aux.config5(ctx, emit=False))):
+                        ("psd_config5", lambda: bench_aux.config5(ctx, emit=False)),
+                        ("dense_single_kkt", lambda: bench_aux.dense_single(ctx, emit=False))):
             try:
                 aux[key] = fn()
             except Exception as e:

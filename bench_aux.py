@@ -215,7 +215,7 @@ def config3(ctx, portfolio=False, nrhs=256, cpu=True):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,3,3p,4,4c,4x,5")
+    ap.add_argument("--configs", default="1,2s,3,3p,4,4c,4x,5")
     args = ap.parse_args()
     import bench_data
     import diffopt_b200
@@ -277,6 +277,36 @@ def main():
         run_psd_batch(ctx)
     if "5" in todo:
         config5(ctx)
+    if "2s" in todo:
+        dense_single(ctx)
+
+
+def dense_single(ctx, emit=True, sizes=((120, 120, 30), (400, 400, 100), (900, 900, 200))):
+    """The stock `solve_system` plug point on ONE dense QP (the reference's `LHS \\ RHS`, QuadraticProgram.jl:486-492, through
+    diffopt_b200_kkt_solve_csc): KKT matrices of order 270 / 900 / 2000 with dense Q, G, A, four right-hand sides -- the blocked
+    LU over the whole GPU against SuperLU (the oracle's stand-in for UMFPACK) and dense LAPACK on the host."""
+    import bench_data
+    import diffopt_b200
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from oracle import qp as oqp
+    lsq = diffopt_b200.submodule("lsqr")
+    rows = []
+    for n, m, p in sizes:
+        d = bench_data.qp_batch(1, n, m, p, n_active=p, seed0=5)
+        K = sp.csc_matrix(oqp.create_lhs(d["z"][0], d["lam"][0], d["Q"][0], d["G"][0], d["h"][0], d["A"][0]))
+        N = K.shape[0]
+        R = np.random.default_rng(0).standard_normal((N, 4))
+        lsq.solve_csc(ctx, K, R)
+        X = lsq.solve_csc(ctx, K, R)
+        dev_ms = ctx.last_kernel_ms
+        t0 = time.perf_counter(); lu = spl.splu(K); lu.solve(R); t1 = time.perf_counter(); np.linalg.solve(K.toarray(), R); t2 = time.perf_counter()
+        rows.append({"N": N, "nnz": int(K.nnz), "device_ms": dev_ms, "max_residual": float(np.abs(K @ X - R).max()),
+                     "cpu_superlu_ms": 1e3 * (t1 - t0), "cpu_dense_lapack_ms": 1e3 * (t2 - t1)})
+    line = {"config": "2s: one dense QP through the solve_system drop-in (kkt_solve_csc), 4 right-hand sides", "systems": rows}
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def config5(ctx, emit=True):

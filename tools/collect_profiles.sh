@@ -18,5 +18,5 @@ python tools/prof_driver.py qp 4096 100 50 0 10 > $O/r02_qp_any_plain.log 2>&1 |
 ncu --set full --clock-control none --import-source on -k regex:qp_kkt_sqd_any -s 1 -c 1 -o $O/r02_qp_sqd_any -f python tools/prof_driver.py qp 4096 100 50 0 10 > $O/r02_qp_any_ncu.log 2>&1
 python bench_aux.py --configs 5 > $O/r02_psd_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/r02_psd_launches_raw.csv python bench_aux.py --configs 5 > $O/r02_psd_ncu.log 2>&1
-python bench_aux.py --configs 1,3,3p,4,4c,4x,5 > $O/r02_bench_aux.jsonl 2> $O/r02_bench_aux.err
+python bench_aux.py --configs 1,2s,3,3p,4,4c,4x,5 > $O/r02_bench_aux.jsonl 2> $O/r02_bench_aux.err
 ls -la $O | grep r02_
