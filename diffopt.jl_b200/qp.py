@@ -338,6 +338,8 @@ class QPModel:
         self.nu = -np.asarray(moi_dual, float).reshape(self.p)      # QuadraticProgram.jl:164-171
 
     # -- the two differentiation entry points -----------------------------------------------------
+    BATCHED_ORDER_MAX = 200   # n + p above which a single instance no longer fits the batched fast path
+
     def _iterative(self):
         return float(np.linalg.norm(self.Q)) == 0.0                 # `norm(Q) ≈ 0`, :333/:436
 
@@ -368,6 +370,17 @@ class QPModel:
                 return -lsqr_csc(self.ctx, K, rhs, trans=False, **tol)[0]
             rhs = self._forward_rhs(*fwd_dir)
             return -lsqr_csc(self.ctx, K, rhs, trans=True, **tol)[0]
+        if self.n + self.p > self.BATCHED_ORDER_MAX:
+            # ONE large dense QP: the batched kernels keep an instance in one CTA's shared memory (reduced order <= ~216);
+            # beyond that the reference's own route -- LHS assembled on the host, `LHS \ RHS` (QuadraticProgram.jl:335, :438)
+            # -- goes through the solve_system drop-in, i.e. the blocked LU over the whole GPU (kkt_dense.cu)
+            from .lsqr import solve_csc
+            K = self._lhs_csc()
+            if seed is not None:
+                rhs = np.zeros(K.shape[0])
+                rhs[:self.n] = seed
+                return -solve_csc(self.ctx, K, rhs, trans=False)
+            return -solve_csc(self.ctx, K, self._forward_rhs(*fwd_dir), trans=True)
         one = lambda v: None if v is None else np.asarray(v, float)[None]
         fd = None if fwd_dir is None else tuple(one(v) for v in fwd_dir)
         fwd, rev, info = solve_batch(self.ctx, self.Q[None], self.G[None] if self.m else None,

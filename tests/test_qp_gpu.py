@@ -743,3 +743,21 @@ def test_direct_solve_of_one_dense_kkt_system_blocked_lu(ctx, n, m, p, na, nrhs)
     Ks[n + m + 1] = 0.0                # an equality row without entries: structurally singular, the zero pivot is exact
     with pytest.raises(diffopt_b200.SingularException):
         lsq.solve_csc(ctx, sp.csc_matrix(Ks), R)
+
+
+def test_qpmodel_routes_one_large_dense_qp_to_the_blocked_lu(ctx):
+    """A single QP beyond the batched kernels' shared-memory order (n = 300, m = 200, p = 40: N = 540) through the
+    reference-shaped model: reverse and forward mode against the oracle."""
+    qpm = diffopt_b200.submodule("qp")
+    n, m, p = 300, 200, 40
+    d = bench_data.qp_batch(1, n, m, p, n_active=30, seed0=9950)
+    model = qpm.QPModel(ctx, d["Q"][0], d["q"][0], d["G"][0], d["h"][0], d["A"][0], d["b"][0])
+    model.set_variable_primal(d["z"][0]); model.set_constraint_dual_le(-d["lam"][0]); model.set_constraint_dual_eq(-d["nu"][0])
+    launches = ctx.launch_count
+    model.reverse_differentiate(d["seed"][0])
+    assert ctx.launch_count - launches > 20      # the blocked factorisation, not one batched launch
+    of, orv = _oracle_batch(d)
+    got = np.concatenate(model.back_grad_cache)
+    assert rel_err(got, orv[0]) <= RTOL_DIRECT
+    model.forward_differentiate(d["dQ"][0], d["dq"][0], d["dG"][0], d["dh"][0], d["dA"][0], d["db"][0])
+    assert rel_err(np.concatenate(model.forw_grad_cache), of[0]) <= RTOL_DIRECT
