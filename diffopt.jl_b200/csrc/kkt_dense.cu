@@ -223,6 +223,100 @@ __global__ void __launch_bounds__(1024, 1) bl_panel_kernel(const int N, const in
             for (int r = tid; r < mr; r += 1024) G0[(size_t)c * N + r] = P[c * pld + r];
 }
 
+// Panel factorisation with the panel in REGISTERS: one thread per row of the panel (mr = N - k0 <= blockDim.x), its KB
+// entries in registers for the whole panel.  No row ever moves: a pivot step elects the thread whose row has the largest
+// entry in the current column (shuffle + shared-memory argmax), that thread publishes its row and retires, the others apply
+// the rank-1 update in registers; a position table in shared memory replays LAPACK's interchanges so that every row is
+// written back to the place (and ipiv gets the values) the sequential algorithm gives.  Two block barriers per column.
+template <int KB>
+__global__ void __launch_bounds__(KB == 32 ? 512 : 1024, 1) bl_panel_reg_kernel(const int N, const int k0, const int kb, double* __restrict__ M,
+                                                                                 int* __restrict__ ipiv, int* __restrict__ info) {
+    constexpr int NT = KB == 32 ? 512 : 1024;
+    __shared__ int who[NT];  // thread whose row currently sits at this position of the panel
+    __shared__ double s_val[32];
+    __shared__ int s_pos[32], s_tid[32];
+    __shared__ double s_row[KB];
+    __shared__ double s_rinv;
+    __shared__ int s_q, s_pi;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = NT / 32;
+    const int mr = N - k0;
+    const size_t ld = (size_t)N;
+    double* const G0 = M + (size_t)k0 * ld + k0;
+    const bool row = tid < mr;
+    double a[KB];
+#pragma unroll
+    for (int c = 0; c < KB; ++c) a[c] = (row && c < kb) ? G0[(size_t)c * ld + tid] : 0.0;
+    who[tid] = tid;
+    int mypos = tid;
+    bool done = !row;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
+        if (j < kb) {  // (block-uniform)
+            double best = done ? -1.0 : fabs(a[j]);
+            int bpos = mypos, btid = tid;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos, o), ot = __shfl_xor_sync(0xffffffffu, btid, o);
+                if (ov > best || (ov == best && op < bpos)) {
+                    best = ov;
+                    bpos = op;
+                    btid = ot;
+                }
+            }
+            if (lane == 0) {
+                s_val[warp] = best;
+                s_pos[warp] = bpos;
+                s_tid[warp] = btid;
+            }
+            __syncthreads();
+            best = lane < nwarp ? s_val[lane] : -2.0;  // every warp finishes the reduction for itself
+            bpos = lane < nwarp ? s_pos[lane] : 0x7fffffff;
+            btid = lane < nwarp ? s_tid[lane] : 0;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos, o), ot = __shfl_xor_sync(0xffffffffu, btid, o);
+                if (ov > best || (ov == best && op < bpos)) {
+                    best = ov;
+                    bpos = op;
+                    btid = ot;
+                }
+            }
+            if (tid == btid) {  // the pivot row's thread: publish the row, replay the interchange of positions j and bpos
+                const bool singular = best == 0.0 || !(best == best);
+                if (singular && *info == 0) *info = k0 + j + 1;  // exactly zero pivot: the reference's SingularException
+                s_rinv = singular ? 0.0 : 1.0 / a[j];
+#pragma unroll
+                for (int c = 0; c < KB; ++c) s_row[c] = a[c];
+                const int q = who[j];
+                who[bpos] = q;
+                who[j] = tid;
+                s_q = q;
+                s_pi = bpos;
+                ipiv[k0 + j] = k0 + bpos;
+            }
+            __syncthreads();
+            if (tid == btid) {
+                mypos = j;
+                done = true;
+            } else if (tid == s_q) {
+                mypos = s_pi;
+            }
+            if (!done) {
+                const double l = a[j] * s_rinv;
+                a[j] = l;
+#pragma unroll
+                for (int c = j + 1; c < KB; ++c) a[c] = fma(-l, s_row[c], a[c]);
+            }
+        }
+    }
+    if (row) {
+#pragma unroll
+        for (int c = 0; c < KB; ++c)
+            if (c < kb) G0[(size_t)c * ld + mypos] = a[c];
+    }
+}
+
 // one thread per column outside the panel (W = N + nrhs columns): the panel's interchanges, then U12 = L11^-1 A12.
 // The kb interchanges touch at most 2 kb rows; their net effect is worked out once per CTA (which original row ends up in
 // each of them), so a column thread issues all its loads together instead of kb dependent swaps.
@@ -365,9 +459,17 @@ int32_t dense_blocked_lu_solve(diffopt_b200_ctx* ctx, const int N, const int nrh
         // the panel is factorised in shared memory when it fits; a tall panel is narrowed to 16 columns if that makes it fit
         auto fits = [&](int w) { return sizeof(double) * (size_t)(N - k0) * w + 2048 <= ctx->smem_optin; };
         if (!fits(kb) && kb > 16 && fits(16)) kb = 16;
-        const size_t pbytes = sizeof(double) * (size_t)(N - k0) * kb;
-        const int staged = fits(kb);
-        bl_panel_kernel<<<1, 1024, staged ? pbytes : 0, ctx->stream>>>(N, k0, kb, M, ipiv, info, staged);
+        const int mr = N - k0;
+        if (mr <= 512) {  // the panel lives in registers: 32 columns x 512 rows, or 16 columns x 1024 rows
+            bl_panel_reg_kernel<32><<<1, 512, 0, ctx->stream>>>(N, k0, kb, M, ipiv, info);
+        } else if (mr <= 1024) {
+            kb = std::min(16, kb);
+            bl_panel_reg_kernel<16><<<1, 1024, 0, ctx->stream>>>(N, k0, kb, M, ipiv, info);
+        } else {
+            const size_t pbytes = sizeof(double) * (size_t)mr * kb;
+            const int staged = fits(kb);
+            bl_panel_kernel<<<1, 1024, staged ? pbytes : 0, ctx->stream>>>(N, k0, kb, M, ipiv, info, staged);
+        }
         const int others = W - kb;
         if (others > 0) bl_swap_trsm_kernel<<<(others + 127) / 128, 128, 0, ctx->stream>>>(N, W, k0, kb, M, ipiv);
         const int nr = N - k0 - kb, nc = W - k0 - kb;
