@@ -343,7 +343,15 @@ constexpr int MF_TT = 256;
 constexpr int MF_RG = MF_TT / MF_TC;   // row groups
 constexpr int MF_NB = 8;
 constexpr int MF_LDT = MF_TC + 1;      // leading dimension of YW: conflict-free by row and by column
-constexpr int MF_US_CAP = 8192;        // update lists up to this many entries are staged in shared memory
+#ifndef MF_BT_MINB
+#define MF_BT_MINB 4                   // resident CTAs per SM the backward tiled kernel is compiled for (64 registers, 24 bytes of spills)
+#endif
+constexpr int MF_US_CAP = 8192;
+#ifndef MF_HINTS
+#define MF_HINTS 0                     // bit 0: evict-first loads of B, bit 1: evict-first stores of X
+#endif
+__device__ __forceinline__ double ld_b(const double* p) { return (MF_HINTS & 1) ? __ldcs(p) : __ldg(p); }
+__device__ __forceinline__ void st_x(double* p, const double v) { if (MF_HINTS & 2) __stcs(p, v); else *p = v; }        // update lists up to this many entries are staged in shared memory
 
 // one CTA per front: net effect of the front's row interchanges.  psrc[first + r] = row (0..k-1, before the interchanges)
 // that ends at position r; pdst = inverse.
@@ -402,6 +410,11 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
         for (int jj = 0; jj < MF_NB; ++jj) lreg[jj] = (i < nf && jj < nbk) ? L[i + (size_t)(jb + jj) * nf] : 0.0;
     };
     prefetch(0);   // first panel block in flight under the gathers below
+    {   // ... and the whole panel on its way into L2: the block steps below then wait for an L2 hit, not for DRAM
+        const char* pb = reinterpret_cast<const char*>(L);
+        const size_t bytes = (size_t)nf * k * sizeof(double);
+        for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)MF_TT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
+    }
     for (int r = tid; r < k; r += MF_TT) {
         const int loc = psrc[fr.first + r];
         locs[r] = loc;
@@ -423,27 +436,49 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
 #pragma unroll
         for (int u = 0; u < MF_TC / (MF_TT / 32); ++u) {
             const int cc = wid + u * (MF_TT / 32);
-            if (cc < ncol) dst[cc] = __ldcs(src + (size_t)N * cc);
+            if (cc < ncol) dst[cc] = ld_b(src + (size_t)N * cc);
         }
     }
     __syncthreads();
     // extend-add as a gather: every row of the tile is owned by one thread per column, which adds the children's
     // workspace rows that land on it in the children's list order (deterministic; no barrier per child)
+    // (four rows per pass with the first two entries of each in flight together: a row of a front with two children has
+    // at most two entries, so a pass costs one global round trip instead of four)
     if (live)
-        for (int pos = q; pos < nf; pos += MF_RG) {
-            const int loc = pos < k ? locs[pos] : pos;
-            const int e0 = up[loc], e1 = up[loc + 1];
-            double acc = pos < k ? YW[pos * MF_LDT + c] : 0.0;
-            int e = e0;
-            for (; e + 8 <= e1; e += 8) {   // eight loads in flight, added in list order
-                double v[8];
+        for (int pos0 = q; pos0 < nf; pos0 += 4 * MF_RG) {
+            int e0[4], e1[4];
+            double v0[4], v1[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = W[(size_t)ulist[e + u] * nrhs + col];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) acc += v[u];
+            for (int u = 0; u < 4; ++u) {
+                const int pos = pos0 + u * MF_RG;
+                const int loc = pos < nf ? (pos < k ? locs[pos] : pos) : 0;
+                e0[u] = pos < nf ? up[loc] : 0;
+                e1[u] = pos < nf ? up[loc + 1] : 0;
             }
-            for (; e < e1; ++e) acc += W[(size_t)ulist[e] * nrhs + col];
-            YW[pos * MF_LDT + c] = acc;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v0[u] = e0[u] < e1[u] ? W[(size_t)ulist[e0[u]] * nrhs + col] : 0.0;
+                v1[u] = e0[u] + 1 < e1[u] ? W[(size_t)ulist[e0[u] + 1] * nrhs + col] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pos = pos0 + u * MF_RG;
+                if (pos >= nf) break;
+                double acc = pos < k ? YW[pos * MF_LDT + c] : 0.0;
+                acc += v0[u];
+                acc += v1[u];
+                int e = e0[u] + 2;
+                const int ee = e1[u];
+                for (; e + 8 <= ee; e += 8) {   // eight loads in flight, added in list order
+                    double v[8];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) v[w] = W[(size_t)ulist[e + w] * nrhs + col];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) acc += v[w];
+                }
+                for (; e < ee; ++e) acc += W[(size_t)ulist[e] * nrhs + col];
+                YW[pos * MF_LDT + c] = acc;
+            }
         }
     // blocked forward substitution with the unit-lower L11 and the boundary update w -= L21 y in one sweep over the rows
     for (int jb = 0; jb < k; jb += MF_NB) {
@@ -498,7 +533,7 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
     }
 }
 
-__global__ void __launch_bounds__(MF_TT) mf_backward_tiled_kernel(const int* list, const MfFront* fronts, const int* strct, const int* perm,
+__global__ void __launch_bounds__(MF_TT, MF_BT_MINB) mf_backward_tiled_kernel(const int* list, const MfFront* fronts, const int* strct, const int* perm,
                                                                   const double* Lp, const double* Up, double* Y, double* X,
                                                                   const long long N, const int nrhs) {
     extern __shared__ __align__(16) double mf_smem[];
@@ -652,7 +687,7 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
         const size_t row = lane < k ? (size_t)rows[lane] : 0;
 #pragma unroll 8
         for (int c = wid; c < ncol; c += MF_LEAF_TC / 32)
-            if (lane < k) Ts[c * LDT + lane] = __ldcs(B + row + (size_t)N * (c0 + c));
+            if (lane < k) Ts[c * LDT + lane] = ld_b(B + row + (size_t)N * (c0 + c));
     }
     __syncthreads();
     double y[MF_KMAX];
@@ -712,10 +747,12 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int*
     const int tid = threadIdx.x, col = blockIdx.y * MF_LEAF_TC + tid;
     double* U11s = mf_smem;                      // row i at U11s[i * KMAX ..], strictly upper part, zero elsewhere
     double* U12s = U11s + MF_KMAX * MF_LLD;      // boundary column t at U12s[t * KMAX ..] (entries i < k)
+#pragma unroll
     for (int i = tid; i < MF_KMAX * MF_KMAX; i += MF_LEAF_TC) {   // global reads run down the columns (coalesced)
         const int c = i / MF_KMAX, r = i % MF_KMAX;
         U11s[r * MF_LLD + c] = (r < k && c < k && c > r) ? Lp[fr.lp + r + (size_t)c * nf] : 0.0;
     }
+#pragma unroll 4
     for (int i = tid; i < s * MF_KMAX; i += MF_LEAF_TC) {
         const int t = i / MF_KMAX, r = i % MF_KMAX;
         U12s[i] = r < k ? Up[fr.up + r + (size_t)t * k] : 0.0;
@@ -732,10 +769,15 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int*
     const double* yi = Y + (size_t)fr.first * nrhs + col;
 #pragma unroll
     for (int r = 0; r < MF_KMAX; ++r) y[r] = r < k ? yi[(size_t)r * nrhs] : 0.0;
-    for (int t0 = 0; t0 < s; t0 += 4) {  // y -= U12 x2, four boundary solutions in flight
+    double xn[4];   // boundary solutions of the next group of four, loaded under the updates of the current one
+#pragma unroll
+    for (int u4 = 0; u4 < 4; ++u4) xn[u4] = u4 < s ? Y[(size_t)sps[u4] * nrhs + col] : 0.0;
+    for (int t0 = 0; t0 < s; t0 += 4) {  // y -= U12 x2
         double x2[4];
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) x2[u4] = t0 + u4 < s ? Y[(size_t)sps[t0 + u4] * nrhs + col] : 0.0;
+        for (int u4 = 0; u4 < 4; ++u4) x2[u4] = xn[u4];
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) xn[u4] = t0 + 4 + u4 < s ? Y[(size_t)sps[t0 + 4 + u4] * nrhs + col] : 0.0;
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
             if (t0 + u4 >= s) break;
@@ -779,7 +821,7 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_backward_leaf_kernel(const int*
         const size_t row = lane < k ? (size_t)rows[lane] : 0;
 #pragma unroll 8
         for (int c = wid; c < ncol; c += MF_LEAF_TC / 32)
-            if (lane < k) __stcs(X + row + (size_t)N * (c0 + c), Ts[c * LDT + lane]);
+            if (lane < k) st_x(X + row + (size_t)N * (c0 + c), Ts[c * LDT + lane]);
     }
 }
 
@@ -1172,6 +1214,13 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
                 }
             }
             L.count = (int)(j - i);
+            // within a size class the fronts run in the order of their rows in the caller's numbering: neighbouring fronts
+            // share the sectors at the ends of their row runs (gathers of b, scatters of x), which then meet in L2
+            if (!big && !getenv("DIFFOPT_B200_MF_NO_LOCALITY_SORT"))
+                std::sort(H.lists.begin() + L.offset, H.lists.begin() + L.offset + L.count, [&](int32_t a, int32_t b) {
+                    const int32_t ra = H.perm[(size_t)H.fronts[(size_t)a].first], rb = H.perm[(size_t)H.fronts[(size_t)b].first];
+                    return ra != rb ? ra < rb : a < b;
+                });
             H.launches.push_back(L);
             i = j;
         }
@@ -1485,6 +1534,25 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
             return -3;
         }
         M.analysis_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (getenv("DIFFOPT_B200_MF_DEBUG")) {   // how scattered are the rows of a front in the caller's numbering?
+            long long rows = 0, sectors = 0, lines = 0, leaves = 0, srows = 0, lists = 0;
+            for (const MfFront& f : M.H.fronts) {
+                int32_t last = -1, lastl = -1;
+                for (int r = 0; r < f.k; ++r) {   // rows of a front are sorted
+                    const int32_t v = M.H.perm[(size_t)f.first + r];
+                    sectors += (v >> 2) != last;
+                    lines += (v >> 4) != lastl;
+                    last = v >> 2;
+                    lastl = v >> 4;
+                }
+                rows += f.k;
+                leaves += f.leaf != 0;
+                srows += f.s;
+                lists += f.un;
+            }
+            fprintf(stderr, "sparse_setup: %zu fronts (%lld leaves), %lld pivot rows in %lld 32-byte sectors / %lld 128-byte lines, %lld boundary rows, %lld update-list entries\n",
+                    M.H.fronts.size(), leaves, rows, sectors, lines, srows, lists);
+        }
         std::vector<int32_t> failed;
         rc = mf_numeric(ctx, M, nnz, failed);
         if (rc != -5) break;
