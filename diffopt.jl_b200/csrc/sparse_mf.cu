@@ -350,6 +350,10 @@ constexpr int MF_US_CAP = 8192;
 #ifndef MF_HINTS
 #define MF_HINTS 0                     // bit 0: evict-first loads of B, bit 1: evict-first stores of X
 #endif
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {   // one double, global -> shared, no register staging
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ double ld_b(const double* p) { return (MF_HINTS & 1) ? __ldcs(p) : __ldg(p); }
 __device__ __forceinline__ void st_x(double* p, const double v) { if (MF_HINTS & 2) __stcs(p, v); else *p = v; }        // update lists up to this many entries are staged in shared memory
 
@@ -430,15 +434,16 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
     const int* const ulist = fr.un <= MF_US_CAP ? us : usrc + uptr[fr.u0];
     __syncthreads();
     // own rows from the caller's column-major block (lanes: consecutive positions of one column), boundary rows zero
-    for (int r = lane; r < k; r += 32) {   // eight columns in flight per lane
+    for (int r = lane; r < k; r += 32) {   // asynchronous copies: every entry of the tile in flight at once
         const double* src = B + (size_t)rows[r] + (size_t)N * c0;
         double* dst = YW + r * MF_LDT;
 #pragma unroll
         for (int u = 0; u < MF_TC / (MF_TT / 32); ++u) {
             const int cc = wid + u * (MF_TT / 32);
-            if (cc < ncol) dst[cc] = ld_b(src + (size_t)N * cc);
+            if (cc < ncol) cp_async8(dst + cc, src + (size_t)N * cc);
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     // extend-add as a gather: every row of the tile is owned by one thread per column, which adds the children's
     // workspace rows that land on it in the children's list order (deterministic; no barrier per child)
@@ -514,7 +519,23 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
             for (int ii = 0; ii < MF_NB; ++ii)
                 if (ii < nbk) yo[(size_t)ii * nrhs] = yb[ii];
         }
-        for (int i = jb + nbk + q; i < nf; i += MF_RG) {
+        int i = jb + nbk + q;
+        for (; i + MF_RG < nf; i += 2 * MF_RG) {   // two rows at a time: their dependent chains interleave
+            const double2* la = reinterpret_cast<const double2*>(Lb + (size_t)(i - jb) * MF_NB);
+            const double2* lb = reinterpret_cast<const double2*>(Lb + (size_t)(i + MF_RG - jb) * MF_NB);
+            double a0 = YW[i * MF_LDT + c], a1 = 0.0, b0 = YW[(i + MF_RG) * MF_LDT + c], b1 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < MF_NB; jj += 2) {
+                const double2 l = la[jj >> 1], m = lb[jj >> 1];
+                a0 = fma(-l.x, yb[jj], a0);
+                b0 = fma(-m.x, yb[jj], b0);
+                a1 = fma(-l.y, yb[jj + 1], a1);
+                b1 = fma(-m.y, yb[jj + 1], b1);
+            }
+            YW[i * MF_LDT + c] = a0 + a1;
+            YW[(i + MF_RG) * MF_LDT + c] = b0 + b1;
+        }
+        if (i < nf) {
             const double2* l2 = reinterpret_cast<const double2*>(Lb + (size_t)(i - jb) * MF_NB);
             double acc = YW[i * MF_LDT + c], acc2 = 0.0;
 #pragma unroll
@@ -550,11 +571,11 @@ __global__ void __launch_bounds__(MF_TT, MF_BT_MINB) mf_backward_tiled_kernel(co
     const double* L = Lp + fr.lp;
     const double* U12 = Up + fr.up;
     const int* sp = strct + fr.soff;
+    // the whole tile in flight at once (asynchronous copies: no register staging); the first panel block rides along
     if (live) {
+        for (int r = q; r < k; r += MF_RG) cp_async8(&YW[r * MF_LDT + c], &Y[(size_t)(fr.first + r) * nrhs + col]);
 #pragma unroll 4
-        for (int r = q; r < k; r += MF_RG) YW[r * MF_LDT + c] = Y[(size_t)(fr.first + r) * nrhs + col];
-#pragma unroll 4
-        for (int t = q; t < s; t += MF_RG) YW[(k + t) * MF_LDT + c] = Y[(size_t)sp[t] * nrhs + col];
+        for (int t = q; t < s; t += MF_RG) cp_async8(&YW[(k + t) * MF_LDT + c], &Y[(size_t)sp[t] * nrhs + col]);
     }
     // column blocks of [U11 U12] from the right: boundary blocks (plain updates), then the blocks of U11 (solve + update)
     const int nbb = (s + MF_NB - 1) / MF_NB, npb = (k + MF_NB - 1) / MF_NB;
@@ -576,6 +597,7 @@ __global__ void __launch_bounds__(MF_TT, MF_BT_MINB) mf_backward_tiled_kernel(co
     int pend_jb = -1;
     const int nblocks = nbb + npb;
     prefetch(0);
+    cp_async_wait_all();
     for (int b = 0; b < nblocks; ++b) {
         const int jb = block_col0(b);
         const bool pivot_block = jb < k;
@@ -617,7 +639,23 @@ __global__ void __launch_bounds__(MF_TT, MF_BT_MINB) mf_backward_tiled_kernel(co
             pend_jb = jb;
             top = jb;
         }
-        for (int i = q; i < top; i += MF_RG) {
+        int i = q;
+        for (; i + MF_RG < top; i += 2 * MF_RG) {   // two rows at a time: their dependent chains interleave
+            const double2* ua = reinterpret_cast<const double2*>(Ub + (size_t)i * MF_NB);
+            const double2* ub = reinterpret_cast<const double2*>(Ub + (size_t)(i + MF_RG) * MF_NB);
+            double a0 = YW[i * MF_LDT + c], a1 = 0.0, b0 = YW[(i + MF_RG) * MF_LDT + c], b1 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < MF_NB; jj += 2) {
+                const double2 u = ua[jj >> 1], v = ub[jj >> 1];
+                a0 = fma(-u.x, xb[jj], a0);
+                b0 = fma(-v.x, xb[jj], b0);
+                a1 = fma(-u.y, xb[jj + 1], a1);
+                b1 = fma(-v.y, xb[jj + 1], b1);
+            }
+            YW[i * MF_LDT + c] = a0 + a1;
+            YW[(i + MF_RG) * MF_LDT + c] = b0 + b1;
+        }
+        if (i < top) {
             const double2* u2 = reinterpret_cast<const double2*>(Ub + (size_t)i * MF_NB);
             double acc = YW[i * MF_LDT + c], acc2 = 0.0;
 #pragma unroll
