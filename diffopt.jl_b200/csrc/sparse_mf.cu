@@ -519,23 +519,7 @@ __global__ void __launch_bounds__(MF_TT) mf_forward_tiled_kernel(const int* list
             for (int ii = 0; ii < MF_NB; ++ii)
                 if (ii < nbk) yo[(size_t)ii * nrhs] = yb[ii];
         }
-        int i = jb + nbk + q;
-        for (; i + MF_RG < nf; i += 2 * MF_RG) {   // two rows at a time: their dependent chains interleave
-            const double2* la = reinterpret_cast<const double2*>(Lb + (size_t)(i - jb) * MF_NB);
-            const double2* lb = reinterpret_cast<const double2*>(Lb + (size_t)(i + MF_RG - jb) * MF_NB);
-            double a0 = YW[i * MF_LDT + c], a1 = 0.0, b0 = YW[(i + MF_RG) * MF_LDT + c], b1 = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < MF_NB; jj += 2) {
-                const double2 l = la[jj >> 1], m = lb[jj >> 1];
-                a0 = fma(-l.x, yb[jj], a0);
-                b0 = fma(-m.x, yb[jj], b0);
-                a1 = fma(-l.y, yb[jj + 1], a1);
-                b1 = fma(-m.y, yb[jj + 1], b1);
-            }
-            YW[i * MF_LDT + c] = a0 + a1;
-            YW[(i + MF_RG) * MF_LDT + c] = b0 + b1;
-        }
-        if (i < nf) {
+        for (int i = jb + nbk + q; i < nf; i += MF_RG) {
             const double2* l2 = reinterpret_cast<const double2*>(Lb + (size_t)(i - jb) * MF_NB);
             double acc = YW[i * MF_LDT + c], acc2 = 0.0;
 #pragma unroll
@@ -639,23 +623,7 @@ __global__ void __launch_bounds__(MF_TT, MF_BT_MINB) mf_backward_tiled_kernel(co
             pend_jb = jb;
             top = jb;
         }
-        int i = q;
-        for (; i + MF_RG < top; i += 2 * MF_RG) {   // two rows at a time: their dependent chains interleave
-            const double2* ua = reinterpret_cast<const double2*>(Ub + (size_t)i * MF_NB);
-            const double2* ub = reinterpret_cast<const double2*>(Ub + (size_t)(i + MF_RG) * MF_NB);
-            double a0 = YW[i * MF_LDT + c], a1 = 0.0, b0 = YW[(i + MF_RG) * MF_LDT + c], b1 = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < MF_NB; jj += 2) {
-                const double2 u = ua[jj >> 1], v = ub[jj >> 1];
-                a0 = fma(-u.x, xb[jj], a0);
-                b0 = fma(-v.x, xb[jj], b0);
-                a1 = fma(-u.y, xb[jj + 1], a1);
-                b1 = fma(-v.y, xb[jj + 1], b1);
-            }
-            YW[i * MF_LDT + c] = a0 + a1;
-            YW[(i + MF_RG) * MF_LDT + c] = b0 + b1;
-        }
-        if (i < top) {
+        for (int i = q; i < top; i += MF_RG) {
             const double2* u2 = reinterpret_cast<const double2*>(Ub + (size_t)i * MF_NB);
             double acc = YW[i * MF_LDT + c], acc2 = 0.0;
 #pragma unroll
