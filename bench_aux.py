@@ -254,6 +254,8 @@ def main():
         print(json.dumps(config3(ctx, cpu=False)), flush=True)
     if "3p" in todo:
         print(json.dumps(config3(ctx, portfolio=True)), flush=True)
+    if "3pnocpu" in todo:
+        print(json.dumps(config3(ctx, portfolio=True, cpu=False)), flush=True)
     if "4" in todo:
         run_conic(ctx, "4: conic n=5000 m=7500 (zeros 500 + nonneg 4000 + 300 x SOC(10)), reverse, matrix-free M",
                   bench_data.conic_config4(), iters=2000, cpu_iters=300)

@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(MF_TC) mf_backward_kernel(const int* list, con
     const int k = fr.k, s = fr.s, nf = k + s;
     const int c0 = blockIdx.y * MF_TC, tid = threadIdx.x, col = c0 + tid;
     const int ncol = min(MF_TC, nrhs - c0);
+    if (k == 0) return;                                       // assembly node: nothing to solve
     const int ldy = (k | 1), ldw = (s | 1);
     double* U11s = mf_smem;                                   // k x k (upper part of the L panel), ld k
     double* U12s = BIG ? nullptr : U11s + (size_t)k * k;      // k x s
@@ -346,7 +347,7 @@ constexpr int MF_LDT = MF_TC + 1;      // leading dimension of YW: conflict-free
 #ifndef MF_BT_MINB
 #define MF_BT_MINB 4                   // resident CTAs per SM the backward tiled kernel is compiled for (64 registers, 24 bytes of spills)
 #endif
-constexpr int MF_US_CAP = 8192;
+constexpr int MF_US_CAP = 8192;        // update lists up to this many entries are staged in shared memory
 #ifndef MF_HINTS
 #define MF_HINTS 0                     // bit 0: evict-first loads of B, bit 1: evict-first stores of X
 #endif
@@ -355,7 +356,7 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ double ld_b(const double* p) { return (MF_HINTS & 1) ? __ldcs(p) : __ldg(p); }
-__device__ __forceinline__ void st_x(double* p, const double v) { if (MF_HINTS & 2) __stcs(p, v); else *p = v; }        // update lists up to this many entries are staged in shared memory
+__device__ __forceinline__ void st_x(double* p, const double v) { if (MF_HINTS & 2) __stcs(p, v); else *p = v; }
 
 // one CTA per front: net effect of the front's row interchanges.  psrc[first + r] = row (0..k-1, before the interchanges)
 // that ends at position r; pdst = inverse.
@@ -549,6 +550,7 @@ __global__ void __launch_bounds__(MF_TT, MF_BT_MINB) mf_backward_tiled_kernel(co
     const int c0 = blockIdx.y * MF_TC, col = c0 + c;
     const int ncol = min(MF_TC, nrhs - c0);
     const bool live = col < nrhs;
+    if (k == 0) return;                                    // assembly node: nothing to solve
     double* YW = mf_smem;                                  // rows 0..k-1: y -> x; rows k..nf-1: boundary solutions
     double* Ub = YW + (size_t)nf * MF_LDT;                 // [k][MF_NB]: rows of the current column block of [U11 U12]
     Ub += ((size_t)nf * MF_LDT) & 1;
@@ -1011,6 +1013,7 @@ struct MfHost {
     double flops = 0.0;
     long long nnz_lu = 0;
     int max_front = 0;
+    int nreal = 0;                   // fronts [0, nreal) eliminate supernodes; the others are assembly nodes (k = 0)
 };
 
 // symbolic factorisation on a given supernode partition (snodes in elimination order)
@@ -1081,9 +1084,72 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
             return false;
         }
     }
+    // Assembly nodes.  A front with very many children (the top front of an arrowhead: thousands of leaves under the
+    // dense rows) would add their contribution blocks / boundary updates one after the other on ONE CTA.  Its children
+    // are regrouped under intermediate fronts without pivots (k = 0, boundary = all rows of the parent, identity
+    // relative indices): they only sum their group, in parallel with each other, and hand ONE block each to the parent
+    // (repeated while a front keeps more than MF_MANY children: a tree reduction in a fixed order -- deterministic).
+    H.nreal = S;
+    {
+        constexpr size_t MF_MANY = 32;
+        constexpr long long NODE_BUDGET = (long long)1 << 27;   // doubles of extra contribution-block storage (1 GiB)
+        for (int s = 0; s < H.nreal; ++s) {
+            while (children[(size_t)s].size() > MF_MANY && !getenv("DIFFOPT_B200_MF_NO_ASSEMBLY_NODES")) {
+                const std::vector<int32_t> ch = children[(size_t)s];
+                const MfFront p = H.fronts[(size_t)s];
+                const long long nfp = p.k + p.s;
+                size_t fan = 24;
+                while ((long long)((ch.size() + fan - 1) / fan) * nfp * nfp > NODE_BUDGET) fan *= 2;
+                if (fan >= ch.size()) break;
+                std::vector<int32_t> groups;
+                for (size_t i0 = 0; i0 < ch.size(); i0 += fan) {
+                    MfFront a{};
+                    a.k = 0;
+                    a.s = (int)nfp;
+                    a.first = p.first;
+                    a.soff = (int)H.strct.size();
+                    a.leaf = 0;
+                    a.parent = s;
+                    for (int r = 0; r < p.k; ++r) H.strct.push_back(p.first + r);
+                    for (int t = 0; t < p.s; ++t) H.strct.push_back(H.strct[(size_t)p.soff + t]);
+                    const int32_t id = (int32_t)H.fronts.size();
+                    std::vector<int32_t> grp(ch.begin() + (long)i0, ch.begin() + (long)std::min(ch.size(), i0 + fan));
+                    for (int32_t c : grp) H.fronts[(size_t)c].parent = id;
+                    H.fronts.push_back(a);
+                    children.push_back(std::move(grp));
+                    groups.push_back(id);
+                }
+                children[(size_t)s] = groups;
+            }
+        }
+    }
+    const int S_all = (int)H.fronts.size();
+    if (S_all != S) {   // tree levels again (the nodes sit between their group and the parent)
+        lvl.assign((size_t)S_all, -1);
+        std::vector<int32_t> stack;
+        for (int r = 0; r < S_all; ++r) {
+            if (lvl[(size_t)r] >= 0) continue;
+            stack.push_back(r);
+            while (!stack.empty()) {
+                const int32_t f = stack.back();
+                int l = 0;
+                bool ready = true;
+                for (int32_t c : children[(size_t)f]) {
+                    if (lvl[(size_t)c] < 0) {
+                        stack.push_back(c);
+                        ready = false;
+                    } else l = std::max(l, lvl[(size_t)c] + 1);
+                }
+                if (ready) {
+                    lvl[(size_t)f] = l;
+                    stack.pop_back();
+                }
+            }
+        }
+    }
     // relative indices into the parent, children lists, storage offsets
     H.rel.assign(H.strct.size(), 0);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < S_all; ++s) {
         MfFront& f = H.fronts[(size_t)s];
         f.c0 = (int)H.child_idx.size();
         for (int32_t c : children[(size_t)s]) H.child_idx.push_back(c);
@@ -1121,7 +1187,7 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
     }
     // matrix entries -> (front, local offset).  Entry (i, j) lives in the front that eliminates min(pos i, pos j).
     {
-        std::vector<int32_t> cnt((size_t)S + 1, 0);
+        std::vector<int32_t> cnt((size_t)S_all + 1, 0);
         const int64_t nnz = colptr[N] - 1;
         std::vector<int32_t> ef((size_t)nnz), el((size_t)nnz);
         for (int64_t c = 0; c < N; ++c)
@@ -1142,7 +1208,7 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
                 el[(size_t)e] = loc(pr) + loc(pc) * nf;
                 ++cnt[(size_t)s + 1];
             }
-        for (int s = 0; s < S; ++s) cnt[(size_t)s + 1] += cnt[(size_t)s];
+        for (int s = 0; s < S_all; ++s) cnt[(size_t)s + 1] += cnt[(size_t)s];
         H.aloc.resize((size_t)nnz);
         H.asrc.resize((size_t)nnz);
         std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
@@ -1151,7 +1217,7 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
             H.aloc[(size_t)d] = el[(size_t)e];
             H.asrc[(size_t)d] = (int32_t)e;
         }
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < S_all; ++s) {
             H.fronts[(size_t)s].a0 = cnt[(size_t)s];
             H.fronts[(size_t)s].a1 = cnt[(size_t)s + 1];
         }
@@ -1165,7 +1231,7 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
     }
     {
         std::vector<int32_t> cnt;
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < S_all; ++s) {
             MfFront& f = H.fronts[(size_t)s];
             const int nf = f.k + f.s;
             f.u0 = (int)H.uptr.size();
@@ -1187,9 +1253,9 @@ bool mf_symbolic(const Graph& g, const std::vector<std::vector<int32_t>>& snodes
     }
     // launch groups: per tree level, fronts that fit shared memory (sorted by size) and the others
     H.nlevels = 0;
-    for (int s = 0; s < S; ++s) H.nlevels = std::max(H.nlevels, lvl[(size_t)s] + 1);
+    for (int s = 0; s < S_all; ++s) H.nlevels = std::max(H.nlevels, lvl[(size_t)s] + 1);
     std::vector<std::vector<int32_t>> bylevel((size_t)H.nlevels);
-    for (int s = 0; s < S; ++s) bylevel[(size_t)lvl[(size_t)s]].push_back(s);
+    for (int s = 0; s < S_all; ++s) bylevel[(size_t)lvl[(size_t)s]].push_back(s);
     for (int l = 0; l < H.nlevels; ++l) {
         auto& v = bylevel[(size_t)l];
         std::stable_sort(v.begin(), v.end(), [&](int32_t a, int32_t b) {
@@ -1572,7 +1638,8 @@ extern "C" int32_t diffopt_b200_sparse_setup(diffopt_b200_ctx* ctx, int64_t N, c
         std::vector<char> drop(M.snodes.size(), 0);
         bool progress = false;
         for (int32_t f : failed) {
-            const int p = M.H.fronts[(size_t)f].parent;
+            int p = M.H.fronts[(size_t)f].parent;
+            while (p >= M.H.nreal) p = M.H.fronts[(size_t)p].parent;   // (assembly nodes stand in for their parent)
             if (p < 0) continue;  // a root cannot delay: the pivot is simply unacceptable
             auto& dst = M.snodes[(size_t)p];
             dst.insert(dst.begin(), M.snodes[(size_t)f].begin(), M.snodes[(size_t)f].end());
