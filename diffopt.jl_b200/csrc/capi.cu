@@ -19,7 +19,6 @@ int32_t diffopt_b200_create(int32_t device, diffopt_b200_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -2;
     if (prop.major != 10) return -4;  // this library only carries sm_100a code
-    if (const char* fg = getenv("DIFFOPT_B200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
     diffopt_b200_ctx* ctx = new diffopt_b200_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;

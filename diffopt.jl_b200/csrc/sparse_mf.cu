@@ -72,9 +72,10 @@ __device__ void mf_factor_front(const MfFront fr, double* F, const int ld, doubl
         const int sc = ch.s;
         const int* r = rel + ch.soff;
         const double* cb = CB + ch.cb;
-        for (int idx = tid; idx < sc * sc; idx += THREADS) {
-            const int a = idx % sc, b = idx / sc;
-            F[r[a] + r[b] * ld] += cb[idx];
+        for (int b = warp; b < sc; b += THREADS / 32) {   // lanes run down a column of the child's block (coalesced, no div/mod)
+            const int rb = r[b] * ld;
+            const double* cbb = cb + (size_t)b * sc;
+            for (int a = lane; a < sc; a += 32) F[r[a] + rb] += cbb[a];
         }
         __syncthreads();
     }
@@ -128,20 +129,25 @@ __device__ void mf_factor_front(const MfFront fr, double* F, const int ld, doubl
             rinv[j] = ri;
             piv[fr.first + j] = p;
         }
-        const int rem = nf - j - 1;
-        for (int idx = tid; idx < rem * rem; idx += THREADS) {
-            const int i = j + 1 + idx % rem, c = j + 1 + idx / rem;
-            F[i + c * ld] = fma(-(F[i + j * ld] * ri), F[j + c * ld], F[i + c * ld]);
+        // rank-1 update: lanes <-> rows (their multiplier in a register), warps <-> columns (the pivot-row entry is a broadcast)
+        for (int i = j + 1 + lane; i < nf; i += 32) {
+            const double l = -(F[i + j * ld] * ri);
+            double* Fi = F + i;
+            const double* Fj = F + j;
+#pragma unroll 4
+            for (int c = j + 1 + warp; c < nf; c += THREADS / 32) Fi[c * ld] = fma(l, Fj[c * ld], Fi[c * ld]);
         }
         __syncthreads();
     }
     // write-back: L panel (unit-lower L11 scaled, U11 on and above the diagonal, L21), U12, contribution block
-    for (int idx = tid; idx < nf * k; idx += THREADS) {
-        const int r = idx % nf, c = idx / nf;
-        Lp[fr.lp + idx] = r > c ? F[r + c * ld] * rinv[c] : F[r + c * ld];
+    for (int c = warp; c < k; c += THREADS / 32) {
+        const double rc = rinv[c];
+        for (int r = lane; r < nf; r += 32) Lp[fr.lp + r + (size_t)c * nf] = r > c ? F[r + c * ld] * rc : F[r + c * ld];
     }
-    for (int idx = tid; idx < k * s; idx += THREADS) Up[fr.up + idx] = F[(idx % k) + (k + idx / k) * ld];
-    for (int idx = tid; idx < s * s; idx += THREADS) CB[fr.cb + idx] = F[(k + idx % s) + (k + idx / s) * ld];
+    for (int t = warp; t < s; t += THREADS / 32) {
+        for (int r = lane; r < k; r += 32) Up[fr.up + r + (size_t)t * k] = F[r + (k + t) * ld];
+        for (int r = lane; r < s; r += 32) CB[fr.cb + r + (size_t)t * s] = F[(k + r) + (k + t) * ld];
+    }
     if (tid == 0) status[fid] = sh_flag;
     __syncthreads();
 }

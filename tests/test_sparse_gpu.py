@@ -65,6 +65,21 @@ def test_portfolio_kkt_arrowhead(ctx):
         _check(ctx, d["K"], 12, trans, seed=3)
 
 
+def test_assembly_nodes_regroup_many_children(ctx, monkeypatch):
+    """A top front with a thousand children (16 000 assets under 21 dense rows): the children are regrouped under
+    assembly nodes (fronts without pivots) in two levels; same solution as with the plain one-level tree, and as SuperLU."""
+    d = bench_data.portfolio_config3(n=16000, nfac=20, density=0.2)
+    lsq = diffopt_b200.submodule("lsqr")
+    R = np.random.default_rng(5).standard_normal((d["K"].shape[0], 70))
+    F = _check(ctx, d["K"], 70, True, seed=5)
+    X = F.solve(R)
+    monkeypatch.setenv("DIFFOPT_B200_MF_NO_ASSEMBLY_NODES", "1")
+    F0 = lsq.SparseFactorization(ctx, d["K"], trans=True)
+    X0 = F0.solve(R)
+    assert F.stats["levels"] == F0.stats["levels"] + 2 and F.stats["fronts"] > F0.stats["fronts"], (F.stats, F0.stats)
+    assert (np.linalg.norm(X - X0, axis=0) / np.linalg.norm(X0, axis=0)).max() <= 1e-10
+
+
 def test_grid_pattern_with_large_fronts(ctx):
     """2-D grid (five-point) pattern, 70 x 70: the top separators exceed what the shared-memory kernels hold, so the
     in-place global-memory path for large fronts runs too."""
