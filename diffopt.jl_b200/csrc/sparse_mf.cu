@@ -152,15 +152,18 @@ __device__ void mf_factor_front(const MfFront fr, double* F, const int ld, doubl
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(MF_FACT_THREADS) mf_factor_kernel(const int* list, const MfFront* fronts, const int* child_idx, const int* rel,
-                                                                    const int* aloc, const int* asrc, const double* vals, double* Lp,
-                                                                    double* Up, double* CB, int* piv, int* status) {
+// THREADS follows the front size: a launch group whose fronts leave room for one or two CTAs per SM runs them with 1024 / 512
+// threads, so that the SM still has warps to overlap the dependent steps of the elimination.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) mf_factor_kernel(const int* list, const MfFront* fronts, const int* child_idx, const int* rel,
+                                                            const int* aloc, const int* asrc, const double* vals, double* Lp,
+                                                            double* Up, double* CB, int* piv, int* status) {
     extern __shared__ __align__(16) double mf_smem[];
     const int fid = list[blockIdx.x];
     const MfFront fr = fronts[fid];
     const int nf = fr.k + fr.s, ld = nf | 1;
-    mf_factor_front<MF_FACT_THREADS>(fr, mf_smem, ld, mf_smem + (size_t)nf * ld, fronts, child_idx, rel, aloc, asrc, vals, Lp, Up, CB,
-                                     piv, status, fid);
+    mf_factor_front<THREADS>(fr, mf_smem, ld, mf_smem + (size_t)nf * ld, fronts, child_idx, rel, aloc, asrc, vals, Lp, Up, CB, piv, status,
+                             fid);
 }
 
 // fronts beyond shared memory: the same elimination in a global scratch area (scratch[b]: nf * ld + k doubles)
@@ -1526,11 +1529,20 @@ int32_t mf_numeric(diffopt_b200_ctx* ctx, SparseMfImpl& M, int64_t nnz, std::vec
         if (L.count == 0) continue;
         if (!L.big) {
             const size_t smem = ((size_t)L.max_nf * (L.max_nf | 1) + (size_t)L.max_k) * sizeof(double);
-            DO_CUDA(ctx, cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-            mf_factor_kernel<<<(unsigned)L.count, MF_FACT_THREADS, smem, ctx->stream>>>(
-                M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.child_idx.as<int>(), M.rel.as<int>(), M.aloc.as<int>(),
-                M.asrc.as<int>(), M.vals.as<double>(), M.Lp.as<double>(), M.Up.as<double>(), M.CB.as<double>(), M.piv.as<int>(),
-                M.status.as<int>());
+            auto launch = [&](auto kernel, const int threads) -> cudaError_t {
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+                if (e != cudaSuccess) return e;
+                kernel<<<(unsigned)L.count, threads, smem, ctx->stream>>>(
+                    M.lists.as<int>() + L.offset, M.fronts.as<MfFront>(), M.child_idx.as<int>(), M.rel.as<int>(), M.aloc.as<int>(),
+                    M.asrc.as<int>(), M.vals.as<double>(), M.Lp.as<double>(), M.Up.as<double>(), M.CB.as<double>(), M.piv.as<int>(),
+                    M.status.as<int>());
+                return cudaSuccess;
+            };
+            const char* ft = getenv("DIFFOPT_B200_MF_FACT_THREADS");
+            const int want = ft ? atoi(ft) : (smem > 100 * 1024 ? 1024 : smem > 50 * 1024 ? 512 : MF_FACT_THREADS);
+            if (want >= 1024) DO_CUDA(ctx, launch(mf_factor_kernel<1024>, 1024));
+            else if (want >= 512) DO_CUDA(ctx, launch(mf_factor_kernel<512>, 512));
+            else DO_CUDA(ctx, launch(mf_factor_kernel<MF_FACT_THREADS>, MF_FACT_THREADS));
         } else {
             mf_factor_big_kernel<<<(unsigned)L.count, MF_BIG_THREADS, 0, ctx->stream>>>(
                 M.lists.as<int>() + L.offset, M.big_off.as<long long>() + big_seen, M.big_scratch.as<double>(), M.fronts.as<MfFront>(),
