@@ -351,7 +351,10 @@ __global__ void __launch_bounds__(MF_TC) mf_backward_kernel(const int* list, con
 // Row interchanges enter as the NET permutation of the front (psrc / pdst, mf_netperm_kernel).
 constexpr int MF_TT = 256;
 constexpr int MF_RG = MF_TT / MF_TC;   // row groups
-constexpr int MF_NB = 8;
+#ifndef MF_NB_W
+#define MF_NB_W 8                      // columns per block step of the tiled sweeps (16 measured slower: registers)
+#endif
+constexpr int MF_NB = MF_NB_W;
 constexpr int MF_LDT = MF_TC + 1;      // leading dimension of YW: conflict-free by row and by column
 #ifndef MF_BT_MINB
 #define MF_BT_MINB 4                   // resident CTAs per SM the backward tiled kernel is compiled for (64 registers, 24 bytes of spills)
