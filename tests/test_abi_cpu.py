@@ -105,3 +105,23 @@ def test_coo_batch_packing_matches_the_references_triplets():
     ptr, I, J, V = qp.coo_batch(m0, 5, shared=True)
     assert ptr.tolist() == [0, 2]
     assert qp.coo_batch(None, 3) is None
+
+
+def test_sparse_analysis_assembly_nodes_and_row_ordered_lists(monkeypatch):
+    """Host-only analysis of the multifrontal path (`diffopt_b200_sparse_analyze`, no GPU): a top front with a thousand
+    children gets two levels of assembly nodes (fronts without pivots: same factors, more fronts, two more launches);
+    a chain-structured KKT pattern (config 3 at reduced horizon) is left alone."""
+    import bench_data
+    lsq = diffopt_b200.submodule("lsqr")
+    K = bench_data.portfolio_config3(n=16000, nfac=20, density=0.2)["K"]
+    with_nodes = lsq.sparse_analyze(K, trans=True)
+    monkeypatch.setenv("DIFFOPT_B200_MF_NO_ASSEMBLY_NODES", "1")
+    plain = lsq.sparse_analyze(K, trans=True)
+    assert plain["levels"] == 2 and with_nodes["levels"] == 4
+    assert with_nodes["fronts"] == plain["fronts"] + 42 + 2          # 1000 leaves / 24 -> 42 nodes / 24 -> 2 nodes
+    assert with_nodes["nnz_lu"] == plain["nnz_lu"] and with_nodes["factor_flops"] == plain["factor_flops"]
+    Km = bench_data.mpc_config3(T=300)["K"]
+    a = lsq.sparse_analyze(Km, trans=True)
+    monkeypatch.delenv("DIFFOPT_B200_MF_NO_ASSEMBLY_NODES")
+    b = lsq.sparse_analyze(Km, trans=True)
+    assert {k: v for k, v in a.items() if k != "analysis_ms"} == {k: v for k, v in b.items() if k != "analysis_ms"}
