@@ -75,7 +75,20 @@ __device__ void mf_factor_front(const MfFront fr, double* F, const int ld, doubl
         for (int b = warp; b < sc; b += THREADS / 32) {   // lanes run down a column of the child's block (coalesced, no div/mod)
             const int rb = r[b] * ld;
             const double* cbb = cb + (size_t)b * sc;
-            for (int a = lane; a < sc; a += 32) F[r[a] + rb] += cbb[a];
+            int a = lane;
+            for (; a + 96 < sc; a += 128) {   // four entries in flight (distinct targets: the relative indices are injective)
+                double* t0 = F + r[a] + rb;
+                double* t1 = F + r[a + 32] + rb;
+                double* t2 = F + r[a + 64] + rb;
+                double* t3 = F + r[a + 96] + rb;
+                const double v0 = cbb[a], v1 = cbb[a + 32], v2 = cbb[a + 64], v3 = cbb[a + 96];
+                const double f0 = *t0, f1 = *t1, f2 = *t2, f3 = *t3;
+                *t0 = f0 + v0;
+                *t1 = f1 + v1;
+                *t2 = f2 + v2;
+                *t3 = f3 + v3;
+            }
+            for (; a < sc; a += 32) F[r[a] + rb] += cbb[a];
         }
         __syncthreads();
     }
@@ -134,8 +147,17 @@ __device__ void mf_factor_front(const MfFront fr, double* F, const int ld, doubl
             const double l = -(F[i + j * ld] * ri);
             double* Fi = F + i;
             const double* Fj = F + j;
-#pragma unroll 4
-            for (int c = j + 1 + warp; c < nf; c += THREADS / 32) Fi[c * ld] = fma(l, Fj[c * ld], Fi[c * ld]);
+            constexpr int NW = THREADS / 32;
+            int c = j + 1 + warp;
+            for (; c + 3 * NW < nf; c += 4 * NW) {   // four columns in flight (row j and row i never alias: i > j)
+                const double u0 = Fj[c * ld], u1 = Fj[(c + NW) * ld], u2 = Fj[(c + 2 * NW) * ld], u3 = Fj[(c + 3 * NW) * ld];
+                const double f0 = Fi[c * ld], f1 = Fi[(c + NW) * ld], f2 = Fi[(c + 2 * NW) * ld], f3 = Fi[(c + 3 * NW) * ld];
+                Fi[c * ld] = fma(l, u0, f0);
+                Fi[(c + NW) * ld] = fma(l, u1, f1);
+                Fi[(c + 2 * NW) * ld] = fma(l, u2, f2);
+                Fi[(c + 3 * NW) * ld] = fma(l, u3, f3);
+            }
+            for (; c < nf; c += NW) Fi[c * ld] = fma(l, Fj[c * ld], Fi[c * ld]);
         }
         __syncthreads();
     }
