@@ -113,6 +113,23 @@ def test_delayed_pivots_are_merged_into_the_parent(ctx, diag):
         assert F.stats["method"] == "band" or F.stats["delayed_pivot_retries"] >= 1, F.stats
 
 
+def test_delayed_pivots_below_assembly_nodes(ctx):
+    """Arrowhead with weak diagonal entries in a few leaves (1e-5 against couplings of order 1 to the dense rows): those
+    leaves fail the threshold test and report a delayed pivot; their parent is an ASSEMBLY NODE, which stands in for the top
+    front -- the merge goes into the real parent and the repeated factorisation matches SuperLU."""
+    n, d = 3000, 12
+    rng = np.random.default_rng(8)
+    diag = rng.uniform(1, 2, n) * rng.choice([-1, 1], n)
+    weak = rng.choice(n, 6, replace=False)
+    diag[weak] = 1e-5
+    B = sp.random(n, d, density=0.3, random_state=np.random.RandomState(8), format="csc", data_rvs=lambda k: rng.uniform(0.5, 1.5, k))
+    C = sp.random(d, n, density=0.3, random_state=np.random.RandomState(9), format="csc", data_rvs=lambda k: rng.uniform(0.5, 1.5, k))
+    D = sp.csc_matrix(rng.standard_normal((d, d)) + 40.0 * np.eye(d))
+    K = sp.bmat([[sp.diags(diag), B], [C, D]], format="csc")
+    F = _check(ctx, K, 5, False, seed=8)
+    assert F.stats["delayed_pivot_retries"] >= 1 and F.stats["levels"] >= 3, F.stats
+
+
 def test_singular_matrix_is_reported(ctx):
     lsq = diffopt_b200.submodule("lsqr")
     S = sp.csc_matrix(np.array([[1.0, 2.0, 0.0], [1.0, 2.0, 0.0], [0.0, 1.0, 1.0]]))
