@@ -447,6 +447,10 @@ def run_b200(args, rank, world, local_rank):
             aux["sparse_config3"] = bench_aux.config3(ctx, cpu=not args.no_cpu)
         except Exception as e:  # the headline line must survive a failure here
             aux["sparse_config3"] = {"error": str(e)[:300]}
+        try:   # ... and its portfolio (arrowhead) variant; CPU time of this one: profiles/r02_bench_aux.jsonl (35 s of SuperLU)
+            aux["sparse_config3_portfolio"] = bench_aux.config3(ctx, portfolio=True, cpu=False)
+        except Exception as e:
+            aux["sparse_config3_portfolio"] = {"error": str(e)[:300]}
         # conic side of the path (configs 4, 5): lock-step batch of config-4 problems (the HBM-meaningful form),
         # config 4 converged on the conditioned generator, the 200 x 200 PSD cone
         for key, fn in (("conic_batch_config4", lambda: bench_aux.run_conic_batch(ctx, B=296, iters=100, emit=False)),
