@@ -20,3 +20,11 @@ python bench_aux.py --configs 5 > $O/r02_psd_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/r02_psd_launches_raw.csv python bench_aux.py --configs 5 > $O/r02_psd_ncu.log 2>&1
 python bench_aux.py --configs 1,2s,3,3p,4,4c,4x,5 > $O/r02_bench_aux.jsonl 2> $O/r02_bench_aux.err
 ls -la $O | grep r02_
+# end of round 2: sparse path after the row-ordered launch lists / asynchronous tiles / assembly nodes
+python tools/prof_driver.py sparse > $O/r02_sparse_plain.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active \
+    --clock-control none -c 400 --csv --log-file $O/r02_sparse_launches_raw.csv python tools/prof_driver.py sparse > $O/r02_sparse_ncu.log 2>&1
+python tools/sparse_launch_report.py $O/r02_sparse_launches_raw.csv > $O/r02_sparse_launches.txt
+ncu --set full --clock-control none --import-source on -k regex:"mf_(forward|backward|factor)" -s 34 -c 34 -o $O/r02_sparse_kernels -f python tools/prof_driver.py sparse > $O/r02_sparse_kernels_ncu.log 2>&1
+python bench_aux.py --configs 3pnocpu > $O/r02_sparse_portfolio_plain.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/r02_sparse_portfolio_launches_raw.csv python bench_aux.py --configs 3pnocpu > /dev/null 2>&1
