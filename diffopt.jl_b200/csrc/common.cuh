@@ -6,7 +6,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/diffopt_b200.h"
@@ -151,6 +154,35 @@ struct diffopt_b200_ctx {
     int sparse_method = 0;        // factorisation currently held: 0 none, 1 banded LU (RCM), 2 multifrontal LU
     int64_t sparse_N = 0;
 };
+
+// Launch configuration of a kernel at one dynamic shared-memory size: the attribute call is made only when the size differs
+// from the last one set for this (kernel, device), the occupancy answer is cached.  Both runtime calls cost host
+// microseconds per call, which a stream of small batches (512 instances per rank at 8 GPUs: 50 us of device time per
+// call) cannot hide.
+inline cudaError_t kernel_config(const void* kernel, int device, int threads, size_t smem, int* per_sm) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> last_smem;
+    static std::map<std::tuple<const void*, int, int, size_t>, int> occupancy;
+    std::lock_guard<std::mutex> lock(mu);
+    auto ls = last_smem.find({kernel, device});
+    if (ls == last_smem.end() || ls->second != smem) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        last_smem[{kernel, device}] = smem;
+    }
+    if (per_sm) {
+        auto key = std::make_tuple(kernel, device, threads, smem);
+        auto oc = occupancy.find(key);
+        if (oc == occupancy.end()) {
+            int n = 1;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
+            if (e != cudaSuccess) return e;
+            oc = occupancy.emplace(key, n).first;
+        }
+        *per_sm = oc->second;
+    }
+    return cudaSuccess;
+}
 
 // Entry points make the ctx's device current for their duration and restore the caller's device on exit (a host
 // process that drives several GPUs, e.g. through torch or CUDA.jl, keeps its own current device).

@@ -793,9 +793,8 @@ static int32_t lu_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap
     const size_t smem = sizeof(SmemHdr) + (size_t)nt_cap * nt_cap * 64 * sizeof(double);
     if (smem > ctx->smem_optin) return 0;  // falls back to the generic kernel
     *handled = true;
-    DO_CUDA(ctx, cudaFuncSetAttribute(qp_kkt_n144_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    DO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_kkt_n144_kernel, THREADS, smem));
+    DO_CUDA(ctx, kernel_config((const void*)qp_kkt_n144_kernel, ctx->device, THREADS, smem, &per_sm));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > a.B) grid = a.B;

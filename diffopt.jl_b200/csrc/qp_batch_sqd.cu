@@ -473,9 +473,8 @@ int32_t qp_sqd_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_cap, b
     int* fb_count = ctx->qp_fb.as<int>();
     int* fb_list = fb_count + 1;
     DO_CUDA(ctx, cudaMemsetAsync(fb_count, 0, sizeof(int), ctx->stream));
-    DO_CUDA(ctx, cudaFuncSetAttribute(qp_kkt_sqd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    DO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_kkt_sqd_kernel, THREADS, smem));
+    DO_CUDA(ctx, kernel_config((const void*)qp_kkt_sqd_kernel, ctx->device, THREADS, smem, &per_sm));
     if (per_sm < 1) per_sm = 1;
     if (const char* cap = getenv("DIFFOPT_B200_SQD_PER_SM")) per_sm = atoi(cap) < per_sm && atoi(cap) > 0 ? atoi(cap) : per_sm;
     int64_t grid = (int64_t)ctx->sm_count * per_sm;

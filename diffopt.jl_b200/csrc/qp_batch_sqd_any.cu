@@ -434,9 +434,8 @@ int32_t qp_sqd_any_launch(diffopt_b200_ctx* ctx, const QpSolveArgs& a, int nt_ca
     int* fb_count = ctx->qp_fb.as<int>();
     int* fb_list = fb_count + 1;
     DO_CUDA(ctx, cudaMemsetAsync(fb_count, 0, sizeof(int), ctx->stream));
-    DO_CUDA(ctx, cudaFuncSetAttribute(qp_kkt_sqd_any_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    DO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_kkt_sqd_any_kernel, THREADS, smem));
+    DO_CUDA(ctx, kernel_config((const void*)qp_kkt_sqd_any_kernel, ctx->device, THREADS, smem, &per_sm));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > a.B) grid = a.B;
