@@ -3,7 +3,7 @@
 set -x
 O=gpurun_out
 python bench.py --steps 2 --warmup 3 --no-cpu > $O/r02_bench_plain.json 2> $O/r02_bench_plain.err || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_bench_launches_raw.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/r02_bench_launches_raw.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $O/r02_bench_ncu.log 2>&1
 python tools/prof_driver.py qp 4096 > $O/r02_qp_plain.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:qp_kkt_sqd -s 1 -c 1 -o $O/r02_qp_sqd -f python tools/prof_driver.py qp 4096 > $O/r02_qp_ncu.log 2>&1
