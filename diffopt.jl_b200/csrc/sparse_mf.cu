@@ -707,6 +707,11 @@ __global__ void __launch_bounds__(MF_LEAF_TC) mf_forward_leaf_kernel(const int* 
     constexpr int LDT = MF_KMAX + 1;       // tile leading dimension: conflict-free both ways
     double* Ts = mf_smem;                  // [column][row] tile of b (first), then the L panel (same storage)
     double* Ls = mf_smem;                  // row r of the L panel at Ls[r * KMAX .. ], columns >= k zero
+    {   // the panel is read after the gather of b: on its way into L2 meanwhile
+        const char* pb = reinterpret_cast<const char*>(Lp + fr.lp);
+        const size_t bytes = (size_t)nf * k * sizeof(double);
+        for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)MF_LEAF_TC * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
+    }
     if (psrc) {      // net effect of the row interchanges, precomputed per front (mf_netperm_kernel)
         if (tid < k) rows[tid] = perm[fr.first + psrc[fr.first + tid]];
     } else if (tid == 0) {  // ... or worked out here: position r of P b comes from row src[r]
